@@ -1,0 +1,381 @@
+"""ctypes binding of include/fishgym.h — numpy only, no torch on the sim path.
+
+The product loads ``csrc/libfishgym_cuda.so`` and fails loudly when it is missing; there is no CPU
+fallback.  ``load_library("oracle")`` exists for tests/, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` leg of ``bench.py`` only (the oracle is the checker, never the product).
+
+Boundary defined by BASELINE.json:5 (the reference ships no interface: /root/reference/README.md:14).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+FG_ABI_VERSION = 3
+Q = 19
+
+FG_OK, FG_EINVAL, FG_ENOMEM, FG_ECUDA, FG_ESTATE, FG_ENOTSUP, FG_EPEER = 0, -1, -2, -3, -4, -5, -6
+BGK, MRT = 0, 1
+XLO, XHI, YLO, YHI, ZLO, ZHI = range(6)
+BC_PERIODIC, BC_WALL, BC_INLET, BC_OUTLET = range(4)
+FLAG_NO_OVERLAP = 1
+
+_ERR_NAMES = {FG_EINVAL: "FG_EINVAL", FG_ENOMEM: "FG_ENOMEM", FG_ECUDA: "FG_ECUDA", FG_ESTATE: "FG_ESTATE",
+              FG_ENOTSUP: "FG_ENOTSUP", FG_EPEER: "FG_EPEER"}
+
+# lattice constants, exported for tests and host-side helpers
+CX = np.array([0, 1, -1, 0, 0, 0, 0, 1, -1, 1, -1, 1, -1, 1, -1, 0, 0, 0, 0])
+CY = np.array([0, 0, 0, 1, -1, 0, 0, 1, 1, -1, -1, 0, 0, 0, 0, 1, -1, 1, -1])
+CZ = np.array([0, 0, 0, 0, 0, 1, -1, 0, 0, 0, 0, 1, 1, -1, -1, 1, 1, -1, -1])
+OPP = np.array([0, 2, 1, 4, 3, 6, 5, 10, 9, 8, 7, 14, 13, 12, 11, 18, 17, 16, 15])
+W = np.array([1 / 3] + [1 / 18] * 6 + [1 / 36] * 12)
+
+
+class FgError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"{_ERR_NAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+class FgConfig(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32),
+        ("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32),
+        ("collision", C.c_int32),
+        ("bc", C.c_int32 * 6),
+        ("n_ranks", C.c_int32), ("rank", C.c_int32),
+        ("device", C.c_int32),
+        ("max_markers", C.c_int32),
+        ("max_links", C.c_int32),
+        ("flags", C.c_int32),
+        ("reserved_i", C.c_int32 * 3),
+        ("tau", C.c_double),
+        ("mrt_rates", C.c_double * 19),
+        ("wall_u", (C.c_double * 3) * 6),
+        ("inlet_u", C.c_double * 3),
+        ("inlet_rho", C.c_double),
+        ("body_force", C.c_double * 3),
+        ("reserved_d", C.c_double * 4),
+    ]
+
+
+class FgStats(C.Structure):
+    _fields_ = [
+        ("steps", C.c_int64), ("cells", C.c_int64),
+        ("last_step_ms", C.c_double), ("last_mlups", C.c_double),
+        ("kernel_launches", C.c_int64),
+        ("n_markers", C.c_int32), ("n_links", C.c_int32),
+        ("band_cells", C.c_int32), ("parity", C.c_int32),
+    ]
+
+
+class FgFishDesc(C.Structure):
+    _fields_ = [
+        ("n_links", C.c_int32), ("markers_per_link", C.c_int32),
+        ("link_len", C.c_double * 8), ("link_rad", C.c_double * 8),
+        ("root_pos", C.c_double * 3),
+        ("heading", C.c_double), ("density_ratio", C.c_double),
+        ("joint_gain", C.c_double), ("joint_limit", C.c_double), ("joint_rate_max", C.c_double),
+        ("free_root", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class FgPeerHandle(C.Structure):
+    _fields_ = [("bytes", C.c_ubyte * 192)]
+
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_REPO = os.path.dirname(_HERE)
+LIB_PATHS = {
+    "cuda": os.path.join(_HERE, "csrc", "libfishgym_cuda.so"),
+    "oracle": os.path.join(_REPO, "oracle", "libfishgym_oracle.so"),
+}
+
+# every symbol include/fishgym.h declares: (name, restype, argtypes)
+_P = C.c_void_p
+_f32 = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+_f64 = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_i32 = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+SYMBOLS = [
+    ("fg_abi_version", C.c_int, []),
+    ("fg_backend_name", C.c_char_p, []),
+    ("fg_last_error", C.c_char_p, [_P]),
+    ("fg_config_default", C.c_int, [C.POINTER(FgConfig)]),
+    ("fg_create", C.c_int, [C.POINTER(FgConfig), C.POINTER(_P)]),
+    ("fg_destroy", C.c_int, [_P]),
+    ("fg_reset", C.c_int, [_P, C.c_uint64]),
+    ("fg_set_fields", C.c_int, [_P, _f32, _f32]),
+    ("fg_get_fields", C.c_int, [_P, _f32, _f32]),
+    ("fg_get_fields_f64", C.c_int, [_P, _f64, _f64]),
+    ("fg_set_populations", C.c_int, [_P, _f32]),
+    ("fg_get_populations", C.c_int, [_P, _f32]),
+    ("fg_set_solid", C.c_int, [_P, C.c_void_p]),
+    ("fg_set_markers", C.c_int, [_P, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("fg_set_link_origins", C.c_int, [_P, C.c_int32, C.c_void_p]),
+    ("fg_get_index_map", C.c_int, [_P, _i32, _i32]),
+    ("fg_get_marker_forces", C.c_int, [_P, _f32]),
+    ("fg_get_marker_velocities", C.c_int, [_P, _f32]),
+    ("fg_get_link_wrenches", C.c_int, [_P, _f64]),
+    ("fg_get_force_field", C.c_int, [_P, _f32]),
+    ("fg_add_fish", C.c_int, [_P, C.POINTER(FgFishDesc), C.POINTER(C.c_int32)]),
+    ("fg_set_action", C.c_int, [_P, C.c_void_p, C.c_int32]),
+    ("fg_get_obs", C.c_int, [_P, _f32, C.c_int32]),
+    ("fg_obs_size", C.c_int, [_P]),
+    ("fg_action_size", C.c_int, [_P]),
+    ("fg_get_markers", C.c_int, [_P, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
+    ("fg_step", C.c_int, [_P, C.c_int32]),
+    ("fg_sync", C.c_int, [_P]),
+    ("fg_get_stats", C.c_int, [_P, C.POINTER(FgStats)]),
+    ("fg_halo_bytes", C.c_int64, [_P]),
+    ("fg_halo_pack", C.c_int, [_P, C.c_int32, C.c_void_p]),
+    ("fg_halo_unpack", C.c_int, [_P, C.c_int32, C.c_void_p]),
+    ("fg_peer_export", C.c_int, [_P, C.POINTER(FgPeerHandle)]),
+    ("fg_peer_connect", C.c_int, [_P, C.POINTER(FgPeerHandle), C.POINTER(FgPeerHandle)]),
+]
+
+_LIBS: dict = {}
+
+
+def load_library(backend: str = "cuda") -> C.CDLL:
+    """dlopen a backend and bind every symbol of the ABI.  Raises if the library is missing:
+    the product never degrades to another backend."""
+    if backend in _LIBS:
+        return _LIBS[backend]
+    path = LIB_PATHS.get(backend, backend)
+    if not os.path.exists(path):
+        hint = ("run `python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a)" if backend == "cuda"
+                else "run `make -C oracle`")
+        raise FileNotFoundError(f"fishgym backend '{backend}' not built: {path} is missing; {hint}")
+    lib = C.CDLL(path, mode=C.RTLD_LOCAL)
+    for name, restype, argtypes in SYMBOLS:
+        fn = getattr(lib, name)   # AttributeError here means the library does not export the ABI
+        fn.restype = restype
+        fn.argtypes = argtypes
+    ver = lib.fg_abi_version()
+    if ver != FG_ABI_VERSION:
+        raise RuntimeError(f"{path}: ABI version {ver}, binding expects {FG_ABI_VERSION}")
+    _LIBS[backend] = lib
+    return lib
+
+
+def default_config(**kw) -> FgConfig:
+    """FgConfig with the same defaults as fg_config_default(), overridable by keyword."""
+    cfg = FgConfig()
+    cfg.struct_size = C.sizeof(FgConfig)
+    cfg.nx = cfg.ny = cfg.nz = 32
+    cfg.collision = BGK
+    cfg.n_ranks = 1
+    cfg.tau = 0.8
+    cfg.inlet_rho = 1.0
+    for k, v in kw.items():
+        if k == "bc":
+            for i, b in enumerate(v):
+                cfg.bc[i] = int(b)
+        elif k == "wall_u":
+            for face, vec in dict(v).items():
+                for d in range(3):
+                    cfg.wall_u[face][d] = float(vec[d])
+        elif k in ("mrt_rates", "inlet_u", "body_force"):
+            arr = getattr(cfg, k)
+            for i, x in enumerate(v):
+                arr[i] = float(x)
+        else:
+            if not hasattr(cfg, k):
+                raise TypeError(f"FgConfig has no field '{k}'")
+            setattr(cfg, k, v)
+    return cfg
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Sim:
+    """Thin object wrapper over one FgSim handle (reset/step plumbing for the env and the tests)."""
+
+    def __init__(self, cfg: Optional[FgConfig] = None, backend: str = "cuda", **kw):
+        self.lib = load_library(backend)
+        self.backend = backend
+        self.cfg = cfg if cfg is not None else default_config(**kw)
+        h = C.c_void_p()
+        rc = self.lib.fg_create(C.byref(self.cfg), C.byref(h))
+        if rc != FG_OK:
+            raise FgError(rc, (self.lib.fg_last_error(None) or b"").decode())
+        self.h = h
+        self.nx, self.ny = self.cfg.nx, self.cfg.ny
+        self.nz = self.cfg.nz // self.cfg.n_ranks   # local slab height
+        self.shape = (self.nz, self.ny, self.nx)
+
+    # -- plumbing --
+    def _ck(self, rc: int):
+        if rc < 0:
+            raise FgError(rc, (self.lib.fg_last_error(self.h) or b"").decode())
+        return rc
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.fg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def backend_name(self) -> str:
+        return self.lib.fg_backend_name().decode()
+
+    # -- fluid --
+    def reset(self, seed: int = 0):
+        self._ck(self.lib.fg_reset(self.h, seed))
+
+    def set_fields(self, rho: np.ndarray, u: np.ndarray):
+        rho = np.ascontiguousarray(rho, dtype=np.float32).reshape(self.shape)
+        u = np.ascontiguousarray(u, dtype=np.float32).reshape((3,) + self.shape)
+        self._ck(self.lib.fg_set_fields(self.h, rho, u))
+
+    def get_fields(self, f64: bool = False):
+        dt = np.float64 if f64 else np.float32
+        rho = np.empty(self.shape, dtype=dt)
+        u = np.empty((3,) + self.shape, dtype=dt)
+        fn = self.lib.fg_get_fields_f64 if f64 else self.lib.fg_get_fields
+        self._ck(fn(self.h, rho, u))
+        return rho, u
+
+    def set_populations(self, f: np.ndarray):
+        f = np.ascontiguousarray(f, dtype=np.float32).reshape((Q,) + self.shape)
+        self._ck(self.lib.fg_set_populations(self.h, f))
+
+    def get_populations(self) -> np.ndarray:
+        f = np.empty((Q,) + self.shape, dtype=np.float32)
+        self._ck(self.lib.fg_get_populations(self.h, f))
+        return f
+
+    def set_solid(self, solid_global: Optional[np.ndarray]):
+        if solid_global is None:
+            self._ck(self.lib.fg_set_solid(self.h, None))
+            return
+        s = np.ascontiguousarray(solid_global, dtype=np.uint8).reshape((self.cfg.nz, self.ny, self.nx))
+        self._ck(self.lib.fg_set_solid(self.h, _ptr(s)))
+
+    # -- immersed boundary --
+    def set_markers(self, X, U, dV, link_id=None):
+        X = np.ascontiguousarray(X, dtype=np.float32).reshape(-1, 3)
+        n = X.shape[0]
+        U = np.ascontiguousarray(U, dtype=np.float32).reshape(n, 3)
+        dV = np.ascontiguousarray(np.broadcast_to(np.asarray(dV, dtype=np.float32), (n,)))
+        link = None if link_id is None else np.ascontiguousarray(link_id, dtype=np.int32).reshape(n)
+        self._ck(self.lib.fg_set_markers(self.h, n, _ptr(X), _ptr(U), _ptr(dV), _ptr(link)))
+        self._n_markers = n
+
+    def set_link_origins(self, origins):
+        o = np.ascontiguousarray(origins, dtype=np.float64).reshape(-1, 3)
+        self._ck(self.lib.fg_set_link_origins(self.h, o.shape[0], _ptr(o)))
+
+    def stats(self) -> FgStats:
+        st = FgStats()
+        self._ck(self.lib.fg_get_stats(self.h, C.byref(st)))
+        return st
+
+    def get_index_map(self):
+        n = self.stats().n_markers
+        base = np.empty((n, 3), dtype=np.int32)
+        owner = np.empty((n,), dtype=np.int32)
+        self._ck(self.lib.fg_get_index_map(self.h, base, owner))
+        return base, owner
+
+    def get_marker_forces(self) -> np.ndarray:
+        F = np.empty((self.stats().n_markers, 3), dtype=np.float32)
+        self._ck(self.lib.fg_get_marker_forces(self.h, F))
+        return F
+
+    def get_marker_velocities(self) -> np.ndarray:
+        U = np.empty((self.stats().n_markers, 3), dtype=np.float32)
+        self._ck(self.lib.fg_get_marker_velocities(self.h, U))
+        return U
+
+    def get_link_wrenches(self) -> np.ndarray:
+        w = np.zeros((max(self.stats().n_links, 1), 6), dtype=np.float64)
+        self._ck(self.lib.fg_get_link_wrenches(self.h, w))
+        return w[: self.stats().n_links]
+
+    def get_force_field(self) -> np.ndarray:
+        F = np.empty((3,) + self.shape, dtype=np.float32)
+        self._ck(self.lib.fg_get_force_field(self.h, F))
+        return F
+
+    # -- bodies --
+    def add_fish(self, desc: FgFishDesc) -> int:
+        fid = C.c_int32(-1)
+        self._ck(self.lib.fg_add_fish(self.h, C.byref(desc), C.byref(fid)))
+        return fid.value
+
+    def action_size(self) -> int:
+        return self._ck(self.lib.fg_action_size(self.h))
+
+    def obs_size(self) -> int:
+        return self._ck(self.lib.fg_obs_size(self.h))
+
+    def set_action(self, a):
+        a = np.ascontiguousarray(a, dtype=np.float32).reshape(-1)
+        self._ck(self.lib.fg_set_action(self.h, _ptr(a), a.shape[0]))
+
+    def get_obs(self) -> np.ndarray:
+        o = np.empty((self.obs_size(),), dtype=np.float32)
+        self._ck(self.lib.fg_get_obs(self.h, o, o.shape[0]))
+        return o
+
+    def get_markers(self):
+        n = self._ck(self.lib.fg_get_markers(self.h, None, None, None, 0))
+        X = np.empty((n, 3), dtype=np.float32)
+        U = np.empty((n, 3), dtype=np.float32)
+        link = np.empty((n,), dtype=np.int32)
+        self._ck(self.lib.fg_get_markers(self.h, _ptr(X), _ptr(U), _ptr(link), n))
+        return X, U, link
+
+    # -- stepping --
+    def step(self, n_substeps: int = 1):
+        self._ck(self.lib.fg_step(self.h, n_substeps))
+
+    def sync(self):
+        self._ck(self.lib.fg_sync(self.h))
+
+    # -- halos --
+    def halo_bytes(self) -> int:
+        return int(self._ck(self.lib.fg_halo_bytes(self.h)))
+
+    def halo_pack(self, face: int) -> np.ndarray:
+        buf = np.empty((self.halo_bytes(),), dtype=np.uint8)
+        self._ck(self.lib.fg_halo_pack(self.h, face, _ptr(buf)))
+        return buf
+
+    def halo_unpack(self, face: int, buf: np.ndarray):
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        if buf.nbytes != self.halo_bytes():
+            raise ValueError("halo message has the wrong size")
+        self._ck(self.lib.fg_halo_unpack(self.h, face, _ptr(buf)))
+
+    def peer_export(self) -> bytes:
+        h = FgPeerHandle()
+        self._ck(self.lib.fg_peer_export(self.h, C.byref(h)))
+        return bytes(h.bytes)
+
+    def peer_connect(self, zlo: Optional[bytes], zhi: Optional[bytes]):
+        def mk(b):
+            if b is None:
+                return None
+            h = FgPeerHandle()
+            C.memmove(h.bytes, b, 192)
+            return C.byref(h)
+        self._ck(self.lib.fg_peer_connect(self.h, mk(zlo), mk(zhi)))

@@ -1,0 +1,173 @@
+/* fishgym.h — the C ABI of the coupled fluid step (drop-in boundary).
+ *
+ * Reference interface replaced: none exists.  /root/reference/README.md:2-3 names the path
+ * ("physical articulated underwater agent interaction with fluid", "coupled interation between
+ * agents and fluid") and README.md:14 only promises "control through Python interface"; the
+ * shape of this boundary is the one BASELINE.json:5 (`north_star`) prescribes: a Gym-style Python
+ * env over a thin C ABI into a CUDA library, no PyTorch on the sim path.
+ *
+ * Two shared libraries export exactly these symbols:
+ *   gym-fish_b200/csrc/libfishgym_cuda.so   the product: CUDA sm_100a, fp32 populations
+ *   oracle/libfishgym_oracle.so             the checker: OpenMP C++, fp64 (tests/bench baseline only)
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every function returns FG_OK (0) or a negative FG_E* code;
+ *     fg_last_error() gives the message; no exception or abort crosses the boundary.
+ *   - the library owns everything behind the opaque FgSim*; the caller owns every buffer it passes
+ *     and the library never keeps a caller pointer past the call.
+ *   - host arrays are C-contiguous: scalars [nz][ny][nx] (x fastest, z slowest = swim axis),
+ *     vectors [3][nz][ny][nx], populations [19][nz][ny][nx].  With z-slab decomposition
+ *     (n_ranks > 1) nz in array shapes is the LOCAL slab height nz/n_ranks.
+ *   - lattice: D3Q19 in d'Humieres ordering; lattice units dx = dt = 1.
+ *   - one FgSim is single-caller; distinct handles are independent.
+ */
+#ifndef FISHGYM_H
+#define FISHGYM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FG_ABI_VERSION 3
+#define FG_Q 19
+
+/* error codes */
+#define FG_OK        0
+#define FG_EINVAL   -1   /* bad argument / config */
+#define FG_ENOMEM   -2   /* host or device allocation failed */
+#define FG_ECUDA    -3   /* CUDA runtime error (message has the cudaError string) */
+#define FG_ESTATE   -4   /* call not valid in the current state */
+#define FG_ENOTSUP  -5   /* feature not supported by this backend */
+#define FG_EPEER    -6   /* peer (multi-GPU) setup or exchange failed */
+
+/* collision models */
+#define FG_BGK 0
+#define FG_MRT 1
+
+/* face ids and boundary conditions (inlet/outlet on z faces only: z is the swim/flow axis) */
+#define FG_XLO 0
+#define FG_XHI 1
+#define FG_YLO 2
+#define FG_YHI 3
+#define FG_ZLO 4
+#define FG_ZHI 5
+#define FG_BC_PERIODIC 0
+#define FG_BC_WALL     1   /* half-way bounce-back, optional tangential wall velocity */
+#define FG_BC_INLET    2   /* equilibrium at (inlet_rho, inlet_u) pulled from outside the face */
+#define FG_BC_OUTLET   3   /* zero-gradient: pull source clamped to the last plane */
+
+/* FgConfig.flags */
+#define FG_FLAG_NO_OVERLAP 1   /* multi-GPU: halo after the full-slab kernel (overlap off) */
+
+typedef struct FgConfig {
+    int32_t struct_size;      /* = sizeof(FgConfig); checked by fg_create */
+    int32_t nx, ny, nz;       /* GLOBAL lattice size; nz % n_ranks == 0 */
+    int32_t collision;        /* FG_BGK | FG_MRT */
+    int32_t bc[6];            /* per face, FG_BC_* */
+    int32_t n_ranks, rank;    /* z-slab decomposition: this handle owns slab `rank` */
+    int32_t device;           /* CUDA device ordinal (ignored by the oracle) */
+    int32_t max_markers;      /* capacity for IB markers (0 = no immersed boundary) */
+    int32_t max_links;        /* capacity for rigid links markers can belong to */
+    int32_t flags;            /* FG_FLAG_* */
+    int32_t reserved_i[3];
+    double  tau;              /* relaxation time; nu = (tau - 1/2)/3 */
+    double  mrt_rates[19];    /* MRT relaxation rates per moment; all zero => SURVEY.md A3 defaults */
+    double  wall_u[6][3];     /* wall velocity per face (used where bc == WALL) */
+    double  inlet_u[3];
+    double  inlet_rho;        /* 0 => 1.0 */
+    double  body_force[3];    /* uniform Guo body force density */
+    double  reserved_d[4];
+} FgConfig;
+
+typedef struct FgStats {
+    int64_t steps;            /* fluid steps taken since create/reset */
+    int64_t cells;            /* local lattice cells (nx*ny*nz_local) */
+    double  last_step_ms;     /* device (CUDA events) or host time of the last fg_step call */
+    double  last_mlups;       /* cells * n_substeps / last_step_ms / 1e3 */
+    int64_t kernel_launches;  /* kernels of this library launched since create */
+    int32_t n_markers, n_links;
+    int32_t band_cells;       /* cells inside marker stencils in the last step */
+    int32_t parity;           /* AA-pattern parity of the next step (0 even / 1 odd); oracle: 0 */
+} FgStats;
+
+/* articulated swimmer description: a planar chain of n_links ellipsoid links, yawing joints */
+typedef struct FgFishDesc {
+    int32_t n_links;          /* >= 1; n_joints = n_links - 1 */
+    int32_t markers_per_link; /* target count; actual chosen by the surface sampler */
+    double  link_len[8];      /* full length along the body axis (lattice units) */
+    double  link_rad[8];      /* half-width (y and lateral radius) */
+    double  root_pos[3];      /* position of the head link centre, lattice coords (x,y,z) */
+    double  heading;          /* yaw of the body axis about +y, radians; 0 => nose towards -z */
+    double  density_ratio;    /* body/fluid density (mass and inertia of the ellipsoids) */
+    double  joint_gain;       /* PD stiffness: joint rate = gain*(target - angle) clipped to joint_rate_max */
+    double  joint_limit;      /* |joint angle| <= limit, radians */
+    double  joint_rate_max;   /* radians per lattice step */
+    int32_t free_root;        /* 1: root integrates hydrodynamic wrench (planar x-z + yaw); 0: pinned */
+    int32_t reserved;
+} FgFishDesc;
+
+typedef struct FgSim FgSim;
+
+/* 64-byte opaque blob a rank publishes so that z-neighbours can map its lattice (CUDA IPC) */
+typedef struct FgPeerHandle { unsigned char bytes[192]; } FgPeerHandle;
+
+int         fg_abi_version(void);
+const char *fg_backend_name(void);                 /* "cuda-sm100a" | "oracle-fp64" */
+const char *fg_last_error(const FgSim *sim);       /* sim may be NULL: last create error */
+
+/* ---- lifecycle ---- */
+int fg_config_default(FgConfig *cfg);              /* fills struct_size, BGK, tau 0.8, periodic, 1 rank */
+int fg_create(const FgConfig *cfg, FgSim **out);
+int fg_destroy(FgSim *sim);
+int fg_reset(FgSim *sim, uint64_t seed);           /* f <- f_eq(1,0); bodies to initial pose; step counter 0 */
+
+/* ---- fluid state (local slab, natural layout = populations ARRIVING at the cell at time t) ---- */
+int fg_set_fields(FgSim *sim, const float *rho, const float *u);      /* f <- f_eq(rho,u) */
+int fg_get_fields(FgSim *sim, float *rho, float *u);                  /* rho = sum f, u = sum c f / rho (no force) */
+int fg_get_fields_f64(FgSim *sim, double *rho, double *u);            /* same, double out (oracle: exact) */
+int fg_set_populations(FgSim *sim, const float *f19);
+int fg_get_populations(FgSim *sim, float *f19);
+int fg_set_solid(FgSim *sim, const uint8_t *solid_global);            /* [nz_global][ny][nx], 1 = solid; NULL clears */
+
+/* ---- immersed boundary: Lagrangian markers (prescribed, or generated by fish bodies) ---- */
+int fg_set_markers(FgSim *sim, int32_t n, const float *X, const float *U,
+                   const float *dV, const int32_t *link_id);          /* X,U: [n][3]; dV,link_id: [n] */
+int fg_set_link_origins(FgSim *sim, int32_t n_links, const double *origin3); /* torque reference points */
+int fg_get_index_map(FgSim *sim, int32_t *base3, int32_t *owner);     /* base: [n][3] = floor(X)-1; owner rank: [n] */
+int fg_get_marker_forces(FgSim *sim, float *F3);                      /* force density on fluid at markers, last step */
+int fg_get_marker_velocities(FgSim *sim, float *Ustar3);              /* interpolated unforced fluid velocity, last step */
+int fg_get_link_wrenches(FgSim *sim, double *w6);                     /* [n_links][6]: hydrodynamic force, torque ON the link */
+int fg_get_force_field(FgSim *sim, float *F);                         /* [3][nz][ny][nx] Eulerian IB force of the last step */
+
+/* ---- articulated bodies, integrated on the host every substep ---- */
+int fg_add_fish(FgSim *sim, const FgFishDesc *desc, int32_t *fish_id);
+int fg_set_action(FgSim *sim, const float *a, int32_t n);             /* joint targets in [-1,1], all fish concatenated */
+int fg_get_obs(FgSim *sim, float *obs, int32_t n);                    /* per fish: pos3, heading, vel3, yaw rate, joints, joint rates */
+int fg_obs_size(FgSim *sim);
+int fg_action_size(FgSim *sim);
+int fg_get_markers(FgSim *sim, float *X, float *U, int32_t *link_id, int32_t cap); /* returns count or <0 */
+
+/* ---- stepping ---- */
+int fg_step(FgSim *sim, int32_t n_substeps);       /* synchronous for wrenches/obs; fields stay on device */
+int fg_sync(FgSim *sim);
+int fg_get_stats(FgSim *sim, FgStats *out);
+
+/* ---- z-slab halos ----
+ * host-staged form (works on both backends; used by the CPU gloo tests):
+ *   after every fg_step(sim, 1) each rank packs the 5 populations crossing each internal face,
+ *   ships them to the neighbour, and the neighbour unpacks.  Messages are opaque bytes of the
+ *   backend's own population type (fp32 on CUDA, fp64 in the oracle): fg_halo_bytes() per face.
+ * device form (CUDA backend): publish/connect CUDA-IPC handles once; fg_step then pushes halos
+ *   over NVLink with peer stores and neighbour flags, no host involvement. */
+int64_t fg_halo_bytes(FgSim *sim);                                    /* bytes per face message: 5*nx*ny*sizeof(pop) */
+int fg_halo_pack(FgSim *sim, int32_t face /*FG_ZLO|FG_ZHI*/, void *buf);
+int fg_halo_unpack(FgSim *sim, int32_t face, const void *buf);
+int fg_peer_export(FgSim *sim, FgPeerHandle *out);
+int fg_peer_connect(FgSim *sim, const FgPeerHandle *zlo_neighbour, const FgPeerHandle *zhi_neighbour);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FISHGYM_H */
