@@ -22,6 +22,7 @@ BGK, MRT = 0, 1
 XLO, XHI, YLO, YHI, ZLO, ZHI = range(6)
 BC_PERIODIC, BC_WALL, BC_INLET, BC_OUTLET = range(4)
 FLAG_NO_OVERLAP = 1
+FLAG_PROFILE = 2
 
 _ERR_NAMES = {FG_EINVAL: "FG_EINVAL", FG_ENOMEM: "FG_ENOMEM", FG_ECUDA: "FG_ECUDA", FG_ESTATE: "FG_ESTATE",
               FG_ENOTSUP: "FG_ENOTSUP", FG_EPEER: "FG_EPEER"}
@@ -69,6 +70,7 @@ class FgStats(C.Structure):
         ("kernel_launches", C.c_int64),
         ("n_markers", C.c_int32), ("n_links", C.c_int32),
         ("band_cells", C.c_int32), ("parity", C.c_int32),
+        ("collide_ms", C.c_double), ("collide_launches", C.c_int64), ("ib_ms", C.c_double),
     ]
 
 

@@ -1,0 +1,242 @@
+// dev_cuda.cuh — the product's device policy: CUDA runtime only (no torch, no NCCL on the sim path).
+// One non-blocking stream per handle, CUDA events for timing, CUDA-IPC / peer access for z-neighbours,
+// acquire/release flags in peer memory for the per-step neighbour hand-shake.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unistd.h>
+#include <utility>
+#include <vector>
+
+#include "lbm_core.cuh"
+
+namespace fg {
+
+template <class K, class P>
+__global__ void __launch_bounds__(K::kThreads, K::kMinBlocks) kern(const __grid_constant__ P p) {
+    K::run(p, int(blockIdx.x), int(blockIdx.y), int(blockIdx.z), int(threadIdx.x));
+}
+
+// neighbour hand-shake: one thread, system-scope release / acquire on a word in (peer) device memory
+__global__ void signal_kernel(int *lo, int *hi, int value) {
+    __threadfence_system();
+    if (lo) asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(lo), "r"(value) : "memory");
+    if (hi) asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(hi), "r"(value) : "memory");
+}
+__global__ void wait_kernel(int *flags, int lo, int hi, int value, unsigned long long timeout_ns) {
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    for (int s = 0; s < 2; ++s) {
+        if (!(s == 0 ? lo : hi)) continue;
+        for (;;) {
+            int v;
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flags + s) : "memory");
+            if (v >= value) break;
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+            if (t - t0 > timeout_ns) { flags[3] = 1; return; }   // sticky: the host reports FG_EPEER
+            __nanosleep(200);
+        }
+    }
+}
+
+class CudaDev {
+public:
+    std::string err;
+    long long launches = 0;
+
+    bool init(int device, std::string &e) {
+        int n = 0;
+        cudaError_t rc = cudaGetDeviceCount(&n);
+        if (rc != cudaSuccess || n == 0) {
+            e = std::string("no CUDA device: ") + cudaGetErrorString(rc) + " — this library has no CPU path";
+            return false;
+        }
+        if (device < 0 || device >= n) { e = "FgConfig.device out of range"; return false; }
+        device_ = device;
+        if (!ck(cudaSetDevice(device_), "cudaSetDevice")) { e = err; return false; }
+        cudaDeviceProp prop;
+        if (!ck(cudaGetDeviceProperties(&prop, device_), "cudaGetDeviceProperties")) { e = err; return false; }
+        if (prop.major < 10) {
+            e = std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                "; this library is built for sm_100a only";
+            return false;
+        }
+        bool ok = ck(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), "cudaStreamCreate") &&
+                  ck(cudaEventCreate(&ev0_), "cudaEventCreate") && ck(cudaEventCreate(&ev1_), "cudaEventCreate");
+        if (!ok) e = err;
+        return ok;
+    }
+    void shutdown() {
+        if (device_ < 0) return;
+        cudaSetDevice(device_);
+        if (stream_) { cudaStreamSynchronize(stream_); cudaStreamDestroy(stream_); stream_ = nullptr; }
+        if (ev0_) cudaEventDestroy(ev0_);
+        if (ev1_) cudaEventDestroy(ev1_);
+        ev0_ = ev1_ = nullptr;
+        for (auto &pool : marks_) { for (auto e : pool) cudaEventDestroy(e); pool.clear(); }
+    }
+
+    void *alloc(size_t bytes, std::string &e) {
+        cudaSetDevice(device_);
+        void *p = nullptr;
+        cudaError_t rc = cudaMalloc(&p, bytes ? bytes : 4);
+        if (rc != cudaSuccess) {
+            e = std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(rc);
+            cudaGetLastError();
+            return nullptr;
+        }
+        return p;
+    }
+    void free(void *p) {
+        if (!p) return;
+        cudaSetDevice(device_);
+        cudaFree(p);
+    }
+    bool h2d(void *d, const void *s, size_t n) {
+        cudaSetDevice(device_);
+        return ck(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, stream_), "H2D") && ck(cudaStreamSynchronize(stream_), "H2D sync");
+    }
+    bool d2h(void *d, const void *s, size_t n) {
+        cudaSetDevice(device_);
+        return ck(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, stream_), "D2H") && ck(cudaStreamSynchronize(stream_), "D2H sync");
+    }
+    bool zero(void *d, size_t n) {
+        cudaSetDevice(device_);
+        return ck(cudaMemsetAsync(d, 0, n, stream_), "memset");
+    }
+    bool sync() {
+        cudaSetDevice(device_);
+        return ck(cudaStreamSynchronize(stream_), "stream sync");
+    }
+    void tic() {
+        cudaSetDevice(device_);
+        cudaEventRecord(ev0_, stream_);
+    }
+    double toc() {
+        cudaEventRecord(ev1_, stream_);
+        if (cudaEventSynchronize(ev1_) != cudaSuccess) return 0.0;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev0_, ev1_);
+        return double(ms);
+    }
+
+    // FG_FLAG_PROFILE: event pairs around launches of one kernel class (0 = stream-collide, 1 = immersed boundary);
+    // consecutive mark(c) calls open / close an interval on the launching stream
+    void marks_reset() { nmarks_[0] = nmarks_[1] = 0; }
+    void mark(int c) {
+        cudaSetDevice(device_);
+        auto &pool = marks_[c];
+        if (nmarks_[c] >= kMaxMarks) return;   // long runs: the first kMaxMarks/2 intervals are a fair sample
+        if (int(pool.size()) <= nmarks_[c]) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) return;
+            pool.push_back(e);
+        }
+        cudaEventRecord(pool[nmarks_[c]++], stream_);
+    }
+    double marks_elapsed(int c) {
+        double tot = 0;
+        for (int i = 0; i + 1 < nmarks_[c]; i += 2) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, marks_[c][i], marks_[c][i + 1]) == cudaSuccess) tot += ms;
+        }
+        return tot;
+    }
+    int marks_intervals(int c) const { return nmarks_[c] / 2; }
+
+    template <class K, class P>
+    bool launch(Dim3 g, const P &p) {
+        cudaSetDevice(device_);
+        kern<K, P><<<dim3(g.x, g.y, g.z), K::kThreads, 0, stream_>>>(p);
+        ++launches;
+        return ck(cudaGetLastError(), "kernel launch");
+    }
+
+    // ---- z-neighbour lattices: same process => raw pointer (+ peer access); other process => CUDA IPC
+    template <class Blob>
+    bool export_peer(float *f, int *flags, Blob &b, std::string &e) {
+        cudaSetDevice(device_);
+        b.pid = int(getpid()); b.device = device_;
+        b.f_ptr = reinterpret_cast<uint64_t>(f); b.flag_ptr = reinterpret_cast<uint64_t>(flags);
+        cudaIpcMemHandle_t h1, h2;
+        static_assert(sizeof(h1) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        if (!ck(cudaIpcGetMemHandle(&h1, f), "cudaIpcGetMemHandle(lattice)") || !ck(cudaIpcGetMemHandle(&h2, flags), "cudaIpcGetMemHandle(flags)")) {
+            e = err;
+            return false;
+        }
+        std::memcpy(b.f_ipc, &h1, 64); std::memcpy(b.flag_ipc, &h2, 64);
+        return true;
+    }
+    template <class Blob>
+    bool open_peer(const Blob &b, float **f, int **flags, std::string &e) {
+        cudaSetDevice(device_);
+        if (b.pid == int(getpid())) {
+            if (b.device != device_) {
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, device_, b.device);
+                if (!can) { e = "devices " + std::to_string(device_) + " and " + std::to_string(b.device) + " have no peer access"; return false; }
+                cudaError_t rc = cudaDeviceEnablePeerAccess(b.device, 0);
+                if (rc != cudaSuccess && rc != cudaErrorPeerAccessAlreadyEnabled) { ck(rc, "cudaDeviceEnablePeerAccess"); e = err; return false; }
+                cudaGetLastError();
+            }
+            *f = reinterpret_cast<float *>(b.f_ptr); *flags = reinterpret_cast<int *>(b.flag_ptr);
+            return true;
+        }
+        void *pf = open_ipc(b.f_ipc), *pg = open_ipc(b.flag_ipc);
+        if (!pf || !pg) { e = err; return false; }
+        *f = static_cast<float *>(pf); *flags = static_cast<int *>(pg);
+        return true;
+    }
+    void close_peers() {
+        if (device_ < 0) return;
+        cudaSetDevice(device_);
+        for (auto &o : opened_) cudaIpcCloseMemHandle(o.second);
+        opened_.clear();
+    }
+    bool signal_flags(int *lo, int *hi, int value) {
+        cudaSetDevice(device_);
+        signal_kernel<<<1, 1, 0, stream_>>>(lo, hi, value);
+        ++launches;
+        return ck(cudaGetLastError(), "signal launch");
+    }
+    bool wait_flags(int *flags, bool lo, bool hi, int value) {
+        if (!lo && !hi) return true;
+        cudaSetDevice(device_);
+        wait_kernel<<<1, 1, 0, stream_>>>(flags, lo, hi, value, 20ull * 1000ull * 1000ull * 1000ull);
+        ++launches;
+        return ck(cudaGetLastError(), "wait launch");
+    }
+
+    cudaStream_t stream() const { return stream_; }
+
+private:
+    bool ck(cudaError_t rc, const char *what) {
+        if (rc == cudaSuccess) return true;
+        err = std::string(what) + ": " + cudaGetErrorString(rc);
+        return false;
+    }
+    void *open_ipc(const unsigned char *bytes) {
+        for (auto &o : opened_)
+            if (std::memcmp(o.first.data(), bytes, 64) == 0) return o.second;
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, bytes, 64);
+        void *p = nullptr;
+        if (!ck(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle")) return nullptr;
+        opened_.emplace_back(std::string(reinterpret_cast<const char *>(bytes), 64), p);
+        return p;
+    }
+
+    int device_ = -1;
+    cudaStream_t stream_ = nullptr;
+    cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+    std::vector<std::pair<std::string, void *>> opened_;
+    static constexpr int kMaxMarks = 8192;
+    std::vector<cudaEvent_t> marks_[2];
+    int nmarks_[2] = {0, 0};
+};
+
+}  // namespace fg

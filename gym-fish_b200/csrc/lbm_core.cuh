@@ -1,0 +1,541 @@
+// lbm_core.cuh — device code of the fused D3Q19 stream-collide path.
+//
+// Path and boundary: /root/reference/README.md:2-3 names the coupled agent-fluid step; there is no
+// reference source, the scheme is BASELINE.json:5 (a): single-lattice in-place streaming
+// (AA pattern), SoA fp32 populations, MRT moment transform in registers, bounce-back and Guo
+// forcing fused into the collide.
+//
+// Data layout in HBM: one array f[19][nz+2][ny][nx] of fp32 (x fastest).  Planes zz=0 and zz=nz+1
+// are ghost planes: EVERY z-face condition (periodic wrap, slab neighbour, inlet, outlet) is a
+// plane operation on 5 populations between steps (ZFaceOp below), so the main kernel never
+// wraps in z.  Populations are stored SHIFTED, h_i = f_i - w_i (SURVEY.md §7 "DDF shifting"), which
+// is what keeps fp32 within 1e-5 of the fp64 oracle.
+//
+// AA pattern.  Even step: read slot i at x, collide, write slot opp(i) at x.
+// Odd step: read f_i from slot opp(i) at x-c_i and f_opp(i) from slot i at x+c_i, collide, write
+// f*_i to slot i at x+c_i and f*_opp(i) to slot opp(i) at x-c_i.  Each thread reads and writes the
+// same 19 addresses, so the update is in place and race-free.  Half-way bounce-back redirects a
+// blocked link to the cell's own opposite slot on both the read and the write side.
+//
+// Everything here is __host__ __device__: tests/emu compiles the same functions with g++ and
+// loops over the grid on the CPU (test infrastructure only; the product library is CUDA-only).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define FG_HD __host__ __device__ __forceinline__
+#define FG_UNROLL _Pragma("unroll")
+#else
+#define FG_HD inline
+#define FG_UNROLL
+#endif
+
+namespace fg {
+
+constexpr int Q = 19;
+// SURVEY.md A1 (d'Humieres ordering)
+constexpr int CXT[Q] = {0, 1, -1, 0, 0, 0, 0, 1, -1, 1, -1, 1, -1, 1, -1, 0, 0, 0, 0};
+constexpr int CYT[Q] = {0, 0, 0, 1, -1, 0, 0, 1, 1, -1, -1, 0, 0, 0, 0, 1, -1, 1, -1};
+constexpr int CZT[Q] = {0, 0, 0, 0, 0, 1, -1, 0, 0, 0, 0, 1, 1, -1, -1, 1, 1, -1, -1};
+constexpr int OPPT[Q] = {0, 2, 1, 4, 3, 6, 5, 10, 9, 8, 7, 14, 13, 12, 11, 18, 17, 16, 15};
+constexpr float W0 = 1.0f / 3.0f, W1 = 1.0f / 18.0f, W2 = 1.0f / 36.0f;
+constexpr double WD[Q] = {1.0 / 3, 1.0 / 18, 1.0 / 18, 1.0 / 18, 1.0 / 18, 1.0 / 18, 1.0 / 18,
+                          1.0 / 36, 1.0 / 36, 1.0 / 36, 1.0 / 36, 1.0 / 36, 1.0 / 36,
+                          1.0 / 36, 1.0 / 36, 1.0 / 36, 1.0 / 36, 1.0 / 36, 1.0 / 36};
+// the five populations crossing a z face
+constexpr int ZPT[5] = {5, 11, 12, 15, 16};   // c_z = +1
+constexpr int ZMT[5] = {6, 13, 14, 17, 18};   // c_z = -1
+
+// run-time indexed copies (namespace-scope constexpr arrays are not addressable in device code)
+FG_HD int cxr(int i) { constexpr int t[Q] = {0, 1, -1, 0, 0, 0, 0, 1, -1, 1, -1, 1, -1, 1, -1, 0, 0, 0, 0}; return t[i]; }
+FG_HD int cyr(int i) { constexpr int t[Q] = {0, 0, 0, 1, -1, 0, 0, 1, 1, -1, -1, 0, 0, 0, 0, 1, -1, 1, -1}; return t[i]; }
+FG_HD int czr(int i) { constexpr int t[Q] = {0, 0, 0, 0, 0, 1, -1, 0, 0, 0, 0, 1, 1, -1, -1, 1, 1, -1, -1}; return t[i]; }
+FG_HD int oppr(int i) { constexpr int t[Q] = {0, 2, 1, 4, 3, 6, 5, 10, 9, 8, 7, 14, 13, 12, 11, 18, 17, 16, 15}; return t[i]; }
+FG_HD int zpr(int k) { constexpr int t[5] = {5, 11, 12, 15, 16}; return t[k]; }
+FG_HD int zmr(int k) { constexpr int t[5] = {6, 13, 14, 17, 18}; return t[k]; }
+
+struct Dim3 { int x = 1, y = 1, z = 1; };   // launch grid (blocks); block size is the kernel's kThreads
+
+enum : int { BC_PERIODIC = 0, BC_WALL = 1, BC_INLET = 2, BC_OUTLET = 3, BC_PEER = 4 };
+enum : int { F_XLO = 0, F_XHI = 1, F_YLO = 2, F_YHI = 3, F_ZLO = 4, F_ZHI = 5 };
+
+struct Lattice {
+    float *f;             // slot q lives at f + q*slot
+    long long slot;       // (nz+2)*ny*nx
+    int nx, ny, nz;       // local slab (interior planes zz = 1..nz)
+    int plane;            // nx*ny
+    int z0, nzg;          // first owned global plane, global height
+    int wall_x, wall_y;   // 1: both faces of the axis are walls; 0: periodic
+    int bc_zlo, bc_zhi;   // GLOBAL z-face conditions (BC_*), relevant where the slab touches them
+    const uint8_t *solid; // [(nz+2)*plane] interior obstacles (incl. ghost planes) or nullptr
+};
+
+struct Collision {
+    float omega;          // 1/tau
+    float rate[Q];        // MRT relaxation rates (conserved rows 0)
+    float g[3];           // uniform body force density
+    float wallterm[6][Q]; // 6 w_i c_i.u_wall(face): moving-wall bounce-back correction
+    float heq_in[Q];      // shifted inlet equilibrium h_eq,i(inlet_rho, inlet_u)
+};
+
+// Eulerian IB force, band-sparse: cellslot[idx] = 1 + position in the band arrays, 0 = no force
+struct ForceField {
+    const int *cellslot;   // [(nz+2)*plane] or nullptr (no immersed boundary)
+    const float *bandF;    // [3][band_cap]
+    int band_cap;
+    const uint8_t *rowflag; // [(nz+2)*ny] rows that contain band cells (lets whole rows skip the lookup)
+};
+
+struct StepParams {
+    Lattice L;
+    Collision C;
+    ForceField F;
+    int zz_begin, zz_end;  // storage planes [zz_begin, zz_end) this launch covers
+};
+
+// ---------------------------------------------------------------- collide (registers only)
+// shifted populations: rho = 1 + sum h, j = sum c h, u = (j + F/2)/rho  
+
+template <int I> struct Dir {
+    static constexpr int cx = CXT[I], cy = CYT[I], cz = CZT[I], opp = OPPT[I];
+    static constexpr float w = I == 0 ? W0 : (I < 7 ? W1 : W2);
+};
+
+template <int I>
+FG_HD void bgk_pair(float (&h)[Q], float dr, float rho, float ux, float uy, float uz, float uu15, float Fx, float Fy,
+                    float Fz, float uF3, float om, float kf) {
+    using D = Dir<I>;
+    constexpr int J = D::opp;
+    const float cu = D::cx * ux + D::cy * uy + D::cz * uz;
+    const float cF = D::cx * Fx + D::cy * Fy + D::cz * Fz;
+    const float sym = D::w * (dr + rho * (4.5f * cu * cu - uu15));
+    const float asym = D::w * rho * 3.0f * cu;
+    const float psym = D::w * (9.0f * cu * cF - uF3);
+    const float pasym = D::w * 3.0f * cF;
+    h[I] = h[I] - om * (h[I] - (sym + asym)) + kf * (psym + pasym);
+    h[J] = h[J] - om * (h[J] - (sym - asym)) + kf * (psym - pasym);
+}
+
+FG_HD void collide_bgk(float (&h)[Q], float Fx, float Fy, float Fz, const Collision &c) {
+    const float sx = h[1] + h[2], sy = h[3] + h[4], sz = h[5] + h[6];
+    const float sxy = (h[7] + h[8]) + (h[9] + h[10]), sxz = (h[11] + h[12]) + (h[13] + h[14]),
+                syz = (h[15] + h[16]) + (h[17] + h[18]);
+    const float dr = h[0] + ((sx + sy) + sz) + ((sxy + sxz) + syz);
+    const float jx = (h[1] - h[2]) + ((h[7] - h[8]) + (h[9] - h[10])) + ((h[11] - h[12]) + (h[13] - h[14]));
+    const float jy = (h[3] - h[4]) + ((h[7] + h[8]) - (h[9] + h[10])) + ((h[15] - h[16]) + (h[17] - h[18]));
+    const float jz = (h[5] - h[6]) + ((h[11] + h[12]) - (h[13] + h[14])) + ((h[15] + h[16]) - (h[17] + h[18]));
+    const float rho = 1.0f + dr, inv = 1.0f / rho;
+    const float ux = (jx + 0.5f * Fx) * inv, uy = (jy + 0.5f * Fy) * inv, uz = (jz + 0.5f * Fz) * inv;
+    const float uu15 = 1.5f * (ux * ux + uy * uy + uz * uz);
+    const float uF3 = 3.0f * (ux * Fx + uy * Fy + uz * Fz);
+    const float om = c.omega, kf = 1.0f - 0.5f * om;
+    h[0] = h[0] - om * (h[0] - W0 * (dr - rho * uu15)) - kf * W0 * uF3;
+    bgk_pair<1>(h, dr, rho, ux, uy, uz, uu15, Fx, Fy, Fz, uF3, om, kf);
+    bgk_pair<3>(h, dr, rho, ux, uy, uz, uu15, Fx, Fy, Fz, uF3, om, kf);
+    bgk_pair<5>(h, dr, rho, ux, uy, uz, uu15, Fx, Fy, Fz, uF3, om, kf);
+    bgk_pair<7>(h, dr, rho, ux, uy, uz, uu15, Fx, Fy, Fz, uF3, om, kf);
+    bgk_pair<8>(h, dr, rho, ux, uy, uz, uu15, Fx, Fy, Fz, uF3, om, kf);
+    bgk_pair<11>(h, dr, rho, ux, uy, uz, uu15, Fx, Fy, Fz, uF3, om, kf);
+    bgk_pair<12>(h, dr, rho, ux, uy, uz, uu15, Fx, Fy, Fz, uF3, om, kf);
+    bgk_pair<15>(h, dr, rho, ux, uy, uz, uu15, Fx, Fy, Fz, uF3, om, kf);
+    bgk_pair<16>(h, dr, rho, ux, uy, uz, uu15, Fx, Fy, Fz, uF3, om, kf);
+}
+
+// MRT in the d'Humieres basis, closed forms for M h, m_eq, M*source and M^-1.
+// Works on shifted moments: M w = (1,-11,3,0,...) only offsets rho, e, eps, which cancel in m - m_eq.
+FG_HD void collide_mrt(float (&h)[Q], float Fx, float Fy, float Fz, const Collision &c) {
+    const float sx = h[1] + h[2], sy = h[3] + h[4], sz = h[5] + h[6];
+    const float sxy = (h[7] + h[8]) + (h[9] + h[10]), sxz = (h[11] + h[12]) + (h[13] + h[14]),
+                syz = (h[15] + h[16]) + (h[17] + h[18]);
+    const float saxis = (sx + sy) + sz, sedge = (sxy + sxz) + syz;
+    const float ax = h[1] - h[2], ay = h[3] - h[4], az = h[5] - h[6];
+    const float exy_x = (h[7] - h[8]) + (h[9] - h[10]);    // sum c_x over xy edges
+    const float exz_x = (h[11] - h[12]) + (h[13] - h[14]); // sum c_x over xz edges
+    const float exy_y = (h[7] + h[8]) - (h[9] + h[10]);
+    const float eyz_y = (h[15] - h[16]) + (h[17] - h[18]);
+    const float exz_z = (h[11] + h[12]) - (h[13] + h[14]);
+    const float eyz_z = (h[15] + h[16]) - (h[17] + h[18]);
+    // moments of h
+    const float dr = h[0] + saxis + sedge;
+    const float m_e = -30.0f * h[0] - 11.0f * saxis + 8.0f * sedge;
+    const float m_eps = 12.0f * h[0] - 4.0f * saxis + sedge;
+    const float ex = exy_x + exz_x, ey = exy_y + eyz_y, ez = exz_z + eyz_z;
+    const float jx = ax + ex, jy = ay + ey, jz = az + ez;
+    const float qx = ex - 4.0f * ax, qy = ey - 4.0f * ay, qz = ez - 4.0f * az;
+    const float pa = 2.0f * sx - sy - sz, pe = sxy + sxz - 2.0f * syz;
+    const float m_pxx = pa + pe, m_pixx = pe - 2.0f * pa;
+    const float wa = sy - sz, we = sxy - sxz;
+    const float m_pww = wa + we, m_piww = we - 2.0f * wa;
+    const float m_pxy = (h[7] - h[8]) - (h[9] - h[10]);
+    const float m_pyz = (h[15] - h[16]) - (h[17] - h[18]);
+    const float m_pxz = (h[11] - h[12]) - (h[13] - h[14]);
+    const float m_mx = exy_x - exz_x, m_my = eyz_y - exy_y, m_mz = exz_z - eyz_z;
+    // macroscopic
+    const float rho = 1.0f + dr, inv = 1.0f / rho;
+    const float ux = (jx + 0.5f * Fx) * inv, uy = (jy + 0.5f * Fy) * inv, uz = (jz + 0.5f * Fz) * inv;
+    const float ruxx = rho * ux * ux, ruyy = rho * uy * uy, ruzz = rho * uz * uz;
+    const float ruu = ruxx + ruyy + ruzz;
+    const float uF = ux * Fx + uy * Fy + uz * Fz;
+    const float fxx = 2.0f * ux * Fx - uy * Fy - uz * Fz;   // source of 3p_xx / 2
+    const float fww = uy * Fy - uz * Fz;
+    const float *s = c.rate;
+    // d_k = [ -s_k (m_k - m_eq,k) + (1 - s_k/2) Psi_k ] / |row_k|^2
+    const float d1 = (-s[1] * (m_e - (-11.0f * dr + 19.0f * ruu)) + (1.0f - 0.5f * s[1]) * 38.0f * uF) * (1.0f / 2394.0f);
+    const float d2 = (-s[2] * (m_eps - (3.0f * dr - 5.5f * ruu)) - (1.0f - 0.5f * s[2]) * 11.0f * uF) * (1.0f / 252.0f);
+    const float d3 = Fx * 0.1f, d5 = Fy * 0.1f, d7 = Fz * 0.1f;
+    const float k23 = 2.0f / 3.0f;
+    const float d4 = (-s[4] * (qx + k23 * rho * ux) - (1.0f - 0.5f * s[4]) * k23 * Fx) * 0.025f;
+    const float d6 = (-s[6] * (qy + k23 * rho * uy) - (1.0f - 0.5f * s[6]) * k23 * Fy) * 0.025f;
+    const float d8 = (-s[8] * (qz + k23 * rho * uz) - (1.0f - 0.5f * s[8]) * k23 * Fz) * 0.025f;
+    const float pxx_eq = 2.0f * ruxx - ruyy - ruzz, pww_eq = ruyy - ruzz;
+    const float d9 = (-s[9] * (m_pxx - pxx_eq) + (1.0f - 0.5f * s[9]) * 2.0f * fxx) * (1.0f / 36.0f);
+    const float d10 = (-s[10] * (m_pixx + 0.5f * pxx_eq) - (1.0f - 0.5f * s[10]) * fxx) * (1.0f / 72.0f);
+    const float d11 = (-s[11] * (m_pww - pww_eq) + (1.0f - 0.5f * s[11]) * 2.0f * fww) * (1.0f / 12.0f);
+    const float d12 = (-s[12] * (m_piww + 0.5f * pww_eq) - (1.0f - 0.5f * s[12]) * fww) * (1.0f / 24.0f);
+    const float d13 = (-s[13] * (m_pxy - rho * ux * uy) + (1.0f - 0.5f * s[13]) * (ux * Fy + uy * Fx)) * 0.25f;
+    const float d14 = (-s[14] * (m_pyz - rho * uy * uz) + (1.0f - 0.5f * s[14]) * (uy * Fz + uz * Fy)) * 0.25f;
+    const float d15 = (-s[15] * (m_pxz - rho * ux * uz) + (1.0f - 0.5f * s[15]) * (ux * Fz + uz * Fx)) * 0.25f;
+    const float d16 = -s[16] * m_mx * 0.125f, d17 = -s[17] * m_my * 0.125f, d18 = -s[18] * m_mz * 0.125f;
+    // h* = h + M^T d
+    h[0] += -30.0f * d1 + 12.0f * d2;
+    const float ca = -11.0f * d1 - 4.0f * d2;
+    const float cax = ca + 2.0f * d9 - 4.0f * d10;
+    const float cay = ca - d9 + 2.0f * d10 + d11 - 2.0f * d12;
+    const float caz = ca - d9 + 2.0f * d10 - d11 + 2.0f * d12;
+    const float vx = d3 - 4.0f * d4, vy = d5 - 4.0f * d6, vz = d7 - 4.0f * d8;
+    h[1] += cax + vx; h[2] += cax - vx;
+    h[3] += cay + vy; h[4] += cay - vy;
+    h[5] += caz + vz; h[6] += caz - vz;
+    const float ce = 8.0f * d1 + d2;
+    const float cxy = ce + d9 + d10 + d11 + d12, cxz = ce + d9 + d10 - d11 - d12, cyz = ce - 2.0f * (d9 + d10);
+    const float tx = d3 + d4, ty = d5 + d6, tz = d7 + d8;
+    {   // xy edges 7:(+,+) 8:(-,+) 9:(+,-) 10:(-,-)
+        const float a = tx + d16, b = ty - d17;
+        h[7] += cxy + a + b + d13; h[8] += cxy - a + b - d13;
+        h[9] += cxy + a - b - d13; h[10] += cxy - a - b + d13;
+    }
+    {   // xz edges 11:(+,+) 12:(-,+) 13:(+,-) 14:(-,-)
+        const float a = tx - d16, b = tz + d18;
+        h[11] += cxz + a + b + d15; h[12] += cxz - a + b - d15;
+        h[13] += cxz + a - b - d15; h[14] += cxz - a - b + d15;
+    }
+    {   // yz edges 15:(+,+) 16:(-,+) 17:(+,-) 18:(-,-)
+        const float a = ty + d17, b = tz - d18;
+        h[15] += cyz + a + b + d14; h[16] += cyz - a + b - d14;
+        h[17] += cyz + a - b - d14; h[18] += cyz - a - b + d14;
+    }
+}
+
+// rho - 1 and momentum of shifted populations (no force)
+FG_HD void moments(const float (&h)[Q], float &dr, float &jx, float &jy, float &jz) {
+    const float sx = h[1] + h[2], sy = h[3] + h[4], sz = h[5] + h[6];
+    const float sxy = (h[7] + h[8]) + (h[9] + h[10]), sxz = (h[11] + h[12]) + (h[13] + h[14]),
+                syz = (h[15] + h[16]) + (h[17] + h[18]);
+    dr = h[0] + ((sx + sy) + sz) + ((sxy + sxz) + syz);
+    jx = (h[1] - h[2]) + ((h[7] - h[8]) + (h[9] - h[10])) + ((h[11] - h[12]) + (h[13] - h[14]));
+    jy = (h[3] - h[4]) + ((h[7] + h[8]) - (h[9] + h[10])) + ((h[15] - h[16]) + (h[17] - h[18]));
+    jz = (h[5] - h[6]) + ((h[11] + h[12]) - (h[13] + h[14])) + ((h[15] + h[16]) - (h[17] + h[18]));
+}
+
+// ---------------------------------------------------------------- neighbourhood of one cell
+struct Nbr {
+    int dxm, dxp, dym, dyp, dzm, dzp;       // index offsets to x-1, x+1, y-1, y+1, z-1, z+1 (periodic wrap in x,y)
+    bool wxm, wxp, wym, wyp, wzm, wzp;      // the link towards that side crosses a wall face
+
+    template <int CX, int CY, int CZ> FG_HD int off() const {
+        return (CX > 0 ? dxp : (CX < 0 ? dxm : 0)) + (CY > 0 ? dyp : (CY < 0 ? dym : 0)) + (CZ > 0 ? dzp : (CZ < 0 ? dzm : 0));
+    }
+    // first wall face crossed by a link in direction (CX,CY,CZ), priority x, y, z (oracle: pull()), -1 if none
+    template <int CX, int CY, int CZ> FG_HD int wall() const {
+        if (CX > 0 && wxp) return F_XHI;
+        if (CX < 0 && wxm) return F_XLO;
+        if (CY > 0 && wyp) return F_YHI;
+        if (CY < 0 && wym) return F_YLO;
+        if (CZ > 0 && wzp) return F_ZHI;
+        if (CZ < 0 && wzm) return F_ZLO;
+        return -1;
+    }
+};
+
+FG_HD Nbr make_nbr(const Lattice &L, int x, int y, int zz) {
+    Nbr n;
+    n.dxm = x == 0 ? L.nx - 1 : -1;
+    n.dxp = x == L.nx - 1 ? -(L.nx - 1) : 1;
+    n.dym = y == 0 ? (L.ny - 1) * L.nx : -L.nx;
+    n.dyp = y == L.ny - 1 ? -(L.ny - 1) * L.nx : L.nx;
+    n.dzm = -L.plane;
+    n.dzp = L.plane;
+    const int zg = L.z0 + zz - 1;
+    n.wxm = L.wall_x && x == 0;
+    n.wxp = L.wall_x && x == L.nx - 1;
+    n.wym = L.wall_y && y == 0;
+    n.wyp = L.wall_y && y == L.ny - 1;
+    n.wzm = L.bc_zlo == BC_WALL && zg == 0;
+    n.wzp = L.bc_zhi == BC_WALL && zg == L.nzg - 1;
+    return n;
+}
+
+// ---------------------------------------------------------------- AA-pattern loads / stores
+// Load the populations ARRIVING at the cell (f_i(x,t)) for the given storage parity.
+template <int I, bool CHECK>
+FG_HD void odd_load_pair(float (&h)[Q], const Lattice &L, const Collision &C, const Nbr &nb, long long idx) {
+    using D = Dir<I>;
+    constexpr int J = D::opp;
+    const float *fI = L.f + I * L.slot, *fJ = L.f + J * L.slot;
+    const int om = nb.off<-D::cx, -D::cy, -D::cz>();   // towards x - c_I
+    const int op = nb.off<D::cx, D::cy, D::cz>();      // towards x + c_I
+    if (CHECK) {
+        const int wm = nb.wall<-D::cx, -D::cy, -D::cz>();
+        const int wp = nb.wall<D::cx, D::cy, D::cz>();
+        const bool bm = wm >= 0 || (L.solid && L.solid[idx + om]);
+        const bool bp = wp >= 0 || (L.solid && L.solid[idx + op]);
+        h[I] = bm ? fI[idx] + (wm >= 0 ? C.wallterm[wm][I] : 0.0f) : fJ[idx + om];
+        h[J] = bp ? fJ[idx] + (wp >= 0 ? C.wallterm[wp][J] : 0.0f) : fI[idx + op];
+    } else {
+        h[I] = fJ[idx + om];
+        h[J] = fI[idx + op];
+    }
+}
+
+template <int I, bool CHECK>
+FG_HD void odd_store_pair(const float (&h)[Q], const Lattice &L, const Collision &C, const Nbr &nb, long long idx) {
+    using D = Dir<I>;
+    constexpr int J = D::opp;
+    float *fI = L.f + I * L.slot, *fJ = L.f + J * L.slot;
+    const int om = nb.off<-D::cx, -D::cy, -D::cz>();
+    const int op = nb.off<D::cx, D::cy, D::cz>();
+    if (CHECK) {
+        const int wm = nb.wall<-D::cx, -D::cy, -D::cz>();
+        const int wp = nb.wall<D::cx, D::cy, D::cz>();
+        const bool bm = wm >= 0 || (L.solid && L.solid[idx + om]);
+        const bool bp = wp >= 0 || (L.solid && L.solid[idx + op]);
+        if (bp) fJ[idx] = h[I] + (wp >= 0 ? C.wallterm[wp][J] : 0.0f); else fI[idx + op] = h[I];
+        if (bm) fI[idx] = h[J] + (wm >= 0 ? C.wallterm[wm][I] : 0.0f); else fJ[idx + om] = h[J];
+    } else {
+        fI[idx + op] = h[I];
+        fJ[idx + om] = h[J];
+    }
+}
+
+#define FG_FOR_PAIRS(X) X(1) X(3) X(5) X(7) X(8) X(11) X(12) X(15) X(16)
+
+template <int PARITY, bool CHECK>
+FG_HD void load_arriving(float (&h)[Q], const Lattice &L, const Collision &C, const Nbr &nb, long long idx) {
+    if (PARITY == 0) {
+        FG_UNROLL
+        for (int i = 0; i < Q; ++i) h[i] = L.f[i * L.slot + idx];
+    } else {
+        h[0] = L.f[idx];
+#define FG_X(I) odd_load_pair<I, CHECK>(h, L, C, nb, idx);
+        FG_FOR_PAIRS(FG_X)
+#undef FG_X
+    }
+}
+
+template <int PARITY, bool CHECK>
+FG_HD void store_departing(const float (&h)[Q], const Lattice &L, const Collision &C, const Nbr &nb, long long idx) {
+    if (PARITY == 0) {
+        L.f[idx] = h[0];
+#define FG_X(I) L.f[Dir<I>::opp * L.slot + idx] = h[I]; L.f[I * L.slot + idx] = h[Dir<I>::opp];
+        FG_FOR_PAIRS(FG_X)
+#undef FG_X
+    } else {
+        L.f[idx] = h[0];
+#define FG_X(I) odd_store_pair<I, CHECK>(h, L, C, nb, idx);
+        FG_FOR_PAIRS(FG_X)
+#undef FG_X
+    }
+}
+
+FG_HD bool row_needs_checks(const Lattice &L, int y, int zz) {
+    const int zg = L.z0 + zz - 1;
+    return L.solid != nullptr || L.wall_x || (L.wall_y && (y == 0 || y == L.ny - 1)) ||
+           (L.bc_zlo == BC_WALL && zg == 0) || (L.bc_zhi == BC_WALL && zg == L.nzg - 1);
+}
+
+// ---------------------------------------------------------------- kernel bodies
+// grid: (ceil(nx/threads), ny, planes); one thread per cell, x fastest => coalesced 128 B per warp per slot
+template <int PARITY, bool MRT>
+struct StreamCollide {
+    static constexpr int kThreads = 128;
+    static constexpr int kMinBlocks = 4;
+    template <bool CHECK>
+    FG_HD static void cell(const StepParams &p, int x, int y, int zz) {
+        const Lattice &L = p.L;
+        const long long idx = ((long long)zz * L.ny + y) * L.nx + x;
+        if (CHECK && L.solid && L.solid[idx]) return;
+        const Nbr nb = make_nbr(L, x, y, zz);
+        float h[Q];
+        load_arriving<PARITY, CHECK>(h, L, p.C, nb, idx);
+        float Fx = p.C.g[0], Fy = p.C.g[1], Fz = p.C.g[2];
+        if (p.F.cellslot && p.F.rowflag[zz * L.ny + y]) {
+            const int s = p.F.cellslot[idx];
+            if (s > 0) {
+                Fx += p.F.bandF[s - 1];
+                Fy += p.F.bandF[p.F.band_cap + s - 1];
+                Fz += p.F.bandF[2 * p.F.band_cap + s - 1];
+            }
+        }
+        if (MRT) collide_mrt(h, Fx, Fy, Fz, p.C); else collide_bgk(h, Fx, Fy, Fz, p.C);
+        store_departing<PARITY, CHECK>(h, L, p.C, nb, idx);
+    }
+    FG_HD static void run(const StepParams &p, int bx, int by, int bz, int tx) {
+        const int x = bx * kThreads + tx, y = by, zz = p.zz_begin + bz;
+        if (x >= p.L.nx) return;
+        if (PARITY == 1 && row_needs_checks(p.L, y, zz)) cell<true>(p, x, y, zz);
+        else if (PARITY == 0 && p.L.solid) cell<true>(p, x, y, zz);
+        else cell<false>(p, x, y, zz);
+    }
+};
+
+// f <- shifted equilibrium of (rho, u) given per cell, or of a constant state: natural layout, all planes
+struct InitParams {
+    Lattice L;
+    const float *rho, *u;   // device [nz][ny][nx], [3][nz][ny][nx] (local, no ghosts) or nullptr => (1, 0)
+};
+FG_HD void shifted_equilibrium(float dr, float ux, float uy, float uz, float (&h)[Q]) {
+    const float rho = 1.0f + dr, uu15 = 1.5f * (ux * ux + uy * uy + uz * uz);
+    FG_UNROLL
+    for (int i = 0; i < Q; ++i) {
+        const float cu = cxr(i) * ux + cyr(i) * uy + czr(i) * uz;
+        const float w = i == 0 ? W0 : (i < 7 ? W1 : W2);
+        h[i] = w * (dr + rho * (3.0f * cu + 4.5f * cu * cu - uu15));
+    }
+}
+struct InitEquilibrium {
+    static constexpr int kThreads = 128;
+    static constexpr int kMinBlocks = 4;
+    FG_HD static void run(const InitParams &p, int bx, int by, int bz, int tx) {
+        const Lattice &L = p.L;
+        const int x = bx * kThreads + tx, y = by, zz = bz;   // all nz+2 planes
+        if (x >= L.nx) return;
+        const long long idx = ((long long)zz * L.ny + y) * L.nx + x;
+        float dr = 0.f, ux = 0.f, uy = 0.f, uz = 0.f;
+        if (p.rho && zz >= 1 && zz <= L.nz) {
+            const long long l = ((long long)(zz - 1) * L.ny + y) * L.nx + x, n = (long long)L.nz * L.plane;
+            dr = p.rho[l] - 1.0f; ux = p.u[l]; uy = p.u[n + l]; uz = p.u[2 * n + l];
+        }
+        float h[Q];
+        shifted_equilibrium(dr, ux, uy, uz, h);
+        FG_UNROLL
+        for (int i = 0; i < Q; ++i) L.f[i * L.slot + idx] = h[i];
+    }
+};
+
+// arriving populations / moments for read-out (parity aware): out19 natural layout [19][nz][ny][nx] (shifted),
+// or mom [4][nz][ny][nx] = (rho-1, u)
+struct GatherParams {
+    Lattice L;
+    Collision C;
+    float *out19;
+    float *mom;
+};
+template <int PARITY>
+struct GatherArriving {
+    static constexpr int kThreads = 128;
+    static constexpr int kMinBlocks = 4;
+    FG_HD static void run(const GatherParams &p, int bx, int by, int bz, int tx) {
+        const Lattice &L = p.L;
+        const int x = bx * kThreads + tx, y = by, zz = bz + 1;
+        if (x >= L.nx) return;
+        const long long idx = ((long long)zz * L.ny + y) * L.nx + x;
+        const long long l = ((long long)(zz - 1) * L.ny + y) * L.nx + x, n = (long long)L.nz * L.plane;
+        const Nbr nb = make_nbr(L, x, y, zz);
+        float h[Q];
+        if (L.solid && L.solid[idx]) {
+            FG_UNROLL
+            for (int i = 0; i < Q; ++i) h[i] = L.f[i * L.slot + idx];   // solid cells keep whatever they hold
+        } else {
+            load_arriving<PARITY, true>(h, L, p.C, nb, idx);
+        }
+        if (p.out19) {
+            FG_UNROLL
+            for (int i = 0; i < Q; ++i) p.out19[i * n + l] = h[i];
+        }
+        if (p.mom) {
+            float dr, jx, jy, jz;
+            moments(h, dr, jx, jy, jz);
+            const float inv = 1.0f / (1.0f + dr);
+            p.mom[l] = dr; p.mom[n + l] = jx * inv; p.mom[2 * n + l] = jy * inv; p.mom[3 * n + l] = jz * inv;
+        }
+    }
+};
+
+// ---------------------------------------------------------------- z-face plane operations (a10)
+// After every step the 5 populations crossing each z face are moved between boundary / ghost planes
+// (SURVEY.md A8 "slot subtlety for halos").  `dst` may be this rank's own lattice (periodic wrap on one GPU),
+// or a z-neighbour's lattice mapped over NVLink (peer stores), so this kernel IS the halo exchange.
+//   after EVEN step (parity_done = 0):  boundary plane, slots opp(movers leaving)  ->  neighbour ghost plane
+//   after ODD  step (parity_done = 1):  own ghost plane, slots of movers that left  ->  neighbour boundary plane
+// Inlet / outlet are the same operation with a constant or the adjacent plane as the source.
+struct FaceOp {
+    int mode;                  // BC_WALL: nothing; BC_PEER: copy src -> dst; BC_INLET; BC_OUTLET
+    int hi;                    // which face of the SENDER (copy) / of this lattice (inlet, outlet) the op is for
+    const float *src;          // copy source: element (k, c) = src[k*src_slot + src_off + c]
+    long long src_slot, src_off;
+    int src_by_index;          // 1: k = 0..4 (a packed message); 0: k = lattice slot number
+    float *dst;                // copy destination lattice base (own, or a z-neighbour's over NVLink); slot stride L.slot
+    long long dst_off;
+    const uint8_t *sender_solid;   // solid flags of the sender's boundary plane (plane-sized) or nullptr
+};
+struct HaloParams {
+    Lattice L;
+    Collision C;
+    FaceOp op[2];
+    int parity_done;
+};
+
+// does the link that brings population i into cell (x,y) cross an x/y wall?  (then bounce-back owns that slot)
+FG_HD bool link_from_wall(const Lattice &L, int i, int x, int y) {
+    const int sx = x - cxr(i), sy = y - cyr(i);
+    return (L.wall_x && (sx < 0 || sx >= L.nx)) || (L.wall_y && (sy < 0 || sy >= L.ny));
+}
+
+struct ZFaceOp {
+    static constexpr int kThreads = 128;
+    static constexpr int kMinBlocks = 4;
+    // grid: (ceil(plane/threads), 5 slots, 2 ops)
+    FG_HD static void run(const HaloParams &p, int bx, int by, int bz, int tx) {
+        const Lattice &L = p.L;
+        const int c = bx * kThreads + tx;
+        if (c >= L.plane) return;
+        const FaceOp &op = p.op[bz];
+        if (op.mode == BC_WALL) return;
+        const bool hi = op.hi != 0;
+        const int y = c / L.nx, x = c - y * L.nx;
+        if (op.mode == BC_PEER) {
+            // even: movers leaving through the sender's face sit in slot opp(i) of its boundary plane (hi: slots ZM)
+            // odd : pushes that crossed the face landed in the sender's ghost plane, natural slot i (hi: slots ZP)
+            const int slot = p.parity_done == 0 ? (hi ? zmr(by) : zpr(by)) : (hi ? zpr(by) : zmr(by));
+            if (p.parity_done == 1) {
+                if (link_from_wall(L, slot, x, y)) return;   // nothing was pushed here; the receiver's bounce-back owns the slot
+                if (op.sender_solid) {
+                    int sx = x - cxr(slot), sy = y - cyr(slot);   // the would-be sender; solid cells do not push
+                    sx = sx < 0 ? sx + L.nx : (sx >= L.nx ? sx - L.nx : sx);
+                    sy = sy < 0 ? sy + L.ny : (sy >= L.ny ? sy - L.ny : sy);
+                    if (op.sender_solid[sy * L.nx + sx]) return;
+                }
+            }
+            const int k = op.src_by_index ? by : slot;
+            op.dst[slot * L.slot + op.dst_off + c] = op.src[k * op.src_slot + op.src_off + c];
+            return;
+        }
+        // inlet / outlet: populations ENTERING through this face, direction i (lo: ZP, hi: ZM)
+        const int i = hi ? zmr(by) : zpr(by);
+        if (p.parity_done == 0) {
+            // the next (odd) step pulls them from ghost slot opp(i)
+            const int gs = oppr(i);
+            float *ghost = L.f + gs * L.slot + (long long)(hi ? L.nz + 1 : 0) * L.plane + c;
+            if (op.mode == BC_INLET) *ghost = p.C.heq_in[i];
+            else *ghost = L.f[gs * L.slot + (long long)(hi ? L.nz : 1) * L.plane + c];   // outlet: copy of the last plane
+        } else {
+            // the next (even) step reads them from natural slot i of the boundary plane
+            if (link_from_wall(L, i, x, y)) return;
+            float *cell = L.f + i * L.slot + (long long)(hi ? L.nz : 1) * L.plane + c;
+            if (op.mode == BC_INLET) *cell = p.C.heq_in[i];
+            else *cell = L.f[i * L.slot + (long long)(hi ? L.nz - 1 : 2) * L.plane + c];   // outlet: what the plane inside received
+        }
+    }
+};
+
+}  // namespace fg

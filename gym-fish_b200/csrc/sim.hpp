@@ -1,0 +1,549 @@
+// sim.hpp — host runtime of the coupled step: handle state, step orchestration, z-slab halos.
+//
+// SURVEY.md §3b call stack (env.step -> fg_step -> per-substep launches); nothing in /root/reference to
+// mirror (README.md only).  Templated on a device policy:
+//   CudaDev (dev_cuda.cuh)   the product — CUDA streams/events, sm_100a kernels, CUDA-IPC peers
+//   HostDev (tests/emu)      test infrastructure — runs the same kernel bodies in a CPU loop
+#pragma once
+#include "../../include/fishgym.h"
+#include "lbm_core.cuh"
+#include "ib_core.cuh"
+#include "body.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace fg {
+
+// what one rank publishes to its z-neighbours (fits FgPeerHandle.bytes)
+struct PeerBlob {
+    uint64_t magic;
+    int32_t pid, device;
+    uint64_t f_ptr, flag_ptr;      // valid inside the publishing process
+    unsigned char f_ipc[64], flag_ipc[64];
+    int32_t nx, ny, nz;
+};
+static_assert(sizeof(PeerBlob) <= sizeof(FgPeerHandle), "PeerBlob must fit the ABI blob");
+constexpr uint64_t kPeerMagic = 0x4647504545523033ull;   // "FGPEER03"
+
+template <class Dev>
+class SimT {
+public:
+    std::string err;
+    FgConfig cfg{};
+    Dev dev;
+
+    // ------------------------------------------------------------------ lifecycle
+    int create(const FgConfig &c) {
+        cfg = c;
+        if (cfg.inlet_rho == 0) cfg.inlet_rho = 1.0;
+        nzl_ = cfg.nz / cfg.n_ranks;
+        if (nzl_ < 2) return fail(FG_EINVAL, "each z-slab needs at least 2 planes");
+        if (!dev.init(cfg.device, err)) return FG_ECUDA;
+        L_ = Lattice{};
+        L_.nx = cfg.nx; L_.ny = cfg.ny; L_.nz = nzl_;
+        const long long plane = (long long)cfg.nx * cfg.ny;
+        if (plane >= (1ll << 30) || plane * (nzl_ + 2) >= (1ll << 31))
+            return fail(FG_EINVAL, "slab too large for 32-bit cell indices");
+        L_.plane = int(plane);
+        L_.slot = plane * (nzl_ + 2);
+        L_.z0 = cfg.rank * nzl_; L_.nzg = cfg.nz;
+        L_.wall_x = cfg.bc[FG_XLO] == FG_BC_WALL; L_.wall_y = cfg.bc[FG_YLO] == FG_BC_WALL;
+        L_.bc_zlo = cfg.bc[FG_ZLO]; L_.bc_zhi = cfg.bc[FG_ZHI];
+        L_.solid = nullptr;
+        L_.f = static_cast<float *>(dev.alloc(size_t(Q) * L_.slot * sizeof(float), err));
+        if (!L_.f) return FG_ENOMEM;
+        flags_ = static_cast<int *>(dev.alloc(4 * sizeof(int), err));
+        if (!flags_) return FG_ENOMEM;
+        if (!dev.zero(flags_, 4 * sizeof(int))) return cuda_fail();
+        setup_collision();
+        if (cfg.max_markers > 0) {
+            if (int rc = ib_.create(dev, cfg, L_, err)) return rc;
+        }
+        return reset(0);
+    }
+
+    void destroy() {
+        ib_.destroy(dev);
+        dev.close_peers();
+        dev.free(L_.f); L_.f = nullptr;
+        dev.free(flags_); flags_ = nullptr;
+        dev.free(solid_); solid_ = nullptr;
+        dev.free(stage_[0]); dev.free(stage_[1]); stage_[0] = stage_[1] = nullptr;
+        dev.shutdown();
+    }
+
+    int reset(uint64_t) {
+        InitParams p{L_, nullptr, nullptr};
+        if (!dev.template launch<InitEquilibrium>(grid_planes(L_.nz + 2), p)) return cuda_fail();
+        parity_ = 0; steps_ = 0;
+        for (auto &f : fish_) f.reset();
+        std::fill(action_.begin(), action_.end(), 0.f);
+        if (!fish_.empty()) {
+            if (int rc = bodies_to_markers()) return rc;
+            ib_.clear_wrenches();
+        }
+        if (!dev.sync()) return cuda_fail();
+        return FG_OK;
+    }
+
+    // ------------------------------------------------------------------ fluid state
+    int set_fields(const float *rho, const float *u) {
+        const size_t n = size_t(L_.plane) * L_.nz;
+        float *d = static_cast<float *>(dev.alloc(4 * n * sizeof(float), err));
+        if (!d) return FG_ENOMEM;
+        bool ok = dev.h2d(d, rho, n * sizeof(float)) && dev.h2d(d + n, u, 3 * n * sizeof(float));
+        InitParams p{L_, d, d + n};
+        ok = ok && dev.template launch<InitEquilibrium>(grid_planes(L_.nz + 2), p) && dev.sync();
+        dev.free(d);
+        if (!ok) return cuda_fail();
+        parity_ = 0;
+        return FG_OK;
+    }
+
+    int get_moments(std::vector<float> &mom) {
+        const size_t n = size_t(L_.plane) * L_.nz;
+        float *d = static_cast<float *>(dev.alloc(4 * n * sizeof(float), err));
+        if (!d) return FG_ENOMEM;
+        GatherParams p{L_, C_, nullptr, d};
+        bool ok = parity_ == 0 ? dev.template launch<GatherArriving<0>>(grid_planes(L_.nz), p)
+                               : dev.template launch<GatherArriving<1>>(grid_planes(L_.nz), p);
+        mom.resize(4 * n);
+        ok = ok && dev.sync() && dev.d2h(mom.data(), d, 4 * n * sizeof(float));
+        dev.free(d);
+        return ok ? FG_OK : cuda_fail();
+    }
+
+    int get_fields(float *rho, float *u) {
+        std::vector<float> mom;
+        if (int rc = get_moments(mom)) return rc;
+        const size_t n = size_t(L_.plane) * L_.nz;
+        for (size_t i = 0; i < n; ++i) rho[i] = 1.0f + mom[i];
+        std::memcpy(u, mom.data() + n, 3 * n * sizeof(float));
+        return FG_OK;
+    }
+    int get_fields_f64(double *rho, double *u) {
+        std::vector<float> mom;
+        if (int rc = get_moments(mom)) return rc;
+        const size_t n = size_t(L_.plane) * L_.nz;
+        for (size_t i = 0; i < n; ++i) rho[i] = 1.0 + double(mom[i]);   // rho-1 travels in fp32, the 1 is added in fp64
+        for (size_t i = 0; i < 3 * n; ++i) u[i] = double(mom[n + i]);
+        return FG_OK;
+    }
+
+    int set_populations(const float *f19) {
+        const size_t n = size_t(L_.plane) * L_.nz;
+        std::vector<float> h(n);
+        for (int i = 0; i < Q; ++i) {
+            const float w = float(WD[i]);
+            for (size_t k = 0; k < n; ++k) h[k] = float(double(f19[i * n + k]) - WD[i]);
+            (void)w;
+            if (!dev.h2d(L_.f + i * L_.slot + L_.plane, h.data(), n * sizeof(float))) return cuda_fail();
+        }
+        parity_ = 0;
+        return FG_OK;
+    }
+
+    int get_populations(float *f19) {
+        const size_t n = size_t(L_.plane) * L_.nz;
+        float *d = static_cast<float *>(dev.alloc(size_t(Q) * n * sizeof(float), err));
+        if (!d) return FG_ENOMEM;
+        GatherParams p{L_, C_, d, nullptr};
+        bool ok = parity_ == 0 ? dev.template launch<GatherArriving<0>>(grid_planes(L_.nz), p)
+                               : dev.template launch<GatherArriving<1>>(grid_planes(L_.nz), p);
+        ok = ok && dev.sync() && dev.d2h(f19, d, size_t(Q) * n * sizeof(float));
+        dev.free(d);
+        if (!ok) return cuda_fail();
+        for (int i = 0; i < Q; ++i)
+            for (size_t k = 0; k < n; ++k) f19[i * n + k] = float(double(f19[i * n + k]) + WD[i]);
+        return FG_OK;
+    }
+
+    int set_solid(const uint8_t *g) {
+        if (!g) {
+            dev.free(solid_); solid_ = nullptr; L_.solid = nullptr;
+            return FG_OK;
+        }
+        const size_t tot = size_t(L_.plane) * (L_.nz + 2);
+        std::vector<uint8_t> h(tot, 0);
+        const bool pz = cfg.bc[FG_ZLO] == FG_BC_PERIODIC;
+        bool any = false;
+        for (int zl = -1; zl <= L_.nz; ++zl) {
+            int zg = L_.z0 + zl;
+            if (zg < 0 || zg >= L_.nzg) { if (!pz) continue; zg = (zg + L_.nzg) % L_.nzg; }
+            for (int p = 0; p < L_.plane; ++p) {
+                const uint8_t v = g[size_t(zg) * L_.plane + p] ? 1 : 0;
+                h[size_t(zl + 1) * L_.plane + p] = v;
+                any = any || v;
+            }
+        }
+        if (!any) return set_solid(nullptr);
+        if (!solid_) solid_ = static_cast<uint8_t *>(dev.alloc(tot, err));
+        if (!solid_) return FG_ENOMEM;
+        if (!dev.h2d(solid_, h.data(), tot)) return cuda_fail();
+        L_.solid = solid_;
+        return FG_OK;
+    }
+
+    // ------------------------------------------------------------------ immersed boundary / bodies
+    int set_markers(int n, const float *X, const float *U, const float *dV, const int32_t *link) {
+        if (n > cfg.max_markers) return fail(FG_EINVAL, "more markers than FgConfig.max_markers");
+        if (!fish_.empty()) return fail(FG_ESTATE, "markers are generated by fish bodies on this handle");
+        if (cfg.n_ranks > 1) {
+            // no marker exchange between slabs yet: every 4-wide stencil must lie inside this rank's planes
+            for (int k = 0; k < n; ++k) {
+                const int k0 = int(std::floor(X[3 * k + 2])) - 1;
+                if (k0 < L_.z0 || k0 + 3 >= L_.z0 + L_.nz)
+                    return fail(FG_ENOTSUP, "a marker stencil crosses a z-slab face: immersed boundary across slabs is not supported yet");
+            }
+        }
+        if (n > 0 && !ib_.ready()) return fail(FG_ESTATE, "FgConfig.max_markers was 0 at create");
+        if (!ib_.ready()) return FG_OK;
+        return ib_.set_markers(dev, n, X, U, dV, link, err);
+    }
+    int set_link_origins(int n, const double *o) {
+        if (!ib_.ready()) return fail(FG_ESTATE, "FgConfig.max_markers was 0 at create");
+        return ib_.set_link_origins(n, o, err);
+    }
+    IbState<Dev> &ib() { return ib_; }
+    int get_force_field(float *F) {
+        if (!ib_.ready()) {
+            std::fill(F, F + 3 * size_t(L_.plane) * L_.nz, 0.f);
+            return FG_OK;
+        }
+        return ib_.get_force_field(dev, L_, F, err);
+    }
+
+    int add_fish(const FgFishDesc &d, int32_t *id) {
+        if (cfg.n_ranks > 1) return fail(FG_ENOTSUP, "bodies across z-slabs are not supported yet");
+        if (!ib_.ready()) return fail(FG_ESTATE, "FgConfig.max_markers was 0 at create");
+        Fish f;
+        if (!f.init(d, err)) return FG_EINVAL;
+        int n = f.n_markers(), nl = f.n_links();
+        for (auto &o : fish_) { n += o.n_markers(); nl += o.n_links(); }
+        if (n > cfg.max_markers || nl > cfg.max_links) return fail(FG_EINVAL, "fish exceeds FgConfig.max_markers / max_links");
+        fish_.push_back(f);
+        int na = 0;
+        for (auto &o : fish_) na += o.n_joints();
+        action_.assign(na, 0.f);
+        if (int rc = bodies_to_markers()) return rc;
+        if (id) *id = int(fish_.size()) - 1;
+        return FG_OK;
+    }
+    int action_size() const { return int(action_.size()); }
+    int obs_size() const {
+        int n = 0;
+        for (auto &f : fish_) n += f.obs_size();
+        return n;
+    }
+    int set_action(const float *a, int n) {
+        if (n != action_size()) return fail(FG_EINVAL, "action length != fg_action_size()");
+        for (int i = 0; i < n; ++i) action_[i] = std::min(1.f, std::max(-1.f, a[i]));
+        return FG_OK;
+    }
+    int get_obs(float *o, int n) {
+        if (n != obs_size()) return fail(FG_EINVAL, "obs length != fg_obs_size()");
+        int k = 0;
+        for (auto &f : fish_) { f.write_obs(o + k); k += f.obs_size(); }
+        return FG_OK;
+    }
+
+    // ------------------------------------------------------------------ stepping
+    int step(int n) {
+        if (n < 0) return fail(FG_EINVAL, "n_substeps < 0");
+        const bool ranks = cfg.n_ranks > 1;
+        if (ranks && !peers_ && n != 1)
+            return fail(FG_ESTATE, "z-slabs without device peers: step one substep at a time and exchange halos (fg_halo_pack/unpack)");
+        if (ranks && !peers_ && pending_faces_ > 0)
+            return fail(FG_ESTATE, "halo exchange incomplete: unpack every internal face after fg_step");
+        const bool prof = (cfg.flags & FG_FLAG_PROFILE) != 0;
+        dev.marks_reset();
+        dev.tic();
+        for (int it = 0; it < n; ++it) {
+            if (!fish_.empty()) {
+                // A7 (1): bodies advance on the host with the wrenches of the previous substep
+                if (int rc = ib_.fetch_wrenches(dev, err)) return rc;
+                int lo = 0, ao = 0;
+                for (auto &f : fish_) {
+                    f.advance(&action_[ao], ib_.wrench_ptr() + 6 * lo, ib_.origin_ptr() + 3 * lo);
+                    lo += f.n_links(); ao += f.n_joints();
+                }
+                if (int rc = bodies_to_markers()) return rc;
+            }
+            ForceField F{};
+            if (ib_.ready() && ib_.n_markers() > 0) {
+                if (prof) dev.mark(1);
+                if (int rc = ib_.compute_forces(dev, L_, C_, parity_, err)) return rc;
+                if (prof) dev.mark(1);
+                F = ib_.force_view();
+            }
+            const bool overlap = ranks && peers_ && !(cfg.flags & FG_FLAG_NO_OVERLAP) && L_.nz >= 4;
+            if (ranks && peers_ && !dev.wait_flags(flags_, has_lo_peer(), has_hi_peer(), tick_)) return cuda_fail();
+            if (overlap) {
+                // boundary planes first, push halos over NVLink, then the interior hides the exchange
+                if (prof) dev.mark(0);
+                if (!launch_collide(1, 2, F) || !launch_collide(L_.nz, L_.nz + 1, F)) return cuda_fail();
+                if (prof) dev.mark(0);
+                if (!launch_faces()) return cuda_fail();
+                if (prof) dev.mark(0);
+                if (!launch_collide(2, L_.nz, F)) return cuda_fail();
+                if (prof) dev.mark(0);
+                collide_launches_ += 3;
+            } else {
+                if (prof) dev.mark(0);
+                if (!launch_collide(1, L_.nz + 1, F)) return cuda_fail();
+                if (prof) dev.mark(0);
+                if (!launch_faces()) return cuda_fail();
+                collide_launches_ += 1;
+            }
+            if (ib_.ready() && ib_.n_markers() > 0) {
+                if (int rc = ib_.after_collide(dev, err)) return rc;
+            }
+            parity_ ^= 1;
+            ++steps_; ++tick_;
+        }
+        last_ms_ = dev.toc();
+        if (!dev.sync()) return cuda_fail();
+        if (prof) {
+            collide_ms_ = dev.marks_elapsed(0); ib_ms_ = dev.marks_elapsed(1);
+            last_collide_launches_ = collide_launches_;
+        }
+        collide_launches_ = 0;
+        if (peers_) {
+            int timed_out = 0;
+            if (!dev.d2h(&timed_out, flags_ + 3, sizeof(int))) return cuda_fail();
+            if (timed_out) return fail(FG_EPEER, "timed out waiting for a z-neighbour's halo (ranks out of step?)");
+        }
+        if (ib_.ready() && ib_.n_markers() > 0) {
+            if (int rc = ib_.fetch_wrenches(dev, err)) return rc;
+        }
+        last_mlups_ = last_ms_ > 0 ? double(L_.plane) * L_.nz * n / last_ms_ / 1e3 : 0;
+        if (ranks && !peers_) pending_faces_ = int(internal_lo()) + int(internal_hi());
+        return FG_OK;
+    }
+
+    int get_stats(FgStats *o) {
+        std::memset(o, 0, sizeof(*o));
+        o->steps = steps_;
+        o->cells = int64_t(L_.plane) * L_.nz;
+        o->last_step_ms = last_ms_;
+        o->last_mlups = last_mlups_;
+        o->kernel_launches = dev.launches;
+        o->n_markers = ib_.n_markers(); o->n_links = ib_.n_links(); o->band_cells = ib_.band_cells();
+        o->parity = parity_;
+        o->collide_ms = collide_ms_; o->collide_launches = last_collide_launches_; o->ib_ms = ib_ms_;
+        return FG_OK;
+    }
+
+    // ------------------------------------------------------------------ halos
+    bool internal_lo() const { return cfg.n_ranks > 1 && (cfg.rank > 0 || cfg.bc[FG_ZLO] == FG_BC_PERIODIC); }
+    bool internal_hi() const { return cfg.n_ranks > 1 && (cfg.rank < cfg.n_ranks - 1 || cfg.bc[FG_ZHI] == FG_BC_PERIODIC); }
+    bool has_lo_peer() const { return peers_ && internal_lo(); }
+    bool has_hi_peer() const { return peers_ && internal_hi(); }
+    int64_t halo_bytes() const { return int64_t(5) * L_.plane * sizeof(float); }
+
+    // the last step's parity decides which plane / slots carry the populations that crossed the face
+    int halo_pack(int face, void *buf) {
+        if (face != FG_ZLO && face != FG_ZHI) return fail(FG_EINVAL, "face must be FG_ZLO or FG_ZHI");
+        if (steps_ == 0) return fail(FG_ESTATE, "fg_halo_pack: call after fg_step");
+        const bool hi = face == FG_ZHI;
+        const int done = parity_ ^ 1;
+        float *out = static_cast<float *>(buf);
+        for (int q = 0; q < 5; ++q) {
+            const int slot = done == 0 ? (hi ? ZMT[q] : ZPT[q]) : (hi ? ZPT[q] : ZMT[q]);
+            const int zz = done == 0 ? (hi ? L_.nz : 1) : (hi ? L_.nz + 1 : 0);
+            if (!dev.d2h(out + size_t(q) * L_.plane, L_.f + slot * L_.slot + (long long)zz * L_.plane, L_.plane * sizeof(float)))
+                return cuda_fail();
+        }
+        return FG_OK;
+    }
+
+    int halo_unpack(int face, const void *buf) {
+        if (face != FG_ZLO && face != FG_ZHI) return fail(FG_EINVAL, "face must be FG_ZLO or FG_ZHI");
+        if (pending_faces_ <= 0) return fail(FG_ESTATE, "fg_halo_unpack: call after fg_step");
+        const bool hi = face == FG_ZHI;
+        float *&st = stage_[hi];
+        if (!st) st = static_cast<float *>(dev.alloc(size_t(5) * L_.plane * sizeof(float), err));
+        if (!st) return FG_ENOMEM;
+        if (!dev.h2d(st, buf, size_t(5) * L_.plane * sizeof(float))) return cuda_fail();
+        const int done = parity_ ^ 1;
+        HaloParams p{};
+        p.L = L_; p.C = C_; p.parity_done = done;
+        p.op[1].mode = BC_WALL;
+        FaceOp &op = p.op[0];
+        op.mode = BC_PEER;
+        op.hi = hi ? 0 : 1;                 // what arrives at my low face left the sender through ITS high face
+        op.src = st; op.src_slot = L_.plane; op.src_off = 0; op.src_by_index = 1;
+        op.dst = L_.f;
+        // even: into my ghost plane; odd: into my boundary plane
+        const int dzz = done == 0 ? (hi ? L_.nz + 1 : 0) : (hi ? L_.nz : 1);
+        op.dst_off = (long long)dzz * L_.plane;
+        // the sender's boundary plane is my ghost plane
+        op.sender_solid = L_.solid ? L_.solid + (long long)(hi ? L_.nz + 1 : 0) * L_.plane : nullptr;
+        Dim3 g{(L_.plane + ZFaceOp::kThreads - 1) / ZFaceOp::kThreads, 5, 1};
+        if (!dev.template launch<ZFaceOp>(g, p) || !dev.sync()) return cuda_fail();
+        --pending_faces_;
+        return FG_OK;
+    }
+
+    int peer_export(FgPeerHandle *out) {
+        PeerBlob b{};
+        b.magic = kPeerMagic;
+        b.nx = L_.nx; b.ny = L_.ny; b.nz = L_.nz;
+        if (!dev.export_peer(L_.f, flags_, b, err)) return FG_EPEER;
+        std::memset(out, 0, sizeof(*out));
+        std::memcpy(out->bytes, &b, sizeof(b));
+        return FG_OK;
+    }
+
+    int peer_connect(const FgPeerHandle *lo, const FgPeerHandle *hi) {
+        if (cfg.n_ranks < 2) return fail(FG_ESTATE, "fg_peer_connect needs n_ranks > 1");
+        if (internal_lo() != (lo != nullptr) || internal_hi() != (hi != nullptr))
+            return fail(FG_EINVAL, "pass a handle for exactly the internal faces of this slab");
+        const FgPeerHandle *hs[2] = {lo, hi};
+        for (int s = 0; s < 2; ++s) {
+            peer_f_[s] = nullptr; peer_flags_[s] = nullptr;
+            if (!hs[s]) continue;
+            PeerBlob b;
+            std::memcpy(&b, hs[s]->bytes, sizeof(b));
+            if (b.magic != kPeerMagic) return fail(FG_EPEER, "peer handle: bad magic");
+            if (b.nx != L_.nx || b.ny != L_.ny || b.nz != L_.nz) return fail(FG_EPEER, "peer handle: slab geometry differs");
+            if (!dev.open_peer(b, &peer_f_[s], &peer_flags_[s], err)) return FG_EPEER;
+        }
+        peers_ = true;
+        pending_faces_ = 0;
+        return FG_OK;
+    }
+
+    int fail(int code, const std::string &m) { err = m; return code; }
+    int cuda_fail() { err = dev.err; return FG_ECUDA; }
+
+private:
+    Dim3 grid_planes(int planes) const {
+        return Dim3{(L_.nx + 127) / 128, L_.ny, planes};
+    }
+
+    void setup_collision() {
+        C_ = Collision{};
+        C_.omega = float(1.0 / cfg.tau);
+        bool all_zero = true;
+        for (int k = 0; k < Q; ++k) all_zero = all_zero && cfg.mrt_rates[k] == 0.0;
+        const double sn = 1.0 / cfg.tau;
+        const double dflt[Q] = {0, 1.19, 1.4, 0, 1.2, 0, 1.2, 0, 1.2, sn, 1.4, sn, 1.4, sn, sn, sn, 1.98, 1.98, 1.98};
+        for (int k = 0; k < Q; ++k) C_.rate[k] = float(all_zero ? dflt[k] : cfg.mrt_rates[k]);
+        C_.rate[0] = C_.rate[3] = C_.rate[5] = C_.rate[7] = 0.f;
+        for (int d = 0; d < 3; ++d) C_.g[d] = float(cfg.body_force[d]);
+        for (int f = 0; f < 6; ++f)
+            for (int i = 0; i < Q; ++i)
+                C_.wallterm[f][i] = float(6.0 * WD[i] * (CXT[i] * cfg.wall_u[f][0] + CYT[i] * cfg.wall_u[f][1] + CZT[i] * cfg.wall_u[f][2]));
+        const double r = cfg.inlet_rho, ux = cfg.inlet_u[0], uy = cfg.inlet_u[1], uz = cfg.inlet_u[2];
+        const double uu = ux * ux + uy * uy + uz * uz;
+        for (int i = 0; i < Q; ++i) {
+            const double cu = CXT[i] * ux + CYT[i] * uy + CZT[i] * uz;
+            C_.heq_in[i] = float(WD[i] * ((r - 1.0) + r * (3.0 * cu + 4.5 * cu * cu - 1.5 * uu)));
+        }
+    }
+
+    template <int PARITY>
+    bool launch_collide_p(const StepParams &p, Dim3 g) {
+        return cfg.collision == FG_MRT ? dev.template launch<StreamCollide<PARITY, true>>(g, p)
+                                       : dev.template launch<StreamCollide<PARITY, false>>(g, p);
+    }
+    bool launch_collide(int zz_begin, int zz_end, const ForceField &F) {
+        if (zz_end <= zz_begin) return true;
+        StepParams p{L_, C_, F, zz_begin, zz_end};
+        const Dim3 g = grid_planes(zz_end - zz_begin);
+        return parity_ == 0 ? launch_collide_p<0>(p, g) : launch_collide_p<1>(p, g);
+    }
+
+    // z-face plane ops after the step of parity `parity_`: one launch covers both faces
+    bool launch_faces() {
+        HaloParams p{};
+        p.L = L_; p.C = C_; p.parity_done = parity_;
+        bool any = false;
+        for (int s = 0; s < 2; ++s) {
+            const bool hi = s == 1;
+            FaceOp &op = p.op[s];
+            op.mode = BC_WALL;
+            op.hi = hi;
+            const bool at_global = hi ? (cfg.rank == cfg.n_ranks - 1) : (cfg.rank == 0);
+            const int bc = hi ? cfg.bc[FG_ZHI] : cfg.bc[FG_ZLO];
+            const bool internal = hi ? internal_hi() : internal_lo();
+            float *dst = nullptr;
+            if (cfg.n_ranks == 1) {
+                if (bc == FG_BC_PERIODIC) dst = L_.f;            // wrap onto myself
+                else if (bc == FG_BC_INLET || bc == FG_BC_OUTLET) op.mode = bc;
+            } else if (internal) {
+                if (peers_) dst = peer_f_[s];                    // neighbour's lattice over NVLink
+            } else if (at_global && (bc == FG_BC_INLET || bc == FG_BC_OUTLET)) {
+                op.mode = bc;
+            }
+            if (dst) {
+                op.mode = BC_PEER;
+                op.src = L_.f; op.src_slot = L_.slot; op.src_by_index = 0;
+                op.dst = dst;
+                if (parity_ == 0) {   // boundary plane -> neighbour ghost plane
+                    op.src_off = (long long)(hi ? L_.nz : 1) * L_.plane;
+                    op.dst_off = (long long)(hi ? 0 : L_.nz + 1) * L_.plane;
+                } else {              // my ghost plane -> neighbour boundary plane
+                    op.src_off = (long long)(hi ? L_.nz + 1 : 0) * L_.plane;
+                    op.dst_off = (long long)(hi ? 1 : L_.nz) * L_.plane;
+                }
+                op.sender_solid = L_.solid ? L_.solid + (long long)(hi ? L_.nz : 1) * L_.plane : nullptr;
+            }
+            any = any || op.mode != BC_WALL;
+        }
+        if (any) {
+            Dim3 g{(L_.plane + ZFaceOp::kThreads - 1) / ZFaceOp::kThreads, 5, 2};
+            if (!dev.template launch<ZFaceOp>(g, p)) return false;
+        }
+        if (peers_) {
+            // publish "my halos of tick+1 are in your memory" to both neighbours
+            if (!dev.signal_flags(has_lo_peer() ? peer_flags_[0] + 1 : nullptr, has_hi_peer() ? peer_flags_[1] + 0 : nullptr, tick_ + 1))
+                return false;
+        }
+        return true;
+    }
+
+    int bodies_to_markers() {
+        int n = 0, nl = 0;
+        for (auto &f : fish_) { n += f.n_markers(); nl += f.n_links(); }
+        mX_.resize(3 * size_t(n)); mU_.resize(3 * size_t(n)); mdV_.resize(n); mlink_.resize(n);
+        morigin_.resize(3 * size_t(nl));
+        int mo = 0, lo = 0;
+        for (auto &f : fish_) {
+            f.emit_markers(&mX_[3 * size_t(mo)], &mU_[3 * size_t(mo)], &mdV_[mo], &mlink_[mo], lo, &morigin_[3 * size_t(lo)]);
+            mo += f.n_markers(); lo += f.n_links();
+        }
+        if (int rc = ib_.set_markers(dev, n, mX_.data(), mU_.data(), mdV_.data(), mlink_.data(), err)) return rc;
+        return ib_.set_link_origins(nl, morigin_.data(), err);
+    }
+
+    Lattice L_{};
+    Collision C_{};
+    int nzl_ = 0;
+    int parity_ = 0;
+    int64_t steps_ = 0;
+    int tick_ = 0;                 // never reset: orders halo flags between neighbours
+    double last_ms_ = 0, last_mlups_ = 0, collide_ms_ = 0, ib_ms_ = 0;
+    int64_t collide_launches_ = 0, last_collide_launches_ = 0;
+    uint8_t *solid_ = nullptr;
+    int *flags_ = nullptr;         // [0] written by my z-low neighbour, [1] by my z-high neighbour
+    float *stage_[2] = {nullptr, nullptr};
+    bool peers_ = false;
+    float *peer_f_[2] = {nullptr, nullptr};
+    int *peer_flags_[2] = {nullptr, nullptr};
+    int pending_faces_ = 0;
+    IbState<Dev> ib_;
+    std::vector<Fish> fish_;
+    std::vector<float> action_;
+    std::vector<float> mX_, mU_, mdV_;
+    std::vector<int32_t> mlink_;
+    std::vector<double> morigin_;
+};
+
+}  // namespace fg

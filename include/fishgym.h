@@ -60,6 +60,7 @@ extern "C" {
 
 /* FgConfig.flags */
 #define FG_FLAG_NO_OVERLAP 1   /* multi-GPU: halo after the full-slab kernel (overlap off) */
+#define FG_FLAG_PROFILE    2   /* bracket every stream-collide launch with events -> FgStats.collide_ms */
 
 typedef struct FgConfig {
     int32_t struct_size;      /* = sizeof(FgConfig); checked by fg_create */
@@ -90,6 +91,9 @@ typedef struct FgStats {
     int32_t n_markers, n_links;
     int32_t band_cells;       /* cells inside marker stencils in the last step */
     int32_t parity;           /* AA-pattern parity of the next step (0 even / 1 odd); oracle: 0 */
+    double  collide_ms;       /* FG_FLAG_PROFILE: summed device time of the stream-collide launches of the last fg_step */
+    int64_t collide_launches; /* ... and how many launches that covers */
+    double  ib_ms;            /* FG_FLAG_PROFILE: summed device time of the immersed-boundary kernels of the last fg_step */
 } FgStats;
 
 /* articulated swimmer description: a planar chain of n_links ellipsoid links, yawing joints */

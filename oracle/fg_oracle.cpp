@@ -24,6 +24,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -116,6 +117,7 @@ struct FgSim {
     std::vector<uint8_t> solid;   // [nz+2][ny][nx] incl. ghost planes
     bool has_solid = false;
     double rates[Q]{};
+    double AT[Q][Q]{}, BT[Q][Q]{};   // transposed relaxation matrices A = M^-1 S M, B = M^-1 (I - S/2) M
     double omega = 1.25;
     double feq_in[Q]{};
     // immersed boundary
@@ -165,17 +167,34 @@ void set_equilibrium_everywhere(FgSim *s, double rho, double ux, double uy, doub
 }
 
 // -------- collide: f -> fs on owned cells --------
-void collide(FgSim *s) {
+// m* = m - S (m - m_eq) + (I - S/2) M Phi  and  f* = M^-1 m*  collapse into two constant matrices,
+//   f* = f - A (f - f_eq) + B Phi,   A = M^-1 S M,   B = M^-1 (I - S/2) M     (BGK: A = omega I, B = (1 - omega/2) I)
+// stored transposed so that the products run in vectorisable axpy form (no reassociation needed).
+void build_relaxation(FgSim *s) {
     const Moments &mm = moments();
+    for (int k = 0; k < Q; ++k)
+        for (int i = 0; i < Q; ++i) {
+            double a = 0, b = 0;
+            for (int r = 0; r < Q; ++r) {
+                a += mm.Minv[i][r] * s->rates[r] * mm.M[r][k];
+                b += mm.Minv[i][r] * (1.0 - 0.5 * s->rates[r]) * mm.M[r][k];
+            }
+            s->AT[k][i] = a;   // AT[k][i] = A[i][k]
+            s->BT[k][i] = b;
+        }
+}
+
+void collide(FgSim *s) {
     const bool mrt = s->cfg.collision == FG_MRT;
     const double gx = s->cfg.body_force[0], gy = s->cfg.body_force[1], gz = s->cfg.body_force[2];
     const bool ibf = s->force_dirty;
+    const bool any_force = ibf || gx != 0 || gy != 0 || gz != 0;
 #pragma omp parallel for schedule(static)
     for (int z = 0; z < s->nz; ++z)
         for (int y = 0; y < s->ny; ++y)
             for (int x = 0; x < s->nx; ++x) {
                 const size_t c = s->idx(x, y, z);
-                double fi[Q], feq[Q], phi[Q], out[Q];
+                double fi[Q], feq[Q], phi[Q], d[Q], out[Q];
                 for (int i = 0; i < Q; ++i) fi[i] = s->F(s->f, i)[c];
                 if (s->has_solid && s->solid[c]) {
                     for (int i = 0; i < Q; ++i) s->F(s->fs, i)[c] = fi[i];
@@ -197,26 +216,22 @@ void collide(FgSim *s) {
                     phi[i] = W[i] * ((3.0 * (CX[i] - ux) + 9.0 * cu * CX[i]) * Fxc +
                                      (3.0 * (CY[i] - uy) + 9.0 * cu * CY[i]) * Fyc +
                                      (3.0 * (CZ[i] - uz) + 9.0 * cu * CZ[i]) * Fzc);
+                    d[i] = fi[i] - feq[i];
                 }
                 if (!mrt) {
                     const double om = s->omega;
-                    for (int i = 0; i < Q; ++i) out[i] = fi[i] - om * (fi[i] - feq[i]) + (1.0 - 0.5 * om) * phi[i];
+                    for (int i = 0; i < Q; ++i) out[i] = fi[i] - om * d[i] + (1.0 - 0.5 * om) * phi[i];
                 } else {
-                    double m[Q];
+                    for (int i = 0; i < Q; ++i) out[i] = fi[i];
                     for (int k = 0; k < Q; ++k) {
-                        double a = 0, b = 0, p = 0;
-                        for (int i = 0; i < Q; ++i) {
-                            a += mm.M[k][i] * fi[i];
-                            b += mm.M[k][i] * feq[i];
-                            p += mm.M[k][i] * phi[i];
+                        const double dk = d[k];
+                        for (int i = 0; i < Q; ++i) out[i] -= s->AT[k][i] * dk;
+                    }
+                    if (any_force)
+                        for (int k = 0; k < Q; ++k) {
+                            const double pk = phi[k];
+                            for (int i = 0; i < Q; ++i) out[i] += s->BT[k][i] * pk;
                         }
-                        m[k] = a - s->rates[k] * (a - b) + (1.0 - 0.5 * s->rates[k]) * p;
-                    }
-                    for (int i = 0; i < Q; ++i) {
-                        double a = 0;
-                        for (int k = 0; k < Q; ++k) a += mm.Minv[i][k] * m[k];
-                        out[i] = a;
-                    }
                 }
                 for (int i = 0; i < Q; ++i) s->F(s->fs, i)[c] = out[i];
             }
@@ -263,6 +278,13 @@ void stream(FgSim *s) {
             for (int x = 0; x < s->nx; ++x) {
                 const size_t c = s->idx(x, y, z);
                 if (s->has_solid && s->solid[c]) continue;
+                const int zg = s->z0 + z;
+                if (!s->has_solid && x > 0 && x < s->nx - 1 && y > 0 && y < s->ny - 1 && zg > 0 && zg < s->nzg - 1) {
+                    // interior cell: no face is crossed, the pull rule reduces to f_i(x) = f*_i(x - c_i)
+                    for (int i = 0; i < Q; ++i)
+                        s->F(s->f, i)[c] = s->F(s->fs, i)[c - (ptrdiff_t(CZ[i]) * s->ny + CY[i]) * s->nx - CX[i]];
+                    continue;
+                }
                 for (int i = 0; i < Q; ++i) s->F(s->f, i)[c] = pull(s, s->fs, i, x, y, z);
             }
     s->stream_pending = false;
@@ -483,6 +505,7 @@ int fg_create(const FgConfig *cfg, FgSim **out) {
         std::copy(cfg->mrt_rates, cfg->mrt_rates + Q, s->rates);
         s->rates[0] = s->rates[3] = s->rates[5] = s->rates[7] = 0.0;   // conserved moments
     }
+    build_relaxation(s);
     equilibrium(s->cfg.inlet_rho, cfg->inlet_u[0], cfg->inlet_u[1], cfg->inlet_u[2], s->feq_in);
     set_equilibrium_everywhere(s, 1.0, 0, 0, 0);
     if (cfg->max_markers > 0) ensure_ib_storage(s);

@@ -31,6 +31,7 @@ public:
         desc_ = d;
         nl_ = d.n_links;
         mass_.resize(nl_); inertia_.resize(nl_); first_.resize(nl_ + 1);
+        cmark_.assign(nl_, 0.0); cmark2_.assign(nl_, 0.0); ctot_ = 0;
         xi_.clear(); dV_.clear();
         const double PI = 3.14159265358979323846;
         for (int k = 0; k < nl_; ++k) {
@@ -54,6 +55,10 @@ public:
                 xi_.push_back(r * sx); xi_.push_back(r * sy); xi_.push_back(a * sz);
                 const double stretch = std::sqrt((r * a * sx) * (r * a * sx) + (r * a * sy) * (r * a * sy) + (r * r * sz) * (r * r * sz));
                 dV_.push_back(4.0 * PI / n * stretch);   // area element x unit shell thickness
+                // penalty stiffness of the direct forcing seen by the body: sum 2 dV (translation), sum 2 dV |xi_planar|^2 (yaw)
+                cmark_[k] += 2.0 * dV_.back();
+                cmark2_[k] += 2.0 * dV_.back() * ((r * sx) * (r * sx) + (a * sz) * (a * sz));
+                ctot_ += 2.0 * dV_.back();
             }
         }
         first_[nl_] = int(dV_.size());
@@ -71,7 +76,7 @@ public:
     void reset() {
         std::fill(q_.begin(), q_.end(), 0.0);
         std::fill(qd_.begin(), qd_.end(), 0.0);
-        th0_ = desc_.heading; om0_ = 0; P_ = V2{}; L_ = 0;
+        th0_ = desc_.heading; om0_ = 0; P_ = V2{}; L_ = 0; dP_ = V2{}; dL_ = 0;
         // place the head centre at root_pos: com = head + com_rel
         shape(th0_);
         com_.x = desc_.root_pos[0] + com_rel_.x;
@@ -100,17 +105,26 @@ public:
                 const V2 arm{origin3[3 * k] - com_.x, origin3[3 * k + 2] - com_.z};
                 T += w[4] + cross_y(arm, V2{w[0], w[2]});
             }
-            P_.x += F.x; P_.z += F.z; L_ += T;
             double M = 0;
             for (double m : mass_) M += m;
-            com_.x += P_.x / M; com_.z += P_.z / M;
-            // yaw rate from conserved angular momentum, geometry at the old heading and new joints
+            // geometry at the old heading and new joints
             shape(th0_);
-            double I = 0, Ls = 0;
+            double I = 0, Ls = 0, Cr = 0;
             for (int k = 0; k < nl_; ++k) {
-                I += inertia_[k] + mass_[k] * (rel_[k].x * rel_[k].x + rel_[k].z * rel_[k].z);
+                const double r2 = rel_[k].x * rel_[k].x + rel_[k].z * rel_[k].z;
+                I += inertia_[k] + mass_[k] * r2;
                 Ls += inertia_[k] * omr_[k] + mass_[k] * cross_y(rel_[k], srel_[k]);
+                Cr += cmark_[k] * r2 + cmark2_[k];
             }
+            // explicit coupling with the direct-forcing penalty F = 2(U_d - U*) is unstable for light bodies
+            // (added-mass instability); a virtual mass Mv = beta * sum(2 dV) filters the momentum increment:
+            // (M + Mv) a_new = F + Mv a_old, fixed point a = F/M, unconditionally stable for beta >= 1/4
+            const double Mv = kBeta * ctot_, Iv = kBeta * Cr;
+            dP_.x = (M * F.x + Mv * dP_.x) / (M + Mv);
+            dP_.z = (M * F.z + Mv * dP_.z) / (M + Mv);
+            dL_ = (I * T + Iv * dL_) / (I + Iv);
+            P_.x += dP_.x; P_.z += dP_.z; L_ += dL_;
+            com_.x += P_.x / M; com_.z += P_.z / M;
             om0_ = (L_ - Ls) / I;
             th0_ += om0_;
         }
@@ -206,8 +220,11 @@ private:
     std::vector<int> first_;
     std::vector<double> xi_, dV_;          // body-frame marker points [n][3] (lateral, y, axial), volumes
     std::vector<double> q_, qd_;
-    double th0_ = 0, om0_ = 0, L_ = 0;
-    V2 P_{}, com_{}, com_rel_{};
+    static constexpr double kBeta = 0.5;
+    std::vector<double> cmark_, cmark2_;   // per link: sum 2 dV, sum 2 dV |xi|^2 in the swimming plane
+    double ctot_ = 0;
+    double th0_ = 0, om0_ = 0, L_ = 0, dL_ = 0;
+    V2 P_{}, dP_{}, com_{}, com_rel_{};
     std::vector<V2> rel_, srel_, c_, v_;
     std::vector<double> omr_, thl_, th_, om_;
 };

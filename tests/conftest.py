@@ -1,0 +1,48 @@
+"""pytest configuration: the `gpu` marker, library fixtures and shared helpers.
+
+-m "not gpu": oracle vs analytic results and golden vectors, host logic, the CUDA kernel bodies run through the
+              test-only host emulation (tests/emu), ABI symbol checks.  No compute call into the CUDA library.
+-m gpu      : parity of the CUDA library against the oracle, through the C ABI, on a B200.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+EMU = os.path.join(ROOT, "tests", "emu", "libfishgym_emu.so")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
+
+
+def _ensure(path, directory):
+    if not os.path.exists(path):
+        subprocess.run(["make", "-C", os.path.join(ROOT, directory)], check=True, stdout=subprocess.DEVNULL)
+    return path
+
+
+@pytest.fixture(scope="session")
+def g():
+    import gym_fish_b200
+    _ensure(gym_fish_b200._abi.LIB_PATHS["oracle"], "oracle")
+    return gym_fish_b200
+
+
+@pytest.fixture(scope="session")
+def emu(g):
+    return _ensure(EMU, "tests/emu")
+
+
+@pytest.fixture(scope="session")
+def cuda(g):
+    """Backend name for GPU tests; fails (not skips) if the library is missing."""
+    g.load_library("cuda")
+    return "cuda"

@@ -1,0 +1,81 @@
+// dev_host.hpp — TEST INFRASTRUCTURE: a device policy that runs the kernel bodies of
+// gym-fish_b200/csrc/*.cuh in plain CPU loops (block by block, thread by thread).
+// It exists so that AA-pattern indexing, bounce-back, z-face ops and the IB kernels can be checked
+// against the fp64 oracle in this GPU-less container before GPU time is spent.  It is never loaded by
+// the product (gym-fish_b200/_abi.py knows only the CUDA library); results from it are not benchmarks.
+#pragma once
+#include <chrono>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <unistd.h>
+
+namespace fg {
+
+struct PeerBlob;
+
+class HostDev {
+public:
+    std::string err;
+    long long launches = 0;
+
+    bool init(int, std::string &) { return true; }
+    void shutdown() {}
+    void *alloc(size_t bytes, std::string &e) {
+        void *p = std::malloc(bytes ? bytes : 1);
+        if (!p) e = "host emulation: malloc failed";
+        return p;
+    }
+    void free(void *p) { std::free(p); }
+    bool h2d(void *d, const void *s, size_t n) { std::memcpy(d, s, n); return true; }
+    bool d2h(void *d, const void *s, size_t n) { std::memcpy(d, s, n); return true; }
+    bool zero(void *d, size_t n) { std::memset(d, 0, n); return true; }
+    bool sync() { return true; }
+    void tic() { t0_ = std::chrono::steady_clock::now(); }
+    void marks_reset() {}
+    void mark(int) {}
+    double marks_elapsed(int) { return 0.0; }
+    double toc() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0_).count(); }
+
+    template <class K, class P>
+    bool launch(Dim3 g, const P &p) {
+        ++launches;
+        for (int bz = 0; bz < g.z; ++bz)
+            for (int by = 0; by < g.y; ++by)
+                for (int bx = 0; bx < g.x; ++bx)
+                    for (int tx = 0; tx < K::kThreads; ++tx) K::run(p, bx, by, bz, tx);
+        return true;
+    }
+
+    // peers: only same-process handles (raw pointers) — lets the CPU tests run two slabs in one process
+    template <class Blob>
+    bool export_peer(float *f, int *flags, Blob &b, std::string &) {
+        b.pid = int(getpid()); b.device = -1;
+        b.f_ptr = reinterpret_cast<uint64_t>(f); b.flag_ptr = reinterpret_cast<uint64_t>(flags);
+        return true;
+    }
+    template <class Blob>
+    bool open_peer(const Blob &b, float **f, int **flags, std::string &e) {
+        if (b.pid != int(getpid())) { e = "host emulation: peers must live in the same process"; return false; }
+        *f = reinterpret_cast<float *>(b.f_ptr); *flags = reinterpret_cast<int *>(b.flag_ptr);
+        return true;
+    }
+    void close_peers() {}
+    bool signal_flags(int *lo, int *hi, int value) {
+        if (lo) *lo = value;
+        if (hi) *hi = value;
+        return true;
+    }
+    bool wait_flags(const int *flags, bool lo, bool hi, int value) {
+        if ((lo && flags[0] < value) || (hi && flags[1] < value)) {
+            err = "host emulation: neighbour slab is behind (step the slabs in lock-step)";
+            return false;
+        }
+        return true;
+    }
+
+private:
+    std::chrono::steady_clock::time_point t0_;
+};
+
+}  // namespace fg

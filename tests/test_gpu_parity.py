@@ -1,0 +1,155 @@
+"""GPU parity: the CUDA library against the fp64 oracle through the C ABI (include/fishgym.h).
+
+Tolerances are BASELINE.json:5's: rel-L2 of velocity / density <= 1e-5 (fp32 vs fp64), per-link hydrodynamic force
+within 1e-4, marker->grid index maps bit-exact.
+"""
+import numpy as np
+import pytest
+
+import util
+
+pytestmark = pytest.mark.gpu
+
+TOL_FIELD = 1e-5
+TOL_FORCE = 1e-4
+
+
+def test_backend_is_cuda(g, cuda):
+    s = g.Sim(backend=cuda, nx=16, ny=16, nz=16)
+    assert s.backend_name == "cuda-sm100a"
+    s.step(2)
+    assert s.stats().kernel_launches >= 3
+    s.close()
+
+
+@pytest.mark.parametrize("name", list(util.parity_cases(__import__("gym_fish_b200")).keys()))
+def test_case_table(g, cuda, name):
+    kw = util.parity_cases(g)[name]
+    w = util.run_pair(g, "oracle", cuda, kw)
+    assert w["u"] <= TOL_FIELD and w["rho"] <= TOL_FIELD, (name, w)
+    assert w["f"] <= 2e-7, (name, w)
+
+
+@pytest.mark.parametrize("name", ["bgk_periodic", "mrt_inlet_outlet_ywalls"])
+def test_solid_obstacles(g, cuda, name):
+    kw = util.parity_cases(g)[name]
+    w = util.run_pair(g, "oracle", cuda, kw, solid=util.solid_block(kw))
+    assert w["u"] <= TOL_FIELD and w["rho"] <= TOL_FIELD, (name, w)
+
+
+@pytest.mark.parametrize("coll", ["bgk", "mrt"])
+def test_taylor_green_64_1000_steps(g, cuda, coll):
+    """BASELINE.json configs[0]: 64^3 Taylor-Green, N = 1000 steps (15 % amplitude left)."""
+    n = 64
+    kw = dict(nx=n, ny=n, nz=n, tau=0.8, collision=g.MRT if coll == "mrt" else g.BGK)
+    a, b = g.Sim(backend="oracle", **kw), g.Sim(backend=cuda, **kw)
+    rho, u = util.taylor_green(n, "xy")
+    for s in (a, b):
+        s.set_fields(rho, u)
+        s.step(1000)
+    ra, ua = a.get_fields(f64=True)
+    rb, ub = b.get_fields(f64=True)
+    assert util.rel_l2(ub, ua) <= TOL_FIELD
+    assert util.rel_l2(rb, ra) <= TOL_FIELD
+    # and the oracle itself decays at 2 nu k^2
+    nu, k = (0.8 - 0.5) / 3, 2 * np.pi / n
+    amp = np.sqrt((ua ** 2).mean()) / np.sqrt((u ** 2).mean())
+    assert abs(-np.log(amp) / 1000 / (2 * nu * k * k) - 1) < 5e-3
+
+
+def _ib_pair(g, cuda, kw, X, U, dV, link, origins, init_u, steps):
+    out = []
+    for backend in ("oracle", cuda):
+        s = g.Sim(backend=backend, **kw)
+        s.set_markers(X, U, dV, link)
+        s.set_link_origins(origins)
+        rho = np.ones(s.shape)
+        u = np.zeros((3,) + s.shape)
+        u[2] = init_u
+        s.set_fields(rho, u)
+        s.step(steps)
+        out.append(s)
+    return out
+
+
+def test_immersed_boundary_prescribed_markers(g, cuda):
+    P, Wl, IN, OUT = g.BC_PERIODIC, g.BC_WALL, g.BC_INLET, g.BC_OUTLET
+    kw = dict(nx=20, ny=18, nz=24, tau=0.8, collision=g.MRT, max_markers=4000, max_links=4,
+              bc=[P, P, Wl, Wl, IN, OUT], inlet_u=[0, 0, 0.05])
+    X = np.concatenate([util.sphere_markers((10.3, 9.1, 8.2), 4.0, 200), util.sphere_markers((1.0, 16.5, 20.0), 3.0, 120)])
+    U = np.zeros_like(X)
+    U[200:, 0] = 0.01
+    link = np.array([0] * 200 + [1] * 120, np.int32)
+    a, b = _ib_pair(g, cuda, kw, X, U, np.ones(len(X), np.float32), link, [[10.3, 9.1, 8.2], [1.0, 16.5, 20.0]], 0.05, 11)
+    ba, oa = a.get_index_map()
+    bb, ob = b.get_index_map()
+    assert np.array_equal(ba, bb) and np.array_equal(oa, ob)          # bit-exact
+    assert a.stats().band_cells == b.stats().band_cells
+    assert util.rel_l2(b.get_marker_forces(), a.get_marker_forces()) <= TOL_FORCE
+    wa, wb = a.get_link_wrenches(), b.get_link_wrenches()
+    assert np.abs(wb - wa).max() / np.abs(wa).max() <= TOL_FORCE
+    ra, ua = a.get_fields(f64=True)
+    rb, ub = b.get_fields(f64=True)
+    assert util.rel_l2(ub, ua) <= TOL_FIELD and util.rel_l2(rb, ra) <= TOL_FIELD
+    assert util.rel_l2(b.get_force_field(), a.get_force_field()) <= TOL_FORCE
+    a.close(); b.close()
+
+
+def test_swimming_fish_loop(g, cuda):
+    kw = dict(nx=20, ny=18, nz=40, tau=0.8, max_markers=4000, max_links=8)
+    a, b = g.Sim(backend="oracle", **kw), g.Sim(backend=cuda, **kw)
+    for s in (a, b):
+        s.add_fish(util.fish_desc(g))
+    assert a.stats().n_markers == b.stats().n_markers
+    for it in range(12):
+        act = np.sin(0.4 * it + np.arange(3))
+        for s in (a, b):
+            s.set_action(act)
+            s.step(10)
+        wa, wb = a.get_link_wrenches(), b.get_link_wrenches()
+        assert np.abs(wb - wa).max() / np.abs(wa).max() <= TOL_FORCE
+        assert np.abs(a.get_obs() - b.get_obs()).max() <= 1e-4
+    a.close(); b.close()
+
+
+def test_mass_and_momentum_conservation_full_size(g, cuda):
+    """Size-independent property at BASELINE.json configs[1] size (256x128x128, z = flow axis): a periodic box
+    conserves mass and momentum to fp32 round-off."""
+    kw = dict(nx=128, ny=128, nz=256, tau=0.6, collision=g.MRT)
+    s = g.Sim(backend=cuda, **kw)
+    rho, u = util.smooth_fields(s.shape, amp=0.03)
+    s.set_fields(rho, u)
+    r0, u0 = s.get_fields(f64=True)
+    m0, p0 = r0.sum(), (r0 * u0).sum(axis=(1, 2, 3))
+    s.step(101)
+    r1, u1 = s.get_fields(f64=True)
+    m1, p1 = r1.sum(), (r1 * u1).sum(axis=(1, 2, 3))
+    assert abs(m1 - m0) / m0 < 1e-9
+    assert np.abs(p1 - p0).max() / r0.size < 1e-9
+    assert np.isfinite(u1).all()
+    s.close()
+
+
+def test_two_slabs_on_one_gpu_equal_unsplit(g, cuda):
+    """z-slab halos with device peers: two handles in one process push halos into each other's lattice; the
+    populations must be bit-identical with the unsplit run (stream-collide is per-cell deterministic)."""
+    P = g.BC_PERIODIC
+    kw = dict(nx=16, ny=12, nz=16, tau=0.7, collision=g.MRT)
+    whole = g.Sim(backend=cuda, **kw)
+    parts = [g.Sim(backend=cuda, n_ranks=2, rank=r, **kw) for r in range(2)]
+    rho, u = util.smooth_fields(whole.shape)
+    whole.set_fields(rho, u)
+    for r, s in enumerate(parts):
+        s.set_fields(rho[8 * r:8 * r + 8], u[:, 8 * r:8 * r + 8])
+    h = [s.peer_export() for s in parts]
+    parts[0].peer_connect(h[1], h[1])
+    parts[1].peer_connect(h[0], h[0])
+    for it in range(7):
+        whole.step(1)
+        for s in parts:
+            s.step(1)
+    f = whole.get_populations()
+    fs = np.concatenate([s.get_populations() for s in parts], axis=1)
+    assert np.array_equal(f, fs)
+    for s in parts + [whole]:
+        s.close()
