@@ -91,6 +91,7 @@ struct StepParams {
     Collision C;
     ForceField F;
     int zz_begin, zz_end;  // storage planes [zz_begin, zz_end) this launch covers
+    int y0, ystride;       // rows this launch covers: y = y0 + blockIdx.y * ystride
 };
 
 // ---------------------------------------------------------------- collide (registers only)
@@ -347,18 +348,19 @@ FG_HD void store_departing(const float (&h)[Q], const Lattice &L, const Collisio
     }
 }
 
-FG_HD bool row_needs_checks(const Lattice &L, int y, int zz) {
-    const int zg = L.z0 + zz - 1;
-    return L.solid != nullptr || L.wall_x || (L.wall_y && (y == 0 || y == L.ny - 1)) ||
-           (L.bc_zlo == BC_WALL && zg == 0) || (L.bc_zhi == BC_WALL && zg == L.nzg - 1);
-}
-
 // ---------------------------------------------------------------- kernel bodies
-// grid: (ceil(nx/threads), ny, planes); one thread per cell, x fastest => coalesced 128 B per warp per slot
-template <int PARITY, bool MRT>
+// grid: (ceil(nx/threads), rows, planes); one thread per cell, x fastest => coalesced 128 B per warp per slot.
+// MODE is decided by the HOST per launch (sim.hpp launch_collide partitions the slab), so the bulk kernel carries no
+// boundary code and fits 64 registers (8 CTAs of 128 threads per SM):
+//   CHECK_NONE  no link can be blocked in the rows / planes of this launch
+//   CHECK_XEDGE only the two cells at the ends of each row can (x walls): those threads take the checked path
+//   CHECK_ALL   wall rows (y walls), wall planes (z walls), or obstacles anywhere
+enum : int { CHECK_NONE = 0, CHECK_ALL = 1, CHECK_XEDGE = 2 };
+
+template <int PARITY, bool MRT, int MODE>
 struct StreamCollide {
     static constexpr int kThreads = 128;
-    static constexpr int kMinBlocks = 4;
+    static constexpr int kMinBlocks = 8;
     template <bool CHECK>
     FG_HD static void cell(const StepParams &p, int x, int y, int zz) {
         const Lattice &L = p.L;
@@ -380,10 +382,10 @@ struct StreamCollide {
         store_departing<PARITY, CHECK>(h, L, p.C, nb, idx);
     }
     FG_HD static void run(const StepParams &p, int bx, int by, int bz, int tx) {
-        const int x = bx * kThreads + tx, y = by, zz = p.zz_begin + bz;
+        const int x = bx * kThreads + tx, y = p.y0 + by * p.ystride, zz = p.zz_begin + bz;
         if (x >= p.L.nx) return;
-        if (PARITY == 1 && row_needs_checks(p.L, y, zz)) cell<true>(p, x, y, zz);
-        else if (PARITY == 0 && p.L.solid) cell<true>(p, x, y, zz);
+        if (MODE == CHECK_ALL) cell<true>(p, x, y, zz);
+        else if (MODE == CHECK_XEDGE && PARITY == 1 && (x == 0 || x == p.L.nx - 1)) cell<true>(p, x, y, zz);
         else cell<false>(p, x, y, zz);
     }
 };
@@ -531,6 +533,13 @@ struct ZFaceOp {
         } else {
             // the next (even) step reads them from natural slot i of the boundary plane
             if (link_from_wall(L, i, x, y)) return;
+            if (op.mode == BC_OUTLET && L.solid) {
+                // the clamped pull source (x-cx, y-cy) of the same plane is an obstacle: bounce-back owns the slot
+                int sx = x - cxr(i), sy = y - cyr(i);
+                sx = sx < 0 ? sx + L.nx : (sx >= L.nx ? sx - L.nx : sx);
+                sy = sy < 0 ? sy + L.ny : (sy >= L.ny ? sy - L.ny : sy);
+                if (L.solid[((long long)(hi ? L.nz : 1) * L.ny + sy) * L.nx + sx]) return;
+            }
             float *cell = L.f + i * L.slot + (long long)(hi ? L.nz : 1) * L.plane + c;
             if (op.mode == BC_INLET) *cell = p.C.heq_in[i];
             else *cell = L.f[i * L.slot + (long long)(hi ? L.nz - 1 : 2) * L.plane + c];   // outlet: what the plane inside received

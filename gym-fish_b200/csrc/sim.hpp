@@ -174,7 +174,12 @@ public:
         bool any = false;
         for (int zl = -1; zl <= L_.nz; ++zl) {
             int zg = L_.z0 + zl;
-            if (zg < 0 || zg >= L_.nzg) { if (!pz) continue; zg = (zg + L_.nzg) % L_.nzg; }
+            if (zg < 0 || zg >= L_.nzg) {
+                const int bc = zg < 0 ? cfg.bc[FG_ZLO] : cfg.bc[FG_ZHI];
+                if (pz) zg = (zg + L_.nzg) % L_.nzg;
+                else if (bc == FG_BC_OUTLET) zg = zg < 0 ? 0 : L_.nzg - 1;   // zero-gradient: the pull source is clamped (oracle pull())
+                else continue;
+            }
             for (int p = 0; p < L_.plane; ++p) {
                 const uint8_t v = g[size_t(zg) * L_.plane + p] ? 1 : 0;
                 h[size_t(zl + 1) * L_.plane + p] = v;
@@ -292,13 +297,11 @@ public:
                 if (prof) dev.mark(0);
                 if (!launch_collide(2, L_.nz, F)) return cuda_fail();
                 if (prof) dev.mark(0);
-                collide_launches_ += 3;
             } else {
                 if (prof) dev.mark(0);
                 if (!launch_collide(1, L_.nz + 1, F)) return cuda_fail();
                 if (prof) dev.mark(0);
                 if (!launch_faces()) return cuda_fail();
-                collide_launches_ += 1;
             }
             if (ib_.ready() && ib_.n_markers() > 0) {
                 if (int rc = ib_.after_collide(dev, err)) return rc;
@@ -448,16 +451,46 @@ private:
         }
     }
 
-    template <int PARITY>
-    bool launch_collide_p(const StepParams &p, Dim3 g) {
-        return cfg.collision == FG_MRT ? dev.template launch<StreamCollide<PARITY, true>>(g, p)
-                                       : dev.template launch<StreamCollide<PARITY, false>>(g, p);
+    template <int PARITY, int MODE>
+    bool launch_collide_pm(const StepParams &p, Dim3 g) {
+        return cfg.collision == FG_MRT ? dev.template launch<StreamCollide<PARITY, true, MODE>>(g, p)
+                                       : dev.template launch<StreamCollide<PARITY, false, MODE>>(g, p);
     }
+    bool launch_rows(int mode, int zb, int ze, int y0, int ystride, int rows, const ForceField &F) {
+        if (ze <= zb || rows <= 0) return true;
+        StepParams p{L_, C_, F, zb, ze, y0, ystride};
+        const Dim3 g{(L_.nx + 127) / 128, rows, ze - zb};
+        ++collide_launches_;
+        if (parity_ == 0) {
+            // the even step is purely local: only obstacles need the checked variant
+            return mode == CHECK_ALL && L_.solid ? launch_collide_pm<0, CHECK_ALL>(p, g) : launch_collide_pm<0, CHECK_NONE>(p, g);
+        }
+        switch (mode) {
+            case CHECK_ALL: return launch_collide_pm<1, CHECK_ALL>(p, g);
+            case CHECK_XEDGE: return launch_collide_pm<1, CHECK_XEDGE>(p, g);
+            default: return launch_collide_pm<1, CHECK_NONE>(p, g);
+        }
+    }
+    // Partition planes [zz_begin, zz_end) so that boundary code only runs where a link can be blocked.
     bool launch_collide(int zz_begin, int zz_end, const ForceField &F) {
         if (zz_end <= zz_begin) return true;
-        StepParams p{L_, C_, F, zz_begin, zz_end};
-        const Dim3 g = grid_planes(zz_end - zz_begin);
-        return parity_ == 0 ? launch_collide_p<0>(p, g) : launch_collide_p<1>(p, g);
+        const int ny = L_.ny;
+        if (L_.solid || parity_ == 0) return launch_rows(CHECK_ALL, zz_begin, zz_end, 0, 1, ny, F);
+        const bool zlo_wall = L_.bc_zlo == BC_WALL && L_.z0 == 0, zhi_wall = L_.bc_zhi == BC_WALL && L_.z0 + L_.nz == L_.nzg;
+        int zb = zz_begin, ze = zz_end;
+        bool ok = true;
+        if (zlo_wall && zb <= 1 && 1 < ze) { ok = ok && launch_rows(CHECK_ALL, 1, 2, 0, 1, ny, F); zb = 2; }
+        if (zhi_wall && zb <= L_.nz && L_.nz < ze) { ok = ok && launch_rows(CHECK_ALL, L_.nz, L_.nz + 1, 0, 1, ny, F); ze = L_.nz; }
+        const int bulk = L_.wall_x ? CHECK_XEDGE : CHECK_NONE;
+        if (L_.wall_y && ny >= 2) {
+            ok = ok && launch_rows(bulk, zb, ze, 1, 1, ny - 2, F);
+            ok = ok && launch_rows(CHECK_ALL, zb, ze, 0, ny - 1, 2, F);
+        } else if (L_.wall_y) {
+            ok = ok && launch_rows(CHECK_ALL, zb, ze, 0, 1, ny, F);
+        } else {
+            ok = ok && launch_rows(bulk, zb, ze, 0, 1, ny, F);
+        }
+        return ok;
     }
 
     // z-face plane ops after the step of parity `parity_`: one launch covers both faces

@@ -1,0 +1,152 @@
+"""Gym-style environment over the C ABI: reset() / step(action) -> obs, reward, terminated, truncated, info.
+
+/root/reference/README.md:1-3,14 promise a Gym-like Python interface to a coupled agent-fluid simulation and ship
+nothing else; BASELINE.json:5 fixes the surface.  numpy only — neither gym nor gymnasium is
+required (duck-typed API with a minimal Box), and no torch on the sim path.
+
+One env step = `n_substeps` coupled lattice steps inside ONE fg_step call: the action goes down (a few floats), the
+library integrates the articulated body on the host every substep, and the observation comes back (a few floats).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _abi
+from ._abi import FgFishDesc, Sim
+
+
+class Box:
+    """Minimal stand-in for gym.spaces.Box."""
+
+    def __init__(self, low, high, shape, dtype=np.float32, seed: Optional[int] = None):
+        self.low = np.full(shape, low, dtype=dtype)
+        self.high = np.full(shape, high, dtype=dtype)
+        self.shape = tuple(shape)
+        self.dtype = np.dtype(dtype)
+        self._rng = np.random.default_rng(seed)
+
+    def seed(self, seed: Optional[int]):
+        self._rng = np.random.default_rng(seed)
+
+    def sample(self) -> np.ndarray:
+        return self._rng.uniform(self.low, self.high).astype(self.dtype)
+
+    def contains(self, x) -> bool:
+        x = np.asarray(x)
+        return x.shape == self.shape and bool(np.all(x >= self.low) and np.all(x <= self.high))
+
+
+@dataclass
+class FishSpec:
+    """A 5-link / 4-joint swimmer (BASELINE.json configs[2]: ~2k markers at one marker per unit area)."""
+    links: Sequence[Tuple[float, float]] = ((28, 7), (24, 7), (22, 6), (20, 5), (18, 3.5))   # (length, radius)
+    root: Optional[Tuple[float, float, float]] = None     # head-link centre; default: tank centre, 1/3 along z
+    heading: float = 0.0
+    density_ratio: float = 1.0
+    joint_gain: float = 0.2
+    joint_limit: float = 0.5
+    joint_rate_max: float = 0.01
+    free_root: bool = True
+
+    def desc(self, grid) -> FgFishDesc:
+        nx, ny, nz = grid
+        d = FgFishDesc()
+        d.n_links = len(self.links)
+        for k, (length, rad) in enumerate(self.links):
+            d.link_len[k], d.link_rad[k] = float(length), float(rad)
+        root = self.root if self.root is not None else (nx / 2, ny / 2, nz / 3)
+        for i in range(3):
+            d.root_pos[i] = float(root[i])
+        d.heading, d.density_ratio = float(self.heading), float(self.density_ratio)
+        d.joint_gain, d.joint_limit, d.joint_rate_max = float(self.joint_gain), float(self.joint_limit), float(self.joint_rate_max)
+        d.free_root = int(self.free_root)
+        return d
+
+
+@dataclass
+class EnvConfig:
+    grid: Tuple[int, int, int] = (256, 256, 512)          # (nx, ny, nz); z is the swim axis
+    tau: float = 0.53
+    collision: int = _abi.MRT
+    n_substeps: int = 20
+    max_episode_steps: int = 500
+    fish: Sequence[FishSpec] = field(default_factory=lambda: (FishSpec(),))
+    walls: bool = True                                    # tank walls on x, y; periodic along z
+    energy_weight: float = 0.01
+    device: int = 0
+
+
+class FishEnv:
+    """Cruise task: swim along the initial heading; reward = progress (body lengths) - energy_weight * |a|^2."""
+
+    metadata = {"render_modes": []}
+
+    def __init__(self, config: Optional[EnvConfig] = None, backend: str = "cuda"):
+        self.cfg = config or EnvConfig()
+        nx, ny, nz = self.cfg.grid
+        W, P = _abi.BC_WALL, _abi.BC_PERIODIC
+        bc = [W, W, W, W, P, P] if self.cfg.walls else [P] * 6
+        descs = [f.desc(self.cfg.grid) for f in self.cfg.fish]
+        # one marker per unit area: capacity from the spheroid areas (+25 %)
+        cap = 0
+        for f in self.cfg.fish:
+            for length, rad in f.links:
+                a, r, p = length / 2, rad, 1.6075
+                cap += int(1.25 * 4 * np.pi * (((r * r) ** p + 2 * (r * a) ** p) / 3) ** (1 / p)) + 16
+        self.sim = Sim(backend=backend, nx=nx, ny=ny, nz=nz, tau=self.cfg.tau, collision=self.cfg.collision, bc=bc,
+                       max_markers=cap, max_links=sum(len(f.links) for f in self.cfg.fish), device=self.cfg.device)
+        for d in descs:
+            self.sim.add_fish(d)
+        self._n_act, self._n_obs = self.sim.action_size(), self.sim.obs_size()
+        self.action_space = Box(-1.0, 1.0, (self._n_act,))
+        self.observation_space = Box(-np.inf, np.inf, (self._n_obs,))
+        self._body_len = [sum(length for length, _ in f.links) for f in self.cfg.fish]
+        self._obs_stride = [8 + 2 * (len(f.links) - 1) for f in self.cfg.fish]
+        self._t = 0
+        self._last = None
+
+    # ---- Gym API
+    def reset(self, *, seed: Optional[int] = None, options=None):
+        if seed is not None:
+            self.action_space.seed(seed)
+        self.sim.reset(0 if seed is None else int(seed))
+        self._t = 0
+        obs = self.sim.get_obs()
+        self._last = obs.copy()
+        return obs, {"n_markers": self.sim.stats().n_markers}
+
+    def step(self, action):
+        a = np.clip(np.asarray(action, dtype=np.float32).reshape(self._n_act), -1.0, 1.0)
+        self.sim.set_action(a)
+        self.sim.step(self.cfg.n_substeps)
+        obs = self.sim.get_obs()
+        reward, terminated = self._reward(obs, a)
+        self._last = obs.copy()
+        self._t += 1
+        truncated = self._t >= self.cfg.max_episode_steps
+        st = self.sim.stats()
+        info = {"mlups": st.last_mlups, "step_ms": st.last_step_ms, "diverged": bool(not np.isfinite(obs).all())}
+        return obs, float(reward), bool(terminated or info["diverged"]), bool(truncated), info
+
+    def close(self):
+        self.sim.close()
+
+    # ---- task
+    def _reward(self, obs, a):
+        nx, ny, nz = self.cfg.grid
+        reward, off, terminated = 0.0, 0, False
+        for f, length, stride in zip(self.cfg.fish, self._body_len, self._obs_stride):
+            o, p = obs[off:off + stride], self._last[off:off + stride]
+            dx, dz = float(o[0] - p[0]), float(o[2] - p[2])
+            if not self.cfg.walls or True:
+                dz = (dz + nz / 2) % nz - nz / 2          # z is periodic
+            # progress along the nose direction of the initial heading: nose = -(sin h, cos h)
+            reward += -(np.sin(f.heading) * dx + np.cos(f.heading) * dz) / length
+            if self.cfg.walls and not (0.1 * nx < o[0] < 0.9 * nx):
+                terminated = True
+            off += stride
+        reward -= self.cfg.energy_weight * float(np.mean(a * a))
+        return reward, terminated

@@ -1,0 +1,160 @@
+"""z-slab decomposition: the N>1 path on CPU.
+
+ * oracle, host-staged halos, N in-process slabs == unsplit run, bit-identical (fp64 messages)
+ * emulated CUDA runtime, host-staged halos and device-peer pushes == unsplit run, bit-identical
+ * world_size-2 `gloo` processes exchanging the halo messages with torch.distributed (the plumbing bench.py uses)
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import util
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def exchange_in_process(g, parts, periodic):
+    A = g._abi
+    n = len(parts)
+    msgs = {}
+    for r, s in enumerate(parts):
+        if r < n - 1 or periodic:
+            msgs[(r, "up")] = s.halo_pack(A.ZHI)
+        if r > 0 or periodic:
+            msgs[(r, "down")] = s.halo_pack(A.ZLO)
+    for r, s in enumerate(parts):
+        if r > 0 or periodic:
+            s.halo_unpack(A.ZLO, msgs[((r - 1) % n, "up")])
+        if r < n - 1 or periodic:
+            s.halo_unpack(A.ZHI, msgs[((r + 1) % n, "down")])
+
+
+def split_case(g, name):
+    P, Wl, IN, OUT = g.BC_PERIODIC, g.BC_WALL, g.BC_INLET, g.BC_OUTLET
+    return {
+        "periodic_mrt": dict(nx=10, ny=8, nz=12, tau=0.7, collision=g.MRT, body_force=[1e-4, 0, 2e-4]),
+        "inlet_outlet_walls": dict(nx=10, ny=8, nz=12, tau=0.8, collision=g.MRT, bc=[Wl, Wl, P, P, IN, OUT], inlet_u=[0, 0.01, 0.04]),
+        "zwalls_bgk": dict(nx=10, ny=8, nz=12, tau=0.8, bc=[P, P, Wl, Wl, Wl, Wl], wall_u={g._abi.ZLO: [0.02, 0, 0]}),
+    }[name]
+
+
+@pytest.mark.parametrize("backend_name", ["oracle", "emu"])
+@pytest.mark.parametrize("case", ["periodic_mrt", "inlet_outlet_walls", "zwalls_bgk"])
+@pytest.mark.parametrize("n_ranks", [2, 3])
+def test_host_staged_slabs_equal_unsplit(g, emu, backend_name, case, n_ranks):
+    backend = emu if backend_name == "emu" else "oracle"
+    kw = split_case(g, case)
+    periodic = kw.get("bc", [0] * 6)[4] == g.BC_PERIODIC
+    whole = g.Sim(backend=backend, **kw)
+    parts = [g.Sim(backend=backend, n_ranks=n_ranks, rank=r, **kw) for r in range(n_ranks)]
+    rho, u = util.smooth_fields(whole.shape)
+    solid = np.zeros(whole.shape, np.uint8)
+    solid[3:5, 2:4, 3:6] = 1          # straddles the slab face at z=4 (3 ranks) and sits next to z=6 (2 ranks)
+    whole.set_solid(solid)
+    whole.set_fields(rho, u)
+    h = whole.nz // n_ranks
+    for r, s in enumerate(parts):
+        s.set_solid(solid)
+        s.set_fields(rho[r * h:(r + 1) * h], u[:, r * h:(r + 1) * h])
+    for it in range(7):
+        whole.step(1)
+        for s in parts:
+            s.step(1)
+        exchange_in_process(g, parts, periodic)
+    f = whole.get_populations()
+    fs = np.concatenate([s.get_populations() for s in parts], axis=1)
+    keep = solid == 0
+    assert np.array_equal(f * keep, fs * keep)
+    with pytest.raises(g.FgError):       # stepping again without having exchanged is a state error
+        parts[0].step(1)
+        parts[0].step(1)
+
+
+@pytest.mark.parametrize("case", ["periodic_mrt", "inlet_outlet_walls"])
+@pytest.mark.parametrize("overlap", [True, False])
+def test_device_peer_pushes_equal_unsplit(g, emu, case, overlap):
+    """The product's multi-GPU path (halo pushes into the neighbour's lattice + step flags), here with both slabs in
+    one process on the emulated device; boundary-first ordering (overlap) must not change a bit."""
+    kw = split_case(g, case)
+    kw["nz"] = 16
+    periodic = kw.get("bc", [0] * 6)[4] == g.BC_PERIODIC
+    whole = g.Sim(backend=emu, **kw)
+    flags = 0 if overlap else g._abi.FLAG_NO_OVERLAP
+    parts = [g.Sim(backend=emu, n_ranks=2, rank=r, flags=flags, **kw) for r in range(2)]
+    rho, u = util.smooth_fields(whole.shape)
+    whole.set_fields(rho, u)
+    for r, s in enumerate(parts):
+        s.set_fields(rho[8 * r:8 * r + 8], u[:, 8 * r:8 * r + 8])
+    h = [s.peer_export() for s in parts]
+    parts[0].peer_connect(h[1] if periodic else None, h[1])
+    parts[1].peer_connect(h[0], h[0] if periodic else None)
+    for it in range(9):
+        whole.step(1)
+        for s in parts:
+            s.step(1)
+    assert np.array_equal(whole.get_populations(), np.concatenate([s.get_populations() for s in parts], axis=1))
+    with pytest.raises(g.FgError):       # a slab that runs ahead of its neighbour is caught, not silently wrong
+        parts[0].step(1)
+        parts[0].step(1)
+
+
+def test_markers_inside_one_slab_and_across_a_face(g, emu):
+    kw = dict(nx=12, ny=12, nz=24, tau=0.8, max_markers=256, max_links=1)
+    s = g.Sim(backend=emu, n_ranks=2, rank=0, **kw)
+    X = util.sphere_markers((6, 6, 5.5), 2.0, 40)
+    s.set_markers(X, np.zeros_like(X), np.ones(40, np.float32))          # stencils inside planes 0..11
+    with pytest.raises(g.FgError) as e:
+        s.set_markers(X + np.array([0, 0, 5], np.float32), np.zeros_like(X), np.ones(40, np.float32))
+    assert e.value.code == g._abi.FG_ENOTSUP
+
+
+WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
+import numpy as np, torch, torch.distributed as dist
+import gym_fish_b200 as g, util
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+backend = {backend!r}
+kw = dict(nx=10, ny=8, nz=12, tau=0.7, collision=g.MRT, body_force=[1e-4, 0, 2e-4])
+s = g.Sim(backend=backend, n_ranks=world, rank=rank, **kw)
+h = kw["nz"] // world
+rho, u = util.smooth_fields((kw["nz"], kw["ny"], kw["nx"]))
+s.set_fields(rho[rank*h:(rank+1)*h], u[:, rank*h:(rank+1)*h])
+A = g._abi
+up, down = (rank + 1) % world, (rank - 1) % world
+for it in range(7):
+    s.step(1)
+    out_hi, out_lo = torch.from_numpy(s.halo_pack(A.ZHI)), torch.from_numpy(s.halo_pack(A.ZLO))
+    in_lo, in_hi = torch.empty_like(out_hi), torch.empty_like(out_lo)
+    reqs = [dist.isend(out_hi, up, tag=1), dist.isend(out_lo, down, tag=2), dist.irecv(in_lo, down, tag=1), dist.irecv(in_hi, up, tag=2)]
+    for r in reqs: r.wait()
+    s.halo_unpack(A.ZLO, in_lo.numpy()); s.halo_unpack(A.ZHI, in_hi.numpy())
+f = torch.from_numpy(s.get_populations())
+parts = [torch.empty_like(f) for _ in range(world)]
+dist.all_gather(parts, f)
+if rank == 0:
+    np.save({out!r}, torch.cat(parts, dim=1).numpy())
+dist.barrier(); dist.destroy_process_group()
+"""
+
+
+@pytest.mark.parametrize("backend_name", ["oracle", "emu"])
+def test_gloo_world_size_2(g, emu, backend_name, tmp_path):
+    backend = emu if backend_name == "emu" else "oracle"
+    out = str(tmp_path / "f.npy")
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT, tests=os.path.join(ROOT, "tests"), backend=backend, out=out))
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                    "--master-port", str(29500 + os.getpid() % 2000), str(script)], check=True, env=env, timeout=300,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+    kw = dict(nx=10, ny=8, nz=12, tau=0.7, collision=g.MRT, body_force=[1e-4, 0, 2e-4])
+    whole = g.Sim(backend=backend, **kw)
+    rho, u = util.smooth_fields(whole.shape)
+    whole.set_fields(rho, u)
+    whole.step(7)
+    assert np.array_equal(whole.get_populations(), np.load(out))
