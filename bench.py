@@ -39,6 +39,8 @@ WORKLOADS = {
                                desc="D3Q19 MRT flow past fixed IB sphere, 256x128x128 (z flow axis) per GPU"),
     "box_512": dict(nx=512, ny=512, nz=512, D=0.0, U=0.02, Re=0.0,
                     desc="D3Q19 MRT periodic box 512^3 per GPU (weak-scaling sweep, BASELINE.json configs[4])"),
+    "box_512_ib": dict(nx=512, ny=512, nz=512, D=22.2, U=0.02, Re=0.0,
+                       desc="D3Q19 MRT periodic box 512^3 per GPU with ~1e5 IB markers on 64 spheres (IB overhead, configs[4])"),
     "tank_512x256x256": dict(nx=256, ny=256, nz=512, D=0.0, U=0.0, Re=0.0,
                              desc="D3Q19 MRT tank 512x256x256 (z swim axis) with one 5-link fish, Gym substeps"),
 }
@@ -71,6 +73,16 @@ def make_sim(g, backend, wl, rank, world, device, flags=0, nz_override=None):
                    np.array([[w["nx"] / 2 + 0.21, w["ny"] / 2 + 0.13, zc]]))
     elif wl == "box_512":
         kw.update(tau=0.6)
+    elif wl == "box_512_ib":
+        kw.update(tau=0.6, max_markers=110000, max_links=64)
+        R = w["D"] / 2
+        n1 = int(round(4 * np.pi * R * R))
+        Xs, links, origins = [], [], []
+        for s_ in range(64):
+            c = (64.3 + 128 * (s_ % 4), 64.1 + 128 * ((s_ // 4) % 4), rank * nzl + 64.2 + 128 * (s_ // 16))
+            Xs.append(sphere_markers(c, R, n1)); links.append(np.full(n1, s_, np.int32)); origins.append(c)
+        X = np.concatenate(Xs)
+        markers = (X, np.zeros_like(X), np.full(len(X), 4 * np.pi * R * R / n1, np.float32), np.concatenate(links), np.array(origins))
     else:
         kw.update(tau=0.6, bc=[g.BC_WALL] * 4 + [g.BC_PERIODIC] * 2, max_markers=8192, max_links=8)
     sim = g.Sim(backend=backend, **kw)
@@ -250,7 +262,7 @@ def main():
     if world > 1:
         handles = [None] * world
         dist.all_gather_object(handles, sim.peer_export())
-        per = wl == "box_512" or wl == "tank_512x256x256"
+        per = wl in ("box_512", "box_512_ib", "tank_512x256x256")
         lo = handles[(rank - 1) % world] if (rank > 0 or per) else None
         hi = handles[(rank + 1) % world] if (rank < world - 1 or per) else None
         sim.peer_connect(lo, hi)

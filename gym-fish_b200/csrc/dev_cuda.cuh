@@ -78,6 +78,7 @@ public:
         if (ev1_) cudaEventDestroy(ev1_);
         ev0_ = ev1_ = nullptr;
         for (auto &pool : marks_) { for (auto e : pool) cudaEventDestroy(e); pool.clear(); }
+        for (auto &e : named_) { if (e) cudaEventDestroy(e); e = nullptr; }
     }
 
     void *alloc(size_t bytes, std::string &e) {
@@ -111,6 +112,41 @@ public:
     bool sync() {
         cudaSetDevice(device_);
         return ck(cudaStreamSynchronize(stream_), "stream sync");
+    }
+    // pinned host memory + asynchronous copies on the handle's stream + a few named events (IbState)
+    void *alloc_host(size_t bytes, std::string &e) {
+        cudaSetDevice(device_);
+        void *p = nullptr;
+        cudaError_t rc = cudaMallocHost(&p, bytes ? bytes : 4);
+        if (rc != cudaSuccess) {
+            e = std::string("cudaMallocHost(") + std::to_string(bytes) + "): " + cudaGetErrorString(rc);
+            cudaGetLastError();
+            return nullptr;
+        }
+        return p;
+    }
+    void free_host(void *p) {
+        if (!p) return;
+        cudaSetDevice(device_);
+        cudaFreeHost(p);
+    }
+    bool h2d_async(void *d, const void *pinned, size_t n) {
+        cudaSetDevice(device_);
+        return ck(cudaMemcpyAsync(d, pinned, n, cudaMemcpyHostToDevice, stream_), "H2D async");
+    }
+    bool d2h_async(void *pinned, const void *s, size_t n) {
+        cudaSetDevice(device_);
+        return ck(cudaMemcpyAsync(pinned, s, n, cudaMemcpyDeviceToHost, stream_), "D2H async");
+    }
+    bool ev_record(int id) {
+        cudaSetDevice(device_);
+        if (id < 0 || id >= kNamedEvents) return false;
+        if (!named_[id] && !ck(cudaEventCreateWithFlags(&named_[id], cudaEventDisableTiming), "cudaEventCreate")) return false;
+        return ck(cudaEventRecord(named_[id], stream_), "cudaEventRecord");
+    }
+    bool ev_sync(int id) {
+        if (id < 0 || id >= kNamedEvents || !named_[id]) return true;
+        return ck(cudaEventSynchronize(named_[id]), "cudaEventSynchronize");
     }
     void tic() {
         cudaSetDevice(device_);
@@ -234,6 +270,8 @@ private:
     cudaStream_t stream_ = nullptr;
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
     std::vector<std::pair<std::string, void *>> opened_;
+    static constexpr int kNamedEvents = 4;
+    cudaEvent_t named_[kNamedEvents] = {nullptr, nullptr, nullptr, nullptr};
     static constexpr int kMaxMarks = 8192;
     std::vector<cudaEvent_t> marks_[2];
     int nmarks_[2] = {0, 0};

@@ -14,6 +14,7 @@
 #include "lbm_core.cuh"
 
 #include <cmath>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -77,7 +78,8 @@ struct IbParams {
     int *band_cell;              // [cap]
     float *band_u;               // [3][cap]
     float *bandF;                // [3][cap]
-    int *band_count;             // [1]
+    int *band_count;             // this step's band size (device counter)
+    int *band_count_next;        // the other counter: previous step's size until IbClearBand ran, then zeroed for the next
     int band_cap;
     uint8_t *rowflag;            // [(nz+2)*ny]
     const float *origin;         // [links][3] torque reference points
@@ -99,35 +101,70 @@ FG_HD long long stencil_cell(const IbParams &p, int i0, int j0, int k0, int a, i
     return ((long long)(zl + 1) * L.ny + y) * L.nx + x;
 }
 
+// Thread mapping of the marker kernels: one thread per stencil node, 64 consecutive threads per marker
+// (a = x offset fastest, so a warp touches runs of 4 consecutive cells), 2 markers per 128-thread CTA.
+constexpr int kNodes = 64;
+constexpr int kMarkersPerCta = 2;
+
+// sum over the 32 lanes of a warp, result valid in lane 0 (device); identity in the host emulation, where every
+// "thread" then adds its own partial atomically — same sum, different association
+FG_HD float warp_sum(float v) {
+#if defined(__CUDA_ARCH__)
+    v += __shfl_down_sync(0xffffffffu, v, 16);
+    v += __shfl_down_sync(0xffffffffu, v, 8);
+    v += __shfl_down_sync(0xffffffffu, v, 4);
+    v += __shfl_down_sync(0xffffffffu, v, 2);
+    v += __shfl_down_sync(0xffffffffu, v, 1);
+#endif
+    return v;
+}
+FG_HD double warp_sum(double v) {
+#if defined(__CUDA_ARCH__)
+    v += __shfl_down_sync(0xffffffffu, v, 16);
+    v += __shfl_down_sync(0xffffffffu, v, 8);
+    v += __shfl_down_sync(0xffffffffu, v, 4);
+    v += __shfl_down_sync(0xffffffffu, v, 2);
+    v += __shfl_down_sync(0xffffffffu, v, 1);
+#endif
+    return v;
+}
+FG_HD bool reduction_leader(int tx) {
+#if defined(__CUDA_ARCH__)
+    return (tx & 31) == 0;
+#else
+    (void)tx;
+    return true;
+#endif
+}
+
 // (a3) marker -> grid index map (integer outputs bit-exact with the oracle) + band registration
 struct IbIndexMark {
-    static constexpr int kThreads = 128;
-    static constexpr int kMinBlocks = 4;
+    static constexpr int kThreads = kNodes * kMarkersPerCta;
+    static constexpr int kMinBlocks = 8;
     FG_HD static void run(const IbParams &p, int bx, int, int, int tx) {
-        const int k = bx * kThreads + tx;
+        const int k = bx * kMarkersPerCta + tx / kNodes, node = tx % kNodes;
         if (k >= p.n) return;
         const Lattice &L = p.L;
         const float X = p.X[3 * k], Y = p.X[3 * k + 1], Z = p.X[3 * k + 2];
         const int i0 = int(floorf(X)) - 1, j0 = int(floorf(Y)) - 1, k0 = int(floorf(Z)) - 1;
-        p.base[3 * k] = i0; p.base[3 * k + 1] = j0; p.base[3 * k + 2] = k0;
-        int kc = wrap_or_skip(k0 + 1, L.nzg, p.per_z != 0);
-        if (kc < 0) kc = k0 + 1 < 0 ? 0 : L.nzg - 1;
-        p.owner[k] = kc / L.nz;
-        for (int c = 0; c < 4; ++c)
-            for (int b = 0; b < 4; ++b)
-                for (int a = 0; a < 4; ++a) {
-                    const long long cell = stencil_cell(p, i0, j0, k0, a, b, c);
-                    if (cell < 0) continue;
-                    if (p.cellslot[cell] != 0) continue;
-                    if (atomic_cas_i(&p.cellslot[cell], 0, -1) == 0) {
-                        const int pos = atomic_add_i(p.band_count, 1);
-                        if (pos < p.band_cap) {
-                            p.band_cell[pos] = int(cell);
-                            p.cellslot[cell] = pos + 1;
-                            p.rowflag[cell / L.nx] = 1;
-                        }
-                    }
-                }
+        if (node == 0) {
+            p.base[3 * k] = i0; p.base[3 * k + 1] = j0; p.base[3 * k + 2] = k0;
+            int kc = wrap_or_skip(k0 + 1, L.nzg, p.per_z != 0);
+            if (kc < 0) kc = k0 + 1 < 0 ? 0 : L.nzg - 1;
+            p.owner[k] = kc / L.nz;
+        }
+        if (node < 3) p.Ustar[3 * k + node] = 0.0f;          // accumulated by IbInterpolate
+        const long long cell = stencil_cell(p, i0, j0, k0, node & 3, (node >> 2) & 3, node >> 4);
+        if (cell < 0) return;
+        if (p.cellslot[cell] != 0) return;
+        if (atomic_cas_i(&p.cellslot[cell], 0, -1) == 0) {
+            const int pos = atomic_add_i(p.band_count, 1);
+            if (pos < p.band_cap) {
+                p.band_cell[pos] = int(cell);
+                p.cellslot[cell] = pos + 1;
+                p.rowflag[cell / L.nx] = 1;
+            }
+        }
     }
 };
 
@@ -138,6 +175,7 @@ struct IbBandMoments {
     static constexpr int kMinBlocks = 4;
     FG_HD static void run(const IbParams &p, int bx, int, int, int tx) {
         const int pos = bx * kThreads + tx;
+        if (pos == 0) *p.band_count_next = 0;                 // the other counter is free again (IbClearBand has run)
         const int cnt = *p.band_count < p.band_cap ? *p.band_count : p.band_cap;
         if (pos >= cnt) return;
         const Lattice &L = p.L;
@@ -161,61 +199,91 @@ struct IbBandMoments {
     }
 };
 
-// (a5-a7) interpolate U*, direct forcing, spread.  One thread per marker in this first version.
-struct IbInterpSpread {
+FG_HD float node_weight(const IbParams &p, int k, int node, long long &cell, int &slot) {
+    const float X = p.X[3 * k], Y = p.X[3 * k + 1], Z = p.X[3 * k + 2];
+    const int i0 = p.base[3 * k], j0 = p.base[3 * k + 1], k0 = p.base[3 * k + 2];
+    const int a = node & 3, b = (node >> 2) & 3, c = node >> 4;
+    cell = stencil_cell(p, i0, j0, k0, a, b, c);
+    slot = cell >= 0 ? p.cellslot[cell] - 1 : -1;
+    return peskin4(X - float(i0 + a)) * peskin4(Y - float(j0 + b)) * peskin4(Z - float(k0 + c));
+}
+
+// (a5) U*_k = sum over the 64 nodes of w u*: warp-reduced, 2 x 3 atomics per marker
+struct IbInterpolate {
+    static constexpr int kThreads = kNodes * kMarkersPerCta;
+    static constexpr int kMinBlocks = 8;
+    FG_HD static void run(const IbParams &p, int bx, int, int, int tx) {
+        const int gt = bx * kThreads + tx;
+        if (gt < 6 * p.n_links) p.wrench[gt] = 0.0;           // accumulated by IbLinkReduce
+        const int k = bx * kMarkersPerCta + tx / kNodes, node = tx % kNodes;
+        if (k >= p.n) return;                                 // whole warps leave together (64 threads per marker)
+        long long cell; int s;
+        const float w = node_weight(p, k, node, cell, s);
+        float u0 = 0.f, u1 = 0.f, u2 = 0.f;
+        if (s >= 0) { u0 = w * p.band_u[s]; u1 = w * p.band_u[p.band_cap + s]; u2 = w * p.band_u[2 * p.band_cap + s]; }
+        u0 = warp_sum(u0); u1 = warp_sum(u1); u2 = warp_sum(u2);
+        if (reduction_leader(tx)) {
+            atomic_add_f(&p.Ustar[3 * k], u0); atomic_add_f(&p.Ustar[3 * k + 1], u1); atomic_add_f(&p.Ustar[3 * k + 2], u2);
+        }
+    }
+};
+
+// (a6, a7) direct forcing F_k = 2 rho0 (U_d - U*) and spreading F(x) += F_k w dV: one reduction atomic per node and
+// component; nodes of one marker are distinct cells, so a warp never collides with itself
+struct IbForceSpread {
+    static constexpr int kThreads = kNodes * kMarkersPerCta;
+    static constexpr int kMinBlocks = 8;
+    FG_HD static void run(const IbParams &p, int bx, int, int, int tx) {
+        const int k = bx * kMarkersPerCta + tx / kNodes, node = tx % kNodes;
+        if (k >= p.n) return;
+        const float f0 = 2.0f * (p.U[3 * k] - p.Ustar[3 * k]), f1 = 2.0f * (p.U[3 * k + 1] - p.Ustar[3 * k + 1]),
+                    f2 = 2.0f * (p.U[3 * k + 2] - p.Ustar[3 * k + 2]);
+        if (node == 0) { p.Fm[3 * k] = f0; p.Fm[3 * k + 1] = f1; p.Fm[3 * k + 2] = f2; }
+        long long cell; int s;
+        const float w = node_weight(p, k, node, cell, s) * p.dV[k];
+        if (s < 0) return;
+        atomic_add_f(&p.bandF[s], w * f0);
+        atomic_add_f(&p.bandF[p.band_cap + s], w * f1);
+        atomic_add_f(&p.bandF[2 * p.band_cap + s], w * f2);
+    }
+};
+
+// (a8) hydrodynamic wrench ON each link = minus what its markers exert on the fluid; markers arrive sorted by link,
+// so a warp usually holds one link: shuffle-reduce in fp64, 6 atomics per warp
+struct IbLinkReduce {
     static constexpr int kThreads = 128;
     static constexpr int kMinBlocks = 4;
     FG_HD static void run(const IbParams &p, int bx, int, int, int tx) {
         const int k = bx * kThreads + tx;
-        if (k >= p.n) return;
-        const float X = p.X[3 * k], Y = p.X[3 * k + 1], Z = p.X[3 * k + 2];
-        const int i0 = p.base[3 * k], j0 = p.base[3 * k + 1], k0 = p.base[3 * k + 2];
-        float wx[4], wy[4], wz[4];
-        FG_UNROLL
-        for (int a = 0; a < 4; ++a) {
-            wx[a] = peskin4(X - float(i0 + a));
-            wy[a] = peskin4(Y - float(j0 + a));
-            wz[a] = peskin4(Z - float(k0 + a));
+        const bool live = k < p.n;
+        int l = live ? p.link[k] : -1;
+        if (l >= p.n_links) l = -1;
+        double v[6] = {0, 0, 0, 0, 0, 0};
+        if (l >= 0) {
+            const double dV = p.dV[k];
+            const double fx = -double(p.Fm[3 * k]) * dV, fy = -double(p.Fm[3 * k + 1]) * dV, fz = -double(p.Fm[3 * k + 2]) * dV;
+            const double rx = double(p.X[3 * k]) - double(p.origin[3 * l]), ry = double(p.X[3 * k + 1]) - double(p.origin[3 * l + 1]),
+                         rz = double(p.X[3 * k + 2]) - double(p.origin[3 * l + 2]);
+            v[0] = fx; v[1] = fy; v[2] = fz;
+            v[3] = ry * fz - rz * fy; v[4] = rz * fx - rx * fz; v[5] = rx * fy - ry * fx;
         }
-        float us0 = 0.f, us1 = 0.f, us2 = 0.f;
-        for (int c = 0; c < 4; ++c)
-            for (int b = 0; b < 4; ++b)
-                for (int a = 0; a < 4; ++a) {
-                    const long long cell = stencil_cell(p, i0, j0, k0, a, b, c);
-                    if (cell < 0) continue;
-                    const int s = p.cellslot[cell] - 1;
-                    if (s < 0) continue;
-                    const float w = wx[a] * wy[b] * wz[c];
-                    us0 += w * p.band_u[s]; us1 += w * p.band_u[p.band_cap + s]; us2 += w * p.band_u[2 * p.band_cap + s];
+#if defined(__CUDA_ARCH__)
+        const int l0 = __shfl_sync(0xffffffffu, l, 0);
+        if (__all_sync(0xffffffffu, l == l0 || l < 0) ) {
+            if (l0 < 0) { /* lane 0 idle: fall through to the per-lane path below for the stragglers */ }
+            else {
+                FG_UNROLL
+                for (int c = 0; c < 6; ++c) v[c] = warp_sum(v[c]);
+                if ((tx & 31) == 0) {
+                    FG_UNROLL
+                    for (int c = 0; c < 6; ++c) atomicAdd(p.wrench + 6 * l0 + c, v[c]);
                 }
-        const float f0 = 2.0f * (p.U[3 * k] - us0), f1 = 2.0f * (p.U[3 * k + 1] - us1), f2 = 2.0f * (p.U[3 * k + 2] - us2);
-        p.Ustar[3 * k] = us0; p.Ustar[3 * k + 1] = us1; p.Ustar[3 * k + 2] = us2;
-        p.Fm[3 * k] = f0; p.Fm[3 * k + 1] = f1; p.Fm[3 * k + 2] = f2;
-        const float dV = p.dV[k];
-        for (int c = 0; c < 4; ++c)
-            for (int b = 0; b < 4; ++b)
-                for (int a = 0; a < 4; ++a) {
-                    const long long cell = stencil_cell(p, i0, j0, k0, a, b, c);
-                    if (cell < 0) continue;
-                    const int s = p.cellslot[cell] - 1;
-                    if (s < 0) continue;
-                    const float w = wx[a] * wy[b] * wz[c] * dV;
-                    atomic_add_f(&p.bandF[s], w * f0);
-                    atomic_add_f(&p.bandF[p.band_cap + s], w * f1);
-                    atomic_add_f(&p.bandF[2 * p.band_cap + s], w * f2);
-                }
-        // (a8) hydrodynamic wrench ON the link = minus what the markers exert on the fluid
-        const int l = p.link[k];
-        if (l >= 0 && l < p.n_links) {
-            const double fx = -double(f0) * dV, fy = -double(f1) * dV, fz = -double(f2) * dV;
-            const double rx = double(X) - double(p.origin[3 * l]), ry = double(Y) - double(p.origin[3 * l + 1]),
-                         rz = double(Z) - double(p.origin[3 * l + 2]);
-            double *w = p.wrench + 6 * l;
-            atomic_add_d(w + 0, fx); atomic_add_d(w + 1, fy); atomic_add_d(w + 2, fz);
-            atomic_add_d(w + 3, ry * fz - rz * fy);
-            atomic_add_d(w + 4, rz * fx - rx * fz);
-            atomic_add_d(w + 5, rx * fy - ry * fx);
+                return;
+            }
         }
+#endif
+        if (l >= 0)
+            for (int c = 0; c < 6; ++c) atomic_add_d(p.wrench + 6 * l + c, v[c]);
     }
 };
 
@@ -225,7 +293,7 @@ struct IbClearBand {
     static constexpr int kMinBlocks = 4;
     FG_HD static void run(const IbParams &p, int bx, int, int, int tx) {
         const int pos = bx * kThreads + tx;
-        const int cnt = *p.band_count < p.band_cap ? *p.band_count : p.band_cap;
+        const int cnt = *p.band_count_next < p.band_cap ? *p.band_count_next : p.band_cap;   // the previous step's counter
         if (pos >= cnt) return;
         const long long idx = p.band_cell[pos];
         p.cellslot[idx] = 0;
@@ -234,16 +302,22 @@ struct IbClearBand {
 };
 
 // ---------------------------------------------------------------- host-side state
+// PCIe traffic per substep (BASELINE.json:5 (c)): one pinned H2D message [X 3n | U 3n | dV n | link n | origins 3L]
+// (32 B per marker) and one pinned D2H message [wrench 6L doubles | band counters], both asynchronous on the
+// handle's stream; the host waits on an event recorded right after the IB kernels, i.e. BEFORE the stream-collide of
+// the same substep has run, so body integration and the next upload overlap the fluid kernel.
 template <class Dev>
 class IbState {
 public:
+    enum { EV_STAGE0 = 0, EV_STAGE1 = 1, EV_WRENCH = 2 };
+
     bool ready() const { return cap_ > 0; }
     int n_markers() const { return n_; }
     int n_links() const { return nl_; }
     int band_cells() const { return band_cells_; }
-    const double *wrench_ptr() const { return h_wrench_.data(); }
+    const double *wrench_ptr() const { return h_out_; }
     const double *origin_ptr() const { return h_origin_.data(); }
-    void clear_wrenches() { std::fill(h_wrench_.begin(), h_wrench_.end(), 0.0); }
+    void clear_wrenches() { if (h_out_) std::fill(h_out_, h_out_ + 6 * size_t(maxl_), 0.0); }
 
     int create(Dev &dev, const FgConfig &cfg, const Lattice &L, std::string &err) {
         cap_ = cfg.max_markers;
@@ -252,91 +326,121 @@ public:
         band_cap_ = int(std::min<long long>(64ll * cap_, (long long)L.plane * L.nz));
         per_[0] = cfg.bc[FG_XLO] == FG_BC_PERIODIC; per_[1] = cfg.bc[FG_YLO] == FG_BC_PERIODIC; per_[2] = cfg.bc[FG_ZLO] == FG_BC_PERIODIC;
         auto A = [&](size_t bytes) { void *p = dev.alloc(bytes, err); if (p && !dev.zero(p, bytes)) { err = dev.err; p = nullptr; } return p; };
-        dX_ = (float *)A(sizeof(float) * 3 * cap_); dU_ = (float *)A(sizeof(float) * 3 * cap_);
-        ddV_ = (float *)A(sizeof(float) * cap_); dlink_ = (int *)A(sizeof(int) * cap_);
+        msg_floats_ = 8 * size_t(cap_) + 3 * size_t(maxl_);
+        dmsg_ = (float *)A(sizeof(float) * msg_floats_);
         dbase_ = (int *)A(sizeof(int) * 3 * cap_); downer_ = (int *)A(sizeof(int) * cap_);
         dF_ = (float *)A(sizeof(float) * 3 * cap_); dUs_ = (float *)A(sizeof(float) * 3 * cap_);
         cellslot_ = (int *)A(sizeof(int) * cells);
         band_cell_ = (int *)A(sizeof(int) * band_cap_);
         band_u_ = (float *)A(sizeof(float) * 3 * band_cap_);
         bandF_ = (float *)A(sizeof(float) * 3 * band_cap_);
-        band_count_ = (int *)A(sizeof(int));
+        band_count_ = (int *)A(2 * sizeof(int));
         rowflag_ = (uint8_t *)A(size_t(L.nz + 2) * L.ny);
-        dorigin_ = (float *)A(sizeof(float) * 3 * maxl_);
         dwrench_ = (double *)A(sizeof(double) * 6 * maxl_);
-        if (!dX_ || !dU_ || !ddV_ || !dlink_ || !dbase_ || !downer_ || !dF_ || !dUs_ || !cellslot_ || !band_cell_ || !band_u_ ||
-            !bandF_ || !band_count_ || !rowflag_ || !dorigin_ || !dwrench_)
+        for (int i = 0; i < 2; ++i) h_stage_[i] = (float *)dev.alloc_host(sizeof(float) * msg_floats_, err);
+        h_out_ = (double *)dev.alloc_host(sizeof(double) * 6 * maxl_ + 2 * sizeof(int), err);
+        if (!dmsg_ || !dbase_ || !downer_ || !dF_ || !dUs_ || !cellslot_ || !band_cell_ || !band_u_ || !bandF_ || !band_count_ ||
+            !rowflag_ || !dwrench_ || !h_stage_[0] || !h_stage_[1] || !h_out_)
             return FG_ENOMEM;
-        h_wrench_.assign(6 * size_t(maxl_), 0.0);
+        std::memset(h_out_, 0, sizeof(double) * 6 * maxl_ + 2 * sizeof(int));
         h_origin_.assign(3 * size_t(maxl_), 0.0);
         return FG_OK;
     }
 
     void destroy(Dev &dev) {
-        void *ps[] = {dX_, dU_, ddV_, dlink_, dbase_, downer_, dF_, dUs_, cellslot_, band_cell_, band_u_, bandF_, band_count_, rowflag_,
-                      dorigin_, dwrench_};
+        void *ps[] = {dmsg_, dbase_, downer_, dF_, dUs_, cellslot_, band_cell_, band_u_, bandF_, band_count_, rowflag_, dwrench_};
         for (void *p : ps) dev.free(p);
+        dev.free_host(h_stage_[0]); dev.free_host(h_stage_[1]); dev.free_host(h_out_);
+        h_stage_[0] = h_stage_[1] = nullptr; h_out_ = nullptr;
         cap_ = 0;
     }
 
-    int set_markers(Dev &dev, int n, const float *X, const float *U, const float *dV, const int32_t *link, std::string &err) {
+    // origins: nullptr keeps the current torque reference points
+    int set_markers(Dev &dev, int n, const float *X, const float *U, const float *dV, const int32_t *link, const double *origins,
+                    int n_origins, std::string &err) {
         if (n > cap_) { err = "more markers than FgConfig.max_markers"; return FG_EINVAL; }
+        if (n_origins > maxl_) { err = "more links than FgConfig.max_links"; return FG_EINVAL; }
         int nl = 0;
-        std::vector<int32_t> zero;
-        if (!link) { zero.assign(n, 0); link = zero.data(); }
-        for (int k = 0; k < n; ++k) nl = std::max(nl, link[k] + 1);
+        if (link)
+            for (int k = 0; k < n; ++k) nl = std::max(nl, link[k] + 1);
+        else if (n > 0) nl = 1;
         if (nl > maxl_) { err = "link id exceeds FgConfig.max_links"; return FG_EINVAL; }
-        bool ok = true;
-        if (n > 0)
-            ok = dev.h2d(dX_, X, sizeof(float) * 3 * n) && dev.h2d(dU_, U, sizeof(float) * 3 * n) &&
-                 dev.h2d(ddV_, dV, sizeof(float) * n) && dev.h2d(dlink_, link, sizeof(int) * n);
-        if (!ok) { err = dev.err; return FG_ECUDA; }
+        if (origins) {
+            for (int i = 0; i < 3 * n_origins; ++i) h_origin_[i] = origins[i];
+            nl_origins_ = n_origins;
+        }
+        // pack the message in a pinned staging buffer (double-buffered: wait for the copy issued two calls ago)
+        const int sb = stage_next_;
+        stage_next_ ^= 1;
+        if (stage_used_[sb] && !dev.ev_sync(EV_STAGE0 + sb)) { err = dev.err; return FG_ECUDA; }
+        float *m = h_stage_[sb];
+        const size_t N = size_t(n);
+        if (n > 0) {
+            std::memcpy(m, X, sizeof(float) * 3 * N);
+            std::memcpy(m + 3 * N, U, sizeof(float) * 3 * N);
+            std::memcpy(m + 6 * N, dV, sizeof(float) * N);
+            if (link) std::memcpy(m + 7 * N, link, sizeof(int) * N);
+            else std::memset(m + 7 * N, 0, sizeof(int) * N);
+        }
+        for (size_t i = 0; i < 3 * size_t(maxl_); ++i) m[8 * N + i] = float(h_origin_[i]);
+        const size_t bytes = sizeof(float) * (8 * N + 3 * size_t(maxl_));
+        if (!dev.h2d_async(dmsg_, m, bytes) || !dev.ev_record(EV_STAGE0 + sb)) { err = dev.err; return FG_ECUDA; }
+        stage_used_[sb] = true;
         n_ = n;
         nl_ = std::max(nl, nl_origins_);
         forces_valid_ = false;
+        have_host_copy_ = sb;
         return FG_OK;
     }
 
-    int set_link_origins(int n, const double *o, std::string &err) {
+    int set_link_origins(Dev &dev, int n, const double *o, std::string &err) {
         if (n > maxl_) { err = "more links than FgConfig.max_links"; return FG_EINVAL; }
         for (int i = 0; i < 3 * n; ++i) h_origin_[i] = o[i];
         nl_origins_ = n;
         nl_ = std::max(nl_, n);
-        origins_dirty_ = true;
+        // rare path (prescribed markers): small synchronous upload behind the marker message
+        std::vector<float> of(3 * size_t(maxl_));
+        for (size_t i = 0; i < of.size(); ++i) of[i] = float(h_origin_[i]);
+        if (!dev.h2d(dmsg_ + 8 * size_t(n_), of.data(), sizeof(float) * of.size())) { err = dev.err; return FG_ECUDA; }
         return FG_OK;
     }
 
     IbParams params(const Lattice &L, const Collision &C) const {
         IbParams p{};
+        const size_t N = size_t(n_);
         p.L = L; p.C = C; p.n = n_;
         p.per_x = per_[0]; p.per_y = per_[1]; p.per_z = per_[2];
-        p.X = dX_; p.U = dU_; p.dV = ddV_; p.link = dlink_;
+        p.X = dmsg_; p.U = dmsg_ + 3 * N; p.dV = dmsg_ + 6 * N; p.link = reinterpret_cast<const int *>(dmsg_ + 7 * N);
+        p.origin = dmsg_ + 8 * N;
         p.base = dbase_; p.owner = downer_; p.Fm = dF_; p.Ustar = dUs_;
         p.cellslot = cellslot_; p.band_cell = band_cell_; p.band_u = band_u_; p.bandF = bandF_;
-        p.band_count = band_count_; p.band_cap = band_cap_; p.rowflag = rowflag_;
-        p.origin = dorigin_; p.wrench = dwrench_; p.n_links = nl_;
+        p.band_count = band_count_ + cur_; p.band_count_next = band_count_ + (cur_ ^ 1);
+        p.band_cap = band_cap_; p.rowflag = rowflag_;
+        p.wrench = dwrench_; p.n_links = nl_;
         return p;
     }
 
     // SURVEY.md A7 (2)-(5),(7) on the device; the collide that follows reads force_view()
     int compute_forces(Dev &dev, const Lattice &L, const Collision &C, int parity, std::string &err) {
+        cur_ ^= 1;                                            // this step's counter; the other one still holds the old size
         const IbParams p = params(L, C);
-        const int bound = int(std::min<long long>(band_cap_, 64ll * std::max(n_prev_, 1)));
         bool ok = true;
-        if (band_live_) ok = dev.template launch<IbClearBand>(Dim3x((bound + 127) / 128), p);
-        ok = ok && dev.zero(band_count_, sizeof(int)) && dev.zero(dwrench_, sizeof(double) * 6 * maxl_);
-        if (origins_dirty_) {
-            std::vector<float> o(3 * size_t(maxl_));
-            for (size_t i = 0; i < o.size(); ++i) o[i] = float(h_origin_[i]);
-            ok = ok && dev.h2d(dorigin_, o.data(), sizeof(float) * o.size());
-            origins_dirty_ = false;
+        if (band_live_) {
+            const int bound = int(std::min<long long>(band_cap_, (long long)kNodes * std::max(n_prev_, 1)));
+            ok = dev.template launch<IbClearBand>(Dim3x((bound + 127) / 128), p);
         }
-        const int nb = (n_ + 127) / 128;
+        const int nb = (n_ + kMarkersPerCta - 1) / kMarkersPerCta;
         ok = ok && dev.template launch<IbIndexMark>(Dim3x(nb), p);
-        const int bound2 = int(std::min<long long>(band_cap_, 64ll * n_));
+        const int bound2 = int(std::min<long long>(band_cap_, (long long)kNodes * n_));
         ok = ok && (parity == 0 ? dev.template launch<IbBandMoments<0>>(Dim3x((bound2 + 127) / 128), p)
                                 : dev.template launch<IbBandMoments<1>>(Dim3x((bound2 + 127) / 128), p));
-        ok = ok && dev.template launch<IbInterpSpread>(Dim3x(nb), p);
+        ok = ok && dev.template launch<IbInterpolate>(Dim3x(std::max(nb, (6 * nl_ + 127) / 128)), p);
+        ok = ok && dev.template launch<IbForceSpread>(Dim3x(nb), p);
+        ok = ok && dev.template launch<IbLinkReduce>(Dim3x((n_ + 127) / 128), p);
+        // results the host needs, queued right behind the IB kernels (not behind the collide that follows)
+        ok = ok && dev.d2h_async(h_out_, dwrench_, sizeof(double) * 6 * maxl_) &&
+             dev.d2h_async(reinterpret_cast<char *>(h_out_) + sizeof(double) * 6 * maxl_, band_count_, 2 * sizeof(int)) &&
+             dev.ev_record(EV_WRENCH);
         if (!ok) { err = dev.err; return FG_ECUDA; }
         band_live_ = true; n_prev_ = n_; forces_valid_ = true; wrench_fetched_ = false;
         return FG_OK;
@@ -347,11 +451,10 @@ public:
 
     int fetch_wrenches(Dev &dev, std::string &err) {
         if (!forces_valid_ || wrench_fetched_) return FG_OK;
-        if (!dev.sync() || !dev.d2h(h_wrench_.data(), dwrench_, sizeof(double) * 6 * maxl_)) { err = dev.err; return FG_ECUDA; }
-        int cnt = 0;
-        if (!dev.d2h(&cnt, band_count_, sizeof(int))) { err = dev.err; return FG_ECUDA; }
-        if (cnt > band_cap_) { err = "IB band overflow"; return FG_ENOMEM; }
-        band_cells_ = cnt;
+        if (!dev.ev_sync(EV_WRENCH)) { err = dev.err; return FG_ECUDA; }
+        const int *cnts = reinterpret_cast<const int *>(reinterpret_cast<const char *>(h_out_) + sizeof(double) * 6 * maxl_);
+        if (cnts[cur_] > band_cap_) { err = "IB band overflow"; return FG_ENOMEM; }
+        band_cells_ = cnts[cur_];
         wrench_fetched_ = true;
         return FG_OK;
     }
@@ -372,7 +475,7 @@ public:
         std::fill(F, F + 3 * nloc, 0.f);
         if (!band_live_) return FG_OK;
         int cnt = 0;
-        if (!dev.sync() || !dev.d2h(&cnt, band_count_, sizeof(int))) { err = dev.err; return FG_ECUDA; }
+        if (!dev.sync() || !dev.d2h(&cnt, band_count_ + cur_, sizeof(int))) { err = dev.err; return FG_ECUDA; }
         cnt = std::min(cnt, band_cap_);
         std::vector<int> cells(cnt);
         std::vector<float> bf(3 * size_t(band_cap_));
@@ -387,10 +490,11 @@ public:
     }
     int get_markers(Dev &dev, float *X, float *U, int32_t *link, int cap, std::string &err) {
         const int n = std::min(cap, n_);
-        bool ok = true;
-        if (n > 0 && X) ok = ok && dev.d2h(X, dX_, sizeof(float) * 3 * n);
-        if (n > 0 && U) ok = ok && dev.d2h(U, dU_, sizeof(float) * 3 * n);
-        if (n > 0 && link) ok = ok && dev.d2h(link, dlink_, sizeof(int) * n);
+        const size_t N = size_t(n_);
+        bool ok = dev.sync();
+        if (n > 0 && X) ok = ok && dev.d2h(X, dmsg_, sizeof(float) * 3 * n);
+        if (n > 0 && U) ok = ok && dev.d2h(U, dmsg_ + 3 * N, sizeof(float) * 3 * n);
+        if (n > 0 && link) ok = ok && dev.d2h(link, dmsg_ + 7 * N, sizeof(int) * n);
         if (!ok) { err = dev.err; return FG_ECUDA; }
         return n_;
     }
@@ -398,14 +502,18 @@ public:
 private:
     static Dim3 Dim3x(int x) { Dim3 d; d.x = std::max(x, 1); return d; }
     int cap_ = 0, maxl_ = 1, n_ = 0, nl_ = 0, nl_origins_ = 0, n_prev_ = 0, band_cap_ = 0, band_cells_ = 0;
+    int cur_ = 0, stage_next_ = 0, have_host_copy_ = 0;
+    size_t msg_floats_ = 0;
     int per_[3] = {1, 1, 1};
-    bool band_live_ = false, forces_valid_ = false, wrench_fetched_ = true, origins_dirty_ = true;
-    float *dX_ = nullptr, *dU_ = nullptr, *ddV_ = nullptr, *dF_ = nullptr, *dUs_ = nullptr, *band_u_ = nullptr, *bandF_ = nullptr,
-          *dorigin_ = nullptr;
-    int *dlink_ = nullptr, *dbase_ = nullptr, *downer_ = nullptr, *cellslot_ = nullptr, *band_cell_ = nullptr, *band_count_ = nullptr;
+    bool band_live_ = false, forces_valid_ = false, wrench_fetched_ = true;
+    bool stage_used_[2] = {false, false};
+    float *dmsg_ = nullptr, *dF_ = nullptr, *dUs_ = nullptr, *band_u_ = nullptr, *bandF_ = nullptr;
+    int *dbase_ = nullptr, *downer_ = nullptr, *cellslot_ = nullptr, *band_cell_ = nullptr, *band_count_ = nullptr;
     uint8_t *rowflag_ = nullptr;
     double *dwrench_ = nullptr;
-    std::vector<double> h_wrench_, h_origin_;
+    float *h_stage_[2] = {nullptr, nullptr};   // pinned
+    double *h_out_ = nullptr;                  // pinned: [6 maxl doubles][2 ints]
+    std::vector<double> h_origin_;
 };
 
 }  // namespace fg

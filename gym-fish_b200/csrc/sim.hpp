@@ -208,11 +208,11 @@ public:
         }
         if (n > 0 && !ib_.ready()) return fail(FG_ESTATE, "FgConfig.max_markers was 0 at create");
         if (!ib_.ready()) return FG_OK;
-        return ib_.set_markers(dev, n, X, U, dV, link, err);
+        return ib_.set_markers(dev, n, X, U, dV, link, nullptr, 0, err);
     }
     int set_link_origins(int n, const double *o) {
         if (!ib_.ready()) return fail(FG_ESTATE, "FgConfig.max_markers was 0 at create");
-        return ib_.set_link_origins(n, o, err);
+        return ib_.set_link_origins(dev, n, o, err);
     }
     IbState<Dev> &ib() { return ib_; }
     int get_force_field(float *F) {
@@ -552,8 +552,7 @@ private:
             f.emit_markers(&mX_[3 * size_t(mo)], &mU_[3 * size_t(mo)], &mdV_[mo], &mlink_[mo], lo, &morigin_[3 * size_t(lo)]);
             mo += f.n_markers(); lo += f.n_links();
         }
-        if (int rc = ib_.set_markers(dev, n, mX_.data(), mU_.data(), mdV_.data(), mlink_.data(), err)) return rc;
-        return ib_.set_link_origins(nl, morigin_.data(), err);
+        return ib_.set_markers(dev, n, mX_.data(), mU_.data(), mdV_.data(), mlink_.data(), morigin_.data(), nl, err);
     }
 
     Lattice L_{};

@@ -31,6 +31,12 @@ public:
     bool d2h(void *d, const void *s, size_t n) { std::memcpy(d, s, n); return true; }
     bool zero(void *d, size_t n) { std::memset(d, 0, n); return true; }
     bool sync() { return true; }
+    void *alloc_host(size_t bytes, std::string &e) { return alloc(bytes, e); }
+    void free_host(void *p) { std::free(p); }
+    bool h2d_async(void *d, const void *s, size_t n) { return h2d(d, s, n); }
+    bool d2h_async(void *d, const void *s, size_t n) { return d2h(d, s, n); }
+    bool ev_record(int) { return true; }
+    bool ev_sync(int) { return true; }
     void tic() { t0_ = std::chrono::steady_clock::now(); }
     void marks_reset() {}
     void mark(int) {}
