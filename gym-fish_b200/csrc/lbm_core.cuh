@@ -97,22 +97,32 @@ struct StepParams {
 // ---------------------------------------------------------------- collide (registers only)
 // shifted populations: rho = 1 + sum h, j = sum c h, u = (j + F/2)/rho  
 
+// 3 w_i for the momentum-carrying (odd) part of the equilibrium and of the Guo source.  In fp32, 18*fl(1/18) != 1:
+// with rounded weights the equilibrium carries (1+delta) j and BGK drifts momentum by omega*delta per step — a
+// SYSTEMATIC error that reaches 1e-5 within ~1000 steps.  These two constants satisfy 2*A1 + 8*A2 == 1 exactly in
+// fp32 (A2 = fl(1/12), A1 = 1/2 - 4*A2 is representable), and the odd part is built from j itself (no division),
+// so sum_i c_i h*_i == j + F up to unbiased rounding.
+constexpr float A2 = 1.0f / 12.0f;
+constexpr float A1 = 0.5f - 4.0f * A2;
+static_assert(2.0f * A1 + 8.0f * A2 == 1.0f, "odd-part weights must sum to exactly 1");
+
 template <int I> struct Dir {
     static constexpr int cx = CXT[I], cy = CYT[I], cz = CZT[I], opp = OPPT[I];
     static constexpr float w = I == 0 ? W0 : (I < 7 ? W1 : W2);
+    static constexpr float a = I < 7 ? A1 : A2;   // 3 w_i, see above
 };
 
 template <int I>
 FG_HD void bgk_pair(float (&h)[Q], float dr, float rho, float ux, float uy, float uz, float uu15, float Fx, float Fy,
-                    float Fz, float uF3, float om, float kf) {
+                    float Fz, float uF3, float om, float kf, float jx, float jy, float jz) {
     using D = Dir<I>;
     constexpr int J = D::opp;
     const float cu = D::cx * ux + D::cy * uy + D::cz * uz;
     const float cF = D::cx * Fx + D::cy * Fy + D::cz * Fz;
     const float sym = D::w * (dr + rho * (4.5f * cu * cu - uu15));
-    const float asym = D::w * rho * 3.0f * cu;
+    const float asym = D::a * (D::cx * jx + D::cy * jy + D::cz * jz);   // 3 w rho c.u with rho u = j + F/2 taken as is
     const float psym = D::w * (9.0f * cu * cF - uF3);
-    const float pasym = D::w * 3.0f * cF;
+    const float pasym = D::a * cF;
     h[I] = h[I] - om * (h[I] - (sym + asym)) + kf * (psym + pasym);
     h[J] = h[J] - om * (h[J] - (sym - asym)) + kf * (psym - pasym);
 }
@@ -126,20 +136,21 @@ FG_HD void collide_bgk(float (&h)[Q], float Fx, float Fy, float Fz, const Collis
     const float jy = (h[3] - h[4]) + ((h[7] + h[8]) - (h[9] + h[10])) + ((h[15] - h[16]) + (h[17] - h[18]));
     const float jz = (h[5] - h[6]) + ((h[11] + h[12]) - (h[13] + h[14])) + ((h[15] + h[16]) - (h[17] + h[18]));
     const float rho = 1.0f + dr, inv = 1.0f / rho;
-    const float ux = (jx + 0.5f * Fx) * inv, uy = (jy + 0.5f * Fy) * inv, uz = (jz + 0.5f * Fz) * inv;
+    const float ex = jx + 0.5f * Fx, ey = jy + 0.5f * Fy, ez = jz + 0.5f * Fz;   // rho u
+    const float ux = ex * inv, uy = ey * inv, uz = ez * inv;
     const float uu15 = 1.5f * (ux * ux + uy * uy + uz * uz);
     const float uF3 = 3.0f * (ux * Fx + uy * Fy + uz * Fz);
     const float om = c.omega, kf = 1.0f - 0.5f * om;
     h[0] = h[0] - om * (h[0] - W0 * (dr - rho * uu15)) - kf * W0 * uF3;
-    bgk_pair<1>(h, dr, rho, ux, uy, uz, uu15, Fx, Fy, Fz, uF3, om, kf);
-    bgk_pair<3>(h, dr, rho, ux, uy, uz, uu15, Fx, Fy, Fz, uF3, om, kf);
-    bgk_pair<5>(h, dr, rho, ux, uy, uz, uu15, Fx, Fy, Fz, uF3, om, kf);
-    bgk_pair<7>(h, dr, rho, ux, uy, uz, uu15, Fx, Fy, Fz, uF3, om, kf);
-    bgk_pair<8>(h, dr, rho, ux, uy, uz, uu15, Fx, Fy, Fz, uF3, om, kf);
-    bgk_pair<11>(h, dr, rho, ux, uy, uz, uu15, Fx, Fy, Fz, uF3, om, kf);
-    bgk_pair<12>(h, dr, rho, ux, uy, uz, uu15, Fx, Fy, Fz, uF3, om, kf);
-    bgk_pair<15>(h, dr, rho, ux, uy, uz, uu15, Fx, Fy, Fz, uF3, om, kf);
-    bgk_pair<16>(h, dr, rho, ux, uy, uz, uu15, Fx, Fy, Fz, uF3, om, kf);
+    bgk_pair<1>(h, dr, rho, ux, uy, uz, uu15, Fx, Fy, Fz, uF3, om, kf, ex, ey, ez);
+    bgk_pair<3>(h, dr, rho, ux, uy, uz, uu15, Fx, Fy, Fz, uF3, om, kf, ex, ey, ez);
+    bgk_pair<5>(h, dr, rho, ux, uy, uz, uu15, Fx, Fy, Fz, uF3, om, kf, ex, ey, ez);
+    bgk_pair<7>(h, dr, rho, ux, uy, uz, uu15, Fx, Fy, Fz, uF3, om, kf, ex, ey, ez);
+    bgk_pair<8>(h, dr, rho, ux, uy, uz, uu15, Fx, Fy, Fz, uF3, om, kf, ex, ey, ez);
+    bgk_pair<11>(h, dr, rho, ux, uy, uz, uu15, Fx, Fy, Fz, uF3, om, kf, ex, ey, ez);
+    bgk_pair<12>(h, dr, rho, ux, uy, uz, uu15, Fx, Fy, Fz, uF3, om, kf, ex, ey, ez);
+    bgk_pair<15>(h, dr, rho, ux, uy, uz, uu15, Fx, Fy, Fz, uF3, om, kf, ex, ey, ez);
+    bgk_pair<16>(h, dr, rho, ux, uy, uz, uu15, Fx, Fy, Fz, uF3, om, kf, ex, ey, ez);
 }
 
 // MRT in the d'Humieres basis, closed forms for M h, m_eq, M*source and M^-1.
@@ -173,8 +184,9 @@ FG_HD void collide_mrt(float (&h)[Q], float Fx, float Fy, float Fz, const Collis
     const float m_mx = exy_x - exz_x, m_my = eyz_y - exy_y, m_mz = exz_z - eyz_z;
     // macroscopic
     const float rho = 1.0f + dr, inv = 1.0f / rho;
-    const float ux = (jx + 0.5f * Fx) * inv, uy = (jy + 0.5f * Fy) * inv, uz = (jz + 0.5f * Fz) * inv;
-    const float ruxx = rho * ux * ux, ruyy = rho * uy * uy, ruzz = rho * uz * uz;
+    const float rux = jx + 0.5f * Fx, ruy = jy + 0.5f * Fy, ruz = jz + 0.5f * Fz;   // rho u, no division
+    const float ux = rux * inv, uy = ruy * inv, uz = ruz * inv;
+    const float ruxx = rux * ux, ruyy = ruy * uy, ruzz = ruz * uz;
     const float ruu = ruxx + ruyy + ruzz;
     const float uF = ux * Fx + uy * Fy + uz * Fz;
     const float fxx = 2.0f * ux * Fx - uy * Fy - uz * Fz;   // source of 3p_xx / 2
@@ -185,17 +197,17 @@ FG_HD void collide_mrt(float (&h)[Q], float Fx, float Fy, float Fz, const Collis
     const float d2 = (-s[2] * (m_eps - (3.0f * dr - 5.5f * ruu)) - (1.0f - 0.5f * s[2]) * 11.0f * uF) * (1.0f / 252.0f);
     const float d3 = Fx * 0.1f, d5 = Fy * 0.1f, d7 = Fz * 0.1f;
     const float k23 = 2.0f / 3.0f;
-    const float d4 = (-s[4] * (qx + k23 * rho * ux) - (1.0f - 0.5f * s[4]) * k23 * Fx) * 0.025f;
-    const float d6 = (-s[6] * (qy + k23 * rho * uy) - (1.0f - 0.5f * s[6]) * k23 * Fy) * 0.025f;
-    const float d8 = (-s[8] * (qz + k23 * rho * uz) - (1.0f - 0.5f * s[8]) * k23 * Fz) * 0.025f;
+    const float d4 = (-s[4] * (qx + k23 * rux) - (1.0f - 0.5f * s[4]) * k23 * Fx) * 0.025f;
+    const float d6 = (-s[6] * (qy + k23 * ruy) - (1.0f - 0.5f * s[6]) * k23 * Fy) * 0.025f;
+    const float d8 = (-s[8] * (qz + k23 * ruz) - (1.0f - 0.5f * s[8]) * k23 * Fz) * 0.025f;
     const float pxx_eq = 2.0f * ruxx - ruyy - ruzz, pww_eq = ruyy - ruzz;
     const float d9 = (-s[9] * (m_pxx - pxx_eq) + (1.0f - 0.5f * s[9]) * 2.0f * fxx) * (1.0f / 36.0f);
     const float d10 = (-s[10] * (m_pixx + 0.5f * pxx_eq) - (1.0f - 0.5f * s[10]) * fxx) * (1.0f / 72.0f);
     const float d11 = (-s[11] * (m_pww - pww_eq) + (1.0f - 0.5f * s[11]) * 2.0f * fww) * (1.0f / 12.0f);
     const float d12 = (-s[12] * (m_piww + 0.5f * pww_eq) - (1.0f - 0.5f * s[12]) * fww) * (1.0f / 24.0f);
-    const float d13 = (-s[13] * (m_pxy - rho * ux * uy) + (1.0f - 0.5f * s[13]) * (ux * Fy + uy * Fx)) * 0.25f;
-    const float d14 = (-s[14] * (m_pyz - rho * uy * uz) + (1.0f - 0.5f * s[14]) * (uy * Fz + uz * Fy)) * 0.25f;
-    const float d15 = (-s[15] * (m_pxz - rho * ux * uz) + (1.0f - 0.5f * s[15]) * (ux * Fz + uz * Fx)) * 0.25f;
+    const float d13 = (-s[13] * (m_pxy - rux * uy) + (1.0f - 0.5f * s[13]) * (ux * Fy + uy * Fx)) * 0.25f;
+    const float d14 = (-s[14] * (m_pyz - ruy * uz) + (1.0f - 0.5f * s[14]) * (uy * Fz + uz * Fy)) * 0.25f;
+    const float d15 = (-s[15] * (m_pxz - rux * uz) + (1.0f - 0.5f * s[15]) * (ux * Fz + uz * Fx)) * 0.25f;
     const float d16 = -s[16] * m_mx * 0.125f, d17 = -s[17] * m_my * 0.125f, d18 = -s[18] * m_mz * 0.125f;
     // h* = h + M^T d
     h[0] += -30.0f * d1 + 12.0f * d2;
