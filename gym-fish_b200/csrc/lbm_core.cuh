@@ -92,6 +92,7 @@ struct StepParams {
     ForceField F;
     int zz_begin, zz_end;  // storage planes [zz_begin, zz_end) this launch covers
     int y0, ystride;       // rows this launch covers: y = y0 + blockIdx.y * ystride
+    long long kz[Q][3];    // byte offset of (slot S, plane z-1 / z / z+1) from a cell of plane z: 4*(S*slot + dz*plane)
 };
 
 // ---------------------------------------------------------------- collide (registers only)
@@ -365,24 +366,84 @@ FG_HD void store_departing(const float (&h)[Q], const Lattice &L, const Collisio
 // MODE is decided by the HOST per launch (sim.hpp launch_collide partitions the slab), so the bulk kernel carries no
 // boundary code and fits 64 registers (8 CTAs of 128 threads per SM):
 //   CHECK_NONE  no link can be blocked in the rows / planes of this launch
-//   CHECK_XEDGE only the two cells at the ends of each row can (x walls): those threads take the checked path
+//   CHECK_XEDGE only the two cells at the ends of each row can (x walls): predicated pointer selects, no divergence
 //   CHECK_ALL   wall rows (y walls), wall planes (z walls), or obstacles anywhere
 enum : int { CHECK_NONE = 0, CHECK_ALL = 1, CHECK_XEDGE = 2 };
+
+// ---- bulk path addressing.  ncu showed the first version of the odd kernel issue-limited by 64-bit address
+// arithmetic (4-5 integer instructions per access, more than the MRT itself).  Here a thread builds the 9 pointers to
+// its (x+a, y+b) neighbours in the own plane once (periodic wrap folded in), and every access adds a launch-constant
+// 64-bit byte offset kz[slot][dz] that the host precomputed and that sits in the constant bank: 2 integer
+// instructions per access.  X walls (CHECK_XEDGE) are handled by predicated pointer selects on the ten links with
+// c_x != 0 instead of a divergent checked path.
+struct NbrPtrs {
+    char *p[3][3];      // [a+1][b+1] -> slot 0 of cell (x+a, y+b, z)
+    bool bxm, bxp;      // x wall on the low / high side of this cell (CHECK_XEDGE only)
+};
+
+template <bool XEDGE>
+FG_HD NbrPtrs make_ptrs(const Lattice &L, int x, int y, long long idx) {
+    NbrPtrs n;
+    char *pc = reinterpret_cast<char *>(L.f + idx);
+    const int dxm = (x == 0 ? L.nx - 1 : -1) * 4, dxp = (x == L.nx - 1 ? -(L.nx - 1) : 1) * 4;
+    const int dym = (y == 0 ? (L.ny - 1) * L.nx : -L.nx) * 4, dyp = (y == L.ny - 1 ? -(L.ny - 1) * L.nx : L.nx) * 4;
+    n.p[1][1] = pc;
+    n.p[0][1] = pc + dxm; n.p[2][1] = pc + dxp;
+    n.p[1][0] = pc + dym; n.p[1][2] = pc + dyp;
+    n.p[0][0] = pc + (dxm + dym); n.p[2][0] = pc + (dxp + dym);
+    n.p[0][2] = pc + (dxm + dyp); n.p[2][2] = pc + (dxp + dyp);
+    n.bxm = XEDGE && x == 0;
+    n.bxp = XEDGE && x == L.nx - 1;
+    return n;
+}
+
+template <int I, bool XEDGE>
+FG_HD void fast_odd_load_pair(float (&h)[Q], const StepParams &p, const NbrPtrs &n) {
+    using D = Dir<I>;
+    constexpr int J = D::opp;
+    // f_I arrives from x - c_I (stored in slot J there); f_J arrives from x + c_I (stored in slot I there)
+    const char *am = n.p[1 - D::cx][1 - D::cy] + p.kz[J][1 - D::cz];
+    const char *ap = n.p[1 + D::cx][1 + D::cy] + p.kz[I][1 + D::cz];
+    if (XEDGE && D::cx != 0) {
+        const bool bm = D::cx > 0 ? n.bxm : n.bxp;   // the cell at x - c_I is behind the wall
+        const bool bp = D::cx > 0 ? n.bxp : n.bxm;   // the cell at x + c_I is behind the wall
+        const char *own_i = n.p[1][1] + p.kz[I][1], *own_j = n.p[1][1] + p.kz[J][1];
+        const float wi = p.C.wallterm[D::cx > 0 ? F_XLO : F_XHI][I], wj = p.C.wallterm[D::cx > 0 ? F_XHI : F_XLO][J];
+        h[I] = *reinterpret_cast<const float *>(bm ? own_i : am) + (bm ? wi : 0.0f);
+        h[J] = *reinterpret_cast<const float *>(bp ? own_j : ap) + (bp ? wj : 0.0f);
+    } else {
+        h[I] = *reinterpret_cast<const float *>(am);
+        h[J] = *reinterpret_cast<const float *>(ap);
+    }
+}
+
+template <int I, bool XEDGE>
+FG_HD void fast_odd_store_pair(const float (&h)[Q], const StepParams &p, const NbrPtrs &n) {
+    using D = Dir<I>;
+    constexpr int J = D::opp;
+    char *am = n.p[1 - D::cx][1 - D::cy] + p.kz[J][1 - D::cz];
+    char *ap = n.p[1 + D::cx][1 + D::cy] + p.kz[I][1 + D::cz];
+    if (XEDGE && D::cx != 0) {
+        const bool bm = D::cx > 0 ? n.bxm : n.bxp;
+        const bool bp = D::cx > 0 ? n.bxp : n.bxm;
+        char *own_i = n.p[1][1] + p.kz[I][1], *own_j = n.p[1][1] + p.kz[J][1];
+        const float wi = p.C.wallterm[D::cx > 0 ? F_XLO : F_XHI][I], wj = p.C.wallterm[D::cx > 0 ? F_XHI : F_XLO][J];
+        *reinterpret_cast<float *>(bp ? own_j : ap) = h[I] + (bp ? wj : 0.0f);   // f*_I bounces into slot J of this cell
+        *reinterpret_cast<float *>(bm ? own_i : am) = h[J] + (bm ? wi : 0.0f);
+    } else {
+        *reinterpret_cast<float *>(ap) = h[I];
+        *reinterpret_cast<float *>(am) = h[J];
+    }
+}
 
 template <int PARITY, bool MRT, int MODE>
 struct StreamCollide {
     static constexpr int kThreads = 128;
     static constexpr int kMinBlocks = 8;
-    template <bool CHECK>
-    FG_HD static void cell(const StepParams &p, int x, int y, int zz) {
-        const Lattice &L = p.L;
-        const long long idx = ((long long)zz * L.ny + y) * L.nx + x;
-        if (CHECK && L.solid && L.solid[idx]) return;
-        const Nbr nb = make_nbr(L, x, y, zz);
-        float h[Q];
-        load_arriving<PARITY, CHECK>(h, L, p.C, nb, idx);
-        float Fx = p.C.g[0], Fy = p.C.g[1], Fz = p.C.g[2];
-        if (p.F.cellslot && p.F.rowflag[zz * L.ny + y]) {
+
+    FG_HD static void force_at(const StepParams &p, int y, int zz, long long idx, float &Fx, float &Fy, float &Fz) {
+        Fx = p.C.g[0]; Fy = p.C.g[1]; Fz = p.C.g[2];
+        if (p.F.cellslot && p.F.rowflag[zz * p.L.ny + y]) {
             const int s = p.F.cellslot[idx];
             if (s > 0) {
                 Fx += p.F.bandF[s - 1];
@@ -390,15 +451,58 @@ struct StreamCollide {
                 Fz += p.F.bandF[2 * p.F.band_cap + s - 1];
             }
         }
-        if (MRT) collide_mrt(h, Fx, Fy, Fz, p.C); else collide_bgk(h, Fx, Fy, Fz, p.C);
-        store_departing<PARITY, CHECK>(h, L, p.C, nb, idx);
     }
+
+    // general path: every link checked against walls and obstacles
+    FG_HD static void checked_cell(const StepParams &p, int x, int y, int zz) {
+        const Lattice &L = p.L;
+        const long long idx = ((long long)zz * L.ny + y) * L.nx + x;
+        if (L.solid && L.solid[idx]) return;
+        const Nbr nb = make_nbr(L, x, y, zz);
+        float h[Q];
+        load_arriving<PARITY, true>(h, L, p.C, nb, idx);
+        float Fx, Fy, Fz;
+        force_at(p, y, zz, idx, Fx, Fy, Fz);
+        if (MRT) collide_mrt(h, Fx, Fy, Fz, p.C); else collide_bgk(h, Fx, Fy, Fz, p.C);
+        store_departing<PARITY, true>(h, L, p.C, nb, idx);
+    }
+
+    // bulk path: no blocked link except (XEDGE) across the x walls
+    template <bool XEDGE>
+    FG_HD static void bulk_cell(const StepParams &p, int x, int y, int zz) {
+        const Lattice &L = p.L;
+        const long long idx = ((long long)zz * L.ny + y) * L.nx + x;
+        float h[Q];
+        if (PARITY == 0) {
+            // even step: 19 aligned, purely local accesses; plain indexing compiles to the leanest code here
+            const Nbr nb{};
+            load_arriving<0, false>(h, L, p.C, nb, idx);
+            float Fx, Fy, Fz;
+            force_at(p, y, zz, idx, Fx, Fy, Fz);
+            if (MRT) collide_mrt(h, Fx, Fy, Fz, p.C); else collide_bgk(h, Fx, Fy, Fz, p.C);
+            store_departing<0, false>(h, L, p.C, nb, idx);
+        } else {
+            const NbrPtrs n = make_ptrs<XEDGE>(L, x, y, idx);
+            h[0] = *reinterpret_cast<const float *>(n.p[1][1] + p.kz[0][1]);
+#define FG_X(I) fast_odd_load_pair<I, XEDGE>(h, p, n);
+            FG_FOR_PAIRS(FG_X)
+#undef FG_X
+            float Fx, Fy, Fz;
+            force_at(p, y, zz, idx, Fx, Fy, Fz);
+            if (MRT) collide_mrt(h, Fx, Fy, Fz, p.C); else collide_bgk(h, Fx, Fy, Fz, p.C);
+            *reinterpret_cast<float *>(n.p[1][1] + p.kz[0][1]) = h[0];
+#define FG_X(I) fast_odd_store_pair<I, XEDGE>(h, p, n);
+            FG_FOR_PAIRS(FG_X)
+#undef FG_X
+        }
+    }
+
     FG_HD static void run(const StepParams &p, int bx, int by, int bz, int tx) {
         const int x = bx * kThreads + tx, y = p.y0 + by * p.ystride, zz = p.zz_begin + bz;
         if (x >= p.L.nx) return;
-        if (MODE == CHECK_ALL) cell<true>(p, x, y, zz);
-        else if (MODE == CHECK_XEDGE && PARITY == 1 && (x == 0 || x == p.L.nx - 1)) cell<true>(p, x, y, zz);
-        else cell<false>(p, x, y, zz);
+        if (MODE == CHECK_ALL) checked_cell(p, x, y, zz);
+        else if (MODE == CHECK_XEDGE) bulk_cell<true>(p, x, y, zz);
+        else bulk_cell<false>(p, x, y, zz);
     }
 };
 

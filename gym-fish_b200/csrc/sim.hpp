@@ -458,7 +458,9 @@ private:
     }
     bool launch_rows(int mode, int zb, int ze, int y0, int ystride, int rows, const ForceField &F) {
         if (ze <= zb || rows <= 0) return true;
-        StepParams p{L_, C_, F, zb, ze, y0, ystride};
+        StepParams p{L_, C_, F, zb, ze, y0, ystride, {}};
+        for (int s = 0; s < Q; ++s)
+            for (int d = 0; d < 3; ++d) p.kz[s][d] = 4ll * (s * L_.slot + (long long)(d - 1) * L_.plane);
         const Dim3 g{(L_.nx + 127) / 128, rows, ze - zb};
         ++collide_launches_;
         if (parity_ == 0) {
