@@ -225,6 +225,7 @@ def main():
     ap.add_argument("--workload", default="sphere_256x128x128", choices=list(WORKLOADS))
     ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: halo after the full-slab kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="launch kernels directly instead of per-substep CUDA graphs")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer loop (default: --steps)")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -257,7 +258,7 @@ def main():
 
     wl = args.workload
     w = WORKLOADS[wl]
-    flags = g._abi.FLAG_PROFILE | (g._abi.FLAG_NO_OVERLAP if args.no_overlap else 0)
+    flags = (g._abi.FLAG_NO_OVERLAP if args.no_overlap else 0) | (g._abi.FLAG_NO_GRAPHS if args.no_graphs else 0)
     sim, markers = make_sim(g, "cuda", wl, rank, world, local, flags=flags)
     if world > 1:
         handles = [None] * world
@@ -282,7 +283,16 @@ def main():
     clk = clocks.stop()
     ms_local = st.last_step_ms
     launches = st.kernel_launches - launches0
-    collide_ms, collide_n, ib_ms = st.collide_ms, st.collide_launches, st.ib_ms
+    # second pass of the same K steps with every stream-collide / IB launch bracketed by CUDA events on the library's
+    # stream (FG_FLAG_PROFILE; graphs off): the dominant kernel's own duration for the roofline
+    sim.set_flags(flags | g._abi.FLAG_PROFILE)
+    barrier()
+    sim.step(args.steps)
+    sp = sim.stats()
+    collide_ms, collide_n, ib_ms = sp.collide_ms, sp.collide_launches, sp.ib_ms
+    profiled_ms = sp.last_step_ms
+    sim.set_flags(flags)
+    barrier()
     ms = ms_local
     if dist is not None:
         import torch
@@ -366,7 +376,9 @@ def main():
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "kernel": "fg::StreamCollide<parity, MRT> (even+odd average)", "peak_source": peak_src,
                 "kernel_ms_per_step": collide_ms / args.steps, "launches_timed": int(collide_n),
-                "bytes_per_cell_update": BYTES_PER_CELL_UPDATE, "ib_ms_per_step": ib_ms / args.steps}
+                "bytes_per_cell_update": BYTES_PER_CELL_UPDATE, "ib_ms_per_step": ib_ms / args.steps,
+                "timed_in": "second pass of the same K steps with event brackets (FG_FLAG_PROFILE)",
+                "profiled_pass_ms_per_step": profiled_ms / args.steps}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
@@ -381,7 +393,7 @@ def main():
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": w["desc"], "name": wl, "grid_per_gpu_xyz": [w["nx"], w["ny"], w["nz"]], "ranks": world,
                    "markers_per_gpu": int(st.n_markers), "decomposition": "z-slabs, halos by peer stores over NVLink" if world > 1 else "single GPU",
-                   "halo_overlap": not args.no_overlap,
+                   "halo_overlap": not args.no_overlap, "cuda_graphs": not args.no_graphs,
                    "l2": f"populations {19 * 4 * cells_local / 1e6:.0f} MB per GPU > 126 MB L2, no flush needed"},
         "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
         "pct_of_hbm_roofline": (value / world) * BYTES_PER_CELL_UPDATE / 1e3 / peak * 100.0,

@@ -23,6 +23,7 @@ XLO, XHI, YLO, YHI, ZLO, ZHI = range(6)
 BC_PERIODIC, BC_WALL, BC_INLET, BC_OUTLET = range(4)
 FLAG_NO_OVERLAP = 1
 FLAG_PROFILE = 2
+FLAG_NO_GRAPHS = 4
 
 _ERR_NAMES = {FG_EINVAL: "FG_EINVAL", FG_ENOMEM: "FG_ENOMEM", FG_ECUDA: "FG_ECUDA", FG_ESTATE: "FG_ESTATE",
               FG_ENOTSUP: "FG_ENOTSUP", FG_EPEER: "FG_EPEER"}
@@ -131,6 +132,7 @@ SYMBOLS = [
     ("fg_step", C.c_int, [_P, C.c_int32]),
     ("fg_sync", C.c_int, [_P]),
     ("fg_get_stats", C.c_int, [_P, C.POINTER(FgStats)]),
+    ("fg_set_flags", C.c_int, [_P, C.c_int32]),
     ("fg_halo_bytes", C.c_int64, [_P]),
     ("fg_halo_pack", C.c_int, [_P, C.c_int32, C.c_void_p]),
     ("fg_halo_unpack", C.c_int, [_P, C.c_int32, C.c_void_p]),
@@ -352,6 +354,10 @@ class Sim:
 
     def sync(self):
         self._ck(self.lib.fg_sync(self.h))
+
+    def set_flags(self, flags: int):
+        self._ck(self.lib.fg_set_flags(self.h, int(flags)))
+        self.cfg.flags = int(flags)
 
     # -- halos --
     def halo_bytes(self) -> int:

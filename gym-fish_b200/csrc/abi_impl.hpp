@@ -194,6 +194,13 @@ int fg_get_stats(FgSim *s, FgStats *o) {
     FG_TRY return s->sim.get_stats(o); FG_CATCH(s)
 }
 
+int fg_set_flags(FgSim *s, int32_t flags) {
+    if (!s) return FG_EINVAL;
+    s->sim.cfg.flags = flags;
+    s->sim.dev.graph_clear();
+    return FG_OK;
+}
+
 int64_t fg_halo_bytes(FgSim *s) { return s ? s->sim.halo_bytes() : FG_EINVAL; }
 int fg_halo_pack(FgSim *s, int32_t face, void *buf) {
     if (!s || !buf) return FG_EINVAL;

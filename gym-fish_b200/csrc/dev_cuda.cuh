@@ -8,6 +8,7 @@
 #include <cstring>
 #include <string>
 #include <unistd.h>
+#include <unordered_map>
 #include <utility>
 #include <vector>
 
@@ -21,12 +22,15 @@ __global__ void __launch_bounds__(K::kThreads, K::kMinBlocks) kern(const __grid_
 }
 
 // neighbour hand-shake: one thread, system-scope release / acquire on a word in (peer) device memory
-__global__ void signal_kernel(int *lo, int *hi, int value) {
+__global__ void signal_kernel(int *mine, int *lo, int *hi) {
+    const int value = mine[2] + 1;   // my halo counter lives on the device so that the launch arguments never change
+    mine[2] = value;
     __threadfence_system();
     if (lo) asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(lo), "r"(value) : "memory");
     if (hi) asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(hi), "r"(value) : "memory");
 }
-__global__ void wait_kernel(int *flags, int lo, int hi, int value, unsigned long long timeout_ns) {
+__global__ void wait_kernel(int *flags, int lo, int hi, unsigned long long timeout_ns) {
+    const int value = flags[2];      // neighbours must have pushed as many halos as I have
     unsigned long long t0;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
     for (int s = 0; s < 2; ++s) {
@@ -73,6 +77,7 @@ public:
     void shutdown() {
         if (device_ < 0) return;
         cudaSetDevice(device_);
+        graph_clear();
         if (stream_) { cudaStreamSynchronize(stream_); cudaStreamDestroy(stream_); stream_ = nullptr; }
         if (ev0_) cudaEventDestroy(ev0_);
         if (ev1_) cudaEventDestroy(ev1_);
@@ -132,17 +137,22 @@ public:
     }
     bool h2d_async(void *d, const void *pinned, size_t n) {
         cudaSetDevice(device_);
+        if (gmode_ == 2) return true;
         return ck(cudaMemcpyAsync(d, pinned, n, cudaMemcpyHostToDevice, stream_), "H2D async");
     }
     bool d2h_async(void *pinned, const void *s, size_t n) {
         cudaSetDevice(device_);
+        if (gmode_ == 2) return true;
         return ck(cudaMemcpyAsync(pinned, s, n, cudaMemcpyDeviceToHost, stream_), "D2H async");
     }
     bool ev_record(int id) {
         cudaSetDevice(device_);
         if (id < 0 || id >= kNamedEvents) return false;
         if (!named_[id] && !ck(cudaEventCreateWithFlags(&named_[id], cudaEventDisableTiming), "cudaEventCreate")) return false;
-        return ck(cudaEventRecord(named_[id], stream_), "cudaEventRecord");
+        if (gmode_ == 2) return true;
+        // inside a capture the record must become an event-record NODE the host can wait on, not a capture-internal edge
+        return ck(cudaEventRecordWithFlags(named_[id], stream_, gmode_ == 1 ? cudaEventRecordExternal : cudaEventRecordDefault),
+                  "cudaEventRecord");
     }
     bool ev_sync(int id) {
         if (id < 0 || id >= kNamedEvents || !named_[id]) return true;
@@ -187,8 +197,9 @@ public:
     template <class K, class P>
     bool launch(Dim3 g, const P &p) {
         cudaSetDevice(device_);
-        kern<K, P><<<dim3(g.x, g.y, g.z), K::kThreads, 0, stream_>>>(p);
         ++launches;
+        if (gmode_ == 2) return true;   // replaying a captured substep
+        kern<K, P><<<dim3(g.x, g.y, g.z), K::kThreads, 0, stream_>>>(p);
         return ck(cudaGetLastError(), "kernel launch");
     }
 
@@ -233,18 +244,66 @@ public:
         for (auto &o : opened_) cudaIpcCloseMemHandle(o.second);
         opened_.clear();
     }
-    bool signal_flags(int *lo, int *hi, int value) {
+    bool signal_flags(int *mine, int *lo, int *hi) {
         cudaSetDevice(device_);
-        signal_kernel<<<1, 1, 0, stream_>>>(lo, hi, value);
         ++launches;
+        if (gmode_ == 2) return true;
+        signal_kernel<<<1, 1, 0, stream_>>>(mine, lo, hi);
         return ck(cudaGetLastError(), "signal launch");
     }
-    bool wait_flags(int *flags, bool lo, bool hi, int value) {
+    bool wait_flags(int *flags, bool lo, bool hi) {
         if (!lo && !hi) return true;
         cudaSetDevice(device_);
-        wait_kernel<<<1, 1, 0, stream_>>>(flags, lo, hi, value, 20ull * 1000ull * 1000ull * 1000ull);
         ++launches;
+        if (gmode_ == 2) return true;
+        wait_kernel<<<1, 1, 0, stream_>>>(flags, lo, hi, 20ull * 1000ull * 1000ull * 1000ull);
         return ck(cudaGetLastError(), "wait launch");
+    }
+
+    // ---- per-substep CUDA graphs: capture the stream once per key, replay afterwards.  While replaying (gmode_ 2)
+    // launches and async copies are not enqueued — the caller's host code still runs and keeps its state in step.
+    bool graph_begin(uint64_t key) {
+        cudaSetDevice(device_);
+        auto it = graphs_.find(key);
+        if (it != graphs_.end()) { gmode_ = 2; gexec_ = it->second; return true; }
+        if (graphs_.size() >= 64) graph_clear();
+        if (cudaStreamBeginCapture(stream_, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); return false; }
+        gmode_ = 1; gkey_ = key;
+        return true;
+    }
+    bool graph_end() {
+        cudaSetDevice(device_);
+        if (gmode_ == 1) {
+            gmode_ = 0;
+            cudaGraph_t g = nullptr;
+            if (!ck(cudaStreamEndCapture(stream_, &g), "cudaStreamEndCapture")) return false;
+            cudaGraphExec_t e = nullptr;
+            const bool ok = ck(cudaGraphInstantiate(&e, g, 0), "cudaGraphInstantiate");
+            cudaGraphDestroy(g);
+            if (!ok) return false;
+            graphs_[gkey_] = e;
+            gexec_ = e;
+        } else if (gmode_ != 2) {
+            return true;
+        }
+        gmode_ = 0;
+        return ck(cudaGraphLaunch(gexec_, stream_), "cudaGraphLaunch");
+    }
+    void graph_abort() {
+        if (gmode_ == 1) {
+            cudaGraph_t g = nullptr;
+            cudaStreamEndCapture(stream_, &g);
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+        }
+        gmode_ = 0;
+    }
+    void graph_clear() {
+        if (device_ < 0) return;
+        cudaSetDevice(device_);
+        if (stream_) cudaStreamSynchronize(stream_);
+        for (auto &kv : graphs_) cudaGraphExecDestroy(kv.second);
+        graphs_.clear();
     }
 
     cudaStream_t stream() const { return stream_; }
@@ -270,6 +329,10 @@ private:
     cudaStream_t stream_ = nullptr;
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
     std::vector<std::pair<std::string, void *>> opened_;
+    int gmode_ = 0;                 // 0 direct, 1 capturing, 2 replaying
+    uint64_t gkey_ = 0;
+    cudaGraphExec_t gexec_ = nullptr;
+    std::unordered_map<uint64_t, cudaGraphExec_t> graphs_;
     static constexpr int kNamedEvents = 4;
     cudaEvent_t named_[kNamedEvents] = {nullptr, nullptr, nullptr, nullptr};
     static constexpr int kMaxMarks = 8192;

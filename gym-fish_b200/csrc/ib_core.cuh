@@ -446,6 +446,13 @@ public:
         return FG_OK;
     }
 
+    // what changes the IB launches of the next substep (CUDA-graph cache key, sim.hpp substep_key)
+    uint64_t graph_key() const {
+        uint64_t k = uint64_t(cur_) | (uint64_t(stage_next_) << 1) | (uint64_t(band_live_) << 2) | (uint64_t(n_ > 0) << 3);
+        k |= uint64_t(uint32_t(n_)) << 4;
+        k ^= (uint64_t(uint32_t(n_prev_)) * 0x9E3779B97F4A7C15ull) ^ (uint64_t(uint32_t(nl_)) << 40);
+        return k;
+    }
     ForceField force_view() const { return ForceField{cellslot_, bandF_, band_cap_, rowflag_}; }
     int after_collide(Dev &, std::string &) { return FG_OK; }   // the band stays readable until the next compute_forces
 

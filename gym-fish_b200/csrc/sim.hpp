@@ -164,6 +164,7 @@ public:
     }
 
     int set_solid(const uint8_t *g) {
+        dev.graph_clear();
         if (!g) {
             dev.free(solid_); solid_ = nullptr; L_.solid = nullptr;
             return FG_OK;
@@ -266,6 +267,7 @@ public:
         if (ranks && !peers_ && pending_faces_ > 0)
             return fail(FG_ESTATE, "halo exchange incomplete: unpack every internal face after fg_step");
         const bool prof = (cfg.flags & FG_FLAG_PROFILE) != 0;
+        const bool graphs = !prof && !(cfg.flags & FG_FLAG_NO_GRAPHS);
         dev.marks_reset();
         dev.tic();
         for (int it = 0; it < n; ++it) {
@@ -277,6 +279,15 @@ public:
                     f.advance(&action_[ao], ib_.wrench_ptr() + 6 * lo, ib_.origin_ptr() + 3 * lo);
                     lo += f.n_links(); ao += f.n_joints();
                 }
+            }
+            // The device work of one substep is a fixed sequence for a given (parity, IB counter, staging buffer,
+            // marker count): captured once into a CUDA graph and replayed afterwards (the host code below still runs
+            // on replay to advance its state, the device policy just does not enqueue).
+            struct Scope {
+                Dev &d; bool on; bool done = false;
+                ~Scope() { if (on && !done) d.graph_abort(); }
+            } scope{dev, graphs && dev.graph_begin(substep_key())};
+            if (!fish_.empty()) {
                 if (int rc = bodies_to_markers()) return rc;
             }
             ForceField F{};
@@ -287,7 +298,7 @@ public:
                 F = ib_.force_view();
             }
             const bool overlap = ranks && peers_ && !(cfg.flags & FG_FLAG_NO_OVERLAP) && L_.nz >= 4;
-            if (ranks && peers_ && !dev.wait_flags(flags_, has_lo_peer(), has_hi_peer(), tick_)) return cuda_fail();
+            if (ranks && peers_ && !dev.wait_flags(flags_, has_lo_peer(), has_hi_peer())) return cuda_fail();
             if (overlap) {
                 // boundary planes first, push halos over NVLink, then the interior hides the exchange
                 if (prof) dev.mark(0);
@@ -307,7 +318,11 @@ public:
                 if (int rc = ib_.after_collide(dev, err)) return rc;
             }
             parity_ ^= 1;
-            ++steps_; ++tick_;
+            ++steps_;
+            if (scope.on) {
+                scope.done = true;
+                if (!dev.graph_end()) return cuda_fail();
+            }
         }
         last_ms_ = dev.toc();
         if (!dev.sync()) return cuda_fail();
@@ -419,9 +434,15 @@ public:
         }
         peers_ = true;
         pending_faces_ = 0;
+        dev.graph_clear();
         return FG_OK;
     }
 
+    // everything that selects kernels or changes their arguments from one substep to the next
+    uint64_t substep_key() const {
+        uint64_t k = uint64_t(parity_) | (fish_.empty() ? 0u : 2u) | (uint64_t(ib_.ready() ? ib_.graph_key() : 0) << 2);
+        return k;
+    }
     int fail(int code, const std::string &m) { err = m; return code; }
     int cuda_fail() { err = dev.err; return FG_ECUDA; }
 
@@ -538,7 +559,7 @@ private:
         }
         if (peers_) {
             // publish "my halos of tick+1 are in your memory" to both neighbours
-            if (!dev.signal_flags(has_lo_peer() ? peer_flags_[0] + 1 : nullptr, has_hi_peer() ? peer_flags_[1] + 0 : nullptr, tick_ + 1))
+            if (!dev.signal_flags(flags_, has_lo_peer() ? peer_flags_[0] + 1 : nullptr, has_hi_peer() ? peer_flags_[1] + 0 : nullptr))
                 return false;
         }
         return true;
@@ -562,11 +583,11 @@ private:
     int nzl_ = 0;
     int parity_ = 0;
     int64_t steps_ = 0;
-    int tick_ = 0;                 // never reset: orders halo flags between neighbours
     double last_ms_ = 0, last_mlups_ = 0, collide_ms_ = 0, ib_ms_ = 0;
     int64_t collide_launches_ = 0, last_collide_launches_ = 0;
     uint8_t *solid_ = nullptr;
-    int *flags_ = nullptr;         // [0] written by my z-low neighbour, [1] by my z-high neighbour
+    int *flags_ = nullptr;         // [0] written by my z-low neighbour, [1] by my z-high neighbour, [2] my own halo
+                                   // counter (device-resident, never reset: orders pushes between neighbours), [3] timeout
     float *stage_[2] = {nullptr, nullptr};
     bool peers_ = false;
     float *peer_f_[2] = {nullptr, nullptr};

@@ -60,7 +60,8 @@ extern "C" {
 
 /* FgConfig.flags */
 #define FG_FLAG_NO_OVERLAP 1   /* multi-GPU: halo after the full-slab kernel (overlap off) */
-#define FG_FLAG_PROFILE    2   /* bracket every stream-collide launch with events -> FgStats.collide_ms */
+#define FG_FLAG_PROFILE    2   /* bracket every stream-collide launch with events -> FgStats.collide_ms (disables graphs) */
+#define FG_FLAG_NO_GRAPHS  4   /* launch every kernel directly instead of replaying per-substep CUDA graphs */
 
 typedef struct FgConfig {
     int32_t struct_size;      /* = sizeof(FgConfig); checked by fg_create */
@@ -157,6 +158,7 @@ int fg_get_markers(FgSim *sim, float *X, float *U, int32_t *link_id, int32_t cap
 int fg_step(FgSim *sim, int32_t n_substeps);       /* synchronous for wrenches/obs; fields stay on device */
 int fg_sync(FgSim *sim);
 int fg_get_stats(FgSim *sim, FgStats *out);
+int fg_set_flags(FgSim *sim, int32_t flags);        /* change FgConfig.flags (FG_FLAG_PROFILE, FG_FLAG_NO_GRAPHS, FG_FLAG_NO_OVERLAP) */
 
 /* ---- z-slab halos ----
  * host-staged form (works on both backends; used by the CPU gloo tests):

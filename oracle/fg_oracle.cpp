@@ -769,6 +769,12 @@ int fg_get_stats(FgSim *s, FgStats *o) {
     return FG_OK;
 }
 
+int fg_set_flags(FgSim *s, int32_t flags) {
+    if (!s) return FG_EINVAL;
+    s->cfg.flags = flags;
+    return FG_OK;
+}
+
 // ---- host-staged halos: ship post-collision f* of the boundary plane into the neighbour's ghost plane ----
 int64_t fg_halo_bytes(FgSim *s) { return s ? int64_t(5 * s->plane * sizeof(double)) : FG_EINVAL; }
 

@@ -67,12 +67,18 @@ public:
         return true;
     }
     void close_peers() {}
-    bool signal_flags(int *lo, int *hi, int value) {
+    bool graph_begin(uint64_t) { return false; }   // no graphs in the emulation: everything runs directly
+    bool graph_end() { return true; }
+    void graph_abort() {}
+    void graph_clear() {}
+    bool signal_flags(int *mine, int *lo, int *hi) {
+        const int value = ++mine[2];
         if (lo) *lo = value;
         if (hi) *hi = value;
         return true;
     }
-    bool wait_flags(const int *flags, bool lo, bool hi, int value) {
+    bool wait_flags(const int *flags, bool lo, bool hi) {
+        const int value = flags[2];
         if ((lo && flags[0] < value) || (hi && flags[1] < value)) {
             err = "host emulation: neighbour slab is behind (step the slabs in lock-step)";
             return false;
