@@ -24,6 +24,7 @@ BC_PERIODIC, BC_WALL, BC_INLET, BC_OUTLET = range(4)
 FLAG_NO_OVERLAP = 1
 FLAG_PROFILE = 2
 FLAG_NO_GRAPHS = 4
+FLAG_SPLIT_IB = 8
 
 _ERR_NAMES = {FG_EINVAL: "FG_EINVAL", FG_ENOMEM: "FG_ENOMEM", FG_ECUDA: "FG_ECUDA", FG_ESTATE: "FG_ESTATE",
               FG_ENOTSUP: "FG_ENOTSUP", FG_EPEER: "FG_EPEER"}
@@ -212,6 +213,8 @@ class Sim:
         self.nx, self.ny = self.cfg.nx, self.cfg.ny
         self.nz = self.cfg.nz // self.cfg.n_ranks   # local slab height
         self.shape = (self.nz, self.ny, self.nx)
+        self._counts = (0, 0)
+        self._wrench_buf = np.zeros((1, 6), dtype=np.float64)
 
     # -- plumbing --
     def _ck(self, rc: int):
@@ -274,18 +277,35 @@ class Sim:
         self._ck(self.lib.fg_set_solid(self.h, _ptr(s)))
 
     # -- immersed boundary --
+    @staticmethod
+    def _ready(a, dtype, shape):
+        return isinstance(a, np.ndarray) and a.dtype == dtype and a.flags.c_contiguous and a.shape == shape
+
     def set_markers(self, X, U, dV, link_id=None):
-        X = np.ascontiguousarray(X, dtype=np.float32).reshape(-1, 3)
-        n = X.shape[0]
-        U = np.ascontiguousarray(U, dtype=np.float32).reshape(n, 3)
-        dV = np.ascontiguousarray(np.broadcast_to(np.asarray(dV, dtype=np.float32), (n,)))
-        link = None if link_id is None else np.ascontiguousarray(link_id, dtype=np.int32).reshape(n)
-        self._ck(self.lib.fg_set_markers(self.h, n, _ptr(X), _ptr(U), _ptr(dV), _ptr(link)))
-        self._n_markers = n
+        n = len(X)
+        f32, i32 = np.float32, np.int32
+        if not (self._ready(X, f32, (n, 3)) and self._ready(U, f32, (n, 3)) and self._ready(dV, f32, (n,))
+                and (link_id is None or self._ready(link_id, i32, (n,)))):
+            # slow path: convert; callers in a hot loop pass float32/int32 C-contiguous arrays and skip this
+            X = np.ascontiguousarray(X, dtype=f32).reshape(-1, 3)
+            n = X.shape[0]
+            U = np.ascontiguousarray(U, dtype=f32).reshape(n, 3)
+            dV = np.ascontiguousarray(np.broadcast_to(np.asarray(dV, dtype=f32), (n,)))
+            link_id = None if link_id is None else np.ascontiguousarray(link_id, dtype=i32).reshape(n)
+        self._ck(self.lib.fg_set_markers(self.h, n, X.ctypes.data, U.ctypes.data, dV.ctypes.data,
+                                         None if link_id is None else link_id.ctypes.data))
+        if n != self._counts[0]:
+            self._refresh_counts()
 
     def set_link_origins(self, origins):
         o = np.ascontiguousarray(origins, dtype=np.float64).reshape(-1, 3)
         self._ck(self.lib.fg_set_link_origins(self.h, o.shape[0], _ptr(o)))
+        self._refresh_counts()
+
+    def _refresh_counts(self):
+        st = self.stats()
+        self._counts = (st.n_markers, st.n_links)
+        self._wrench_buf = np.zeros((max(st.n_links, 1), 6), dtype=np.float64)
 
     def stats(self) -> FgStats:
         st = FgStats()
@@ -293,26 +313,26 @@ class Sim:
         return st
 
     def get_index_map(self):
-        n = self.stats().n_markers
+        n = self._counts[0]
         base = np.empty((n, 3), dtype=np.int32)
         owner = np.empty((n,), dtype=np.int32)
         self._ck(self.lib.fg_get_index_map(self.h, base, owner))
         return base, owner
 
     def get_marker_forces(self) -> np.ndarray:
-        F = np.empty((self.stats().n_markers, 3), dtype=np.float32)
+        F = np.empty((self._counts[0], 3), dtype=np.float32)
         self._ck(self.lib.fg_get_marker_forces(self.h, F))
         return F
 
     def get_marker_velocities(self) -> np.ndarray:
-        U = np.empty((self.stats().n_markers, 3), dtype=np.float32)
+        U = np.empty((self._counts[0], 3), dtype=np.float32)
         self._ck(self.lib.fg_get_marker_velocities(self.h, U))
         return U
 
     def get_link_wrenches(self) -> np.ndarray:
-        w = np.zeros((max(self.stats().n_links, 1), 6), dtype=np.float64)
-        self._ck(self.lib.fg_get_link_wrenches(self.h, w))
-        return w[: self.stats().n_links]
+        """[n_links][6] hydrodynamic (force, torque) on each link; returns a view of a reused buffer."""
+        self._ck(self.lib.fg_get_link_wrenches(self.h, self._wrench_buf))
+        return self._wrench_buf[: self._counts[1]]
 
     def get_force_field(self) -> np.ndarray:
         F = np.empty((3,) + self.shape, dtype=np.float32)
@@ -323,6 +343,7 @@ class Sim:
     def add_fish(self, desc: FgFishDesc) -> int:
         fid = C.c_int32(-1)
         self._ck(self.lib.fg_add_fish(self.h, C.byref(desc), C.byref(fid)))
+        self._refresh_counts()
         return fid.value
 
     def action_size(self) -> int:

@@ -2,6 +2,7 @@
 // One non-blocking stream per handle, CUDA events for timing, CUDA-IPC / peer access for z-neighbours,
 // acquire/release flags in peer memory for the per-step neighbour hand-shake.
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include <cstdio>
@@ -19,6 +20,18 @@ namespace fg {
 template <class K, class P>
 __global__ void __launch_bounds__(K::kThreads, K::kMinBlocks) kern(const __grid_constant__ P p) {
     K::run(p, int(blockIdx.x), int(blockIdx.y), int(blockIdx.z), int(threadIdx.x));
+}
+
+// phased kernel: K::kPhases phases of grid-stride work separated by grid-wide barriers (cooperative launch)
+template <class K, class P>
+__global__ void __launch_bounds__(K::kThreads, K::kMinBlocks) kern_phased(const __grid_constant__ P p) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    for (int ph = 0; ph < K::kPhases; ++ph) {
+        const long long n = K::items(p, ph);
+        for (long long i = (long long)blockIdx.x * K::kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * K::kThreads)
+            K::item(p, ph, i);
+        if (ph + 1 < K::kPhases) grid.sync();
+    }
 }
 
 // neighbour hand-shake: one thread, system-scope release / acquire on a word in (peer) device memory
@@ -69,6 +82,8 @@ public:
                 "; this library is built for sm_100a only";
             return false;
         }
+        sm_count_ = prop.multiProcessorCount;
+        coop_ = prop.cooperativeLaunch != 0;
         bool ok = ck(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), "cudaStreamCreate") &&
                   ck(cudaEventCreate(&ev0_), "cudaEventCreate") && ck(cudaEventCreate(&ev1_), "cudaEventCreate");
         if (!ok) e = err;
@@ -203,6 +218,25 @@ public:
         return ck(cudaGetLastError(), "kernel launch");
     }
 
+    bool supports_phased() const { return coop_; }
+    template <class K, class P>
+    bool launch_phased(long long max_items, const P &p) {
+        cudaSetDevice(device_);
+        ++launches;
+        if (gmode_ == 2) return true;
+        static thread_local int per_sm = 0;      // per kernel instantiation
+        if (per_sm == 0) {
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern_phased<K, P>, K::kThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+        }
+        long long want = (max_items + K::kThreads - 1) / K::kThreads;
+        const long long cap = (long long)per_sm * sm_count_;
+        if (want > cap) want = cap;
+        if (want < 1) want = 1;
+        void *args[] = {const_cast<P *>(&p)};
+        return ck(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(kern_phased<K, P>), dim3(unsigned(want)), dim3(K::kThreads), args, 0, stream_),
+                  "cooperative launch");
+    }
+
     // ---- z-neighbour lattices: same process => raw pointer (+ peer access); other process => CUDA IPC
     template <class Blob>
     bool export_peer(float *f, int *flags, Blob &b, std::string &e) {
@@ -329,6 +363,8 @@ private:
     cudaStream_t stream_ = nullptr;
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
     std::vector<std::pair<std::string, void *>> opened_;
+    int sm_count_ = 148;
+    bool coop_ = false;
     int gmode_ = 0;                 // 0 direct, 1 capturing, 2 replaying
     uint64_t gkey_ = 0;
     cudaGraphExec_t gexec_ = nullptr;

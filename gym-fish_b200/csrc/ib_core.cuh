@@ -301,6 +301,39 @@ struct IbClearBand {
     }
 };
 
+// The whole IB pipeline as ONE cooperative launch: the phases are the kernel bodies above, separated by grid-wide
+// barriers instead of kernel boundaries (6 launches of ~3-5 us each were a fifth of the step on the 256x128x128
+// workload).  Phase work counts are rounded up to whole CTAs so warps stay intact for the shuffle reductions.
+template <int PARITY>
+struct IbFused {
+    static constexpr int kThreads = 128;
+    static constexpr int kMinBlocks = 8;
+    static constexpr int kPhases = 6;
+    FG_HD static long long round_cta(long long n) { return (n + kThreads - 1) / kThreads * kThreads; }
+    FG_HD static long long items(const IbParams &p, int phase) {
+        const long long nodes = round_cta((long long)(p.n + kMarkersPerCta - 1) / kMarkersPerCta * kThreads);
+        switch (phase) {
+            case 0: { const int c = *p.band_count_next; return round_cta(c < p.band_cap ? c : p.band_cap); }
+            case 1: return nodes;
+            case 2: { const int c = *p.band_count; return round_cta((c < p.band_cap ? c : p.band_cap) > 0 ? (c < p.band_cap ? c : p.band_cap) : 1); }
+            case 3: { const long long w = round_cta(6ll * p.n_links); return nodes > w ? nodes : w; }
+            case 4: return nodes;
+            default: return round_cta(p.n);
+        }
+    }
+    FG_HD static void item(const IbParams &p, int phase, long long i) {
+        const int bx = int(i / kThreads), tx = int(i % kThreads);
+        switch (phase) {
+            case 0: IbClearBand::run(p, bx, 0, 0, tx); break;
+            case 1: IbIndexMark::run(p, bx, 0, 0, tx); break;
+            case 2: IbBandMoments<PARITY>::run(p, bx, 0, 0, tx); break;
+            case 3: IbInterpolate::run(p, bx, 0, 0, tx); break;
+            case 4: IbForceSpread::run(p, bx, 0, 0, tx); break;
+            default: IbLinkReduce::run(p, bx, 0, 0, tx); break;
+        }
+    }
+};
+
 // ---------------------------------------------------------------- host-side state
 // PCIe traffic per substep (BASELINE.json:5 (c)): one pinned H2D message [X 3n | U 3n | dV n | link n | origins 3L]
 // (32 B per marker) and one pinned D2H message [wrench 6L doubles | band counters], both asynchronous on the
@@ -317,6 +350,7 @@ public:
     int band_cells() const { return band_cells_; }
     const double *wrench_ptr() const { return h_out_; }
     const double *origin_ptr() const { return h_origin_.data(); }
+    void set_fused(bool on) { fused_ = on; }
     void clear_wrenches() { if (h_out_) std::fill(h_out_, h_out_ + 6 * size_t(maxl_), 0.0); }
 
     int create(Dev &dev, const FgConfig &cfg, const Lattice &L, std::string &err) {
@@ -425,18 +459,24 @@ public:
         cur_ ^= 1;                                            // this step's counter; the other one still holds the old size
         const IbParams p = params(L, C);
         bool ok = true;
-        if (band_live_) {
-            const int bound = int(std::min<long long>(band_cap_, (long long)kNodes * std::max(n_prev_, 1)));
-            ok = dev.template launch<IbClearBand>(Dim3x((bound + 127) / 128), p);
-        }
         const int nb = (n_ + kMarkersPerCta - 1) / kMarkersPerCta;
-        ok = ok && dev.template launch<IbIndexMark>(Dim3x(nb), p);
-        const int bound2 = int(std::min<long long>(band_cap_, (long long)kNodes * n_));
-        ok = ok && (parity == 0 ? dev.template launch<IbBandMoments<0>>(Dim3x((bound2 + 127) / 128), p)
-                                : dev.template launch<IbBandMoments<1>>(Dim3x((bound2 + 127) / 128), p));
-        ok = ok && dev.template launch<IbInterpolate>(Dim3x(std::max(nb, (6 * nl_ + 127) / 128)), p);
-        ok = ok && dev.template launch<IbForceSpread>(Dim3x(nb), p);
-        ok = ok && dev.template launch<IbLinkReduce>(Dim3x((n_ + 127) / 128), p);
+        if (fused_ && dev.supports_phased()) {
+            // upper bound of any phase's work, for the launch geometry (the kernel loops grid-stride)
+            const long long most = std::max<long long>((long long)nb * 128, std::min<long long>(band_cap_, (long long)kNodes * std::max(n_, n_prev_)));
+            ok = parity == 0 ? dev.template launch_phased<IbFused<0>>(most, p) : dev.template launch_phased<IbFused<1>>(most, p);
+        } else {
+            if (band_live_) {
+                const int bound = int(std::min<long long>(band_cap_, (long long)kNodes * std::max(n_prev_, 1)));
+                ok = dev.template launch<IbClearBand>(Dim3x((bound + 127) / 128), p);
+            }
+            ok = ok && dev.template launch<IbIndexMark>(Dim3x(nb), p);
+            const int bound2 = int(std::min<long long>(band_cap_, (long long)kNodes * n_));
+            ok = ok && (parity == 0 ? dev.template launch<IbBandMoments<0>>(Dim3x((bound2 + 127) / 128), p)
+                                    : dev.template launch<IbBandMoments<1>>(Dim3x((bound2 + 127) / 128), p));
+            ok = ok && dev.template launch<IbInterpolate>(Dim3x(std::max(nb, (6 * nl_ + 127) / 128)), p);
+            ok = ok && dev.template launch<IbForceSpread>(Dim3x(nb), p);
+            ok = ok && dev.template launch<IbLinkReduce>(Dim3x((n_ + 127) / 128), p);
+        }
         // results the host needs, queued right behind the IB kernels (not behind the collide that follows)
         ok = ok && dev.d2h_async(h_out_, dwrench_, sizeof(double) * 6 * maxl_) &&
              dev.d2h_async(reinterpret_cast<char *>(h_out_) + sizeof(double) * 6 * maxl_, band_count_, 2 * sizeof(int)) &&
@@ -448,7 +488,7 @@ public:
 
     // what changes the IB launches of the next substep (CUDA-graph cache key, sim.hpp substep_key)
     uint64_t graph_key() const {
-        uint64_t k = uint64_t(cur_) | (uint64_t(stage_next_) << 1) | (uint64_t(band_live_) << 2) | (uint64_t(n_ > 0) << 3);
+        uint64_t k = uint64_t(cur_) | (uint64_t(stage_next_) << 1) | (uint64_t(band_live_) << 2) | (uint64_t(n_ > 0) << 3) | (uint64_t(fused_) << 36);
         k |= uint64_t(uint32_t(n_)) << 4;
         k ^= (uint64_t(uint32_t(n_prev_)) * 0x9E3779B97F4A7C15ull) ^ (uint64_t(uint32_t(nl_)) << 40);
         return k;
@@ -512,7 +552,7 @@ private:
     int cur_ = 0, stage_next_ = 0, have_host_copy_ = 0;
     size_t msg_floats_ = 0;
     int per_[3] = {1, 1, 1};
-    bool band_live_ = false, forces_valid_ = false, wrench_fetched_ = true;
+    bool band_live_ = false, forces_valid_ = false, wrench_fetched_ = true, fused_ = true;
     bool stage_used_[2] = {false, false};
     float *dmsg_ = nullptr, *dF_ = nullptr, *dUs_ = nullptr, *band_u_ = nullptr, *bandF_ = nullptr;
     int *dbase_ = nullptr, *downer_ = nullptr, *cellslot_ = nullptr, *band_cell_ = nullptr, *band_count_ = nullptr;

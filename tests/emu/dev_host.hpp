@@ -53,6 +53,18 @@ public:
         return true;
     }
 
+    // phased kernels (one cooperative launch on the GPU): phases in order, every item of a phase before the next
+    bool supports_phased() const { return true; }
+    template <class K, class P>
+    bool launch_phased(long long, const P &p) {
+        ++launches;
+        for (int ph = 0; ph < K::kPhases; ++ph) {
+            const long long n = K::items(p, ph);
+            for (long long i = 0; i < n; ++i) K::item(p, ph, i);
+        }
+        return true;
+    }
+
     // peers: only same-process handles (raw pointers) — lets the CPU tests run two slabs in one process
     template <class Blob>
     bool export_peer(float *f, int *flags, Blob &b, std::string &) {
