@@ -24,7 +24,7 @@ BC_PERIODIC, BC_WALL, BC_INLET, BC_OUTLET = range(4)
 FLAG_NO_OVERLAP = 1
 FLAG_PROFILE = 2
 FLAG_NO_GRAPHS = 4
-FLAG_SPLIT_IB = 8
+FLAG_FUSED_IB = 8
 
 _ERR_NAMES = {FG_EINVAL: "FG_EINVAL", FG_ENOMEM: "FG_ENOMEM", FG_ECUDA: "FG_ECUDA", FG_ESTATE: "FG_ESTATE",
               FG_ENOTSUP: "FG_ENOTSUP", FG_EPEER: "FG_EPEER"}

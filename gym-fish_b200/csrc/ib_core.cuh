@@ -552,7 +552,7 @@ private:
     int cur_ = 0, stage_next_ = 0, have_host_copy_ = 0;
     size_t msg_floats_ = 0;
     int per_[3] = {1, 1, 1};
-    bool band_live_ = false, forces_valid_ = false, wrench_fetched_ = true, fused_ = true;
+    bool band_live_ = false, forces_valid_ = false, wrench_fetched_ = true, fused_ = false;
     bool stage_used_[2] = {false, false};
     float *dmsg_ = nullptr, *dF_ = nullptr, *dUs_ = nullptr, *band_u_ = nullptr, *bandF_ = nullptr;
     int *dbase_ = nullptr, *downer_ = nullptr, *cellslot_ = nullptr, *band_cell_ = nullptr, *band_count_ = nullptr;

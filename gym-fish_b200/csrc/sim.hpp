@@ -293,7 +293,7 @@ public:
             ForceField F{};
             if (ib_.ready() && ib_.n_markers() > 0) {
                 if (prof) dev.mark(1);
-                ib_.set_fused(!(cfg.flags & FG_FLAG_SPLIT_IB));
+                ib_.set_fused((cfg.flags & FG_FLAG_FUSED_IB) != 0);
                 if (int rc = ib_.compute_forces(dev, L_, C_, parity_, err)) return rc;
                 if (prof) dev.mark(1);
                 F = ib_.force_view();

@@ -61,7 +61,7 @@ extern "C" {
 /* FgConfig.flags */
 #define FG_FLAG_NO_OVERLAP 1   /* multi-GPU: halo after the full-slab kernel (overlap off) */
 #define FG_FLAG_PROFILE    2   /* bracket every stream-collide launch with events -> FgStats.collide_ms (disables graphs) */
-#define FG_FLAG_SPLIT_IB   8   /* run the IB phases as separate launches instead of one cooperative kernel */
+#define FG_FLAG_FUSED_IB   8   /* run the IB phases as ONE cooperative kernel with grid barriers (measured slower on B200: r1) */
 #define FG_FLAG_NO_GRAPHS  4   /* launch every kernel directly instead of replaying per-substep CUDA graphs */
 
 typedef struct FgConfig {

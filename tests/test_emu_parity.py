@@ -53,12 +53,12 @@ def test_set_get_populations_roundtrip_both_parities(g, emu):
         assert s.stats().parity == s.stats().steps % 2
 
 
-@pytest.mark.parametrize("split", [False, True])
-def test_immersed_boundary_prescribed_markers(g, emu, split):
-    """split=False: the IB pipeline as one phased (cooperative) kernel; True: one launch per phase."""
+@pytest.mark.parametrize("fused", [False, True])
+def test_immersed_boundary_prescribed_markers(g, emu, fused):
+    """fused=True: the IB pipeline as one phased (cooperative) kernel; False (default): one launch per phase."""
     P, Wl, IN, OUT = g.BC_PERIODIC, g.BC_WALL, g.BC_INLET, g.BC_OUTLET
     kw = dict(nx=20, ny=18, nz=24, tau=0.8, collision=g.MRT, max_markers=4000, max_links=4,
-              bc=[P, P, Wl, Wl, IN, OUT], inlet_u=[0, 0, 0.05], flags=g._abi.FLAG_SPLIT_IB if split else 0)
+              bc=[P, P, Wl, Wl, IN, OUT], inlet_u=[0, 0, 0.05], flags=g._abi.FLAG_FUSED_IB if fused else 0)
     # the second cloud wraps across periodic x and pokes through the y wall (nodes outside are dropped)
     X = np.concatenate([util.sphere_markers((10.3, 9.1, 8.2), 4.0, 200), util.sphere_markers((1.0, 16.5, 20.0), 3.0, 120)])
     U = np.zeros_like(X)
