@@ -7,7 +7,7 @@ A "step" is one lattice update of the whole domain (fused D3Q19 MRT stream-colli
 z-face operations).  Workload at N=1 is BASELINE.json configs[1]: MRT flow past a fixed sphere in a 256x128x128
 channel (z = flow axis, inlet/outlet on z, walls on y), the sphere an immersed boundary of ~1.8k markers.  At N>1
 every rank owns one such 256x128x128 slab with its own sphere (weak scaling, z-slab decomposition, halos pushed
-over NVLink by the library itself; torch.distributed is used only to exchange the 192-byte peer handles, for the
+over NVLink by the library itself; torch.distributed is used only to exchange the 320-byte peer handles, for the
 barriers and for the max over ranks).
 
 Printed JSON line: see the contract in the task statement; `value` is device-timed with inputs resident in HBM,
@@ -41,6 +41,9 @@ WORKLOADS = {
                     desc="D3Q19 MRT periodic box 512^3 per GPU (weak-scaling sweep, BASELINE.json configs[4])"),
     "box_512_ib": dict(nx=512, ny=512, nz=512, D=22.2, U=0.02, Re=0.0,
                        desc="D3Q19 MRT periodic box 512^3 per GPU with ~1e5 IB markers on 64 spheres (IB overhead, configs[4])"),
+    "school_1024x512x512": dict(nx=512, ny=512, nz=1024, D=0.0, U=0.0, Re=0.0, strong=True,
+                                desc="D3Q19 MRT tank 1024x512x512 (z swim axis), school of 16 five-link fish (~4e4 markers); "
+                                     "z-slabs across the ranks (strong scaling, BASELINE.json configs[3])"),
     "tank_512x256x256": dict(nx=256, ny=256, nz=512, D=0.0, U=0.0, Re=0.0,
                              desc="D3Q19 MRT tank 512x256x256 (z swim axis) with one 5-link fish, Gym substeps"),
 }
@@ -58,7 +61,7 @@ def sphere_markers(center, radius, n):
 def make_sim(g, backend, wl, rank, world, device, flags=0, nz_override=None):
     """Create one slab of the workload and put it in its initial state."""
     w = WORKLOADS[wl]
-    nzl = nz_override or w["nz"]
+    nzl = nz_override or (w["nz"] // world if w.get("strong") else w["nz"])
     kw = dict(nx=w["nx"], ny=w["ny"], nz=nzl * world, n_ranks=world, rank=rank, device=device, collision=g.MRT, flags=flags)
     markers = None
     if wl == "sphere_256x128x128":
@@ -83,6 +86,8 @@ def make_sim(g, backend, wl, rank, world, device, flags=0, nz_override=None):
             Xs.append(sphere_markers(c, R, n1)); links.append(np.full(n1, s_, np.int32)); origins.append(c)
         X = np.concatenate(Xs)
         markers = (X, np.zeros_like(X), np.full(len(X), 4 * np.pi * R * R / n1, np.float32), np.concatenate(links), np.array(origins))
+    elif wl == "school_1024x512x512":
+        kw.update(tau=0.6, bc=[g.BC_WALL] * 4 + [g.BC_PERIODIC] * 2, max_markers=49152, max_links=80)
     else:
         kw.update(tau=0.6, bc=[g.BC_WALL] * 4 + [g.BC_PERIODIC] * 2, max_markers=8192, max_links=8)
     sim = g.Sim(backend=backend, **kw)
@@ -97,6 +102,8 @@ def make_sim(g, backend, wl, rank, world, device, flags=0, nz_override=None):
     if markers is not None:
         sim.set_markers(*markers[:4])
         sim.set_link_origins(markers[4])
+    elif wl == "school_1024x512x512":
+        sim._school = True      # fish are added after the ranks are connected (they cross slab faces)
     elif wl == "tank_512x256x256" and rank == 0:
         d = g.FgFishDesc()
         d.n_links = 5
@@ -263,11 +270,27 @@ def main():
     if world > 1:
         handles = [None] * world
         dist.all_gather_object(handles, sim.peer_export())
-        per = wl in ("box_512", "box_512_ib", "tank_512x256x256")
+        per = wl in ("box_512", "box_512_ib", "tank_512x256x256", "school_1024x512x512")
         lo = handles[(rank - 1) % world] if (rank > 0 or per) else None
         hi = handles[(rank + 1) % world] if (rank < world - 1 or per) else None
-        sim.peer_connect(lo, hi)
-    cells_local = w["nx"] * w["ny"] * w["nz"]
+        if wl == "school_1024x512x512":
+            sim.peer_connect_all(handles)
+        else:
+            sim.peer_connect(lo, hi)
+    if wl == "school_1024x512x512":
+        # 4 x 2 x 2 school; heads placed so that bodies straddle slab faces (z = 512 at N=2) and the periodic wrap
+        for iz, zc in enumerate((200.0, 456.0, 712.0, 968.0)):
+            for yc in (128.0, 384.0):
+                for xc in (128.0, 384.0):
+                    d = g.FgFishDesc()
+                    d.n_links = 5
+                    for k, (length, rad) in enumerate([(28, 7), (24, 7), (22, 6), (20, 5), (18, 3.5)]):
+                        d.link_len[k], d.link_rad[k] = length, rad
+                    d.root_pos[0], d.root_pos[1], d.root_pos[2] = xc, yc, zc
+                    d.density_ratio, d.joint_gain, d.joint_limit, d.joint_rate_max, d.free_root = 1.0, 0.2, 0.5, 0.01, 1
+                    sim.add_fish(d)
+    nz_local = w["nz"] // world if w.get("strong") else w["nz"]
+    cells_local = w["nx"] * w["ny"] * nz_local
     cells_total = cells_local * world
 
     # ---- device-timed throughput: inputs resident in HBM, K steps in one call, CUDA events inside the library
@@ -332,24 +355,25 @@ def main():
                "h2d_bytes_per_step": int(sum(a.nbytes for a in pin)), "d2h_bytes_per_step": int(wr.nbytes + 4),
                "steps": k2, "call": "fg_set_markers + fg_step(1) + fg_get_link_wrenches per step, host buffers",
                "drag_Fz": float(wr[0, 2])}
-    elif wl == "tank_512x256x256":
+    elif wl in ("tank_512x256x256", "school_1024x512x512"):
         # the Gym loop: action down, 20 substeps, observation up (env steps/s)
         nsub = 20
-        act = np.zeros(sim.action_size(), np.float32) if rank == 0 else None
+        has_fish = sim.action_size() > 0
+        act = np.zeros(sim.action_size(), np.float32) if has_fish else None
         t0 = time.perf_counter()
         nenv = max(3, k2 // nsub)
         for i in range(nenv):
-            if rank == 0:
+            if has_fish:
                 act[:] = np.sin(0.3 * i + np.arange(act.size))
                 sim.set_action(act)
             sim.step(nsub)
-            if rank == 0:
+            if has_fish:
                 sim.get_obs()
         sim.sync()
         dt = time.perf_counter() - t0
         e2e = {"value": cells_total * nenv * nsub / dt / 1e6, "unit": "MLUPS", "env_steps_per_s": nenv / dt,
-               "substeps_per_env_step": nsub, "h2d_bytes_per_step": int(4 * (sim.action_size() if rank == 0 else 0)),
-               "d2h_bytes_per_step": int(4 * (sim.obs_size() if rank == 0 else 0)),
+               "substeps_per_env_step": nsub, "h2d_bytes_per_step": int(4 * sim.action_size()),
+               "d2h_bytes_per_step": int(4 * sim.obs_size()),
                "call": "env.step: fg_set_action + fg_step(20) + fg_get_obs"}
     else:
         # no per-step host input exists for a pure periodic box: the host-facing call is fg_step(1) + a stats read
@@ -389,9 +413,9 @@ def main():
     line = {
         "metric": "MLUPS (million lattice-cell updates per second), coupled D3Q19 MRT + IB step",
         "value": value, "unit": "MLUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if w.get("strong") else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": w["desc"], "name": wl, "grid_per_gpu_xyz": [w["nx"], w["ny"], w["nz"]], "ranks": world,
+        "config": {"workload": w["desc"], "name": wl, "grid_per_gpu_xyz": [w["nx"], w["ny"], nz_local], "ranks": world,
                    "markers_per_gpu": int(st.n_markers), "decomposition": "z-slabs, halos by peer stores over NVLink" if world > 1 else "single GPU",
                    "halo_overlap": not args.no_overlap, "cuda_graphs": not args.no_graphs,
                    "l2": f"populations {19 * 4 * cells_local / 1e6:.0f} MB per GPU > 126 MB L2, no flush needed"},

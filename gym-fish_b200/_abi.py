@@ -14,7 +14,7 @@ from typing import Optional
 
 import numpy as np
 
-FG_ABI_VERSION = 3
+FG_ABI_VERSION = 4
 Q = 19
 
 FG_OK, FG_EINVAL, FG_ENOMEM, FG_ECUDA, FG_ESTATE, FG_ENOTSUP, FG_EPEER = 0, -1, -2, -3, -4, -5, -6
@@ -88,7 +88,7 @@ class FgFishDesc(C.Structure):
 
 
 class FgPeerHandle(C.Structure):
-    _fields_ = [("bytes", C.c_ubyte * 192)]
+    _fields_ = [("bytes", C.c_ubyte * 320)]
 
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -139,6 +139,7 @@ SYMBOLS = [
     ("fg_halo_unpack", C.c_int, [_P, C.c_int32, C.c_void_p]),
     ("fg_peer_export", C.c_int, [_P, C.POINTER(FgPeerHandle)]),
     ("fg_peer_connect", C.c_int, [_P, C.POINTER(FgPeerHandle), C.POINTER(FgPeerHandle)]),
+    ("fg_peer_connect_all", C.c_int, [_P, C.POINTER(FgPeerHandle), C.c_int32]),
 ]
 
 _LIBS: dict = {}
@@ -405,6 +406,13 @@ class Sim:
             if b is None:
                 return None
             h = FgPeerHandle()
-            C.memmove(h.bytes, b, 192)
+            C.memmove(h.bytes, b, 320)
             return C.byref(h)
         self._ck(self.lib.fg_peer_connect(self.h, mk(zlo), mk(zhi)))
+
+    def peer_connect_all(self, handles):
+        """handles[r] = peer_export() of rank r, for every rank (immersed bodies may then cross slab faces)."""
+        arr = (FgPeerHandle * len(handles))()
+        for i, b in enumerate(handles):
+            C.memmove(arr[i].bytes, b, 320)
+        self._ck(self.lib.fg_peer_connect_all(self.h, arr, len(handles)))

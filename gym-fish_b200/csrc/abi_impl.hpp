@@ -214,6 +214,10 @@ int fg_peer_export(FgSim *s, FgPeerHandle *out) {
     if (!s || !out) return FG_EINVAL;
     FG_TRY return s->sim.peer_export(out); FG_CATCH(s)
 }
+int fg_peer_connect_all(FgSim *s, const FgPeerHandle *handles, int32_t n) {
+    if (!s || !handles) return FG_EINVAL;
+    FG_TRY return s->sim.peer_connect_all(handles, n); FG_CATCH(s)
+}
 int fg_peer_connect(FgSim *s, const FgPeerHandle *lo, const FgPeerHandle *hi) {
     if (!s) return FG_EINVAL;
     FG_TRY return s->sim.peer_connect(lo, hi); FG_CATCH(s)

@@ -60,6 +60,33 @@ __global__ void wait_kernel(int *flags, int lo, int hi, unsigned long long timeo
     }
 }
 
+// exchange counters between ranks (IB across slabs): value = my counter + 1
+struct CounterList { int *p[8]; };
+__global__ void signal_counters_kernel(int *mine, CounterList t, int bump) {
+    const int v = mine[0] + 1;
+    __threadfence_system();
+    for (int i = 0; i < 8; ++i)
+        if (t.p[i]) asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(t.p[i]), "r"(v) : "memory");
+    if (bump) mine[0] = v;
+}
+__global__ void wait_counters_kernel(int *mine, CounterList s, unsigned long long timeout_ns) {
+    const int v = mine[0] + 1;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    for (int i = 0; i < 8; ++i) {
+        if (!s.p[i]) continue;
+        for (;;) {
+            int x;
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(x) : "l"(s.p[i]) : "memory");
+            if (x >= v) break;
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+            if (t - t0 > timeout_ns) { mine[3] = 1; return; }
+            __nanosleep(200);
+        }
+    }
+}
+
 class CudaDev {
 public:
     std::string err;
@@ -85,6 +112,9 @@ public:
         sm_count_ = prop.multiProcessorCount;
         coop_ = prop.cooperativeLaunch != 0;
         bool ok = ck(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), "cudaStreamCreate") &&
+                  ck(cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking), "cudaStreamCreate") &&
+                  ck(cudaEventCreateWithFlags(&fork_ev_, cudaEventDisableTiming), "cudaEventCreate") &&
+                  ck(cudaEventCreateWithFlags(&join_ev_, cudaEventDisableTiming), "cudaEventCreate") &&
                   ck(cudaEventCreate(&ev0_), "cudaEventCreate") && ck(cudaEventCreate(&ev1_), "cudaEventCreate");
         if (!ok) e = err;
         return ok;
@@ -94,6 +124,10 @@ public:
         cudaSetDevice(device_);
         graph_clear();
         if (stream_) { cudaStreamSynchronize(stream_); cudaStreamDestroy(stream_); stream_ = nullptr; }
+        if (side_) { cudaStreamSynchronize(side_); cudaStreamDestroy(side_); side_ = nullptr; }
+        if (fork_ev_) cudaEventDestroy(fork_ev_);
+        if (join_ev_) cudaEventDestroy(join_ev_);
+        fork_ev_ = join_ev_ = nullptr;
         if (ev0_) cudaEventDestroy(ev0_);
         if (ev1_) cudaEventDestroy(ev1_);
         ev0_ = ev1_ = nullptr;
@@ -214,8 +248,24 @@ public:
         cudaSetDevice(device_);
         ++launches;
         if (gmode_ == 2) return true;   // replaying a captured substep
-        kern<K, P><<<dim3(g.x, g.y, g.z), K::kThreads, 0, stream_>>>(p);
+        kern<K, P><<<dim3(g.x, g.y, g.z), K::kThreads, 0, on_side_ ? side_ : stream_>>>(p);
         return ck(cudaGetLastError(), "kernel launch");
+    }
+    // fork_side(): launches go to a side stream that starts where the main stream is now; main_stream(): back to the
+    // main stream (the side work keeps running beside it); join_side(): the main stream waits for the side work.
+    // Inside a capture this becomes two parallel branches of the graph.
+    bool fork_side() {
+        if (gmode_ == 2) return true;
+        cudaSetDevice(device_);
+        on_side_ = true;
+        return ck(cudaEventRecord(fork_ev_, stream_), "fork record") && ck(cudaStreamWaitEvent(side_, fork_ev_, 0), "fork wait");
+    }
+    bool main_stream() { on_side_ = false; return true; }
+    bool join_side() {
+        on_side_ = false;
+        if (gmode_ == 2) return true;
+        cudaSetDevice(device_);
+        return ck(cudaEventRecord(join_ev_, side_), "join record") && ck(cudaStreamWaitEvent(stream_, join_ev_, 0), "join wait");
     }
 
     bool supports_phased() const { return coop_; }
@@ -239,21 +289,43 @@ public:
 
     // ---- z-neighbour lattices: same process => raw pointer (+ peer access); other process => CUDA IPC
     template <class Blob>
-    bool export_peer(float *f, int *flags, Blob &b, std::string &e) {
+    bool export_peer(float *f, int *flags, void *x, Blob &b, std::string &e) {
         cudaSetDevice(device_);
         b.pid = int(getpid()); b.device = device_;
-        b.f_ptr = reinterpret_cast<uint64_t>(f); b.flag_ptr = reinterpret_cast<uint64_t>(flags);
-        cudaIpcMemHandle_t h1, h2;
+        b.f_ptr = reinterpret_cast<uint64_t>(f); b.flag_ptr = reinterpret_cast<uint64_t>(flags); b.x_ptr = reinterpret_cast<uint64_t>(x);
+        cudaIpcMemHandle_t h1, h2, h3;
         static_assert(sizeof(h1) == 64, "cudaIpcMemHandle_t is 64 bytes");
         if (!ck(cudaIpcGetMemHandle(&h1, f), "cudaIpcGetMemHandle(lattice)") || !ck(cudaIpcGetMemHandle(&h2, flags), "cudaIpcGetMemHandle(flags)")) {
             e = err;
             return false;
         }
         std::memcpy(b.f_ipc, &h1, 64); std::memcpy(b.flag_ipc, &h2, 64);
+        if (x) {
+            if (!ck(cudaIpcGetMemHandle(&h3, x), "cudaIpcGetMemHandle(exchange)")) { e = err; return false; }
+            std::memcpy(b.x_ipc, &h3, 64);
+        }
         return true;
     }
+    bool signal_counters(int *mine, int *const *targets, int n, bool bump) {
+        cudaSetDevice(device_);
+        ++launches;
+        if (gmode_ == 2) return true;
+        CounterList t{};
+        for (int i = 0; i < n && i < 8; ++i) t.p[i] = targets ? targets[i] : nullptr;
+        signal_counters_kernel<<<1, 1, 0, stream_>>>(mine, t, bump ? 1 : 0);
+        return ck(cudaGetLastError(), "signal launch");
+    }
+    bool wait_counters(int *mine, int *const *sources, int n) {
+        cudaSetDevice(device_);
+        ++launches;
+        if (gmode_ == 2) return true;
+        CounterList s{};
+        for (int i = 0; i < n && i < 8; ++i) s.p[i] = sources[i];
+        wait_counters_kernel<<<1, 1, 0, stream_>>>(mine, s, 20ull * 1000ull * 1000ull * 1000ull);
+        return ck(cudaGetLastError(), "wait launch");
+    }
     template <class Blob>
-    bool open_peer(const Blob &b, float **f, int **flags, std::string &e) {
+    bool open_peer(const Blob &b, float **f, int **flags, void **x, std::string &e) {
         cudaSetDevice(device_);
         if (b.pid == int(getpid())) {
             if (b.device != device_) {
@@ -264,12 +336,17 @@ public:
                 if (rc != cudaSuccess && rc != cudaErrorPeerAccessAlreadyEnabled) { ck(rc, "cudaDeviceEnablePeerAccess"); e = err; return false; }
                 cudaGetLastError();
             }
-            *f = reinterpret_cast<float *>(b.f_ptr); *flags = reinterpret_cast<int *>(b.flag_ptr);
+            *f = reinterpret_cast<float *>(b.f_ptr); *flags = reinterpret_cast<int *>(b.flag_ptr); *x = reinterpret_cast<void *>(b.x_ptr);
             return true;
         }
         void *pf = open_ipc(b.f_ipc), *pg = open_ipc(b.flag_ipc);
         if (!pf || !pg) { e = err; return false; }
         *f = static_cast<float *>(pf); *flags = static_cast<int *>(pg);
+        *x = nullptr;
+        if (b.x_ptr) {
+            *x = open_ipc(b.x_ipc);
+            if (!*x) { e = err; return false; }
+        }
         return true;
     }
     void close_peers() {
@@ -363,6 +440,9 @@ private:
     cudaStream_t stream_ = nullptr;
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
     std::vector<std::pair<std::string, void *>> opened_;
+    cudaStream_t side_ = nullptr;
+    cudaEvent_t fork_ev_ = nullptr, join_ev_ = nullptr;
+    bool on_side_ = false;
     int sm_count_ = 148;
     bool coop_ = false;
     int gmode_ = 0;                 // 0 direct, 1 capturing, 2 replaying

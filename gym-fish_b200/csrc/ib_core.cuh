@@ -85,7 +85,17 @@ struct IbParams {
     const float *origin;         // [links][3] torque reference points
     double *wrench;              // [links][6]
     int n_links;
+    // ---- bodies crossing z-slab faces (n_ranks > 1, fg_peer_connect_all): see IbExchange below
+    int rank, n_ranks;           // n_ranks <= 1: no exchange
+    int cap, maxl;               // marker / link capacity (buffer strides)
+    int *xside;                  // [n] 0: stencil inside my slab (or not mine at all), 1: also in my z-low neighbour, 2: z-high
+    const int *xcounter;         // my exchange counter (device-resident, bumped once per IB step)
+    const float *ustar_in;       // mine: [2 sets][2 sides][cap][3] partial U* pushed by the z-low (side 0) / z-high (side 1) neighbour
+    float *peer_in_lo, *peer_in_hi;   // the same buffer of my z-low / z-high neighbour (peer memory) or nullptr
+    const double *wrench_all;    // mine: [2 sets][n_ranks][maxl][6] partial wrenches pushed by every rank
+    double *peer_wrench[8];      // wrench_all of every rank (peer memory; [rank] is my own)
 };
+constexpr int kMaxRanks = 8;
 
 // storage index of stencil node (a,b,c) of a marker with base (i0,j0,k0), or -1 when the node is outside
 FG_HD long long stencil_cell(const IbParams &p, int i0, int j0, int k0, int a, int b, int c) {
@@ -258,6 +268,7 @@ struct IbLinkReduce {
         const bool live = k < p.n;
         int l = live ? p.link[k] : -1;
         if (l >= p.n_links) l = -1;
+        if (live && p.n_ranks > 1 && p.owner[k] != p.rank) l = -1;   // across slabs every marker is reduced by its owner only
         double v[6] = {0, 0, 0, 0, 0, 0};
         if (l >= 0) {
             const double dV = p.dV[k];
@@ -298,6 +309,80 @@ struct IbClearBand {
         const long long idx = p.band_cell[pos];
         p.cellslot[idx] = 0;
         p.rowflag[idx / p.L.nx] = 0;
+    }
+};
+
+// ---------------------------------------------------------------- bodies across z-slab faces
+// Every rank holds the same marker list.  A 4-wide stencil spans at most two slabs: the partial sum U*_k of each rank
+// is pushed into the other rank's ustar_in (peer store over NVLink), double-buffered by the parity of the exchange
+// counter so that a rank one step ahead never overwrites what its neighbour still reads.  Link wrenches are reduced
+// by the marker's owner and all-gathered by peer stores, then summed in rank order, so the (replicated) host body
+// integrators of all ranks see bit-identical totals.
+FG_HD int marker_rank(const IbParams &p, int zplane) {
+    const int zg = wrap_or_skip(zplane, p.L.nzg, p.per_z != 0);
+    return zg < 0 ? -1 : zg / p.L.nz;
+}
+
+struct IbPushPartial {
+    static constexpr int kThreads = 128;
+    static constexpr int kMinBlocks = 4;
+    FG_HD static void run(const IbParams &p, int bx, int, int, int tx) {
+        const int k = bx * kThreads + tx;
+        if (k >= p.n) return;
+        const int k0 = p.base[3 * k + 2];
+        const int ra = marker_rank(p, k0), rb = marker_rank(p, k0 + 3);
+        int xs = 0;
+        if (ra != rb) {
+            if (rb == p.rank && ra >= 0) xs = 1;        // the lower part of the stencil lies in my z-low neighbour
+            else if (ra == p.rank && rb >= 0) xs = 2;   // the upper part lies in my z-high neighbour
+        }
+        p.xside[k] = xs;
+        const int set = (p.xcounter[0] + 1) & 1;
+        float *dst = xs == 1 ? p.peer_in_lo : (xs == 2 ? p.peer_in_hi : nullptr);
+        if (!dst) return;
+        const int side = xs == 1 ? 1 : 0;               // I am the receiver's z-high (1) or z-low (0) neighbour
+        float *q = dst + ((size_t)(set * 2 + side) * p.cap + k) * 3;
+        q[0] = p.Ustar[3 * k]; q[1] = p.Ustar[3 * k + 1]; q[2] = p.Ustar[3 * k + 2];
+    }
+};
+
+struct IbAddPartial {
+    static constexpr int kThreads = 128;
+    static constexpr int kMinBlocks = 4;
+    FG_HD static void run(const IbParams &p, int bx, int, int, int tx) {
+        const int k = bx * kThreads + tx;
+        if (k >= p.n) return;
+        const int xs = p.xside[k];
+        if (xs == 0) return;
+        const int set = (p.xcounter[0] + 1) & 1, side = xs == 1 ? 0 : 1;   // what my z-low (0) / z-high (1) neighbour sent
+        const float *q = p.ustar_in + ((size_t)(set * 2 + side) * p.cap + k) * 3;
+        p.Ustar[3 * k] += q[0]; p.Ustar[3 * k + 1] += q[1]; p.Ustar[3 * k + 2] += q[2];
+    }
+};
+
+struct IbPushWrench {
+    static constexpr int kThreads = 128;
+    static constexpr int kMinBlocks = 4;
+    FG_HD static void run(const IbParams &p, int bx, int, int, int tx) {
+        const int i = bx * kThreads + tx;
+        if (i >= 6 * p.n_links) return;
+        const int set = (p.xcounter[0] + 1) & 1;
+        const double v = p.wrench[i];
+        for (int r = 0; r < p.n_ranks; ++r)
+            if (p.peer_wrench[r]) p.peer_wrench[r][((size_t)(set * p.n_ranks + p.rank) * p.maxl) * 6 + i] = v;
+    }
+};
+
+struct IbSumWrench {
+    static constexpr int kThreads = 128;
+    static constexpr int kMinBlocks = 4;
+    FG_HD static void run(const IbParams &p, int bx, int, int, int tx) {
+        const int i = bx * kThreads + tx;
+        if (i >= 6 * p.n_links) return;
+        const int set = (p.xcounter[0] + 1) & 1;
+        double sum = 0.0;
+        for (int r = 0; r < p.n_ranks; ++r) sum += p.wrench_all[((size_t)(set * p.n_ranks + r) * p.maxl) * 6 + i];
+        p.wrench[i] = sum;
     }
 };
 
@@ -371,6 +456,13 @@ public:
         band_count_ = (int *)A(2 * sizeof(int));
         rowflag_ = (uint8_t *)A(size_t(L.nz + 2) * L.ny);
         dwrench_ = (double *)A(sizeof(double) * 6 * maxl_);
+        rank_ = cfg.rank; n_ranks_ = cfg.n_ranks;
+        if (cfg.n_ranks > 1) {
+            x_bytes_ = x_off_wrench() + sizeof(double) * 2 * size_t(cfg.n_ranks) * maxl_ * 6;
+            xbuf_ = (char *)A(x_bytes_);
+            dxside_ = (int *)A(sizeof(int) * cap_);
+            if (!xbuf_ || !dxside_) return FG_ENOMEM;
+        }
         for (int i = 0; i < 2; ++i) h_stage_[i] = (float *)dev.alloc_host(sizeof(float) * msg_floats_, err);
         h_out_ = (double *)dev.alloc_host(sizeof(double) * 6 * maxl_ + 2 * sizeof(int), err);
         if (!dmsg_ || !dbase_ || !downer_ || !dF_ || !dUs_ || !cellslot_ || !band_cell_ || !band_u_ || !bandF_ || !band_count_ ||
@@ -382,11 +474,25 @@ public:
     }
 
     void destroy(Dev &dev) {
-        void *ps[] = {dmsg_, dbase_, downer_, dF_, dUs_, cellslot_, band_cell_, band_u_, bandF_, band_count_, rowflag_, dwrench_};
+        void *ps[] = {dmsg_, dbase_, downer_, dF_, dUs_, cellslot_, band_cell_, band_u_, bandF_, band_count_, rowflag_, dwrench_, xbuf_, dxside_};
+        xbuf_ = nullptr; dxside_ = nullptr; xchg_ = false;
         for (void *p : ps) dev.free(p);
         dev.free_host(h_stage_[0]); dev.free_host(h_stage_[1]); dev.free_host(h_out_);
         h_stage_[0] = h_stage_[1] = nullptr; h_out_ = nullptr;
         cap_ = 0;
+    }
+
+    // ---- exchange across slab faces
+    size_t xbuf_bytes() const { return x_bytes_; }
+    void *xbuf() const { return xbuf_; }
+    bool exchange_on() const { return xchg_; }
+    // layout of the exchange buffer: [ints: 4 + kMaxRanks][ustar_in floats][wrench_all doubles]
+    static size_t x_off_ustar() { return 64; }
+    size_t x_off_wrench() const { return (x_off_ustar() + sizeof(float) * 2 * 2 * size_t(cap_) * 3 + 15) / 16 * 16; }
+    void enable_exchange(int rank, int n_ranks, void *lo_x, void *hi_x, void *const *all_x) {
+        rank_ = rank; n_ranks_ = n_ranks; xchg_ = true;
+        peer_lo_x_ = static_cast<char *>(lo_x); peer_hi_x_ = static_cast<char *>(hi_x);
+        for (int r = 0; r < kMaxRanks; ++r) peer_all_x_[r] = r < n_ranks ? static_cast<char *>(all_x[r]) : nullptr;
     }
 
     // origins: nullptr keeps the current torque reference points
@@ -451,6 +557,17 @@ public:
         p.band_count = band_count_ + cur_; p.band_count_next = band_count_ + (cur_ ^ 1);
         p.band_cap = band_cap_; p.rowflag = rowflag_;
         p.wrench = dwrench_; p.n_links = nl_;
+        p.rank = rank_; p.n_ranks = xchg_ ? n_ranks_ : 1; p.cap = cap_; p.maxl = maxl_;
+        if (xchg_) {
+            p.xside = dxside_;
+            p.xcounter = reinterpret_cast<const int *>(xbuf_);
+            p.ustar_in = reinterpret_cast<const float *>(xbuf_ + x_off_ustar());
+            p.peer_in_lo = peer_lo_x_ ? reinterpret_cast<float *>(peer_lo_x_ + x_off_ustar()) : nullptr;
+            p.peer_in_hi = peer_hi_x_ ? reinterpret_cast<float *>(peer_hi_x_ + x_off_ustar()) : nullptr;
+            p.wrench_all = reinterpret_cast<const double *>(xbuf_ + x_off_wrench());
+            for (int r = 0; r < kMaxRanks; ++r)
+                p.peer_wrench[r] = peer_all_x_[r] ? reinterpret_cast<double *>(peer_all_x_[r] + x_off_wrench()) : nullptr;
+        }
         return p;
     }
 
@@ -460,7 +577,7 @@ public:
         const IbParams p = params(L, C);
         bool ok = true;
         const int nb = (n_ + kMarkersPerCta - 1) / kMarkersPerCta;
-        if (fused_ && dev.supports_phased()) {
+        if (fused_ && !xchg_ && dev.supports_phased()) {
             // upper bound of any phase's work, for the launch geometry (the kernel loops grid-stride)
             const long long most = std::max<long long>((long long)nb * 128, std::min<long long>(band_cap_, (long long)kNodes * std::max(n_, n_prev_)));
             ok = parity == 0 ? dev.template launch_phased<IbFused<0>>(most, p) : dev.template launch_phased<IbFused<1>>(most, p);
@@ -474,8 +591,31 @@ public:
             ok = ok && (parity == 0 ? dev.template launch<IbBandMoments<0>>(Dim3x((bound2 + 127) / 128), p)
                                     : dev.template launch<IbBandMoments<1>>(Dim3x((bound2 + 127) / 128), p));
             ok = ok && dev.template launch<IbInterpolate>(Dim3x(std::max(nb, (6 * nl_ + 127) / 128)), p);
+            if (xchg_) {
+                // partial U* to the face neighbours, wait for theirs (counter value c+1 of this exchange)
+                int *mine = reinterpret_cast<int *>(xbuf_);
+                int *sig[2] = {peer_lo_x_ ? reinterpret_cast<int *>(peer_lo_x_) + 2 : nullptr,    // I am its z-high neighbour
+                               peer_hi_x_ ? reinterpret_cast<int *>(peer_hi_x_) + 1 : nullptr};   // I am its z-low neighbour
+                int *wt[2] = {peer_lo_x_ ? mine + 1 : nullptr, peer_hi_x_ ? mine + 2 : nullptr};
+                ok = ok && dev.template launch<IbPushPartial>(Dim3x((n_ + 127) / 128), p);
+                ok = ok && dev.signal_counters(mine, sig, 2, false) && dev.wait_counters(mine, wt, 2);
+                ok = ok && dev.template launch<IbAddPartial>(Dim3x((n_ + 127) / 128), p);
+            }
             ok = ok && dev.template launch<IbForceSpread>(Dim3x(nb), p);
             ok = ok && dev.template launch<IbLinkReduce>(Dim3x((n_ + 127) / 128), p);
+            if (xchg_) {
+                int *mine = reinterpret_cast<int *>(xbuf_);
+                int *sig[kMaxRanks], *wt[kMaxRanks];
+                for (int r = 0; r < kMaxRanks; ++r) {
+                    sig[r] = peer_all_x_[r] ? reinterpret_cast<int *>(peer_all_x_[r]) + 4 + rank_ : nullptr;
+                    wt[r] = peer_all_x_[r] ? mine + 4 + r : nullptr;
+                }
+                const int g6 = (6 * nl_ + 127) / 128;
+                ok = ok && dev.template launch<IbPushWrench>(Dim3x(g6), p);
+                ok = ok && dev.signal_counters(mine, sig, kMaxRanks, false) && dev.wait_counters(mine, wt, kMaxRanks);
+                ok = ok && dev.template launch<IbSumWrench>(Dim3x(g6), p);
+                ok = ok && dev.signal_counters(mine, nullptr, 0, true);   // bump my counter: this exchange is complete
+            }
         }
         // results the host needs, queued right behind the IB kernels (not behind the collide that follows)
         ok = ok && dev.d2h_async(h_out_, dwrench_, sizeof(double) * 6 * maxl_) &&
@@ -490,6 +630,7 @@ public:
     uint64_t graph_key() const {
         uint64_t k = uint64_t(cur_) | (uint64_t(stage_next_) << 1) | (uint64_t(band_live_) << 2) | (uint64_t(n_ > 0) << 3) | (uint64_t(fused_) << 36);
         k |= uint64_t(uint32_t(n_)) << 4;
+        k ^= uint64_t(xchg_) << 37;
         k ^= (uint64_t(uint32_t(n_prev_)) * 0x9E3779B97F4A7C15ull) ^ (uint64_t(uint32_t(nl_)) << 40);
         return k;
     }
@@ -550,6 +691,11 @@ private:
     static Dim3 Dim3x(int x) { Dim3 d; d.x = std::max(x, 1); return d; }
     int cap_ = 0, maxl_ = 1, n_ = 0, nl_ = 0, nl_origins_ = 0, n_prev_ = 0, band_cap_ = 0, band_cells_ = 0;
     int cur_ = 0, stage_next_ = 0, have_host_copy_ = 0;
+    int rank_ = 0, n_ranks_ = 1;
+    bool xchg_ = false;
+    size_t x_bytes_ = 0;
+    char *xbuf_ = nullptr, *peer_lo_x_ = nullptr, *peer_hi_x_ = nullptr, *peer_all_x_[kMaxRanks] = {};
+    int *dxside_ = nullptr;
     size_t msg_floats_ = 0;
     int per_[3] = {1, 1, 1};
     bool band_live_ = false, forces_valid_ = false, wrench_fetched_ = true, fused_ = false;

@@ -23,12 +23,14 @@ namespace fg {
 struct PeerBlob {
     uint64_t magic;
     int32_t pid, device;
-    uint64_t f_ptr, flag_ptr;      // valid inside the publishing process
-    unsigned char f_ipc[64], flag_ipc[64];
+    uint64_t f_ptr, flag_ptr, x_ptr;   // valid inside the publishing process (x: IB exchange buffer, may be 0)
+    unsigned char f_ipc[64], flag_ipc[64], x_ipc[64];
     int32_t nx, ny, nz;
+    int32_t rank, n_ranks;
+    uint64_t x_bytes;
 };
 static_assert(sizeof(PeerBlob) <= sizeof(FgPeerHandle), "PeerBlob must fit the ABI blob");
-constexpr uint64_t kPeerMagic = 0x4647504545523033ull;   // "FGPEER03"
+constexpr uint64_t kPeerMagic = 0x4647504545523034ull;   // "FGPEER04"
 
 template <class Dev>
 class SimT {
@@ -199,12 +201,12 @@ public:
     int set_markers(int n, const float *X, const float *U, const float *dV, const int32_t *link) {
         if (n > cfg.max_markers) return fail(FG_EINVAL, "more markers than FgConfig.max_markers");
         if (!fish_.empty()) return fail(FG_ESTATE, "markers are generated by fish bodies on this handle");
-        if (cfg.n_ranks > 1) {
-            // no marker exchange between slabs yet: every 4-wide stencil must lie inside this rank's planes
+        if (cfg.n_ranks > 1 && !ib_.exchange_on()) {
+            // without fg_peer_connect_all there is no marker exchange: every 4-wide stencil must lie inside this rank's planes
             for (int k = 0; k < n; ++k) {
                 const int k0 = int(std::floor(X[3 * k + 2])) - 1;
                 if (k0 < L_.z0 || k0 + 3 >= L_.z0 + L_.nz)
-                    return fail(FG_ENOTSUP, "a marker stencil crosses a z-slab face: immersed boundary across slabs is not supported yet");
+                    return fail(FG_ENOTSUP, "a marker stencil crosses a z-slab face: connect all ranks with fg_peer_connect_all first");
             }
         }
         if (n > 0 && !ib_.ready()) return fail(FG_ESTATE, "FgConfig.max_markers was 0 at create");
@@ -225,7 +227,8 @@ public:
     }
 
     int add_fish(const FgFishDesc &d, int32_t *id) {
-        if (cfg.n_ranks > 1) return fail(FG_ENOTSUP, "bodies across z-slabs are not supported yet");
+        if (cfg.n_ranks > 1 && !ib_.exchange_on())
+            return fail(FG_ENOTSUP, "bodies on z-slabs: connect all ranks with fg_peer_connect_all first (and add the same fish on every rank)");
         if (!ib_.ready()) return fail(FG_ESTATE, "FgConfig.max_markers was 0 at create");
         Fish f;
         if (!f.init(d, err)) return FG_EINVAL;
@@ -290,6 +293,9 @@ public:
             if (!fish_.empty()) {
                 if (int rc = bodies_to_markers()) return rc;
             }
+            // neighbours must have delivered the halos of the previous step before anything reads ghost planes
+            // (the IB band moments do, at odd parity)
+            if (ranks && peers_ && !dev.wait_flags(flags_, has_lo_peer(), has_hi_peer())) return cuda_fail();
             ForceField F{};
             if (ib_.ready() && ib_.n_markers() > 0) {
                 if (prof) dev.mark(1);
@@ -299,7 +305,6 @@ public:
                 F = ib_.force_view();
             }
             const bool overlap = ranks && peers_ && !(cfg.flags & FG_FLAG_NO_OVERLAP) && L_.nz >= 4;
-            if (ranks && peers_ && !dev.wait_flags(flags_, has_lo_peer(), has_hi_peer())) return cuda_fail();
             if (overlap) {
                 // boundary planes first, push halos over NVLink, then the interior hides the exchange
                 if (prof) dev.mark(0);
@@ -336,6 +341,10 @@ public:
             int timed_out = 0;
             if (!dev.d2h(&timed_out, flags_ + 3, sizeof(int))) return cuda_fail();
             if (timed_out) return fail(FG_EPEER, "timed out waiting for a z-neighbour's halo (ranks out of step?)");
+            if (ib_.exchange_on()) {
+                if (!dev.d2h(&timed_out, static_cast<int *>(ib_.xbuf()) + 3, sizeof(int))) return cuda_fail();
+                if (timed_out) return fail(FG_EPEER, "timed out waiting for another rank's marker / wrench exchange (ranks out of step?)");
+            }
         }
         if (ib_.ready() && ib_.n_markers() > 0) {
             if (int rc = ib_.fetch_wrenches(dev, err)) return rc;
@@ -413,7 +422,9 @@ public:
         PeerBlob b{};
         b.magic = kPeerMagic;
         b.nx = L_.nx; b.ny = L_.ny; b.nz = L_.nz;
-        if (!dev.export_peer(L_.f, flags_, b, err)) return FG_EPEER;
+        b.rank = cfg.rank; b.n_ranks = cfg.n_ranks;
+        b.x_bytes = ib_.ready() ? ib_.xbuf_bytes() : 0;
+        if (!dev.export_peer(L_.f, flags_, ib_.ready() ? ib_.xbuf() : nullptr, b, err)) return FG_EPEER;
         std::memset(out, 0, sizeof(*out));
         std::memcpy(out->bytes, &b, sizeof(b));
         return FG_OK;
@@ -431,10 +442,36 @@ public:
             std::memcpy(&b, hs[s]->bytes, sizeof(b));
             if (b.magic != kPeerMagic) return fail(FG_EPEER, "peer handle: bad magic");
             if (b.nx != L_.nx || b.ny != L_.ny || b.nz != L_.nz) return fail(FG_EPEER, "peer handle: slab geometry differs");
-            if (!dev.open_peer(b, &peer_f_[s], &peer_flags_[s], err)) return FG_EPEER;
+            void *x = nullptr;
+            if (!dev.open_peer(b, &peer_f_[s], &peer_flags_[s], &x, err)) return FG_EPEER;
         }
         peers_ = true;
         pending_faces_ = 0;
+        dev.graph_clear();
+        return FG_OK;
+    }
+
+    // handles of ALL ranks (indexed by rank): halos as in peer_connect, plus the IB exchange between slabs
+    int peer_connect_all(const FgPeerHandle *hs, int n) {
+        if (cfg.n_ranks < 2) return fail(FG_ESTATE, "fg_peer_connect_all needs n_ranks > 1");
+        if (n != cfg.n_ranks) return fail(FG_EINVAL, "pass one handle per rank");
+        if (n > kMaxRanks) return fail(FG_ENOTSUP, "at most 8 ranks");
+        const int lo = (cfg.rank - 1 + n) % n, hi = (cfg.rank + 1) % n;
+        if (int rc = peer_connect(internal_lo() ? hs + lo : nullptr, internal_hi() ? hs + hi : nullptr)) return rc;
+        if (!ib_.ready()) return FG_OK;
+        if (L_.nz < 4) return fail(FG_EINVAL, "bodies across slabs need at least 4 planes per slab");
+        void *all[kMaxRanks] = {};
+        for (int r = 0; r < n; ++r) {
+            PeerBlob b;
+            std::memcpy(&b, hs[r].bytes, sizeof(b));
+            if (b.magic != kPeerMagic || b.rank != r || b.n_ranks != n) return fail(FG_EPEER, "peer handle: wrong rank order");
+            if (b.x_bytes != ib_.xbuf_bytes()) return fail(FG_EPEER, "peer handle: IB capacity (max_markers / max_links) differs between ranks");
+            if (r == cfg.rank) { all[r] = ib_.xbuf(); continue; }
+            float *f = nullptr; int *fl = nullptr;
+            if (!dev.open_peer(b, &f, &fl, &all[r], err)) return FG_EPEER;
+            if (!all[r]) return fail(FG_EPEER, "peer handle: rank has no IB exchange buffer");
+        }
+        ib_.enable_exchange(cfg.rank, n, internal_lo() ? all[lo] : nullptr, internal_hi() ? all[hi] : nullptr, all);
         dev.graph_clear();
         return FG_OK;
     }
@@ -503,17 +540,22 @@ private:
         const bool zlo_wall = L_.bc_zlo == BC_WALL && L_.z0 == 0, zhi_wall = L_.bc_zhi == BC_WALL && L_.z0 + L_.nz == L_.nzg;
         int zb = zz_begin, ze = zz_end;
         bool ok = true;
+        // The launches below touch disjoint cells, so the thin checked ones run on a forked side stream (parallel
+        // graph branches) while the bulk runs on the main stream.
+        const bool thin = (zlo_wall && zb <= 1 && 1 < ze) || (zhi_wall && zb <= L_.nz && L_.nz < ze) || (L_.wall_y && ny >= 2);
+        if (thin) ok = dev.fork_side();
         if (zlo_wall && zb <= 1 && 1 < ze) { ok = ok && launch_rows(CHECK_ALL, 1, 2, 0, 1, ny, F); zb = 2; }
         if (zhi_wall && zb <= L_.nz && L_.nz < ze) { ok = ok && launch_rows(CHECK_ALL, L_.nz, L_.nz + 1, 0, 1, ny, F); ze = L_.nz; }
         const int bulk = L_.wall_x ? CHECK_XEDGE : CHECK_NONE;
         if (L_.wall_y && ny >= 2) {
-            ok = ok && launch_rows(bulk, zb, ze, 1, 1, ny - 2, F);
             ok = ok && launch_rows(CHECK_ALL, zb, ze, 0, ny - 1, 2, F);
-        } else if (L_.wall_y) {
-            ok = ok && launch_rows(CHECK_ALL, zb, ze, 0, 1, ny, F);
+            if (thin) ok = ok && dev.main_stream();
+            ok = ok && launch_rows(bulk, zb, ze, 1, 1, ny - 2, F);
         } else {
-            ok = ok && launch_rows(bulk, zb, ze, 0, 1, ny, F);
+            if (thin) ok = ok && dev.main_stream();
+            ok = ok && launch_rows(L_.wall_y ? CHECK_ALL : bulk, zb, ze, 0, 1, ny, F);
         }
+        if (thin) ok = dev.join_side() && ok;
         return ok;
     }
 

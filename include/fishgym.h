@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FG_ABI_VERSION 3
+#define FG_ABI_VERSION 4
 #define FG_Q 19
 
 /* error codes */
@@ -116,8 +116,8 @@ typedef struct FgFishDesc {
 
 typedef struct FgSim FgSim;
 
-/* 64-byte opaque blob a rank publishes so that z-neighbours can map its lattice (CUDA IPC) */
-typedef struct FgPeerHandle { unsigned char bytes[192]; } FgPeerHandle;
+/* opaque blob a rank publishes so that other ranks can map its lattice, flags and IB exchange buffer (CUDA IPC) */
+typedef struct FgPeerHandle { unsigned char bytes[320]; } FgPeerHandle;
 
 int         fg_abi_version(void);
 const char *fg_backend_name(void);                 /* "cuda-sm100a" | "oracle-fp64" */
@@ -173,6 +173,10 @@ int fg_halo_pack(FgSim *sim, int32_t face /*FG_ZLO|FG_ZHI*/, void *buf);
 int fg_halo_unpack(FgSim *sim, int32_t face, const void *buf);
 int fg_peer_export(FgSim *sim, FgPeerHandle *out);
 int fg_peer_connect(FgSim *sim, const FgPeerHandle *zlo_neighbour, const FgPeerHandle *zhi_neighbour);
+/* all ranks' handles, indexed by rank: z-neighbours are derived from them, and immersed bodies may then cross slab
+ * faces (partial marker velocities go to the face neighbour, link wrenches are all-gathered, both by peer stores).
+ * Every rank must hold the same (replicated) marker list / fish. */
+int fg_peer_connect_all(FgSim *sim, const FgPeerHandle *handles, int32_t n_handles);
 
 #ifdef __cplusplus
 }

