@@ -113,6 +113,8 @@ def test_multi_gpu_fish_across_slab_faces(g, cuda, tmp_path):
     assert r.returncode == 0, r.stderr[-3000:]
     kw = dict(nx=24, ny=20, nz=24 * world, tau=0.8, max_markers=4000, max_links=8)
     whole = g.Sim(backend=cuda, **kw)
+    rho, u = util.smooth_fields(whole.shape)              # the workers start from the same moving fluid
+    whole.set_fields(rho, u)
     whole.add_fish(util.fish_desc(g, root=(12, 10, 17)))
     ref = []
     for it in range(4):
