@@ -87,7 +87,7 @@ def make_sim(g, backend, wl, rank, world, device, flags=0, nz_override=None):
         X = np.concatenate(Xs)
         markers = (X, np.zeros_like(X), np.full(len(X), 4 * np.pi * R * R / n1, np.float32), np.concatenate(links), np.array(origins))
     elif wl == "school_1024x512x512":
-        kw.update(tau=0.6, bc=[g.BC_WALL] * 4 + [g.BC_PERIODIC] * 2, max_markers=49152, max_links=80)
+        kw.update(tau=0.6, bc=[g.BC_WALL] * 4 + [g.BC_PERIODIC] * 2, max_markers=65536, max_links=80)
     else:
         kw.update(tau=0.6, bc=[g.BC_WALL] * 4 + [g.BC_PERIODIC] * 2, max_markers=8192, max_links=8)
     sim = g.Sim(backend=backend, **kw)
