@@ -127,3 +127,12 @@ def test_swimming_fish_matches_oracle_integrator(g, emu, free):
         assert abs(o[4]) + abs(o[6]) > 0                    # and the body did pick up momentum from the fluid
     a.reset(0); b.reset(0)
     assert np.array_equal(a.get_obs(), b.get_obs())
+
+
+def test_slab_larger_than_32bit_cell_index_is_rejected_before_allocating(g, emu):
+    """Maximum sizes: cell indices are 32-bit inside the kernels; a slab beyond 2^31 cells must be refused up front."""
+    with pytest.raises(g.FgError) as e:
+        g.Sim(backend=emu, nx=2048, ny=2048, nz=512)
+    assert e.value.code == g._abi.FG_EINVAL and "32-bit" in str(e.value)
+    with pytest.raises(g.FgError):
+        g.Sim(backend=emu, nx=8, ny=8, nz=1)          # a slab needs two planes
