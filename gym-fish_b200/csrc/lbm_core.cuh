@@ -90,7 +90,7 @@ struct StepParams {
     Lattice L;
     Collision C;
     ForceField F;
-    int zz_begin, zz_end;  // storage planes [zz_begin, zz_end) this launch covers
+    int zz_begin, zz_stride;  // planes this launch covers: zz = zz_begin + blockIdx.z * zz_stride
     int y0, ystride;       // rows this launch covers: y = y0 + blockIdx.y * ystride
     long long kz[Q][3];    // byte offset of (slot S, plane z-1 / z / z+1) from a cell of plane z: 4*(S*slot + dz*plane)
 };
@@ -498,7 +498,7 @@ struct StreamCollide {
     }
 
     FG_HD static void run(const StepParams &p, int bx, int by, int bz, int tx) {
-        const int x = bx * kThreads + tx, y = p.y0 + by * p.ystride, zz = p.zz_begin + bz;
+        const int x = bx * kThreads + tx, y = p.y0 + by * p.ystride, zz = p.zz_begin + bz * p.zz_stride;
         if (x >= p.L.nx) return;
         if (MODE == CHECK_ALL) checked_cell(p, x, y, zz);
         else if (MODE == CHECK_XEDGE) bulk_cell<true>(p, x, y, zz);

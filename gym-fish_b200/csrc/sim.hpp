@@ -308,7 +308,11 @@ public:
             if (overlap) {
                 // boundary planes first, push halos over NVLink, then the interior hides the exchange
                 if (prof) dev.mark(0);
-                if (!launch_collide(1, 2, F) || !launch_collide(L_.nz, L_.nz + 1, F)) return cuda_fail();
+                // both boundary planes in one launch (plane stride nz-1), unless one of them is a z-wall plane
+                const bool zwall = (L_.bc_zlo == BC_WALL && L_.z0 == 0) || (L_.bc_zhi == BC_WALL && L_.z0 + L_.nz == L_.nzg);
+                if (zwall) {
+                    if (!launch_collide(1, 2, F) || !launch_collide(L_.nz, L_.nz + 1, F)) return cuda_fail();
+                } else if (!launch_collide(1, L_.nz + 1, F, L_.nz - 1)) return cuda_fail();
                 if (prof) dev.mark(0);
                 if (!launch_faces()) return cuda_fail();
                 if (prof) dev.mark(0);
@@ -515,12 +519,12 @@ private:
         return cfg.collision == FG_MRT ? dev.template launch<StreamCollide<PARITY, true, MODE>>(g, p)
                                        : dev.template launch<StreamCollide<PARITY, false, MODE>>(g, p);
     }
-    bool launch_rows(int mode, int zb, int ze, int y0, int ystride, int rows, const ForceField &F) {
+    bool launch_rows(int mode, int zb, int ze, int y0, int ystride, int rows, const ForceField &F, int zstride = 1) {
         if (ze <= zb || rows <= 0) return true;
-        StepParams p{L_, C_, F, zb, ze, y0, ystride, {}};
+        StepParams p{L_, C_, F, zb, zstride, y0, ystride, {}};
         for (int s = 0; s < Q; ++s)
             for (int d = 0; d < 3; ++d) p.kz[s][d] = 4ll * (s * L_.slot + (long long)(d - 1) * L_.plane);
-        const Dim3 g{(L_.nx + 127) / 128, rows, ze - zb};
+        const Dim3 g{(L_.nx + 127) / 128, rows, (ze - zb + zstride - 1) / zstride};
         ++collide_launches_;
         if (parity_ == 0) {
             // the even step is purely local: only obstacles need the checked variant
@@ -533,10 +537,11 @@ private:
         }
     }
     // Partition planes [zz_begin, zz_end) so that boundary code only runs where a link can be blocked.
-    bool launch_collide(int zz_begin, int zz_end, const ForceField &F) {
+    // zstride > 1 covers planes zz_begin, zz_begin + zstride, ... (the two boundary planes of a slab in one launch)
+    bool launch_collide(int zz_begin, int zz_end, const ForceField &F, int zstride = 1) {
         if (zz_end <= zz_begin) return true;
         const int ny = L_.ny;
-        if (L_.solid || parity_ == 0) return launch_rows(CHECK_ALL, zz_begin, zz_end, 0, 1, ny, F);
+        if (L_.solid || parity_ == 0) return launch_rows(CHECK_ALL, zz_begin, zz_end, 0, 1, ny, F, zstride);
         const bool zlo_wall = L_.bc_zlo == BC_WALL && L_.z0 == 0, zhi_wall = L_.bc_zhi == BC_WALL && L_.z0 + L_.nz == L_.nzg;
         int zb = zz_begin, ze = zz_end;
         bool ok = true;
@@ -548,12 +553,12 @@ private:
         if (zhi_wall && zb <= L_.nz && L_.nz < ze) { ok = ok && launch_rows(CHECK_ALL, L_.nz, L_.nz + 1, 0, 1, ny, F); ze = L_.nz; }
         const int bulk = L_.wall_x ? CHECK_XEDGE : CHECK_NONE;
         if (L_.wall_y && ny >= 2) {
-            ok = ok && launch_rows(CHECK_ALL, zb, ze, 0, ny - 1, 2, F);
+            ok = ok && launch_rows(CHECK_ALL, zb, ze, 0, ny - 1, 2, F, zstride);
             if (thin) ok = ok && dev.main_stream();
-            ok = ok && launch_rows(bulk, zb, ze, 1, 1, ny - 2, F);
+            ok = ok && launch_rows(bulk, zb, ze, 1, 1, ny - 2, F, zstride);
         } else {
             if (thin) ok = ok && dev.main_stream();
-            ok = ok && launch_rows(L_.wall_y ? CHECK_ALL : bulk, zb, ze, 0, 1, ny, F);
+            ok = ok && launch_rows(L_.wall_y ? CHECK_ALL : bulk, zb, ze, 0, 1, ny, F, zstride);
         }
         if (thin) ok = dev.join_side() && ok;
         return ok;
