@@ -86,6 +86,7 @@ struct IbParams {
     double *wrench;              // [links][6]
     int n_links;
     // ---- bodies crossing z-slab faces (n_ranks > 1, fg_peer_connect_all): see IbExchange below
+    const int *gidx;             // [n] global marker id of local marker k (multi-rank culling), < 0: padding; nullptr: identity
     int rank, n_ranks;           // n_ranks <= 1: no exchange
     int cap, maxl;               // marker / link capacity (buffer strides)
     int *xside;                  // [n] 0: stencil inside my slab (or not mine at all), 1: also in my z-low neighbour, 2: z-high
@@ -153,7 +154,7 @@ struct IbIndexMark {
     static constexpr int kMinBlocks = 8;
     FG_HD static void run(const IbParams &p, int bx, int, int, int tx) {
         const int k = bx * kMarkersPerCta + tx / kNodes, node = tx % kNodes;
-        if (k >= p.n) return;
+        if (k >= p.n || (p.gidx && p.gidx[k] < 0)) return;
         const Lattice &L = p.L;
         const float X = p.X[3 * k], Y = p.X[3 * k + 1], Z = p.X[3 * k + 2];
         const int i0 = int(floorf(X)) - 1, j0 = int(floorf(Y)) - 1, k0 = int(floorf(Z)) - 1;
@@ -226,7 +227,7 @@ struct IbInterpolate {
         const int gt = bx * kThreads + tx;
         if (gt < 6 * p.n_links) p.wrench[gt] = 0.0;           // accumulated by IbLinkReduce
         const int k = bx * kMarkersPerCta + tx / kNodes, node = tx % kNodes;
-        if (k >= p.n) return;                                 // whole warps leave together (64 threads per marker)
+        if (k >= p.n || (p.gidx && p.gidx[k] < 0)) return;    // whole warps leave together (64 threads per marker)
         long long cell; int s;
         const float w = node_weight(p, k, node, cell, s);
         float u0 = 0.f, u1 = 0.f, u2 = 0.f;
@@ -245,7 +246,7 @@ struct IbForceSpread {
     static constexpr int kMinBlocks = 8;
     FG_HD static void run(const IbParams &p, int bx, int, int, int tx) {
         const int k = bx * kMarkersPerCta + tx / kNodes, node = tx % kNodes;
-        if (k >= p.n) return;
+        if (k >= p.n || (p.gidx && p.gidx[k] < 0)) return;
         const float f0 = 2.0f * (p.U[3 * k] - p.Ustar[3 * k]), f1 = 2.0f * (p.U[3 * k + 1] - p.Ustar[3 * k + 1]),
                     f2 = 2.0f * (p.U[3 * k + 2] - p.Ustar[3 * k + 2]);
         if (node == 0) { p.Fm[3 * k] = f0; p.Fm[3 * k + 1] = f1; p.Fm[3 * k + 2] = f2; }
@@ -265,7 +266,7 @@ struct IbLinkReduce {
     static constexpr int kMinBlocks = 4;
     FG_HD static void run(const IbParams &p, int bx, int, int, int tx) {
         const int k = bx * kThreads + tx;
-        const bool live = k < p.n;
+        const bool live = k < p.n && !(p.gidx && p.gidx[k] < 0);
         int l = live ? p.link[k] : -1;
         if (l >= p.n_links) l = -1;
         if (live && p.n_ranks > 1 && p.owner[k] != p.rank) l = -1;   // across slabs every marker is reduced by its owner only
@@ -329,6 +330,8 @@ struct IbPushPartial {
     FG_HD static void run(const IbParams &p, int bx, int, int, int tx) {
         const int k = bx * kThreads + tx;
         if (k >= p.n) return;
+        const int gk = p.gidx ? p.gidx[k] : k;               // exchange buffers are indexed by the GLOBAL marker id
+        if (gk < 0) { p.xside[k] = 0; return; }
         const int k0 = p.base[3 * k + 2];
         const int ra = marker_rank(p, k0), rb = marker_rank(p, k0 + 3);
         int xs = 0;
@@ -341,7 +344,7 @@ struct IbPushPartial {
         float *dst = xs == 1 ? p.peer_in_lo : (xs == 2 ? p.peer_in_hi : nullptr);
         if (!dst) return;
         const int side = xs == 1 ? 1 : 0;               // I am the receiver's z-high (1) or z-low (0) neighbour
-        float *q = dst + ((size_t)(set * 2 + side) * p.cap + k) * 3;
+        float *q = dst + ((size_t)(set * 2 + side) * p.cap + gk) * 3;
         q[0] = p.Ustar[3 * k]; q[1] = p.Ustar[3 * k + 1]; q[2] = p.Ustar[3 * k + 2];
     }
 };
@@ -354,8 +357,9 @@ struct IbAddPartial {
         if (k >= p.n) return;
         const int xs = p.xside[k];
         if (xs == 0) return;
+        const int gk = p.gidx ? p.gidx[k] : k;
         const int set = (p.xcounter[0] + 1) & 1, side = xs == 1 ? 0 : 1;   // what my z-low (0) / z-high (1) neighbour sent
-        const float *q = p.ustar_in + ((size_t)(set * 2 + side) * p.cap + k) * 3;
+        const float *q = p.ustar_in + ((size_t)(set * 2 + side) * p.cap + gk) * 3;
         p.Ustar[3 * k] += q[0]; p.Ustar[3 * k + 1] += q[1]; p.Ustar[3 * k + 2] += q[2];
     }
 };
@@ -430,7 +434,8 @@ public:
     enum { EV_STAGE0 = 0, EV_STAGE1 = 1, EV_WRENCH = 2 };
 
     bool ready() const { return cap_ > 0; }
-    int n_markers() const { return n_; }
+    int n_markers() const { return xchg_ ? n_total_ : n_; }
+    int n_local() const { return n_; }
     int n_links() const { return nl_; }
     int band_cells() const { return band_cells_; }
     const double *wrench_ptr() const { return h_out_; }
@@ -445,10 +450,12 @@ public:
         band_cap_ = int(std::min<long long>(64ll * cap_, (long long)L.plane * L.nz));
         per_[0] = cfg.bc[FG_XLO] == FG_BC_PERIODIC; per_[1] = cfg.bc[FG_YLO] == FG_BC_PERIODIC; per_[2] = cfg.bc[FG_ZLO] == FG_BC_PERIODIC;
         auto A = [&](size_t bytes) { void *p = dev.alloc(bytes, err); if (p && !dev.zero(p, bytes)) { err = dev.err; p = nullptr; } return p; };
-        msg_floats_ = 8 * size_t(cap_) + 3 * size_t(maxl_);
+        cap_pad_ = cfg.n_ranks > 1 ? (cap_ + kPad - 1) / kPad * kPad : cap_;
+        nzl_ = L.nz; nzg_ = L.nzg;
+        msg_floats_ = 9 * size_t(cap_pad_) + 3 * size_t(maxl_);
         dmsg_ = (float *)A(sizeof(float) * msg_floats_);
-        dbase_ = (int *)A(sizeof(int) * 3 * cap_); downer_ = (int *)A(sizeof(int) * cap_);
-        dF_ = (float *)A(sizeof(float) * 3 * cap_); dUs_ = (float *)A(sizeof(float) * 3 * cap_);
+        dbase_ = (int *)A(sizeof(int) * 3 * cap_pad_); downer_ = (int *)A(sizeof(int) * cap_pad_);
+        dF_ = (float *)A(sizeof(float) * 3 * cap_pad_); dUs_ = (float *)A(sizeof(float) * 3 * cap_pad_);
         cellslot_ = (int *)A(sizeof(int) * cells);
         band_cell_ = (int *)A(sizeof(int) * band_cap_);
         band_u_ = (float *)A(sizeof(float) * 3 * band_cap_);
@@ -460,7 +467,7 @@ public:
         if (cfg.n_ranks > 1) {
             x_bytes_ = x_off_wrench() + sizeof(double) * 2 * size_t(cfg.n_ranks) * maxl_ * 6;
             xbuf_ = (char *)A(x_bytes_);
-            dxside_ = (int *)A(sizeof(int) * cap_);
+            dxside_ = (int *)A(sizeof(int) * cap_pad_);
             if (!xbuf_ || !dxside_) return FG_ENOMEM;
         }
         for (int i = 0; i < 2; ++i) h_stage_[i] = (float *)dev.alloc_host(sizeof(float) * msg_floats_, err);
@@ -509,24 +516,55 @@ public:
             for (int i = 0; i < 3 * n_origins; ++i) h_origin_[i] = origins[i];
             nl_origins_ = n_origins;
         }
+        // multi-rank: keep only the markers whose 4-wide stencil touches this slab, padded to a multiple of kPad so that
+        // the launch geometry (and the CUDA-graph key) does not change every time a marker crosses a face
+        act_.clear();
+        if (xchg_) {
+            for (int k = 0; k < n; ++k) {
+                const int k0 = int(std::floor(X[3 * k + 2])) - 1;
+                if (slab_of(k0) == rank_ || slab_of(k0 + 3) == rank_) act_.push_back(k);
+            }
+        }
+        const int m = xchg_ ? int((act_.size() + kPad - 1) / kPad * kPad) : n;
+        if (m > cap_pad_) { err = "more markers than FgConfig.max_markers"; return FG_EINVAL; }
         // pack the message in a pinned staging buffer (double-buffered: wait for the copy issued two calls ago)
         const int sb = stage_next_;
         stage_next_ ^= 1;
         if (stage_used_[sb] && !dev.ev_sync(EV_STAGE0 + sb)) { err = dev.err; return FG_ECUDA; }
-        float *m = h_stage_[sb];
-        const size_t N = size_t(n);
-        if (n > 0) {
-            std::memcpy(m, X, sizeof(float) * 3 * N);
-            std::memcpy(m + 3 * N, U, sizeof(float) * 3 * N);
-            std::memcpy(m + 6 * N, dV, sizeof(float) * N);
-            if (link) std::memcpy(m + 7 * N, link, sizeof(int) * N);
-            else std::memset(m + 7 * N, 0, sizeof(int) * N);
+        float *msg = h_stage_[sb];
+        const size_t M = size_t(m);
+        if (!xchg_) {
+            if (n > 0) {
+                std::memcpy(msg, X, sizeof(float) * 3 * M);
+                std::memcpy(msg + 3 * M, U, sizeof(float) * 3 * M);
+                std::memcpy(msg + 6 * M, dV, sizeof(float) * M);
+                if (link) std::memcpy(msg + 7 * M, link, sizeof(int) * M);
+                else std::memset(msg + 7 * M, 0, sizeof(int) * M);
+            }
+        } else {
+            int *lk = reinterpret_cast<int *>(msg + 7 * M), *gi = reinterpret_cast<int *>(msg + 8 * M);
+            for (size_t j = 0; j < M; ++j) {
+                const bool real = j < act_.size();
+                const int k = real ? act_[j] : (act_.empty() ? 0 : act_[0]);
+                for (int d = 0; d < 3; ++d) {
+                    msg[3 * j + d] = n > 0 ? X[3 * k + d] : 0.f;
+                    msg[3 * M + 3 * j + d] = n > 0 ? U[3 * k + d] : 0.f;
+                }
+                msg[6 * M + j] = real ? dV[k] : 0.f;
+                lk[j] = real ? (link ? link[k] : 0) : -1;
+                gi[j] = real ? k : -1;
+            }
         }
-        for (size_t i = 0; i < 3 * size_t(maxl_); ++i) m[8 * N + i] = float(h_origin_[i]);
-        const size_t bytes = sizeof(float) * (8 * N + 3 * size_t(maxl_));
-        if (!dev.h2d_async(dmsg_, m, bytes) || !dev.ev_record(EV_STAGE0 + sb)) { err = dev.err; return FG_ECUDA; }
+        const size_t head = (xchg_ ? 9 : 8) * M;
+        for (size_t i = 0; i < 3 * size_t(maxl_); ++i) msg[head + i] = float(h_origin_[i]);
+        const size_t bytes = sizeof(float) * (head + 3 * size_t(maxl_));
+        if (!dev.h2d_async(dmsg_, msg, bytes) || !dev.ev_record(EV_STAGE0 + sb)) { err = dev.err; return FG_ECUDA; }
         stage_used_[sb] = true;
-        n_ = n;
+        n_ = m;
+        n_total_ = n;
+        if (xchg_) {        // host copy of the coordinates for the read-outs of markers this rank does not hold
+            hX_.assign(X, X + 3 * size_t(n));
+        }
         nl_ = std::max(nl, nl_origins_);
         forces_valid_ = false;
         have_host_copy_ = sb;
@@ -541,7 +579,7 @@ public:
         // rare path (prescribed markers): small synchronous upload behind the marker message
         std::vector<float> of(3 * size_t(maxl_));
         for (size_t i = 0; i < of.size(); ++i) of[i] = float(h_origin_[i]);
-        if (!dev.h2d(dmsg_ + 8 * size_t(n_), of.data(), sizeof(float) * of.size())) { err = dev.err; return FG_ECUDA; }
+        if (!dev.h2d(dmsg_ + (xchg_ ? 9 : 8) * size_t(n_), of.data(), sizeof(float) * of.size())) { err = dev.err; return FG_ECUDA; }
         return FG_OK;
     }
 
@@ -551,7 +589,8 @@ public:
         p.L = L; p.C = C; p.n = n_;
         p.per_x = per_[0]; p.per_y = per_[1]; p.per_z = per_[2];
         p.X = dmsg_; p.U = dmsg_ + 3 * N; p.dV = dmsg_ + 6 * N; p.link = reinterpret_cast<const int *>(dmsg_ + 7 * N);
-        p.origin = dmsg_ + 8 * N;
+        p.gidx = xchg_ ? reinterpret_cast<const int *>(dmsg_ + 8 * N) : nullptr;
+        p.origin = dmsg_ + (xchg_ ? 9 : 8) * N;
         p.base = dbase_; p.owner = downer_; p.Fm = dF_; p.Ustar = dUs_;
         p.cellslot = cellslot_; p.band_cell = band_cell_; p.band_u = band_u_; p.bandF = bandF_;
         p.band_count = band_count_ + cur_; p.band_count_next = band_count_ + (cur_ ^ 1);
@@ -649,13 +688,38 @@ public:
 
     // read-outs for tests and observations
     int get_index_map(Dev &dev, int32_t *base3, int32_t *owner, std::string &err) {
-        if (n_ == 0) return FG_OK;
-        if (!dev.sync() || !dev.d2h(base3, dbase_, sizeof(int) * 3 * n_) || !dev.d2h(owner, downer_, sizeof(int) * n_)) { err = dev.err; return FG_ECUDA; }
+        if (n_markers() == 0) return FG_OK;
+        if (!xchg_) {
+            if (!dev.sync() || !dev.d2h(base3, dbase_, sizeof(int) * 3 * n_) || !dev.d2h(owner, downer_, sizeof(int) * n_)) { err = dev.err; return FG_ECUDA; }
+            return FG_OK;
+        }
+        // culled: the device holds this rank's markers only; the map is pure integer arithmetic on the fp32 coordinates
+        // (same formula as IbIndexMark), so the others are filled in on the host and the held ones come from the device
+        for (int k = 0; k < n_total_; ++k) {
+            for (int d = 0; d < 3; ++d) base3[3 * k + d] = int(std::floor(hX_[3 * k + d])) - 1;
+            int kc = slab_plane(base3[3 * k + 2] + 1);
+            if (kc < 0) kc = base3[3 * k + 2] + 1 < 0 ? 0 : nzg_ - 1;
+            owner[k] = kc / nzl_;
+        }
+        std::vector<int> b(3 * size_t(n_)), o(n_);
+        if (!dev.sync() || !dev.d2h(b.data(), dbase_, sizeof(int) * 3 * n_) || !dev.d2h(o.data(), downer_, sizeof(int) * n_)) { err = dev.err; return FG_ECUDA; }
+        for (size_t j = 0; j < act_.size(); ++j) {
+            for (int d = 0; d < 3; ++d) base3[3 * act_[j] + d] = b[3 * j + d];
+            owner[act_[j]] = o[j];
+        }
         return FG_OK;
     }
     int get_marker_array(Dev &dev, bool forces, float *out, std::string &err) {
-        if (n_ == 0) return FG_OK;
-        if (!dev.sync() || !dev.d2h(out, forces ? dF_ : dUs_, sizeof(float) * 3 * n_)) { err = dev.err; return FG_ECUDA; }
+        if (n_markers() == 0) return FG_OK;
+        if (!xchg_) {
+            if (!dev.sync() || !dev.d2h(out, forces ? dF_ : dUs_, sizeof(float) * 3 * n_)) { err = dev.err; return FG_ECUDA; }
+            return FG_OK;
+        }
+        std::vector<float> loc(3 * size_t(n_));
+        if (!dev.sync() || !dev.d2h(loc.data(), forces ? dF_ : dUs_, sizeof(float) * 3 * n_)) { err = dev.err; return FG_ECUDA; }
+        std::fill(out, out + 3 * size_t(n_total_), 0.f);       // markers this rank does not hold read as zero
+        for (size_t j = 0; j < act_.size(); ++j)
+            for (int d = 0; d < 3; ++d) out[3 * act_[j] + d] = loc[3 * j + d];
         return FG_OK;
     }
     int get_force_field(Dev &dev, const Lattice &L, float *F, std::string &err) {
@@ -677,6 +741,10 @@ public:
         return FG_OK;
     }
     int get_markers(Dev &dev, float *X, float *U, int32_t *link, int cap, std::string &err) {
+        if (xchg_) {
+            if (cap > 0) { err = "fg_get_markers: not available with culled markers (fg_peer_connect_all); count only"; return cap >= n_total_ && !X && !U && !link ? n_total_ : FG_ENOTSUP; }
+            return n_total_;
+        }
         const int n = std::min(cap, n_);
         const size_t N = size_t(n_);
         bool ok = dev.sync();
@@ -690,6 +758,17 @@ public:
 private:
     static Dim3 Dim3x(int x) { Dim3 d; d.x = std::max(x, 1); return d; }
     int cap_ = 0, maxl_ = 1, n_ = 0, nl_ = 0, nl_origins_ = 0, n_prev_ = 0, band_cap_ = 0, band_cells_ = 0;
+    static constexpr int kPad = 512;
+    int slab_plane(int z) const {
+        if (z >= 0 && z < nzg_) return z;
+        if (!per_[2]) return -1;
+        z %= nzg_;
+        return z < 0 ? z + nzg_ : z;
+    }
+    int slab_of(int z) const { const int zg = slab_plane(z); return zg < 0 ? -1 : zg / nzl_; }
+    int cap_pad_ = 0, n_total_ = 0, nzl_ = 1, nzg_ = 1;
+    std::vector<int> act_;
+    std::vector<float> hX_;
     int cur_ = 0, stage_next_ = 0, have_host_copy_ = 0;
     int rank_ = 0, n_ranks_ = 1;
     bool xchg_ = false;
