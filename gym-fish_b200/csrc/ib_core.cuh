@@ -567,7 +567,6 @@ public:
         }
         nl_ = std::max(nl, nl_origins_);
         forces_valid_ = false;
-        have_host_copy_ = sb;
         return FG_OK;
     }
 
@@ -674,7 +673,6 @@ public:
         return k;
     }
     ForceField force_view() const { return ForceField{cellslot_, bandF_, band_cap_, rowflag_}; }
-    int after_collide(Dev &, std::string &) { return FG_OK; }   // the band stays readable until the next compute_forces
 
     int fetch_wrenches(Dev &dev, std::string &err) {
         if (!forces_valid_ || wrench_fetched_) return FG_OK;
@@ -769,7 +767,7 @@ private:
     int cap_pad_ = 0, n_total_ = 0, nzl_ = 1, nzg_ = 1;
     std::vector<int> act_;
     std::vector<float> hX_;
-    int cur_ = 0, stage_next_ = 0, have_host_copy_ = 0;
+    int cur_ = 0, stage_next_ = 0;
     int rank_ = 0, n_ranks_ = 1;
     bool xchg_ = false;
     size_t x_bytes_ = 0;

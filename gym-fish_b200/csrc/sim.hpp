@@ -141,9 +141,7 @@ public:
         const size_t n = size_t(L_.plane) * L_.nz;
         std::vector<float> h(n);
         for (int i = 0; i < Q; ++i) {
-            const float w = float(WD[i]);
             for (size_t k = 0; k < n; ++k) h[k] = float(double(f19[i * n + k]) - WD[i]);
-            (void)w;
             if (!dev.h2d(L_.f + i * L_.slot + L_.plane, h.data(), n * sizeof(float))) return cuda_fail();
         }
         parity_ = 0;
@@ -323,9 +321,6 @@ public:
                 if (!launch_collide(1, L_.nz + 1, F)) return cuda_fail();
                 if (prof) dev.mark(0);
                 if (!launch_faces()) return cuda_fail();
-            }
-            if (ib_.ready() && ib_.n_markers() > 0) {
-                if (int rc = ib_.after_collide(dev, err)) return rc;
             }
             parity_ ^= 1;
             ++steps_;
