@@ -397,7 +397,14 @@ def main():
     if collide_n > 0 and collide_ms > 0:
         # algorithmic bytes per launch = 152 B x cells the launch updates; averaged over the launches of the timed region
         achieved = BYTES_PER_CELL_UPDATE * cells_local * args.steps / (collide_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        traffic, traffic_src = None, None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[wl]
+            traffic, traffic_src = tj["dram_bytes_per_launch"], "profiles/r1_traffic.json (ncu --set full capture of this workload)"
+        except Exception:
+            pass
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": traffic_src, "algorithmic_bytes_per_launch": BYTES_PER_CELL_UPDATE * cells_local,
                 "kernel": "fg::StreamCollide<parity, MRT> (even+odd average)", "peak_source": peak_src,
                 "kernel_ms_per_step": collide_ms / args.steps, "launches_timed": int(collide_n),
                 "bytes_per_cell_update": BYTES_PER_CELL_UPDATE, "ib_ms_per_step": ib_ms / args.steps,

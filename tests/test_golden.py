@@ -76,3 +76,20 @@ def test_cuda_matches_golden(g, cuda, name):
 def test_cuda_ib_matches_golden(g, cuda):
     e = run_ib(g, cuda)
     assert e["u"] <= 1e-5 and e["rho"] <= 1e-5 and e["base"] and e["owner"] and e["wrench"] <= 1e-4 and e["Fm"] <= 1e-4
+
+
+def test_poiseuille_steady_state_fixture_is_a_fixed_point(g, emu):
+    """The converged NY = 128 Poiseuille column (oracle, wall-exact MRT rates) tiled into a thin slab: both the oracle
+    and the emulated fp32 kernels must keep the analytic parabola (the GPU test does the same at 256x128x128)."""
+    P, Wl = g.BC_PERIODIC, g.BC_WALL
+    gold = np.load(os.path.join(GOLD, "poiseuille_ny128.npz"))
+    gf = float(gold["gf"])
+    kw = dict(nx=6, ny=128, nz=3, tau=float(gold["tau"]), collision=g.MRT, bc=[P, P, Wl, Wl, P, P], body_force=[0, 0, gf],
+              mrt_rates=list(gold["rates"]))
+    for backend, tol in (("oracle", 3e-6), (emu, 1e-5)):      # the fixture itself went through a float32 interface
+        s = g.Sim(backend=backend, **kw)
+        s.set_populations(np.ascontiguousarray(np.broadcast_to(gold["f"][:, None, :, None], (19,) + s.shape), dtype=np.float32))
+        s.step(501)
+        _, uu = s.get_fields(f64=True)
+        assert util.rel_l2(uu[2].mean(axis=(0, 2)) + gf / 2, gold["analytic"]) <= tol
+        s.close()
