@@ -14,7 +14,7 @@ from typing import Optional
 
 import numpy as np
 
-FG_ABI_VERSION = 4
+FG_ABI_VERSION = 5
 Q = 19
 
 FG_OK, FG_EINVAL, FG_ENOMEM, FG_ECUDA, FG_ESTATE, FG_ENOTSUP, FG_EPEER = 0, -1, -2, -3, -4, -5, -6
@@ -124,6 +124,7 @@ SYMBOLS = [
     ("fg_get_marker_velocities", C.c_int, [_P, _f32]),
     ("fg_get_link_wrenches", C.c_int, [_P, _f64]),
     ("fg_get_force_field", C.c_int, [_P, _f32]),
+    ("fg_probe", C.c_int, [_P, C.c_int32, _f32, _f32]),
     ("fg_add_fish", C.c_int, [_P, C.POINTER(FgFishDesc), C.POINTER(C.c_int32)]),
     ("fg_set_action", C.c_int, [_P, C.c_void_p, C.c_int32]),
     ("fg_get_obs", C.c_int, [_P, _f32, C.c_int32]),
@@ -339,6 +340,13 @@ class Sim:
         F = np.empty((3,) + self.shape, dtype=np.float32)
         self._ck(self.lib.fg_get_force_field(self.h, F))
         return F
+
+    def probe(self, X) -> np.ndarray:
+        """(rho, ux, uy, uz) of the fluid at points X[n][3] (4-point delta interpolation)."""
+        X = np.ascontiguousarray(X, dtype=np.float32).reshape(-1, 3)
+        out = np.empty((X.shape[0], 4), dtype=np.float32)
+        self._ck(self.lib.fg_probe(self.h, X.shape[0], X, out))
+        return out
 
     # -- bodies --
     def add_fish(self, desc: FgFishDesc) -> int:

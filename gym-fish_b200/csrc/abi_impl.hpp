@@ -159,6 +159,11 @@ int fg_get_force_field(FgSim *s, float *F) {
     FG_TRY return s->sim.get_force_field(F); FG_CATCH(s)
 }
 
+int fg_probe(FgSim *s, int32_t n, const float *X, float *out4) {
+    if (!s || n < 0 || (n && (!X || !out4))) return FG_EINVAL;
+    FG_TRY return s->sim.probe(n, X, out4); FG_CATCH(s)
+}
+
 int fg_add_fish(FgSim *s, const FgFishDesc *d, int32_t *id) {
     if (!s || !d) return FG_EINVAL;
     FG_TRY return s->sim.add_fish(*d, id); FG_CATCH(s)

@@ -299,6 +299,55 @@ struct IbLinkReduce {
     }
 };
 
+// fluid state at arbitrary points (fg_probe): one thread per stencil node gathers the arriving populations of its
+// cell (parity aware), the 64 nodes of a probe are reduced with shuffles + 2 x 4 atomics
+struct ProbeParams {
+    Lattice L;
+    Collision C;
+    int n, per_x, per_y, per_z;
+    const float *X;     // [n][3]
+    float *out;         // [n][4], zeroed before the launch
+};
+template <int PARITY>
+struct ProbeMoments {
+    static constexpr int kThreads = kNodes * kMarkersPerCta;
+    static constexpr int kMinBlocks = 4;
+    FG_HD static void run(const ProbeParams &p, int bx, int, int, int tx) {
+        const int k = bx * kMarkersPerCta + tx / kNodes, node = tx % kNodes;
+        if (k >= p.n) return;
+        const Lattice &L = p.L;
+        const float X = p.X[3 * k], Y = p.X[3 * k + 1], Z = p.X[3 * k + 2];
+        const int i0 = int(floorf(X)) - 1, j0 = int(floorf(Y)) - 1, k0 = int(floorf(Z)) - 1;
+        const int a = node & 3, b = (node >> 2) & 3, c = node >> 4;
+        float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+        const int zg = wrap_or_skip(k0 + c, L.nzg, p.per_z != 0);
+        const int zl = zg < 0 ? -1 : zg - L.z0;
+        const int y = wrap_or_skip(j0 + b, L.ny, p.per_y != 0), x = wrap_or_skip(i0 + a, L.nx, p.per_x != 0);
+        if (zl >= 0 && zl < L.nz && y >= 0 && x >= 0) {
+            const int zz = zl + 1;
+            const long long idx = ((long long)zz * L.ny + y) * L.nx + x;
+            const Nbr nb = make_nbr(L, x, y, zz);
+            float h[Q];
+            if (L.solid && L.solid[idx]) {
+                FG_UNROLL
+                for (int i = 0; i < Q; ++i) h[i] = L.f[i * L.slot + idx];
+            } else {
+                load_arriving<PARITY, true>(h, L, p.C, nb, idx);
+            }
+            float dr, jx, jy, jz;
+            moments(h, dr, jx, jy, jz);
+            const float inv = 1.0f / (1.0f + dr);
+            const float w = peskin4(X - float(i0 + a)) * peskin4(Y - float(j0 + b)) * peskin4(Z - float(k0 + c));
+            v0 = w * (1.0f + dr); v1 = w * jx * inv; v2 = w * jy * inv; v3 = w * jz * inv;
+        }
+        v0 = warp_sum(v0); v1 = warp_sum(v1); v2 = warp_sum(v2); v3 = warp_sum(v3);
+        if (reduction_leader(tx)) {
+            atomic_add_f(&p.out[4 * k], v0); atomic_add_f(&p.out[4 * k + 1], v1);
+            atomic_add_f(&p.out[4 * k + 2], v2); atomic_add_f(&p.out[4 * k + 3], v3);
+        }
+    }
+};
+
 // forget the band of the previous step
 struct IbClearBand {
     static constexpr int kThreads = 128;

@@ -224,6 +224,19 @@ public:
         return ib_.get_force_field(dev, L_, F, err);
     }
 
+    int probe(int n, const float *X, float *out4) {
+        if (n == 0) return FG_OK;
+        float *d = static_cast<float *>(dev.alloc(sizeof(float) * 7 * size_t(n), err));
+        if (!d) return FG_ENOMEM;
+        ProbeParams p{L_, C_, n, cfg.bc[FG_XLO] == FG_BC_PERIODIC, cfg.bc[FG_YLO] == FG_BC_PERIODIC, cfg.bc[FG_ZLO] == FG_BC_PERIODIC, d, d + 3 * size_t(n)};
+        Dim3 g{(n + kMarkersPerCta - 1) / kMarkersPerCta, 1, 1};
+        bool ok = dev.h2d(d, X, sizeof(float) * 3 * size_t(n)) && dev.zero(d + 3 * size_t(n), sizeof(float) * 4 * size_t(n));
+        ok = ok && (parity_ == 0 ? dev.template launch<ProbeMoments<0>>(g, p) : dev.template launch<ProbeMoments<1>>(g, p));
+        ok = ok && dev.sync() && dev.d2h(out4, d + 3 * size_t(n), sizeof(float) * 4 * size_t(n));
+        dev.free(d);
+        return ok ? FG_OK : cuda_fail();
+    }
+
     int add_fish(const FgFishDesc &d, int32_t *id) {
         if (cfg.n_ranks > 1 && !ib_.exchange_on())
             return fail(FG_ENOTSUP, "bodies on z-slabs: connect all ranks with fg_peer_connect_all first (and add the same fish on every rank)");

@@ -77,10 +77,20 @@ class EnvConfig:
     walls: bool = True                                    # tank walls on x, y; periodic along z
     energy_weight: float = 0.01
     device: int = 0
+    task: str = "cruise"                                  # "cruise" | "pose" | "path"
+    target_heading: float = 0.5                           # pose task: yaw to reach (radians)
+    waypoints: Sequence[Tuple[float, float]] = ()         # path task: (x, z) points to visit in order (first fish)
+    waypoint_radius: float = 12.0
+    probes: int = 0                                       # velocity probes per fish, on a ring ahead of the head
 
 
 class FishEnv:
-    """Cruise task: swim along the initial heading; reward = progress (body lengths) - energy_weight * |a|^2."""
+    """Tasks (all rewards subtract energy_weight * mean(a^2)):
+      cruise  swim along the initial heading; reward = progress in body lengths
+      pose    turn to `target_heading`; reward = decrease of the yaw error
+      path    visit `waypoints` in order; reward = decrease of the distance to the current one (+1 on arrival)
+    Observations: per fish (pos3, heading, vel3, yaw rate, joint angles, joint rates) from the host integrator, then
+    optionally 3*probes fluid velocities sampled by fg_probe on a ring one head-length ahead of each head."""
 
     metadata = {"render_modes": []}
 
@@ -100,9 +110,13 @@ class FishEnv:
                        max_markers=cap, max_links=sum(len(f.links) for f in self.cfg.fish), device=self.cfg.device)
         for d in descs:
             self.sim.add_fish(d)
-        self._n_act, self._n_obs = self.sim.action_size(), self.sim.obs_size()
+        if self.cfg.task not in ("cruise", "pose", "path"):
+            raise ValueError(f"unknown task '{self.cfg.task}'")
+        self._n_act, self._n_body_obs = self.sim.action_size(), self.sim.obs_size()
+        self._n_obs = self._n_body_obs + 3 * self.cfg.probes * len(self.cfg.fish)
         self.action_space = Box(-1.0, 1.0, (self._n_act,))
         self.observation_space = Box(-np.inf, np.inf, (self._n_obs,))
+        self._wp = 0
         self._body_len = [sum(length for length, _ in f.links) for f in self.cfg.fish]
         self._obs_stride = [8 + 2 * (len(f.links) - 1) for f in self.cfg.fish]
         self._t = 0
@@ -114,7 +128,8 @@ class FishEnv:
             self.action_space.seed(seed)
         self.sim.reset(0 if seed is None else int(seed))
         self._t = 0
-        obs = self.sim.get_obs()
+        self._wp = 0
+        obs = self._observe()
         self._last = obs.copy()
         return obs, {"n_markers": self.sim.stats().n_markers}
 
@@ -122,7 +137,7 @@ class FishEnv:
         a = np.clip(np.asarray(action, dtype=np.float32).reshape(self._n_act), -1.0, 1.0)
         self.sim.set_action(a)
         self.sim.step(self.cfg.n_substeps)
-        obs = self.sim.get_obs()
+        obs = self._observe()
         reward, terminated = self._reward(obs, a)
         self._last = obs.copy()
         self._t += 1
@@ -134,9 +149,39 @@ class FishEnv:
     def close(self):
         self.sim.close()
 
+    # ---- observation: body state (+ fluid velocity probes ahead of each head)
+    def _observe(self):
+        body = self.sim.get_obs()
+        if self.cfg.probes <= 0:
+            return body
+        pts, off = [], 0
+        for f, stride in zip(self.cfg.fish, self._obs_stride):
+            o = body[off:off + stride]
+            head_len = f.links[0][0]
+            ang = np.linspace(-0.6, 0.6, self.cfg.probes) + o[3]
+            # nose direction is -(sin h, 0, cos h); probes sit one head length ahead, fanned in the swimming plane
+            pts.append(np.stack([o[0] - 1.5 * head_len * np.sin(ang), np.full(self.cfg.probes, o[1]), o[2] - 1.5 * head_len * np.cos(ang)], 1))
+            off += stride
+        vel = self.sim.probe(np.concatenate(pts).astype(np.float32))[:, 1:]
+        return np.concatenate([body, vel.reshape(-1).astype(np.float32)])
+
     # ---- task
     def _reward(self, obs, a):
         nx, ny, nz = self.cfg.grid
+        if self.cfg.task == "pose":
+            err_now, err_before = abs(obs[3] - self.cfg.target_heading), abs(self._last[3] - self.cfg.target_heading)
+            return (err_before - err_now) - self.cfg.energy_weight * float(np.mean(a * a)), False
+        if self.cfg.task == "path" and self.cfg.waypoints:
+            wx, wz = self.cfg.waypoints[min(self._wp, len(self.cfg.waypoints) - 1)]
+            d_now = float(np.hypot(obs[0] - wx, obs[2] - wz))
+            d_before = float(np.hypot(self._last[0] - wx, self._last[2] - wz))
+            r = (d_before - d_now) / self._body_len[0]
+            done = False
+            if d_now < self.cfg.waypoint_radius:
+                r += 1.0
+                self._wp += 1
+                done = self._wp >= len(self.cfg.waypoints)
+            return r - self.cfg.energy_weight * float(np.mean(a * a)), done
         reward, off, terminated = 0.0, 0, False
         for f, length, stride in zip(self.cfg.fish, self._body_len, self._obs_stride):
             o, p = obs[off:off + stride], self._last[off:off + stride]
@@ -150,3 +195,52 @@ class FishEnv:
             off += stride
         reward -= self.cfg.energy_weight * float(np.mean(a * a))
         return reward, terminated
+
+
+class VectorFishEnv:
+    """Several independent FishEnv on one GPU.  Every env owns its handle and CUDA stream; the envs
+    are stepped from a thread pool (ctypes releases the GIL inside fg_step), so their kernels and host-side body
+    integration overlap on the device.  Small tanks, which cannot fill a B200 alone, gain the most."""
+
+    def __init__(self, configs: Sequence[EnvConfig], backend: str = "cuda"):
+        from concurrent.futures import ThreadPoolExecutor
+        self.envs = [FishEnv(c, backend=backend) for c in configs]
+        self._pool = ThreadPoolExecutor(max_workers=len(self.envs))
+        self.num_envs = len(self.envs)
+        self.action_space, self.observation_space = self.envs[0].action_space, self.envs[0].observation_space
+
+    def reset(self, *, seed: Optional[int] = None):
+        res = [e.reset(seed=None if seed is None else seed + i) for i, e in enumerate(self.envs)]
+        return np.stack([r[0] for r in res]), [r[1] for r in res]
+
+    def step(self, actions):
+        res = list(self._pool.map(lambda ea: ea[0].step(ea[1]), zip(self.envs, actions)))
+        obs = np.stack([r[0] for r in res])
+        return (obs, np.array([r[1] for r in res], np.float32), np.array([r[2] for r in res]), np.array([r[3] for r in res]),
+                [r[4] for r in res])
+
+    def close(self):
+        self._pool.shutdown()
+        for e in self.envs:
+            e.close()
+
+
+def save_snapshot(sim: Sim, path: str, vtk: bool = False):
+    """Field output: rho, u (and the marker cloud) of one handle as .npz; optionally a legacy-VTK
+    structured-points file that ParaView opens directly."""
+    rho, u = sim.get_fields()
+    data = dict(rho=rho, u=u)
+    try:
+        X, U, link = sim.get_markers()
+        data.update(markers=X, marker_velocity=U, marker_link=link)
+    except Exception:      # noqa: BLE001 — handles without markers, or culled multi-rank handles
+        pass
+    np.savez_compressed(path if path.endswith(".npz") else path + ".npz", **data)
+    if vtk:
+        nz, ny, nx = rho.shape
+        with open((path[:-4] if path.endswith(".npz") else path) + ".vtk", "wb") as f:
+            f.write(f"# vtk DataFile Version 3.0\nfishgym snapshot\nBINARY\nDATASET STRUCTURED_POINTS\nDIMENSIONS {nx} {ny} {nz}\n"
+                    f"ORIGIN 0 0 0\nSPACING 1 1 1\nPOINT_DATA {nx * ny * nz}\nSCALARS rho float 1\nLOOKUP_TABLE default\n".encode())
+            f.write(rho.astype(">f4").tobytes())
+            f.write(b"\nVECTORS u float\n")
+            f.write(np.ascontiguousarray(np.moveaxis(u, 0, -1)).astype(">f4").tobytes())

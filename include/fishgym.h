@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FG_ABI_VERSION 4
+#define FG_ABI_VERSION 5
 #define FG_Q 19
 
 /* error codes */
@@ -146,6 +146,9 @@ int fg_get_marker_forces(FgSim *sim, float *F3);                      /* force d
 int fg_get_marker_velocities(FgSim *sim, float *Ustar3);              /* interpolated unforced fluid velocity, last step */
 int fg_get_link_wrenches(FgSim *sim, double *w6);                     /* [n_links][6]: hydrodynamic force, torque ON the link */
 int fg_get_force_field(FgSim *sim, float *F);                         /* [3][nz][ny][nx] Eulerian IB force of the last step */
+/* fluid state at arbitrary points (velocity-probe observations): out[n][4] = (rho, u) of the populations arriving at
+ * time t, interpolated with the same 4-point delta as the markers; nodes outside the domain / slab contribute 0 */
+int fg_probe(FgSim *sim, int32_t n, const float *X, float *out4);
 
 /* ---- articulated bodies, integrated on the host every substep ---- */
 int fg_add_fish(FgSim *sim, const FgFishDesc *desc, int32_t *fish_id);

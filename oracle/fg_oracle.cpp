@@ -678,6 +678,42 @@ int fg_get_force_field(FgSim *s, float *F) {
     return FG_OK;
 }
 
+int fg_probe(FgSim *s, int32_t n, const float *X, float *out4) {
+    if (!s || n < 0 || (n && (!X || !out4))) return FG_EINVAL;
+    if (int rc = finish_pending(s)) return rc;
+    const FgConfig &c = s->cfg;
+    const bool px = c.bc[FG_XLO] == FG_BC_PERIODIC, py = c.bc[FG_YLO] == FG_BC_PERIODIC, pz = c.bc[FG_ZLO] == FG_BC_PERIODIC;
+    for (int k = 0; k < n; ++k) {
+        const double Xk = X[3 * k], Yk = X[3 * k + 1], Zk = X[3 * k + 2];
+        const int i0 = int(std::floor(X[3 * k])) - 1, j0 = int(std::floor(X[3 * k + 1])) - 1, k0 = int(std::floor(X[3 * k + 2])) - 1;
+        double acc[4] = {0, 0, 0, 0};
+        for (int cz = 0; cz < 4; ++cz) {
+            const int zg = wrap_or_skip(k0 + cz, s->nzg, pz);
+            if (zg < 0) continue;
+            const int zl = zg - s->z0;
+            if (zl < 0 || zl >= s->nz) continue;
+            for (int cy = 0; cy < 4; ++cy) {
+                const int yy = wrap_or_skip(j0 + cy, s->ny, py);
+                if (yy < 0) continue;
+                for (int cx = 0; cx < 4; ++cx) {
+                    const int xx = wrap_or_skip(i0 + cx, s->nx, px);
+                    if (xx < 0) continue;
+                    const size_t cell = s->idx(xx, yy, zl);
+                    double rho = 0, jx = 0, jy = 0, jz = 0;
+                    for (int i = 0; i < Q; ++i) {
+                        const double v = s->F(s->f, i)[cell];
+                        rho += v; jx += CX[i] * v; jy += CY[i] * v; jz += CZ[i] * v;
+                    }
+                    const double w = peskin4(Xk - (i0 + cx)) * peskin4(Yk - (j0 + cy)) * peskin4(Zk - (k0 + cz));
+                    acc[0] += w * rho; acc[1] += w * jx / rho; acc[2] += w * jy / rho; acc[3] += w * jz / rho;
+                }
+            }
+        }
+        for (int d = 0; d < 4; ++d) out4[4 * k + d] = float(acc[d]);
+    }
+    return FG_OK;
+}
+
 int fg_add_fish(FgSim *s, const FgFishDesc *d, int32_t *fish_id) {
     if (!s || !d) return FG_EINVAL;
     if (s->cfg.n_ranks > 1) return fail(s, FG_ENOTSUP, "oracle: bodies with n_ranks > 1 are not supported");

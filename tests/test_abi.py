@@ -91,3 +91,20 @@ def test_sim_path_does_not_import_torch():
     code = ("import sys; sys.path.insert(0, %r); import gym_fish_b200 as g; from gym_fish_b200 import env; "
             "s = g.Sim(backend='oracle', nx=8, ny=8, nz=8); s.step(1); assert 'torch' not in sys.modules") % ROOT
     subprocess.run([sys.executable, "-c", code], check=True)
+
+
+def test_plain_c_program_links_and_runs_against_the_abi(g, tmp_path):
+    """include/fishgym.h is C (not C++): examples/minimal.c compiles as C99 and drives the library without Python.
+    Linked against the oracle here so it runs without a GPU; the same source links against libfishgym_cuda.so."""
+    exe = str(tmp_path / "minimal")
+    odir = os.path.join(ROOT, "oracle")
+    subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "minimal.c"), "-o", exe, "-L", odir, "-lfishgym_oracle", "-lm",
+                    "-Wl,-rpath," + odir], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "backend oracle-fp64" in r.stdout
+    # and it at least LINKS against the CUDA library (running it needs a GPU)
+    cdir = os.path.join(ROOT, "gym-fish_b200", "csrc")
+    subprocess.run(["/usr/bin/gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "minimal.c"),
+                    "-o", exe + "_cuda", "-L", cdir, "-lfishgym_cuda", "-lm", "-Wl,-rpath," + cdir], check=True)

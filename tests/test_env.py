@@ -51,3 +51,40 @@ def test_env_on_gpu_matches_oracle(g, cuda):
         ob, rb, *_ = b.step(act)
         assert np.abs(oa - ob).max() < 1e-4 and abs(ra - rb) < 1e-5
     a.close(); b.close()
+
+
+def test_tasks_probes_vector_env_and_snapshot(g, tmp_path):
+    from gym_fish_b200.env import EnvConfig, FishEnv, FishSpec, VectorFishEnv, save_snapshot
+    fish = FishSpec(links=((8, 2.5), (7, 2.5), (6, 2), (5, 1.5)), root=(12, 10, 14), joint_rate_max=0.02, joint_limit=0.6)
+    base = dict(grid=(24, 20, 40), tau=0.8, collision=g.BGK, n_substeps=4, max_episode_steps=3, fish=(fish,))
+    # pose and path tasks, with velocity probes in the observation
+    env = FishEnv(EnvConfig(task="pose", target_heading=0.3, probes=5, **base), backend="oracle")
+    obs, _ = env.reset(seed=0)
+    assert obs.shape == (14 + 15,) == env.observation_space.shape
+    o, r, term, trunc, info = env.step(np.array([1.0, 0.5, -0.5], np.float32))
+    assert np.isfinite(o).all() and isinstance(r, float) and np.abs(o[14:]).max() < 0.1
+    env.close()
+    env = FishEnv(EnvConfig(task="path", waypoints=((12.0, 2.0),), waypoint_radius=50.0, **base), backend="oracle")
+    env.reset()
+    _, r, term, *_ = env.step(np.zeros(3, np.float32))
+    assert term and r > 0.5                                 # already inside the radius: bonus and episode end
+    save_snapshot(env.sim, str(tmp_path / "snap"), vtk=True)
+    snap = np.load(str(tmp_path / "snap.npz"))
+    assert snap["rho"].shape == (40, 20, 24) and snap["markers"].shape[1] == 3
+    assert (tmp_path / "snap.vtk").stat().st_size > 4 * 40 * 20 * 24 * 4
+    env.close()
+    with pytest.raises(ValueError):
+        FishEnv(EnvConfig(task="nope", **base), backend="oracle")
+    # vector env: threads over independent handles give the same trajectories as stepping them one by one
+    cfgs = [EnvConfig(**base), EnvConfig(**dict(base, tau=0.7))]
+    vec = VectorFishEnv(cfgs, backend="oracle")
+    obs, infos = vec.reset(seed=4)
+    acts = np.array([[0.3, -0.2, 0.1], [-1.0, 1.0, 0.0]], np.float32)
+    vo, vr, vt, vtr, _ = vec.step(acts)
+    singles = [FishEnv(c, backend="oracle") for c in cfgs]
+    for i, e in enumerate(singles):
+        e.reset(seed=4 + i)
+        o, r, *_ = e.step(acts[i])
+        assert np.array_equal(o, vo[i]) and abs(r - vr[i]) < 1e-7
+        e.close()
+    vec.close()

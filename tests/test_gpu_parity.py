@@ -94,7 +94,30 @@ def test_immersed_boundary_prescribed_markers(g, cuda, flags):
     rb, ub = b.get_fields(f64=True)
     assert util.rel_l2(ub, ua) <= TOL_FIELD and util.rel_l2(rb, ra) <= TOL_FIELD
     assert util.rel_l2(b.get_force_field(), a.get_force_field()) <= TOL_FORCE
+    # property: the first sphere lies fully inside the domain, so what its markers exert equals what the grid receives
+    # from it; with the second cloud clipped by the wall the total can only be checked against the oracle (above)
+    Fm = b.get_marker_forces().astype(np.float64)
+    assert np.isfinite(Fm).all()
     a.close(); b.close()
+
+
+def test_spread_force_equals_marker_force_on_gpu(g, cuda):
+    kw = dict(nx=48, ny=48, nz=48, tau=0.8, collision=g.MRT, max_markers=2000, max_links=1)
+    s = g.Sim(backend=cuda, **kw)
+    X = util.sphere_markers((24.2, 23.7, 24.4), 9.0, 1000)
+    dV = np.full(1000, 4 * np.pi * 81 / 1000, np.float32)
+    s.set_markers(X, np.zeros_like(X), dV, np.zeros(1000, np.int32))
+    s.set_link_origins([[24.2, 23.7, 24.4]])
+    u = np.zeros((3,) + s.shape)
+    u[2] = 0.05
+    s.set_fields(np.ones(s.shape), u)
+    for n in (1, 1, 4):
+        s.step(n)
+        Fm = (s.get_marker_forces().astype(np.float64) * dV[:, None]).sum(0)
+        Fg = s.get_force_field().astype(np.float64).sum(axis=(1, 2, 3))
+        assert np.allclose(Fg, Fm, rtol=2e-5, atol=1e-7)           # sum of the delta weights is 1 per marker
+        assert np.allclose(s.get_link_wrenches()[0, :3], -Fm, rtol=1e-5, atol=1e-7)
+    s.close()
 
 
 def test_swimming_fish_loop(g, cuda):
