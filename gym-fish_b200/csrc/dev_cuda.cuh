@@ -22,6 +22,15 @@ __global__ void __launch_bounds__(K::kThreads, K::kMinBlocks) kern(const __grid_
     K::run(p, int(blockIdx.x), int(blockIdx.y), int(blockIdx.z), int(threadIdx.x));
 }
 
+// block-phased kernel: K::kBlockPhases phases separated by a CTA barrier
+template <class K, class P>
+__global__ void __launch_bounds__(K::kThreads, K::kMinBlocks) kern_bp(const __grid_constant__ P p) {
+    for (int ph = 0; ph < K::kBlockPhases; ++ph) {
+        K::run(p, int(blockIdx.x), int(blockIdx.y), int(blockIdx.z), int(threadIdx.x), ph);
+        if (ph + 1 < K::kBlockPhases) { __threadfence(); __syncthreads(); }   // phase results travel through L2 atomics
+    }
+}
+
 // phased kernel: K::kPhases phases of grid-stride work separated by grid-wide barriers (cooperative launch)
 template <class K, class P>
 __global__ void __launch_bounds__(K::kThreads, K::kMinBlocks) kern_phased(const __grid_constant__ P p) {
@@ -268,6 +277,14 @@ public:
         return ck(cudaEventRecord(join_ev_, side_), "join record") && ck(cudaStreamWaitEvent(stream_, join_ev_, 0), "join wait");
     }
 
+    template <class K, class P>
+    bool launch_block_phased(Dim3 g, const P &p) {
+        cudaSetDevice(device_);
+        ++launches;
+        if (gmode_ == 2) return true;
+        kern_bp<K, P><<<dim3(g.x, g.y, g.z), K::kThreads, 0, on_side_ ? side_ : stream_>>>(p);
+        return ck(cudaGetLastError(), "kernel launch");
+    }
     bool supports_phased() const { return coop_; }
     template <class K, class P>
     bool launch_phased(long long max_items, const P &p) {

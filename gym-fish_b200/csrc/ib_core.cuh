@@ -219,6 +219,14 @@ FG_HD float node_weight(const IbParams &p, int k, int node, long long &cell, int
     return peskin4(X - float(i0 + a)) * peskin4(Y - float(j0 + b)) * peskin4(Z - float(k0 + c));
 }
 
+FG_HD float ld_cg(const float *p) {
+#if defined(__CUDA_ARCH__)
+    return __ldcg(p);       // L2: the value was just produced by atomics of other warps of this CTA
+#else
+    return *p;
+#endif
+}
+
 // (a5) U*_k = sum over the 64 nodes of w u*: warp-reduced, 2 x 3 atomics per marker
 struct IbInterpolate {
     static constexpr int kThreads = kNodes * kMarkersPerCta;
@@ -247,8 +255,8 @@ struct IbForceSpread {
     FG_HD static void run(const IbParams &p, int bx, int, int, int tx) {
         const int k = bx * kMarkersPerCta + tx / kNodes, node = tx % kNodes;
         if (k >= p.n || (p.gidx && p.gidx[k] < 0)) return;
-        const float f0 = 2.0f * (p.U[3 * k] - p.Ustar[3 * k]), f1 = 2.0f * (p.U[3 * k + 1] - p.Ustar[3 * k + 1]),
-                    f2 = 2.0f * (p.U[3 * k + 2] - p.Ustar[3 * k + 2]);
+        const float f0 = 2.0f * (p.U[3 * k] - ld_cg(&p.Ustar[3 * k])), f1 = 2.0f * (p.U[3 * k + 1] - ld_cg(&p.Ustar[3 * k + 1])),
+                    f2 = 2.0f * (p.U[3 * k + 2] - ld_cg(&p.Ustar[3 * k + 2]));
         if (node == 0) { p.Fm[3 * k] = f0; p.Fm[3 * k + 1] = f1; p.Fm[3 * k + 2] = f2; }
         long long cell; int s;
         const float w = node_weight(p, k, node, cell, s) * p.dV[k];
@@ -256,6 +264,18 @@ struct IbForceSpread {
         atomic_add_f(&p.bandF[s], w * f0);
         atomic_add_f(&p.bandF[p.band_cap + s], w * f1);
         atomic_add_f(&p.bandF[2 * p.band_cap + s], w * f2);
+    }
+};
+
+// (a5-a7) in one launch: both phases of a marker run in the same CTA (2 markers x 64 nodes), so a CTA barrier between
+// them is all the ordering U*_k needs (single-rank path; across slabs the exchange sits between the two)
+struct IbInterpSpread {
+    static constexpr int kThreads = kNodes * kMarkersPerCta;
+    static constexpr int kMinBlocks = 8;
+    static constexpr int kBlockPhases = 2;
+    FG_HD static void run(const IbParams &p, int bx, int by, int bz, int tx, int phase) {
+        if (phase == 0) IbInterpolate::run(p, bx, by, bz, tx);
+        else IbForceSpread::run(p, bx, by, bz, tx);
     }
 };
 
@@ -490,6 +510,7 @@ public:
     const double *wrench_ptr() const { return h_out_; }
     const double *origin_ptr() const { return h_origin_.data(); }
     void set_fused(bool on) { fused_ = on; }
+    void set_reuse_static(bool on) { reuse_static_ = on; }
     void clear_wrenches() { if (h_out_) std::fill(h_out_, h_out_ + 6 * size_t(maxl_), 0.0); }
 
     int create(Dev &dev, const FgConfig &cfg, const Lattice &L, std::string &err) {
@@ -611,6 +632,7 @@ public:
         stage_used_[sb] = true;
         n_ = m;
         n_total_ = n;
+        markers_dirty_ = true;
         if (xchg_) {        // host copy of the coordinates for the read-outs of markers this rank does not hold
             hX_.assign(X, X + 3 * size_t(n));
         }
@@ -660,23 +682,34 @@ public:
 
     // SURVEY.md A7 (2)-(5),(7) on the device; the collide that follows reads force_view()
     int compute_forces(Dev &dev, const Lattice &L, const Collision &C, int parity, std::string &err) {
-        cur_ ^= 1;                                            // this step's counter; the other one still holds the old size
+        // static bodies: the marker set was not re-sent since the last step, so its index map and band are still valid
+        const bool use_fused = fused_ && !xchg_ && dev.supports_phased();
+        const bool rebuild = markers_dirty_ || !band_live_ || !reuse_static_ || use_fused;
+        if (rebuild) cur_ ^= 1;                               // this step's counter; the other one still holds the old size
         const IbParams p = params(L, C);
         bool ok = true;
         const int nb = (n_ + kMarkersPerCta - 1) / kMarkersPerCta;
-        if (fused_ && !xchg_ && dev.supports_phased()) {
+        if (use_fused) {
             // upper bound of any phase's work, for the launch geometry (the kernel loops grid-stride)
             const long long most = std::max<long long>((long long)nb * 128, std::min<long long>(band_cap_, (long long)kNodes * std::max(n_, n_prev_)));
             ok = parity == 0 ? dev.template launch_phased<IbFused<0>>(most, p) : dev.template launch_phased<IbFused<1>>(most, p);
         } else {
-            if (band_live_) {
-                const int bound = int(std::min<long long>(band_cap_, (long long)kNodes * std::max(n_prev_, 1)));
-                ok = dev.template launch<IbClearBand>(Dim3x((bound + 127) / 128), p);
+            if (rebuild) {
+                if (band_live_) {
+                    const int bound = int(std::min<long long>(band_cap_, (long long)kNodes * std::max(n_prev_, 1)));
+                    ok = dev.template launch<IbClearBand>(Dim3x((bound + 127) / 128), p);
+                }
+                ok = ok && dev.template launch<IbIndexMark>(Dim3x(nb), p);
+            } else {
+                ok = dev.zero(dUs_, sizeof(float) * 3 * size_t(n_));   // IbIndexMark would have cleared the U* accumulators
             }
-            ok = ok && dev.template launch<IbIndexMark>(Dim3x(nb), p);
             const int bound2 = int(std::min<long long>(band_cap_, (long long)kNodes * n_));
             ok = ok && (parity == 0 ? dev.template launch<IbBandMoments<0>>(Dim3x((bound2 + 127) / 128), p)
                                     : dev.template launch<IbBandMoments<1>>(Dim3x((bound2 + 127) / 128), p));
+            if (!xchg_) {
+                ok = ok && dev.template launch_block_phased<IbInterpSpread>(Dim3x(std::max(nb, (6 * nl_ + 127) / 128)), p);
+                ok = ok && dev.template launch<IbLinkReduce>(Dim3x((n_ + 127) / 128), p);
+            } else {
             ok = ok && dev.template launch<IbInterpolate>(Dim3x(std::max(nb, (6 * nl_ + 127) / 128)), p);
             if (xchg_) {
                 // partial U* to the face neighbours, wait for theirs (counter value c+1 of this exchange)
@@ -703,7 +736,9 @@ public:
                 ok = ok && dev.template launch<IbSumWrench>(Dim3x(g6), p);
                 ok = ok && dev.signal_counters(mine, nullptr, 0, true);   // bump my counter: this exchange is complete
             }
+            }
         }
+        markers_dirty_ = false;
         // results the host needs, queued right behind the IB kernels (not behind the collide that follows)
         ok = ok && dev.d2h_async(h_out_, dwrench_, sizeof(double) * 6 * maxl_) &&
              dev.d2h_async(reinterpret_cast<char *>(h_out_) + sizeof(double) * 6 * maxl_, band_count_, 2 * sizeof(int)) &&
@@ -716,6 +751,7 @@ public:
     // what changes the IB launches of the next substep (CUDA-graph cache key, sim.hpp substep_key)
     uint64_t graph_key() const {
         uint64_t k = uint64_t(cur_) | (uint64_t(stage_next_) << 1) | (uint64_t(band_live_) << 2) | (uint64_t(n_ > 0) << 3) | (uint64_t(fused_) << 36);
+        k ^= uint64_t(markers_dirty_ || !reuse_static_) << 38;
         k |= uint64_t(uint32_t(n_)) << 4;
         k ^= uint64_t(xchg_) << 37;
         k ^= (uint64_t(uint32_t(n_prev_)) * 0x9E3779B97F4A7C15ull) ^ (uint64_t(uint32_t(nl_)) << 40);
@@ -825,6 +861,7 @@ private:
     size_t msg_floats_ = 0;
     int per_[3] = {1, 1, 1};
     bool band_live_ = false, forces_valid_ = false, wrench_fetched_ = true, fused_ = false;
+    bool markers_dirty_ = true, reuse_static_ = true;
     bool stage_used_[2] = {false, false};
     float *dmsg_ = nullptr, *dF_ = nullptr, *dUs_ = nullptr, *band_u_ = nullptr, *bandF_ = nullptr;
     int *dbase_ = nullptr, *downer_ = nullptr, *cellslot_ = nullptr, *band_cell_ = nullptr, *band_count_ = nullptr;

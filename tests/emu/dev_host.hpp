@@ -56,6 +56,18 @@ public:
         return true;
     }
 
+    // block-phased kernels: CTA barrier between the phases -> per block: all threads of phase 0, then phase 1, ...
+    template <class K, class P>
+    bool launch_block_phased(Dim3 g, const P &p) {
+        ++launches;
+        for (int bz = 0; bz < g.z; ++bz)
+            for (int by = 0; by < g.y; ++by)
+                for (int bx = 0; bx < g.x; ++bx)
+                    for (int ph = 0; ph < K::kBlockPhases; ++ph)
+                        for (int tx = 0; tx < K::kThreads; ++tx) K::run(p, bx, by, bz, tx, ph);
+        return true;
+    }
+
     // phased kernels (one cooperative launch on the GPU): phases in order, every item of a phase before the next
     bool supports_phased() const { return true; }
     template <class K, class P>
