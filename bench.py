@@ -233,6 +233,8 @@ def main():
     ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: halo after the full-slab kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="launch kernels directly instead of per-substep CUDA graphs")
+    ap.add_argument("--no-flip", action="store_true", help="sweep planes upwards in every step (no L2 reuse between steps)")
+    ap.add_argument("--no-split", action="store_true", help="collide all planes after the IB kernels (no far-plane branch beside them)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer loop (default: --steps)")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -265,7 +267,8 @@ def main():
 
     wl = args.workload
     w = WORKLOADS[wl]
-    flags = (g._abi.FLAG_NO_OVERLAP if args.no_overlap else 0) | (g._abi.FLAG_NO_GRAPHS if args.no_graphs else 0)
+    flags = ((g._abi.FLAG_NO_OVERLAP if args.no_overlap else 0) | (g._abi.FLAG_NO_GRAPHS if args.no_graphs else 0) |
+             (g._abi.FLAG_NO_SPLIT if args.no_split else 0) | (g._abi.FLAG_NO_SWEEP_FLIP if args.no_flip else 0))
     sim, markers = make_sim(g, "cuda", wl, rank, world, local, flags=flags)
     if world > 1:
         handles = [None] * world
@@ -312,7 +315,7 @@ def main():
     barrier()
     sim.step(args.steps)
     sp = sim.stats()
-    collide_ms, collide_n, ib_ms = sp.collide_ms, sp.collide_launches, sp.ib_ms
+    collide_ms, collide_n, ib_ms, collide_cells = sp.collide_ms, sp.collide_launches, sp.ib_ms, sp.collide_cells
     profiled_ms = sp.last_step_ms
     sim.set_flags(flags)
     barrier()
@@ -395,8 +398,9 @@ def main():
     peak, peak_src = measured_peak()
     roof = None
     if collide_n > 0 and collide_ms > 0:
-        # algorithmic bytes per launch = 152 B x cells the launch updates; averaged over the launches of the timed region
-        achieved = BYTES_PER_CELL_UPDATE * cells_local * args.steps / (collide_ms * 1e-3) / 1e9
+        # algorithmic bytes per launch = 152 B x cells the launch updates; averaged over the bulk launches of the timed
+        # region (the thin checked launches for wall rows run beside them on another stream and are in neither sum)
+        achieved = BYTES_PER_CELL_UPDATE * collide_cells / (collide_ms * 1e-3) / 1e9
         traffic, traffic_src = None, None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[wl]
@@ -404,9 +408,10 @@ def main():
         except Exception:
             pass
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "traffic_source": traffic_src, "algorithmic_bytes_per_launch": BYTES_PER_CELL_UPDATE * cells_local,
+                "traffic_source": traffic_src, "algorithmic_bytes_per_launch": BYTES_PER_CELL_UPDATE * collide_cells / collide_n,
                 "kernel": "fg::StreamCollide<parity, MRT> (even+odd average)", "peak_source": peak_src,
-                "kernel_ms_per_step": collide_ms / args.steps, "launches_timed": int(collide_n),
+                "kernel_ms_per_launch": collide_ms / collide_n, "launches_timed": int(collide_n),
+                "cells_per_launch": collide_cells / collide_n,
                 "bytes_per_cell_update": BYTES_PER_CELL_UPDATE, "ib_ms_per_step": ib_ms / args.steps,
                 "timed_in": "second pass of the same K steps with event brackets (FG_FLAG_PROFILE)",
                 "profiled_pass_ms_per_step": profiled_ms / args.steps}
@@ -425,6 +430,7 @@ def main():
         "config": {"workload": w["desc"], "name": wl, "grid_per_gpu_xyz": [w["nx"], w["ny"], nz_local], "ranks": world,
                    "markers_per_gpu": int(st.n_markers), "decomposition": "z-slabs, halos by peer stores over NVLink" if world > 1 else "single GPU",
                    "halo_overlap": not args.no_overlap, "cuda_graphs": not args.no_graphs,
+                   "plane_split_substeps": int(st.split_substeps),
                    "l2": f"populations {19 * 4 * cells_local / 1e6:.0f} MB per GPU > 126 MB L2, no flush needed"},
         "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
         "pct_of_hbm_roofline": (value / world) * BYTES_PER_CELL_UPDATE / 1e3 / peak * 100.0,

@@ -14,7 +14,7 @@ from typing import Optional
 
 import numpy as np
 
-FG_ABI_VERSION = 5
+FG_ABI_VERSION = 6
 Q = 19
 
 FG_OK, FG_EINVAL, FG_ENOMEM, FG_ECUDA, FG_ESTATE, FG_ENOTSUP, FG_EPEER = 0, -1, -2, -3, -4, -5, -6
@@ -25,6 +25,8 @@ FLAG_NO_OVERLAP = 1
 FLAG_PROFILE = 2
 FLAG_NO_GRAPHS = 4
 FLAG_FUSED_IB = 8
+FLAG_NO_SPLIT = 16
+FLAG_NO_SWEEP_FLIP = 32
 
 _ERR_NAMES = {FG_EINVAL: "FG_EINVAL", FG_ENOMEM: "FG_ENOMEM", FG_ECUDA: "FG_ECUDA", FG_ESTATE: "FG_ESTATE",
               FG_ENOTSUP: "FG_ENOTSUP", FG_EPEER: "FG_EPEER"}
@@ -54,7 +56,8 @@ class FgConfig(C.Structure):
         ("max_markers", C.c_int32),
         ("max_links", C.c_int32),
         ("flags", C.c_int32),
-        ("reserved_i", C.c_int32 * 3),
+        ("split_min_cells", C.c_int32),
+        ("reserved_i", C.c_int32 * 2),
         ("tau", C.c_double),
         ("mrt_rates", C.c_double * 19),
         ("wall_u", (C.c_double * 3) * 6),
@@ -73,6 +76,7 @@ class FgStats(C.Structure):
         ("n_markers", C.c_int32), ("n_links", C.c_int32),
         ("band_cells", C.c_int32), ("parity", C.c_int32),
         ("collide_ms", C.c_double), ("collide_launches", C.c_int64), ("ib_ms", C.c_double),
+        ("collide_cells", C.c_int64), ("split_substeps", C.c_int64), ("reserved", C.c_int64 * 2),
     ]
 
 

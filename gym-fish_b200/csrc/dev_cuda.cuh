@@ -9,7 +9,7 @@
 #include <cstring>
 #include <string>
 #include <unistd.h>
-#include <unordered_map>
+#include <map>
 #include <utility>
 #include <vector>
 
@@ -22,13 +22,10 @@ __global__ void __launch_bounds__(K::kThreads, K::kMinBlocks) kern(const __grid_
     K::run(p, int(blockIdx.x), int(blockIdx.y), int(blockIdx.z), int(threadIdx.x));
 }
 
-// block-phased kernel: K::kBlockPhases phases separated by a CTA barrier
+// CTA-phased kernel: K::cta() holds its own CTA barrier(s) (the host emulation runs K::run(..., phase) per phase instead)
 template <class K, class P>
 __global__ void __launch_bounds__(K::kThreads, K::kMinBlocks) kern_bp(const __grid_constant__ P p) {
-    for (int ph = 0; ph < K::kBlockPhases; ++ph) {
-        K::run(p, int(blockIdx.x), int(blockIdx.y), int(blockIdx.z), int(threadIdx.x), ph);
-        if (ph + 1 < K::kBlockPhases) { __threadfence(); __syncthreads(); }   // phase results travel through L2 atomics
-    }
+    K::cta(p, int(blockIdx.x), int(threadIdx.x));
 }
 
 // phased kernel: K::kPhases phases of grid-stride work separated by grid-wide barriers (cooperative launch)
@@ -120,11 +117,19 @@ public:
         }
         sm_count_ = prop.multiProcessorCount;
         coop_ = prop.cooperativeLaunch != 0;
-        bool ok = ck(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), "cudaStreamCreate") &&
-                  ck(cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking), "cudaStreamCreate") &&
-                  ck(cudaEventCreateWithFlags(&fork_ev_, cudaEventDisableTiming), "cudaEventCreate") &&
-                  ck(cudaEventCreateWithFlags(&join_ev_, cudaEventDisableTiming), "cudaEventCreate") &&
-                  ck(cudaEventCreate(&ev0_), "cudaEventCreate") && ck(cudaEventCreate(&ev1_), "cudaEventCreate");
+        // Streams 0/1 (main + its thin branch) run at the highest priority, 2/3 (the far-plane collide that overlaps
+        // the IB kernels, sim.hpp step()) at the lowest: pending CTAs of the short IB kernels are then dispatched
+        // ahead of the tens of thousands of queued collide CTAs instead of behind them.
+        int least = 0, greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        prio_low_ = least; prio_high_ = greatest;
+        bool ok = true;
+        for (int i = 0; i < kStreams && ok; ++i)
+            ok = ck(cudaStreamCreateWithPriority(&s_[i], cudaStreamNonBlocking, i < 2 ? greatest : least), "cudaStreamCreate") &&
+                 ck(cudaEventCreateWithFlags(&fork_ev_[i], cudaEventDisableTiming), "cudaEventCreate") &&
+                 ck(cudaEventCreateWithFlags(&join_ev_[i], cudaEventDisableTiming), "cudaEventCreate");
+        stream_ = s_[0];
+        ok = ok && ck(cudaEventCreate(&ev0_), "cudaEventCreate") && ck(cudaEventCreate(&ev1_), "cudaEventCreate");
         if (!ok) e = err;
         return ok;
     }
@@ -132,11 +137,13 @@ public:
         if (device_ < 0) return;
         cudaSetDevice(device_);
         graph_clear();
-        if (stream_) { cudaStreamSynchronize(stream_); cudaStreamDestroy(stream_); stream_ = nullptr; }
-        if (side_) { cudaStreamSynchronize(side_); cudaStreamDestroy(side_); side_ = nullptr; }
-        if (fork_ev_) cudaEventDestroy(fork_ev_);
-        if (join_ev_) cudaEventDestroy(join_ev_);
-        fork_ev_ = join_ev_ = nullptr;
+        for (int i = 0; i < kStreams; ++i) {
+            if (s_[i]) { cudaStreamSynchronize(s_[i]); cudaStreamDestroy(s_[i]); s_[i] = nullptr; }
+            if (fork_ev_[i]) cudaEventDestroy(fork_ev_[i]);
+            if (join_ev_[i]) cudaEventDestroy(join_ev_[i]);
+            fork_ev_[i] = join_ev_[i] = nullptr;
+        }
+        stream_ = nullptr;
         if (ev0_) cudaEventDestroy(ev0_);
         if (ev1_) cudaEventDestroy(ev1_);
         ev0_ = ev1_ = nullptr;
@@ -257,24 +264,37 @@ public:
         cudaSetDevice(device_);
         ++launches;
         if (gmode_ == 2) return true;   // replaying a captured substep
-        kern<K, P><<<dim3(g.x, g.y, g.z), K::kThreads, 0, on_side_ ? side_ : stream_>>>(p);
-        return ck(cudaGetLastError(), "kernel launch");
+        return launch_on_current(kern<K, P>, dim3(g.x, g.y, g.z), K::kThreads, p);
     }
-    // fork_side(): launches go to a side stream that starts where the main stream is now; main_stream(): back to the
-    // main stream (the side work keeps running beside it); join_side(): the main stream waits for the side work.
-    // Inside a capture this becomes two parallel branches of the graph.
-    bool fork_side() {
+    // The priority travels as a launch attribute, not only as a stream property: a captured kernel node keeps it,
+    // whereas nodes of a graph launched into one stream would otherwise all run at that stream's priority.
+    template <class P>
+    bool launch_on_current(void (*kernel)(const P), dim3 grid, int threads, const P &p) {
+        cudaLaunchConfig_t lc{};
+        lc.gridDim = grid; lc.blockDim = dim3(threads); lc.dynamicSmemBytes = 0; lc.stream = s_[cur_];
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributePriority;
+        at[0].val.priority = cur_ < 2 ? prio_high_ : prio_low_;
+        lc.attrs = at; lc.numAttrs = 1;
+        return ck(cudaLaunchKernelEx(&lc, kernel, p), "kernel launch");
+    }
+    // Kernel launches go to stream `current()`.  fork_to(s): stream s starts where the current stream is now and
+    // becomes current; switch_to(s): make s current (work already queued elsewhere keeps running beside it);
+    // join_from(s): the current stream waits for everything queued on s.  Inside a capture these are the parallel
+    // branches of the graph.  Copies, memsets and event records always use stream 0.
+    int current() const { return cur_; }
+    bool fork_to(int s) {
+        const int from = cur_;
+        cur_ = s;
         if (gmode_ == 2) return true;
         cudaSetDevice(device_);
-        on_side_ = true;
-        return ck(cudaEventRecord(fork_ev_, stream_), "fork record") && ck(cudaStreamWaitEvent(side_, fork_ev_, 0), "fork wait");
+        return ck(cudaEventRecord(fork_ev_[s], s_[from]), "fork record") && ck(cudaStreamWaitEvent(s_[s], fork_ev_[s], 0), "fork wait");
     }
-    bool main_stream() { on_side_ = false; return true; }
-    bool join_side() {
-        on_side_ = false;
+    bool switch_to(int s) { cur_ = s; return true; }
+    bool join_from(int s) {
         if (gmode_ == 2) return true;
         cudaSetDevice(device_);
-        return ck(cudaEventRecord(join_ev_, side_), "join record") && ck(cudaStreamWaitEvent(stream_, join_ev_, 0), "join wait");
+        return ck(cudaEventRecord(join_ev_[s], s_[s]), "join record") && ck(cudaStreamWaitEvent(s_[cur_], join_ev_[s], 0), "join wait");
     }
 
     template <class K, class P>
@@ -282,8 +302,7 @@ public:
         cudaSetDevice(device_);
         ++launches;
         if (gmode_ == 2) return true;
-        kern_bp<K, P><<<dim3(g.x, g.y, g.z), K::kThreads, 0, on_side_ ? side_ : stream_>>>(p);
-        return ck(cudaGetLastError(), "kernel launch");
+        return launch_on_current(kern_bp<K, P>, dim3(g.x, g.y, g.z), K::kThreads, p);
     }
     bool supports_phased() const { return coop_; }
     template <class K, class P>
@@ -390,13 +409,13 @@ public:
 
     // ---- per-substep CUDA graphs: capture the stream once per key, replay afterwards.  While replaying (gmode_ 2)
     // launches and async copies are not enqueued — the caller's host code still runs and keeps its state in step.
-    bool graph_begin(uint64_t key) {
+    bool graph_begin(const GraphKey &key) {
         cudaSetDevice(device_);
         auto it = graphs_.find(key);
         if (it != graphs_.end()) { gmode_ = 2; gexec_ = it->second; return true; }
         if (graphs_.size() >= 64) graph_clear();
         if (cudaStreamBeginCapture(stream_, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); return false; }
-        gmode_ = 1; gkey_ = key;
+        gmode_ = 1; gkey_ = key; cur_ = 0;
         return true;
     }
     bool graph_end() {
@@ -406,7 +425,8 @@ public:
             cudaGraph_t g = nullptr;
             if (!ck(cudaStreamEndCapture(stream_, &g), "cudaStreamEndCapture")) return false;
             cudaGraphExec_t e = nullptr;
-            const bool ok = ck(cudaGraphInstantiate(&e, g, 0), "cudaGraphInstantiate");
+            // per-node priorities (the launch attribute above), not the priority of the stream the graph is launched into
+            const bool ok = ck(cudaGraphInstantiateWithFlags(&e, g, cudaGraphInstantiateFlagUseNodePriority), "cudaGraphInstantiate");
             cudaGraphDestroy(g);
             if (!ok) return false;
             graphs_[gkey_] = e;
@@ -425,6 +445,7 @@ public:
             cudaGetLastError();
         }
         gmode_ = 0;
+        cur_ = 0;
     }
     void graph_clear() {
         if (device_ < 0) return;
@@ -457,15 +478,17 @@ private:
     cudaStream_t stream_ = nullptr;
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
     std::vector<std::pair<std::string, void *>> opened_;
-    cudaStream_t side_ = nullptr;
-    cudaEvent_t fork_ev_ = nullptr, join_ev_ = nullptr;
-    bool on_side_ = false;
+    static constexpr int kStreams = 4;
+    cudaStream_t s_[kStreams] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t fork_ev_[kStreams] = {nullptr, nullptr, nullptr, nullptr}, join_ev_[kStreams] = {nullptr, nullptr, nullptr, nullptr};
+    int cur_ = 0;
+    int prio_low_ = 0, prio_high_ = 0;
     int sm_count_ = 148;
     bool coop_ = false;
     int gmode_ = 0;                 // 0 direct, 1 capturing, 2 replaying
-    uint64_t gkey_ = 0;
+    GraphKey gkey_{};
     cudaGraphExec_t gexec_ = nullptr;
-    std::unordered_map<uint64_t, cudaGraphExec_t> graphs_;
+    std::map<GraphKey, cudaGraphExec_t> graphs_;
     static constexpr int kNamedEvents = 4;
     cudaEvent_t named_[kNamedEvents] = {nullptr, nullptr, nullptr, nullptr};
     static constexpr int kMaxMarks = 8192;

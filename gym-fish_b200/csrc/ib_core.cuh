@@ -148,36 +148,60 @@ FG_HD bool reduction_leader(int tx) {
 #endif
 }
 
-// (a3) marker -> grid index map (integer outputs bit-exact with the oracle) + band registration
-struct IbIndexMark {
-    static constexpr int kThreads = kNodes * kMarkersPerCta;
-    static constexpr int kMinBlocks = 8;
+// (a3) marker -> grid index map (integer outputs bit-exact with the oracle) + band registration.
+// Band positions come from ONE global counter.  CTA_AGG (the product's launch): the CTA counts its new cells in shared
+// memory and reserves its range with a single atomic — 8 markers (512 threads) per CTA, so 1e5 markers cost 12k
+// same-address atomics instead of one per warp (the first version spent 115 us there, profiles/r1_ncu_ib.csv).
+template <bool CTA_AGG>
+struct IbIndexMarkT {
+    static constexpr int kMarkers = CTA_AGG ? 8 : kMarkersPerCta;
+    static constexpr int kThreads = kNodes * kMarkers;
+    static constexpr int kMinBlocks = CTA_AGG ? 2 : 8;
     FG_HD static void run(const IbParams &p, int bx, int, int, int tx) {
-        const int k = bx * kMarkersPerCta + tx / kNodes, node = tx % kNodes;
-        if (k >= p.n || (p.gidx && p.gidx[k] < 0)) return;
+        const int k = bx * kMarkers + tx / kNodes, node = tx % kNodes;
+        const bool live = k < p.n && !(p.gidx && p.gidx[k] < 0);
         const Lattice &L = p.L;
-        const float X = p.X[3 * k], Y = p.X[3 * k + 1], Z = p.X[3 * k + 2];
-        const int i0 = int(floorf(X)) - 1, j0 = int(floorf(Y)) - 1, k0 = int(floorf(Z)) - 1;
-        if (node == 0) {
-            p.base[3 * k] = i0; p.base[3 * k + 1] = j0; p.base[3 * k + 2] = k0;
-            int kc = wrap_or_skip(k0 + 1, L.nzg, p.per_z != 0);
-            if (kc < 0) kc = k0 + 1 < 0 ? 0 : L.nzg - 1;
-            p.owner[k] = kc / L.nz;
-        }
-        if (node < 3) p.Ustar[3 * k + node] = 0.0f;          // accumulated by IbInterpolate
-        const long long cell = stencil_cell(p, i0, j0, k0, node & 3, (node >> 2) & 3, node >> 4);
-        if (cell < 0) return;
-        if (p.cellslot[cell] != 0) return;
-        if (atomic_cas_i(&p.cellslot[cell], 0, -1) == 0) {
-            const int pos = atomic_add_i(p.band_count, 1);
-            if (pos < p.band_cap) {
-                p.band_cell[pos] = int(cell);
-                p.cellslot[cell] = pos + 1;
-                p.rowflag[cell / L.nx] = 1;
+        long long cell = -1;
+        if (live) {
+            const float X = p.X[3 * k], Y = p.X[3 * k + 1], Z = p.X[3 * k + 2];
+            const int i0 = int(floorf(X)) - 1, j0 = int(floorf(Y)) - 1, k0 = int(floorf(Z)) - 1;
+            if (node == 0) {
+                p.base[3 * k] = i0; p.base[3 * k + 1] = j0; p.base[3 * k + 2] = k0;
+                int kc = wrap_or_skip(k0 + 1, L.nzg, p.per_z != 0);
+                if (kc < 0) kc = k0 + 1 < 0 ? 0 : L.nzg - 1;
+                p.owner[k] = kc / L.nz;
             }
+            if (node < 3) p.Ustar[3 * k + node] = 0.0f;          // accumulated by IbInterpolate
+            cell = stencil_cell(p, i0, j0, k0, node & 3, (node >> 2) & 3, node >> 4);
+        }
+        const bool won = cell >= 0 && p.cellslot[cell] == 0 && atomic_cas_i(&p.cellslot[cell], 0, -1) == 0;
+        int pos = -1;
+#if defined(__CUDA_ARCH__)
+        if (CTA_AGG) {
+            __shared__ int s_count, s_base;
+            if (tx == 0) s_count = 0;
+            __syncthreads();
+            const int mine = won ? atomicAdd(&s_count, 1) : 0;
+            __syncthreads();
+            if (tx == 0 && s_count > 0) s_base = atomicAdd(p.band_count, s_count);
+            __syncthreads();
+            if (won) pos = s_base + mine;
+        } else
+#endif
+        if (won) pos = atomic_add_i(p.band_count, 1);
+        if (won && pos < p.band_cap) {
+            p.band_cell[pos] = int(cell);
+            p.cellslot[cell] = pos + 1;
+            p.rowflag[cell / L.nx] = 1;
         }
     }
 };
+using IbIndexMark = IbIndexMarkT<false>;      // per-thread form: the cooperative single-kernel variant and the host emulation
+#if defined(__CUDACC__)
+using IbIndexMarkLaunch = IbIndexMarkT<true>;
+#else
+using IbIndexMarkLaunch = IbIndexMarkT<false>;
+#endif
 
 // (a4) unforced velocity of the band cells from the populations arriving at time t (parity aware)
 template <int PARITY>
@@ -268,7 +292,10 @@ struct IbForceSpread {
 };
 
 // (a5-a7) in one launch: both phases of a marker run in the same CTA (2 markers x 64 nodes), so a CTA barrier between
-// them is all the ordering U*_k needs (single-rank path; across slabs the exchange sits between the two)
+// them is all the ordering U*_k needs (single-rank path; across slabs the exchange sits between the two).
+// run(): the two phases as the host emulation executes them.  cta(): what the GPU runs — stencil weights and band slot
+// computed once and kept in registers across the barrier, the three 1-D delta weights of a node fetched by shuffles
+// from the 12 lanes that evaluated them (one sqrt per thread instead of three; same values, same arithmetic).
 struct IbInterpSpread {
     static constexpr int kThreads = kNodes * kMarkersPerCta;
     static constexpr int kMinBlocks = 8;
@@ -277,6 +304,41 @@ struct IbInterpSpread {
         if (phase == 0) IbInterpolate::run(p, bx, by, bz, tx);
         else IbForceSpread::run(p, bx, by, bz, tx);
     }
+#if defined(__CUDACC__)
+    __device__ __forceinline__ static void cta(const IbParams &p, int bx, int tx) {
+        const int gt = bx * kThreads + tx;
+        if (gt < 6 * p.n_links) p.wrench[gt] = 0.0;           // accumulated by IbLinkReduce
+        const int k = bx * kMarkersPerCta + tx / kNodes, node = tx % kNodes;
+        const bool live = k < p.n && !(p.gidx && p.gidx[k] < 0);     // warp-uniform: a warp holds half a marker
+        float w = 0.f;
+        int s = -1;
+        if (live) {
+            const int lane = tx & 31;
+            const int sel = lane % 12, axis = sel >> 2, j = sel & 3;
+            const float w1 = peskin4(p.X[3 * k + axis] - float(p.base[3 * k + axis] + j));
+            const int a = node & 3, b = (node >> 2) & 3, c = node >> 4;
+            const float wx = __shfl_sync(0xffffffffu, w1, a), wy = __shfl_sync(0xffffffffu, w1, 4 + b), wz = __shfl_sync(0xffffffffu, w1, 8 + c);
+            w = wx * wy * wz;
+            const long long cell = stencil_cell(p, p.base[3 * k], p.base[3 * k + 1], p.base[3 * k + 2], a, b, c);
+            s = cell >= 0 ? p.cellslot[cell] - 1 : -1;
+            float u0 = 0.f, u1 = 0.f, u2 = 0.f;
+            if (s >= 0) { u0 = w * p.band_u[s]; u1 = w * p.band_u[p.band_cap + s]; u2 = w * p.band_u[2 * p.band_cap + s]; }
+            u0 = warp_sum(u0); u1 = warp_sum(u1); u2 = warp_sum(u2);
+            if (lane == 0) { atomicAdd(&p.Ustar[3 * k], u0); atomicAdd(&p.Ustar[3 * k + 1], u1); atomicAdd(&p.Ustar[3 * k + 2], u2); }
+        }
+        __threadfence();          // the partial sums of the marker's two warps meet in L2
+        __syncthreads();
+        if (!live) return;
+        const float f0 = 2.0f * (p.U[3 * k] - __ldcg(&p.Ustar[3 * k])), f1 = 2.0f * (p.U[3 * k + 1] - __ldcg(&p.Ustar[3 * k + 1])),
+                    f2 = 2.0f * (p.U[3 * k + 2] - __ldcg(&p.Ustar[3 * k + 2]));
+        if (node == 0) { p.Fm[3 * k] = f0; p.Fm[3 * k + 1] = f1; p.Fm[3 * k + 2] = f2; }
+        if (s < 0) return;
+        w *= p.dV[k];
+        atomicAdd(&p.bandF[s], w * f0);
+        atomicAdd(&p.bandF[p.band_cap + s], w * f1);
+        atomicAdd(&p.bandF[2 * p.band_cap + s], w * f2);
+    }
+#endif
 };
 
 // (a8) hydrodynamic wrench ON each link = minus what its markers exert on the fluid; markers arrive sorted by link,
@@ -573,9 +635,41 @@ public:
     }
 
     // origins: nullptr keeps the current torque reference points
+    // The planes (local zz, ghost offset included) that marker stencils of this rank touch.  Cheap on purpose: one
+    // floor per marker; a body that wraps around the periodic z axis simply reports "everywhere".
+    void update_range(int n, const float *X) {
+        int kmin = 0x7fffffff, kmax = -0x7fffffff;
+        const int z0 = rank_ * nzl_;
+        for (int k = 0; k < n; ++k) {
+            const int k0 = int(std::floor(X[3 * k + 2])) - 1;
+            if (xchg_ && slab_of(k0) != rank_ && slab_of(k0 + 3) != rank_) continue;
+            kmin = std::min(kmin, k0); kmax = std::max(kmax, k0 + 3);
+        }
+        z_any_ = kmin <= kmax;
+        z_all_ = z_any_ && per_[2] && (kmin < 0 || kmax >= nzg_);
+        zmin_ = std::max(kmin, z0) - z0 + 1;
+        zmax_ = std::min(kmax, z0 + nzl_ - 1) - z0 + 1;
+    }
+    // planes [za, zb) contain every cell the IB kernels of this step read or write.  In the AA pattern every storage
+    // location is read and written by exactly ONE cell per step, and IbBandMoments reads precisely the locations its
+    // band cells own, so the collide of any cell outside the band may run beside the IB kernels; one plane of margin
+    // is kept anyway.  Snapped outwards to multiples of 8 so that a slowly moving body keeps its launch geometry
+    // (and CUDA graph) for many steps.
+    bool near_planes(int &za, int &zb) const {
+        if (z_all_) return false;
+        if (!z_any_ || zmax_ < zmin_) { za = zb = 1; return true; }   // no stencil on this slab: everything is far
+        constexpr int q = 8;
+        const int a = zmin_ - 1, b = zmax_ + 2;       // [a, b)
+        za = a <= 1 ? 1 : 1 + (a - 1) / q * q;
+        zb = 1 + (b - 1 + q - 1) / q * q;
+        return true;
+    }
+
+    // origins: nullptr keeps the current torque reference points
     int set_markers(Dev &dev, int n, const float *X, const float *U, const float *dV, const int32_t *link, const double *origins,
-                    int n_origins, std::string &err) {
+                    int n_origins, std::string &err, bool range_known = false) {
         if (n > cap_) { err = "more markers than FgConfig.max_markers"; return FG_EINVAL; }
+        if (!range_known) update_range(n, X);
         if (n_origins > maxl_) { err = "more links than FgConfig.max_links"; return FG_EINVAL; }
         int nl = 0;
         if (link)
@@ -699,7 +793,7 @@ public:
                     const int bound = int(std::min<long long>(band_cap_, (long long)kNodes * std::max(n_prev_, 1)));
                     ok = dev.template launch<IbClearBand>(Dim3x((bound + 127) / 128), p);
                 }
-                ok = ok && dev.template launch<IbIndexMark>(Dim3x(nb), p);
+                ok = ok && dev.template launch<IbIndexMarkLaunch>(Dim3x((n_ + IbIndexMarkLaunch::kMarkers - 1) / IbIndexMarkLaunch::kMarkers), p);
             } else {
                 ok = dev.zero(dUs_, sizeof(float) * 3 * size_t(n_));   // IbIndexMark would have cleared the U* accumulators
             }
@@ -749,13 +843,11 @@ public:
     }
 
     // what changes the IB launches of the next substep (CUDA-graph cache key, sim.hpp substep_key)
-    uint64_t graph_key() const {
-        uint64_t k = uint64_t(cur_) | (uint64_t(stage_next_) << 1) | (uint64_t(band_live_) << 2) | (uint64_t(n_ > 0) << 3) | (uint64_t(fused_) << 36);
-        k ^= uint64_t(markers_dirty_ || !reuse_static_) << 38;
-        k |= uint64_t(uint32_t(n_)) << 4;
-        k ^= uint64_t(xchg_) << 37;
-        k ^= (uint64_t(uint32_t(n_prev_)) * 0x9E3779B97F4A7C15ull) ^ (uint64_t(uint32_t(nl_)) << 40);
-        return k;
+    void graph_key(uint64_t (&w)[3]) const {
+        w[0] = uint64_t(cur_) | (uint64_t(stage_next_) << 1) | (uint64_t(band_live_) << 2) | (uint64_t(n_ > 0) << 3) | (uint64_t(fused_) << 4) |
+               (uint64_t(markers_dirty_ || !reuse_static_) << 5) | (uint64_t(xchg_) << 6);
+        w[1] = uint64_t(uint32_t(n_)) | (uint64_t(uint32_t(n_prev_)) << 32);
+        w[2] = uint64_t(uint32_t(nl_));
     }
     ForceField force_view() const { return ForceField{cellslot_, bandF_, band_cap_, rowflag_}; }
 
@@ -862,6 +954,8 @@ private:
     int per_[3] = {1, 1, 1};
     bool band_live_ = false, forces_valid_ = false, wrench_fetched_ = true, fused_ = false;
     bool markers_dirty_ = true, reuse_static_ = true;
+    bool z_any_ = false, z_all_ = true;
+    int zmin_ = 1, zmax_ = 0;
     bool stage_used_[2] = {false, false};
     float *dmsg_ = nullptr, *dF_ = nullptr, *dUs_ = nullptr, *band_u_ = nullptr, *bandF_ = nullptr;
     int *dbase_ = nullptr, *downer_ = nullptr, *cellslot_ = nullptr, *band_cell_ = nullptr, *band_count_ = nullptr;

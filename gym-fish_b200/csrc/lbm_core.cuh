@@ -54,7 +54,15 @@ FG_HD int oppr(int i) { constexpr int t[Q] = {0, 2, 1, 4, 3, 6, 5, 10, 9, 8, 7, 
 FG_HD int zpr(int k) { constexpr int t[5] = {5, 11, 12, 15, 16}; return t[k]; }
 FG_HD int zmr(int k) { constexpr int t[5] = {6, 13, 14, 17, 18}; return t[k]; }
 
-struct Dim3 { int x = 1, y = 1, z = 1; };   // launch grid (blocks); block size is the kernel's kThreads
+struct Dim3 { int x = 1, y = 1, z = 1; };
+struct GraphKey {            // everything that selects the kernels of a substep or changes their arguments
+    uint64_t w[4];
+    uint64_t &operator[](int i) { return w[i]; }
+    bool operator<(const GraphKey &o) const {
+        for (int i = 0; i < 4; ++i) if (w[i] != o.w[i]) return w[i] < o.w[i];
+        return false;
+    }
+};   // launch grid (blocks); block size is the kernel's kThreads
 
 enum : int { BC_PERIODIC = 0, BC_WALL = 1, BC_INLET = 2, BC_OUTLET = 3, BC_PEER = 4 };
 enum : int { F_XLO = 0, F_XHI = 1, F_YLO = 2, F_YHI = 3, F_ZLO = 4, F_ZHI = 5 };
@@ -90,7 +98,9 @@ struct StepParams {
     Lattice L;
     Collision C;
     ForceField F;
-    int zz_begin, zz_stride;  // planes this launch covers: zz = zz_begin + blockIdx.z * zz_stride
+    int zz_begin, zz_stride;  // planes this launch covers: zz = zz_begin + blockIdx.z * zz_stride ...
+    int zz_skip_begin, zz_skip_len;   // ... and from zz_skip_begin on, zz_skip_len planes further up (a launch with a hole)
+    int zz_flip;              // >= 0: blockIdx.z is replaced by zz_flip - blockIdx.z, i.e. the planes are swept downwards
     int y0, ystride;       // rows this launch covers: y = y0 + blockIdx.y * ystride
     long long kz[Q][3];    // byte offset of (slot S, plane z-1 / z / z+1) from a cell of plane z: 4*(S*slot + dz*plane)
 };
@@ -498,7 +508,11 @@ struct StreamCollide {
     }
 
     FG_HD static void run(const StepParams &p, int bx, int by, int bz, int tx) {
-        const int x = bx * kThreads + tx, y = p.y0 + by * p.ystride, zz = p.zz_begin + bz * p.zz_stride;
+        const int x = bx * kThreads + tx, y = p.y0 + by * p.ystride;
+        // CTAs are dispatched in blockIdx order: odd steps sweep the planes downwards, so a step starts on the planes
+        // the previous one touched last and finds them in the 126 MB L2 (a third of a 256x128x128 lattice)
+        int zz = p.zz_begin + (p.zz_flip >= 0 ? p.zz_flip - bz : bz) * p.zz_stride;
+        if (zz >= p.zz_skip_begin) zz += p.zz_skip_len;
         if (x >= p.L.nx) return;
         if (MODE == CHECK_ALL) checked_cell(p, x, y, zz);
         else if (MODE == CHECK_XEDGE) bulk_cell<true>(p, x, y, zz);

@@ -295,46 +295,64 @@ public:
                 }
             }
             // The device work of one substep is a fixed sequence for a given (parity, IB counter, staging buffer,
-            // marker count): captured once into a CUDA graph and replayed afterwards (the host code below still runs
-            // on replay to advance its state, the device policy just does not enqueue).
+            // marker count, plane split): captured once into a CUDA graph and replayed afterwards (the host code below
+            // still runs on replay to advance its state, the device policy just does not enqueue).
+            if (!fish_.empty()) emit_bodies();      // host only: marker coordinates of this substep (and their z-range)
+            const bool ib_on = ib_.ready() && ib_.n_markers() > 0;
+            const bool overlap = ranks && peers_ && !(cfg.flags & FG_FLAG_NO_OVERLAP) && L_.nz >= 4;
+            // planes the halo push does not wait for: all of them, or the interior ones when boundary planes go first
+            const int lo = overlap ? 2 : 1, hi = overlap ? L_.nz : L_.nz + 1;
+            // Plane split: only planes [near_a_, near_b_) hold cells the IB kernels read or write (IbState::near_planes).
+            // The collide of the other ("far") planes needs neither the force nor the marker upload, so it runs on a
+            // low-priority branch BESIDE the IB kernels instead of after them.
+            split_ = false; near_a_ = lo; near_b_ = hi;
+            if (ib_on && !prof && !(cfg.flags & FG_FLAG_NO_SPLIT)) {
+                int a, b;
+                if (ib_.near_planes(a, b)) {
+                    a = std::min(std::max(a, lo), hi); b = std::max(std::min(b, hi), a);
+                    // worth it when the far planes are at least a quarter of the slab and ~25 us of work (1 M cells)
+                    const int far = (a - lo) + (hi - b);
+                    if (far * 4 >= hi - lo && (long long)far * L_.plane >= (cfg.split_min_cells > 0 ? cfg.split_min_cells : (1 << 20))) { split_ = true; near_a_ = a; near_b_ = b; }
+                }
+            }
+            // A substep with a far branch is launched kernel by kernel: inside a captured graph the two priorities had no
+            // effect on B200 (r1 pass 8/9: 0.137 ms/step as a graph with either the stream priorities, per-node priority
+            // attributes + cudaGraphInstantiateFlagUseNodePriority, or the far branch outside the graph; 0.1125 ms direct),
+            // and with the IB chain hidden beside the far collide its launch latencies no longer matter.
             struct Scope {
                 Dev &d; bool on; bool done = false;
                 ~Scope() { if (on && !done) d.graph_abort(); }
-            } scope{dev, graphs && dev.graph_begin(substep_key())};
+            } scope{dev, graphs && !split_ && dev.graph_begin(substep_key())};
+            if (split_) {
+                ++split_substeps_;
+                if (!dev.fork_to(2) || !launch_collide(lo, hi, ForceField{}, 1, near_a_, near_b_) || !dev.switch_to(0)) return cuda_fail();
+            }
             if (!fish_.empty()) {
-                if (int rc = bodies_to_markers()) return rc;
+                if (int rc = upload_bodies()) return rc;
             }
             // neighbours must have delivered the halos of the previous step before anything reads ghost planes
-            // (the IB band moments do, at odd parity)
+            // (the IB band moments do, at odd parity) or boundary planes
             if (ranks && peers_ && !dev.wait_flags(flags_, has_lo_peer(), has_hi_peer())) return cuda_fail();
             ForceField F{};
-            if (ib_.ready() && ib_.n_markers() > 0) {
+            if (ib_on) {
                 if (prof) dev.mark(1);
                 ib_.set_fused((cfg.flags & FG_FLAG_FUSED_IB) != 0);
                 if (int rc = ib_.compute_forces(dev, L_, C_, parity_, err)) return rc;
                 if (prof) dev.mark(1);
                 F = ib_.force_view();
             }
-            const bool overlap = ranks && peers_ && !(cfg.flags & FG_FLAG_NO_OVERLAP) && L_.nz >= 4;
             if (overlap) {
                 // boundary planes first, push halos over NVLink, then the interior hides the exchange
-                if (prof) dev.mark(0);
                 // both boundary planes in one launch (plane stride nz-1), unless one of them is a z-wall plane
                 const bool zwall = (L_.bc_zlo == BC_WALL && L_.z0 == 0) || (L_.bc_zhi == BC_WALL && L_.z0 + L_.nz == L_.nzg);
                 if (zwall) {
                     if (!launch_collide(1, 2, F) || !launch_collide(L_.nz, L_.nz + 1, F)) return cuda_fail();
                 } else if (!launch_collide(1, L_.nz + 1, F, L_.nz - 1)) return cuda_fail();
-                if (prof) dev.mark(0);
-                if (!launch_faces()) return cuda_fail();
-                if (prof) dev.mark(0);
-                if (!launch_collide(2, L_.nz, F)) return cuda_fail();
-                if (prof) dev.mark(0);
-            } else {
-                if (prof) dev.mark(0);
-                if (!launch_collide(1, L_.nz + 1, F)) return cuda_fail();
-                if (prof) dev.mark(0);
                 if (!launch_faces()) return cuda_fail();
             }
+            if (!launch_collide(near_a_, near_b_, F)) return cuda_fail();
+            if (split_ && !dev.join_from(2)) return cuda_fail();
+            if (!overlap && !launch_faces()) return cuda_fail();
             parity_ ^= 1;
             ++steps_;
             if (scope.on) {
@@ -346,9 +364,9 @@ public:
         if (!dev.sync()) return cuda_fail();
         if (prof) {
             collide_ms_ = dev.marks_elapsed(0); ib_ms_ = dev.marks_elapsed(1);
-            last_collide_launches_ = collide_launches_;
+            last_collide_launches_ = collide_launches_; last_collide_cells_ = collide_cells_;
         }
-        collide_launches_ = 0;
+        collide_launches_ = 0; collide_cells_ = 0;
         if (peers_) {
             int timed_out = 0;
             if (!dev.d2h(&timed_out, flags_ + 3, sizeof(int))) return cuda_fail();
@@ -376,6 +394,8 @@ public:
         o->n_markers = ib_.n_markers(); o->n_links = ib_.n_links(); o->band_cells = ib_.band_cells();
         o->parity = parity_;
         o->collide_ms = collide_ms_; o->collide_launches = last_collide_launches_; o->ib_ms = ib_ms_;
+        o->collide_cells = last_collide_cells_;
+        o->split_substeps = split_substeps_;
         return FG_OK;
     }
 
@@ -489,8 +509,14 @@ public:
     }
 
     // everything that selects kernels or changes their arguments from one substep to the next
-    uint64_t substep_key() const {
-        uint64_t k = uint64_t(parity_) | (fish_.empty() ? 0u : 2u) | (uint64_t(ib_.ready() ? ib_.graph_key() : 0) << 2);
+    GraphKey substep_key() const {
+        GraphKey k{};
+        k[0] = uint64_t(parity_) | (fish_.empty() ? 0u : 2u);      // (substeps with a plane split are not captured)
+        if (ib_.ready()) {
+            uint64_t w[3];
+            ib_.graph_key(w);
+            k[1] = w[0]; k[2] = w[1]; k[3] = w[2];
+        }
         return k;
     }
     int fail(int code, const std::string &m) { err = m; return code; }
@@ -527,48 +553,70 @@ private:
         return cfg.collision == FG_MRT ? dev.template launch<StreamCollide<PARITY, true, MODE>>(g, p)
                                        : dev.template launch<StreamCollide<PARITY, false, MODE>>(g, p);
     }
-    bool launch_rows(int mode, int zb, int ze, int y0, int ystride, int rows, const ForceField &F, int zstride = 1) {
-        if (ze <= zb || rows <= 0) return true;
-        StepParams p{L_, C_, F, zb, zstride, y0, ystride, {}};
+    // hole: planes [hole_b, hole_e) inside [zb, ze) are left out (zstride 1 only)
+    bool launch_rows(int mode, int zb, int ze, int y0, int ystride, int rows, const ForceField &F, int zstride = 1, int hole_b = 0, int hole_e = 0,
+                     bool timed = false) {
+        const int hole = hole_e > hole_b ? hole_e - hole_b : 0;
+        const int planes = (ze - zb - hole + zstride - 1) / zstride;
+        if (planes <= 0 || rows <= 0) return true;
+        const bool down = parity_ == 1 && !(cfg.flags & FG_FLAG_NO_SWEEP_FLIP);
+        StepParams p{L_, C_, F, zb, zstride, hole ? hole_b : 0x7fffffff, hole, down ? planes - 1 : -1, y0, ystride, {}};
         for (int s = 0; s < Q; ++s)
             for (int d = 0; d < 3; ++d) p.kz[s][d] = 4ll * (s * L_.slot + (long long)(d - 1) * L_.plane);
-        const Dim3 g{(L_.nx + 127) / 128, rows, (ze - zb + zstride - 1) / zstride};
-        ++collide_launches_;
+        const Dim3 g{(L_.nx + 127) / 128, rows, planes};
+        const bool prof = timed && (cfg.flags & FG_FLAG_PROFILE);
+        if (prof) {   // FG_FLAG_PROFILE: event pair around the bulk launch alone, and the cells it updates
+            dev.mark(0);
+            ++collide_launches_;
+            collide_cells_ += int64_t(L_.nx) * rows * planes;
+        }
+        bool ok;
         if (parity_ == 0) {
             // the even step is purely local: only obstacles need the checked variant
-            return mode == CHECK_ALL && L_.solid ? launch_collide_pm<0, CHECK_ALL>(p, g) : launch_collide_pm<0, CHECK_NONE>(p, g);
+            ok = mode == CHECK_ALL && L_.solid ? launch_collide_pm<0, CHECK_ALL>(p, g) : launch_collide_pm<0, CHECK_NONE>(p, g);
+        } else {
+            switch (mode) {
+                case CHECK_ALL: ok = launch_collide_pm<1, CHECK_ALL>(p, g); break;
+                case CHECK_XEDGE: ok = launch_collide_pm<1, CHECK_XEDGE>(p, g); break;
+                default: ok = launch_collide_pm<1, CHECK_NONE>(p, g); break;
+            }
         }
-        switch (mode) {
-            case CHECK_ALL: return launch_collide_pm<1, CHECK_ALL>(p, g);
-            case CHECK_XEDGE: return launch_collide_pm<1, CHECK_XEDGE>(p, g);
-            default: return launch_collide_pm<1, CHECK_NONE>(p, g);
-        }
+        if (prof) dev.mark(0);
+        return ok;
     }
-    // Partition planes [zz_begin, zz_end) so that boundary code only runs where a link can be blocked.
+    // Partition planes [zz_begin, zz_end) (minus the hole) so that boundary code only runs where a link can be blocked.
     // zstride > 1 covers planes zz_begin, zz_begin + zstride, ... (the two boundary planes of a slab in one launch)
-    bool launch_collide(int zz_begin, int zz_end, const ForceField &F, int zstride = 1) {
+    bool launch_collide(int zz_begin, int zz_end, const ForceField &F, int zstride = 1, int hole_b = 0, int hole_e = 0) {
+        if (hole_e <= hole_b || hole_e <= zz_begin || hole_b >= zz_end) hole_b = hole_e = 0;
+        if (hole_e > hole_b) {           // a hole touching an end of the range just shortens the range
+            if (hole_b <= zz_begin) { zz_begin = hole_e; hole_b = hole_e = 0; }
+            else if (hole_e >= zz_end) { zz_end = hole_b; hole_b = hole_e = 0; }
+        }
         if (zz_end <= zz_begin) return true;
         const int ny = L_.ny;
-        if (L_.solid || parity_ == 0) return launch_rows(CHECK_ALL, zz_begin, zz_end, 0, 1, ny, F, zstride);
+        if (L_.solid || parity_ == 0) return launch_rows(CHECK_ALL, zz_begin, zz_end, 0, 1, ny, F, zstride, hole_b, hole_e, true);
         const bool zlo_wall = L_.bc_zlo == BC_WALL && L_.z0 == 0, zhi_wall = L_.bc_zhi == BC_WALL && L_.z0 + L_.nz == L_.nzg;
+        if (hole_e > hole_b && (zlo_wall || zhi_wall))   // wall planes are peeled off the ends below: keep that logic hole-free
+            return launch_collide(zz_begin, hole_b, F) && launch_collide(hole_e, zz_end, F);
         int zb = zz_begin, ze = zz_end;
         bool ok = true;
-        // The launches below touch disjoint cells, so the thin checked ones run on a forked side stream (parallel
-        // graph branches) while the bulk runs on the main stream.
+        // The launches below touch disjoint cells, so the thin checked ones run on a forked stream (parallel
+        // graph branches) while the bulk runs on the current one.
+        const int base = dev.current();
         const bool thin = (zlo_wall && zb <= 1 && 1 < ze) || (zhi_wall && zb <= L_.nz && L_.nz < ze) || (L_.wall_y && ny >= 2);
-        if (thin) ok = dev.fork_side();
+        if (thin) ok = dev.fork_to(base + 1);
         if (zlo_wall && zb <= 1 && 1 < ze) { ok = ok && launch_rows(CHECK_ALL, 1, 2, 0, 1, ny, F); zb = 2; }
         if (zhi_wall && zb <= L_.nz && L_.nz < ze) { ok = ok && launch_rows(CHECK_ALL, L_.nz, L_.nz + 1, 0, 1, ny, F); ze = L_.nz; }
         const int bulk = L_.wall_x ? CHECK_XEDGE : CHECK_NONE;
         if (L_.wall_y && ny >= 2) {
-            ok = ok && launch_rows(CHECK_ALL, zb, ze, 0, ny - 1, 2, F, zstride);
-            if (thin) ok = ok && dev.main_stream();
-            ok = ok && launch_rows(bulk, zb, ze, 1, 1, ny - 2, F, zstride);
+            ok = ok && launch_rows(CHECK_ALL, zb, ze, 0, ny - 1, 2, F, zstride, hole_b, hole_e);
+            if (thin) ok = ok && dev.switch_to(base);
+            ok = ok && launch_rows(bulk, zb, ze, 1, 1, ny - 2, F, zstride, hole_b, hole_e, true);
         } else {
-            if (thin) ok = ok && dev.main_stream();
-            ok = ok && launch_rows(L_.wall_y ? CHECK_ALL : bulk, zb, ze, 0, 1, ny, F, zstride);
+            if (thin) ok = ok && dev.switch_to(base);
+            ok = ok && launch_rows(L_.wall_y ? CHECK_ALL : bulk, zb, ze, 0, 1, ny, F, zstride, hole_b, hole_e, true);
         }
-        if (thin) ok = dev.join_side() && ok;
+        if (thin) ok = dev.join_from(base + 1) && ok;
         return ok;
     }
 
@@ -621,7 +669,8 @@ private:
         return true;
     }
 
-    int bodies_to_markers() {
+    // host part: marker coordinates of all bodies (and the planes their stencils touch)
+    void emit_bodies() {
         int n = 0, nl = 0;
         for (auto &f : fish_) { n += f.n_markers(); nl += f.n_links(); }
         mX_.resize(3 * size_t(n)); mU_.resize(3 * size_t(n)); mdV_.resize(n); mlink_.resize(n);
@@ -631,7 +680,16 @@ private:
             f.emit_markers(&mX_[3 * size_t(mo)], &mU_[3 * size_t(mo)], &mdV_[mo], &mlink_[mo], lo, &morigin_[3 * size_t(lo)]);
             mo += f.n_markers(); lo += f.n_links();
         }
-        return ib_.set_markers(dev, n, mX_.data(), mU_.data(), mdV_.data(), mlink_.data(), morigin_.data(), nl, err);
+        ib_.update_range(n, mX_.data());
+    }
+    // device part: the pinned marker message goes up (inside the substep's graph)
+    int upload_bodies() {
+        return ib_.set_markers(dev, int(mdV_.size()), mX_.data(), mU_.data(), mdV_.data(), mlink_.data(), morigin_.data(),
+                               int(morigin_.size() / 3), err, /*range_known=*/true);
+    }
+    int bodies_to_markers() {
+        emit_bodies();
+        return upload_bodies();
     }
 
     Lattice L_{};
@@ -640,7 +698,10 @@ private:
     int parity_ = 0;
     int64_t steps_ = 0;
     double last_ms_ = 0, last_mlups_ = 0, collide_ms_ = 0, ib_ms_ = 0;
-    int64_t collide_launches_ = 0, last_collide_launches_ = 0;
+    int64_t collide_launches_ = 0, last_collide_launches_ = 0, collide_cells_ = 0, last_collide_cells_ = 0;
+    int64_t split_substeps_ = 0;
+    bool split_ = false;           // this substep: far planes collide beside the IB kernels
+    int near_a_ = 1, near_b_ = 1;  // planes [near_a_, near_b_) wait for the IB force
     uint8_t *solid_ = nullptr;
     int *flags_ = nullptr;         // [0] written by my z-low neighbour, [1] by my z-high neighbour, [2] my own halo
                                    // counter (device-resident, never reset: orders pushes between neighbours), [3] timeout

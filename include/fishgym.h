@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FG_ABI_VERSION 5
+#define FG_ABI_VERSION 6
 #define FG_Q 19
 
 /* error codes */
@@ -60,9 +60,11 @@ extern "C" {
 
 /* FgConfig.flags */
 #define FG_FLAG_NO_OVERLAP 1   /* multi-GPU: halo after the full-slab kernel (overlap off) */
-#define FG_FLAG_PROFILE    2   /* bracket every stream-collide launch with events -> FgStats.collide_ms (disables graphs) */
+#define FG_FLAG_PROFILE    2   /* bracket every bulk stream-collide launch with events -> FgStats.collide_ms/_cells (no graphs, no split) */
 #define FG_FLAG_FUSED_IB   8   /* run the IB phases as ONE cooperative kernel with grid barriers (measured slower on B200: r1) */
 #define FG_FLAG_NO_GRAPHS  4   /* launch every kernel directly instead of replaying per-substep CUDA graphs */
+#define FG_FLAG_NO_SWEEP_FLIP 32 /* sweep the planes upwards in every step (default: odd steps downwards, for L2 reuse between steps) */
+#define FG_FLAG_NO_SPLIT  16   /* collide all planes after the IB kernels (default: planes away from the bodies run beside them) */
 
 typedef struct FgConfig {
     int32_t struct_size;      /* = sizeof(FgConfig); checked by fg_create */
@@ -74,7 +76,8 @@ typedef struct FgConfig {
     int32_t max_markers;      /* capacity for IB markers (0 = no immersed boundary) */
     int32_t max_links;        /* capacity for rigid links markers can belong to */
     int32_t flags;            /* FG_FLAG_* */
-    int32_t reserved_i[3];
+    int32_t split_min_cells;  /* plane split only when at least this many cells lie in far planes; 0 => 1<<20 (~25 us of work) */
+    int32_t reserved_i[2];
     double  tau;              /* relaxation time; nu = (tau - 1/2)/3 */
     double  mrt_rates[19];    /* MRT relaxation rates per moment; all zero => SURVEY.md A3 defaults */
     double  wall_u[6][3];     /* wall velocity per face (used where bc == WALL) */
@@ -93,9 +96,12 @@ typedef struct FgStats {
     int32_t n_markers, n_links;
     int32_t band_cells;       /* cells inside marker stencils in the last step */
     int32_t parity;           /* AA-pattern parity of the next step (0 even / 1 odd); oracle: 0 */
-    double  collide_ms;       /* FG_FLAG_PROFILE: summed device time of the stream-collide launches of the last fg_step */
-    int64_t collide_launches; /* ... and how many launches that covers */
+    double  collide_ms;       /* FG_FLAG_PROFILE: summed device time of the bulk stream-collide launches of the last fg_step */
+    int64_t collide_launches; /* ... how many launches that covers */
     double  ib_ms;            /* FG_FLAG_PROFILE: summed device time of the immersed-boundary kernels of the last fg_step */
+    int64_t collide_cells;    /* ... and how many cell updates those launches did (thin wall-row launches are not in either) */
+    int64_t split_substeps;   /* substeps since create whose far-plane collide ran beside the IB kernels (plane split) */
+    int64_t reserved[2];
 } FgStats;
 
 /* articulated swimmer description: a planar chain of n_links ellipsoid links, yawing joints */

@@ -119,10 +119,11 @@ public:
         return true;
     }
     void close_peers() {}
-    bool fork_side() { return true; }      // side stream: sequential here
-    bool main_stream() { return true; }
-    bool join_side() { return true; }
-    bool graph_begin(uint64_t) { return false; }   // no graphs in the emulation: everything runs directly
+    int current() const { return cur_; }   // streams: everything runs sequentially here, in submission order
+    bool fork_to(int s) { cur_ = s; return true; }
+    bool switch_to(int s) { cur_ = s; return true; }
+    bool join_from(int) { return true; }
+    bool graph_begin(const GraphKey &) { return false; }   // no graphs in the emulation: everything runs directly
     bool graph_end() { return true; }
     void graph_abort() {}
     void graph_clear() {}
@@ -148,6 +149,7 @@ public:
     }
 
 private:
+    int cur_ = 0;
     std::chrono::steady_clock::time_point t0_;
 };
 

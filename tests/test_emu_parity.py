@@ -89,6 +89,40 @@ def test_immersed_boundary_prescribed_markers(g, emu, fused):
         assert util.rel_l2(b.get_fields(f64=True)[1], a.get_fields(f64=True)[1]) <= TOL_FIELD
 
 
+@pytest.mark.parametrize("walls", ["periodic", "channel", "tank"])
+def test_plane_split_far_collide_beside_ib_kernels(g, emu, walls):
+    """Planes away from the bodies collide on a parallel branch that does not wait for the IB kernels (sim.hpp step()).
+    The emulation runs that branch FIRST, the default order without the split runs it LAST: identical populations
+    prove that the far planes neither read what the IB kernels write nor write what they read.  The sphere moves
+    3 planes per step so that the old band (cleared by IbClearBand) regularly lies outside the new near range."""
+    P, Wl, IN, OUT = g.BC_PERIODIC, g.BC_WALL, g.BC_INLET, g.BC_OUTLET
+    bc = {"periodic": [P] * 6, "channel": [P, P, Wl, Wl, IN, OUT], "tank": [Wl] * 6}[walls]
+    kw = dict(nx=14, ny=12, nz=64, tau=0.8, collision=g.MRT, max_markers=300, max_links=1, bc=bc, inlet_u=[0, 0, 0.03],
+              split_min_cells=1)
+    sims = [g.Sim(backend="oracle", **kw), g.Sim(backend=emu, **kw), g.Sim(backend=emu, flags=g._abi.FLAG_NO_SPLIT, **kw)]
+    rho, u = util.smooth_fields(sims[0].shape, amp=0.01)
+    for s in sims:
+        s.set_fields(rho, u)
+    for it in range(9):
+        zc = 12.3 + 3.0 * it
+        X = util.sphere_markers((7.2, 6.1, zc), 3.0, 150)
+        U = np.zeros_like(X)
+        U[:, 2] = 0.02
+        for s in sims:
+            s.set_markers(X, U, np.ones(150, np.float32))
+            s.set_link_origins([[7.2, 6.1, zc]])
+            s.step(1)
+    for s in sims:       # ... and a few steps with the markers left alone (static reuse of the index map and band)
+        s.step(3)
+    o, a, b = sims
+    assert a.stats().split_substeps == 12 and b.stats().split_substeps == 0
+    assert np.array_equal(a.get_populations(), b.get_populations())
+    assert np.array_equal(a.get_link_wrenches(), b.get_link_wrenches())
+    assert util.rel_l2(a.get_fields(f64=True)[1], o.get_fields(f64=True)[1]) <= TOL_FIELD
+    wa, wo = a.get_link_wrenches(), o.get_link_wrenches()
+    assert np.abs(wa - wo).max() / np.abs(wo).max() <= TOL_FORCE
+
+
 def test_no_markers_and_marker_removal(g, emu):
     kw = dict(nx=10, ny=10, nz=10, tau=0.8, max_markers=64, max_links=1)
     a, b = g.Sim(backend="oracle", **kw), g.Sim(backend=emu, **kw)

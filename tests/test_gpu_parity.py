@@ -101,6 +101,59 @@ def test_immersed_boundary_prescribed_markers(g, cuda, flags):
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("graphs", [True, False])
+def test_plane_split_matches_unsplit_and_oracle(g, cuda, graphs):
+    """Far planes collide on a low-priority stream beside the IB kernels (default) vs everything after them
+    (FG_FLAG_NO_SPLIT): same fluid up to the order of the spreading atomics; both match the oracle.  The sphere is
+    re-sent every step and moves 3 planes per step, so old bands get cleared outside the new near range."""
+    P, Wl, IN, OUT = g.BC_PERIODIC, g.BC_WALL, g.BC_INLET, g.BC_OUTLET
+    fl = 0 if graphs else g._abi.FLAG_NO_GRAPHS
+    kw = dict(nx=40, ny=36, nz=96, tau=0.8, collision=g.MRT, max_markers=1000, max_links=1, bc=[P, P, Wl, Wl, IN, OUT], inlet_u=[0, 0, 0.03],
+              split_min_cells=1)
+    sims = [g.Sim(backend="oracle", **kw), g.Sim(backend=cuda, flags=fl, **kw), g.Sim(backend=cuda, flags=fl | g._abi.FLAG_NO_SPLIT, **kw)]
+    rho, u = util.smooth_fields(sims[0].shape, amp=0.01)
+    for s in sims:
+        s.set_fields(rho, u)
+    for it in range(12):
+        zc = 14.3 + 3.0 * it
+        X = util.sphere_markers((20.2, 18.1, zc), 6.0, 450)
+        U = np.zeros_like(X)
+        U[:, 2] = 0.02
+        for s in sims:
+            s.set_markers(X, U, np.ones(450, np.float32))
+            s.set_link_origins([[20.2, 18.1, zc]])
+            s.step(1)
+    for s in sims:
+        s.step(5)            # markers left alone: static reuse of index map and band
+    o, a, b = sims
+    assert a.stats().split_substeps == 17 and b.stats().split_substeps == 0
+    assert np.abs(a.get_populations() - b.get_populations()).max() < 2e-7
+    assert util.rel_l2(a.get_fields(f64=True)[1], o.get_fields(f64=True)[1]) <= TOL_FIELD
+    wa, wb, wo = a.get_link_wrenches(), b.get_link_wrenches(), o.get_link_wrenches()
+    assert np.abs(wa - wo).max() / np.abs(wo).max() <= TOL_FORCE
+    assert np.abs(wa - wb).max() / np.abs(wo).max() <= 1e-5
+    for s in sims:
+        s.close()
+
+
+def test_plane_split_full_size_sphere_channel(g, cuda):
+    """bench default workload (256x128x128 channel, 1.8k-marker sphere): 200 steps with and without the split."""
+    import bench
+    sims = []
+    for fl in (0, g._abi.FLAG_NO_SPLIT):
+        s, _ = bench.make_sim(g, cuda, "sphere_256x128x128", 0, 1, 0, flags=fl)
+        s.step(200)
+        sims.append(s)
+    a, b = sims
+    assert a.stats().split_substeps == 200 and b.stats().split_substeps == 0
+    ua, ub = a.get_fields()[1], b.get_fields()[1]
+    assert util.rel_l2(ua, ub) < 1e-6
+    wa, wb = a.get_link_wrenches(), b.get_link_wrenches()
+    assert np.abs(wa - wb).max() / np.abs(wb).max() < 1e-5
+    for s in sims:
+        s.close()
+
+
 def test_spread_force_equals_marker_force_on_gpu(g, cuda):
     kw = dict(nx=48, ny=48, nz=48, tau=0.8, collision=g.MRT, max_markers=2000, max_links=1)
     s = g.Sim(backend=cuda, **kw)

@@ -101,6 +101,39 @@ def test_device_peer_pushes_equal_unsplit(g, emu, case, overlap):
         parts[0].step(1)
 
 
+@pytest.mark.parametrize("overlap", [True, False])
+def test_plane_split_on_peered_slabs(g, emu, overlap):
+    """Plane split + z-slabs: on each rank the interior planes away from its body collide before the rank even waits
+    for its neighbours' halos (sim.hpp step()).  Each slab holds a moving sphere; populations must equal the unsplit,
+    un-decomposed run bit for bit (the emulation adds in a fixed order)."""
+    P = g.BC_PERIODIC
+    kw = dict(nx=12, ny=10, nz=64, tau=0.8, collision=g.MRT, max_markers=400, max_links=2, bc=[P] * 6, body_force=[0, 0, 2e-5])
+    whole = g.Sim(backend=emu, flags=g._abi.FLAG_NO_SPLIT, **kw)
+    flags = 0 if overlap else g._abi.FLAG_NO_OVERLAP
+    parts = [g.Sim(backend=emu, n_ranks=2, rank=r, flags=flags, split_min_cells=1, **kw) for r in range(2)]
+    rho, u = util.smooth_fields(whole.shape, amp=0.01)
+    whole.set_fields(rho, u)
+    for r, s in enumerate(parts):
+        s.set_fields(rho[32 * r:32 * r + 32], u[:, 32 * r:32 * r + 32])
+    h = [s.peer_export() for s in parts]
+    parts[0].peer_connect(h[1], h[1])
+    parts[1].peer_connect(h[0], h[0])
+    for it in range(8):
+        Xa = util.sphere_markers((6.2, 5.1, 8.3 + 2.0 * it), 2.5, 100)           # stays inside slab 0
+        Xb = util.sphere_markers((5.7, 4.6, 56.1 - 2.0 * it), 2.5, 100)          # stays inside slab 1
+        U = np.zeros((100, 3), np.float32)
+        U[:, 2] = 0.01
+        one = np.ones(100, np.float32)
+        whole.set_markers(np.concatenate([Xa, Xb]), np.concatenate([U, -U]), np.ones(200, np.float32), np.array([0] * 100 + [1] * 100, np.int32))
+        parts[0].set_markers(Xa, U, one, np.zeros(100, np.int32))
+        parts[1].set_markers(Xb, -U, one, np.zeros(100, np.int32))
+        whole.step(1)
+        for s in parts:
+            s.step(1)
+    assert parts[0].stats().split_substeps >= 5 and parts[1].stats().split_substeps >= 5 and whole.stats().split_substeps == 0
+    assert np.array_equal(whole.get_populations(), np.concatenate([s.get_populations() for s in parts], axis=1))
+
+
 def test_markers_inside_one_slab_and_across_a_face(g, emu):
     kw = dict(nx=12, ny=12, nz=24, tau=0.8, max_markers=256, max_links=1)
     s = g.Sim(backend=emu, n_ranks=2, rank=0, **kw)

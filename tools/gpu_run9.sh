@@ -1,0 +1,17 @@
+# GPU pass 9: far branch outside the graph, alternating sweep direction (L2 reuse), IB index-mark / interp-spread rewrite
+mkdir -p gpurun_out
+set -x
+timeout 1200 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log
+timeout 400 python bench.py > gpurun_out/bench.log 2>&1
+timeout 300 python bench.py --no-flip --no-cpu-baseline > gpurun_out/bench_noflip.log 2>&1
+timeout 300 python bench.py --no-split --no-cpu-baseline > gpurun_out/bench_nosplit.log 2>&1
+timeout 300 python bench.py --no-graphs --no-cpu-baseline > gpurun_out/bench_nographs.log 2>&1
+timeout 300 python bench.py --no-split --no-flip --no-cpu-baseline > gpurun_out/bench_nosplit_noflip.log 2>&1
+timeout 300 python bench.py --workload tank_512x256x256 --steps 400 --warmup 40 --no-cpu-baseline > gpurun_out/bench_tank.log 2>&1
+timeout 300 python bench.py --workload tank_512x256x256 --steps 400 --warmup 40 --no-cpu-baseline --no-flip > gpurun_out/bench_tank_noflip.log 2>&1
+timeout 300 python bench.py --workload box_512_ib --steps 100 --warmup 10 --no-cpu-baseline --e2e-steps 20 > gpurun_out/bench_512_ib.log 2>&1
+timeout 300 python bench.py --workload box_512 --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/bench_512.log 2>&1
+timeout 300 python bench.py --workload box_512 --steps 100 --warmup 10 --no-cpu-baseline --no-flip > gpurun_out/bench_512_noflip.log 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:Ib -c 60 --csv --log-file gpurun_out/ib_launches.csv python bench.py --workload box_512_ib --steps 6 --warmup 3 --no-cpu-baseline --e2e-steps 2 > gpurun_out/ncu_ib.log 2>&1
+for f in pytest_gpu smoke; do echo "== $f"; tail -n 3 gpurun_out/$f.log | cut -c1-330; done
