@@ -721,9 +721,10 @@ public:
         }
         const size_t head = (xchg_ ? 9 : 8) * M;
         for (size_t i = 0; i < 3 * size_t(maxl_); ++i) msg[head + i] = float(h_origin_[i]);
-        const size_t bytes = sizeof(float) * (head + 3 * size_t(maxl_));
-        if (!dev.h2d_async(dmsg_, msg, bytes) || !dev.ev_record(EV_STAGE0 + sb)) { err = dev.err; return FG_ECUDA; }
-        stage_used_[sb] = true;
+        // The copy itself is queued by flush_upload() at the start of the next compute_forces(), i.e. AFTER the step has
+        // launched the far-plane collide, which therefore does not wait for the upload.
+        pending_sb_ = sb;
+        pending_bytes_ = sizeof(float) * (head + 3 * size_t(maxl_));
         n_ = m;
         n_total_ = n;
         markers_dirty_ = true;
@@ -735,8 +736,19 @@ public:
         return FG_OK;
     }
 
+    // queue the staged marker message (if any) on the handle's stream
+    bool flush_upload(Dev &dev) {
+        if (pending_sb_ < 0) return true;
+        const int sb = pending_sb_;
+        pending_sb_ = -1;
+        if (!dev.h2d_async(dmsg_, h_stage_[sb], pending_bytes_) || !dev.ev_record(EV_STAGE0 + sb)) return false;
+        stage_used_[sb] = true;
+        return true;
+    }
+
     int set_link_origins(Dev &dev, int n, const double *o, std::string &err) {
         if (n > maxl_) { err = "more links than FgConfig.max_links"; return FG_EINVAL; }
+        if (!flush_upload(dev)) { err = dev.err; return FG_ECUDA; }
         for (int i = 0; i < 3 * n; ++i) h_origin_[i] = o[i];
         nl_origins_ = n;
         nl_ = std::max(nl_, n);
@@ -781,21 +793,21 @@ public:
         const bool rebuild = markers_dirty_ || !band_live_ || !reuse_static_ || use_fused;
         if (rebuild) cur_ ^= 1;                               // this step's counter; the other one still holds the old size
         const IbParams p = params(L, C);
-        bool ok = true;
+        bool ok = flush_upload(dev);
         const int nb = (n_ + kMarkersPerCta - 1) / kMarkersPerCta;
         if (use_fused) {
             // upper bound of any phase's work, for the launch geometry (the kernel loops grid-stride)
             const long long most = std::max<long long>((long long)nb * 128, std::min<long long>(band_cap_, (long long)kNodes * std::max(n_, n_prev_)));
-            ok = parity == 0 ? dev.template launch_phased<IbFused<0>>(most, p) : dev.template launch_phased<IbFused<1>>(most, p);
+            ok = ok && (parity == 0 ? dev.template launch_phased<IbFused<0>>(most, p) : dev.template launch_phased<IbFused<1>>(most, p));
         } else {
             if (rebuild) {
                 if (band_live_) {
                     const int bound = int(std::min<long long>(band_cap_, (long long)kNodes * std::max(n_prev_, 1)));
-                    ok = dev.template launch<IbClearBand>(Dim3x((bound + 127) / 128), p);
+                    ok = ok && dev.template launch<IbClearBand>(Dim3x((bound + 127) / 128), p);
                 }
                 ok = ok && dev.template launch<IbIndexMarkLaunch>(Dim3x((n_ + IbIndexMarkLaunch::kMarkers - 1) / IbIndexMarkLaunch::kMarkers), p);
             } else {
-                ok = dev.zero(dUs_, sizeof(float) * 3 * size_t(n_));   // IbIndexMark would have cleared the U* accumulators
+                ok = ok && dev.zero(dUs_, sizeof(float) * 3 * size_t(n_));   // IbIndexMark would have cleared the U* accumulators
             }
             const int bound2 = int(std::min<long long>(band_cap_, (long long)kNodes * n_));
             ok = ok && (parity == 0 ? dev.template launch<IbBandMoments<0>>(Dim3x((bound2 + 127) / 128), p)
@@ -922,7 +934,7 @@ public:
         }
         const int n = std::min(cap, n_);
         const size_t N = size_t(n_);
-        bool ok = dev.sync();
+        bool ok = flush_upload(dev) && dev.sync();
         if (n > 0 && X) ok = ok && dev.d2h(X, dmsg_, sizeof(float) * 3 * n);
         if (n > 0 && U) ok = ok && dev.d2h(U, dmsg_ + 3 * N, sizeof(float) * 3 * n);
         if (n > 0 && link) ok = ok && dev.d2h(link, dmsg_ + 7 * N, sizeof(int) * n);
@@ -957,6 +969,8 @@ private:
     bool z_any_ = false, z_all_ = true;
     int zmin_ = 1, zmax_ = 0;
     bool stage_used_[2] = {false, false};
+    int pending_sb_ = -1;           // staging buffer holding a marker message that has not been queued yet
+    size_t pending_bytes_ = 0;
     float *dmsg_ = nullptr, *dF_ = nullptr, *dUs_ = nullptr, *band_u_ = nullptr, *bandF_ = nullptr;
     int *dbase_ = nullptr, *downer_ = nullptr, *cellslot_ = nullptr, *band_cell_ = nullptr, *band_count_ = nullptr;
     uint8_t *rowflag_ = nullptr;

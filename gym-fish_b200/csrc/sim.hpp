@@ -323,6 +323,9 @@ public:
                 Dev &d; bool on; bool done = false;
                 ~Scope() { if (on && !done) d.graph_abort(); }
             } scope{dev, graphs && !split_ && dev.graph_begin(substep_key())};
+            // without the boundary-first order the far branch contains the boundary planes, which do read what the
+            // neighbours pushed in the previous step
+            if (ranks && peers_ && !overlap && !dev.wait_flags(flags_, has_lo_peer(), has_hi_peer())) return cuda_fail();
             if (split_) {
                 ++split_substeps_;
                 if (!dev.fork_to(2) || !launch_collide(lo, hi, ForceField{}, 1, near_a_, near_b_) || !dev.switch_to(0)) return cuda_fail();
@@ -332,7 +335,7 @@ public:
             }
             // neighbours must have delivered the halos of the previous step before anything reads ghost planes
             // (the IB band moments do, at odd parity) or boundary planes
-            if (ranks && peers_ && !dev.wait_flags(flags_, has_lo_peer(), has_hi_peer())) return cuda_fail();
+            if (ranks && peers_ && overlap && !dev.wait_flags(flags_, has_lo_peer(), has_hi_peer())) return cuda_fail();
             ForceField F{};
             if (ib_on) {
                 if (prof) dev.mark(1);

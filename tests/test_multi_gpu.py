@@ -33,10 +33,13 @@ P, Wl, IN, OUT = g.BC_PERIODIC, g.BC_WALL, g.BC_INLET, g.BC_OUTLET
 kw = dict(nx=40, ny=24, nz=16 * world, tau=0.7, collision=g.MRT, body_force=[1e-4, 0, 2e-4])
 if case == "channel":
     kw.update(bc=[P, P, Wl, Wl, IN, OUT], inlet_u=[0, 0.01, 0.04], body_force=[0, 0, 0])
-periodic = case in ("periodic", "fish")
+periodic = case in ("periodic", "fish", "spheres")
 fish = case == "fish"
 if fish:
     kw = dict(nx=24, ny=20, nz=24 * world, tau=0.8, max_markers=4000, max_links=8)
+spheres = case == "spheres"
+if spheres:      # plane split on every rank: its own moving sphere, far interior planes collide beside the IB kernels
+    kw = dict(nx=40, ny=36, nz=64 * world, tau=0.8, collision=g.MRT, max_markers=1000, max_links=1, split_min_cells=1)
 s = g.Sim(backend="cuda", n_ranks=world, rank=rank, device=local, flags={flags}, **kw)
 h = kw["nz"] // world
 rho, u = util.smooth_fields((kw["nz"], kw["ny"], kw["nx"]))
@@ -58,6 +61,18 @@ if fish:
     dist.all_gather(allo, o)
     if rank == 0:
         np.save({out!r} + ".obs.npy", torch.stack(allo).numpy())
+elif spheres:
+    s.peer_connect(lo, hi)
+    dist.barrier()
+    for it in range(10):
+        zc = 64 * rank + 14.3 + 3.0 * it
+        X = util.sphere_markers((20.2, 18.1, zc), 6.0, 450)
+        U = np.zeros_like(X); U[:, 2] = 0.02
+        s.set_markers(X, U, np.ones(450, np.float32), np.zeros(450, np.int32))
+        s.set_link_origins([[20.2, 18.1, zc]])
+        s.step(1)
+    s.step(5)
+    assert s.stats().split_substeps >= 10, s.stats().split_substeps
 else:
     s.peer_connect(lo, hi)
     dist.barrier()
@@ -126,3 +141,37 @@ def test_multi_gpu_fish_across_slab_faces(g, cuda, tmp_path):
         assert np.array_equal(obs[rk], obs[0])
     assert np.abs(obs[0] - np.stack(ref)).max() < 1e-4
     assert np.abs(whole.get_populations() - np.load(out)).max() < 1e-6
+
+
+@pytest.mark.parametrize("overlap", [True, False])
+def test_multi_gpu_plane_split_matches_one_gpu(g, cuda, overlap, tmp_path):
+    """Plane split on z-slabs (each rank: far interior planes before it even waits for its neighbours, IB kernels and
+    boundary planes at high priority): the fluid must match the unsplit one-GPU run up to the order of the spreading
+    atomics."""
+    n = gpu_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2 if n < 4 else 4
+    out = str(tmp_path / "f.npy")
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT, tests=os.path.join(ROOT, "tests"), case="spheres", out=out,
+                                    flags=0 if overlap else g._abi.FLAG_NO_OVERLAP))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
+                        "127.0.0.1", "--master-port", str(29500 + os.getpid() % 2000), str(script)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    kw = dict(nx=40, ny=36, nz=64 * world, tau=0.8, collision=g.MRT, max_markers=1000 * world, max_links=world, flags=g._abi.FLAG_NO_SPLIT)
+    whole = g.Sim(backend=cuda, **kw)
+    rho, u = util.smooth_fields(whole.shape)
+    whole.set_fields(rho, u)
+    for it in range(10):
+        Xs, Us, origins = [], [], []
+        for rk in range(world):
+            zc = 64 * rk + 14.3 + 3.0 * it
+            X = util.sphere_markers((20.2, 18.1, zc), 6.0, 450)
+            U = np.zeros_like(X); U[:, 2] = 0.02
+            Xs.append(X); Us.append(U); origins.append([20.2, 18.1, zc])
+        whole.set_markers(np.concatenate(Xs), np.concatenate(Us), np.ones(450 * world, np.float32), np.repeat(np.arange(world), 450).astype(np.int32))
+        whole.set_link_origins(origins)
+        whole.step(1)
+    whole.step(5)
+    assert np.abs(whole.get_populations() - np.load(out)).max() < 2e-7
