@@ -37,6 +37,8 @@ WORKLOADS = {
     # name: (nx, ny, nz per GPU, sphere diameter, description)
     "sphere_256x128x128": dict(nx=128, ny=128, nz=256, D=24.0, U=0.05, Re=100.0,
                                desc="D3Q19 MRT flow past fixed IB sphere, 256x128x128 (z flow axis) per GPU"),
+    "box_256": dict(nx=256, ny=256, nz=256, D=0.0, U=0.02, Re=0.0,
+                    desc="D3Q19 MRT periodic box 256^3 per GPU (1.3 GB lattice)"),
     "box_512": dict(nx=512, ny=512, nz=512, D=0.0, U=0.02, Re=0.0,
                     desc="D3Q19 MRT periodic box 512^3 per GPU (weak-scaling sweep, BASELINE.json configs[4])"),
     "box_512_ib": dict(nx=512, ny=512, nz=512, D=22.2, U=0.02, Re=0.0,
@@ -58,11 +60,12 @@ def sphere_markers(center, radius, n):
     return X.astype(np.float32)
 
 
-def make_sim(g, backend, wl, rank, world, device, flags=0, nz_override=None):
+def make_sim(g, backend, wl, rank, world, device, flags=0, nz_override=None, extra=None):
     """Create one slab of the workload and put it in its initial state."""
     w = WORKLOADS[wl]
     nzl = nz_override or (w["nz"] // world if w.get("strong") else w["nz"])
     kw = dict(nx=w["nx"], ny=w["ny"], nz=nzl * world, n_ranks=world, rank=rank, device=device, collision=g.MRT, flags=flags)
+    kw.update(extra or {})
     markers = None
     if wl == "sphere_256x128x128":
         nu = w["U"] * w["D"] / w["Re"]
@@ -74,7 +77,7 @@ def make_sim(g, backend, wl, rank, world, device, flags=0, nz_override=None):
         X = sphere_markers((w["nx"] / 2 + 0.21, w["ny"] / 2 + 0.13, zc), R, n)
         markers = (X, np.zeros_like(X), np.full(n, 4 * np.pi * R * R / n, np.float32), np.zeros(n, np.int32),
                    np.array([[w["nx"] / 2 + 0.21, w["ny"] / 2 + 0.13, zc]]))
-    elif wl == "box_512":
+    elif wl in ("box_512", "box_256"):
         kw.update(tau=0.6)
     elif wl == "box_512_ib":
         kw.update(tau=0.6, max_markers=110000, max_links=64)
@@ -234,6 +237,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="launch kernels directly instead of per-substep CUDA graphs")
     ap.add_argument("--no-flip", action="store_true", help="sweep planes upwards in every step (no L2 reuse between steps)")
+    ap.add_argument("--pairs", action="store_true", help="fused even+odd wavefront launches (opt-in experiment, measured slower)")
+    ap.add_argument("--pair-lag", type=int, default=0, help="planes between the even and odd wavefront (0: automatic)")
     ap.add_argument("--no-split", action="store_true", help="collide all planes after the IB kernels (no far-plane branch beside them)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer loop (default: --steps)")
     args = ap.parse_args()
@@ -268,12 +273,13 @@ def main():
     wl = args.workload
     w = WORKLOADS[wl]
     flags = ((g._abi.FLAG_NO_OVERLAP if args.no_overlap else 0) | (g._abi.FLAG_NO_GRAPHS if args.no_graphs else 0) |
-             (g._abi.FLAG_NO_SPLIT if args.no_split else 0) | (g._abi.FLAG_NO_SWEEP_FLIP if args.no_flip else 0))
-    sim, markers = make_sim(g, "cuda", wl, rank, world, local, flags=flags)
+             (g._abi.FLAG_NO_SPLIT if args.no_split else 0) | (g._abi.FLAG_NO_SWEEP_FLIP if args.no_flip else 0) |
+             (g._abi.FLAG_FUSED_PAIRS if args.pairs else 0))
+    sim, markers = make_sim(g, "cuda", wl, rank, world, local, flags=flags, extra=dict(pair_lag=args.pair_lag))
     if world > 1:
         handles = [None] * world
         dist.all_gather_object(handles, sim.peer_export())
-        per = wl in ("box_512", "box_512_ib", "tank_512x256x256", "school_1024x512x512")
+        per = wl in ("box_512", "box_256", "box_512_ib", "tank_512x256x256", "school_1024x512x512")
         lo = handles[(rank - 1) % world] if (rank > 0 or per) else None
         hi = handles[(rank + 1) % world] if (rank < world - 1 or per) else None
         if wl == "school_1024x512x512":
@@ -430,7 +436,7 @@ def main():
         "config": {"workload": w["desc"], "name": wl, "grid_per_gpu_xyz": [w["nx"], w["ny"], nz_local], "ranks": world,
                    "markers_per_gpu": int(st.n_markers), "decomposition": "z-slabs, halos by peer stores over NVLink" if world > 1 else "single GPU",
                    "halo_overlap": not args.no_overlap, "cuda_graphs": not args.no_graphs,
-                   "plane_split_substeps": int(st.split_substeps),
+                   "plane_split_substeps": int(st.split_substeps), "fused_pair_substeps": int(st.pair_substeps),
                    "l2": f"populations {19 * 4 * cells_local / 1e6:.0f} MB per GPU > 126 MB L2, no flush needed"},
         "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
         "pct_of_hbm_roofline": (value / world) * BYTES_PER_CELL_UPDATE / 1e3 / peak * 100.0,

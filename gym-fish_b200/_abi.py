@@ -27,6 +27,7 @@ FLAG_NO_GRAPHS = 4
 FLAG_FUSED_IB = 8
 FLAG_NO_SPLIT = 16
 FLAG_NO_SWEEP_FLIP = 32
+FLAG_FUSED_PAIRS = 64
 
 _ERR_NAMES = {FG_EINVAL: "FG_EINVAL", FG_ENOMEM: "FG_ENOMEM", FG_ECUDA: "FG_ECUDA", FG_ESTATE: "FG_ESTATE",
               FG_ENOTSUP: "FG_ENOTSUP", FG_EPEER: "FG_EPEER"}
@@ -57,7 +58,8 @@ class FgConfig(C.Structure):
         ("max_links", C.c_int32),
         ("flags", C.c_int32),
         ("split_min_cells", C.c_int32),
-        ("reserved_i", C.c_int32 * 2),
+        ("pair_lag", C.c_int32),
+        ("reserved_i", C.c_int32 * 1),
         ("tau", C.c_double),
         ("mrt_rates", C.c_double * 19),
         ("wall_u", (C.c_double * 3) * 6),
@@ -76,7 +78,7 @@ class FgStats(C.Structure):
         ("n_markers", C.c_int32), ("n_links", C.c_int32),
         ("band_cells", C.c_int32), ("parity", C.c_int32),
         ("collide_ms", C.c_double), ("collide_launches", C.c_int64), ("ib_ms", C.c_double),
-        ("collide_cells", C.c_int64), ("split_substeps", C.c_int64), ("reserved", C.c_int64 * 2),
+        ("collide_cells", C.c_int64), ("split_substeps", C.c_int64), ("pair_substeps", C.c_int64), ("reserved", C.c_int64 * 1),
     ]
 
 

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unistd.h>
@@ -26,6 +27,12 @@ __global__ void __launch_bounds__(K::kThreads, K::kMinBlocks) kern(const __grid_
 template <class K, class P>
 __global__ void __launch_bounds__(K::kThreads, K::kMinBlocks) kern_bp(const __grid_constant__ P p) {
     K::cta(p, int(blockIdx.x), int(threadIdx.x));
+}
+
+// ticket-scheduled kernel (StreamCollidePair): one-dimensional grid, the CTA finds its work through an atomic ticket
+template <class K, class P>
+__global__ void __launch_bounds__(K::kThreads, K::kMinBlocks) kern_ticket(const __grid_constant__ P p) {
+    K::cta(p, int(threadIdx.x));
 }
 
 // phased kernel: K::kPhases phases of grid-stride work separated by grid-wide barriers (cooperative launch)
@@ -123,6 +130,7 @@ public:
         int least = 0, greatest = 0;
         cudaDeviceGetStreamPriorityRange(&least, &greatest);
         prio_low_ = least; prio_high_ = greatest;
+        debug_sync_ = getenv("FG_DEBUG_SYNC") != nullptr;       // debugging aid: serialise every launch
         bool ok = true;
         for (int i = 0; i < kStreams && ok; ++i)
             ok = ck(cudaStreamCreateWithPriority(&s_[i], cudaStreamNonBlocking, i < 2 ? greatest : least), "cudaStreamCreate") &&
@@ -177,6 +185,7 @@ public:
     }
     bool zero(void *d, size_t n) {
         cudaSetDevice(device_);
+        if (gmode_ == 2) return true;   // replaying: the memset is a node of the graph
         return ck(cudaMemsetAsync(d, 0, n, stream_), "memset");
     }
     bool sync() {
@@ -276,7 +285,9 @@ public:
         at[0].id = cudaLaunchAttributePriority;
         at[0].val.priority = cur_ < 2 ? prio_high_ : prio_low_;
         lc.attrs = at; lc.numAttrs = 1;
-        return ck(cudaLaunchKernelEx(&lc, kernel, p), "kernel launch");
+        if (!ck(cudaLaunchKernelEx(&lc, kernel, p), "kernel launch")) return false;
+        if (debug_sync_ && gmode_ == 0) return ck(cudaDeviceSynchronize(), "debug sync");
+        return true;
     }
     // Kernel launches go to stream `current()`.  fork_to(s): stream s starts where the current stream is now and
     // becomes current; switch_to(s): make s current (work already queued elsewhere keeps running beside it);
@@ -303,6 +314,21 @@ public:
         ++launches;
         if (gmode_ == 2) return true;
         return launch_on_current(kern_bp<K, P>, dim3(g.x, g.y, g.z), K::kThreads, p);
+    }
+    // g = (x-blocks, rows, planes) of ONE phase; the launch holds K::kGridPhases times as many CTAs in one dimension
+    template <class K, class P>
+    bool launch_ticketed(Dim3 g, const P &p) {
+        cudaSetDevice(device_);
+        ++launches;
+        if (gmode_ == 2) return true;
+        const long long n = (long long)g.x * g.y * g.z * K::kGridPhases;
+        if (n > 0x7fffffffll) { err = "ticketed launch too large"; return false; }
+        return launch_on_current(kern_ticket<K, P>, dim3(unsigned(n)), K::kThreads, p);
+    }
+    bool zero_on_current(void *d, size_t n) {
+        cudaSetDevice(device_);
+        if (gmode_ == 2) return true;
+        return ck(cudaMemsetAsync(d, 0, n, s_[cur_]), "memset");
     }
     bool supports_phased() const { return coop_; }
     template <class K, class P>
@@ -483,6 +509,7 @@ private:
     cudaEvent_t fork_ev_[kStreams] = {nullptr, nullptr, nullptr, nullptr}, join_ev_[kStreams] = {nullptr, nullptr, nullptr, nullptr};
     int cur_ = 0;
     int prio_low_ = 0, prio_high_ = 0;
+    bool debug_sync_ = false;
     int sm_count_ = 148;
     bool coop_ = false;
     int gmode_ = 0;                 // 0 direct, 1 capturing, 2 replaying

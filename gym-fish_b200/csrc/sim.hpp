@@ -62,6 +62,9 @@ public:
         flags_ = static_cast<int *>(dev.alloc(4 * sizeof(int), err));
         if (!flags_) return FG_ENOMEM;
         if (!dev.zero(flags_, 4 * sizeof(int))) return cuda_fail();
+        pair_ctr_ = static_cast<int *>(dev.alloc(sizeof(int) * size_t(L_.nz + 3), err));
+        if (!pair_ctr_) return FG_ENOMEM;
+        if (!dev.zero(pair_ctr_, sizeof(int) * size_t(L_.nz + 3))) return cuda_fail();
         setup_collision();
         if (cfg.max_markers > 0) {
             if (int rc = ib_.create(dev, cfg, L_, err)) return rc;
@@ -74,6 +77,7 @@ public:
         dev.close_peers();
         dev.free(L_.f); L_.f = nullptr;
         dev.free(flags_); flags_ = nullptr;
+        dev.free(pair_ctr_); pair_ctr_ = nullptr;
         dev.free(solid_); solid_ = nullptr;
         dev.free(stage_[0]); dev.free(stage_[1]); stage_[0] = stage_[1] = nullptr;
         dev.shutdown();
@@ -315,6 +319,27 @@ public:
                     if (far * 4 >= hi - lo && (long long)far * L_.plane >= (cfg.split_min_cells > 0 ? cfg.split_min_cells : (1 << 20))) { split_ = true; near_a_ = a; near_b_ = b; }
                 }
             }
+            // Two substeps in one wavefront launch (StreamCollidePair): opt-in, measured slower than two plain launches
+            // (lbm_core.cuh); no bodies, one rank.
+            if (!prof && (cfg.flags & FG_FLAG_FUSED_PAIRS) && parity_ == 0 && it + 1 < n && !ib_on && !ranks && !L_.solid && L_.nz >= 8) {
+                struct Scope {
+                    Dev &d; bool on; bool done = false;
+                    ~Scope() { if (on && !done) d.graph_abort(); }
+                } scope{dev, graphs && dev.graph_begin(GraphKey{{0x50414952ull, 0, 0, 0}})};
+                int done[2][2];
+                if (!launch_pair(1, L_.nz + 1, 0, 0, done) || !launch_faces()) return cuda_fail();
+                parity_ = 1;
+                // the planes at the range ends (their z-neighbours are ghost planes, set by the face operations above)
+                if (!launch_collide_except(1, L_.nz + 1, ForceField{}, done) || !launch_faces()) return cuda_fail();
+                parity_ = 0;
+                steps_ += 2; pair_substeps_ += 2;
+                ++it;
+                if (scope.on) {
+                    scope.done = true;
+                    if (!dev.graph_end()) return cuda_fail();
+                }
+                continue;
+            }
             // A substep with a far branch is launched kernel by kernel: inside a captured graph the two priorities had no
             // effect on B200 (r1 pass 8/9: 0.137 ms/step as a graph with either the stream priorities, per-node priority
             // attributes + cudaGraphInstantiateFlagUseNodePriority, or the far branch outside the graph; 0.1125 ms direct),
@@ -399,6 +424,7 @@ public:
         o->collide_ms = collide_ms_; o->collide_launches = last_collide_launches_; o->ib_ms = ib_ms_;
         o->collide_cells = last_collide_cells_;
         o->split_substeps = split_substeps_;
+        o->pair_substeps = pair_substeps_;
         return FG_OK;
     }
 
@@ -623,6 +649,60 @@ private:
         return ok;
     }
 
+    // planes [zb, ze) that are in neither of the (ascending, disjoint) ranges done[0], done[1]
+    bool launch_collide_except(int zb, int ze, const ForceField &F, const int done[2][2]) {
+        int at = zb;
+        for (int i = 0; i < 2; ++i) {
+            if (done[i][1] <= done[i][0]) continue;
+            if (!launch_collide(at, std::min(done[i][0], ze), F)) return false;
+            at = std::max(at, done[i][1]);
+        }
+        return launch_collide(at, ze, F);
+    }
+    // EVEN step on planes [zb, ze) minus the hole and, `lag` planes behind it in the same launch, the following ODD step
+    // on the planes whose z-neighbours belong to the launch (lbm_core.cuh StreamCollidePair).  Returns the planes that
+    // took both steps in done[2][2] = up to two ranges [b, e).
+    bool launch_pair(int zb, int ze, int hole_b, int hole_e, int done[2][2]) {
+        if (hole_e <= hole_b || hole_e <= zb || hole_b >= ze) hole_b = hole_e = 0;
+        if (hole_e > hole_b) {
+            if (hole_b <= zb) { zb = hole_e; hole_b = hole_e = 0; }
+            else if (hole_e >= ze) { ze = hole_b; hole_b = hole_e = 0; }
+        }
+        const int hole = hole_e - hole_b, planes = ze - zb - hole;
+        done[0][0] = done[0][1] = done[1][0] = done[1][1] = 0;
+        if (planes <= 0) return true;
+        PairParams p{};
+        p.s = StepParams{L_, C_, ForceField{}, zb, 1, hole ? hole_b : 0x7fffffff, hole, -1, 0, 1, {}};
+        for (int s = 0; s < Q; ++s)
+            for (int d = 0; d < 3; ++d) p.s.kz[s][d] = 4ll * (s * L_.slot + (long long)(d - 1) * L_.plane);
+        p.planes = planes; p.rows = L_.ny; p.xblocks = (L_.nx + 127) / 128;
+        p.lag = std::min(pair_lag(), planes);
+        // a zero-gradient outlet copies from the boundary plane after the even step what the odd step of the plane
+        // next to it would already have overwritten: that plane waits, too
+        const bool out_lo = L_.bc_zlo == BC_OUTLET && L_.z0 == 0 && zb == 1, out_hi = L_.bc_zhi == BC_OUTLET && L_.z0 + L_.nz == L_.nzg && ze == L_.nz + 1;
+        p.odd_lo = out_lo ? 2 : 1; p.odd_hi = planes - (out_hi ? 2 : 1);
+        p.odd_skip_v = hole ? hole_b - zb : -1;
+        p.odd_y_lo = L_.wall_y ? 1 : 0; p.odd_y_hi = L_.wall_y ? L_.ny - 1 : L_.ny;
+        p.ticket = pair_ctr_; p.done = pair_ctr_ + 1;
+        if (hole) { done[0][0] = zb + p.odd_lo; done[0][1] = hole_b - 1; done[1][0] = hole_e + 1; done[1][1] = ze - (out_hi ? 2 : 1); }
+        else { done[0][0] = zb + p.odd_lo; done[0][1] = ze - (out_hi ? 2 : 1); }
+        for (int i = 0; i < 2; ++i) if (done[i][1] < done[i][0]) done[i][0] = done[i][1] = 0;
+        const Dim3 g{p.xblocks, p.rows, planes};
+        if (!dev.zero_on_current(pair_ctr_, sizeof(int) * size_t(planes + 1))) return false;
+        const bool mrt = cfg.collision == FG_MRT;
+        if (L_.wall_x) return mrt ? dev.template launch_ticketed<StreamCollidePair<true, CHECK_XEDGE>>(g, p)
+                                  : dev.template launch_ticketed<StreamCollidePair<false, CHECK_XEDGE>>(g, p);
+        return mrt ? dev.template launch_ticketed<StreamCollidePair<true, CHECK_NONE>>(g, p)
+                   : dev.template launch_ticketed<StreamCollidePair<false, CHECK_NONE>>(g, p);
+    }
+    // the odd step runs this many planes behind the even step: far enough that it never waits, near enough that the
+    // planes in between (lag x 76 B x nx x ny) stay in L2
+    int pair_lag() const {
+        if (cfg.pair_lag > 0) return cfg.pair_lag;
+        const long long plane_bytes = 76ll * L_.plane;
+        return int(std::max<long long>(2, std::min<long long>(8, (24ll << 20) / plane_bytes)));
+    }
+
     // z-face plane ops after the step of parity `parity_`: one launch covers both faces
     bool launch_faces() {
         HaloParams p{};
@@ -702,7 +782,8 @@ private:
     int64_t steps_ = 0;
     double last_ms_ = 0, last_mlups_ = 0, collide_ms_ = 0, ib_ms_ = 0;
     int64_t collide_launches_ = 0, last_collide_launches_ = 0, collide_cells_ = 0, last_collide_cells_ = 0;
-    int64_t split_substeps_ = 0;
+    int64_t split_substeps_ = 0, pair_substeps_ = 0;
+    int *pair_ctr_ = nullptr;      // [1 + nz + 2] ticket + per-plane completion counters of StreamCollidePair
     bool split_ = false;           // this substep: far planes collide beside the IB kernels
     int near_a_ = 1, near_b_ = 1;  // planes [near_a_, near_b_) wait for the IB force
     uint8_t *solid_ = nullptr;

@@ -64,6 +64,7 @@ extern "C" {
 #define FG_FLAG_FUSED_IB   8   /* run the IB phases as ONE cooperative kernel with grid barriers (measured slower on B200: r1) */
 #define FG_FLAG_NO_GRAPHS  4   /* launch every kernel directly instead of replaying per-substep CUDA graphs */
 #define FG_FLAG_NO_SWEEP_FLIP 32 /* sweep the planes upwards in every step (default: odd steps downwards, for L2 reuse between steps) */
+#define FG_FLAG_FUSED_PAIRS 64 /* even step + following odd step as ONE L2-resident wavefront launch (no bodies, one rank); halves DRAM traffic but measured slower on B200 (r1) */
 #define FG_FLAG_NO_SPLIT  16   /* collide all planes after the IB kernels (default: planes away from the bodies run beside them) */
 
 typedef struct FgConfig {
@@ -77,7 +78,8 @@ typedef struct FgConfig {
     int32_t max_links;        /* capacity for rigid links markers can belong to */
     int32_t flags;            /* FG_FLAG_* */
     int32_t split_min_cells;  /* plane split only when at least this many cells lie in far planes; 0 => 1<<20 (~25 us of work) */
-    int32_t reserved_i[2];
+    int32_t pair_lag;         /* FG_FLAG_FUSED_PAIRS: planes between the even and the odd wavefront; 0 => chosen from the plane size */
+    int32_t reserved_i[1];
     double  tau;              /* relaxation time; nu = (tau - 1/2)/3 */
     double  mrt_rates[19];    /* MRT relaxation rates per moment; all zero => SURVEY.md A3 defaults */
     double  wall_u[6][3];     /* wall velocity per face (used where bc == WALL) */
@@ -101,7 +103,8 @@ typedef struct FgStats {
     double  ib_ms;            /* FG_FLAG_PROFILE: summed device time of the immersed-boundary kernels of the last fg_step */
     int64_t collide_cells;    /* ... and how many cell updates those launches did (thin wall-row launches are not in either) */
     int64_t split_substeps;   /* substeps since create whose far-plane collide ran beside the IB kernels (plane split) */
-    int64_t reserved[2];
+    int64_t pair_substeps;    /* substeps since create that ran as half of a fused even+odd pair (StreamCollidePair) */
+    int64_t reserved[1];
 } FgStats;
 
 /* articulated swimmer description: a planar chain of n_links ellipsoid links, yawing joints */

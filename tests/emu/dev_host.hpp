@@ -68,6 +68,19 @@ public:
         return true;
     }
 
+    // ticket-scheduled kernels: on the GPU the phases interleave along a wavefront; here every CTA of phase 0, then phase 1
+    template <class K, class P>
+    bool launch_ticketed(Dim3 g, const P &p) {
+        ++launches;
+        for (int ph = 0; ph < K::kGridPhases; ++ph)
+            for (int bz = 0; bz < g.z; ++bz)
+                for (int by = 0; by < g.y; ++by)
+                    for (int bx = 0; bx < g.x; ++bx)
+                        for (int tx = 0; tx < K::kThreads; ++tx) K::run(p, bx, by, bz, tx, ph);
+        return true;
+    }
+    bool zero_on_current(void *d, size_t n) { std::memset(d, 0, n); return true; }
+
     // phased kernels (one cooperative launch on the GPU): phases in order, every item of a phase before the next
     bool supports_phased() const { return true; }
     template <class K, class P>

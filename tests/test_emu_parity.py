@@ -123,6 +123,28 @@ def test_plane_split_far_collide_beside_ib_kernels(g, emu, walls):
     assert np.abs(wa - wo).max() / np.abs(wo).max() <= TOL_FORCE
 
 
+@pytest.mark.parametrize("name", ["bgk_periodic", "mrt_force", "bgk_ywall_moving", "mrt_xy_walls", "mrt_all_walls_lid", "bgk_inlet_outlet",
+                                  "mrt_inlet_outlet_ywalls", "mrt_outlet_inlet_xwalls"])
+def test_fused_step_pairs_are_bit_identical_to_single_steps(g, emu, name):
+    """StreamCollidePair (opt-in, FG_FLAG_FUSED_PAIRS): even step + following odd step of the same planes in one launch.  Per cell it is the same
+    arithmetic in the same order, so populations must not differ by a bit from stepping one launch per step, for any
+    number of substeps per call (pairs only form inside one fg_step call) and every boundary kind."""
+    kw = dict(util.parity_cases(g)[name], nz=12)
+    a, b = g.Sim(backend=emu, flags=g._abi.FLAG_FUSED_PAIRS, **kw), g.Sim(backend=emu, **kw)
+    rho, u = util.smooth_fields(a.shape)
+    for s in (a, b):
+        s.set_fields(rho, u)
+    for n in (2, 1, 5, 4):
+        a.step(n)
+        b.step(n)
+        assert np.array_equal(a.get_populations(), b.get_populations()), (name, n)
+    assert a.stats().pair_substeps == 10 and b.stats().pair_substeps == 0     # 2 + 0 + (1 single, then 4) + 4
+    o = g.Sim(backend="oracle", **kw)
+    o.set_fields(rho, u)
+    o.step(12)
+    assert util.rel_l2(a.get_fields(f64=True)[1], o.get_fields(f64=True)[1]) <= TOL_FIELD
+
+
 def test_no_markers_and_marker_removal(g, emu):
     kw = dict(nx=10, ny=10, nz=10, tau=0.8, max_markers=64, max_links=1)
     a, b = g.Sim(backend="oracle", **kw), g.Sim(backend=emu, **kw)

@@ -154,6 +154,26 @@ def test_plane_split_full_size_sphere_channel(g, cuda):
         s.close()
 
 
+@pytest.mark.parametrize("name", ["bgk_periodic", "mrt_force", "bgk_ywall_moving", "mrt_xy_walls", "mrt_all_walls_lid",
+                                  "mrt_inlet_outlet_ywalls", "mrt_outlet_inlet_xwalls"])
+@pytest.mark.parametrize("lag", [0, 1, 3])
+def test_fused_step_pairs_are_bit_identical_to_single_steps(g, cuda, name, lag):
+    """StreamCollidePair on the GPU: the odd step chases the even step through the planes inside one launch (tickets +
+    per-plane completion counters).  Large enough that thousands of CTAs are in flight; populations must equal the
+    one-launch-per-step run bit for bit (any race would show up as a difference)."""
+    kw = dict(util.parity_cases(g)[name], nx=200, ny=48, nz=40, pair_lag=lag)
+    a, b = g.Sim(backend=cuda, flags=g._abi.FLAG_FUSED_PAIRS, **kw), g.Sim(backend=cuda, **kw)
+    rho, u = util.smooth_fields(a.shape)
+    for s in (a, b):
+        s.set_fields(rho, u)
+    for n in (2, 1, 5, 40):
+        a.step(n)
+        b.step(n)
+        assert np.array_equal(a.get_populations(), b.get_populations()), (name, n)
+    assert a.stats().pair_substeps == 46 and b.stats().pair_substeps == 0
+    a.close(); b.close()
+
+
 def test_spread_force_equals_marker_force_on_gpu(g, cuda):
     kw = dict(nx=48, ny=48, nz=48, tau=0.8, collision=g.MRT, max_markers=2000, max_links=1)
     s = g.Sim(backend=cuda, **kw)
