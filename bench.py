@@ -239,6 +239,7 @@ def main():
     ap.add_argument("--no-flip", action="store_true", help="sweep planes upwards in every step (no L2 reuse between steps)")
     ap.add_argument("--pairs", action="store_true", help="fused even+odd wavefront launches (opt-in experiment, measured slower)")
     ap.add_argument("--pair-lag", type=int, default=0, help="planes between the even and odd wavefront (0: automatic)")
+    ap.add_argument("--no-xwarp", action="store_true", help="x walls: predicated wall code in every thread instead of only in the row-end warps")
     ap.add_argument("--no-split", action="store_true", help="collide all planes after the IB kernels (no far-plane branch beside them)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer loop (default: --steps)")
     args = ap.parse_args()
@@ -274,7 +275,7 @@ def main():
     w = WORKLOADS[wl]
     flags = ((g._abi.FLAG_NO_OVERLAP if args.no_overlap else 0) | (g._abi.FLAG_NO_GRAPHS if args.no_graphs else 0) |
              (g._abi.FLAG_NO_SPLIT if args.no_split else 0) | (g._abi.FLAG_NO_SWEEP_FLIP if args.no_flip else 0) |
-             (g._abi.FLAG_FUSED_PAIRS if args.pairs else 0))
+             (g._abi.FLAG_FUSED_PAIRS if args.pairs else 0) | (g._abi.FLAG_NO_XWARP if args.no_xwarp else 0))
     sim, markers = make_sim(g, "cuda", wl, rank, world, local, flags=flags, extra=dict(pair_lag=args.pair_lag))
     if world > 1:
         handles = [None] * world

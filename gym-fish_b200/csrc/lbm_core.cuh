@@ -377,8 +377,9 @@ FG_HD void store_departing(const float (&h)[Q], const Lattice &L, const Collisio
 // boundary code and fits 64 registers (8 CTAs of 128 threads per SM):
 //   CHECK_NONE  no link can be blocked in the rows / planes of this launch
 //   CHECK_XEDGE only the two cells at the ends of each row can (x walls): predicated pointer selects, no divergence
+//   CHECK_XWARP the same, but only the two warps at the ends of a row run the predicated code (warp-uniform branch)
 //   CHECK_ALL   wall rows (y walls), wall planes (z walls), or obstacles anywhere
-enum : int { CHECK_NONE = 0, CHECK_ALL = 1, CHECK_XEDGE = 2 };
+enum : int { CHECK_NONE = 0, CHECK_ALL = 1, CHECK_XEDGE = 2, CHECK_XWARP = 3 };
 
 // ---- bulk path addressing.  ncu showed the first version of the odd kernel issue-limited by 64-bit address
 // arithmetic (4-5 integer instructions per access, more than the MRT itself).  Here a thread builds the 9 pointers to
@@ -516,6 +517,12 @@ struct StreamCollide {
         if (x >= p.L.nx) return;
         if (MODE == CHECK_ALL) checked_cell(p, x, y, zz);
         else if (MODE == CHECK_XEDGE) bulk_cell<true>(p, x, y, zz);
+        else if (MODE == CHECK_XWARP) {
+            // only the warps that hold the first / last cell of a row pay for the wall selects (warp-uniform branch)
+            const int w0 = x & ~31;
+            if (w0 == 0 || w0 + 32 >= p.L.nx) bulk_cell<true>(p, x, y, zz);
+            else bulk_cell<false>(p, x, y, zz);
+        }
         else bulk_cell<false>(p, x, y, zz);
     }
 };

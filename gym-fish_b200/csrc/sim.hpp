@@ -607,6 +607,7 @@ private:
             switch (mode) {
                 case CHECK_ALL: ok = launch_collide_pm<1, CHECK_ALL>(p, g); break;
                 case CHECK_XEDGE: ok = launch_collide_pm<1, CHECK_XEDGE>(p, g); break;
+                case CHECK_XWARP: ok = launch_collide_pm<1, CHECK_XWARP>(p, g); break;
                 default: ok = launch_collide_pm<1, CHECK_NONE>(p, g); break;
             }
         }
@@ -636,7 +637,7 @@ private:
         if (thin) ok = dev.fork_to(base + 1);
         if (zlo_wall && zb <= 1 && 1 < ze) { ok = ok && launch_rows(CHECK_ALL, 1, 2, 0, 1, ny, F); zb = 2; }
         if (zhi_wall && zb <= L_.nz && L_.nz < ze) { ok = ok && launch_rows(CHECK_ALL, L_.nz, L_.nz + 1, 0, 1, ny, F); ze = L_.nz; }
-        const int bulk = L_.wall_x ? CHECK_XEDGE : CHECK_NONE;
+        const int bulk = L_.wall_x ? ((cfg.flags & FG_FLAG_NO_XWARP) ? CHECK_XEDGE : CHECK_XWARP) : CHECK_NONE;
         if (L_.wall_y && ny >= 2) {
             ok = ok && launch_rows(CHECK_ALL, zb, ze, 0, ny - 1, 2, F, zstride, hole_b, hole_e);
             if (thin) ok = ok && dev.switch_to(base);

@@ -145,6 +145,27 @@ def test_fused_step_pairs_are_bit_identical_to_single_steps(g, emu, name):
     assert util.rel_l2(a.get_fields(f64=True)[1], o.get_fields(f64=True)[1]) <= TOL_FIELD
 
 
+@pytest.mark.parametrize("name", ["mrt_xy_walls", "mrt_all_walls_lid", "mrt_outlet_inlet_xwalls"])
+def test_xwall_warp_uniform_variant_is_bit_identical(g, emu, name):
+    """CHECK_XWARP (default): only the warps at the ends of a row run the x-wall code.  Same arithmetic per cell
+    as CHECK_XEDGE (FG_FLAG_NO_XWARP: predicated selects in every thread), on rows wide enough to have interior warps, with a moving
+    x wall so that the wall term matters."""
+    kw = dict(util.parity_cases(g)[name], nx=100, ny=9, nz=6)
+    wu = dict(kw.get("wall_u", {}))
+    wu[g._abi.XLO] = [0, 0.02, 0.01]
+    kw["wall_u"] = wu
+    a, b = g.Sim(backend=emu, flags=g._abi.FLAG_NO_XWARP, **kw), g.Sim(backend=emu, **kw)
+    rho, u = util.smooth_fields(a.shape)
+    for s in (a, b):
+        s.set_fields(rho, u)
+        s.step(7)
+    assert np.array_equal(a.get_populations(), b.get_populations())
+    o = g.Sim(backend="oracle", **kw)
+    o.set_fields(rho, u)
+    o.step(7)
+    assert util.rel_l2(a.get_fields(f64=True)[1], o.get_fields(f64=True)[1]) <= TOL_FIELD
+
+
 def test_no_markers_and_marker_removal(g, emu):
     kw = dict(nx=10, ny=10, nz=10, tau=0.8, max_markers=64, max_links=1)
     a, b = g.Sim(backend="oracle", **kw), g.Sim(backend=emu, **kw)
