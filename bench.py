@@ -240,6 +240,8 @@ def main():
     ap.add_argument("--pairs", action="store_true", help="fused even+odd wavefront launches (opt-in experiment, measured slower)")
     ap.add_argument("--pair-lag", type=int, default=0, help="planes between the even and odd wavefront (0: automatic)")
     ap.add_argument("--no-xwarp", action="store_true", help="x walls: predicated wall code in every thread instead of only in the row-end warps")
+    ap.add_argument("--storage", default="f32", choices=["f32", "f16"],
+                    help="f16: the opt-in 16-bit-storage build (fp32 arithmetic, 76 B per cell update; NOT the headline configuration)")
     ap.add_argument("--no-split", action="store_true", help="collide all planes after the IB kernels (no far-plane branch beside them)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer loop (default: --steps)")
     args = ap.parse_args()
@@ -276,7 +278,9 @@ def main():
     flags = ((g._abi.FLAG_NO_OVERLAP if args.no_overlap else 0) | (g._abi.FLAG_NO_GRAPHS if args.no_graphs else 0) |
              (g._abi.FLAG_NO_SPLIT if args.no_split else 0) | (g._abi.FLAG_NO_SWEEP_FLIP if args.no_flip else 0) |
              (g._abi.FLAG_FUSED_PAIRS if args.pairs else 0) | (g._abi.FLAG_NO_XWARP if args.no_xwarp else 0))
-    sim, markers = make_sim(g, "cuda", wl, rank, world, local, flags=flags, extra=dict(pair_lag=args.pair_lag))
+    gpu_backend = "cuda" if args.storage == "f32" else "cuda_f16"
+    bytes_per_update = BYTES_PER_CELL_UPDATE if args.storage == "f32" else BYTES_PER_CELL_UPDATE / 2
+    sim, markers = make_sim(g, gpu_backend, wl, rank, world, local, flags=flags, extra=dict(pair_lag=args.pair_lag))
     if world > 1:
         handles = [None] * world
         dist.all_gather_object(handles, sim.peer_export())
@@ -407,19 +411,19 @@ def main():
     if collide_n > 0 and collide_ms > 0:
         # algorithmic bytes per launch = 152 B x cells the launch updates; averaged over the bulk launches of the timed
         # region (the thin checked launches for wall rows run beside them on another stream and are in neither sum)
-        achieved = BYTES_PER_CELL_UPDATE * collide_cells / (collide_ms * 1e-3) / 1e9
+        achieved = bytes_per_update * collide_cells / (collide_ms * 1e-3) / 1e9
         traffic, traffic_src = None, None
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[wl]
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[wl if args.storage == "f32" else wl + "_f16"]
             traffic, traffic_src = tj["dram_bytes_per_launch"], "profiles/r1_traffic.json (ncu --set full capture of this workload)"
         except Exception:
             pass
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "traffic_source": traffic_src, "algorithmic_bytes_per_launch": BYTES_PER_CELL_UPDATE * collide_cells / collide_n,
+                "traffic_source": traffic_src, "algorithmic_bytes_per_launch": bytes_per_update * collide_cells / collide_n,
                 "kernel": "fg::StreamCollide<parity, MRT> (even+odd average)", "peak_source": peak_src,
                 "kernel_ms_per_launch": collide_ms / collide_n, "launches_timed": int(collide_n),
                 "cells_per_launch": collide_cells / collide_n,
-                "bytes_per_cell_update": BYTES_PER_CELL_UPDATE, "ib_ms_per_step": ib_ms / args.steps,
+                "bytes_per_cell_update": bytes_per_update, "ib_ms_per_step": ib_ms / args.steps,
                 "timed_in": "second pass of the same K steps with event brackets (FG_FLAG_PROFILE)",
                 "profiled_pass_ms_per_step": profiled_ms / args.steps}
     cpu = None
@@ -433,14 +437,14 @@ def main():
         "metric": "MLUPS (million lattice-cell updates per second), coupled D3Q19 MRT + IB step",
         "value": value, "unit": "MLUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if w.get("strong") else "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": w["desc"], "name": wl, "grid_per_gpu_xyz": [w["nx"], w["ny"], nz_local], "ranks": world,
+        "dtype": "f32" if args.storage == "f32" else "f32 arithmetic on f16-stored populations (opt-in build)", "data": "synthetic",
+        "config": {"workload": w["desc"], "name": wl, "population_storage": args.storage, "grid_per_gpu_xyz": [w["nx"], w["ny"], nz_local], "ranks": world,
                    "markers_per_gpu": int(st.n_markers), "decomposition": "z-slabs, halos by peer stores over NVLink" if world > 1 else "single GPU",
                    "halo_overlap": not args.no_overlap, "cuda_graphs": not args.no_graphs,
                    "plane_split_substeps": int(st.split_substeps), "fused_pair_substeps": int(st.pair_substeps),
-                   "l2": f"populations {19 * 4 * cells_local / 1e6:.0f} MB per GPU > 126 MB L2, no flush needed"},
+                   "l2": f"populations {19 * (4 if args.storage == 'f32' else 2) * cells_local / 1e6:.0f} MB per GPU > 126 MB L2, no flush needed"},
         "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
-        "pct_of_hbm_roofline": (value / world) * BYTES_PER_CELL_UPDATE / 1e3 / peak * 100.0,
+        "pct_of_hbm_roofline": (value / world) * bytes_per_update / 1e3 / peak * 100.0,
     }
     print(json.dumps(line), flush=True)
     sim.close()

@@ -102,6 +102,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _REPO = os.path.dirname(_HERE)
 LIB_PATHS = {
     "cuda": os.path.join(_HERE, "csrc", "libfishgym_cuda.so"),
+    # opt-in build of the same sources: 16-bit population storage, fp32 arithmetic (half the HBM bytes per update)
+    "cuda_f16": os.path.join(_HERE, "csrc", "libfishgym_cuda_f16.so"),
     "oracle": os.path.join(_REPO, "oracle", "libfishgym_oracle.so"),
 }
 
@@ -160,7 +162,7 @@ def load_library(backend: str = "cuda") -> C.CDLL:
         return _LIBS[backend]
     path = LIB_PATHS.get(backend, backend)
     if not os.path.exists(path):
-        hint = ("run `python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a)" if backend == "cuda"
+        hint = ("run `python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a)" if backend.startswith("cuda")
                 else "run `make -C oracle`")
         raise FileNotFoundError(f"fishgym backend '{backend}' not built: {path} is missing; {hint}")
     lib = C.CDLL(path, mode=C.RTLD_LOCAL)

@@ -351,7 +351,7 @@ public:
 
     // ---- z-neighbour lattices: same process => raw pointer (+ peer access); other process => CUDA IPC
     template <class Blob>
-    bool export_peer(float *f, int *flags, void *x, Blob &b, std::string &e) {
+    bool export_peer(pop_t *f, int *flags, void *x, Blob &b, std::string &e) {
         cudaSetDevice(device_);
         b.pid = int(getpid()); b.device = device_;
         b.f_ptr = reinterpret_cast<uint64_t>(f); b.flag_ptr = reinterpret_cast<uint64_t>(flags); b.x_ptr = reinterpret_cast<uint64_t>(x);
@@ -387,7 +387,7 @@ public:
         return ck(cudaGetLastError(), "wait launch");
     }
     template <class Blob>
-    bool open_peer(const Blob &b, float **f, int **flags, void **x, std::string &e) {
+    bool open_peer(const Blob &b, pop_t **f, int **flags, void **x, std::string &e) {
         cudaSetDevice(device_);
         if (b.pid == int(getpid())) {
             if (b.device != device_) {
@@ -398,12 +398,12 @@ public:
                 if (rc != cudaSuccess && rc != cudaErrorPeerAccessAlreadyEnabled) { ck(rc, "cudaDeviceEnablePeerAccess"); e = err; return false; }
                 cudaGetLastError();
             }
-            *f = reinterpret_cast<float *>(b.f_ptr); *flags = reinterpret_cast<int *>(b.flag_ptr); *x = reinterpret_cast<void *>(b.x_ptr);
+            *f = reinterpret_cast<pop_t *>(b.f_ptr); *flags = reinterpret_cast<int *>(b.flag_ptr); *x = reinterpret_cast<void *>(b.x_ptr);
             return true;
         }
         void *pf = open_ipc(b.f_ipc), *pg = open_ipc(b.flag_ipc);
         if (!pf || !pg) { e = err; return false; }
-        *f = static_cast<float *>(pf); *flags = static_cast<int *>(pg);
+        *f = static_cast<pop_t *>(pf); *flags = static_cast<int *>(pg);
         *x = nullptr;
         if (b.x_ptr) {
             *x = open_ipc(b.x_ipc);

@@ -3,5 +3,9 @@
 #include "lbm_core.cuh"
 #include "dev_cuda.cuh"
 #define FG_DEV fg::CudaDev
+#if defined(FG_POP16)
+#define FG_BACKEND_NAME "cuda-sm100a-f16"    // 16-bit population storage, fp32 arithmetic (opt-in build)
+#else
 #define FG_BACKEND_NAME "cuda-sm100a"
+#endif
 #include "abi_impl.hpp"

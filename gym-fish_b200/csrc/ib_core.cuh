@@ -220,7 +220,7 @@ struct IbBandMoments {
         float h[Q];
         if (L.solid && L.solid[idx]) {
             FG_UNROLL
-            for (int i = 0; i < Q; ++i) h[i] = L.f[i * L.slot + idx];   // obstacles keep their initial state (as in the oracle)
+            for (int i = 0; i < Q; ++i) h[i] = pop_ld(L.f + i * L.slot + idx);   // obstacles keep their initial state (as in the oracle)
         } else {
             load_arriving<PARITY, true>(h, L, p.C, nb, idx);
         }
@@ -412,7 +412,7 @@ struct ProbeMoments {
             float h[Q];
             if (L.solid && L.solid[idx]) {
                 FG_UNROLL
-                for (int i = 0; i < Q; ++i) h[i] = L.f[i * L.slot + idx];
+                for (int i = 0; i < Q; ++i) h[i] = pop_ld(L.f + i * L.slot + idx);
             } else {
                 load_arriving<PARITY, true>(h, L, p.C, nb, idx);
             }

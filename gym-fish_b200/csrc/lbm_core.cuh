@@ -30,7 +30,35 @@
 #define FG_UNROLL
 #endif
 
+// Population storage type, fixed at compile time.  The product library stores fp32 (BASELINE.json:5); the same sources
+// built with -DFG_POP16 give libfishgym_cuda_f16.so: 16-bit storage of the SHIFTED populations, scaled by 2^12 so that
+// near-rest flows stay out of the subnormal range, fp32 arithmetic — 76 B per cell update instead of 152.
+#if defined(FG_POP16)
+#if defined(__CUDACC__)
+#include <cuda_fp16.h>
+#endif
+#endif
+
 namespace fg {
+
+#if defined(FG_POP16)
+#if defined(__CUDACC__)
+typedef __half pop_t;
+FG_HD float pop_ld(const pop_t *p) { return __half2float(*p) * (1.0f / 4096.0f); }
+FG_HD void pop_st(pop_t *p, float v) { *p = __float2half_rn(v * 4096.0f); }
+#else
+typedef _Float16 pop_t;
+FG_HD float pop_ld(const pop_t *p) { return float(*p) * (1.0f / 4096.0f); }
+FG_HD void pop_st(pop_t *p, float v) { *p = pop_t(v * 4096.0f); }
+#endif
+#define FG_POP_NAME "f16"
+#else
+typedef float pop_t;
+FG_HD float pop_ld(const pop_t *p) { return *p; }
+FG_HD void pop_st(pop_t *p, float v) { *p = v; }
+#define FG_POP_NAME "f32"
+#endif
+constexpr int kPopBytes = int(sizeof(pop_t));
 
 constexpr int Q = 19;
 // SURVEY.md A1 (d'Humieres ordering)
@@ -68,7 +96,7 @@ enum : int { BC_PERIODIC = 0, BC_WALL = 1, BC_INLET = 2, BC_OUTLET = 3, BC_PEER 
 enum : int { F_XLO = 0, F_XHI = 1, F_YLO = 2, F_YHI = 3, F_ZLO = 4, F_ZHI = 5 };
 
 struct Lattice {
-    float *f;             // slot q lives at f + q*slot
+    pop_t *f;             // slot q lives at f + q*slot
     long long slot;       // (nz+2)*ny*nx
     int nx, ny, nz;       // local slab (interior planes zz = 1..nz)
     int plane;            // nx*ny
@@ -102,7 +130,7 @@ struct StepParams {
     int zz_skip_begin, zz_skip_len;   // ... and from zz_skip_begin on, zz_skip_len planes further up (a launch with a hole)
     int zz_flip;              // >= 0: blockIdx.z is replaced by zz_flip - blockIdx.z, i.e. the planes are swept downwards
     int y0, ystride;       // rows this launch covers: y = y0 + blockIdx.y * ystride
-    long long kz[Q][3];    // byte offset of (slot S, plane z-1 / z / z+1) from a cell of plane z: 4*(S*slot + dz*plane)
+    long long kz[Q][3];    // byte offset of (slot S, plane z-1 / z / z+1) from a cell of plane z: kPopBytes*(S*slot + dz*plane)
 };
 
 // ---------------------------------------------------------------- collide (registers only)
@@ -305,7 +333,7 @@ template <int I, bool CHECK>
 FG_HD void odd_load_pair(float (&h)[Q], const Lattice &L, const Collision &C, const Nbr &nb, long long idx) {
     using D = Dir<I>;
     constexpr int J = D::opp;
-    const float *fI = L.f + I * L.slot, *fJ = L.f + J * L.slot;
+    const pop_t *fI = L.f + I * L.slot, *fJ = L.f + J * L.slot;
     const int om = nb.off<-D::cx, -D::cy, -D::cz>();   // towards x - c_I
     const int op = nb.off<D::cx, D::cy, D::cz>();      // towards x + c_I
     if (CHECK) {
@@ -313,11 +341,11 @@ FG_HD void odd_load_pair(float (&h)[Q], const Lattice &L, const Collision &C, co
         const int wp = nb.wall<D::cx, D::cy, D::cz>();
         const bool bm = wm >= 0 || (L.solid && L.solid[idx + om]);
         const bool bp = wp >= 0 || (L.solid && L.solid[idx + op]);
-        h[I] = bm ? fI[idx] + (wm >= 0 ? C.wallterm[wm][I] : 0.0f) : fJ[idx + om];
-        h[J] = bp ? fJ[idx] + (wp >= 0 ? C.wallterm[wp][J] : 0.0f) : fI[idx + op];
+        h[I] = bm ? pop_ld(fI + idx) + (wm >= 0 ? C.wallterm[wm][I] : 0.0f) : pop_ld(fJ + idx + om);
+        h[J] = bp ? pop_ld(fJ + idx) + (wp >= 0 ? C.wallterm[wp][J] : 0.0f) : pop_ld(fI + idx + op);
     } else {
-        h[I] = fJ[idx + om];
-        h[J] = fI[idx + op];
+        h[I] = pop_ld(fJ + idx + om);
+        h[J] = pop_ld(fI + idx + op);
     }
 }
 
@@ -325,7 +353,7 @@ template <int I, bool CHECK>
 FG_HD void odd_store_pair(const float (&h)[Q], const Lattice &L, const Collision &C, const Nbr &nb, long long idx) {
     using D = Dir<I>;
     constexpr int J = D::opp;
-    float *fI = L.f + I * L.slot, *fJ = L.f + J * L.slot;
+    pop_t *fI = L.f + I * L.slot, *fJ = L.f + J * L.slot;
     const int om = nb.off<-D::cx, -D::cy, -D::cz>();
     const int op = nb.off<D::cx, D::cy, D::cz>();
     if (CHECK) {
@@ -333,11 +361,11 @@ FG_HD void odd_store_pair(const float (&h)[Q], const Lattice &L, const Collision
         const int wp = nb.wall<D::cx, D::cy, D::cz>();
         const bool bm = wm >= 0 || (L.solid && L.solid[idx + om]);
         const bool bp = wp >= 0 || (L.solid && L.solid[idx + op]);
-        if (bp) fJ[idx] = h[I] + (wp >= 0 ? C.wallterm[wp][J] : 0.0f); else fI[idx + op] = h[I];
-        if (bm) fI[idx] = h[J] + (wm >= 0 ? C.wallterm[wm][I] : 0.0f); else fJ[idx + om] = h[J];
+        if (bp) pop_st(fJ + idx, h[I] + (wp >= 0 ? C.wallterm[wp][J] : 0.0f)); else pop_st(fI + idx + op, h[I]);
+        if (bm) pop_st(fI + idx, h[J] + (wm >= 0 ? C.wallterm[wm][I] : 0.0f)); else pop_st(fJ + idx + om, h[J]);
     } else {
-        fI[idx + op] = h[I];
-        fJ[idx + om] = h[J];
+        pop_st(fI + idx + op, h[I]);
+        pop_st(fJ + idx + om, h[J]);
     }
 }
 
@@ -347,9 +375,9 @@ template <int PARITY, bool CHECK>
 FG_HD void load_arriving(float (&h)[Q], const Lattice &L, const Collision &C, const Nbr &nb, long long idx) {
     if (PARITY == 0) {
         FG_UNROLL
-        for (int i = 0; i < Q; ++i) h[i] = L.f[i * L.slot + idx];
+        for (int i = 0; i < Q; ++i) h[i] = pop_ld(L.f + i * L.slot + idx);
     } else {
-        h[0] = L.f[idx];
+        h[0] = pop_ld(L.f + idx);
 #define FG_X(I) odd_load_pair<I, CHECK>(h, L, C, nb, idx);
         FG_FOR_PAIRS(FG_X)
 #undef FG_X
@@ -359,12 +387,12 @@ FG_HD void load_arriving(float (&h)[Q], const Lattice &L, const Collision &C, co
 template <int PARITY, bool CHECK>
 FG_HD void store_departing(const float (&h)[Q], const Lattice &L, const Collision &C, const Nbr &nb, long long idx) {
     if (PARITY == 0) {
-        L.f[idx] = h[0];
-#define FG_X(I) L.f[Dir<I>::opp * L.slot + idx] = h[I]; L.f[I * L.slot + idx] = h[Dir<I>::opp];
+        pop_st(L.f + idx, h[0]);
+#define FG_X(I) pop_st(L.f + Dir<I>::opp * L.slot + idx, h[I]); pop_st(L.f + I * L.slot + idx, h[Dir<I>::opp]);
         FG_FOR_PAIRS(FG_X)
 #undef FG_X
     } else {
-        L.f[idx] = h[0];
+        pop_st(L.f + idx, h[0]);
 #define FG_X(I) odd_store_pair<I, CHECK>(h, L, C, nb, idx);
         FG_FOR_PAIRS(FG_X)
 #undef FG_X
@@ -396,8 +424,8 @@ template <bool XEDGE>
 FG_HD NbrPtrs make_ptrs(const Lattice &L, int x, int y, long long idx) {
     NbrPtrs n;
     char *pc = reinterpret_cast<char *>(L.f + idx);
-    const int dxm = (x == 0 ? L.nx - 1 : -1) * 4, dxp = (x == L.nx - 1 ? -(L.nx - 1) : 1) * 4;
-    const int dym = (y == 0 ? (L.ny - 1) * L.nx : -L.nx) * 4, dyp = (y == L.ny - 1 ? -(L.ny - 1) * L.nx : L.nx) * 4;
+    const int dxm = (x == 0 ? L.nx - 1 : -1) * kPopBytes, dxp = (x == L.nx - 1 ? -(L.nx - 1) : 1) * kPopBytes;
+    const int dym = (y == 0 ? (L.ny - 1) * L.nx : -L.nx) * kPopBytes, dyp = (y == L.ny - 1 ? -(L.ny - 1) * L.nx : L.nx) * kPopBytes;
     n.p[1][1] = pc;
     n.p[0][1] = pc + dxm; n.p[2][1] = pc + dxp;
     n.p[1][0] = pc + dym; n.p[1][2] = pc + dyp;
@@ -420,11 +448,11 @@ FG_HD void fast_odd_load_pair(float (&h)[Q], const StepParams &p, const NbrPtrs 
         const bool bp = D::cx > 0 ? n.bxp : n.bxm;   // the cell at x + c_I is behind the wall
         const char *own_i = n.p[1][1] + p.kz[I][1], *own_j = n.p[1][1] + p.kz[J][1];
         const float wi = p.C.wallterm[D::cx > 0 ? F_XLO : F_XHI][I], wj = p.C.wallterm[D::cx > 0 ? F_XHI : F_XLO][J];
-        h[I] = *reinterpret_cast<const float *>(bm ? own_i : am) + (bm ? wi : 0.0f);
-        h[J] = *reinterpret_cast<const float *>(bp ? own_j : ap) + (bp ? wj : 0.0f);
+        h[I] = pop_ld(reinterpret_cast<const pop_t *>(bm ? own_i : am)) + (bm ? wi : 0.0f);
+        h[J] = pop_ld(reinterpret_cast<const pop_t *>(bp ? own_j : ap)) + (bp ? wj : 0.0f);
     } else {
-        h[I] = *reinterpret_cast<const float *>(am);
-        h[J] = *reinterpret_cast<const float *>(ap);
+        h[I] = pop_ld(reinterpret_cast<const pop_t *>(am));
+        h[J] = pop_ld(reinterpret_cast<const pop_t *>(ap));
     }
 }
 
@@ -439,11 +467,11 @@ FG_HD void fast_odd_store_pair(const float (&h)[Q], const StepParams &p, const N
         const bool bp = D::cx > 0 ? n.bxp : n.bxm;
         char *own_i = n.p[1][1] + p.kz[I][1], *own_j = n.p[1][1] + p.kz[J][1];
         const float wi = p.C.wallterm[D::cx > 0 ? F_XLO : F_XHI][I], wj = p.C.wallterm[D::cx > 0 ? F_XHI : F_XLO][J];
-        *reinterpret_cast<float *>(bp ? own_j : ap) = h[I] + (bp ? wj : 0.0f);   // f*_I bounces into slot J of this cell
-        *reinterpret_cast<float *>(bm ? own_i : am) = h[J] + (bm ? wi : 0.0f);
+        pop_st(reinterpret_cast<pop_t *>(bp ? own_j : ap), h[I] + (bp ? wj : 0.0f));   // f*_I bounces into slot J of this cell
+        pop_st(reinterpret_cast<pop_t *>(bm ? own_i : am), h[J] + (bm ? wi : 0.0f));
     } else {
-        *reinterpret_cast<float *>(ap) = h[I];
-        *reinterpret_cast<float *>(am) = h[J];
+        pop_st(reinterpret_cast<pop_t *>(ap), h[I]);
+        pop_st(reinterpret_cast<pop_t *>(am), h[J]);
     }
 }
 
@@ -494,14 +522,14 @@ struct StreamCollide {
             store_departing<0, false>(h, L, p.C, nb, idx);
         } else {
             const NbrPtrs n = make_ptrs<XEDGE>(L, x, y, idx);
-            h[0] = *reinterpret_cast<const float *>(n.p[1][1] + p.kz[0][1]);
+            h[0] = pop_ld(reinterpret_cast<const pop_t *>(n.p[1][1] + p.kz[0][1]));
 #define FG_X(I) fast_odd_load_pair<I, XEDGE>(h, p, n);
             FG_FOR_PAIRS(FG_X)
 #undef FG_X
             float Fx, Fy, Fz;
             force_at(p, y, zz, idx, Fx, Fy, Fz);
             if (MRT) collide_mrt(h, Fx, Fy, Fz, p.C); else collide_bgk(h, Fx, Fy, Fz, p.C);
-            *reinterpret_cast<float *>(n.p[1][1] + p.kz[0][1]) = h[0];
+            pop_st(reinterpret_cast<pop_t *>(n.p[1][1] + p.kz[0][1]), h[0]);
 #define FG_X(I) fast_odd_store_pair<I, XEDGE>(h, p, n);
             FG_FOR_PAIRS(FG_X)
 #undef FG_X
@@ -665,7 +693,7 @@ struct InitEquilibrium {
         float h[Q];
         shifted_equilibrium(dr, ux, uy, uz, h);
         FG_UNROLL
-        for (int i = 0; i < Q; ++i) L.f[i * L.slot + idx] = h[i];
+        for (int i = 0; i < Q; ++i) pop_st(L.f + i * L.slot + idx, h[i]);
     }
 };
 
@@ -691,7 +719,7 @@ struct GatherArriving {
         float h[Q];
         if (L.solid && L.solid[idx]) {
             FG_UNROLL
-            for (int i = 0; i < Q; ++i) h[i] = L.f[i * L.slot + idx];   // solid cells keep whatever they hold
+            for (int i = 0; i < Q; ++i) h[i] = pop_ld(L.f + i * L.slot + idx);   // solid cells keep whatever they hold
         } else {
             load_arriving<PARITY, true>(h, L, p.C, nb, idx);
         }
@@ -718,10 +746,10 @@ struct GatherArriving {
 struct FaceOp {
     int mode;                  // BC_WALL: nothing; BC_PEER: copy src -> dst; BC_INLET; BC_OUTLET
     int hi;                    // which face of the SENDER (copy) / of this lattice (inlet, outlet) the op is for
-    const float *src;          // copy source: element (k, c) = src[k*src_slot + src_off + c]
+    const pop_t *src;          // copy source: element (k, c) = src[k*src_slot + src_off + c]
     long long src_slot, src_off;
     int src_by_index;          // 1: k = 0..4 (a packed message); 0: k = lattice slot number
-    float *dst;                // copy destination lattice base (own, or a z-neighbour's over NVLink); slot stride L.slot
+    pop_t *dst;                // copy destination lattice base (own, or a z-neighbour's over NVLink); slot stride L.slot
     long long dst_off;
     const uint8_t *sender_solid;   // solid flags of the sender's boundary plane (plane-sized) or nullptr
 };
@@ -772,8 +800,8 @@ struct ZFaceOp {
         if (p.parity_done == 0) {
             // the next (odd) step pulls them from ghost slot opp(i)
             const int gs = oppr(i);
-            float *ghost = L.f + gs * L.slot + (long long)(hi ? L.nz + 1 : 0) * L.plane + c;
-            if (op.mode == BC_INLET) *ghost = p.C.heq_in[i];
+            pop_t *ghost = L.f + gs * L.slot + (long long)(hi ? L.nz + 1 : 0) * L.plane + c;
+            if (op.mode == BC_INLET) pop_st(ghost, p.C.heq_in[i]);
             else *ghost = L.f[gs * L.slot + (long long)(hi ? L.nz : 1) * L.plane + c];   // outlet: copy of the last plane
         } else {
             // the next (even) step reads them from natural slot i of the boundary plane
@@ -785,8 +813,8 @@ struct ZFaceOp {
                 sy = sy < 0 ? sy + L.ny : (sy >= L.ny ? sy - L.ny : sy);
                 if (L.solid[((long long)(hi ? L.nz : 1) * L.ny + sy) * L.nx + sx]) return;
             }
-            float *cell = L.f + i * L.slot + (long long)(hi ? L.nz : 1) * L.plane + c;
-            if (op.mode == BC_INLET) *cell = p.C.heq_in[i];
+            pop_t *cell = L.f + i * L.slot + (long long)(hi ? L.nz : 1) * L.plane + c;
+            if (op.mode == BC_INLET) pop_st(cell, p.C.heq_in[i]);
             else *cell = L.f[i * L.slot + (long long)(hi ? L.nz - 1 : 2) * L.plane + c];   // outlet: what the plane inside received
         }
     }

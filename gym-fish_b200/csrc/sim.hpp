@@ -30,7 +30,7 @@ struct PeerBlob {
     uint64_t x_bytes;
 };
 static_assert(sizeof(PeerBlob) <= sizeof(FgPeerHandle), "PeerBlob must fit the ABI blob");
-constexpr uint64_t kPeerMagic = 0x4647504545523034ull;   // "FGPEER04"
+constexpr uint64_t kPeerMagic = 0x4647504545523034ull + kPopBytes;   // "FGPEER04" + bytes per population (f32 and f16 builds do not mix)
 
 template <class Dev>
 class SimT {
@@ -57,7 +57,7 @@ public:
         L_.wall_x = cfg.bc[FG_XLO] == FG_BC_WALL; L_.wall_y = cfg.bc[FG_YLO] == FG_BC_WALL;
         L_.bc_zlo = cfg.bc[FG_ZLO]; L_.bc_zhi = cfg.bc[FG_ZHI];
         L_.solid = nullptr;
-        L_.f = static_cast<float *>(dev.alloc(size_t(Q) * L_.slot * sizeof(float), err));
+        L_.f = static_cast<pop_t *>(dev.alloc(size_t(Q) * L_.slot * sizeof(pop_t), err));
         if (!L_.f) return FG_ENOMEM;
         flags_ = static_cast<int *>(dev.alloc(4 * sizeof(int), err));
         if (!flags_) return FG_ENOMEM;
@@ -143,10 +143,10 @@ public:
 
     int set_populations(const float *f19) {
         const size_t n = size_t(L_.plane) * L_.nz;
-        std::vector<float> h(n);
+        std::vector<pop_t> h(n);
         for (int i = 0; i < Q; ++i) {
-            for (size_t k = 0; k < n; ++k) h[k] = float(double(f19[i * n + k]) - WD[i]);
-            if (!dev.h2d(L_.f + i * L_.slot + L_.plane, h.data(), n * sizeof(float))) return cuda_fail();
+            for (size_t k = 0; k < n; ++k) pop_st(&h[k], float(double(f19[i * n + k]) - WD[i]));
+            if (!dev.h2d(L_.f + i * L_.slot + L_.plane, h.data(), n * sizeof(pop_t))) return cuda_fail();
         }
         parity_ = 0;
         return FG_OK;
@@ -433,7 +433,7 @@ public:
     bool internal_hi() const { return cfg.n_ranks > 1 && (cfg.rank < cfg.n_ranks - 1 || cfg.bc[FG_ZHI] == FG_BC_PERIODIC); }
     bool has_lo_peer() const { return peers_ && internal_lo(); }
     bool has_hi_peer() const { return peers_ && internal_hi(); }
-    int64_t halo_bytes() const { return int64_t(5) * L_.plane * sizeof(float); }
+    int64_t halo_bytes() const { return int64_t(5) * L_.plane * sizeof(pop_t); }
 
     // the last step's parity decides which plane / slots carry the populations that crossed the face
     int halo_pack(int face, void *buf) {
@@ -441,11 +441,11 @@ public:
         if (steps_ == 0) return fail(FG_ESTATE, "fg_halo_pack: call after fg_step");
         const bool hi = face == FG_ZHI;
         const int done = parity_ ^ 1;
-        float *out = static_cast<float *>(buf);
+        pop_t *out = static_cast<pop_t *>(buf);
         for (int q = 0; q < 5; ++q) {
             const int slot = done == 0 ? (hi ? ZMT[q] : ZPT[q]) : (hi ? ZPT[q] : ZMT[q]);
             const int zz = done == 0 ? (hi ? L_.nz : 1) : (hi ? L_.nz + 1 : 0);
-            if (!dev.d2h(out + size_t(q) * L_.plane, L_.f + slot * L_.slot + (long long)zz * L_.plane, L_.plane * sizeof(float)))
+            if (!dev.d2h(out + size_t(q) * L_.plane, L_.f + slot * L_.slot + (long long)zz * L_.plane, L_.plane * sizeof(pop_t)))
                 return cuda_fail();
         }
         return FG_OK;
@@ -455,10 +455,10 @@ public:
         if (face != FG_ZLO && face != FG_ZHI) return fail(FG_EINVAL, "face must be FG_ZLO or FG_ZHI");
         if (pending_faces_ <= 0) return fail(FG_ESTATE, "fg_halo_unpack: call after fg_step");
         const bool hi = face == FG_ZHI;
-        float *&st = stage_[hi];
-        if (!st) st = static_cast<float *>(dev.alloc(size_t(5) * L_.plane * sizeof(float), err));
+        pop_t *&st = stage_[hi];
+        if (!st) st = static_cast<pop_t *>(dev.alloc(size_t(5) * L_.plane * sizeof(pop_t), err));
         if (!st) return FG_ENOMEM;
-        if (!dev.h2d(st, buf, size_t(5) * L_.plane * sizeof(float))) return cuda_fail();
+        if (!dev.h2d(st, buf, size_t(5) * L_.plane * sizeof(pop_t))) return cuda_fail();
         const int done = parity_ ^ 1;
         HaloParams p{};
         p.L = L_; p.C = C_; p.parity_done = done;
@@ -528,7 +528,7 @@ public:
             if (b.magic != kPeerMagic || b.rank != r || b.n_ranks != n) return fail(FG_EPEER, "peer handle: wrong rank order");
             if (b.x_bytes != ib_.xbuf_bytes()) return fail(FG_EPEER, "peer handle: IB capacity (max_markers / max_links) differs between ranks");
             if (r == cfg.rank) { all[r] = ib_.xbuf(); continue; }
-            float *f = nullptr; int *fl = nullptr;
+            pop_t *f = nullptr; int *fl = nullptr;
             if (!dev.open_peer(b, &f, &fl, &all[r], err)) return FG_EPEER;
             if (!all[r]) return fail(FG_EPEER, "peer handle: rank has no IB exchange buffer");
         }
@@ -591,7 +591,7 @@ private:
         const bool down = parity_ == 1 && !(cfg.flags & FG_FLAG_NO_SWEEP_FLIP);
         StepParams p{L_, C_, F, zb, zstride, hole ? hole_b : 0x7fffffff, hole, down ? planes - 1 : -1, y0, ystride, {}};
         for (int s = 0; s < Q; ++s)
-            for (int d = 0; d < 3; ++d) p.kz[s][d] = 4ll * (s * L_.slot + (long long)(d - 1) * L_.plane);
+            for (int d = 0; d < 3; ++d) p.kz[s][d] = (long long)kPopBytes * (s * L_.slot + (long long)(d - 1) * L_.plane);
         const Dim3 g{(L_.nx + 127) / 128, rows, planes};
         const bool prof = timed && (cfg.flags & FG_FLAG_PROFILE);
         if (prof) {   // FG_FLAG_PROFILE: event pair around the bulk launch alone, and the cells it updates
@@ -675,7 +675,7 @@ private:
         PairParams p{};
         p.s = StepParams{L_, C_, ForceField{}, zb, 1, hole ? hole_b : 0x7fffffff, hole, -1, 0, 1, {}};
         for (int s = 0; s < Q; ++s)
-            for (int d = 0; d < 3; ++d) p.s.kz[s][d] = 4ll * (s * L_.slot + (long long)(d - 1) * L_.plane);
+            for (int d = 0; d < 3; ++d) p.s.kz[s][d] = (long long)kPopBytes * (s * L_.slot + (long long)(d - 1) * L_.plane);
         p.planes = planes; p.rows = L_.ny; p.xblocks = (L_.nx + 127) / 128;
         p.lag = std::min(pair_lag(), planes);
         // a zero-gradient outlet copies from the boundary plane after the even step what the odd step of the plane
@@ -717,7 +717,7 @@ private:
             const bool at_global = hi ? (cfg.rank == cfg.n_ranks - 1) : (cfg.rank == 0);
             const int bc = hi ? cfg.bc[FG_ZHI] : cfg.bc[FG_ZLO];
             const bool internal = hi ? internal_hi() : internal_lo();
-            float *dst = nullptr;
+            pop_t *dst = nullptr;
             if (cfg.n_ranks == 1) {
                 if (bc == FG_BC_PERIODIC) dst = L_.f;            // wrap onto myself
                 else if (bc == FG_BC_INLET || bc == FG_BC_OUTLET) op.mode = bc;
@@ -790,9 +790,9 @@ private:
     uint8_t *solid_ = nullptr;
     int *flags_ = nullptr;         // [0] written by my z-low neighbour, [1] by my z-high neighbour, [2] my own halo
                                    // counter (device-resident, never reset: orders pushes between neighbours), [3] timeout
-    float *stage_[2] = {nullptr, nullptr};
+    pop_t *stage_[2] = {nullptr, nullptr};
     bool peers_ = false;
-    float *peer_f_[2] = {nullptr, nullptr};
+    pop_t *peer_f_[2] = {nullptr, nullptr};
     int *peer_flags_[2] = {nullptr, nullptr};
     int pending_faces_ = 0;
     IbState<Dev> ib_;

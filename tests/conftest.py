@@ -17,6 +17,7 @@ if ROOT not in sys.path:
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 EMU = os.path.join(ROOT, "tests", "emu", "libfishgym_emu.so")
+EMU_F16 = os.path.join(ROOT, "tests", "emu", "libfishgym_emu_f16.so")
 
 
 def pytest_configure(config):
@@ -39,6 +40,18 @@ def g():
 @pytest.fixture(scope="session")
 def emu(g):
     return _ensure(EMU, "tests/emu")
+
+
+@pytest.fixture(scope="session")
+def emu_f16(g):
+    """The 16-bit-storage build of the kernel bodies, emulated on the CPU (tests/emu, -DFG_POP16)."""
+    return _ensure(EMU_F16, "tests/emu")
+
+
+@pytest.fixture(scope="session")
+def cuda_f16(g):
+    g.load_library("cuda_f16")
+    return "cuda_f16"
 
 
 @pytest.fixture(scope="session")

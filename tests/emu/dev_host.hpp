@@ -95,15 +95,15 @@ public:
 
     // peers: only same-process handles (raw pointers) — lets the CPU tests run two slabs in one process
     template <class Blob>
-    bool export_peer(float *f, int *flags, void *x, Blob &b, std::string &) {
+    bool export_peer(pop_t *f, int *flags, void *x, Blob &b, std::string &) {
         b.pid = int(getpid()); b.device = -1;
         b.f_ptr = reinterpret_cast<uint64_t>(f); b.flag_ptr = reinterpret_cast<uint64_t>(flags); b.x_ptr = reinterpret_cast<uint64_t>(x);
         return true;
     }
     template <class Blob>
-    bool open_peer(const Blob &b, float **f, int **flags, void **x, std::string &e) {
+    bool open_peer(const Blob &b, pop_t **f, int **flags, void **x, std::string &e) {
         if (b.pid != int(getpid())) { e = "host emulation: peers must live in the same process"; return false; }
-        *f = reinterpret_cast<float *>(b.f_ptr); *flags = reinterpret_cast<int *>(b.flag_ptr); *x = reinterpret_cast<void *>(b.x_ptr);
+        *f = reinterpret_cast<pop_t *>(b.f_ptr); *flags = reinterpret_cast<int *>(b.flag_ptr); *x = reinterpret_cast<void *>(b.x_ptr);
         return true;
     }
     // exchange counters (IB across slabs): ranks run in separate host threads in the tests, so these really wait

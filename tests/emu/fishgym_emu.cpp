@@ -4,5 +4,9 @@
 #include "../../gym-fish_b200/csrc/lbm_core.cuh"
 #include "dev_host.hpp"
 #define FG_DEV fg::HostDev
+#if defined(FG_POP16)
+#define FG_BACKEND_NAME "emu-host-f16"
+#else
 #define FG_BACKEND_NAME "emu-host-fp32"
+#endif
 #include "../../gym-fish_b200/csrc/abi_impl.hpp"

@@ -1,0 +1,90 @@
+"""The opt-in 16-bit-storage build (libfishgym_cuda_f16.so): shifted populations stored as fp16 scaled by
+2^12, fp32 arithmetic, 76 B per cell update.  It is NOT held to the 1e-5 parity bar of the fp32 product — these tests
+state what it is held to: a few 1e-4 relative to the fp64 oracle on decaying and forced flows, exact conservation of
+nothing but boundedness, and the same index maps (pure integer work, unaffected by the storage type)."""
+import numpy as np
+import pytest
+
+import util
+
+TOL_U = 2e-3          # relative L2 of velocity against the fp64 oracle (measured 1.2e-4 ... 3.7e-4 on the cases below; the fp32 build: 1e-7)
+TOL_RHO = 2e-5
+
+
+def _pair(g, backend, kw, steps, fields=None, solid=None):
+    a, b = g.Sim(backend="oracle", **kw), g.Sim(backend=backend, **kw)
+    rho, u = fields if fields is not None else util.smooth_fields(a.shape)
+    for s in (a, b):
+        if solid is not None:
+            s.set_solid(solid)
+        s.set_fields(rho, u)
+        s.step(steps)
+    (ra, ua), (rb, ub) = a.get_fields(f64=True), b.get_fields(f64=True)
+    return util.rel_l2(ub, ua), util.rel_l2(rb, ra), a, b
+
+
+@pytest.mark.parametrize("name", ["bgk_periodic", "mrt_force", "mrt_all_walls_lid", "mrt_inlet_outlet_ywalls", "mrt_outlet_inlet_xwalls"])
+def test_f16_storage_case_table_emulated(g, emu_f16, name):
+    eu, er, a, b = _pair(g, emu_f16, util.parity_cases(g)[name], 60)
+    assert b.backend_name == "emu-host-f16"
+    assert eu <= TOL_U and er <= TOL_RHO, (name, eu, er)
+
+
+def test_f16_storage_taylor_green_emulated(g, emu_f16):
+    n = 32
+    eu, er, _, _ = _pair(g, emu_f16, dict(nx=n, ny=n, nz=n, tau=0.8), 300, fields=util.taylor_green(n, "xz"))
+    assert eu <= TOL_U and er <= TOL_RHO, (eu, er)
+
+
+def test_f16_storage_immersed_boundary_and_halo_bytes_emulated(g, emu_f16):
+    P, Wl, IN, OUT = g.BC_PERIODIC, g.BC_WALL, g.BC_INLET, g.BC_OUTLET
+    kw = dict(nx=20, ny=18, nz=24, tau=0.8, collision=g.MRT, max_markers=400, max_links=1, bc=[P, P, Wl, Wl, IN, OUT], inlet_u=[0, 0, 0.05])
+    X = util.sphere_markers((10.3, 9.1, 8.2), 4.0, 200)
+    a, b = g.Sim(backend="oracle", **kw), g.Sim(backend=emu_f16, **kw)
+    u = np.zeros((3,) + a.shape)
+    u[2] = 0.05
+    for s in (a, b):
+        s.set_markers(X, np.zeros_like(X), np.ones(200, np.float32))
+        s.set_link_origins([[10.3, 9.1, 8.2]])
+        s.set_fields(np.ones(a.shape), u)
+        s.step(11)
+    assert np.array_equal(a.get_index_map()[0], b.get_index_map()[0])            # integer work: still bit-exact
+    wa, wb = a.get_link_wrenches(), b.get_link_wrenches()
+    assert np.abs(wb - wa).max() / np.abs(wa).max() <= 5e-3
+    assert util.rel_l2(b.get_fields(f64=True)[1], a.get_fields(f64=True)[1]) <= TOL_U
+    # halo messages travel in the storage type: half the bytes of the fp32 build
+    f32 = g.Sim(backend=g._abi.LIB_PATHS["cuda"].replace("gym-fish_b200/csrc/libfishgym_cuda.so", "tests/emu/libfishgym_emu.so"), n_ranks=2, rank=0, **dict(kw, max_markers=0))
+    f16 = g.Sim(backend=emu_f16, n_ranks=2, rank=0, **dict(kw, max_markers=0))
+    assert f16.lib.fg_halo_bytes(f16.h) * 2 == f32.lib.fg_halo_bytes(f32.h)
+
+
+def test_f16_storage_population_roundtrip_emulated(g, emu_f16):
+    s = g.Sim(backend=emu_f16, nx=6, ny=5, nz=4, tau=0.9)
+    rng = np.random.default_rng(3)
+    f = (g._abi.W[:, None, None, None] * (1 + 0.01 * rng.standard_normal((19,) + s.shape))).astype(np.float32)
+    s.set_populations(f)
+    # shifted values |h| <= 0.02 carry 11 significant bits: absolute error <= 0.02 * 2^-11
+    assert np.abs(s.get_populations() - f).max() < 1.2e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["bgk_periodic", "mrt_force", "mrt_all_walls_lid", "mrt_inlet_outlet_ywalls", "mrt_outlet_inlet_xwalls"])
+def test_f16_storage_case_table_gpu(g, cuda_f16, name):
+    eu, er, a, b = _pair(g, cuda_f16, dict(util.parity_cases(g)[name], nx=140, ny=20, nz=16), 60)
+    assert b.backend_name == "cuda-sm100a-f16"
+    assert eu <= TOL_U and er <= TOL_RHO, (name, eu, er)
+
+
+@pytest.mark.gpu
+def test_f16_storage_sphere_channel_and_split_gpu(g, cuda_f16):
+    """Flow past the IB sphere on the f16 build, plane split active: drag within 1 % of the fp32 build after 400 steps."""
+    import bench
+    out = []
+    for backend in ("cuda", cuda_f16):
+        s, _ = bench.make_sim(g, backend, "sphere_256x128x128", 0, 1, 0)
+        s.step(400)
+        out.append((s.get_link_wrenches()[0, 2], s.stats().split_substeps))
+        s.close()
+    (d32, _), (d16, sp) = out
+    assert sp == 400
+    assert abs(d16 - d32) / abs(d32) < 1e-2, (d16, d32)
