@@ -137,7 +137,8 @@ public:
                  ck(cudaEventCreateWithFlags(&fork_ev_[i], cudaEventDisableTiming), "cudaEventCreate") &&
                  ck(cudaEventCreateWithFlags(&join_ev_[i], cudaEventDisableTiming), "cudaEventCreate");
         stream_ = s_[0];
-        ok = ok && ck(cudaEventCreate(&ev0_), "cudaEventCreate") && ck(cudaEventCreate(&ev1_), "cudaEventCreate");
+        for (int i = 0; i < 2 && ok; ++i)
+            ok = ck(cudaEventCreate(&tev_[i][0]), "cudaEventCreate") && ck(cudaEventCreate(&tev_[i][1]), "cudaEventCreate");
         if (!ok) e = err;
         return ok;
     }
@@ -152,9 +153,8 @@ public:
             fork_ev_[i] = join_ev_[i] = nullptr;
         }
         stream_ = nullptr;
-        if (ev0_) cudaEventDestroy(ev0_);
-        if (ev1_) cudaEventDestroy(ev1_);
-        ev0_ = ev1_ = nullptr;
+        for (auto &pr : tev_)
+            for (auto &e : pr) { if (e) cudaEventDestroy(e); e = nullptr; }
         for (auto &pool : marks_) { for (auto e : pool) cudaEventDestroy(e); pool.clear(); }
         for (auto &e : named_) { if (e) cudaEventDestroy(e); e = nullptr; }
     }
@@ -232,15 +232,24 @@ public:
         if (id < 0 || id >= kNamedEvents || !named_[id]) return true;
         return ck(cudaEventSynchronize(named_[id]), "cudaEventSynchronize");
     }
+    // Timing of one fg_step call: two event pairs used alternately, so that a call can record its own pair while the
+    // previous call (which returned before its collide finished) still owns the other one.
     void tic() {
         cudaSetDevice(device_);
-        cudaEventRecord(ev0_, stream_);
+        tpair_ ^= 1;
+        cudaEventRecord(tev_[tpair_][0], stream_);
     }
-    double toc() {
-        cudaEventRecord(ev1_, stream_);
-        if (cudaEventSynchronize(ev1_) != cudaSuccess) return 0.0;
+    void toc_record() { cudaEventRecord(tev_[tpair_][1], stream_); }
+    // elapsed ms of the latest recorded pair; wait == false: only if it has completed (ok tells)
+    double toc_elapsed(bool wait, bool &ok) {
+        ok = false;
+        cudaSetDevice(device_);
+        cudaEvent_t e1 = tev_[tpair_][1];
+        if (wait) { if (cudaEventSynchronize(e1) != cudaSuccess) return 0.0; }
+        else if (cudaEventQuery(e1) != cudaSuccess) { cudaGetLastError(); return 0.0; }
         float ms = 0.f;
-        cudaEventElapsedTime(&ms, ev0_, ev1_);
+        if (cudaEventElapsedTime(&ms, tev_[tpair_][0], e1) != cudaSuccess) { cudaGetLastError(); return 0.0; }
+        ok = true;
         return double(ms);
     }
 
@@ -502,7 +511,8 @@ private:
 
     int device_ = -1;
     cudaStream_t stream_ = nullptr;
-    cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+    cudaEvent_t tev_[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    int tpair_ = 0;
     std::vector<std::pair<std::string, void *>> opened_;
     static constexpr int kStreams = 4;
     cudaStream_t s_[kStreams] = {nullptr, nullptr, nullptr, nullptr};

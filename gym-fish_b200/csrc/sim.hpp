@@ -388,8 +388,18 @@ public:
                 if (!dev.graph_end()) return cuda_fail();
             }
         }
-        last_ms_ = dev.toc();
-        if (!dev.sync()) return cuda_fail();
+        // The call returns once what it exposes synchronously is there: the link wrenches (event recorded right after the
+        // IB kernels of the last substep) and, with bodies, the host-integrated observation.  The collide of the last
+        // substep may still be running; every later call is ordered behind it on the handle's stream, fg_sync() waits for
+        // it, and the timing of the call is read when fg_get_stats() finds it complete.  A caller that feeds markers /
+        // actions step by step thereby overlaps its own work and the next upload with the fluid kernel.
+        dev.toc_record();
+        timing_pending_ = true; timed_substeps_ = n;
+        const bool wait_all = prof || peers_ || (cfg.flags & FG_FLAG_SYNC_STEP);
+        if (wait_all) {
+            if (!dev.sync()) return cuda_fail();
+            finish_timing(true);
+        }
         if (prof) {
             collide_ms_ = dev.marks_elapsed(0); ib_ms_ = dev.marks_elapsed(1);
             last_collide_launches_ = collide_launches_; last_collide_cells_ = collide_cells_;
@@ -407,12 +417,23 @@ public:
         if (ib_.ready() && ib_.n_markers() > 0) {
             if (int rc = ib_.fetch_wrenches(dev, err)) return rc;
         }
-        last_mlups_ = last_ms_ > 0 ? double(L_.plane) * L_.nz * n / last_ms_ / 1e3 : 0;
         if (ranks && !peers_) pending_faces_ = int(internal_lo()) + int(internal_hi());
         return FG_OK;
     }
 
+    // device time of the latest fg_step call, once its events have completed (wait: block until they have)
+    void finish_timing(bool wait) {
+        if (!timing_pending_) return;
+        bool ok = false;
+        const double ms = dev.toc_elapsed(wait, ok);
+        if (!ok) return;
+        timing_pending_ = false;
+        last_ms_ = ms;
+        last_mlups_ = ms > 0 ? double(L_.plane) * L_.nz * timed_substeps_ / ms / 1e3 : 0;
+    }
+
     int get_stats(FgStats *o) {
+        finish_timing(false);
         std::memset(o, 0, sizeof(*o));
         o->steps = steps_;
         o->cells = int64_t(L_.plane) * L_.nz;
@@ -782,6 +803,8 @@ private:
     int parity_ = 0;
     int64_t steps_ = 0;
     double last_ms_ = 0, last_mlups_ = 0, collide_ms_ = 0, ib_ms_ = 0;
+    bool timing_pending_ = false;
+    int timed_substeps_ = 0;
     int64_t collide_launches_ = 0, last_collide_launches_ = 0, collide_cells_ = 0, last_collide_cells_ = 0;
     int64_t split_substeps_ = 0, pair_substeps_ = 0;
     int *pair_ctr_ = nullptr;      // [1 + nz + 2] ticket + per-plane completion counters of StreamCollidePair

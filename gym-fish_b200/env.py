@@ -143,6 +143,7 @@ class FishEnv:
         self._t += 1
         truncated = self._t >= self.cfg.max_episode_steps
         st = self.sim.stats()
+        # timing of the latest env step whose device work has finished (fg_step returns before its last collide has)
         info = {"mlups": st.last_mlups, "step_ms": st.last_step_ms, "diverged": bool(not np.isfinite(obs).all())}
         return obs, float(reward), bool(terminated or info["diverged"]), bool(truncated), info
 

@@ -66,6 +66,7 @@ extern "C" {
 #define FG_FLAG_NO_SWEEP_FLIP 32 /* sweep the planes upwards in every step (default: odd steps downwards, for L2 reuse between steps) */
 #define FG_FLAG_FUSED_PAIRS 64 /* even step + following odd step as ONE L2-resident wavefront launch (no bodies, one rank); halves DRAM traffic but measured slower on B200 (r1) */
 #define FG_FLAG_NO_XWARP 128   /* x walls: predicated wall selects in every thread (default: only the two warps at the row ends run the wall code) */
+#define FG_FLAG_SYNC_STEP 256  /* fg_step returns only when all its device work has finished (default: when wrenches / obs are there) */
 #define FG_FLAG_NO_SPLIT  16   /* collide all planes after the IB kernels (default: planes away from the bodies run beside them) */
 
 typedef struct FgConfig {
@@ -93,7 +94,7 @@ typedef struct FgConfig {
 typedef struct FgStats {
     int64_t steps;            /* fluid steps taken since create/reset */
     int64_t cells;            /* local lattice cells (nx*ny*nz_local) */
-    double  last_step_ms;     /* device (CUDA events) or host time of the last fg_step call */
+    double  last_step_ms;     /* device time (CUDA events) of the latest fg_step call whose work has finished (fg_sync first to be sure) */
     double  last_mlups;       /* cells * n_substeps / last_step_ms / 1e3 */
     int64_t kernel_launches;  /* kernels of this library launched since create */
     int32_t n_markers, n_links;
@@ -169,7 +170,9 @@ int fg_action_size(FgSim *sim);
 int fg_get_markers(FgSim *sim, float *X, float *U, int32_t *link_id, int32_t cap); /* returns count or <0 */
 
 /* ---- stepping ---- */
-int fg_step(FgSim *sim, int32_t n_substeps);       /* synchronous for wrenches/obs; fields stay on device */
+/* fg_step returns when the outputs it exposes synchronously are there — link wrenches, marker forces' inputs, observations;
+ * the stream-collide of the last substep may still be running.  Every later call is ordered behind it, fg_sync() waits. */
+int fg_step(FgSim *sim, int32_t n_substeps);
 int fg_sync(FgSim *sim);
 int fg_get_stats(FgSim *sim, FgStats *out);
 int fg_set_flags(FgSim *sim, int32_t flags);        /* change FgConfig.flags (FG_FLAG_PROFILE, FG_FLAG_NO_GRAPHS, FG_FLAG_NO_OVERLAP) */

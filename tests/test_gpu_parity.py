@@ -195,6 +195,30 @@ def test_xwall_warp_uniform_variant_is_bit_identical(g, cuda, name):
     assert util.rel_l2(a.get_fields(f64=True)[1], o.get_fields(f64=True)[1]) <= TOL_FIELD
 
 
+def test_step_returns_when_wrenches_are_there_and_later_calls_are_ordered(g, cuda):
+    """fg_step waits for the link wrenches (event after the IB kernels), not for the collide of its last substep: a loop
+    that feeds markers step by step overlaps with the fluid kernel.  Same results as FG_FLAG_SYNC_STEP; the timing of a
+    call is reported once its device work has finished."""
+    import bench
+    sims = []
+    for fl in (0, g._abi.FLAG_SYNC_STEP):
+        s, markers = bench.make_sim(g, cuda, "sphere_256x128x128", 0, 1, 0, flags=fl)
+        X, U, dV, link, _ = markers
+        w = []
+        for it in range(30):
+            s.set_markers(X, U, dV, link)
+            s.step(1)
+            w.append(s.get_link_wrenches().copy())
+        s.sync()
+        st = s.stats()
+        assert st.steps == 30 and 0.05 < st.last_step_ms < 5.0, st.last_step_ms
+        sims.append((s, np.stack(w)))
+    (a, wa), (b, wb) = sims
+    assert np.abs(wa - wb).max() / np.abs(wb).max() < 1e-5
+    assert util.rel_l2(a.get_fields()[1], b.get_fields()[1]) < 1e-6
+    a.close(); b.close()
+
+
 def test_spread_force_equals_marker_force_on_gpu(g, cuda):
     kw = dict(nx=48, ny=48, nz=48, tau=0.8, collision=g.MRT, max_markers=2000, max_links=1)
     s = g.Sim(backend=cuda, **kw)
