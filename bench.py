@@ -257,7 +257,12 @@ def main():
         raise SystemExit("for --gpus N > 1 launch with: python -m torch.distributed.run --nnodes=1 --nproc-per-node N "
                          "--master-addr 127.0.0.1 --master-port P bench.py --gpus N ...")
 
-    os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1))
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU legs (reference arm, cpu_baseline) are meant to use every
+    # host core ("cores" in the JSON line is what they really get), so the variable is set before the oracle is loaded
+    if args.impl == "reference" or world == 1:
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+    else:
+        os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1))
     import gym_fish_b200 as g
 
     if args.impl == "reference":

@@ -192,7 +192,8 @@ int fg_step(FgSim *s, int32_t n) {
 }
 int fg_sync(FgSim *s) {
     if (!s) return FG_EINVAL;
-    return s->sim.dev.sync() ? FG_OK : s->sim.cuda_fail();
+    if (!s->sim.dev.sync()) return s->sim.cuda_fail();
+    return s->sim.check_peer_timeout();
 }
 int fg_get_stats(FgSim *s, FgStats *o) {
     if (!s || !o) return FG_EINVAL;

@@ -55,7 +55,7 @@ __global__ void signal_kernel(int *mine, int *lo, int *hi) {
     if (lo) asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(lo), "r"(value) : "memory");
     if (hi) asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(hi), "r"(value) : "memory");
 }
-__global__ void wait_kernel(int *flags, int lo, int hi, unsigned long long timeout_ns) {
+__global__ void wait_kernel(int *flags, int lo, int hi, unsigned long long timeout_ns, volatile int *host_word) {
     const int value = flags[2];      // neighbours must have pushed as many halos as I have
     unsigned long long t0;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
@@ -67,7 +67,7 @@ __global__ void wait_kernel(int *flags, int lo, int hi, unsigned long long timeo
             if (v >= value) break;
             unsigned long long t;
             asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-            if (t - t0 > timeout_ns) { flags[3] = 1; return; }   // sticky: the host reports FG_EPEER
+            if (t - t0 > timeout_ns) { flags[3] = 1; *host_word = 1; return; }   // sticky; the host word (pinned) lets fg_step see it without a sync
             __nanosleep(200);
         }
     }
@@ -82,7 +82,7 @@ __global__ void signal_counters_kernel(int *mine, CounterList t, int bump) {
         if (t.p[i]) asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(t.p[i]), "r"(v) : "memory");
     if (bump) mine[0] = v;
 }
-__global__ void wait_counters_kernel(int *mine, CounterList s, unsigned long long timeout_ns) {
+__global__ void wait_counters_kernel(int *mine, CounterList s, unsigned long long timeout_ns, volatile int *host_word) {
     const int v = mine[0] + 1;
     unsigned long long t0;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
@@ -94,7 +94,7 @@ __global__ void wait_counters_kernel(int *mine, CounterList s, unsigned long lon
             if (x >= v) break;
             unsigned long long t;
             asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-            if (t - t0 > timeout_ns) { mine[3] = 1; return; }
+            if (t - t0 > timeout_ns) { mine[3] = 1; *host_word = 2; return; }
             __nanosleep(200);
         }
     }
@@ -155,6 +155,7 @@ public:
         stream_ = nullptr;
         for (auto &pr : tev_)
             for (auto &e : pr) { if (e) cudaEventDestroy(e); e = nullptr; }
+        if (timeout_word_) { cudaFreeHost(const_cast<int *>(timeout_word_)); timeout_word_ = nullptr; }
         for (auto &pool : marks_) { for (auto e : pool) cudaEventDestroy(e); pool.clear(); }
         for (auto &e : named_) { if (e) cudaEventDestroy(e); e = nullptr; }
     }
@@ -392,7 +393,7 @@ public:
         if (gmode_ == 2) return true;
         CounterList s{};
         for (int i = 0; i < n && i < 8; ++i) s.p[i] = sources[i];
-        wait_counters_kernel<<<1, 1, 0, stream_>>>(mine, s, 20ull * 1000ull * 1000ull * 1000ull);
+        wait_counters_kernel<<<1, 1, 0, stream_>>>(mine, s, 20ull * 1000ull * 1000ull * 1000ull, timeout_word_);
         return ck(cudaGetLastError(), "wait launch");
     }
     template <class Blob>
@@ -438,7 +439,7 @@ public:
         cudaSetDevice(device_);
         ++launches;
         if (gmode_ == 2) return true;
-        wait_kernel<<<1, 1, 0, stream_>>>(flags, lo, hi, 20ull * 1000ull * 1000ull * 1000ull);
+        wait_kernel<<<1, 1, 0, stream_>>>(flags, lo, hi, 20ull * 1000ull * 1000ull * 1000ull, timeout_word_);
         return ck(cudaGetLastError(), "wait launch");
     }
 
@@ -491,6 +492,8 @@ public:
     }
 
     cudaStream_t stream() const { return stream_; }
+    // 0: none; 1: a halo wait timed out; 2: an IB exchange wait did (set by the wait kernels, sticky)
+    int peer_timeout() const { return timeout_word_ ? *timeout_word_ : 0; }
 
 private:
     bool ck(cudaError_t rc, const char *what) {
@@ -519,6 +522,7 @@ private:
     cudaEvent_t fork_ev_[kStreams] = {nullptr, nullptr, nullptr, nullptr}, join_ev_[kStreams] = {nullptr, nullptr, nullptr, nullptr};
     int cur_ = 0;
     int prio_low_ = 0, prio_high_ = 0;
+    volatile int *timeout_word_ = nullptr;
     bool debug_sync_ = false;
     int sm_count_ = 148;
     bool coop_ = false;

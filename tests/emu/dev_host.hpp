@@ -133,6 +133,7 @@ public:
         return true;
     }
     void close_peers() {}
+    int peer_timeout() const { return 0; }      // the emulated waits report a neighbour that is behind directly
     int current() const { return cur_; }   // streams: everything runs sequentially here, in submission order
     bool fork_to(int s) { cur_ = s; return true; }
     bool switch_to(int s) { cur_ = s; return true; }
