@@ -102,7 +102,8 @@ class FgPeerHandle(C.Structure):
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _REPO = os.path.dirname(_HERE)
 LIB_PATHS = {
-    "cuda": os.path.join(_HERE, "csrc", "libfishgym_cuda.so"),
+    # FG_CUDA_LIB: another build of the same library (kernel experiments, e.g. different launch bounds)
+    "cuda": os.environ.get("FG_CUDA_LIB") or os.path.join(_HERE, "csrc", "libfishgym_cuda.so"),
     # opt-in build of the same sources: 16-bit population storage, fp32 arithmetic (half the HBM bytes per update)
     "cuda_f16": os.path.join(_HERE, "csrc", "libfishgym_cuda_f16.so"),
     "oracle": os.path.join(_REPO, "oracle", "libfishgym_oracle.so"),
