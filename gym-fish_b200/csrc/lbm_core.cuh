@@ -54,8 +54,24 @@ FG_HD void pop_st(pop_t *p, float v) { *p = pop_t(v * 4096.0f); }
 #define FG_POP_NAME "f16"
 #else
 typedef float pop_t;
-FG_HD float pop_ld(const pop_t *p) { return *p; }
-FG_HD void pop_st(pop_t *p, float v) { *p = v; }
+FG_HD float pop_ld(const pop_t *p) {
+#if defined(__CUDA_ARCH__) && defined(FG_LDCS)
+    return __ldcs(p);       // experiment: streaming (evict-first) loads
+#elif defined(__CUDA_ARCH__) && defined(FG_LDCG)
+    return __ldcg(p);       // experiment: L2 only
+#else
+    return *p;
+#endif
+}
+FG_HD void pop_st(pop_t *p, float v) {
+#if defined(__CUDA_ARCH__) && defined(FG_STCS)
+    __stcs(p, v);           // experiment: streaming stores
+#elif defined(__CUDA_ARCH__) && defined(FG_STCG)
+    __stcg(p, v);
+#else
+    *p = v;
+#endif
+}
 #define FG_POP_NAME "f32"
 #endif
 constexpr int kPopBytes = int(sizeof(pop_t));
