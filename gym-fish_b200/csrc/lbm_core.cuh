@@ -491,16 +491,20 @@ FG_HD void fast_odd_store_pair(const float (&h)[Q], const StepParams &p, const N
     }
 }
 
+#if !defined(FG_CTA)
+#define FG_CTA 128          // threads per stream-collide CTA (experiments: 64 with 18 CTAs/SM, 256 with 4)
+#endif
+constexpr int kCollideThreads = FG_CTA;
 template <int PARITY, bool MRT, int MODE>
 struct StreamCollide {
-    static constexpr int kThreads = 128;
+    static constexpr int kThreads = kCollideThreads;
     // 9 CTAs of 128 threads per SM: ptxas then fits every bulk variant into 56 registers without a spill (9 x 128 x 56 =
     // 64 512 of the 65 536 registers).  Measured against 8 (64 registers) and 10 (48 registers, 32-80 B of spills) in
     // gpu pass 21: 9 is 1.7-3.3 % faster than 8 on every workload, 10 is 3-4 % slower.
 #if defined(FG_OCC)
     static constexpr int kMinBlocks = FG_OCC;
 #else
-    static constexpr int kMinBlocks = 9;
+    static constexpr int kMinBlocks = 9 * 128 / kCollideThreads;
 #endif
 
     FG_HD static void force_at(const StepParams &p, int y, int zz, long long idx, float &Fx, float &Fy, float &Fz) {

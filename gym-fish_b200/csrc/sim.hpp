@@ -615,7 +615,7 @@ private:
         StepParams p{L_, C_, F, zb, zstride, hole ? hole_b : 0x7fffffff, hole, down ? planes - 1 : -1, y0, ystride, {}};
         for (int s = 0; s < Q; ++s)
             for (int d = 0; d < 3; ++d) p.kz[s][d] = (long long)kPopBytes * (s * L_.slot + (long long)(d - 1) * L_.plane);
-        const Dim3 g{(L_.nx + 127) / 128, rows, planes};
+        const Dim3 g{(L_.nx + kCollideThreads - 1) / kCollideThreads, rows, planes};
         const bool prof = timed && (cfg.flags & FG_FLAG_PROFILE);
         if (prof) {   // FG_FLAG_PROFILE: event pair around the bulk launch alone, and the cells it updates
             dev.mark(0);
