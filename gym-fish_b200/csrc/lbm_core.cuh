@@ -495,16 +495,19 @@ FG_HD void fast_odd_store_pair(const float (&h)[Q], const StepParams &p, const N
 #define FG_CTA 128          // threads per stream-collide CTA (experiments: 64 with 18 CTAs/SM, 256 with 4)
 #endif
 constexpr int kCollideThreads = FG_CTA;
-template <int PARITY, bool MRT, int MODE>
+template <int PARITY, bool MRT, int MODE, int OCC = 9>
 struct StreamCollide {
     static constexpr int kThreads = kCollideThreads;
     // 9 CTAs of 128 threads per SM: ptxas then fits every bulk variant into 56 registers without a spill (9 x 128 x 56 =
     // 64 512 of the 65 536 registers).  Measured against 8 (64 registers) and 10 (48 registers, 32-80 B of spills) in
     // gpu pass 21: 9 is 1.7-3.3 % faster than 8 on every workload, 10 is 3-4 % slower.
+    // On z-slabs (boundary planes, halo push and IB chain at high priority beside the interior) the SAME comparison comes
+    // out the other way — 0.1174 ms/step with 8 against 0.1214 with 9 on two GPUs, although the kernel alone is faster
+    // with 9 (multi-GPU pass 6) — so peered handles launch the OCC = 8 instantiation.
 #if defined(FG_OCC)
     static constexpr int kMinBlocks = FG_OCC;
 #else
-    static constexpr int kMinBlocks = 9 * 128 / kCollideThreads;
+    static constexpr int kMinBlocks = OCC * 128 / kCollideThreads;
 #endif
 
     FG_HD static void force_at(const StepParams &p, int y, int zz, long long idx, float &Fx, float &Fy, float &Fz) {

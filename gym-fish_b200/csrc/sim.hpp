@@ -602,6 +602,9 @@ private:
 
     template <int PARITY, int MODE>
     bool launch_collide_pm(const StepParams &p, Dim3 g) {
+        if (peers_)     // 8 CTAs/SM (64 registers) on z-slabs, 9 (56 registers) otherwise: lbm_core.cuh StreamCollide
+            return cfg.collision == FG_MRT ? dev.template launch<StreamCollide<PARITY, true, MODE, 8>>(g, p)
+                                           : dev.template launch<StreamCollide<PARITY, false, MODE, 8>>(g, p);
         return cfg.collision == FG_MRT ? dev.template launch<StreamCollide<PARITY, true, MODE>>(g, p)
                                        : dev.template launch<StreamCollide<PARITY, false, MODE>>(g, p);
     }
