@@ -602,7 +602,10 @@ private:
 
     template <int PARITY, int MODE>
     bool launch_collide_pm(const StepParams &p, Dim3 g) {
-        if (peers_)     // 8 CTAs/SM (64 registers) on z-slabs, 9 (56 registers) otherwise: lbm_core.cuh StreamCollide
+        // 8 CTAs/SM (64 registers) on SMALL z-slabs, 9 (56 registers) otherwise (lbm_core.cuh StreamCollide): the ~4 us per
+        // step that 9 cost the high-priority chain on slabs of 4.2 M cells outweigh its 2 % faster kernel only below ~8 M
+        // cells per rank (512^3 and the school on 8 GPUs were measured with 9: 318 252 / 272 528 MLUPS)
+        if (peers_ && (long long)L_.plane * L_.nz < (8ll << 20))
             return cfg.collision == FG_MRT ? dev.template launch<StreamCollide<PARITY, true, MODE, 8>>(g, p)
                                            : dev.template launch<StreamCollide<PARITY, false, MODE, 8>>(g, p);
         return cfg.collision == FG_MRT ? dev.template launch<StreamCollide<PARITY, true, MODE>>(g, p)
