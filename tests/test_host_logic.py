@@ -1,0 +1,81 @@
+"""Host-side logic of the step orchestration, through the C ABI on the emulated device: when the plane split applies,
+the staged (deferred) marker upload, call timing.  No GPU needed; the same code drives the CUDA device policy."""
+import numpy as np
+import pytest
+
+import util
+
+
+def _sim(g, emu, **kw):
+    base = dict(nx=12, ny=10, nz=64, tau=0.8, collision=g.MRT, max_markers=600, max_links=2, split_min_cells=1)
+    base.update(kw)
+    return g.Sim(backend=emu, **base)
+
+
+def _sphere(z, r=2.5, n=80, x=6.2, y=5.1):
+    X = util.sphere_markers((x, y, z), r, n)
+    return X, np.zeros_like(X), np.ones(n, np.float32)
+
+
+@pytest.mark.parametrize("z, expect_split", [(20.0, True),      # stencils inside planes ~16..24: most planes are far
+                                               (58.0, True),      # near the top: only planes below are far
+                                               (63.2, False)])    # wraps around the periodic z boundary: everywhere
+def test_plane_split_applies_only_when_far_planes_exist(g, emu, z, expect_split):
+    s = _sim(g, emu)
+    s.set_markers(*_sphere(z))
+    s.step(2)
+    assert (s.stats().split_substeps == 2) == expect_split
+
+
+def test_plane_split_needs_a_quarter_of_the_planes_and_enough_cells(g, emu):
+    s = _sim(g, emu)
+    X = np.concatenate([_sphere(8.0)[0], _sphere(30.0)[0], _sphere(52.0)[0]])      # bodies spread over the whole height
+    s.set_markers(X, np.zeros_like(X), np.ones(len(X), np.float32))
+    s.step(1)
+    assert s.stats().split_substeps == 0
+    t = _sim(g, emu, split_min_cells=0)          # default threshold: 2^20 far cells — this lattice has 7 680 cells in all
+    t.set_markers(*_sphere(20.0))
+    t.step(1)
+    assert t.stats().split_substeps == 0
+    u = _sim(g, emu, flags=g._abi.FLAG_NO_SPLIT)
+    u.set_markers(*_sphere(20.0))
+    u.step(1)
+    assert u.stats().split_substeps == 0
+
+
+def test_staged_marker_upload_is_flushed_by_whoever_needs_the_markers(g, emu):
+    """fg_set_markers only stages the message; the copy is queued by the next step (after the far-plane launch), by
+    fg_get_markers or by fg_set_link_origins.  Whatever the order of calls, the device sees the LAST marker set."""
+    a, b = _sim(g, emu), _sim(g, emu)
+    X1, U1, dV1 = _sphere(20.0)
+    X2, U2, dV2 = _sphere(33.0, n=90)
+    rho, u = util.smooth_fields(a.shape, amp=0.01)
+    for s in (a, b):
+        s.set_fields(rho, u)
+    # a: two sets in a row (the first is superseded before it was ever uploaded), read-back, origins, then step
+    a.set_markers(X1, U1, dV1)
+    a.set_markers(X2, U2, dV2)
+    Xr, Ur, lr = a.get_markers()
+    assert np.array_equal(Xr, X2) and len(lr) == 90
+    a.set_link_origins([[6.2, 5.1, 33.0]])
+    a.step(3)
+    # b: the plain order
+    b.set_markers(X2, U2, dV2)
+    b.set_link_origins([[6.2, 5.1, 33.0]])
+    b.step(3)
+    assert np.array_equal(a.get_populations(), b.get_populations())
+    assert np.array_equal(a.get_link_wrenches(), b.get_link_wrenches())
+    assert a.stats().n_markers == 90
+
+
+def test_call_timing_is_reported_once_the_call_has_finished(g, emu):
+    s = _sim(g, emu)
+    assert s.stats().last_step_ms == 0 and s.stats().last_mlups == 0
+    s.step(4)
+    s.sync()
+    st = s.stats()
+    assert st.steps == 4 and st.last_step_ms > 0
+    assert abs(st.last_mlups - st.cells * 4 / st.last_step_ms / 1e3) < 1e-6 * st.last_mlups
+    s2 = _sim(g, emu, flags=g._abi.FLAG_SYNC_STEP)
+    s2.step(1)
+    assert s2.stats().last_step_ms > 0
