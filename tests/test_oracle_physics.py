@@ -139,3 +139,52 @@ def test_sphere_drag_reduced_size(g):
     sn = 24 / Re * (1 + 0.15 * Re ** 0.687)
     assert 0.9 * sn < cd < 1.6 * sn, (cd, sn)
     s.close()
+
+
+@pytest.mark.parametrize("coll,tau", [("bgk", 1.0), ("mrt", 0.7)])
+def test_couette_linear_profile_is_exact_with_a_moving_wall(g, coll, tau):
+    """Plane Couette flow between y walls, the upper one moving tangentially in x AND z: the linear profile is an exact
+    solution of half-way bounce-back with the moving-wall term (walls half a cell outside the first / last node), for BGK
+    (to round-off) and for MRT (to third order in the wall speed) — this pins the 6 w_i c_i.u_w correction and the wall location."""
+    P, Wl = g.BC_PERIODIC, g.BC_WALL
+    NY, Uw, Ww = 12, 0.04, -0.02
+    s = g.Sim(backend="oracle", nx=4, ny=NY, nz=4, tau=tau, collision=g.MRT if coll == "mrt" else g.BGK,
+              bc=[P, P, Wl, Wl, P, P], wall_u={g._abi.YHI: [Uw, 0, Ww]})
+    nu = (tau - 0.5) / 3
+    s.step(int(6 * NY * NY / nu))
+    rho, u = s.get_fields(f64=True)
+    lin = (np.arange(NY) + 0.5) / NY
+    # BGK reproduces the line to round-off of the steady-state iteration; MRT with the default (non-magic) rates keeps an
+    # O(u_w^3) kink of ~1e-7 in the two nodes next to the moving wall
+    tol = 5e-9 if coll == "bgk" else 5e-7
+    assert np.abs(u[0][0, :, 0] - Uw * lin).max() < tol
+    assert np.abs(u[2][0, :, 0] - Ww * lin).max() < tol
+    assert np.abs(u[1]).max() < 1e-12 and np.abs(rho - 1).max() < (1e-9 if coll == "bgk" else 1e-5)   # MRT: O(u_w^2) density layer
+    s.close()
+
+
+def test_taylor_green_decay_error_is_second_order_in_resolution(g):
+    """Fitted decay rate against 2 nu k^2 at 16^3 and 32^3 (same tau): the error falls by ~4 when the resolution doubles."""
+    err = {}
+    for n in (16, 32):
+        tau = 0.8
+        s = g.Sim(backend="oracle", nx=n, ny=n, nz=2, tau=tau)
+        k = 2 * np.pi / n
+        z, y, x = np.meshgrid(np.arange(2), np.arange(n), np.arange(n), indexing="ij")
+        u = np.zeros((3, 2, n, n))
+        U0 = 0.01
+        u[0] = U0 * np.sin(k * x) * np.cos(k * y)
+        u[1] = -U0 * np.cos(k * x) * np.sin(k * y)
+        rho = 1 + 3 * (U0 ** 2 / 4) * (np.cos(2 * k * x) + np.cos(2 * k * y))
+        s.set_fields(rho, u)
+        t, amp = [], []
+        steps = n * n // 8
+        for it in range(8):
+            _, uu = s.get_fields(f64=True)
+            t.append(it * steps)
+            amp.append(np.sqrt((uu ** 2).mean()))
+            s.step(steps)
+        rate = -np.polyfit(t, np.log(amp), 1)[0]
+        err[n] = abs(rate / (2 * (tau - 0.5) / 3 * k * k) - 1)
+        s.close()
+    assert 3.0 < err[16] / err[32] < 5.5, err
