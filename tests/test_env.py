@@ -88,3 +88,12 @@ def test_tasks_probes_vector_env_and_snapshot(g, tmp_path):
         assert np.array_equal(o, vo[i]) and abs(r - vr[i]) < 1e-7
         e.close()
     vec.close()
+
+
+def test_python_example_runs_on_the_oracle_backend():
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "examples", "random_policy.py"), "--oracle", "--steps", "3", "--task", "path"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "env steps/s" in r.stdout
