@@ -22,10 +22,10 @@ def test_binding_lists_exactly_the_header(g):
     assert sorted(n for n, _, _ in g._abi.SYMBOLS) == header_functions()
 
 
-@pytest.mark.parametrize("backend", ["cuda", "oracle"])
+@pytest.mark.parametrize("backend", ["cuda", "cuda_f16", "oracle"])
 def test_library_exports_every_symbol(g, backend):
     path = g._abi.LIB_PATHS[backend]
-    if backend == "cuda" and not os.path.exists(path):
+    if backend.startswith("cuda") and not os.path.exists(path):
         import __graft_entry__
         __graft_entry__.build()
     lib = ctypes.CDLL(path)
@@ -34,10 +34,10 @@ def test_library_exports_every_symbol(g, backend):
     lib.fg_abi_version.restype = ctypes.c_int
     assert lib.fg_abi_version() == g._abi.FG_ABI_VERSION
     lib.fg_backend_name.restype = ctypes.c_char_p
-    assert lib.fg_backend_name() == {"cuda": b"cuda-sm100a", "oracle": b"oracle-fp64"}[backend]
+    assert lib.fg_backend_name() == {"cuda": b"cuda-sm100a", "cuda_f16": b"cuda-sm100a-f16", "oracle": b"oracle-fp64"}[backend]
 
 
-@pytest.mark.parametrize("backend", ["cuda", "oracle"])
+@pytest.mark.parametrize("backend", ["cuda", "cuda_f16", "oracle"])
 def test_struct_layout_matches_the_library(g, backend):
     lib = g.load_library(backend)
     cfg = g.FgConfig()
@@ -46,8 +46,9 @@ def test_struct_layout_matches_the_library(g, backend):
     assert (cfg.nx, cfg.collision, cfg.n_ranks, cfg.tau, cfg.inlet_rho) == (32, g.BGK, 1, 0.8, 1.0)
 
 
-def test_cuda_library_is_sm100a_only():
-    out = subprocess.run(["cuobjdump", "-lelf", os.path.join(ROOT, "gym-fish_b200", "csrc", "libfishgym_cuda.so")],
+@pytest.mark.parametrize("lib", ["libfishgym_cuda.so", "libfishgym_cuda_f16.so"])
+def test_cuda_library_is_sm100a_only(lib):
+    out = subprocess.run(["cuobjdump", "-lelf", os.path.join(ROOT, "gym-fish_b200", "csrc", lib)],
                          capture_output=True, text=True).stdout
     assert "sm_100a" in out and not re.search(r"sm_[89]\d", out), out
 
