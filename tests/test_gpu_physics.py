@@ -79,3 +79,14 @@ def test_closed_box_conserves_mass_with_every_wall_kind(g, cuda):
     assert np.isfinite(u1).all() and 1e-3 < u1[0, -1].mean() < 0.05        # the fluid under the lid is dragged along +x
     assert abs(u1[0].mean()) < 0.01
     s.close()
+
+
+def test_lid_driven_cavity_matches_ghia_re100(g, cuda):
+    """The published Re = 100 cavity profiles (Ghia, Ghia & Shin 1982; table in util.py) on the CUDA path alone — no
+    oracle involved: 128^2 nodes, x and y walls (CHECK_XWARP bulk rows + checked wall rows), moving lid, 30 000 steps.
+    The fp64 oracle gives 0.53 % / 0.82 % of the lid speed at this size (the rest is the scheme's Ma = 0.17
+    compressibility, not resolution), and the fp32 path must land on the same numbers."""
+    du, dv, w = util.cavity_vs_ghia(g, cuda, 128, 30000)
+    assert du < 0.012 and dv < 0.012, (du, dv)
+    assert abs(du - 0.00534) < 5e-4 and abs(dv - 0.00823) < 5e-4, (du, dv)     # the oracle's values at 40 000 steps
+    assert w < 1e-6

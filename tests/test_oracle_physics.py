@@ -188,3 +188,12 @@ def test_taylor_green_decay_error_is_second_order_in_resolution(g):
         err[n] = abs(rate / (2 * (tau - 0.5) / 3 * k * k) - 1)
         s.close()
     assert 3.0 < err[16] / err[32] < 5.5, err
+
+
+def test_lid_driven_cavity_matches_ghia_re100(g):
+    """Published benchmark numbers (Ghia, Ghia & Shin 1982, Re = 100) pin walls on four sides, the moving-wall term and the
+    non-linear advection together.  48^2 nodes, 10 000 steps (the flow is steady to 1e-5 by then): both centre-line
+    profiles within 1.2 % of the lid speed (measured 0.72 % / 0.65 %; 0.59 % / 0.73 % at 64^2)."""
+    du, dv, w = util.cavity_vs_ghia(g, "oracle", 48, 10000)
+    assert du < 0.012 and dv < 0.012, (du, dv)
+    assert w < 1e-12      # nothing drives the periodic direction

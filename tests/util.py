@@ -115,3 +115,36 @@ def run_pair(g, ref_backend, test_backend, kw, steps=(1, 2, 3, 10, 11), solid=No
     a.close()
     b.close()
     return worst
+
+
+# Lid-driven cavity at Re = 100: velocities on the two centre lines, in units of the lid speed, as tabulated by
+# Ghia, Ghia & Shin, J. Comput. Phys. 48 (1982) 387, tables I and II (129 x 129 multigrid solution).  A published
+# numerical benchmark — the one set of "golden numbers" for this path that does not come from this repository.
+GHIA_RE100_U = np.array([   # (y, u) along x = 1/2
+    [1.0000, 1.00000], [0.9766, 0.84123], [0.9688, 0.78871], [0.9609, 0.73722], [0.9531, 0.68717], [0.8516, 0.23151],
+    [0.7344, 0.00332], [0.6172, -0.13641], [0.5000, -0.20581], [0.4531, -0.21090], [0.2813, -0.15662], [0.1719, -0.10150],
+    [0.1016, -0.06434], [0.0703, -0.04775], [0.0625, -0.04192], [0.0547, -0.03717], [0.0000, 0.00000]])
+GHIA_RE100_V = np.array([   # (x, v) along y = 1/2
+    [1.0000, 0.00000], [0.9688, -0.05906], [0.9609, -0.07391], [0.9531, -0.08864], [0.9453, -0.10313], [0.9063, -0.16914],
+    [0.8594, -0.22445], [0.8047, -0.24533], [0.5000, 0.05454], [0.2344, 0.17527], [0.2266, 0.17507], [0.1563, 0.16077],
+    [0.0938, 0.12317], [0.0781, 0.10890], [0.0703, 0.10091], [0.0625, 0.09233], [0.0000, 0.00000]])
+
+
+def cavity_vs_ghia(g, backend, n, steps, lid=0.1):
+    """Lid-driven cavity in the x-y plane (lid = y-high wall moving along +x, z periodic and 2 cells deep), Re = 100.
+    Returns the largest deviations of the centre-line profiles from Ghia et al., in units of the lid speed."""
+    P, Wl = g.BC_PERIODIC, g.BC_WALL
+    nu = lid * n / 100.0
+    s = g.Sim(backend=backend, nx=n, ny=n, nz=2, tau=3 * nu + 0.5, collision=g.MRT, bc=[Wl, Wl, Wl, Wl, P, P],
+              wall_u={g._abi.YHI: [lid, 0, 0]})
+    s.step(steps)
+    _, u = s.get_fields(f64=True)
+    s.close()
+    assert np.isfinite(u).all()
+    # walls sit half a cell outside the first / last node; the centre line falls between two columns of nodes
+    at = np.concatenate([[0.0], (np.arange(n) + 0.5) / n, [1.0]])
+    ucl = np.concatenate([[0.0], 0.5 * (u[0][0, :, n // 2 - 1] + u[0][0, :, n // 2]) / lid, [1.0]])
+    vcl = np.concatenate([[0.0], 0.5 * (u[1][0, n // 2 - 1, :] + u[1][0, n // 2, :]) / lid, [0.0]])
+    du = np.abs(np.interp(GHIA_RE100_U[:, 0], at, ucl) - GHIA_RE100_U[:, 1]).max()
+    dv = np.abs(np.interp(GHIA_RE100_V[:, 0], at, vcl) - GHIA_RE100_V[:, 1]).max()
+    return float(du), float(dv), float(np.abs(u[2]).max())
