@@ -67,7 +67,7 @@ __global__ void wait_kernel(int *flags, int lo, int hi, unsigned long long timeo
             if (v >= value) break;
             unsigned long long t;
             asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-            if (t - t0 > timeout_ns) { flags[3] = 1; *host_word = 1; return; }   // sticky; the host word (pinned) lets fg_step see it without a sync
+            if (t - t0 > timeout_ns) { flags[3] = 1; if (host_word) *host_word = 1; return; }   // sticky; the host word (pinned) lets fg_step see it without a sync
             __nanosleep(200);
         }
     }
@@ -94,7 +94,7 @@ __global__ void wait_counters_kernel(int *mine, CounterList s, unsigned long lon
             if (x >= v) break;
             unsigned long long t;
             asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-            if (t - t0 > timeout_ns) { mine[3] = 1; *host_word = 2; return; }
+            if (t - t0 > timeout_ns) { mine[3] = 1; if (host_word) *host_word = 2; return; }
             __nanosleep(200);
         }
     }
@@ -131,6 +131,18 @@ public:
         cudaDeviceGetStreamPriorityRange(&least, &greatest);
         prio_low_ = least; prio_high_ = greatest;
         debug_sync_ = getenv("FG_DEBUG_SYNC") != nullptr;       // debugging aid: serialise every launch
+        // the neighbour-wait kernels give up after this long (ranks out of step); FG_PEER_TIMEOUT_MS shortens it for tests
+        if (const char *t = getenv("FG_PEER_TIMEOUT_MS")) {
+            const long long ms = atoll(t);
+            if (ms > 0) peer_timeout_ns_ = (unsigned long long)ms * 1000000ull;
+        }
+        // one pinned, device-mapped word the wait kernels raise when they time out: fg_step reads it without a sync
+        {
+            int *w = nullptr;
+            if (!ck(cudaHostAlloc(reinterpret_cast<void **>(&w), sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable), "cudaHostAlloc(timeout word)")) { e = err; return false; }
+            *w = 0;
+            timeout_word_ = w;
+        }
         bool ok = true;
         for (int i = 0; i < kStreams && ok; ++i)
             ok = ck(cudaStreamCreateWithPriority(&s_[i], cudaStreamNonBlocking, i < 2 ? greatest : least), "cudaStreamCreate") &&
@@ -393,7 +405,7 @@ public:
         if (gmode_ == 2) return true;
         CounterList s{};
         for (int i = 0; i < n && i < 8; ++i) s.p[i] = sources[i];
-        wait_counters_kernel<<<1, 1, 0, stream_>>>(mine, s, 20ull * 1000ull * 1000ull * 1000ull, timeout_word_);
+        wait_counters_kernel<<<1, 1, 0, stream_>>>(mine, s, peer_timeout_ns_, timeout_word_);
         return ck(cudaGetLastError(), "wait launch");
     }
     template <class Blob>
@@ -439,7 +451,7 @@ public:
         cudaSetDevice(device_);
         ++launches;
         if (gmode_ == 2) return true;
-        wait_kernel<<<1, 1, 0, stream_>>>(flags, lo, hi, 20ull * 1000ull * 1000ull * 1000ull, timeout_word_);
+        wait_kernel<<<1, 1, 0, stream_>>>(flags, lo, hi, peer_timeout_ns_, timeout_word_);
         return ck(cudaGetLastError(), "wait launch");
     }
 
@@ -522,7 +534,8 @@ private:
     cudaEvent_t fork_ev_[kStreams] = {nullptr, nullptr, nullptr, nullptr}, join_ev_[kStreams] = {nullptr, nullptr, nullptr, nullptr};
     int cur_ = 0;
     int prio_low_ = 0, prio_high_ = 0;
-    volatile int *timeout_word_ = nullptr;
+    volatile int *timeout_word_ = nullptr;     // pinned + mapped (UVA: the same pointer is valid on the device)
+    unsigned long long peer_timeout_ns_ = 20ull * 1000ull * 1000ull * 1000ull;
     bool debug_sync_ = false;
     int sm_count_ = 148;
     bool coop_ = false;

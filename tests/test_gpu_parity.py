@@ -333,3 +333,26 @@ def test_vector_env_on_one_gpu(g, cuda):
         assert np.abs(o - vo2[i]).max() < 1e-5 and abs(r - vr2[i]) < 1e-5     # float atomics order may differ
         e.close()
     vec.close()
+
+
+def test_slab_that_runs_ahead_reports_fg_epeer(g, cuda, monkeypatch):
+    """Ranks out of step: a slab stepped twice without its neighbour waits for halos that never come.  The neighbour-wait
+    kernel gives up after FG_PEER_TIMEOUT_MS (20 s by default), raises a pinned host word, and the library reports
+    FG_EPEER — from fg_step if the kernel has already given up, from fg_sync at the latest — instead of hanging."""
+    monkeypatch.setenv("FG_PEER_TIMEOUT_MS", "250")
+    kw = dict(nx=16, ny=12, nz=16, tau=0.7, collision=g.MRT)
+    parts = [g.Sim(backend=cuda, n_ranks=2, rank=r, **kw) for r in range(2)]
+    h = [s.peer_export() for s in parts]
+    parts[0].peer_connect(h[1], h[1])
+    parts[1].peer_connect(h[0], h[0])
+    for it in range(2):
+        for s in parts:
+            s.step(1)
+    parts[0].step(1)              # fine: rank 1's halos of the previous step are there
+    parts[0].sync()
+    with pytest.raises(g.FgError) as ei:
+        parts[0].step(1)          # needs halos rank 1 has not pushed
+        parts[0].sync()
+    assert ei.value.code == g._abi.FG_EPEER, ei.value
+    for s in parts:
+        s.close()
