@@ -816,32 +816,31 @@ public:
                 ok = ok && dev.template launch_block_phased<IbInterpSpread>(Dim3x(std::max(nb, (6 * nl_ + 127) / 128)), p);
                 ok = ok && dev.template launch<IbLinkReduce>(Dim3x((n_ + 127) / 128), p);
             } else {
-            ok = ok && dev.template launch<IbInterpolate>(Dim3x(std::max(nb, (6 * nl_ + 127) / 128)), p);
-            if (xchg_) {
-                // partial U* to the face neighbours, wait for theirs (counter value c+1 of this exchange)
+                // bodies across slab faces: the exchange of partial U* sits between interpolation and spreading
                 int *mine = reinterpret_cast<int *>(xbuf_);
-                int *sig[2] = {peer_lo_x_ ? reinterpret_cast<int *>(peer_lo_x_) + 2 : nullptr,    // I am its z-high neighbour
-                               peer_hi_x_ ? reinterpret_cast<int *>(peer_hi_x_) + 1 : nullptr};   // I am its z-low neighbour
-                int *wt[2] = {peer_lo_x_ ? mine + 1 : nullptr, peer_hi_x_ ? mine + 2 : nullptr};
-                ok = ok && dev.template launch<IbPushPartial>(Dim3x((n_ + 127) / 128), p);
-                ok = ok && dev.signal_counters(mine, sig, 2, false) && dev.wait_counters(mine, wt, 2);
-                ok = ok && dev.template launch<IbAddPartial>(Dim3x((n_ + 127) / 128), p);
-            }
-            ok = ok && dev.template launch<IbForceSpread>(Dim3x(nb), p);
-            ok = ok && dev.template launch<IbLinkReduce>(Dim3x((n_ + 127) / 128), p);
-            if (xchg_) {
-                int *mine = reinterpret_cast<int *>(xbuf_);
-                int *sig[kMaxRanks], *wt[kMaxRanks];
-                for (int r = 0; r < kMaxRanks; ++r) {
-                    sig[r] = peer_all_x_[r] ? reinterpret_cast<int *>(peer_all_x_[r]) + 4 + rank_ : nullptr;
-                    wt[r] = peer_all_x_[r] ? mine + 4 + r : nullptr;
+                ok = ok && dev.template launch<IbInterpolate>(Dim3x(std::max(nb, (6 * nl_ + 127) / 128)), p);
+                {   // partial U* to the face neighbours, wait for theirs (counter value c+1 of this exchange)
+                    int *sig[2] = {peer_lo_x_ ? reinterpret_cast<int *>(peer_lo_x_) + 2 : nullptr,    // I am its z-high neighbour
+                                   peer_hi_x_ ? reinterpret_cast<int *>(peer_hi_x_) + 1 : nullptr};   // I am its z-low neighbour
+                    int *wt[2] = {peer_lo_x_ ? mine + 1 : nullptr, peer_hi_x_ ? mine + 2 : nullptr};
+                    ok = ok && dev.template launch<IbPushPartial>(Dim3x((n_ + 127) / 128), p);
+                    ok = ok && dev.signal_counters(mine, sig, 2, false) && dev.wait_counters(mine, wt, 2);
+                    ok = ok && dev.template launch<IbAddPartial>(Dim3x((n_ + 127) / 128), p);
                 }
-                const int g6 = (6 * nl_ + 127) / 128;
-                ok = ok && dev.template launch<IbPushWrench>(Dim3x(g6), p);
-                ok = ok && dev.signal_counters(mine, sig, kMaxRanks, false) && dev.wait_counters(mine, wt, kMaxRanks);
-                ok = ok && dev.template launch<IbSumWrench>(Dim3x(g6), p);
-                ok = ok && dev.signal_counters(mine, nullptr, 0, true);   // bump my counter: this exchange is complete
-            }
+                ok = ok && dev.template launch<IbForceSpread>(Dim3x(nb), p);
+                ok = ok && dev.template launch<IbLinkReduce>(Dim3x((n_ + 127) / 128), p);
+                {   // owner-reduced link wrenches to every rank, summed in rank order (bit-identical totals everywhere)
+                    int *sig[kMaxRanks], *wt[kMaxRanks];
+                    for (int r = 0; r < kMaxRanks; ++r) {
+                        sig[r] = peer_all_x_[r] ? reinterpret_cast<int *>(peer_all_x_[r]) + 4 + rank_ : nullptr;
+                        wt[r] = peer_all_x_[r] ? mine + 4 + r : nullptr;
+                    }
+                    const int g6 = (6 * nl_ + 127) / 128;
+                    ok = ok && dev.template launch<IbPushWrench>(Dim3x(g6), p);
+                    ok = ok && dev.signal_counters(mine, sig, kMaxRanks, false) && dev.wait_counters(mine, wt, kMaxRanks);
+                    ok = ok && dev.template launch<IbSumWrench>(Dim3x(g6), p);
+                    ok = ok && dev.signal_counters(mine, nullptr, 0, true);   // bump my counter: this exchange is complete
+                }
             }
         }
         markers_dirty_ = false;
