@@ -264,6 +264,8 @@ def main():
     else:
         os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1))
     import gym_fish_b200 as g
+    # the CPU legs (cpu_baseline, --impl reference) time the oracle; the package itself does not know it
+    g.register_backend("oracle", os.path.join(ROOT, "oracle", "libfishgym_oracle.so"))
 
     if args.impl == "reference":
         run_reference(args, g, rank, world)

@@ -6,7 +6,7 @@ importing this package must not import torch (BASELINE.json:5: "no PyTorch depen
 """
 from . import _abi
 from ._abi import (BC_INLET, BC_OUTLET, BC_PERIODIC, BC_WALL, BGK, MRT, FgConfig, FgError, FgFishDesc, FgStats,
-                   Sim, default_config, load_library)
+                   Sim, default_config, load_library, register_backend)
 
-__all__ = ["_abi", "Sim", "FgConfig", "FgFishDesc", "FgStats", "FgError", "default_config", "load_library",
+__all__ = ["_abi", "Sim", "FgConfig", "FgFishDesc", "FgStats", "FgError", "default_config", "load_library", "register_backend",
            "BGK", "MRT", "BC_PERIODIC", "BC_WALL", "BC_INLET", "BC_OUTLET"]

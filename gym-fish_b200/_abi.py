@@ -1,8 +1,8 @@
 """ctypes binding of include/fishgym.h — numpy only, no torch on the sim path.
 
 The product loads ``csrc/libfishgym_cuda.so`` and fails loudly when it is missing; there is no CPU
-fallback.  ``load_library("oracle")`` exists for tests/, ``__graft_entry__.smoke()`` and the
-``cpu_baseline`` leg of ``bench.py`` only (the oracle is the checker, never the product).
+fallback, and this package does not know where the CPU oracle lives.  Checkers (tests/, ``__graft_entry__.smoke()``,
+the ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py``) name it themselves with ``register_backend``.
 
 Boundary defined by BASELINE.json:5 (the reference ships no interface: /root/reference/README.md:14).
 """
@@ -100,14 +100,21 @@ class FgPeerHandle(C.Structure):
 
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_REPO = os.path.dirname(_HERE)
 LIB_PATHS = {
     # FG_CUDA_LIB: another build of the same library (kernel experiments, e.g. different launch bounds)
     "cuda": os.environ.get("FG_CUDA_LIB") or os.path.join(_HERE, "csrc", "libfishgym_cuda.so"),
     # opt-in build of the same sources: 16-bit population storage, fp32 arithmetic (half the HBM bytes per update)
     "cuda_f16": os.path.join(_HERE, "csrc", "libfishgym_cuda_f16.so"),
-    "oracle": os.path.join(_REPO, "oracle", "libfishgym_oracle.so"),
 }
+
+
+def register_backend(name: str, path: str) -> None:
+    """Give another library that exports the ABI of include/fishgym.h a short name (``Sim(backend=name)``).
+    The product registers nothing: tests, smoke() and bench.py's CPU legs use this for the oracle."""
+    if name in ("cuda", "cuda_f16"):
+        raise ValueError("the product backends cannot be re-pointed; use FG_CUDA_LIB for kernel experiments")
+    LIB_PATHS[name] = os.path.abspath(path)
+
 
 # every symbol include/fishgym.h declares: (name, restype, argtypes)
 _P = C.c_void_p
@@ -165,8 +172,8 @@ def load_library(backend: str = "cuda") -> C.CDLL:
     path = LIB_PATHS.get(backend, backend)
     if not os.path.exists(path):
         hint = ("run `python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a)" if backend.startswith("cuda")
-                else "run `make -C oracle`")
-        raise FileNotFoundError(f"fishgym backend '{backend}' not built: {path} is missing; {hint}")
+                else "not a registered backend name nor the path of a library (register_backend)")
+        raise FileNotFoundError(f"fishgym backend '{backend}': {path} is missing; {hint}")
     lib = C.CDLL(path, mode=C.RTLD_LOCAL)
     for name, restype, argtypes in SYMBOLS:
         fn = getattr(lib, name)   # AttributeError here means the library does not export the ABI

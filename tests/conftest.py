@@ -16,6 +16,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
+ORACLE = os.path.join(ROOT, "oracle", "libfishgym_oracle.so")
 EMU = os.path.join(ROOT, "tests", "emu", "libfishgym_emu.so")
 EMU_F16 = os.path.join(ROOT, "tests", "emu", "libfishgym_emu_f16.so")
 
@@ -33,7 +34,8 @@ def _ensure(path, directory):
 @pytest.fixture(scope="session")
 def g():
     import gym_fish_b200
-    _ensure(gym_fish_b200._abi.LIB_PATHS["oracle"], "oracle")
+    # the package itself does not know the oracle: the checker is named here, by the tests
+    gym_fish_b200.register_backend("oracle", _ensure(ORACLE, "oracle"))
     return gym_fish_b200
 
 

@@ -16,6 +16,8 @@ sys.path.insert(0, os.path.dirname(HERE))
 import gym_fish_b200 as g  # noqa: E402
 import util  # noqa: E402
 
+util.register_oracle(g)
+
 STEPS = 11
 CASES = ["bgk_periodic", "mrt_force", "bgk_ywall_moving", "mrt_all_walls_lid", "mrt_inlet_outlet_ywalls", "mrt_ragged"]
 

@@ -90,7 +90,7 @@ def test_no_cpu_fallback_without_gpu(g):
 
 def test_sim_path_does_not_import_torch():
     code = ("import sys; sys.path.insert(0, %r); import gym_fish_b200 as g; from gym_fish_b200 import env; "
-            "s = g.Sim(backend='oracle', nx=8, ny=8, nz=8); s.step(1); assert 'torch' not in sys.modules") % ROOT
+            "s = g.Sim(backend=%r, nx=8, ny=8, nz=8); s.step(1); assert 'torch' not in sys.modules") % (ROOT, os.path.join(ROOT, "oracle", "libfishgym_oracle.so"))
     subprocess.run([sys.executable, "-c", code], check=True)
 
 

@@ -90,10 +90,11 @@ def test_tasks_probes_vector_env_and_snapshot(g, tmp_path):
     vec.close()
 
 
-def test_python_example_runs_on_the_oracle_backend():
+def test_python_example_runs_against_the_checker_library():
     import os, subprocess, sys
+    import util
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, os.path.join(root, "examples", "random_policy.py"), "--oracle", "--steps", "3", "--task", "path"],
+    r = subprocess.run([sys.executable, os.path.join(root, "examples", "random_policy.py"), "--small", "--lib", util.ORACLE_LIB, "--steps", "3", "--task", "path"],
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "env steps/s" in r.stdout

@@ -26,6 +26,7 @@ import os, sys
 sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
 import numpy as np, torch, torch.distributed as dist
 import gym_fish_b200 as g, util
+util.register_oracle(g)
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 dist.init_process_group("gloo", rank=rank, world_size=world)
 case = {case!r}

@@ -1,5 +1,15 @@
 """Shared helpers for the parity tests (seeded synthetic inputs, norms, marker clouds, fish descriptions)."""
+import os
+
 import numpy as np
+
+ORACLE_LIB = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "libfishgym_oracle.so")
+
+
+def register_oracle(g):
+    """The package does not know the CPU oracle (it is the checker, not a backend of the product): tests name it."""
+    g.register_backend("oracle", ORACLE_LIB)
+    return "oracle"
 
 
 def rel_l2(a, b):
