@@ -187,8 +187,7 @@ class FishEnv:
         for f, length, stride in zip(self.cfg.fish, self._body_len, self._obs_stride):
             o, p = obs[off:off + stride], self._last[off:off + stride]
             dx, dz = float(o[0] - p[0]), float(o[2] - p[2])
-            if not self.cfg.walls or True:
-                dz = (dz + nz / 2) % nz - nz / 2          # z is periodic
+            dz = (dz + nz / 2) % nz - nz / 2              # z is periodic with or without tank walls on x, y
             # progress along the nose direction of the initial heading: nose = -(sin h, cos h)
             reward += -(np.sin(f.heading) * dx + np.cos(f.heading) * dz) / length
             if self.cfg.walls and not (0.1 * nx < o[0] < 0.9 * nx):
