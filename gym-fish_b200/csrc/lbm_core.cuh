@@ -782,6 +782,7 @@ struct FaceOp {
     pop_t *dst;                // copy destination lattice base (own, or a z-neighbour's over NVLink); slot stride L.slot
     long long dst_off;
     const uint8_t *sender_solid;   // solid flags of the sender's boundary plane (plane-sized) or nullptr
+    const uint8_t *receiver_solid; // solid flags of the receiver's boundary plane (plane-sized) or nullptr
 };
 struct HaloParams {
     Lattice L;
@@ -821,6 +822,9 @@ struct ZFaceOp {
                     if (op.sender_solid[sy * L.nx + sx]) return;
                 }
             }
+            // An obstacle cell of the receiving boundary plane keeps what it holds (nothing reads it but the immersed-
+            // boundary moments, which see the initial state there, like the oracle).
+            if (p.parity_done == 1 && op.receiver_solid && op.receiver_solid[c]) return;
             const int k = op.src_by_index ? by : slot;
             op.dst[slot * L.slot + op.dst_off + c] = op.src[k * op.src_slot + op.src_off + c];
             return;
@@ -836,12 +840,20 @@ struct ZFaceOp {
         } else {
             // the next (even) step reads them from natural slot i of the boundary plane
             if (link_from_wall(L, i, x, y)) return;
+            if (L.solid && L.solid[(long long)(hi ? L.nz : 1) * L.plane + c]) return;   // obstacle cells keep what they hold
             if (op.mode == BC_OUTLET && L.solid) {
                 // the clamped pull source (x-cx, y-cy) of the same plane is an obstacle: bounce-back owns the slot
                 int sx = x - cxr(i), sy = y - cyr(i);
                 sx = sx < 0 ? sx + L.nx : (sx >= L.nx ? sx - L.nx : sx);
                 sy = sy < 0 ? sy + L.ny : (sy >= L.ny ? sy - L.ny : sy);
                 if (L.solid[((long long)(hi ? L.nz : 1) * L.ny + sy) * L.nx + sx]) return;
+                // The plane inside is an obstacle at (x,y): the source cell's push towards it was bounced into the
+                // source's own slot opp(i) and nothing arrived below, so the post-collision value is taken from there.
+                if (L.solid[(long long)(hi ? L.nz - 1 : 2) * L.plane + c]) {
+                    L.f[i * L.slot + (long long)(hi ? L.nz : 1) * L.plane + c] =
+                        L.f[oppr(i) * L.slot + ((long long)(hi ? L.nz : 1) * L.ny + sy) * L.nx + sx];
+                    return;
+                }
             }
             pop_t *cell = L.f + i * L.slot + (long long)(hi ? L.nz : 1) * L.plane + c;
             if (op.mode == BC_INLET) pop_st(cell, p.C.heq_in[i]);

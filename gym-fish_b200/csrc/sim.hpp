@@ -496,6 +496,7 @@ public:
         op.dst_off = (long long)dzz * L_.plane;
         // the sender's boundary plane is my ghost plane
         op.sender_solid = L_.solid ? L_.solid + (long long)(hi ? L_.nz + 1 : 0) * L_.plane : nullptr;
+        op.receiver_solid = L_.solid ? L_.solid + (long long)(hi ? L_.nz : 1) * L_.plane : nullptr;
         Dim3 g{(L_.plane + ZFaceOp::kThreads - 1) / ZFaceOp::kThreads, 5, 1};
         if (!dev.template launch<ZFaceOp>(g, p) || !dev.sync()) return cuda_fail();
         --pending_faces_;
@@ -767,6 +768,8 @@ private:
                     op.dst_off = (long long)(hi ? 1 : L_.nz) * L_.plane;
                 }
                 op.sender_solid = L_.solid ? L_.solid + (long long)(hi ? L_.nz : 1) * L_.plane : nullptr;
+                // my ghost-plane flags mirror the neighbour's boundary plane (fg_set_solid fills them from the global field)
+                op.receiver_solid = L_.solid ? L_.solid + (long long)(hi ? L_.nz + 1 : 0) * L_.plane : nullptr;
             }
             any = any || op.mode != BC_WALL;
         }
