@@ -186,3 +186,175 @@ def run_slab_case(g, emu, seed):
 def test_random_configurations_in_slabs_equal_unsplit(g, emu):
     bad = [(seed, kw) for seed in range(120) for ok, kw in [run_slab_case(g, emu, seed)] if not ok]
     assert not bad, bad[:3]
+
+
+def stable(rho, keep=1):
+    return bool(np.isfinite(rho).all() and 0.7 < (rho * keep + (1 - keep)).min() and (rho * keep).max() < 1.3)
+
+
+def run_moving_markers_case(g, backend, seed):
+    """A marker cloud that drifts (up to 1.2 planes per step), is sometimes replaced by another one, left alone (static
+    reuse of index map and band) or removed, steps of 1-3 substeps, obstacles, probes, the plane split and the fused
+    step pairs switched on at random: everything the host logic decides per substep, against the oracle."""
+    A = g._abi
+    rng = np.random.default_rng(seed)
+    kw, solid, _ = random_case(g, rng)
+    kw["nz"], kw["ny"] = int(rng.integers(4, 40)), max(kw["ny"], 4)
+    kw["nx"] = max(kw["nx"], 4)
+    nx, ny, nz = kw["nx"], kw["ny"], kw["nz"]
+    if solid is not None:
+        solid = (rng.random((nz, ny, nx)) < 0.05).astype(np.uint8)
+    kw.update(max_markers=64, max_links=4)
+    if rng.random() < 0.3:
+        kw["flags"] |= A.FLAG_FUSED_PAIRS
+    a, b = g.Sim(backend="oracle", **kw), g.Sim(backend=backend, **kw)
+    rho, u = util.smooth_fields(a.shape)
+    rho = (rho + 0.003 * rng.standard_normal(a.shape)).astype(np.float32)
+    u = (u + 0.003 * rng.standard_normal((3,) + a.shape)).astype(np.float32)
+    for s in (a, b):
+        if solid is not None:
+            s.set_solid(solid)
+        s.set_fields(rho, u)
+    nl = int(rng.integers(1, 4))
+
+    def cloud(c):
+        n = int(rng.integers(1, 24))
+        return ((c + rng.uniform(-2.5, 2.5, (n, 3))).astype(np.float32), np.sort(rng.integers(0, nl, n)).astype(np.int32),
+                rng.uniform(0.2, 1.0, n).astype(np.float32))
+
+    c = rng.uniform(0.2, 0.8, 3) * [nx, ny, nz]
+    X, link, dV = cloud(c)
+    V = rng.uniform(-0.4, 0.4, 3) * [1, 1, 3]
+    origins = rng.uniform(0, 10, (nl, 3))
+    keep = 1 if solid is None else (solid == 0)
+    worst, have = {}, False
+    for _ in range(10):
+        r = rng.random()
+        if r < 0.55 or not have:
+            if rng.random() < 0.15:
+                X, link, dV = cloud(c)
+            X, c = (X + V).astype(np.float32), c + V
+            U = np.tile(V.astype(np.float32) * 0.05, (len(X), 1))
+            for s in (a, b):
+                s.set_markers(X, U, dV, link)
+                s.set_link_origins(origins)
+            have = True
+        elif r < 0.65:
+            for s in (a, b):
+                s.set_markers(X[:0], U[:0], dV[:0], link[:0])
+            have = False
+        k = int(rng.integers(1, 4))
+        a.step(k)
+        b.step(k)
+        ra, ua = a.get_fields(f64=True)
+        if not stable(ra, keep):
+            worst = None
+            break
+        rb, ub = b.get_fields(f64=True)
+        e = dict(u=np.abs((ua - ub) * keep).max(), rho=np.abs((ra - rb) * keep).max(),
+                 f=np.abs((a.get_populations() - b.get_populations()) * keep).max())
+        if have:
+            (ba, oa), (bb, ob) = a.get_index_map(), b.get_index_map()
+            wa, wb = a.get_link_wrenches(), b.get_link_wrenches()
+            pts = (rng.uniform(0, 1, (5, 3)) * [nx, ny, nz]).astype(np.float32)
+            e.update(index_map=0.0 if np.array_equal(ba, bb) and np.array_equal(oa, ob) else 1.0,
+                     band=abs(a.stats().band_cells - b.stats().band_cells),
+                     Fm=np.abs(a.get_marker_forces() - b.get_marker_forces()).max(),
+                     wrench=np.abs(wa - wb).max() / max(np.abs(wa).max(), 1e-3), probe=np.abs(a.probe(pts) - b.probe(pts)).max())
+        for key, v in e.items():
+            worst[key] = max(worst.get(key, 0.0), float(v))
+    st = b.stats()
+    a.close()
+    b.close()
+    return worst, kw, st.split_substeps > 0, st.pair_substeps > 0
+
+
+def check_moving(g, backend, seeds):
+    limits = dict(LIMITS, probe=5e-6)
+    bad, ran, splits, pairs = [], 0, 0, 0
+    for seed in seeds:
+        worst, kw, split, pair = run_moving_markers_case(g, backend, seed)
+        if worst is None:
+            continue
+        ran, splits, pairs = ran + 1, splits + split, pairs + pair
+        if any(worst[k] > limits[k] for k in worst):
+            bad.append((seed, worst, kw))
+    assert not bad, bad[:3]
+    assert ran >= 0.75 * len(seeds) and splits >= 0.1 * len(seeds) and pairs >= 2      # the interesting paths were taken
+
+
+def test_random_moving_markers_emulated_kernels_vs_oracle(g, emu):
+    check_moving(g, emu, range(120))
+
+
+def run_fish_case(g, backend, seed):
+    """One or two random articulated fish (1-5 links, pinned or free, random servo gains / limits / densities), random
+    actions, 1-7 substeps per call, now and then a reset: the product's host integrator (csrc/body.hpp) + IB + fluid
+    against the oracle's independently written one (oracle/oracle_body.hpp)."""
+    P, Wl = g.BC_PERIODIC, g.BC_WALL
+    rng = np.random.default_rng(seed)
+    nx, ny, nz = int(rng.integers(16, 26)), int(rng.integers(14, 22)), int(rng.integers(30, 56))
+    kw = dict(nx=nx, ny=ny, nz=nz, tau=float(rng.uniform(0.6, 1.0)), collision=int(rng.integers(0, 2)),
+              bc=[Wl] * 4 + [P] * 2 if rng.random() < 0.5 else [P] * 6, max_markers=6000, max_links=16)
+    if rng.random() < 0.5:
+        kw["split_min_cells"] = 1
+    a, b = g.Sim(backend="oracle", **kw), g.Sim(backend=backend, **kw)
+    nf = int(rng.integers(1, 3))
+    for f in range(nf):
+        links = tuple((float(rng.uniform(4, 8)), float(rng.uniform(1.2, 2.8))) for _ in range(int(rng.integers(1, 6))))
+        d = util.fish_desc(g, root=(nx / 2 + rng.uniform(-2, 2), ny / 2 + rng.uniform(-1, 1), nz * (0.3 + 0.35 * f) + rng.uniform(-2, 2)),
+                           links=links, free=int(rng.random() < 0.6), heading=float(rng.uniform(-0.5, 0.5)))
+        d.density_ratio, d.joint_gain = float(rng.uniform(0.8, 1.5)), float(rng.uniform(0.05, 0.4))
+        d.joint_limit, d.joint_rate_max = float(rng.uniform(0.2, 0.8)), float(rng.uniform(0.005, 0.03))
+        if rng.random() < 0.3:
+            d.markers_per_link = int(rng.integers(8, 60))
+        for s in (a, b):
+            s.add_fish(d)
+    assert a.stats().n_markers == b.stats().n_markers and a.obs_size() == b.obs_size()
+    worst = dict(obs=0.0, wrench=0.0, u=0.0)
+    for it in range(6):
+        act = rng.uniform(-1.3, 1.3, a.action_size()).astype(np.float32)      # beyond [-1, 1]: clipped by the library
+        k = int(rng.integers(1, 8))
+        for s in (a, b):
+            s.set_action(act)
+            s.step(k)
+        oa, ob = a.get_obs(), b.get_obs()
+        ra, ua = a.get_fields(f64=True)
+        if not (np.isfinite(oa).all() and np.isfinite(ra).all() and 0.85 < ra.min() and ra.max() < 1.15):
+            worst = None            # fish too large for their tank: the coupled run itself diverges
+            break
+        wa, wb = a.get_link_wrenches(), b.get_link_wrenches()
+        worst["obs"] = max(worst["obs"], float(np.abs(oa - ob).max()))
+        worst["wrench"] = max(worst["wrench"], float(np.abs(wa - wb).max() / max(np.abs(wa).max(), 1e-6)))
+        if it % 3 == 2:
+            if rng.random() < 0.3:
+                for s in (a, b):
+                    s.reset(0)
+            else:
+                worst["u"] = max(worst["u"], util.rel_l2(b.get_fields(f64=True)[1], ua))
+    a.close()
+    b.close()
+    return worst, kw
+
+
+def check_fish(g, backend, seeds):
+    bad, ran = [], 0
+    for seed in seeds:
+        worst, kw = run_fish_case(g, backend, seed)
+        if worst is None:
+            continue
+        ran += 1
+        if worst["obs"] > 1e-4 or worst["wrench"] > 1e-4 or worst["u"] > 1e-5:
+            bad.append((seed, worst, kw))
+    assert not bad, bad[:3]
+    assert ran >= 0.5 * len(seeds)
+
+
+def test_random_fish_emulated_kernels_vs_oracle(g, emu):
+    check_fish(g, emu, range(24))
+
+
+@pytest.mark.gpu
+def test_random_moving_markers_and_fish_cuda_vs_oracle(g, cuda):
+    check_moving(g, cuda, range(2000, 2080))
+    check_fish(g, cuda, range(2000, 2012))
