@@ -686,7 +686,9 @@ public:
         if (xchg_) {
             for (int k = 0; k < n; ++k) {
                 const int k0 = int(std::floor(X[3 * k + 2])) - 1;
-                if (slab_of(k0) == rank_ || slab_of(k0 + 3) == rank_) act_.push_back(k);
+                // ... or that this rank owns: a marker whose stencil lies entirely outside a non-periodic box touches no slab,
+                // yet its force 2 (U_d - 0) still counts in its link's wrench (as on one rank, and in the oracle)
+                if (slab_of(k0) == rank_ || slab_of(k0 + 3) == rank_ || owner_of(k0) == rank_) act_.push_back(k);
             }
         }
         const int m = xchg_ ? int((act_.size() + kPad - 1) / kPad * kPad) : n;
@@ -883,9 +885,7 @@ public:
         // (same formula as IbIndexMark), so the others are filled in on the host and the held ones come from the device
         for (int k = 0; k < n_total_; ++k) {
             for (int d = 0; d < 3; ++d) base3[3 * k + d] = int(std::floor(hX_[3 * k + d])) - 1;
-            int kc = slab_plane(base3[3 * k + 2] + 1);
-            if (kc < 0) kc = base3[3 * k + 2] + 1 < 0 ? 0 : nzg_ - 1;
-            owner[k] = kc / nzl_;
+            owner[k] = owner_of(base3[3 * k + 2]);
         }
         std::vector<int> b(3 * size_t(n_)), o(n_);
         if (!dev.sync() || !dev.d2h(b.data(), dbase_, sizeof(int) * 3 * n_) || !dev.d2h(o.data(), downer_, sizeof(int) * n_)) { err = dev.err; return FG_ECUDA; }
@@ -952,6 +952,11 @@ private:
         return z < 0 ? z + nzg_ : z;
     }
     int slab_of(int z) const { const int zg = slab_plane(z); return zg < 0 ? -1 : zg / nzl_; }
+    int owner_of(int k0) const {        // IbIndexMark's owner: the slab of the stencil's second plane, clamped into the box
+        int kc = slab_plane(k0 + 1);
+        if (kc < 0) kc = k0 + 1 < 0 ? 0 : nzg_ - 1;
+        return kc / nzl_;
+    }
     int cap_pad_ = 0, n_total_ = 0, nzl_ = 1, nzg_ = 1;
     std::vector<int> act_;
     std::vector<float> hX_;

@@ -358,3 +358,81 @@ def test_random_fish_emulated_kernels_vs_oracle(g, emu):
 def test_random_moving_markers_and_fish_cuda_vs_oracle(g, cuda):
     check_moving(g, cuda, range(2000, 2080))
     check_fish(g, cuda, range(2000, 2012))
+
+
+def run_bodies_across_slabs_case(g, emu, seed):
+    """fg_peer_connect_all on 2-4 slabs (ranks stepped from threads): drifting marker clouds that straddle faces, wrap
+    around a periodic z axis or leave a non-periodic box, against the unsplit run.  Its first run found that a marker
+    whose stencil lies entirely outside the box was culled on every rank and dropped out of its link's wrench."""
+    import test_slabs
+    P, Wl, IN, OUT = g.BC_PERIODIC, g.BC_WALL, g.BC_INLET, g.BC_OUTLET
+    A = g._abi
+    rng = np.random.default_rng(seed)
+    n_ranks, h = int(rng.integers(2, 5)), int(rng.integers(4, 10))
+    nx, ny, nz = int(rng.integers(6, 16)), int(rng.integers(6, 14)), h * n_ranks
+    zlo, zhi = [(P, P), (P, P), (Wl, Wl), (IN, OUT)][int(rng.integers(0, 4))]
+    bc = [P, P, P, P, zlo, zhi]
+    if rng.random() < 0.4:
+        bc[0] = bc[1] = Wl
+    if rng.random() < 0.4:
+        bc[2] = bc[3] = Wl
+    kw = dict(nx=nx, ny=ny, nz=nz, tau=float(rng.uniform(0.6, 1.2)), collision=int(rng.integers(0, 2)), bc=bc, max_markers=600,
+              max_links=4, body_force=[0, 0, float(rng.uniform(0, 3e-5))], inlet_u=[0, 0, 0.02], flags=0)
+    for flag in (A.FLAG_NO_OVERLAP, A.FLAG_NO_SPLIT):
+        if rng.random() < 0.3:
+            kw["flags"] |= flag
+    if rng.random() < 0.6:
+        kw["split_min_cells"] = 1
+    whole = g.Sim(backend=emu, **kw)
+    parts = [g.Sim(backend=emu, n_ranks=n_ranks, rank=r, **kw) for r in range(n_ranks)]
+    rho, u = util.smooth_fields(whole.shape, amp=0.01)
+    whole.set_fields(rho, u)
+    handles = [s.peer_export() for s in parts]
+    for r, s in enumerate(parts):
+        s.set_fields(rho[r * h:(r + 1) * h], u[:, r * h:(r + 1) * h])
+        s.peer_connect_all(handles)
+    clouds = []
+    for _ in range(int(rng.integers(1, 4))):
+        c = np.array([rng.uniform(3, nx - 3), rng.uniform(3, ny - 3), rng.uniform(0, nz)])
+        clouds.append([util.sphere_markers(c, float(rng.uniform(1.0, 3.0)), int(rng.integers(1, 80))), c, rng.uniform(-0.6, 0.6, 3) * [0.3, 0.3, 2.0]])
+    worst = dict(f=0.0, wrench=0.0)
+    for it in range(6):
+        if it == 0 or rng.random() < 0.7:
+            for cl in clouds:
+                cl[0], cl[1] = (cl[0] + cl[2]).astype(np.float32), cl[1] + cl[2]
+            X = np.concatenate([cl[0] for cl in clouds])
+            link = np.concatenate([np.full(len(cl[0]), i, np.int32) for i, cl in enumerate(clouds)])
+            U = np.concatenate([np.tile((cl[2] * 0.02).astype(np.float32), (len(cl[0]), 1)) for cl in clouds])
+            for s in [whole] + parts:
+                s.set_markers(X, U, np.ones(len(X), np.float32), link)
+                s.set_link_origins([list(cl[1]) for cl in clouds])
+        k = int(rng.integers(1, 4))
+        whole.step(k)
+        test_slabs._run_threads([lambda s=s: s.step(k) for s in parts])
+        if not stable(whole.get_fields(f64=True)[0]):
+            worst = None
+            break
+        f, fs = whole.get_populations(), np.concatenate([s.get_populations() for s in parts], axis=1)
+        worst["f"] = max(worst["f"], float(np.abs(f - fs).max()))
+        w = whole.get_link_wrenches()
+        for s in parts:
+            ws = s.get_link_wrenches()
+            worst["wrench"] = max(worst["wrench"], float(np.abs(ws - w).max() / max(np.abs(w).max(), 1e-3)))
+            assert np.array_equal(ws, parts[0].get_link_wrenches())          # replicated integrators need identical bits
+        assert np.array_equal(whole.get_index_map()[0], parts[0].get_index_map()[0])
+    for s in [whole] + parts:
+        s.close()
+    return worst, kw, n_ranks
+
+
+def test_random_bodies_across_slab_faces_equal_unsplit(g, emu):
+    bad, ran = [], 0
+    for seed in range(100):
+        worst, kw, n_ranks = run_bodies_across_slabs_case(g, emu, seed)
+        if worst is None:
+            continue
+        ran += 1
+        if worst["f"] > 1e-6 or worst["wrench"] > 1e-4:
+            bad.append((seed, worst, n_ranks, kw))
+    assert not bad, bad[:3]
+    assert ran >= 80
