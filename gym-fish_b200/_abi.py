@@ -234,7 +234,10 @@ class Sim:
         self.nz = self.cfg.nz // self.cfg.n_ranks   # local slab height
         self.shape = (self.nz, self.ny, self.nx)
         self._counts = (0, 0)
-        self._wrench_buf = np.zeros((1, 6), dtype=np.float64)
+        self._counts_stale = False
+        # link wrenches come back into a buffer of FULL capacity: the library writes n_links rows, and n_links can grow
+        # without the marker count changing (same markers, higher link ids)
+        self._wrench_buf = np.zeros((max(self.cfg.max_links, 1), 6), dtype=np.float64)
 
     # -- plumbing --
     def _ck(self, rc: int):
@@ -316,6 +319,8 @@ class Sim:
                                          None if link_id is None else link_id.ctypes.data))
         if n != self._counts[0]:
             self._refresh_counts()
+        else:
+            self._counts_stale = True       # the link count may have changed: looked up again when a read-out needs it
 
     def set_link_origins(self, origins):
         o = np.ascontiguousarray(origins, dtype=np.float64).reshape(-1, 3)
@@ -325,7 +330,7 @@ class Sim:
     def _refresh_counts(self):
         st = self.stats()
         self._counts = (st.n_markers, st.n_links)
-        self._wrench_buf = np.zeros((max(st.n_links, 1), 6), dtype=np.float64)
+        self._counts_stale = False
 
     def stats(self) -> FgStats:
         st = FgStats()
@@ -351,6 +356,8 @@ class Sim:
 
     def get_link_wrenches(self) -> np.ndarray:
         """[n_links][6] hydrodynamic (force, torque) on each link; returns a view of a reused buffer."""
+        if self._counts_stale:
+            self._refresh_counts()
         self._ck(self.lib.fg_get_link_wrenches(self.h, self._wrench_buf))
         return self._wrench_buf[: self._counts[1]]
 

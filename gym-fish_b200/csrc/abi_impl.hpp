@@ -149,6 +149,10 @@ int fg_get_link_wrenches(FgSim *s, double *w6) {
     if (!s || !w6) return FG_EINVAL;
     FG_TRY
     if (!s->sim.ib().ready()) return FG_OK;
+    if (!s->sim.ib().forces_valid()) {       // markers were (re)set and no step has run since: nothing to report yet
+        std::fill(w6, w6 + 6 * size_t(s->sim.ib().n_links()), 0.0);
+        return FG_OK;
+    }
     if (int rc = s->sim.ib().fetch_wrenches(s->sim.dev, s->sim.err)) return rc;
     std::memcpy(w6, s->sim.ib().wrench_ptr(), sizeof(double) * 6 * s->sim.ib().n_links());
     return FG_OK;

@@ -647,6 +647,7 @@ public:
         }
         z_any_ = kmin <= kmax;
         z_all_ = z_any_ && per_[2] && (kmin < 0 || kmax >= nzg_);
+        if (!z_any_) { zmin_ = 1; zmax_ = 0; return; }        // no stencil on this slab
         zmin_ = std::max(kmin, z0) - z0 + 1;
         zmax_ = std::min(kmax, z0 + nzl_ - 1) - z0 + 1;
     }
@@ -875,8 +876,16 @@ public:
     }
 
     // read-outs for tests and observations
+    // Per-marker read-outs and link wrenches describe the LAST STEP's immersed-boundary pass.  Between fg_set_markers and
+    // the next fg_step there is none for the new marker set: everything reads as zero (the oracle does the same).
+    bool forces_valid() const { return forces_valid_; }
     int get_index_map(Dev &dev, int32_t *base3, int32_t *owner, std::string &err) {
         if (n_markers() == 0) return FG_OK;
+        if (!forces_valid_) {
+            std::fill(base3, base3 + 3 * size_t(n_markers()), 0);
+            std::fill(owner, owner + size_t(n_markers()), 0);
+            return FG_OK;
+        }
         if (!xchg_) {
             if (!dev.sync() || !dev.d2h(base3, dbase_, sizeof(int) * 3 * n_) || !dev.d2h(owner, downer_, sizeof(int) * n_)) { err = dev.err; return FG_ECUDA; }
             return FG_OK;
@@ -897,6 +906,7 @@ public:
     }
     int get_marker_array(Dev &dev, bool forces, float *out, std::string &err) {
         if (n_markers() == 0) return FG_OK;
+        if (!forces_valid_) { std::fill(out, out + 3 * size_t(n_markers()), 0.f); return FG_OK; }
         if (!xchg_) {
             if (!dev.sync() || !dev.d2h(out, forces ? dF_ : dUs_, sizeof(float) * 3 * n_)) { err = dev.err; return FG_ECUDA; }
             return FG_OK;

@@ -766,6 +766,22 @@ struct GatherArriving {
     }
 };
 
+// natural layout <- gathered populations (the inverse read-out): with GatherArriving<1> before it this completes the
+// streaming an even step has left pending, WITHOUT a collision — what fg_set_solid needs before the obstacle mask may change
+struct ScatterNatural {
+    static constexpr int kThreads = 128;
+    static constexpr int kMinBlocks = 4;
+    FG_HD static void run(const GatherParams &p, int bx, int by, int bz, int tx) {
+        const Lattice &L = p.L;
+        const int x = bx * kThreads + tx, y = by, zz = bz + 1;
+        if (x >= L.nx) return;
+        const long long idx = ((long long)zz * L.ny + y) * L.nx + x;
+        const long long l = ((long long)(zz - 1) * L.ny + y) * L.nx + x, n = (long long)L.nz * L.plane;
+        FG_UNROLL
+        for (int i = 0; i < Q; ++i) pop_st(L.f + i * L.slot + idx, p.out19[i * n + l]);
+    }
+};
+
 // ---------------------------------------------------------------- z-face plane operations (a10)
 // After every step the 5 populations crossing each z face are moved between boundary / ghost planes
 // (SURVEY.md A8 "slot subtlety for halos").  `dst` may be this rank's own lattice (periodic wrap on one GPU),

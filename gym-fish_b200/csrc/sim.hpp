@@ -167,8 +167,30 @@ public:
         return FG_OK;
     }
 
+    // After an even step the streaming of that step is still pending (the next odd step performs it while reading, with
+    // the bounce-back links of the mask it sees THEN).  Whatever changes the mask must therefore first complete the
+    // streaming with the old one: gather the arriving populations and store them back in natural layout (parity 0).
+    int finish_pending_streaming() {
+        if (parity_ == 0) return FG_OK;
+        if (cfg.n_ranks > 1 && !peers_ && pending_faces_ > 0)
+            return fail(FG_ESTATE, "halo exchange incomplete: unpack every internal face after fg_step");
+        // on peered slabs the ghost planes must hold the neighbours' halos of the last step (all ranks call this in step)
+        if (peers_ && !dev.wait_flags(flags_, has_lo_peer(), has_hi_peer())) return cuda_fail();
+        const size_t n = size_t(L_.plane) * L_.nz;
+        float *d = static_cast<float *>(dev.alloc(size_t(Q) * n * sizeof(float), err));
+        if (!d) return FG_ENOMEM;
+        GatherParams p{L_, C_, d, nullptr};
+        const bool ok = dev.template launch<GatherArriving<1>>(grid_planes(L_.nz), p) &&
+                        dev.template launch<ScatterNatural>(grid_planes(L_.nz), p) && dev.sync();
+        dev.free(d);
+        if (!ok) return cuda_fail();
+        parity_ = 0;
+        return FG_OK;
+    }
+
     int set_solid(const uint8_t *g) {
         dev.graph_clear();
+        if (int rc = finish_pending_streaming()) return rc;
         if (!g) {
             dev.free(solid_); solid_ = nullptr; L_.solid = nullptr;
             return FG_OK;

@@ -148,7 +148,9 @@ int fg_set_populations(FgSim *sim, const float *f19);
 int fg_get_populations(FgSim *sim, float *f19);
 int fg_set_solid(FgSim *sim, const uint8_t *solid_global);            /* [nz_global][ny][nx], 1 = solid; NULL clears */
 
-/* ---- immersed boundary: Lagrangian markers (prescribed, or generated by fish bodies) ---- */
+/* ---- immersed boundary: Lagrangian markers (prescribed, or generated by fish bodies) ----
+ * The read-outs below describe the immersed-boundary pass of the LAST step.  Between fg_set_markers and the next fg_step
+ * there is none for the new marker set: index map, marker forces / velocities and link wrenches read as zero. */
 int fg_set_markers(FgSim *sim, int32_t n, const float *X, const float *U,
                    const float *dV, const int32_t *link_id);          /* X,U: [n][3]; dV,link_id: [n] */
 int fg_set_link_origins(FgSim *sim, int32_t n_links, const double *origin3); /* torque reference points */

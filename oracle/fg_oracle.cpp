@@ -121,7 +121,7 @@ struct FgSim {
     double omega = 1.25;
     double feq_in[Q]{};
     // immersed boundary
-    int n_markers = 0, n_links = 0;
+    int n_markers = 0, n_links = 0, n_origins = 0;
     std::vector<float> mX, mU, mdV;
     std::vector<int32_t> mlink;
     std::vector<int32_t> mbase, mowner;
@@ -617,18 +617,23 @@ int fg_set_markers(FgSim *s, int32_t n, const float *X, const float *U, const fl
     if (n > s->cfg.max_markers) return fail(s, FG_EINVAL, "more markers than FgConfig.max_markers");
     if (!s->fish.empty()) return fail(s, FG_ESTATE, "markers are generated by fish bodies on this handle");
     if (s->cfg.n_ranks > 1 && n > 0) return fail(s, FG_ENOTSUP, "oracle: immersed boundary with n_ranks > 1 is not supported");
+    // validate everything before touching the state: a rejected call leaves the previous marker set in place
+    int nl = n > 0 ? 1 : 0;
+    if (link)
+        for (int k = 0; k < n; ++k) nl = std::max(nl, link[k] + 1);
+    const int maxl = std::max(s->cfg.max_links, 1);
+    if (nl > maxl) return fail(s, FG_EINVAL, "link id exceeds FgConfig.max_links");
     ensure_ib_storage(s);
     s->n_markers = n;
     s->mX.assign(X, X + 3 * size_t(n));
     s->mU.assign(U, U + 3 * size_t(n));
     s->mdV.assign(dV, dV + n);
     if (link) s->mlink.assign(link, link + n); else s->mlink.assign(n, 0);
-    int nl = 0;
-    for (int k = 0; k < n; ++k) nl = std::max(nl, s->mlink[k] + 1);
-    if (nl > std::max(s->cfg.max_links, 1)) return fail(s, FG_EINVAL, "link id exceeds FgConfig.max_links");
-    if (nl > s->n_links || size_t(3 * nl) > s->link_origin.size()) s->link_origin.resize(3 * size_t(nl), 0.0);
-    s->n_links = nl;
-    s->wrench.assign(6 * size_t(nl), 0.0);
+    // torque reference points live in a table of max_links entries (as in the CUDA library): links without an
+    // explicit origin refer to (0,0,0), and the link count never drops below what fg_set_link_origins announced
+    s->link_origin.resize(3 * size_t(maxl), 0.0);
+    s->n_links = std::max(nl, s->n_origins);
+    s->wrench.assign(6 * size_t(s->n_links), 0.0);
     s->mbase.assign(3 * size_t(n), 0); s->mowner.assign(n, 0);
     s->mF.assign(3 * size_t(n), 0.0); s->mUstar.assign(3 * size_t(n), 0.0);
     return FG_OK;
@@ -636,8 +641,11 @@ int fg_set_markers(FgSim *s, int32_t n, const float *X, const float *U, const fl
 
 int fg_set_link_origins(FgSim *s, int32_t n_links, const double *o) {
     if (!s || n_links < 0 || (n_links && !o)) return FG_EINVAL;
-    if (n_links > std::max(s->cfg.max_links, 1)) return fail(s, FG_EINVAL, "more links than FgConfig.max_links");
-    s->link_origin.assign(o, o + 3 * size_t(n_links));
+    const int maxl = std::max(s->cfg.max_links, 1);
+    if (n_links > maxl) return fail(s, FG_EINVAL, "more links than FgConfig.max_links");
+    s->link_origin.resize(3 * size_t(maxl), 0.0);
+    std::copy(o, o + 3 * size_t(n_links), s->link_origin.begin());      // entries beyond n_links keep their values
+    s->n_origins = n_links;
     if (n_links > s->n_links) { s->n_links = n_links; s->wrench.resize(6 * size_t(n_links), 0.0); }
     return FG_OK;
 }

@@ -436,3 +436,135 @@ def test_random_bodies_across_slab_faces_equal_unsplit(g, emu):
             bad.append((seed, worst, n_ranks, kw))
     assert not bad, bad[:3]
     assert ran >= 80
+
+
+def run_api_sequence_case(g, backend, seed):
+    """A random SEQUENCE of ABI calls, valid and invalid (too many markers, link ids beyond max_links, obstacles changed
+    after an even or an odd step, read-outs before the first step, resets, zero-substep steps), issued to the oracle and to
+    the product's host code: every call must have the same outcome (ok, or the same error code) on both, and every read-out
+    must agree.  First run: a crash in the oracle (state touched before validation), a heap overflow in the Python binding
+    (wrench buffer sized from a stale link count), and fg_set_solid after an even step changing the streaming of that step."""
+    A = g._abi
+    rng = np.random.default_rng(seed)
+    kw, _, _ = random_case(g, rng)
+    kw["nx"], kw["ny"], kw["nz"] = (max(kw["nx"], 4) if kw["nx"] < 100 else kw["nx"]), max(kw["ny"], 4), max(kw["nz"], 4)
+    kw.update(max_markers=40, max_links=3)
+    nx, ny, nz = kw["nx"], kw["ny"], kw["nz"]
+    sims = [g.Sim(backend="oracle", **kw), g.Sim(backend=backend, **kw)]
+    solid, worst, log = None, 0.0, []
+
+    def both(fn, name):
+        res = []
+        for s in sims:
+            try:
+                res.append(("ok", fn(s)))
+            except g.FgError as e:
+                res.append(("err", e.code))
+        log.append((name, res[0][0], res[1][0]))
+        assert res[0][0] == res[1][0] and (res[0][0] == "ok" or res[0][1] == res[1][1]), (seed, name, res, log[-6:])
+        return res[0][0] == "ok", res[0][1], res[1][1]
+
+    try:
+        for _ in range(14):
+            op = int(rng.integers(0, 11))
+            if op == 0:
+                rho, u = util.smooth_fields((nz, ny, nx))
+                rho = (rho + 0.002 * rng.standard_normal(rho.shape)).astype(np.float32)
+                both(lambda s: s.set_fields(rho, u.astype(np.float32)), "set_fields")
+            elif op == 1:
+                n = int(rng.integers(0, 50))                                   # sometimes more than max_markers
+                X = (rng.uniform(-0.2, 1.2, (n, 3)) * [nx, ny, nz]).astype(np.float32)
+                U = rng.uniform(-0.02, 0.02, (n, 3)).astype(np.float32)
+                link = rng.integers(0, int(rng.integers(1, 5)), n).astype(np.int32)   # sometimes a link id >= max_links
+                both(lambda s: s.set_markers(X, U, rng.uniform(0.2, 1, n).astype(np.float32) * 0 + 0.5, link), "set_markers")
+            elif op == 2:
+                o = rng.uniform(0, 10, (int(rng.integers(1, 5)), 3))          # sometimes more than max_links
+                both(lambda s: s.set_link_origins(o), "set_link_origins")
+            elif op == 3:
+                k = int(rng.integers(0, 4))
+                both(lambda s: s.step(k), "step")
+            elif op == 4:
+                both(lambda s: s.reset(0), "reset")
+            elif op == 5:
+                solid = (rng.random((nz, ny, nx)) < 0.05).astype(np.uint8) if rng.random() < 0.7 else None
+                both(lambda s: s.set_solid(solid), "set_solid")
+            elif op == 6:
+                f = (A.W[:, None, None, None] * (1 + 0.01 * rng.standard_normal((19, nz, ny, nx)))).astype(np.float32)
+                both(lambda s: s.set_populations(f), "set_populations")
+            elif op == 7:
+                ok, wa, wb = both(lambda s: s.get_link_wrenches().copy(), "get_link_wrenches")
+                assert not ok or wa.shape == wb.shape, (seed, wa.shape, wb.shape, log[-6:])
+                if ok and wa.size and np.abs(wa).max() < 1e3:
+                    worst = max(worst, float(np.abs(wa - wb).max() / max(np.abs(wa).max(), 1e-3)))
+            elif op == 8:
+                ok, fa, fb = both(lambda s: s.get_force_field(), "get_force_field")
+                if ok and np.isfinite(fa).all() and np.abs(fa).max() < 10:
+                    worst = max(worst, float(np.abs(fa - fb).max()))
+            elif op == 9:
+                pts = (rng.uniform(0, 1, (4, 3)) * [nx, ny, nz]).astype(np.float32)
+                both(lambda s: s.probe(pts), "probe")
+            else:
+                ok, (ra, ua), (rb, ub) = both(lambda s: s.get_fields(f64=True), "get_fields")
+                keep = 1 if solid is None else (solid == 0)
+                if not stable(ra, keep):
+                    return None
+                worst = max(worst, float(np.abs((ua - ub) * keep).max()))
+        return worst
+    finally:
+        for s in sims:
+            s.close()
+
+
+def test_random_api_sequences_same_outcome_on_both_backends(g, emu):
+    bad, ran = [], 0
+    for seed in range(300):
+        w = run_api_sequence_case(g, emu, seed)
+        if w is None:
+            continue
+        ran += 1
+        if w > 2e-5:
+            bad.append((seed, w))
+    assert not bad, bad[:5]
+    assert ran >= 250
+
+
+def test_link_count_can_grow_without_the_marker_count_changing(g, emu):
+    """Regression (found by the API fuzz under AddressSanitizer): the binding sized its wrench buffer from a link count it
+    only refreshed when the MARKER count changed."""
+    for backend in ("oracle", emu):
+        s = g.Sim(backend=backend, nx=12, ny=10, nz=12, max_markers=8, max_links=4)
+        X = util.sphere_markers((6, 5, 6), 2.0, 8)
+        U = np.full_like(X, 0.01)
+        s.set_markers(X, U, np.ones(8, np.float32), np.zeros(8, np.int32))
+        s.step(1)
+        assert s.get_link_wrenches().shape == (1, 6)
+        s.set_markers(X, U, np.ones(8, np.float32), np.arange(8, dtype=np.int32) % 4)      # same 8 markers, 4 links now
+        assert np.array_equal(s.get_link_wrenches(), np.zeros((4, 6)))                      # nothing stepped yet: zeros
+        s.step(1)
+        w = s.get_link_wrenches()
+        assert w.shape == (4, 6) and np.abs(w).min(axis=1).max() > 0
+        s.close()
+
+
+@pytest.mark.parametrize("steps_before", [1, 2])
+def test_obstacles_may_change_after_an_even_or_an_odd_step(g, emu, steps_before):
+    """fg_set_solid between steps: after an even AA step the streaming of that step is still pending and must be completed
+    with the OLD mask (sim.hpp finish_pending_streaming) — the oracle streams inside fg_step."""
+    P, Wl = g.BC_PERIODIC, g.BC_WALL
+    kw = dict(nx=10, ny=8, nz=9, tau=0.8, collision=g.MRT, bc=[P, P, Wl, Wl, P, P], body_force=[1e-4, 0, 2e-4])
+    a, b = g.Sim(backend="oracle", **kw), g.Sim(backend=emu, **kw)
+    rho, u = util.smooth_fields(a.shape)
+    rng = np.random.default_rng(11)
+    s1 = (rng.random(a.shape) < 0.1).astype(np.uint8)
+    s2 = (rng.random(a.shape) < 0.1).astype(np.uint8)
+    for s in (a, b):
+        s.set_solid(s1)
+        s.set_fields(rho, u)
+        s.step(steps_before)
+        s.set_solid(s2)
+        s.step(3)
+    keep = (s1 == 0) & (s2 == 0)
+    assert np.abs((a.get_populations() - b.get_populations()) * keep).max() < 2e-7
+    assert b.stats().parity == (3 if steps_before == 1 else 5) % 2       # the flush brought an odd parity back to even
+    a.close()
+    b.close()
