@@ -88,3 +88,17 @@ def test_f16_storage_sphere_channel_and_split_gpu(g, cuda_f16):
     (d32, _), (d16, sp) = out
     assert sp == 400
     assert abs(d16 - d32) / abs(d32) < 1e-2, (d16, d32)
+
+
+def test_random_configurations_with_16_bit_storage(g, emu_f16):
+    """The randomised cases of test_random_cases.py on the 16-bit-storage build: slabs still bit-identical to the unsplit
+    run (halo messages travel in the storage type), and the fields stay within the looser bounds of this build."""
+    import test_random_cases as t
+    assert all(t.run_slab_case(g, emu_f16, seed)[0] for seed in range(60))
+    limits = dict(u=2e-3, rho=2e-3, f=1e-3, index_map=0.5, band=0.5, Fm=5e-3, wrench=5e-2)
+    bad = []
+    for seed in range(150):
+        worst, kw = t.run_case(g, emu_f16, seed)
+        if worst is not None and any(worst[k] > limits[k] for k in worst):
+            bad.append((seed, worst, kw))
+    assert not bad, bad[:3]

@@ -568,3 +568,53 @@ def test_obstacles_may_change_after_an_even_or_an_odd_step(g, emu, steps_before)
     assert b.stats().parity == (3 if steps_before == 1 else 5) % 2       # the flush brought an odd parity back to even
     a.close()
     b.close()
+
+
+def test_random_fish_across_slab_faces(g, emu):
+    """A random free or pinned fish placed anywhere along z (so it usually straddles a slab face or the periodic wrap),
+    2-3 slabs stepped from threads: replicated host integrators bit-identical on every rank, observations and populations
+    equal to the unsplit run to round-off."""
+    import test_slabs
+    P, Wl = g.BC_PERIODIC, g.BC_WALL
+    bad, ran = [], 0
+    for seed in range(24):
+        rng = np.random.default_rng(seed)
+        n_ranks, h = int(rng.integers(2, 4)), int(rng.integers(14, 22))
+        nx, ny, nz = int(rng.integers(16, 24)), int(rng.integers(14, 20)), h * n_ranks
+        kw = dict(nx=nx, ny=ny, nz=nz, tau=float(rng.uniform(0.7, 1.0)), collision=int(rng.integers(0, 2)),
+                  bc=[Wl] * 4 + [P] * 2 if rng.random() < 0.5 else [P] * 6, max_markers=4000, max_links=8)
+        if rng.random() < 0.5:
+            kw["split_min_cells"] = 1
+        whole = g.Sim(backend=emu, **kw)
+        parts = [g.Sim(backend=emu, n_ranks=n_ranks, rank=r, **kw) for r in range(n_ranks)]
+        handles = [s.peer_export() for s in parts]
+        for s in parts:
+            s.peer_connect_all(handles)
+        links = tuple((float(rng.uniform(5, 8)), float(rng.uniform(1.5, 2.5))) for _ in range(int(rng.integers(2, 5))))
+        d = util.fish_desc(g, root=(nx / 2, ny / 2, float(rng.uniform(0, nz))), links=links, free=int(rng.random() < 0.7),
+                           heading=float(rng.uniform(-0.4, 0.4)))
+        for s in [whole] + parts:
+            s.add_fish(d)
+        worst, ok = 0.0, True
+        for _ in range(4):
+            act, k = rng.uniform(-1, 1, whole.action_size()).astype(np.float32), int(rng.integers(1, 7))
+            whole.set_action(act)
+            whole.step(k)
+            for s in parts:
+                s.set_action(act)
+            test_slabs._run_threads([lambda s=s: s.step(k) for s in parts])
+            ow, r0 = whole.get_obs(), whole.get_fields(f64=True)[0]
+            if not (np.isfinite(ow).all() and np.isfinite(r0).all() and 0.85 < r0.min() and r0.max() < 1.15):
+                ok = False
+                break
+            worst = max([worst] + [float(np.abs(s.get_obs() - ow).max()) for s in parts])
+            assert all(np.array_equal(parts[0].get_obs(), s.get_obs()) for s in parts), seed
+        if ok:
+            ran += 1
+            f, fs = whole.get_populations(), np.concatenate([s.get_populations() for s in parts], axis=1)
+            if worst > 1e-4 or np.abs(f - fs).max() > 1e-6:
+                bad.append((seed, worst, float(np.abs(f - fs).max()), kw))
+        for s in [whole] + parts:
+            s.close()
+    assert not bad, bad[:3]
+    assert ran >= 16
