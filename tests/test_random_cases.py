@@ -618,3 +618,11 @@ def test_random_fish_across_slab_faces(g, emu):
             s.close()
     assert not bad, bad[:3]
     assert ran >= 16
+
+
+@pytest.mark.gpu
+def test_random_api_sequences_cuda_vs_oracle(g, cuda):
+    """The same call sequences through the real library: CUDA graphs captured and replayed under changing marker sets,
+    obstacle masks, flags of the random case, resets and read-outs in any order."""
+    bad = [(seed, w) for seed in range(3000, 3120) for w in [run_api_sequence_case(g, cuda, seed)] if w is not None and w > 2e-5]
+    assert not bad, bad[:5]
