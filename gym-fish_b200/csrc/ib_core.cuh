@@ -669,14 +669,14 @@ public:
     // origins: nullptr keeps the current torque reference points
     int set_markers(Dev &dev, int n, const float *X, const float *U, const float *dV, const int32_t *link, const double *origins,
                     int n_origins, std::string &err, bool range_known = false) {
+        // validate first: a rejected call leaves the handle as it was
         if (n > cap_) { err = "more markers than FgConfig.max_markers"; return FG_EINVAL; }
-        if (!range_known) update_range(n, X);
         if (n_origins > maxl_) { err = "more links than FgConfig.max_links"; return FG_EINVAL; }
-        int nl = 0;
+        int nl = n > 0 ? 1 : 0;
         if (link)
             for (int k = 0; k < n; ++k) nl = std::max(nl, link[k] + 1);
-        else if (n > 0) nl = 1;
         if (nl > maxl_) { err = "link id exceeds FgConfig.max_links"; return FG_EINVAL; }
+        if (!range_known) update_range(n, X);
         if (origins) {
             for (int i = 0; i < 3 * n_origins; ++i) h_origin_[i] = origins[i];
             nl_origins_ = n_origins;
