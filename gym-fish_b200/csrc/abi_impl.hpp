@@ -42,7 +42,8 @@ int validate(const FgConfig *cfg) {
 }
 }  // namespace
 
-#define FG_TRY try {
+// every entry point makes the handle's device current ONCE; the device policy does not repeat it per operation
+#define FG_TRY try { s->sim.dev.enter();
 #define FG_CATCH(s)                                                                   \
     }                                                                                 \
     catch (const std::bad_alloc &) { (s)->sim.err = "host out of memory"; return FG_ENOMEM; } \
@@ -196,6 +197,7 @@ int fg_step(FgSim *s, int32_t n) {
 }
 int fg_sync(FgSim *s) {
     if (!s) return FG_EINVAL;
+    s->sim.dev.enter();
     if (!s->sim.dev.sync()) return s->sim.cuda_fail();
     return s->sim.check_peer_timeout();
 }
@@ -207,6 +209,7 @@ int fg_get_stats(FgSim *s, FgStats *o) {
 int fg_set_flags(FgSim *s, int32_t flags) {
     if (!s) return FG_EINVAL;
     s->sim.cfg.flags = flags;
+    s->sim.dev.enter();
     s->sim.dev.graph_clear();
     return FG_OK;
 }

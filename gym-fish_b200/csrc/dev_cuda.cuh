@@ -172,8 +172,11 @@ public:
         for (auto &e : named_) { if (e) cudaEventDestroy(e); e = nullptr; }
     }
 
+    // Every extern "C" entry point calls enter() once (abi_impl.hpp FG_TRY): the methods below assume the handle's device
+    // is current on the calling thread and do not set it again (33 cudaSetDevice calls per step before).
+    void enter() { if (device_ >= 0) cudaSetDevice(device_); }
+
     void *alloc(size_t bytes, std::string &e) {
-        cudaSetDevice(device_);
         void *p = nullptr;
         cudaError_t rc = cudaMalloc(&p, bytes ? bytes : 4);
         if (rc != cudaSuccess) {
@@ -185,29 +188,23 @@ public:
     }
     void free(void *p) {
         if (!p) return;
-        cudaSetDevice(device_);
         cudaFree(p);
     }
     bool h2d(void *d, const void *s, size_t n) {
-        cudaSetDevice(device_);
         return ck(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, stream_), "H2D") && ck(cudaStreamSynchronize(stream_), "H2D sync");
     }
     bool d2h(void *d, const void *s, size_t n) {
-        cudaSetDevice(device_);
         return ck(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, stream_), "D2H") && ck(cudaStreamSynchronize(stream_), "D2H sync");
     }
     bool zero(void *d, size_t n) {
-        cudaSetDevice(device_);
         if (gmode_ == 2) return true;   // replaying: the memset is a node of the graph
         return ck(cudaMemsetAsync(d, 0, n, stream_), "memset");
     }
     bool sync() {
-        cudaSetDevice(device_);
         return ck(cudaStreamSynchronize(stream_), "stream sync");
     }
     // pinned host memory + asynchronous copies on the handle's stream + a few named events (IbState)
     void *alloc_host(size_t bytes, std::string &e) {
-        cudaSetDevice(device_);
         void *p = nullptr;
         cudaError_t rc = cudaMallocHost(&p, bytes ? bytes : 4);
         if (rc != cudaSuccess) {
@@ -219,21 +216,17 @@ public:
     }
     void free_host(void *p) {
         if (!p) return;
-        cudaSetDevice(device_);
         cudaFreeHost(p);
     }
     bool h2d_async(void *d, const void *pinned, size_t n) {
-        cudaSetDevice(device_);
         if (gmode_ == 2) return true;
         return ck(cudaMemcpyAsync(d, pinned, n, cudaMemcpyHostToDevice, stream_), "H2D async");
     }
     bool d2h_async(void *pinned, const void *s, size_t n) {
-        cudaSetDevice(device_);
         if (gmode_ == 2) return true;
         return ck(cudaMemcpyAsync(pinned, s, n, cudaMemcpyDeviceToHost, stream_), "D2H async");
     }
     bool ev_record(int id) {
-        cudaSetDevice(device_);
         if (id < 0 || id >= kNamedEvents) return false;
         if (!named_[id] && !ck(cudaEventCreateWithFlags(&named_[id], cudaEventDisableTiming), "cudaEventCreate")) return false;
         if (gmode_ == 2) return true;
@@ -248,7 +241,6 @@ public:
     // Timing of one fg_step call: two event pairs used alternately, so that a call can record its own pair while the
     // previous call (which returned before its collide finished) still owns the other one.
     void tic() {
-        cudaSetDevice(device_);
         tpair_ ^= 1;
         cudaEventRecord(tev_[tpair_][0], stream_);
     }
@@ -256,7 +248,6 @@ public:
     // elapsed ms of the latest recorded pair; wait == false: only if it has completed (ok tells)
     double toc_elapsed(bool wait, bool &ok) {
         ok = false;
-        cudaSetDevice(device_);
         cudaEvent_t e1 = tev_[tpair_][1];
         if (wait) { if (cudaEventSynchronize(e1) != cudaSuccess) return 0.0; }
         else if (cudaEventQuery(e1) != cudaSuccess) { cudaGetLastError(); return 0.0; }
@@ -270,7 +261,6 @@ public:
     // consecutive mark(c) calls open / close an interval on the launching stream
     void marks_reset() { nmarks_[0] = nmarks_[1] = 0; }
     void mark(int c) {
-        cudaSetDevice(device_);
         auto &pool = marks_[c];
         if (nmarks_[c] >= kMaxMarks) return;   // long runs: the first kMaxMarks/2 intervals are a fair sample
         if (int(pool.size()) <= nmarks_[c]) {
@@ -292,7 +282,6 @@ public:
 
     template <class K, class P>
     bool launch(Dim3 g, const P &p) {
-        cudaSetDevice(device_);
         ++launches;
         if (gmode_ == 2) return true;   // replaying a captured substep
         return launch_on_current(kern<K, P>, dim3(g.x, g.y, g.z), K::kThreads, p);
@@ -320,19 +309,16 @@ public:
         const int from = cur_;
         cur_ = s;
         if (gmode_ == 2) return true;
-        cudaSetDevice(device_);
         return ck(cudaEventRecord(fork_ev_[s], s_[from]), "fork record") && ck(cudaStreamWaitEvent(s_[s], fork_ev_[s], 0), "fork wait");
     }
     bool switch_to(int s) { cur_ = s; return true; }
     bool join_from(int s) {
         if (gmode_ == 2) return true;
-        cudaSetDevice(device_);
         return ck(cudaEventRecord(join_ev_[s], s_[s]), "join record") && ck(cudaStreamWaitEvent(s_[cur_], join_ev_[s], 0), "join wait");
     }
 
     template <class K, class P>
     bool launch_block_phased(Dim3 g, const P &p) {
-        cudaSetDevice(device_);
         ++launches;
         if (gmode_ == 2) return true;
         return launch_on_current(kern_bp<K, P>, dim3(g.x, g.y, g.z), K::kThreads, p);
@@ -340,7 +326,6 @@ public:
     // g = (x-blocks, rows, planes) of ONE phase; the launch holds K::kGridPhases times as many CTAs in one dimension
     template <class K, class P>
     bool launch_ticketed(Dim3 g, const P &p) {
-        cudaSetDevice(device_);
         ++launches;
         if (gmode_ == 2) return true;
         const long long n = (long long)g.x * g.y * g.z * K::kGridPhases;
@@ -348,14 +333,12 @@ public:
         return launch_on_current(kern_ticket<K, P>, dim3(unsigned(n)), K::kThreads, p);
     }
     bool zero_on_current(void *d, size_t n) {
-        cudaSetDevice(device_);
         if (gmode_ == 2) return true;
         return ck(cudaMemsetAsync(d, 0, n, s_[cur_]), "memset");
     }
     bool supports_phased() const { return coop_; }
     template <class K, class P>
     bool launch_phased(long long max_items, const P &p) {
-        cudaSetDevice(device_);
         ++launches;
         if (gmode_ == 2) return true;
         static thread_local int per_sm = 0;      // per kernel instantiation
@@ -374,7 +357,6 @@ public:
     // ---- z-neighbour lattices: same process => raw pointer (+ peer access); other process => CUDA IPC
     template <class Blob>
     bool export_peer(pop_t *f, int *flags, void *x, Blob &b, std::string &e) {
-        cudaSetDevice(device_);
         b.pid = int(getpid()); b.device = device_;
         b.f_ptr = reinterpret_cast<uint64_t>(f); b.flag_ptr = reinterpret_cast<uint64_t>(flags); b.x_ptr = reinterpret_cast<uint64_t>(x);
         cudaIpcMemHandle_t h1, h2, h3;
@@ -391,7 +373,6 @@ public:
         return true;
     }
     bool signal_counters(int *mine, int *const *targets, int n, bool bump) {
-        cudaSetDevice(device_);
         ++launches;
         if (gmode_ == 2) return true;
         CounterList t{};
@@ -400,7 +381,6 @@ public:
         return ck(cudaGetLastError(), "signal launch");
     }
     bool wait_counters(int *mine, int *const *sources, int n) {
-        cudaSetDevice(device_);
         ++launches;
         if (gmode_ == 2) return true;
         CounterList s{};
@@ -410,7 +390,6 @@ public:
     }
     template <class Blob>
     bool open_peer(const Blob &b, pop_t **f, int **flags, void **x, std::string &e) {
-        cudaSetDevice(device_);
         if (b.pid == int(getpid())) {
             if (b.device != device_) {
                 int can = 0;
@@ -435,12 +414,10 @@ public:
     }
     void close_peers() {
         if (device_ < 0) return;
-        cudaSetDevice(device_);
         for (auto &o : opened_) cudaIpcCloseMemHandle(o.second);
         opened_.clear();
     }
     bool signal_flags(int *mine, int *lo, int *hi) {
-        cudaSetDevice(device_);
         ++launches;
         if (gmode_ == 2) return true;
         signal_kernel<<<1, 1, 0, stream_>>>(mine, lo, hi);
@@ -448,7 +425,6 @@ public:
     }
     bool wait_flags(int *flags, bool lo, bool hi) {
         if (!lo && !hi) return true;
-        cudaSetDevice(device_);
         ++launches;
         if (gmode_ == 2) return true;
         wait_kernel<<<1, 1, 0, stream_>>>(flags, lo, hi, peer_timeout_ns_, timeout_word_);
@@ -458,7 +434,6 @@ public:
     // ---- per-substep CUDA graphs: capture the stream once per key, replay afterwards.  While replaying (gmode_ 2)
     // launches and async copies are not enqueued — the caller's host code still runs and keeps its state in step.
     bool graph_begin(const GraphKey &key) {
-        cudaSetDevice(device_);
         auto it = graphs_.find(key);
         if (it != graphs_.end()) { gmode_ = 2; gexec_ = it->second; return true; }
         if (graphs_.size() >= 64) graph_clear();
@@ -467,7 +442,6 @@ public:
         return true;
     }
     bool graph_end() {
-        cudaSetDevice(device_);
         if (gmode_ == 1) {
             gmode_ = 0;
             cudaGraph_t g = nullptr;
@@ -497,7 +471,6 @@ public:
     }
     void graph_clear() {
         if (device_ < 0) return;
-        cudaSetDevice(device_);
         if (stream_) cudaStreamSynchronize(stream_);
         for (auto &kv : graphs_) cudaGraphExecDestroy(kv.second);
         graphs_.clear();

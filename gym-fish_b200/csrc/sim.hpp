@@ -73,6 +73,7 @@ public:
     }
 
     void destroy() {
+        dev.enter();
         ib_.destroy(dev);
         dev.close_peers();
         dev.free(L_.f); L_.f = nullptr;

@@ -23,6 +23,7 @@ public:
     int wait_ms = 300;   // how long a slab waits for its neighbour's halo before reporting it is behind
 
     bool init(int, std::string &) { return true; }
+    void enter() {}
     void shutdown() {}
     void *alloc(size_t bytes, std::string &e) {
         void *p = std::malloc(bytes ? bytes : 1);
