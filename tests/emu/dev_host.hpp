@@ -6,6 +6,9 @@
 #pragma once
 #include <atomic>
 #include <chrono>
+#include <deque>
+#include <functional>
+#include <memory>
 #include <thread>
 #include <cstdlib>
 #include <cstring>
@@ -22,77 +25,110 @@ public:
     long long launches = 0;
     int wait_ms = 300;   // how long a slab waits for its neighbour's halo before reporting it is behind
 
-    bool init(int, std::string &) { return true; }
+    // ---- streams.  Default (FG_EMU_SCHED unset): every operation runs at once, in submission order.
+    // FG_EMU_SCHED=low | high | rand:<seed>: operations are QUEUED per stream like on the GPU (launches on the current
+    // stream; copies, memsets, event records, neighbour waits / signals on stream 0) and executed only when the host
+    // waits for something — in an order that respects nothing but the recorded event dependencies, preferring the lowest
+    // / highest / a random runnable stream.  A missing fork / join between two launches that touch the same data then
+    // shows up as a result that depends on the policy (tests/test_stream_order.py); work left on a side stream at a
+    // synchronisation is reported as an error.  Nothing stays queued across ABI calls (toc_record drains).
+    static constexpr int kStreams = 6;
+    bool init(int, std::string &) {
+        if (const char *e = std::getenv("FG_EMU_SCHED")) {
+            const std::string v(e);
+            if (v == "low") sched_ = 1;
+            else if (v == "high") sched_ = 2;
+            else if (v.rfind("rand", 0) == 0) { sched_ = 3; rng_ = v.size() > 5 ? std::strtoull(v.c_str() + 5, nullptr, 10) * 2654435761ull + 1 : 12345; }
+        }
+        return true;
+    }
     void enter() {}
-    void shutdown() {}
+    void shutdown() { drain_all(); }
     void *alloc(size_t bytes, std::string &e) {
         void *p = std::malloc(bytes ? bytes : 1);
         if (!p) e = "host emulation: malloc failed";
         return p;
     }
-    void free(void *p) { std::free(p); }
-    bool h2d(void *d, const void *s, size_t n) { std::memcpy(d, s, n); return true; }
-    bool d2h(void *d, const void *s, size_t n) { std::memcpy(d, s, n); return true; }
-    bool zero(void *d, size_t n) { std::memset(d, 0, n); return true; }
-    bool sync() { return true; }
+    void free(void *p) { if (p) drain_all(); std::free(p); }       // cudaFree synchronises the device
+    bool h2d(void *d, const void *s, size_t n) { if (!drain_stream0()) return false; std::memcpy(d, s, n); return true; }
+    bool d2h(void *d, const void *s, size_t n) { if (!drain_stream0()) return false; std::memcpy(d, s, n); return true; }
+    bool zero(void *d, size_t n) { return submit(0, [=] { std::memset(d, 0, n); return true; }); }
+    bool sync() {
+        if (!drain_stream0()) return false;
+        for (int s = 1; s < kStreams; ++s)
+            if (!q_[s].empty()) { err = "host emulation: work on stream " + std::to_string(s) + " was never joined into stream 0 before a synchronisation"; return false; }
+        return !failed_;
+    }
     void *alloc_host(size_t bytes, std::string &e) { return alloc(bytes, e); }
-    void free_host(void *p) { std::free(p); }
-    bool h2d_async(void *d, const void *s, size_t n) { return h2d(d, s, n); }
-    bool d2h_async(void *d, const void *s, size_t n) { return d2h(d, s, n); }
-    bool ev_record(int) { return true; }
-    bool ev_sync(int) { return true; }
+    void free_host(void *p) { if (p) drain_all(); std::free(p); }
+    bool h2d_async(void *d, const void *s, size_t n) { return submit(0, [=] { std::memcpy(d, s, n); return true; }); }   // reads the pinned buffer when it RUNS
+    bool d2h_async(void *d, const void *s, size_t n) { return submit(0, [=] { std::memcpy(d, s, n); return true; }); }
+    bool ev_record(int id) { named_[id] = record(0); return true; }
+    bool ev_sync(int id) {
+        if (id < 0 || id >= 4 || !named_[id]) return true;
+        std::shared_ptr<bool> e = named_[id];
+        return drain_until([e] { return *e; });
+    }
     void tic() { t0_ = std::chrono::steady_clock::now(); }
     void marks_reset() {}
     void mark(int) {}
     double marks_elapsed(int) { return 0.0; }
-    void toc_record() { t1_ = std::chrono::steady_clock::now(); }
+    void toc_record() { drain_all(); t1_ = std::chrono::steady_clock::now(); }
     double toc_elapsed(bool, bool &ok) { ok = true; return std::chrono::duration<double, std::milli>(t1_ - t0_).count(); }
 
     template <class K, class P>
     bool launch(Dim3 g, const P &p) {
         ++launches;
-        for (int bz = 0; bz < g.z; ++bz)
-            for (int by = 0; by < g.y; ++by)
-                for (int bx = 0; bx < g.x; ++bx)
-                    for (int tx = 0; tx < K::kThreads; ++tx) K::run(p, bx, by, bz, tx);
-        return true;
+        return submit(cur_, [=] {
+            for (int bz = 0; bz < g.z; ++bz)
+                for (int by = 0; by < g.y; ++by)
+                    for (int bx = 0; bx < g.x; ++bx)
+                        for (int tx = 0; tx < K::kThreads; ++tx) K::run(p, bx, by, bz, tx);
+            return true;
+        });
     }
 
     // block-phased kernels: CTA barrier between the phases -> per block: all threads of phase 0, then phase 1, ...
     template <class K, class P>
     bool launch_block_phased(Dim3 g, const P &p) {
         ++launches;
-        for (int bz = 0; bz < g.z; ++bz)
-            for (int by = 0; by < g.y; ++by)
-                for (int bx = 0; bx < g.x; ++bx)
-                    for (int ph = 0; ph < K::kBlockPhases; ++ph)
-                        for (int tx = 0; tx < K::kThreads; ++tx) K::run(p, bx, by, bz, tx, ph);
-        return true;
+        return submit(cur_, [=] {
+            for (int bz = 0; bz < g.z; ++bz)
+                for (int by = 0; by < g.y; ++by)
+                    for (int bx = 0; bx < g.x; ++bx)
+                        for (int ph = 0; ph < K::kBlockPhases; ++ph)
+                            for (int tx = 0; tx < K::kThreads; ++tx) K::run(p, bx, by, bz, tx, ph);
+            return true;
+        });
     }
 
     // ticket-scheduled kernels: on the GPU the phases interleave along a wavefront; here every CTA of phase 0, then phase 1
     template <class K, class P>
     bool launch_ticketed(Dim3 g, const P &p) {
         ++launches;
-        for (int ph = 0; ph < K::kGridPhases; ++ph)
-            for (int bz = 0; bz < g.z; ++bz)
-                for (int by = 0; by < g.y; ++by)
-                    for (int bx = 0; bx < g.x; ++bx)
-                        for (int tx = 0; tx < K::kThreads; ++tx) K::run(p, bx, by, bz, tx, ph);
-        return true;
+        return submit(cur_, [=] {
+            for (int ph = 0; ph < K::kGridPhases; ++ph)
+                for (int bz = 0; bz < g.z; ++bz)
+                    for (int by = 0; by < g.y; ++by)
+                        for (int bx = 0; bx < g.x; ++bx)
+                            for (int tx = 0; tx < K::kThreads; ++tx) K::run(p, bx, by, bz, tx, ph);
+            return true;
+        });
     }
-    bool zero_on_current(void *d, size_t n) { std::memset(d, 0, n); return true; }
+    bool zero_on_current(void *d, size_t n) { return submit(cur_, [=] { std::memset(d, 0, n); return true; }); }
 
     // phased kernels (one cooperative launch on the GPU): phases in order, every item of a phase before the next
     bool supports_phased() const { return true; }
     template <class K, class P>
     bool launch_phased(long long, const P &p) {
         ++launches;
-        for (int ph = 0; ph < K::kPhases; ++ph) {
-            const long long n = K::items(p, ph);
-            for (long long i = 0; i < n; ++i) K::item(p, ph, i);
-        }
-        return true;
+        return submit(0, [=] {
+            for (int ph = 0; ph < K::kPhases; ++ph) {
+                const long long n = K::items(p, ph);
+                for (long long i = 0; i < n; ++i) K::item(p, ph, i);
+            }
+            return true;
+        });
     }
 
     // peers: only same-process handles (raw pointers) — lets the CPU tests run two slabs in one process
@@ -110,62 +146,156 @@ public:
     }
     // exchange counters (IB across slabs): ranks run in separate host threads in the tests, so these really wait
     bool signal_counters(int *mine, int *const *targets, int n, bool bump) {
-        const int v = mine[0] + 1;
-        std::atomic_thread_fence(std::memory_order_release);
-        for (int i = 0; i < n; ++i)
-            if (targets[i]) *static_cast<volatile int *>(targets[i]) = v;
-        if (bump) mine[0] = v;
-        return true;
+        int *t[8] = {};
+        for (int i = 0; i < n && i < 8; ++i) t[i] = targets ? targets[i] : nullptr;
+        return submit(0, [=] {
+            const int v = mine[0] + 1;
+            std::atomic_thread_fence(std::memory_order_release);
+            for (int i = 0; i < 8; ++i)
+                if (t[i]) *static_cast<volatile int *>(t[i]) = v;
+            if (bump) mine[0] = v;
+            return true;
+        });
     }
     bool wait_counters(int *mine, int *const *sources, int n) {
-        const int v = mine[0] + 1;
-        const auto t0 = std::chrono::steady_clock::now();
-        for (int i = 0; i < n; ++i) {
-            if (!sources[i]) continue;
-            while (*static_cast<volatile int *>(sources[i]) < v) {
-                if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(20)) {
-                    err = "host emulation: timed out waiting for another rank's exchange";
+        int *src[8] = {};
+        for (int i = 0; i < n && i < 8; ++i) src[i] = sources[i];
+        return submit(0, [=] {
+            const int v = mine[0] + 1;
+            const auto t0 = std::chrono::steady_clock::now();
+            for (int i = 0; i < 8; ++i) {
+                if (!src[i]) continue;
+                while (*static_cast<volatile int *>(src[i]) < v) {
+                    if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(20)) {
+                        err = "host emulation: timed out waiting for another rank's exchange";
+                        fail_kind_ = 2;
+                        return false;
+                    }
+                    std::this_thread::yield();
+                }
+            }
+            std::atomic_thread_fence(std::memory_order_acquire);
+            return true;
+        });
+    }
+    void close_peers() {}
+    int peer_timeout() { drain_all(); return fail_kind_; }   // 1: a halo wait gave up, 2: an exchange wait did (sticky, like the CUDA word)
+    int current() const { return cur_; }
+    // fork_to(s): stream s waits for what is queued on the current stream so far, and becomes current;
+    // join_from(s): the current stream waits for what is queued on s so far (dev_cuda.cuh has the same contract)
+    bool fork_to(int s) {
+        const std::shared_ptr<bool> e = record(cur_);
+        wait(s, e);
+        cur_ = s;
+        return true;
+    }
+    bool switch_to(int s) { cur_ = s; return true; }
+    bool join_from(int s) {
+        const std::shared_ptr<bool> e = record(s);
+        wait(cur_, e);
+        return true;
+    }
+    bool graph_begin(const GraphKey &) { return false; }   // no graphs in the emulation: everything is launched directly
+    bool graph_end() { return true; }
+    void graph_abort() {}
+    void graph_clear() { drain_all(); }
+    bool signal_flags(int *mine, int *lo, int *hi) {
+        return submit(0, [=] {
+            const int value = ++mine[2];
+            std::atomic_thread_fence(std::memory_order_release);
+            if (lo) *static_cast<volatile int *>(lo) = value;
+            if (hi) *static_cast<volatile int *>(hi) = value;
+            return true;
+        });
+    }
+    bool wait_flags(const int *flags, bool lo, bool hi) {
+        if (!lo && !hi) return true;
+        return submit(0, [=] {
+            const int value = flags[2];
+            const auto t0 = std::chrono::steady_clock::now();
+            const volatile int *vf = flags;
+            while ((lo && vf[0] < value) || (hi && vf[1] < value)) {
+                if (std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(wait_ms)) {
+                    err = "host emulation: neighbour slab is behind (step the slabs in lock-step or from separate threads)";
+                    fail_kind_ = 1;
                     return false;
                 }
                 std::this_thread::yield();
             }
-        }
-        std::atomic_thread_fence(std::memory_order_acquire);
-        return true;
-    }
-    void close_peers() {}
-    int peer_timeout() const { return 0; }      // the emulated waits report a neighbour that is behind directly
-    int current() const { return cur_; }   // streams: everything runs sequentially here, in submission order
-    bool fork_to(int s) { cur_ = s; return true; }
-    bool switch_to(int s) { cur_ = s; return true; }
-    bool join_from(int) { return true; }
-    bool graph_begin(const GraphKey &) { return false; }   // no graphs in the emulation: everything runs directly
-    bool graph_end() { return true; }
-    void graph_abort() {}
-    void graph_clear() {}
-    bool signal_flags(int *mine, int *lo, int *hi) {
-        const int value = ++mine[2];
-        if (lo) *lo = value;
-        if (hi) *hi = value;
-        return true;
-    }
-    bool wait_flags(const int *flags, bool lo, bool hi) {
-        const int value = flags[2];
-        const auto t0 = std::chrono::steady_clock::now();
-        const volatile int *vf = flags;
-        while ((lo && vf[0] < value) || (hi && vf[1] < value)) {
-            if (std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(wait_ms)) {
-                err = "host emulation: neighbour slab is behind (step the slabs in lock-step or from separate threads)";
-                return false;
-            }
-            std::this_thread::yield();
-        }
-        std::atomic_thread_fence(std::memory_order_acquire);
-        return true;
+            std::atomic_thread_fence(std::memory_order_acquire);
+            return true;
+        });
     }
 
 private:
+    // ---- queued execution
+    struct Op {
+        int kind;                      // 0: run fn, 1: record ev, 2: wait for ev
+        std::function<bool()> fn;
+        std::shared_ptr<bool> ev;
+    };
+    bool submit(int stream, std::function<bool()> fn) {
+        if (sched_ == 0) {
+            if (!fn()) { failed_ = true; return false; }
+            return true;
+        }
+        q_[stream].push_back(Op{0, std::move(fn), nullptr});
+        return true;
+    }
+    std::shared_ptr<bool> record(int stream) {
+        auto e = std::make_shared<bool>(sched_ == 0);
+        if (sched_ != 0) q_[stream].push_back(Op{1, nullptr, e});
+        return e;
+    }
+    void wait(int stream, const std::shared_ptr<bool> &e) {
+        if (sched_ != 0) q_[stream].push_back(Op{2, nullptr, e});
+    }
+    bool runnable(int s) const { return !q_[s].empty() && (q_[s].front().kind != 2 || *q_[s].front().ev); }
+    bool run_one() {
+        int pick = -1;
+        if (sched_ == 3) {
+            int cand[kStreams], n = 0;
+            for (int s = 0; s < kStreams; ++s) if (runnable(s)) cand[n++] = s;
+            if (n) { rng_ = rng_ * 6364136223846793005ull + 1442695040888963407ull; pick = cand[(rng_ >> 33) % n]; }
+        } else if (sched_ == 2) {
+            for (int s = kStreams - 1; s >= 0 && pick < 0; --s) if (runnable(s)) pick = s;
+        } else {
+            for (int s = 0; s < kStreams && pick < 0; ++s) if (runnable(s)) pick = s;
+        }
+        if (pick < 0) return false;
+        Op op = std::move(q_[pick].front());
+        q_[pick].pop_front();
+        if (op.kind == 0) { if (!op.fn()) failed_ = true; }
+        else if (op.kind == 1) *op.ev = true;
+        return true;
+    }
+    template <class Pred>
+    bool drain_until(Pred done) {
+        while (!done()) {
+            if (!run_one()) {
+                err = "host emulation: queued streams cannot make progress (a wait on an event that is never recorded)";
+                failed_ = true;
+                return false;
+            }
+        }
+        return !failed_;
+    }
+    bool drain_stream0() { return sched_ == 0 ? !failed_ : drain_until([this] { return q_[0].empty(); }); }
+    void drain_all() {
+        if (sched_ == 0) return;
+        drain_until([this] {
+            for (int s = 0; s < kStreams; ++s) if (!q_[s].empty()) return false;
+            return true;
+        });
+    }
+
     int cur_ = 0;
+    int sched_ = 0;                    // 0 immediate, 1 lowest runnable stream first, 2 highest first, 3 random
+    unsigned long long rng_ = 1;
+    bool failed_ = false;
+    int fail_kind_ = 0;
+    std::deque<Op> q_[kStreams];
+    std::shared_ptr<bool> named_[4];
     std::chrono::steady_clock::time_point t0_, t1_;
 };
 
