@@ -238,7 +238,8 @@ def main():
     ap.add_argument("--no-graphs", action="store_true", help="launch kernels directly instead of per-substep CUDA graphs")
     ap.add_argument("--no-flip", action="store_true", help="sweep planes upwards in every step (no L2 reuse between steps)")
     ap.add_argument("--pairs", action="store_true", help="fused even+odd wavefront launches (opt-in experiment, measured slower)")
-    ap.add_argument("--pair-lag", type=int, default=0, help="planes between the even and odd wavefront (0: automatic)")
+    ap.add_argument("--pair-lag", type=int, default=0, help="planes between the even and odd wavefront / per wavefront chunk (0: automatic)")
+    ap.add_argument("--wavefront", action="store_true", help="even + odd step as a launch-level wavefront of plane chunks (opt-in experiment, FG_FLAG_WAVEFRONT)")
     ap.add_argument("--no-xwarp", action="store_true", help="x walls: predicated wall code in every thread instead of only in the row-end warps")
     ap.add_argument("--storage", default="f32", choices=["f32", "f16"],
                     help="f16: the opt-in 16-bit-storage build (fp32 arithmetic, 76 B per cell update; NOT the headline configuration)")
@@ -284,7 +285,8 @@ def main():
     w = WORKLOADS[wl]
     flags = ((g._abi.FLAG_NO_OVERLAP if args.no_overlap else 0) | (g._abi.FLAG_NO_GRAPHS if args.no_graphs else 0) |
              (g._abi.FLAG_NO_SPLIT if args.no_split else 0) | (g._abi.FLAG_NO_SWEEP_FLIP if args.no_flip else 0) |
-             (g._abi.FLAG_FUSED_PAIRS if args.pairs else 0) | (g._abi.FLAG_NO_XWARP if args.no_xwarp else 0))
+             (g._abi.FLAG_FUSED_PAIRS if args.pairs else 0) | (g._abi.FLAG_NO_XWARP if args.no_xwarp else 0) |
+             (g._abi.FLAG_WAVEFRONT if args.wavefront else 0))
     gpu_backend = "cuda" if args.storage == "f32" else "cuda_f16"
     bytes_per_update = BYTES_PER_CELL_UPDATE if args.storage == "f32" else BYTES_PER_CELL_UPDATE / 2
     sim, markers = make_sim(g, gpu_backend, wl, rank, world, local, flags=flags, extra=dict(pair_lag=args.pair_lag))

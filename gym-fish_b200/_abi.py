@@ -30,6 +30,7 @@ FLAG_NO_SWEEP_FLIP = 32
 FLAG_FUSED_PAIRS = 64
 FLAG_NO_XWARP = 128
 FLAG_SYNC_STEP = 256
+FLAG_WAVEFRONT = 512
 
 _ERR_NAMES = {FG_EINVAL: "FG_EINVAL", FG_ENOMEM: "FG_ENOMEM", FG_ECUDA: "FG_ECUDA", FG_ESTATE: "FG_ESTATE",
               FG_ENOTSUP: "FG_ENOTSUP", FG_EPEER: "FG_EPEER"}

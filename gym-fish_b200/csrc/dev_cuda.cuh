@@ -502,9 +502,9 @@ private:
     cudaEvent_t tev_[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
     int tpair_ = 0;
     std::vector<std::pair<std::string, void *>> opened_;
-    static constexpr int kStreams = 4;
-    cudaStream_t s_[kStreams] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t fork_ev_[kStreams] = {nullptr, nullptr, nullptr, nullptr}, join_ev_[kStreams] = {nullptr, nullptr, nullptr, nullptr};
+    static constexpr int kStreams = 6;      // 0/1 high priority (main + thin branch), 2/3 and 4/5 low (far branch; odd wavefront)
+    cudaStream_t s_[kStreams] = {};
+    cudaEvent_t fork_ev_[kStreams] = {}, join_ev_[kStreams] = {};
     int cur_ = 0;
     int prio_low_ = 0, prio_high_ = 0;
     volatile int *timeout_word_ = nullptr;     // pinned + mapped (UVA: the same pointer is valid on the device)

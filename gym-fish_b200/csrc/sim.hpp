@@ -342,6 +342,15 @@ public:
                     if (far * 4 >= hi - lo && (long long)far * L_.plane >= (cfg.split_min_cells > 0 ? cfg.split_min_cells : (1 << 20))) { split_ = true; near_a_ = a; near_b_ = b; }
                 }
             }
+            // Two substeps as a launch-level wavefront (wave_pair below): opt-in experiment.
+            if (!prof && (cfg.flags & FG_FLAG_WAVEFRONT) && parity_ == 0 && it + 1 < n && !ranks && fish_.empty() && L_.nz >= 8) {
+                int rc = FG_OK;
+                if (wave_pair(ib_on, graphs, rc)) {
+                    if (rc != FG_OK) return rc;
+                    ++it;
+                    continue;
+                }
+            }
             // Two substeps in one wavefront launch (StreamCollidePair): opt-in, measured slower than two plain launches
             // (lbm_core.cuh); no bodies, one rank.
             if (!prof && (cfg.flags & FG_FLAG_FUSED_PAIRS) && parity_ == 0 && it + 1 < n && !ib_on && !ranks && !L_.solid && L_.nz >= 8) {
@@ -470,7 +479,7 @@ public:
         o->collide_ms = collide_ms_; o->collide_launches = last_collide_launches_; o->ib_ms = ib_ms_;
         o->collide_cells = last_collide_cells_;
         o->split_substeps = split_substeps_;
-        o->pair_substeps = pair_substeps_;
+        o->pair_substeps = pair_substeps_ + wave_substeps_;
         return FG_OK;
     }
 
@@ -641,7 +650,7 @@ private:
         const int hole = hole_e > hole_b ? hole_e - hole_b : 0;
         const int planes = (ze - zb - hole + zstride - 1) / zstride;
         if (planes <= 0 || rows <= 0) return true;
-        const bool down = parity_ == 1 && !(cfg.flags & FG_FLAG_NO_SWEEP_FLIP);
+        const bool down = parity_ == 1 && !(cfg.flags & FG_FLAG_NO_SWEEP_FLIP) && !wave_;
         StepParams p{L_, C_, F, zb, zstride, hole ? hole_b : 0x7fffffff, hole, down ? planes - 1 : -1, y0, ystride, {}};
         for (int s = 0; s < Q; ++s)
             for (int d = 0; d < 3; ++d) p.kz[s][d] = (long long)kPopBytes * (s * L_.slot + (long long)(d - 1) * L_.plane);
@@ -757,6 +766,109 @@ private:
         return int(std::max<long long>(2, std::min<long long>(8, (24ll << 20) / plane_bytes)));
     }
 
+    // ---- FG_FLAG_WAVEFRONT: an even step and the odd step after it as a wavefront of plane chunks.
+    // The odd step of a plane needs the even step of the planes below, at and above it and nothing else, so it may run one
+    // chunk behind the even step: chunk k+1 takes its even step on one stream while chunk k takes its odd step on another,
+    // and finds what the even step wrote a moment ago in the 126 MB L2 — DRAM then sees one read and one write per cell
+    // for TWO updates.  Unlike StreamCollidePair (tickets and fences inside one kernel, measured slower) the ordering is
+    // between launches: plain StreamCollide kernels, stream events, one CUDA graph per pair.
+    //   * planes next to the box ends take their odd step last: it needs the z-face operation of the even step, and a
+    //     zero-gradient outlet copies from the boundary plane what the odd step of the plane next to it would overwrite;
+    //   * with an immersed boundary, the planes around the bodies (+1 for the odd step) run on the main stream:
+    //     IB(t) -> even -> IB(t+1) -> odd, beside the far-plane wavefront, which needs no force.
+    // Returns false when the pair cannot be run this way (the caller steps normally); rc carries an error.
+    int wave_chunk() const {
+        if (cfg.pair_lag > 0) return cfg.pair_lag;
+        const long long plane_bytes = (long long)kPopBytes * Q * L_.plane;
+        return int(std::max<long long>(1, std::min<long long>(64, (20ll << 20) / plane_bytes)));
+    }
+    bool launch_collide_at(int parity, int zb, int ze, const ForceField &F) {
+        const int keep = parity_;
+        parity_ = parity;
+        const bool ok = launch_collide(zb, ze, F);
+        parity_ = keep;
+        return ok;
+    }
+    bool wave_pair(bool ib_on, bool graphs, int &rc) {
+        const int lo = 1, hi = L_.nz + 1;
+        const bool out_lo = L_.bc_zlo == BC_OUTLET, out_hi = L_.bc_zhi == BC_OUTLET;
+        const int late_lo = lo + (out_lo ? 2 : 1), late_hi = hi - (out_hi ? 2 : 1);     // odd wavefront: [late_lo, late_hi)
+        int na = hi, nb = hi;                                                           // even step of [na, nb) waits for IB(t)
+        if (ib_on) {
+            int a, b;
+            if (!ib_.near_planes(a, b)) return false;                                   // bodies everywhere: nothing is far
+            na = std::min(std::max(a, lo), hi); nb = std::max(std::min(b, hi), na);
+            if (nb <= na) { na = hi; nb = hi; }
+            // bodies next to a box end: their band cells read ghost planes at odd parity, i.e. IB(t+1) would need the z-face
+            // operation of the even step, which here runs after the whole wavefront — such pairs are stepped normally
+            else if (na <= lo || nb >= hi) return false;
+        }
+        if ((na - lo) + (hi - nb) < 4) return false;
+        const int oa = std::max(na - 1, late_lo), ob = std::min(nb + 1, late_hi);       // odd step of [oa, ob) waits for IB(t+1)
+        struct Scope {
+            Dev &d; bool on; bool done = false; bool &wave;
+            ~Scope() { wave = false; if (on && !done) d.graph_abort(); }
+        } scope{dev, false, false, wave_};
+        GraphKey key = substep_key();
+        key[0] |= 0x5741564500000000ull;
+        scope.on = graphs && dev.graph_begin(key);
+        wave_ = true;
+        const int c = wave_chunk();
+        bool ok = true;
+        // ---- far planes: even chunks on stream 2, odd chunks one behind on stream 4
+        ok = ok && dev.fork_to(4) && dev.switch_to(0) && dev.fork_to(2);
+        const int far[2][2] = {{lo, na}, {nb, hi}};
+        int tail[2][2] = {{0, 0}, {0, 0}};      // odd ranges that wait for the even step of planes outside their range
+        for (int r = 0; r < 2 && ok; ++r) {
+            const int a = far[r][0], b = far[r][1];
+            const int fa = std::max(a, late_lo), fb = std::min(b, late_hi);            // ... minus the late planes
+            const int ra = r == 1 && nb < hi ? std::max(fa, nb + 1) : fa;               // ... minus the planes next to the bodies
+            const int rb = r == 0 && na < hi ? std::min(fb, na - 1) : fb;
+            for (int z = a, k = 0; z < b && ok; z += c, ++k) {
+                ok = ok && dev.switch_to(2) && launch_collide_at(0, z, std::min(z + c, b), ForceField{});
+                if (k >= 1) {     // the even step now covers planes up to z + c: the chunk before takes its odd step
+                    const int za = std::max(z - c, ra), zb = std::min(z, rb);
+                    if (zb > za) ok = ok && dev.switch_to(4) && dev.join_from(2) && launch_collide_at(1, za, zb, ForceField{});
+                }
+            }
+            const int last = a + ((b - a - 1) / c) * c;                                 // first plane of the last chunk
+            tail[r][0] = std::max(b > a ? last : b, ra); tail[r][1] = rb;
+        }
+        // ---- planes around the bodies on the main stream
+        ForceField F0{}, F1{};
+        ok = ok && dev.switch_to(0);
+        if (ok && ib_on) {
+            ib_.set_fused(false);
+            if ((rc = ib_.compute_forces(dev, L_, C_, 0, err)) != FG_OK) return true;
+            F0 = ib_.force_view();
+            ok = launch_collide_at(0, na, nb, F0);
+        }
+        // the last odd chunk of each far range needs the even step of the plane above it: every even launch is queued now
+        ok = ok && dev.switch_to(4) && dev.join_from(2) && dev.join_from(0);
+        for (int r = 0; r < 2 && ok; ++r)
+            if (tail[r][1] > tail[r][0]) ok = launch_collide_at(1, tail[r][0], tail[r][1], ForceField{});
+        ok = ok && dev.switch_to(0);
+        if (ok && ib_on) {
+            if ((rc = ib_.compute_forces(dev, L_, C_, 1, err)) != FG_OK) return true;
+            F1 = ib_.force_view();
+            ok = dev.join_from(2);
+            if (ob > oa) ok = ok && launch_collide_at(1, oa, ob, F1);
+        }
+        ok = ok && dev.join_from(2) && dev.join_from(4);
+        // ---- box ends: z-face operation of the even step, odd step of the late planes, z-face operation of the odd step
+        ok = ok && launch_faces();                                                      // parity_ == 0
+        parity_ = 1;
+        ok = ok && launch_collide(lo, std::min(late_lo, hi), F1) && launch_collide(std::max(late_hi, late_lo), hi, F1) && launch_faces();
+        parity_ = 0;
+        if (!ok) { rc = cuda_fail(); return true; }
+        steps_ += 2; wave_substeps_ += 2;
+        if (scope.on) {
+            scope.done = true;
+            if (!dev.graph_end()) { rc = cuda_fail(); return true; }
+        }
+        return true;
+    }
+
     // z-face plane ops after the step of parity `parity_`: one launch covers both faces
     bool launch_faces() {
         HaloParams p{};
@@ -840,7 +952,8 @@ private:
     bool timing_pending_ = false;
     int timed_substeps_ = 0;
     int64_t collide_launches_ = 0, last_collide_launches_ = 0, collide_cells_ = 0, last_collide_cells_ = 0;
-    int64_t split_substeps_ = 0, pair_substeps_ = 0;
+    int64_t split_substeps_ = 0, pair_substeps_ = 0, wave_substeps_ = 0;
+    bool wave_ = false;            // inside wave_pair: chunk launches do not flip the sweep direction
     int *pair_ctr_ = nullptr;      // [1 + nz + 2] ticket + per-plane completion counters of StreamCollidePair
     bool split_ = false;           // this substep: far planes collide beside the IB kernels
     int near_a_ = 1, near_b_ = 1;  // planes [near_a_, near_b_) wait for the IB force

@@ -626,3 +626,79 @@ def test_random_api_sequences_cuda_vs_oracle(g, cuda):
     obstacle masks, flags of the random case, resets and read-outs in any order."""
     bad = [(seed, w) for seed in range(3000, 3120) for w in [run_api_sequence_case(g, cuda, seed)] if w is not None and w > 2e-5]
     assert not bad, bad[:5]
+
+
+def run_wavefront_case(g, emu, seed, exact=True):
+    """FG_FLAG_WAVEFRONT (sim.hpp wave_pair): even + odd step as a wavefront of plane chunks on two streams, with a drifting
+    marker cloud (so the near range moves, sometimes to a box end where the pair falls back to plain steps), obstacles,
+    every face combination, chunk sizes 1-8: populations and wrenches bit-identical to plain stepping.  Under
+    FG_EMU_SCHED (test_stream_order.py) this is what checks the event edges between the even and the odd stream."""
+    A = g._abi
+    rng = np.random.default_rng(seed)
+    kw, solid, _ = random_case(g, rng)
+    kw["nz"], kw["ny"] = int(rng.integers(8, 48)), max(kw["ny"], 3)
+    nx, ny, nz = kw["nx"], kw["ny"], kw["nz"]
+    if solid is not None:
+        solid = (rng.random((nz, ny, nx)) < 0.06).astype(np.uint8)
+    kw.update(max_markers=64, max_links=3, pair_lag=int(rng.integers(1, 9)) if rng.random() < 0.8 else 0)
+    base = kw["flags"]
+    a = g.Sim(backend=emu, **dict(kw, flags=base | A.FLAG_NO_SPLIT))
+    b = g.Sim(backend=emu, **dict(kw, flags=base | A.FLAG_WAVEFRONT))
+    rho, u = util.smooth_fields(a.shape)
+    rho = (rho + 0.003 * rng.standard_normal(a.shape)).astype(np.float32)
+    u = (u + 0.003 * rng.standard_normal((3,) + a.shape)).astype(np.float32)
+    for s in (a, b):
+        if solid is not None:
+            s.set_solid(solid)
+        s.set_fields(rho, u)
+    use_ib = rng.random() < 0.6
+    c, V = np.array([nx / 2, ny / 2, rng.uniform(0, nz)]), np.array([0, 0, rng.uniform(-1.5, 1.5)])
+    n = int(rng.integers(1, 30))
+    X0, link = rng.uniform(-2, 2, (n, 3)), np.sort(rng.integers(0, 3, n)).astype(np.int32)
+    same = True
+    for _ in range(5):
+        if use_ib and rng.random() < 0.7:
+            c = c + V
+            X, U = (c + X0).astype(np.float32), np.tile((V * 0.02).astype(np.float32), (n, 1))
+            for s in (a, b):
+                s.set_markers(X, U, np.ones(n, np.float32), link)
+                s.set_link_origins([list(c)] * 3)
+        k = int(rng.integers(1, 6))
+        a.step(k)
+        b.step(k)
+        if exact:
+            same = same and np.array_equal(a.get_populations(), b.get_populations())
+            same = same and (not use_ib or np.array_equal(a.get_link_wrenches(), b.get_link_wrenches()))
+        else:       # on the GPU the spreading atomics add in a different order from run to run
+            keep = 1 if solid is None else (solid == 0)
+            same = same and np.abs((a.get_populations() - b.get_populations()) * keep).max() < 5e-7
+            wa, wb = a.get_link_wrenches(), b.get_link_wrenches()
+            same = same and (not use_ib or np.abs(wa - wb).max() <= 1e-5 * max(np.abs(wa).max(), 1e-3))
+    waves = b.stats().pair_substeps
+    a.close()
+    b.close()
+    return same, waves, kw
+
+
+def test_random_wavefront_pairs_equal_plain_steps(g, emu):
+    bad, with_waves = [], 0
+    for seed in range(150):
+        same, waves, kw = run_wavefront_case(g, emu, seed)
+        with_waves += waves > 0
+        if not same:
+            bad.append((seed, kw))
+    assert not bad, bad[:3]
+    assert with_waves >= 90
+
+
+@pytest.mark.gpu
+def test_random_wavefront_pairs_cuda(g, cuda):
+    """The same on the GPU, where the chunks really run on two streams (and, with graphs on, as one captured graph per pair)."""
+    bad, with_waves = [], 0
+    for seed in range(4000, 4080):
+        same, waves, kw = run_wavefront_case(g, cuda, seed, exact=False)
+        with_waves += waves > 0
+        if not same:
+            bad.append((seed, kw))
+    assert not bad, bad[:3]
+    assert with_waves >= 40
