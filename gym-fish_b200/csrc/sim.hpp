@@ -809,8 +809,10 @@ private:
             Dev &d; bool on; bool done = false; bool &wave;
             ~Scope() { wave = false; if (on && !done) d.graph_abort(); }
         } scope{dev, false, false, wave_};
+        // the launch geometry depends on where the bodies are: (na, nb) belong to the key (na >= 1, so it never collides
+        // with the key of a plain substep, whose first word is < 4)
         GraphKey key = substep_key();
-        key[0] |= 0x5741564500000000ull;
+        key[0] = (key[0] & 0xffull) | (uint64_t(uint32_t(na)) << 8) | (uint64_t(uint32_t(nb)) << 36);
         scope.on = graphs && dev.graph_begin(key);
         wave_ = true;
         const int c = wave_chunk();
