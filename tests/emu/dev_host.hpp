@@ -7,9 +7,12 @@
 #include <atomic>
 #include <chrono>
 #include <deque>
+#include <map>
+#include <vector>
 #include <functional>
 #include <memory>
 #include <thread>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -40,6 +43,7 @@ public:
             else if (v == "high") sched_ = 2;
             else if (v.rfind("rand", 0) == 0) { sched_ = 3; rng_ = v.size() > 5 ? std::strtoull(v.c_str() + 5, nullptr, 10) * 2654435761ull + 1 : 12345; }
         }
+        graphs_on_ = std::getenv("FG_EMU_GRAPHS") != nullptr;
         return true;
     }
     void enter() {}
@@ -63,7 +67,12 @@ public:
     void free_host(void *p) { if (p) drain_all(); std::free(p); }
     bool h2d_async(void *d, const void *s, size_t n) { return submit(0, [=] { std::memcpy(d, s, n); return true; }); }   // reads the pinned buffer when it RUNS
     bool d2h_async(void *d, const void *s, size_t n) { return submit(0, [=] { std::memcpy(d, s, n); return true; }); }
-    bool ev_record(int id) { named_[id] = record(0); return true; }
+    bool ev_record(int id) {
+        if (gmode_ == 2) return true;
+        if (gmode_ == 1) { graph_->ops.push_back(GOp{0, 1, nullptr, graph_->n_events++, id}); return true; }
+        named_[id] = record(0);
+        return true;
+    }
     bool ev_sync(int id) {
         if (id < 0 || id >= 4 || !named_[id]) return true;
         std::shared_ptr<bool> e = named_[id];
@@ -195,10 +204,45 @@ public:
         wait(cur_, e);
         return true;
     }
-    bool graph_begin(const GraphKey &) { return false; }   // no graphs in the emulation: everything is launched directly
-    bool graph_end() { return true; }
-    void graph_abort() {}
-    void graph_clear() { drain_all(); }
+    // ---- CUDA graphs (FG_EMU_GRAPHS=1; off by default: everything is launched directly).  Capture RECORDS the operations
+    // with the arguments they had at capture time and runs nothing; graph_end launches the recording; for a known key the
+    // host code runs again but what it submits is DROPPED and the first recording is launched instead — exactly what
+    // dev_cuda.cuh does, so a launch argument that changes between substeps without being part of the key gives a wrong
+    // result here, too.
+    bool graph_begin(const GraphKey &key) {
+        if (!graphs_on_) return false;
+        auto it = graphs_.find(key);
+        if (it != graphs_.end()) { gmode_ = 2; graph_ = &it->second; if (std::getenv("FG_EMU_DEBUG")) std::fprintf(stderr, "[emu] replay graph %llx\n", (unsigned long long)key.w[0]); return true; }
+        if (graphs_.size() >= 64) graph_clear();
+        graph_ = &graphs_[key];
+        if (std::getenv("FG_EMU_DEBUG")) std::fprintf(stderr, "[emu] capture graph %llx\n", (unsigned long long)key.w[0]);
+        gkey_ = key;
+        gmode_ = 1;
+        cur_ = 0;
+        cap_ev_.clear();
+        cap_keep_.clear();
+        return true;
+    }
+    bool graph_end() {
+        if (gmode_ == 0) return true;
+        gmode_ = 0;
+        std::vector<std::shared_ptr<bool>> inst(graph_->n_events);
+        for (auto &e : inst) e = std::make_shared<bool>(sched_ == 0);
+        for (const GOp &op : graph_->ops) {
+            if (op.kind == 0) { if (!submit(op.stream, op.fn)) return false; }
+            else if (op.kind == 1) {
+                if (sched_ != 0) q_[op.stream].push_back(Op{1, nullptr, inst[op.ev]});
+                if (op.named >= 0) named_[op.named] = inst[op.ev];
+            } else wait(op.stream, inst[op.ev]);
+        }
+        return true;
+    }
+    void graph_abort() {
+        if (gmode_ == 1) graphs_.erase(gkey_);
+        gmode_ = 0;
+        cur_ = 0;
+    }
+    void graph_clear() { drain_all(); graphs_.clear(); }
     bool signal_flags(int *mine, int *lo, int *hi) {
         return submit(0, [=] {
             const int value = ++mine[2];
@@ -235,6 +279,8 @@ private:
         std::shared_ptr<bool> ev;
     };
     bool submit(int stream, std::function<bool()> fn) {
+        if (gmode_ == 2) return true;                                             // replaying: dropped
+        if (gmode_ == 1) { graph_->ops.push_back(GOp{stream, 0, std::move(fn), -1, -1}); return true; }
         if (sched_ == 0) {
             if (!fn()) { failed_ = true; return false; }
             return true;
@@ -244,10 +290,23 @@ private:
     }
     std::shared_ptr<bool> record(int stream) {
         auto e = std::make_shared<bool>(sched_ == 0);
+        if (gmode_ == 2) return e;
+        if (gmode_ == 1) {
+            cap_keep_.push_back(e);                                               // keeps the address unique for the capture
+            cap_ev_[e.get()] = graph_->n_events;
+            graph_->ops.push_back(GOp{stream, 1, nullptr, graph_->n_events++, -1});
+            return e;
+        }
         if (sched_ != 0) q_[stream].push_back(Op{1, nullptr, e});
         return e;
     }
     void wait(int stream, const std::shared_ptr<bool> &e) {
+        if (gmode_ == 2) return;
+        if (gmode_ == 1) {
+            auto it = cap_ev_.find(e.get());
+            if (it != cap_ev_.end()) graph_->ops.push_back(GOp{stream, 2, nullptr, it->second, -1});
+            return;                                                                // an event from before the capture: complete
+        }
         if (sched_ != 0) q_[stream].push_back(Op{2, nullptr, e});
     }
     bool runnable(int s) const { return !q_[s].empty() && (q_[s].front().kind != 2 || *q_[s].front().ev); }
@@ -289,6 +348,15 @@ private:
         });
     }
 
+    struct GOp { int stream, kind; std::function<bool()> fn; int ev, named; };
+    struct Graph { std::vector<GOp> ops; int n_events = 0; };
+    bool graphs_on_ = false;
+    int gmode_ = 0;                    // 0 direct, 1 capturing, 2 replaying
+    Graph *graph_ = nullptr;
+    GraphKey gkey_{};
+    std::map<GraphKey, Graph> graphs_;
+    std::map<const bool *, int> cap_ev_;
+    std::vector<std::shared_ptr<bool>> cap_keep_;
     int cur_ = 0;
     int sched_ = 0;                    // 0 immediate, 1 lowest runnable stream first, 2 highest first, 3 random
     unsigned long long rng_ = 1;

@@ -7,6 +7,10 @@ waits and signals on stream 0) and runs them only when the host waits, in an ord
 event edges (tests/emu/dev_host.hpp).  The parity and bit-identity tests must hold under every policy: far-plane collide
 beside the IB chain, thin wall-row branches, slab halos, bodies across faces, fused pairs, the wavefront pairs.
 (Removing the join of the far branch in sim.hpp step() makes `low` and `rand` fail; that is how the harness was checked.)
+
+FG_EMU_GRAPHS=1 adds CUDA-graph semantics: a captured substep is recorded with the launch arguments of that moment and
+replayed for every later substep with the same key, while what the host code submits is dropped — so a launch argument
+that is not part of the key goes stale here exactly as it would on the GPU (test_stale_graph_key_would_be_noticed).
 """
 import os
 import subprocess
@@ -21,11 +25,40 @@ SELECT = ["tests/test_emu_parity.py", "tests/test_slabs.py", "tests/test_random_
 
 def test_results_do_not_depend_on_the_order_streams_are_served_in(g, emu):
     procs = {}
-    for policy in ("low", "high", "rand:1", "rand:2"):
+    # the last two also with emulated CUDA graphs (capture once per key, replay the RECORDED arguments afterwards)
+    for policy, graphs in (("low", False), ("high", False), ("rand:1", True), ("rand:2", True)):
         env = dict(os.environ, FG_EMU_SCHED=policy, OMP_NUM_THREADS="2")
+        if graphs:
+            env["FG_EMU_GRAPHS"] = "1"
         procs[policy] = subprocess.Popen([sys.executable, "-m", "pytest", "-x", "-q", "-m", "not gpu", "-p", "no:cacheprovider"] + SELECT,
                                          cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     for policy, p in procs.items():
         out, _ = p.communicate(timeout=900)
         assert p.returncode == 0, (policy, out[-3000:])
         assert " passed" in out and "failed" not in out, (policy, out[-500:])
+
+
+def test_graph_keys_cover_the_wavefront_geometry(g, emu, monkeypatch):
+    """A sphere that jumps 9 planes between calls: the wavefront pair's launch geometry follows the near range, which is part
+    of its graph key.  (With the key reduced to the IB state this test fails under FG_EMU_GRAPHS — checked once by hand.)"""
+    import numpy as np
+    import util
+    monkeypatch.setenv("FG_EMU_GRAPHS", "1")
+    A = g._abi
+    kw = dict(nx=10, ny=8, nz=96, tau=0.8, collision=g.MRT, max_markers=64, max_links=1, pair_lag=4, body_force=[0, 0, 1e-5])
+    a, b = g.Sim(backend=emu, flags=A.FLAG_NO_SPLIT, **kw), g.Sim(backend=emu, flags=A.FLAG_WAVEFRONT, **kw)
+    rho, u = util.smooth_fields(a.shape)
+    X0 = util.sphere_markers((5, 4, 0), 2.0, 30)
+    for s in (a, b):
+        s.set_fields(rho, u)
+    for it in range(7):
+        X = X0.copy()
+        X[:, 2] += 14 + 9 * it
+        for s in (a, b):
+            s.set_markers(X, np.zeros_like(X), np.ones(30, np.float32))
+            s.set_link_origins([[5, 4, 14 + 9 * it]])
+            s.step(6)
+        assert np.array_equal(a.get_populations(), b.get_populations()), it
+    assert b.stats().pair_substeps == 42
+    a.close()
+    b.close()
