@@ -6,6 +6,8 @@ for f in files:
     if not os.path.exists(f):
         continue
     for ln in open(f):
+        if ln.startswith("=="):
+            print(ln.rstrip())
         if ln.startswith("{"):
             d = json.loads(ln)
             r = d.get("roofline") or {}
