@@ -5,6 +5,8 @@ outside the box), the scheduling flags.  The fixed case table (util.parity_cases
 what was not.  Its first run found one: a zero-gradient outlet above an obstacle cell copied a stale value
 (lbm_core.cuh ZFaceOp), kept below as a named regression case.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -692,6 +694,8 @@ def test_random_wavefront_pairs_equal_plain_steps(g, emu):
 
 
 @pytest.mark.gpu
+@pytest.mark.skipif(not os.environ.get("FG_TEST_EXPERIMENTS"), reason="FG_FLAG_WAVEFRONT is an opt-in experiment that has not run on a GPU "
+                    "yet (written after the GPU minutes of round 1 were spent); tools/passes/r2_pass2.sh sets FG_TEST_EXPERIMENTS=1")
 def test_random_wavefront_pairs_cuda(g, cuda):
     """The same on the GPU, where the chunks really run on two streams (and, with graphs on, as one captured graph per pair)."""
     bad, with_waves = [], 0

@@ -13,7 +13,7 @@ for wl in sphere_256x128x128 box_256 box_512; do
   echo "== $wl --wavefront --no-graphs" >> gpurun_out/wave.log
   timeout 200 $B --workload $wl --wavefront --no-graphs 2>&1 | tail -n 1 >> gpurun_out/wave.log
 done
-timeout 300 python -m pytest tests/test_random_cases.py -m gpu -q -k wavefront > gpurun_out/pytest_wave.log 2>&1
+FG_TEST_EXPERIMENTS=1 timeout 300 python -m pytest tests/test_random_cases.py -m gpu -q -k wavefront > gpurun_out/pytest_wave.log 2>&1
 # DRAM traffic of one pair with and without the wavefront (serialised under ncu: only the byte counts are meaningful)
 for mode in "" "--wavefront"; do
   timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --cache-control none --clock-control none \
