@@ -26,6 +26,7 @@ class HostDev {
 public:
     std::string err;
     long long launches = 0;
+    long long n_submit = 0, n_record = 0, n_wait = 0;      // FG_EMU_DEBUG: operations queued (what the CUDA policy would issue as API calls)
     int wait_ms = 300;   // how long a slab waits for its neighbour's halo before reporting it is behind
 
     // ---- streams.  Default (FG_EMU_SCHED unset): every operation runs at once, in submission order.
@@ -82,7 +83,11 @@ public:
     void marks_reset() {}
     void mark(int) {}
     double marks_elapsed(int) { return 0.0; }
-    void toc_record() { drain_all(); t1_ = std::chrono::steady_clock::now(); }
+    void toc_record() {
+        drain_all();
+        t1_ = std::chrono::steady_clock::now();
+        if (std::getenv("FG_EMU_DEBUG")) std::fprintf(stderr, "[emu] call: %lld submits, %lld event records, %lld stream waits so far\n", n_submit, n_record, n_wait);
+    }
     double toc_elapsed(bool, bool &ok) { ok = true; return std::chrono::duration<double, std::milli>(t1_ - t0_).count(); }
 
     template <class K, class P>
@@ -279,6 +284,7 @@ private:
         std::shared_ptr<bool> ev;
     };
     bool submit(int stream, std::function<bool()> fn) {
+        ++n_submit;
         if (gmode_ == 2) return true;                                             // replaying: dropped
         if (gmode_ == 1) { graph_->ops.push_back(GOp{stream, 0, std::move(fn), -1, -1}); return true; }
         if (sched_ == 0) {
@@ -289,6 +295,7 @@ private:
         return true;
     }
     std::shared_ptr<bool> record(int stream) {
+        ++n_record;
         auto e = std::make_shared<bool>(sched_ == 0);
         if (gmode_ == 2) return e;
         if (gmode_ == 1) {
@@ -301,6 +308,7 @@ private:
         return e;
     }
     void wait(int stream, const std::shared_ptr<bool> &e) {
+        ++n_wait;
         if (gmode_ == 2) return;
         if (gmode_ == 1) {
             auto it = cap_ev_.find(e.get());
