@@ -343,7 +343,7 @@ public:
                 }
             }
             // Two substeps as a launch-level wavefront (wave_pair below): opt-in experiment.
-            if (!prof && (cfg.flags & FG_FLAG_WAVEFRONT) && parity_ == 0 && it + 1 < n && !ranks && fish_.empty() && L_.nz >= 8) {
+            if (!prof && (cfg.flags & FG_FLAG_WAVEFRONT) && parity_ == 0 && it + 1 < n && (!ranks || (peers_ && !ib_.exchange_on())) && fish_.empty() && L_.nz >= 8) {
                 int rc = FG_OK;
                 if (wave_pair(ib_on, graphs, rc)) {
                     if (rc != FG_OK) return rc;
@@ -791,7 +791,8 @@ private:
     }
     bool wave_pair(bool ib_on, bool graphs, int &rc) {
         const int lo = 1, hi = L_.nz + 1;
-        const bool out_lo = L_.bc_zlo == BC_OUTLET, out_hi = L_.bc_zhi == BC_OUTLET;
+        const bool slab = cfg.n_ranks > 1;                                              // peered z-slab (the caller checked peers_)
+        const bool out_lo = L_.bc_zlo == BC_OUTLET && L_.z0 == 0, out_hi = L_.bc_zhi == BC_OUTLET && L_.z0 + L_.nz == L_.nzg;
         const int late_lo = lo + (out_lo ? 2 : 1), late_hi = hi - (out_hi ? 2 : 1);     // odd wavefront: [late_lo, late_hi)
         int na = hi, nb = hi;                                                           // even step of [na, nb) waits for IB(t)
         if (ib_on) {
@@ -799,11 +800,11 @@ private:
             if (!ib_.near_planes(a, b)) return false;                                   // bodies everywhere: nothing is far
             na = std::min(std::max(a, lo), hi); nb = std::max(std::min(b, hi), na);
             if (nb <= na) { na = hi; nb = hi; }
-            // bodies next to a box end: their band cells read ghost planes at odd parity, i.e. IB(t+1) would need the z-face
-            // operation of the even step, which here runs after the whole wavefront — such pairs are stepped normally
+            // bodies next to a slab end: their band cells read ghost planes at odd parity and their planes include the
+            // boundary planes, which here go first without a force — such pairs are stepped normally
             else if (na <= lo || nb >= hi) return false;
         }
-        if ((na - lo) + (hi - nb) < 4) return false;
+        if ((na - lo) + (hi - nb) < 6) return false;
         const int oa = std::max(na - 1, late_lo), ob = std::min(nb + 1, late_hi);       // odd step of [oa, ob) waits for IB(t+1)
         struct Scope {
             Dev &d; bool on; bool done = false; bool &wave;
@@ -817,9 +818,22 @@ private:
         wave_ = true;
         const int c = wave_chunk();
         bool ok = true;
-        // ---- far planes: even chunks on stream 2, odd chunks one behind on stream 4
+        // ---- A. boundary planes first (main stream): their even step, then the z-face operation of the even step — wrap,
+        // inlet / outlet, or the halo push into the z-neighbours' ghost planes, which the whole wavefront then hides.
+        // It reads slots of the boundary planes that the odd step of the planes next to them does not touch.
+        if (slab) ok = ok && dev.wait_flags(flags_, has_lo_peer(), has_hi_peer());     // halos of the previous odd step
+        const bool zwall = (L_.bc_zlo == BC_WALL && L_.z0 == 0) || (L_.bc_zhi == BC_WALL && L_.z0 + L_.nz == L_.nzg);
+        if (zwall) ok = ok && launch_collide_at(0, lo, lo + 1, ForceField{}) && launch_collide_at(0, hi - 1, hi, ForceField{});
+        else {
+            const int keep = parity_;
+            parity_ = 0;
+            ok = ok && launch_collide(lo, hi, ForceField{}, L_.nz - 1);               // both boundary planes in one launch
+            parity_ = keep;
+        }
+        ok = ok && launch_faces();                                                      // parity_ == 0
+        // ---- B. far planes: even chunks on stream 2, odd chunks one behind on stream 4
         ok = ok && dev.fork_to(4) && dev.switch_to(0) && dev.fork_to(2);
-        const int far[2][2] = {{lo, na}, {nb, hi}};
+        const int far[2][2] = {{lo + 1, std::min(na, hi - 1)}, {std::max(nb, lo + 1), hi - 1}};
         int tail[2][2] = {{0, 0}, {0, 0}};      // odd ranges that wait for the even step of planes outside their range
         for (int r = 0; r < 2 && ok; ++r) {
             const int a = far[r][0], b = far[r][1];
@@ -857,8 +871,9 @@ private:
             if (ob > oa) ok = ok && launch_collide_at(1, oa, ob, F1);
         }
         ok = ok && dev.join_from(2) && dev.join_from(4);
-        // ---- box ends: z-face operation of the even step, odd step of the late planes, z-face operation of the odd step
-        ok = ok && launch_faces();                                                      // parity_ == 0
+        // ---- C. slab ends: odd step of the late planes (they read the ghost planes: wrap / inlet / outlet data, or what the
+        // z-neighbours pushed after THEIR even step), then the z-face operation of the odd step
+        if (slab) ok = ok && dev.wait_flags(flags_, has_lo_peer(), has_hi_peer());
         parity_ = 1;
         ok = ok && launch_collide(lo, std::min(late_lo, hi), F1) && launch_collide(std::max(late_hi, late_lo), hi, F1) && launch_faces();
         parity_ = 0;

@@ -706,3 +706,68 @@ def test_random_wavefront_pairs_cuda(g, cuda):
             bad.append((seed, kw))
     assert not bad, bad[:3]
     assert with_waves >= 40
+
+
+def run_wavefront_slab_case(g, emu, seed):
+    """FG_FLAG_WAVEFRONT on 2-3 peered z-slabs (ranks stepped from threads: a pair holds two halo exchanges): boundary planes
+    first, their push hidden behind the wavefront of the interior planes, late planes after the neighbours' even-step halos.
+    One marker cloud inside one slab.  Populations bit-identical to the unsplit plain run."""
+    import test_slabs
+    A = g._abi
+    rng = np.random.default_rng(seed)
+    kw, solid, _ = random_case(g, rng)
+    n_ranks, h = int(rng.integers(2, 4)), int(rng.integers(8, 24))
+    kw["nz"], kw["ny"] = h * n_ranks, max(kw["ny"], 3)
+    nx, ny, nz = kw["nx"], kw["ny"], kw["nz"]
+    if solid is not None:
+        solid = (rng.random((nz, ny, nx)) < 0.06).astype(np.uint8)
+    kw.update(max_markers=64, max_links=2, pair_lag=int(rng.integers(1, 7)) if rng.random() < 0.8 else 0)
+    base = kw.pop("flags") | (A.FLAG_NO_OVERLAP if rng.random() < 0.3 else 0)
+    periodic = kw["bc"][4] == g.BC_PERIODIC
+    whole = g.Sim(backend=emu, flags=base | A.FLAG_NO_SPLIT, **kw)
+    parts = [g.Sim(backend=emu, n_ranks=n_ranks, rank=r, flags=base | A.FLAG_WAVEFRONT, **kw) for r in range(n_ranks)]
+    rho, u = util.smooth_fields(whole.shape)
+    rho = (rho + 0.003 * rng.standard_normal(whole.shape)).astype(np.float32)
+    u = (u + 0.003 * rng.standard_normal((3,) + whole.shape)).astype(np.float32)
+    for s in [whole] + parts:
+        if solid is not None:
+            s.set_solid(solid)
+    whole.set_fields(rho, u)
+    for r, s in enumerate(parts):
+        s.set_fields(rho[r * h:(r + 1) * h], u[:, r * h:(r + 1) * h])
+    hs = [s.peer_export() for s in parts]
+    for r, s in enumerate(parts):
+        s.peer_connect(hs[(r - 1) % n_ranks] if (r > 0 or periodic) else None, hs[(r + 1) % n_ranks] if (r < n_ranks - 1 or periodic) else None)
+    use_ib, rk = rng.random() < 0.5, int(rng.integers(0, n_ranks))
+    zc = rk * h + rng.uniform(3.5, h - 3.5)
+    n = int(rng.integers(1, 20))
+    X = (np.array([nx / 2, ny / 2, zc]) + rng.uniform(-1.2, 1.2, (n, 3))).astype(np.float32)
+    U, dV = np.full((n, 3), 0.01, np.float32), np.ones(n, np.float32)
+    same = True
+    keep = 1 if solid is None else (solid == 0)
+    for it in range(4):
+        if use_ib and it in (0, 2):
+            for s in (whole, parts[rk]):
+                s.set_markers(X, U, dV)
+                s.set_link_origins([[nx / 2, ny / 2, zc]])
+        k = int(rng.integers(1, 6))
+        whole.step(k)
+        test_slabs._run_threads([lambda s=s: s.step(k) for s in parts])
+        f, fs = whole.get_populations(), np.concatenate([s.get_populations() for s in parts], axis=1)
+        same = same and np.array_equal(f * keep, fs * keep)
+        same = same and (not use_ib or np.array_equal(whole.get_link_wrenches(), parts[rk].get_link_wrenches()))
+    waves = sum(s.stats().pair_substeps for s in parts)
+    for s in [whole] + parts:
+        s.close()
+    return same, waves, kw
+
+
+def test_random_wavefront_pairs_on_peered_slabs(g, emu):
+    bad, with_waves = [], 0
+    for seed in range(60):
+        same, waves, kw = run_wavefront_slab_case(g, emu, seed)
+        with_waves += waves > 0
+        if not same:
+            bad.append((seed, kw))
+    assert not bad, bad[:3]
+    assert with_waves >= 50
