@@ -818,23 +818,43 @@ private:
         wave_ = true;
         const int c = wave_chunk();
         bool ok = true;
+        // streams 2 (even chunks) and 4 (odd chunks) start here: the interior wavefront waits for nothing
+        ok = ok && dev.fork_to(4) && dev.switch_to(0) && dev.fork_to(2) && dev.switch_to(0);
         // ---- A. boundary planes first (main stream): their even step, then the z-face operation of the even step — wrap,
         // inlet / outlet, or the halo push into the z-neighbours' ghost planes, which the whole wavefront then hides.
         // It reads slots of the boundary planes that the odd step of the planes next to them does not touch.
         if (slab) ok = ok && dev.wait_flags(flags_, has_lo_peer(), has_hi_peer());     // halos of the previous odd step
-        const bool zwall = (L_.bc_zlo == BC_WALL && L_.z0 == 0) || (L_.bc_zhi == BC_WALL && L_.z0 + L_.nz == L_.nzg);
-        if (zwall) ok = ok && launch_collide_at(0, lo, lo + 1, ForceField{}) && launch_collide_at(0, hi - 1, hi, ForceField{});
-        else {
+        {
             const int keep = parity_;
             parity_ = 0;
             ok = ok && launch_collide(lo, hi, ForceField{}, L_.nz - 1);               // both boundary planes in one launch
             parity_ = keep;
         }
         ok = ok && launch_faces();                                                      // parity_ == 0
-        // ---- B. far planes: even chunks on stream 2, odd chunks one behind on stream 4
-        ok = ok && dev.fork_to(4) && dev.switch_to(0) && dev.fork_to(2);
+        ok = ok && dev.switch_to(4) && dev.join_from(0);                                // odd chunks touch the boundary planes
+        // ---- B. far planes: even chunks on stream 2, odd chunks one behind on stream 4; the planes around the bodies on the
+        // main stream beside them: IB(t) -> even, IB(t+1), then their odd step as soon as the even step of the planes
+        // next to them is queued
+        ForceField F0{}, F1{};
+        bool near_even = !ib_on, near_odd = !ib_on;
+        auto near_part1 = [&]() -> bool {
+            near_even = true;
+            if (!dev.switch_to(0)) return false;
+            ib_.set_fused(false);
+            if ((rc = ib_.compute_forces(dev, L_, C_, 0, err)) != FG_OK) return false;
+            F0 = ib_.force_view();
+            if (!launch_collide_at(0, na, nb, F0)) { rc = cuda_fail(); return false; }
+            if ((rc = ib_.compute_forces(dev, L_, C_, 1, err)) != FG_OK) return false;
+            F1 = ib_.force_view();
+            return true;
+        };
+        auto near_part2 = [&]() -> bool {
+            near_odd = true;
+            if (!(dev.switch_to(0) && dev.join_from(2))) { rc = cuda_fail(); return false; }
+            if (ob > oa && !launch_collide_at(1, oa, ob, F1)) { rc = cuda_fail(); return false; }
+            return true;
+        };
         const int far[2][2] = {{lo + 1, std::min(na, hi - 1)}, {std::max(nb, lo + 1), hi - 1}};
-        int tail[2][2] = {{0, 0}, {0, 0}};      // odd ranges that wait for the even step of planes outside their range
         for (int r = 0; r < 2 && ok; ++r) {
             const int a = far[r][0], b = far[r][1];
             const int fa = std::max(a, late_lo), fb = std::min(b, late_hi);            // ... minus the late planes
@@ -846,31 +866,17 @@ private:
                     const int za = std::max(z - c, ra), zb = std::min(z, rb);
                     if (zb > za) ok = ok && dev.switch_to(4) && dev.join_from(2) && launch_collide_at(1, za, zb, ForceField{});
                 }
+                // the even step of the planes just above the bodies is queued: their own odd step need not wait for the rest
+                if (ok && r == 1 && !near_odd && std::min(z + c, b) > std::min(nb + 1, b - 1)) { if (!near_part2()) return true; }
             }
+            // the last odd chunk of the range: the even step of the plane above it is a boundary plane or was queued before
             const int last = a + ((b - a - 1) / c) * c;                                 // first plane of the last chunk
-            tail[r][0] = std::max(b > a ? last : b, ra); tail[r][1] = rb;
+            const int ta = std::max(b > a ? last : b, ra);
+            if (ok && rb > ta) ok = dev.switch_to(4) && dev.join_from(2) && launch_collide_at(1, ta, rb, ForceField{});
+            if (ok && r == 0 && !near_even) { if (!near_part1()) return true; }
         }
-        // ---- planes around the bodies on the main stream
-        ForceField F0{}, F1{};
-        ok = ok && dev.switch_to(0);
-        if (ok && ib_on) {
-            ib_.set_fused(false);
-            if ((rc = ib_.compute_forces(dev, L_, C_, 0, err)) != FG_OK) return true;
-            F0 = ib_.force_view();
-            ok = launch_collide_at(0, na, nb, F0);
-        }
-        // the last odd chunk of each far range needs the even step of the plane above it: every even launch is queued now
-        ok = ok && dev.switch_to(4) && dev.join_from(2) && dev.join_from(0);
-        for (int r = 0; r < 2 && ok; ++r)
-            if (tail[r][1] > tail[r][0]) ok = launch_collide_at(1, tail[r][0], tail[r][1], ForceField{});
-        ok = ok && dev.switch_to(0);
-        if (ok && ib_on) {
-            if ((rc = ib_.compute_forces(dev, L_, C_, 1, err)) != FG_OK) return true;
-            F1 = ib_.force_view();
-            ok = dev.join_from(2);
-            if (ob > oa) ok = ok && launch_collide_at(1, oa, ob, F1);
-        }
-        ok = ok && dev.join_from(2) && dev.join_from(4);
+        if (ok && !near_odd) { if (!near_part2()) return true; }
+        ok = ok && dev.switch_to(0) && dev.join_from(2) && dev.join_from(4);
         // ---- C. slab ends: odd step of the late planes (they read the ghost planes: wrap / inlet / outlet data, or what the
         // z-neighbours pushed after THEIR even step), then the z-face operation of the odd step
         if (slab) ok = ok && dev.wait_flags(flags_, has_lo_peer(), has_hi_peer());
