@@ -861,7 +861,11 @@ private:
             const int ra = r == 1 && nb < hi ? std::max(fa, nb + 1) : fa;               // ... minus the planes next to the bodies
             const int rb = r == 0 && na < hi ? std::min(fb, na - 1) : fb;
             for (int z = a, k = 0; z < b && ok; z += c, ++k) {
-                ok = ok && dev.switch_to(2) && launch_collide_at(0, z, std::min(z + c, b), ForceField{});
+                ok = ok && dev.switch_to(2);
+                // back-pressure: nothing else keeps the even stream from running ahead of the odd one and pushing the chunks
+                // the odd step still has to read out of L2 — even chunk k waits for odd chunk k-2
+                if (k >= 2) ok = ok && dev.join_from(4);
+                ok = ok && launch_collide_at(0, z, std::min(z + c, b), ForceField{});
                 if (k >= 1) {     // the even step now covers planes up to z + c: the chunk before takes its odd step
                     const int za = std::max(z - c, ra), zb = std::min(z, rb);
                     if (zb > za) ok = ok && dev.switch_to(4) && dev.join_from(2) && launch_collide_at(1, za, zb, ForceField{});
