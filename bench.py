@@ -452,6 +452,7 @@ def main():
                    "markers_per_gpu": int(st.n_markers), "decomposition": "z-slabs, halos by peer stores over NVLink" if world > 1 else "single GPU",
                    "halo_overlap": not args.no_overlap, "cuda_graphs": not args.no_graphs,
                    "plane_split_substeps": int(st.split_substeps), "fused_pair_substeps": int(st.pair_substeps),
+                   "wavefront_pairs": bool(args.wavefront),
                    "l2": f"populations {19 * (4 if args.storage == 'f32' else 2) * cells_local / 1e6:.0f} MB per GPU > 126 MB L2, no flush needed"},
         "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
         "pct_of_hbm_roofline": (value / world) * bytes_per_update / 1e3 / peak * 100.0,
