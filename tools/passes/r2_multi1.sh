@@ -10,5 +10,5 @@ for wl in sphere_256x128x128 box_256; do
     timeout 300 $T bench.py --gpus 2 --workload $wl --steps 600 --warmup 100 --no-cpu-baseline $mode 2>&1 | tail -n 1 >> gpurun_out/wave_multi.log
   done
 done
-timeout 300 python -m pytest tests/test_multi_gpu.py -m gpu -x -q > gpurun_out/pytest_multi.log 2>&1; tail -n 2 gpurun_out/pytest_multi.log
+FG_TEST_EXPERIMENTS=1 timeout 400 python -m pytest tests/test_multi_gpu.py -m gpu -x -q > gpurun_out/pytest_multi.log 2>&1; tail -n 2 gpurun_out/pytest_multi.log
 python tools/summarize_bench.py gpurun_out/wave_multi.log
