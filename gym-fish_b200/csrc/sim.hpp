@@ -686,7 +686,15 @@ private:
         }
         if (zz_end <= zz_begin) return true;
         const int ny = L_.ny;
-        if (L_.solid || parity_ == 0) return launch_rows(CHECK_ALL, zz_begin, zz_end, 0, 1, ny, F, zstride, hole_b, hole_e, true);
+        if (L_.solid || parity_ == 0) return wave_rows_ == 2 ? true : launch_rows(CHECK_ALL, zz_begin, zz_end, 0, 1, ny, F, zstride, hole_b, hole_e, true);
+        // wave_pair's far chunks: the two y-wall rows of ALL far planes go in one launch at the end of the pair (wave_rows_
+        // 1: everything but them, 2: only them) instead of a tiny checked launch + fork + join per chunk
+        if (wave_rows_ && L_.wall_y && ny >= 2) {
+            if (wave_rows_ == 2) return launch_rows(CHECK_ALL, zz_begin, zz_end, 0, ny - 1, 2, F, zstride, hole_b, hole_e);
+            const int bulk_only = L_.wall_x ? ((cfg.flags & FG_FLAG_NO_XWARP) ? CHECK_XEDGE : CHECK_XWARP) : CHECK_NONE;
+            return launch_rows(bulk_only, zz_begin, zz_end, 1, 1, ny - 2, F, zstride, hole_b, hole_e, true);
+        }
+        if (wave_rows_ == 2) return true;
         const bool zlo_wall = L_.bc_zlo == BC_WALL && L_.z0 == 0, zhi_wall = L_.bc_zhi == BC_WALL && L_.z0 + L_.nz == L_.nzg;
         if (hole_e > hole_b && (zlo_wall || zhi_wall))   // wall planes are peeled off the ends below: keep that logic hole-free
             return launch_collide(zz_begin, hole_b, F) && launch_collide(hole_e, zz_end, F);
@@ -789,6 +797,13 @@ private:
         parity_ = keep;
         return ok;
     }
+    bool far_odd(int zb, int ze, int rows, int hole_b = 0, int hole_e = 0) {
+        const int keep = parity_;
+        parity_ = 1; wave_rows_ = rows;
+        const bool ok = launch_collide(zb, ze, ForceField{}, 1, hole_b, hole_e);
+        parity_ = keep; wave_rows_ = 0;
+        return ok;
+    }
     bool wave_pair(bool ib_on, bool graphs, int &rc) {
         const int lo = 1, hi = L_.nz + 1;
         const bool slab = cfg.n_ranks > 1;                                              // peered z-slab (the caller checked peers_)
@@ -868,7 +883,7 @@ private:
                 ok = ok && launch_collide_at(0, z, std::min(z + c, b), ForceField{});
                 if (k >= 1) {     // the even step now covers planes up to z + c: the chunk before takes its odd step
                     const int za = std::max(z - c, ra), zb = std::min(z, rb);
-                    if (zb > za) ok = ok && dev.switch_to(4) && dev.join_from(2) && launch_collide_at(1, za, zb, ForceField{});
+                    if (zb > za) ok = ok && dev.switch_to(4) && dev.join_from(2) && far_odd(za, zb, 1);
                 }
                 // the even step of the planes just above the bodies is queued: their own odd step need not wait for the rest
                 if (ok && r == 1 && !near_odd && std::min(z + c, b) > std::min(nb + 1, b - 1)) { if (!near_part2()) return true; }
@@ -876,10 +891,12 @@ private:
             // the last odd chunk of the range: the even step of the plane above it is a boundary plane or was queued before
             const int last = a + ((b - a - 1) / c) * c;                                 // first plane of the last chunk
             const int ta = std::max(b > a ? last : b, ra);
-            if (ok && rb > ta) ok = dev.switch_to(4) && dev.join_from(2) && launch_collide_at(1, ta, rb, ForceField{});
+            if (ok && rb > ta) ok = dev.switch_to(4) && dev.join_from(2) && far_odd(ta, rb, 1);
             if (ok && r == 0 && !near_even) { if (!near_part1()) return true; }
         }
         if (ok && !near_odd) { if (!near_part2()) return true; }
+        // the y-wall rows of every far plane, in one launch with a hole over the planes around the bodies
+        ok = ok && dev.switch_to(4) && dev.join_from(2) && far_odd(late_lo, late_hi, 2, ib_on ? oa : 0, ib_on ? ob : 0);
         ok = ok && dev.switch_to(0) && dev.join_from(2) && dev.join_from(4);
         // ---- C. slab ends: odd step of the late planes (they read the ghost planes: wrap / inlet / outlet data, or what the
         // z-neighbours pushed after THEIR even step), then the z-face operation of the odd step
@@ -981,6 +998,7 @@ private:
     int64_t collide_launches_ = 0, last_collide_launches_ = 0, collide_cells_ = 0, last_collide_cells_ = 0;
     int64_t split_substeps_ = 0, pair_substeps_ = 0, wave_substeps_ = 0;
     bool wave_ = false;            // inside wave_pair: chunk launches do not flip the sweep direction
+    int wave_rows_ = 0;            // inside wave_pair's far odd launches: 1 = without the y-wall rows, 2 = only the y-wall rows
     int *pair_ctr_ = nullptr;      // [1 + nz + 2] ticket + per-plane completion counters of StreamCollidePair
     bool split_ = false;           // this substep: far planes collide beside the IB kernels
     int near_a_ = 1, near_b_ = 1;  // planes [near_a_, near_b_) wait for the IB force
