@@ -6,7 +6,7 @@ B="python bench.py --steps 600 --warmup 100 --no-cpu-baseline"
 for wl in sphere_256x128x128 box_256 box_512; do
   echo "== $wl default" >> gpurun_out/wave.log
   timeout 200 $B --workload $wl 2>&1 | tail -n 1 >> gpurun_out/wave.log
-  for lag in 0 4 8 16 32; do
+  for lag in 0 8 11 16 21 32; do   # 126 bulk CTAs per plane, 1332 resident: 10.6 planes per wave
     echo "== $wl --wavefront --pair-lag $lag" >> gpurun_out/wave.log
     timeout 200 $B --workload $wl --wavefront --pair-lag $lag 2>&1 | tail -n 1 >> gpurun_out/wave.log
   done
