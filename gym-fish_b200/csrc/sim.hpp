@@ -787,8 +787,14 @@ private:
     // Returns false when the pair cannot be run this way (the caller steps normally); rc carries an error.
     int wave_chunk() const {
         if (cfg.pair_lag > 0) return cfg.pair_lag;
+        // ~20 MB of populations per chunk (three chunks in flight stay well inside the 126 MB L2), rounded to a whole number
+        // of waves of resident CTAs (148 SMs x 9) so that a chunk launch does not end on a half-empty wave
         const long long plane_bytes = (long long)kPopBytes * Q * L_.plane;
-        return int(std::max<long long>(1, std::min<long long>(64, (20ll << 20) / plane_bytes)));
+        const long long target = std::max<long long>(1, std::min<long long>(64, (20ll << 20) / plane_bytes));
+        const long long per_plane = (long long)((L_.nx + kCollideThreads - 1) / kCollideThreads) * std::max(1, L_.wall_y ? L_.ny - 2 : L_.ny);
+        const long long resident = 148 * 9;
+        const long long waves = std::max<long long>(1, (target * per_plane + resident / 2) / resident);
+        return int(std::max<long long>(1, std::min<long long>(64, waves * resident / per_plane)));
     }
     bool launch_collide_at(int parity, int zb, int ze, const ForceField &F) {
         const int keep = parity_;
