@@ -98,3 +98,14 @@ def test_python_example_runs_against_the_checker_library():
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "env steps/s" in r.stdout
+
+
+def test_prescribed_body_example_runs_against_the_checker_library():
+    """examples/prescribed_body.py: the caller's own integrator around fg_set_markers / fg_step / fg_get_link_wrenches."""
+    import os, subprocess, sys
+    import util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "examples", "prescribed_body.py"), "--small", "--lib", util.ORACLE_LIB, "--steps", "60"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "MLUPS end to end" in r.stdout
