@@ -656,6 +656,12 @@ public:
     // band cells own, so the collide of any cell outside the band may run beside the IB kernels; one plane of margin
     // is kept anyway.  Snapped outwards to multiples of 8 so that a slowly moving body keeps its launch geometry
     // (and CUDA graph) for many steps.
+    // the planes (local, ghost offset included) marker stencils touch, unsnapped; false: none, or wrapped around a periodic z
+    bool stencil_planes(int &zmin, int &zmax) const {
+        if (z_all_ || !z_any_ || zmax_ < zmin_) return false;
+        zmin = zmin_; zmax = zmax_;
+        return true;
+    }
     bool near_planes(int &za, int &zb) const {
         if (z_all_) return false;
         if (!z_any_ || zmax_ < zmin_) { za = zb = 1; return true; }   // no stencil on this slab: everything is far

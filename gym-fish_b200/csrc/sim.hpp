@@ -314,12 +314,7 @@ public:
         for (int it = 0; it < n; ++it) {
             if (!fish_.empty()) {
                 // A7 (1): bodies advance on the host with the wrenches of the previous substep
-                if (int rc = ib_.fetch_wrenches(dev, err)) return rc;
-                int lo = 0, ao = 0;
-                for (auto &f : fish_) {
-                    f.advance(&action_[ao], ib_.wrench_ptr() + 6 * lo, ib_.origin_ptr() + 3 * lo);
-                    lo += f.n_links(); ao += f.n_joints();
-                }
+                if (int rc = advance_bodies()) return rc;
             }
             // The device work of one substep is a fixed sequence for a given (parity, IB counter, staging buffer,
             // marker count, plane split): captured once into a CUDA graph and replayed afterwards (the host code below
@@ -343,7 +338,7 @@ public:
                 }
             }
             // Two substeps as a launch-level wavefront (wave_pair below): opt-in experiment.
-            if (!prof && (cfg.flags & FG_FLAG_WAVEFRONT) && parity_ == 0 && it + 1 < n && (!ranks || (peers_ && !ib_.exchange_on())) && fish_.empty() && L_.nz >= 8) {
+            if (!prof && (cfg.flags & FG_FLAG_WAVEFRONT) && parity_ == 0 && it + 1 < n && (!ranks || (peers_ && !ib_.exchange_on())) && L_.nz >= 8) {
                 int rc = FG_OK;
                 if (wave_pair(ib_on, graphs, rc)) {
                     if (rc != FG_OK) return rc;
@@ -442,6 +437,17 @@ public:
             if (int rc = ib_.fetch_wrenches(dev, err)) return rc;
         }
         if (ranks && !peers_) pending_faces_ = int(internal_lo()) + int(internal_hi());
+        return FG_OK;
+    }
+
+    // A7 (1): wait for the wrenches of the previous substep's IB pass, integrate every fish one substep on the host
+    int advance_bodies() {
+        if (int rc = ib_.fetch_wrenches(dev, err)) return rc;
+        int lo = 0, ao = 0;
+        for (auto &f : fish_) {
+            f.advance(&action_[ao], ib_.wrench_ptr() + 6 * lo, ib_.origin_ptr() + 3 * lo);
+            lo += f.n_links(); ao += f.n_joints();
+        }
         return FG_OK;
     }
 
@@ -820,10 +826,14 @@ private:
             int a, b;
             if (!ib_.near_planes(a, b)) return false;                                   // bodies everywhere: nothing is far
             na = std::min(std::max(a, lo), hi); nb = std::max(std::min(b, hi), na);
-            if (nb <= na) { na = hi; nb = hi; }
-            // bodies next to a slab end: their band cells read ghost planes at odd parity and their planes include the
-            // boundary planes, which here go first without a force — such pairs are stepped normally
-            else if (na <= lo || nb >= hi) return false;
+            if (nb <= na) { na = hi; nb = hi; }                                         // no stencil on this slab
+            else {
+                // fish move between the two IB passes of the pair (by less than a plane): one more plane on each side
+                if (!fish_.empty()) { na = std::max(na - 1, lo); nb = std::min(nb + 1, hi); }
+                // bodies next to a slab end: their band cells read ghost planes at odd parity and their planes include the
+                // boundary planes, which here go first without a force — such pairs are stepped normally
+                if (na <= lo || nb >= hi) return false;
+            }
         }
         if ((na - lo) + (hi - nb) < 6) return false;
         const int oa = std::max(na - 1, late_lo), ob = std::min(nb + 1, late_hi);       // odd step of [oa, ob) waits for IB(t+1)
@@ -835,7 +845,7 @@ private:
         // with the key of a plain substep, whose first word is < 4)
         GraphKey key = substep_key();
         key[0] = (key[0] & 0xffull) | (uint64_t(uint32_t(na)) << 8) | (uint64_t(uint32_t(nb)) << 36);
-        scope.on = graphs && dev.graph_begin(key);
+        scope.on = graphs && fish_.empty() && dev.graph_begin(key);     // with fish the host integrates in the middle of the pair
         wave_ = true;
         const int c = wave_chunk();
         bool ok = true;
@@ -862,9 +872,23 @@ private:
             near_even = true;
             if (!dev.switch_to(0)) return false;
             ib_.set_fused(false);
+            if (!fish_.empty() && (rc = upload_bodies()) != FG_OK) return false;
             if ((rc = ib_.compute_forces(dev, L_, C_, 0, err)) != FG_OK) return false;
             F0 = ib_.force_view();
             if (!launch_collide_at(0, na, nb, F0)) { rc = cuda_fail(); return false; }
+            if (!fish_.empty()) {
+                // the host round trip of the second substep — wrenches of IB(t) down, bodies advanced, markers up — happens
+                // here, while the far-plane wavefront queued above keeps the GPU busy
+                if ((rc = advance_bodies()) != FG_OK) return false;
+                emit_bodies();
+                int zmin, zmax;
+                // IB(t+1) reads and forces cells whose even step must be the one just queued on THIS stream
+                if (!ib_.stencil_planes(zmin, zmax) || zmin - 1 < na || zmax + 2 > nb) {
+                    rc = fail(FG_ESTATE, "a body moved more than a plane within one substep (FG_FLAG_WAVEFRONT)");
+                    return false;
+                }
+                if ((rc = upload_bodies()) != FG_OK) return false;
+            }
             if ((rc = ib_.compute_forces(dev, L_, C_, 1, err)) != FG_OK) return false;
             F1 = ib_.force_view();
             return true;

@@ -67,7 +67,7 @@ extern "C" {
 #define FG_FLAG_FUSED_PAIRS 64 /* even step + following odd step as ONE L2-resident wavefront launch (no bodies, one rank); halves DRAM traffic but measured slower on B200 (r1) */
 #define FG_FLAG_NO_XWARP 128   /* x walls: predicated wall selects in every thread (default: only the two warps at the row ends run the wall code) */
 #define FG_FLAG_SYNC_STEP 256  /* fg_step returns only when all its device work has finished (default: when wrenches / obs are there) */
-#define FG_FLAG_WAVEFRONT 512  /* EXPERIMENT (unmeasured): even step + following odd step as a launch-level wavefront of plane chunks on two streams, the odd step one chunk behind the even one, so that it finds its populations in L2 (one rank or peered z-slabs; prescribed markers inside a slab; no fish, no bodies across slab faces) */
+#define FG_FLAG_WAVEFRONT 512  /* EXPERIMENT (unmeasured): even step + following odd step as a launch-level wavefront of plane chunks on two streams, the odd step one chunk behind the even one, so that it finds its populations in L2 (one rank or peered z-slabs; prescribed markers or fish inside a slab — with fish the pair is launched directly, not as a graph; no bodies across slab faces) */
 #define FG_FLAG_NO_SPLIT  16   /* collide all planes after the IB kernels (default: planes away from the bodies run beside them) */
 
 typedef struct FgConfig {

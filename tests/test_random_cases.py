@@ -771,3 +771,49 @@ def test_random_wavefront_pairs_on_peered_slabs(g, emu):
             bad.append((seed, kw))
     assert not bad, bad[:3]
     assert with_waves >= 50
+
+
+def test_random_fish_in_wavefront_pairs_equal_plain_steps(g, emu):
+    """Fish inside FG_FLAG_WAVEFRONT pairs: the host round trip of the second substep (wrenches down, bodies advanced,
+    markers up) sits between the two IB passes on the main stream while the far-plane wavefront runs.  Observations,
+    wrenches and populations bit-identical to plain stepping."""
+    A = g._abi
+    P, Wl = g.BC_PERIODIC, g.BC_WALL
+    bad, ran, with_waves = [], 0, 0
+    for seed in range(16):
+        rng = np.random.default_rng(seed)
+        nx, ny, nz = int(rng.integers(16, 24)), int(rng.integers(14, 20)), int(rng.integers(56, 110))
+        kw = dict(nx=nx, ny=ny, nz=nz, tau=float(rng.uniform(0.65, 1.0)), collision=int(rng.integers(0, 2)),
+                  bc=[Wl] * 4 + [P] * 2 if rng.random() < 0.5 else [P] * 6, max_markers=6000, max_links=16,
+                  pair_lag=int(rng.integers(1, 9)) if rng.random() < 0.7 else 0)
+        a, b = g.Sim(backend=emu, flags=A.FLAG_NO_SPLIT, **kw), g.Sim(backend=emu, flags=A.FLAG_WAVEFRONT, **kw)
+        for f in range(int(rng.integers(1, 3))):
+            links = tuple((float(rng.uniform(4, 7)), float(rng.uniform(1.3, 2.3))) for _ in range(int(rng.integers(1, 5))))
+            d = util.fish_desc(g, root=(nx / 2 + rng.uniform(-2, 2), ny / 2, nz * (0.25 + 0.4 * f) + rng.uniform(-3, 3)), links=links,
+                               free=int(rng.random() < 0.7), heading=float(rng.uniform(-0.4, 0.4)))
+            d.joint_rate_max = float(rng.uniform(0.005, 0.03))
+            for s in (a, b):
+                s.add_fish(d)
+        same, ok = True, True
+        for it in range(5):
+            act, k = rng.uniform(-1, 1, a.action_size()).astype(np.float32), int(rng.integers(1, 8))
+            for s in (a, b):
+                s.set_action(act)
+                s.step(k)
+            oa, ob = a.get_obs(), b.get_obs()
+            if not np.isfinite(oa).all():
+                ok = False
+                break
+            same = same and np.array_equal(oa, ob) and np.array_equal(a.get_link_wrenches(), b.get_link_wrenches())
+            if it == 2 and rng.random() < 0.3:
+                for s in (a, b):
+                    s.reset(0)
+        if ok:
+            ran += 1
+            with_waves += b.stats().pair_substeps > 0
+            if not (same and np.array_equal(a.get_populations(), b.get_populations())):
+                bad.append((seed, kw))
+        a.close()
+        b.close()
+    assert not bad, bad[:3]
+    assert ran >= 12 and with_waves >= 10

@@ -3,7 +3,7 @@
 # then one ncu capture of DRAM bytes per launch for the best chunk size (the point of the wavefront is traffic < 152 B/update).
 mkdir -p gpurun_out
 B="python bench.py --steps 600 --warmup 100 --no-cpu-baseline"
-for wl in sphere_256x128x128 box_256 box_512; do
+for wl in sphere_256x128x128 box_256 box_512 tank_512x256x256; do
   echo "== $wl default" >> gpurun_out/wave.log
   timeout 200 $B --workload $wl 2>&1 | tail -n 1 >> gpurun_out/wave.log
   for lag in 0 8 11 16 21 32; do   # 126 bulk CTAs per plane, 1332 resident: 10.6 planes per wave
