@@ -867,22 +867,28 @@ private:
         // main stream beside them: IB(t) -> even, IB(t+1), then their odd step as soon as the even step of the planes
         // next to them is queued
         ForceField F0{}, F1{};
-        bool near_even = !ib_on, near_odd = !ib_on;
-        auto near_part1 = [&]() -> bool {
-            near_even = true;
-            if (!dev.switch_to(0)) return false;
+        bool near_forces = !ib_on, near_odd = !ib_on;
+        const bool with_fish = !fish_.empty();
+        // IB(t) and the even step of the planes around the bodies: queued before the far chunks, so that the wrenches of
+        // this substep are on their way to the host as early as possible
+        if (ok && ib_on) {
+            ok = dev.switch_to(0);
             ib_.set_fused(false);
-            if (!fish_.empty() && (rc = upload_bodies()) != FG_OK) return false;
-            if ((rc = ib_.compute_forces(dev, L_, C_, 0, err)) != FG_OK) return false;
+            if (with_fish && (rc = upload_bodies()) != FG_OK) return true;
+            if ((rc = ib_.compute_forces(dev, L_, C_, 0, err)) != FG_OK) return true;
             F0 = ib_.force_view();
-            if (!launch_collide_at(0, na, nb, F0)) { rc = cuda_fail(); return false; }
-            if (!fish_.empty()) {
-                // the host round trip of the second substep — wrenches of IB(t) down, bodies advanced, markers up — happens
-                // here, while the far-plane wavefront queued above keeps the GPU busy
+            ok = ok && launch_collide_at(0, na, nb, F0);
+        }
+        // IB(t+1).  With fish this holds the host round trip of the second substep — wrenches of IB(t) down, bodies advanced,
+        // markers up — and is therefore called only after every far chunk is queued: the GPU works through them meanwhile.
+        auto near_forces_next = [&]() -> bool {
+            near_forces = true;
+            if (!dev.switch_to(0)) { rc = cuda_fail(); return false; }
+            if (with_fish) {
                 if ((rc = advance_bodies()) != FG_OK) return false;
                 emit_bodies();
                 int zmin, zmax;
-                // IB(t+1) reads and forces cells whose even step must be the one just queued on THIS stream
+                // IB(t+1) reads and forces cells whose even step must be the one queued on THIS stream above
                 if (!ib_.stencil_planes(zmin, zmax) || zmin - 1 < na || zmax + 2 > nb) {
                     rc = fail(FG_ESTATE, "a body moved more than a plane within one substep (FG_FLAG_WAVEFRONT)");
                     return false;
@@ -899,6 +905,7 @@ private:
             if (ob > oa && !launch_collide_at(1, oa, ob, F1)) { rc = cuda_fail(); return false; }
             return true;
         };
+        if (ok && ib_on && !with_fish && !near_forces_next()) return true;
         const int far[2][2] = {{lo + 1, std::min(na, hi - 1)}, {std::max(nb, lo + 1), hi - 1}};
         for (int r = 0; r < 2 && ok; ++r) {
             const int a = far[r][0], b = far[r][1];
@@ -916,14 +923,14 @@ private:
                     if (zb > za) ok = ok && dev.switch_to(4) && dev.join_from(2) && far_odd(za, zb, 1);
                 }
                 // the even step of the planes just above the bodies is queued: their own odd step need not wait for the rest
-                if (ok && r == 1 && !near_odd && std::min(z + c, b) > std::min(nb + 1, b - 1)) { if (!near_part2()) return true; }
+                if (ok && r == 1 && near_forces && !near_odd && std::min(z + c, b) > std::min(nb + 1, b - 1)) { if (!near_part2()) return true; }
             }
             // the last odd chunk of the range: the even step of the plane above it is a boundary plane or was queued before
             const int last = a + ((b - a - 1) / c) * c;                                 // first plane of the last chunk
             const int ta = std::max(b > a ? last : b, ra);
             if (ok && rb > ta) ok = dev.switch_to(4) && dev.join_from(2) && far_odd(ta, rb, 1);
-            if (ok && r == 0 && !near_even) { if (!near_part1()) return true; }
         }
+        if (ok && !near_forces) { if (!near_forces_next()) return true; }
         if (ok && !near_odd) { if (!near_part2()) return true; }
         // the y-wall rows of every far plane, in one launch with a hole over the planes around the bodies
         ok = ok && dev.switch_to(4) && dev.join_from(2) && far_odd(late_lo, late_hi, 2, ib_on ? oa : 0, ib_on ? ob : 0);
