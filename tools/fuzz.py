@@ -1,0 +1,55 @@
+#!/usr/bin/env python
+"""Run the randomised test generators of tests/test_random_cases.py over any seed range (CPU emulation by default).
+
+    python tools/fuzz.py static 0 2000                  # random configurations vs the oracle
+    python tools/fuzz.py moving|fish|api|slabs|xslabs|wavefront|wavefront_slabs 0 500
+    FG_EMU_SCHED=rand:3 FG_EMU_GRAPHS=1 python tools/fuzz.py wavefront 0 500     # queued streams, emulated graphs
+    python tools/fuzz.py static 0 500 --lib cuda        # the real library on a GPU box
+
+Prints the seeds that fail; the committed tests run fixed ranges of the same generators."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import gym_fish_b200 as g  # noqa: E402
+import test_random_cases as t  # noqa: E402
+import util  # noqa: E402
+
+util.register_oracle(g)
+kind, lo, hi = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+lib = sys.argv[sys.argv.index("--lib") + 1] if "--lib" in sys.argv else os.path.join(ROOT, "tests", "emu", "libfishgym_emu.so")
+exact = lib != "cuda"
+bad, ran = [], 0
+for seed in range(lo, hi):
+    if kind == "static":
+        w, kw = t.run_case(g, lib, seed)
+        ok = None if w is None else all(w[k] <= t.LIMITS[k] for k in w)
+    elif kind == "moving":
+        w, kw, _, _ = t.run_moving_markers_case(g, lib, seed)
+        ok = None if w is None else all(w[k] <= dict(t.LIMITS, probe=5e-6)[k] for k in w)
+    elif kind == "fish":
+        w, kw = t.run_fish_case(g, lib, seed)
+        ok = None if w is None else (w["obs"] <= 1e-4 and w["wrench"] <= 1e-4 and w["u"] <= 1e-5)
+    elif kind == "api":
+        w = t.run_api_sequence_case(g, lib, seed)
+        ok, kw = (None if w is None else w <= 2e-5), None
+    elif kind == "slabs":
+        ok, kw = t.run_slab_case(g, lib, seed)
+    elif kind == "xslabs":
+        w, kw, _ = t.run_bodies_across_slabs_case(g, lib, seed)
+        ok = None if w is None else (w["f"] <= 1e-6 and w["wrench"] <= 1e-4)
+    elif kind == "wavefront":
+        ok, _, kw = t.run_wavefront_case(g, lib, seed, exact=exact)
+    elif kind == "wavefront_slabs":
+        ok, _, kw = t.run_wavefront_slab_case(g, lib, seed)
+    else:
+        raise SystemExit(__doc__)
+    if ok is None:
+        continue
+    ran += 1
+    if not ok:
+        bad.append(seed)
+        print("SEED", seed, "FAILS", kw, flush=True)
+print(f"{kind}: {ran} stable cases in [{lo}, {hi}), {len(bad)} failing: {bad[:20]}")
