@@ -935,9 +935,10 @@ private:
         // the y-wall rows of every far plane, in one launch with a hole over the planes around the bodies
         ok = ok && dev.switch_to(4) && dev.join_from(2) && far_odd(late_lo, late_hi, 2, ib_on ? oa : 0, ib_on ? ob : 0);
         ok = ok && dev.switch_to(0) && dev.join_from(2);
-        // ---- C. slab ends (beside the last odd chunks, which touch neither the late planes' own locations nor the slots of
-        // the boundary planes the z-face operation writes): odd step of the late planes (they read the ghost planes: wrap / inlet / outlet data, or what the
-        // z-neighbours pushed after THEIR even step), then the z-face operation of the odd step
+        // ---- C. slab ends, beside the last odd chunks (which touch neither the late planes' own locations nor the slots of
+        // the boundary planes the z-face operation writes): odd step of the late planes — they read the ghost planes, i.e.
+        // wrap / inlet / outlet data or what the z-neighbours pushed after THEIR even step — then the z-face operation of
+        // the odd step
         if (slab) ok = ok && dev.wait_flags(flags_, has_lo_peer(), has_hi_peer());
         parity_ = 1;
         ok = ok && launch_collide(lo, std::min(late_lo, hi), F1) && launch_collide(std::max(late_hi, late_lo), hi, F1) && launch_faces();
