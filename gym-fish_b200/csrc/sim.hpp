@@ -88,6 +88,7 @@ public:
         InitParams p{L_, nullptr, nullptr};
         if (!dev.template launch<InitEquilibrium>(grid_planes(L_.nz + 2), p)) return cuda_fail();
         parity_ = 0; steps_ = 0;
+        pending_faces_ = 0;     // the ghost planes were rebuilt: no halo of an earlier step is owed any more
         for (auto &f : fish_) f.reset();
         std::fill(action_.begin(), action_.end(), 0.f);
         if (!fish_.empty()) {
@@ -109,6 +110,7 @@ public:
         dev.free(d);
         if (!ok) return cuda_fail();
         parity_ = 0;
+        pending_faces_ = 0;
         return FG_OK;
     }
 
@@ -150,6 +152,7 @@ public:
             if (!dev.h2d(L_.f + i * L_.slot + L_.plane, h.data(), n * sizeof(pop_t))) return cuda_fail();
         }
         parity_ = 0;
+        pending_faces_ = 0;
         return FG_OK;
     }
 
@@ -579,6 +582,10 @@ public:
         if (cfg.n_ranks < 2) return fail(FG_ESTATE, "fg_peer_connect_all needs n_ranks > 1");
         if (n != cfg.n_ranks) return fail(FG_EINVAL, "pass one handle per rank");
         if (n > kMaxRanks) return fail(FG_ENOTSUP, "at most 8 ranks");
+        // the marker message on the device was packed WITHOUT the culled layout of the exchange (no global-id column):
+        // reading it with the other layout would silently mis-assign link origins and drop markers
+        if (ib_.ready() && !ib_.exchange_on() && ib_.n_local() > 0)
+            return fail(FG_ESTATE, "fg_peer_connect_all: call before fg_set_markers / fg_add_fish (the marker set must be sent again after connecting)");
         const int lo = (cfg.rank - 1 + n) % n, hi = (cfg.rank + 1) % n;
         if (int rc = peer_connect(internal_lo() ? hs + lo : nullptr, internal_hi() ? hs + hi : nullptr)) return rc;
         if (!ib_.ready()) return FG_OK;

@@ -25,9 +25,17 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
 
 
+_MADE = set()
+
+
 def _ensure(path, directory):
-    if not os.path.exists(path):
-        subprocess.run(["make", "-C", os.path.join(ROOT, directory)], check=True, stdout=subprocess.DEVNULL)
+    """Always `make` (once per session and directory): the Makefiles track header dependencies, so this is a no-op when
+    the library is current and a rebuild when a header was edited after the (git-ignored) binary was built."""
+    if directory not in _MADE:
+        _MADE.add(directory)
+        r = subprocess.run(["make", "-C", os.path.join(ROOT, directory)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0 and not os.path.exists(path):
+            raise RuntimeError(f"make -C {directory} failed:\n{r.stdout[-3000:]}")
     return path
 
 
@@ -52,6 +60,7 @@ def emu_f16(g):
 
 @pytest.fixture(scope="session")
 def cuda_f16(g):
+    _ensure(g._abi.LIB_PATHS["cuda_f16"], "gym-fish_b200/csrc")
     g.load_library("cuda_f16")
     return "cuda_f16"
 
@@ -59,5 +68,6 @@ def cuda_f16(g):
 @pytest.fixture(scope="session")
 def cuda(g):
     """Backend name for GPU tests; fails (not skips) if the library is missing."""
+    _ensure(g._abi.LIB_PATHS["cuda"], "gym-fish_b200/csrc")
     g.load_library("cuda")
     return "cuda"

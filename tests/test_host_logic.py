@@ -79,3 +79,49 @@ def test_call_timing_is_reported_once_the_call_has_finished(g, emu):
     s2 = _sim(g, emu, flags=g._abi.FLAG_SYNC_STEP)
     s2.step(1)
     assert s2.stats().last_step_ms > 0
+
+
+@pytest.mark.parametrize("backend", ["oracle", "emu"])
+@pytest.mark.parametrize("how", ["reset", "set_fields", "set_populations"])
+def test_reset_clears_an_owed_halo_exchange(g, emu, backend, how):
+    """Host-staged z-slabs: fg_step(1) leaves a halo exchange owed.  fg_reset / fg_set_fields / fg_set_populations rebuild
+    the ghost planes, so the handle must be steppable again afterwards — same behaviour on the oracle and the product."""
+    lib = emu if backend == "emu" else "oracle"
+    kw = dict(nx=8, ny=6, nz=8, tau=0.8)
+    parts = [g.Sim(backend=lib, n_ranks=2, rank=r, **kw) for r in range(2)]
+    for s in parts:
+        s.step(1)
+        with pytest.raises(g.FgError):           # the exchange is owed: stepping on is refused
+            s.step(1)
+        if how == "reset":
+            s.reset()
+        elif how == "set_fields":
+            s.set_fields(np.ones(s.shape, np.float32), np.zeros((3,) + s.shape, np.float32))
+        else:
+            s.set_populations(np.broadcast_to(g._abi.W[:, None, None, None], (19,) + s.shape).astype(np.float32))
+        s.step(1)                                # accepted again
+    # and the protocol still works from here: exchange, step
+    msgs = [(s.halo_pack(g._abi.ZLO), s.halo_pack(g._abi.ZHI)) for s in parts]
+    parts[0].halo_unpack(g._abi.ZHI, msgs[1][0]); parts[0].halo_unpack(g._abi.ZLO, msgs[1][1])
+    parts[1].halo_unpack(g._abi.ZLO, msgs[0][1]); parts[1].halo_unpack(g._abi.ZHI, msgs[0][0])
+    for s in parts:
+        s.step(1)
+
+
+def test_peer_connect_all_after_set_markers_is_refused(g, emu):
+    """The marker message on the device has another layout once bodies may cross slab faces (a global-id column): a marker
+    set sent BEFORE fg_peer_connect_all would be read with the wrong layout, so the call is refused."""
+    kw = dict(nx=16, ny=14, nz=24, tau=0.8, max_markers=600, max_links=2)
+    parts = [g.Sim(backend=emu, n_ranks=2, rank=r, **kw) for r in range(2)]
+    handles = [s.peer_export() for s in parts]
+    X = util.sphere_markers((8.2, 7.1, 5.5), 2.0, 60)         # inside slab 0: accepted without the exchange
+    parts[0].set_markers(X, np.zeros_like(X), np.ones(60, np.float32))
+    with pytest.raises(g.FgError) as e:
+        parts[0].peer_connect_all(handles)
+    assert e.value.code == g._abi.FG_ESTATE
+    parts[0].set_markers(X[:0], X[:0], np.ones(0, np.float32))   # withdrawn: connecting works, then the set is sent again
+    parts[0].peer_connect_all(handles)
+    parts[1].peer_connect_all(handles)
+    for s in parts:
+        s.set_markers(X, np.zeros_like(X), np.ones(60, np.float32))
+        s.set_link_origins([[8.2, 7.1, 5.5]])
