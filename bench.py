@@ -4,16 +4,21 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
 
 A "step" is one lattice update of the whole domain (fused D3Q19 MRT stream-collide + immersed-boundary coupling +
-z-face operations).  Workload at N=1 is BASELINE.json configs[1]: MRT flow past a fixed sphere in a 256x128x128
-channel (z = flow axis, inlet/outlet on z, walls on y), the sphere an immersed boundary of ~1.8k markers.  At N>1
-every rank owns one such 256x128x128 slab with its own sphere (weak scaling, z-slab decomposition, halos pushed
-over NVLink by the library itself; torch.distributed is used only to exchange the 320-byte peer handles, for the
-barriers and for the max over ranks).
+z-face operations).  The default workload is the one BASELINE.json quotes the metric on: 512^3 cells PER GPU (configs[4],
+the weak-scaling sweep; a periodic box, z-slabs across the ranks, halos pushed over NVLink by the library itself —
+torch.distributed is used only to exchange the 320-byte peer handles, for the barriers and for the max over ranks).
 
-Printed JSON line: see the contract in the task statement; `value` is device-timed with inputs resident in HBM,
-`e2e` goes through the C ABI with host buffers (markers up, link wrenches down, every step), `roofline` is the
-stream-collide kernel alone (CUDA events around each launch, on the library's stream), `cpu_baseline` is the fp64
-OpenMP oracle on this box's host cores.
+The same JSON line carries sub-records for the other headline configurations (own sims, timed the same way):
+  N = 1   ib_overhead   512^3 + 1e5 immersed-boundary markers, static and re-sent every step (target: <= 15 % step time)
+          env           512x256x256 tank with one 5-link fish, Gym loop of 20 substeps  -> env steps / s (configs[2])
+          sphere        256x128x128 channel with a fixed IB sphere (configs[1], the round-1 default, kept for continuity)
+  N > 1   overlap_off   the same slabs with the halo push after the full-slab kernel (configs[4] "overlap on vs off")
+          sphere        one 256x128x128 sphere channel per GPU (latency-dominated weak scaling)
+          parity_vs_1gpu  a small box split over the N GPUs is bit-identical to the same box on rank 0's GPU alone
+
+Printed JSON line: see the contract in the task statement; `value` is device-timed with inputs resident in HBM, `e2e`
+goes through the C ABI with host buffers every step, `roofline` is the stream-collide kernel alone (CUDA events around
+each launch, on the library's stream), `cpu_baseline` is the fp64 OpenMP oracle on this box's host cores.
 """
 from __future__ import annotations
 
@@ -24,6 +29,7 @@ import statistics
 import subprocess
 import sys
 import tempfile
+import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -32,6 +38,8 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 BYTES_PER_CELL_UPDATE = 152.0   # 19 populations x 4 B x (read + write), SURVEY.md §8(d)
+METRIC = "MLUPS (million lattice-cell updates per second), coupled D3Q19 MRT + IB step"
+DEFAULT_WORKLOAD = "box_512"
 
 WORKLOADS = {
     # name: (nx, ny, nz per GPU, sphere diameter, description)
@@ -49,6 +57,11 @@ WORKLOADS = {
     "tank_512x256x256": dict(nx=256, ny=256, nz=512, D=0.0, U=0.0, Re=0.0,
                              desc="D3Q19 MRT tank 512x256x256 (z swim axis) with one 5-link fish, Gym substeps"),
 }
+# FG_BENCH_SHRINK=k divides every axis of every workload by k: DRY RUNS of this script on a machine without a GPU (with
+# FG_CUDA_LIB pointing at the CPU emulation of the kernels); such a line says so ("dry_run_shrink") and is not a measurement
+SHRINK = int(os.environ.get("FG_BENCH_SHRINK", "1"))
+PERIODIC_Z = ("box_512", "box_256", "box_512_ib", "tank_512x256x256", "school_1024x512x512")
+FISH_LINKS = [(28, 7), (24, 7), (22, 6), (20, 5), (18, 3.5)]
 
 
 def sphere_markers(center, radius, n):
@@ -60,32 +73,45 @@ def sphere_markers(center, radius, n):
     return X.astype(np.float32)
 
 
-def make_sim(g, backend, wl, rank, world, device, flags=0, nz_override=None, extra=None):
-    """Create one slab of the workload and put it in its initial state."""
+def fish_desc(g, root, scale=1.0):
+    """The 5-link swimmer of BASELINE.json configs[2] (~2k markers); `scale` shrinks it with a reduced tank (tests)."""
+    d = g.FgFishDesc()
+    d.n_links = len(FISH_LINKS)
+    for k, (length, rad) in enumerate(FISH_LINKS):
+        d.link_len[k], d.link_rad[k] = length * scale, rad * scale
+    d.root_pos[0], d.root_pos[1], d.root_pos[2] = root
+    d.density_ratio, d.joint_gain, d.joint_limit, d.joint_rate_max, d.free_root = 1.0, 0.2, 0.5, 0.01, 1
+    return d
+
+
+def make_sim(g, backend, wl, rank, world, device, flags=0, nz_override=None, extra=None, shrink=SHRINK):
+    """Create one slab of the workload and put it in its initial state.  `shrink` divides every axis (and the bodies) —
+    the parity tests run reduced copies of the same set-up through the CPU emulation."""
     w = WORKLOADS[wl]
-    nzl = nz_override or (w["nz"] // world if w.get("strong") else w["nz"])
-    kw = dict(nx=w["nx"], ny=w["ny"], nz=nzl * world, n_ranks=world, rank=rank, device=device, collision=g.MRT, flags=flags)
+    nx, ny = w["nx"] // shrink, w["ny"] // shrink
+    nzl = nz_override or ((w["nz"] // world if w.get("strong") else w["nz"]) // shrink)
+    kw = dict(nx=nx, ny=ny, nz=nzl * world, n_ranks=world, rank=rank, device=device, collision=g.MRT, flags=flags)
     kw.update(extra or {})
     markers = None
     if wl == "sphere_256x128x128":
         nu = w["U"] * w["D"] / w["Re"]
         kw.update(tau=3 * nu + 0.5, bc=[g.BC_PERIODIC, g.BC_PERIODIC, g.BC_WALL, g.BC_WALL, g.BC_INLET, g.BC_OUTLET],
                   inlet_u=[0, 0, w["U"]], max_markers=4096, max_links=2)
-        R = w["D"] / 2
+        R = w["D"] / 2 / shrink
         n = int(round(4 * np.pi * R * R))
-        zc = rank * nzl + min(64.0, nzl / 4.0) + 0.37
-        X = sphere_markers((w["nx"] / 2 + 0.21, w["ny"] / 2 + 0.13, zc), R, n)
+        zc = rank * nzl + min(64.0 / shrink, nzl / 4.0) + 0.37
+        X = sphere_markers((nx / 2 + 0.21, ny / 2 + 0.13, zc), R, n)
         markers = (X, np.zeros_like(X), np.full(n, 4 * np.pi * R * R / n, np.float32), np.zeros(n, np.int32),
-                   np.array([[w["nx"] / 2 + 0.21, w["ny"] / 2 + 0.13, zc]]))
+                   np.array([[nx / 2 + 0.21, ny / 2 + 0.13, zc]]))
     elif wl in ("box_512", "box_256"):
         kw.update(tau=0.6)
     elif wl == "box_512_ib":
         kw.update(tau=0.6, max_markers=110000, max_links=64)
-        R = w["D"] / 2
+        R = w["D"] / 2 / shrink
         n1 = int(round(4 * np.pi * R * R))
         Xs, links, origins = [], [], []
         for s_ in range(64):
-            c = (64.3 + 128 * (s_ % 4), 64.1 + 128 * ((s_ // 4) % 4), rank * nzl + 64.2 + 128 * (s_ // 16))
+            c = ((64.3 + 128 * (s_ % 4)) / shrink, (64.1 + 128 * ((s_ // 4) % 4)) / shrink, rank * nzl + (64.2 + 128 * (s_ // 16)) / shrink)
             Xs.append(sphere_markers(c, R, n1)); links.append(np.full(n1, s_, np.int32)); origins.append(c)
         X = np.concatenate(Xs)
         markers = (X, np.zeros_like(X), np.full(len(X), 4 * np.pi * R * R / n1, np.float32), np.concatenate(links), np.array(origins))
@@ -98,8 +124,9 @@ def make_sim(g, backend, wl, rank, world, device, flags=0, nz_override=None, ext
     shape = sim.shape
     rng = np.random.default_rng(1234 + rank)
     rho = np.ones(shape, np.float32)
-    u = (1e-3 * rng.standard_normal((3,) + shape)).astype(np.float32)
-    u[2] += w["U"]
+    u = rng.standard_normal((3,) + shape, dtype=np.float32)
+    u *= np.float32(1e-3)
+    u[2] += np.float32(w["U"])
     sim.set_fields(rho, u)
     del rho, u
     if markers is not None:
@@ -108,57 +135,108 @@ def make_sim(g, backend, wl, rank, world, device, flags=0, nz_override=None, ext
     elif wl == "school_1024x512x512":
         sim._school = True      # fish are added after the ranks are connected (they cross slab faces)
     elif wl == "tank_512x256x256" and rank == 0:
-        d = g.FgFishDesc()
-        d.n_links = 5
-        for k, (length, rad) in enumerate([(28, 7), (24, 7), (22, 6), (20, 5), (18, 3.5)]):
-            d.link_len[k], d.link_rad[k] = length, rad
-        d.root_pos[0], d.root_pos[1], d.root_pos[2] = w["nx"] / 2, w["ny"] / 2, nzl / 3
-        d.density_ratio, d.joint_gain, d.joint_limit, d.joint_rate_max, d.free_root = 1.0, 0.2, 0.5, 0.01, 1
-        sim.add_fish(d)
+        sim.add_fish(fish_desc(g, (nx / 2, ny / 2, nzl / 3), 1.0 / shrink))
     return sim, markers
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and clock-event reasons sampled DURING the run (B200_PROFILING.md recipe) — through NVML from a thread of
+    this process (every ~2 ms; ctypes releases the GIL while fg_step / fg_sync run), so that even a timed region of a few
+    milliseconds gets its own samples; `nvidia-smi -lms` (the round-1 sampler) needs ~100 ms before its first line.
+    window(t0, t1) marks the timed region; samples outside it (warm-up, the profiled pass: same load) are reported apart."""
 
-    def __init__(self, device):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+    def __init__(self, device, period_s=0.002):
+        self.samples = []          # (t, sm_mhz, reasons bitmask, power_w)
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+        self._nv = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--id={device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
-        except OSError:
-            self.p = None
+            import pynvml
+            pynvml.nvmlInit()
+            idx = device
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    idx = int(vis.split(",")[device])
+                except (ValueError, IndexError):
+                    idx = device
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self._nv = pynvml
+        except Exception:       # noqa: BLE001 — no NVML: fall back to one nvidia-smi query at stop()
+            self._nv = None
+            return
+        self._period = period_s
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
 
-    def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.p is None:
-            return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        sm, mx, reasons = [], [], set()
-        for line in self.f.read().splitlines():
-            c = [x.strip() for x in line.split(",")]
-            if len(c) < 9:
-                continue
+    def _run(self):
+        nv, h = self._nv, self._h
+        while not self._stop.is_set():
             try:
-                sm.append(float(c[1]))
-                mx.append(float(c[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        self.f.close()
-        os.unlink(self.f.name)
-        if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+                mhz = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:   # noqa: BLE001
+                    rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                self.samples.append((time.perf_counter(), mhz, rs, pw))
+            except Exception:       # noqa: BLE001
+                pass
+            self._stop.wait(self._period)
+
+    def sample_now(self):
+        """One synchronous sample (called by the timing code while the GPU is under load)."""
+        if self._nv is None:
+            return
+        nv, h = self._nv, self._h
+        try:
+            self.samples.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)),
+                                 int(nv.nvmlDeviceGetCurrentClocksEventReasons(h)), nv.nvmlDeviceGetPowerUsage(h) / 1000.0))
+        except Exception:           # noqa: BLE001
+            pass
+
+    def stop(self, t0=None, t1=None):
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0, "source": "NVML, sampled from a thread of this process"}
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=2)
+        if self._nv is None:
+            return self._smi_once(out)
+        nv = self._nv
+        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap,
+                 "hw_power_brake": nv.nvmlClocksEventReasonHwPowerBrakeSlowdown}
+        inside = [s for s in self.samples if t0 is not None and t0 <= s[0] <= t1]
+        # under load = power well above idle or inside the timed region
+        use = inside if inside else [s for s in self.samples if s[3] > 300.0] or self.samples
+        if use:
+            out["sm_mhz"] = statistics.median(s[1] for s in use)
+            out["sm_mhz_min"] = min(s[1] for s in use)
+            out["power_w_max"] = max(s[3] for s in use)
+            seen = 0
+            for s in use:
+                seen |= s[2]
+            out["reasons"] = sorted(k for k, bit in names.items() if seen & bit)
+        out["samples"] = len(use)
+        out["samples_in_timed_region"] = len(inside)
+        out["samples_total"] = len(self.samples)
+        out["window"] = "timed region" if inside else "samples under load around the timed region (warm-up / profiled pass)"
+        return out
+
+    @staticmethod
+    def _smi_once(out):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            r = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=20)
+            c = [x.strip() for x in r.stdout.splitlines()[0].split(",")]
+            out.update(sm_mhz=float(c[0]), sm_max_mhz=float(c[1]), samples=1, source="nvidia-smi, one query after the timed region",
+                       reasons=[n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[2:6])
+                                if v.lower().startswith("active")])
+        except Exception:           # noqa: BLE001
+            pass
         return out
 
 
@@ -167,9 +245,18 @@ def measured_peak():
     if os.path.exists(p):
         try:
             return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-        except Exception:
+        except Exception:           # noqa: BLE001
             pass
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def base_config(wl, world):
+    """What names the workload — the same keys and values in the b200 and the reference arm."""
+    w = WORKLOADS[wl]
+    nz_local = w["nz"] // world if w.get("strong") else w["nz"]
+    cells_local = w["nx"] * w["ny"] * nz_local
+    return {"workload": w["desc"], "name": wl, "grid_per_gpu_xyz": [w["nx"], w["ny"], nz_local], "gpus": world,
+            "l2": f"populations {19 * 4 * cells_local / 1e6:.0f} MB per GPU (fp32) vs 126 MB L2: inputs larger than L2, no flush between steps"}
 
 
 def cpu_oracle_mlups(g, wl, seconds=15.0, steps=None, warmup=1, nz_sample=None):
@@ -178,7 +265,7 @@ def cpu_oracle_mlups(g, wl, seconds=15.0, steps=None, warmup=1, nz_sample=None):
     w = WORKLOADS[wl]
     nzl = nz_sample or w["nz"]
     sim, _ = make_sim(g, "oracle", wl, 0, 1, 0, nz_override=nzl)
-    cells = w["nx"] * w["ny"] * nzl
+    cells = sim.nx * sim.ny * sim.nz
     for _ in range(warmup):
         sim.step(1)
     t0 = time.perf_counter()
@@ -189,36 +276,46 @@ def cpu_oracle_mlups(g, wl, seconds=15.0, steps=None, warmup=1, nz_sample=None):
     sim.step(n)
     dt = time.perf_counter() - t0
     sim.close()
-    return cells * n / dt / 1e6, cores, f"{n} steps of {w['nx']}x{w['ny']}x{nzl} ({wl}), fp64 two-lattice OpenMP oracle, {cores} threads", dt / n * 1e3
+    return cells * n / dt / 1e6, cores, f"{n} steps of {sim.nx}x{sim.ny}x{sim.nz} ({wl}), fp64 two-lattice OpenMP oracle, {cores} threads", dt / n * 1e3
+
+
+def oracle_sample_nz(wl, per_plane_ms, n_steps, budget_s):
+    """Height of the slab of `wl` the oracle can step n_steps times within budget_s (and within ~10 GB of host memory)."""
+    w = WORKLOADS[wl]
+    nz = int(min(w["nz"], max(16, budget_s * 1e3 / max(n_steps, 1) / max(per_plane_ms, 1e-9))))
+    nz = min(nz, max(16, (1 << 25) // (w["nx"] * w["ny"])))      # two fp64 lattices: 304 B per cell
+    return max(16, nz - nz % 8)
 
 
 def run_reference(args, g, rank, world):
     """--impl reference: the reference's own CPU implementation of the path.  The reference checkout ships no code
-    (README only), so this is the from-scratch fp64 oracle (BASELINE.json north_star (2)); rank 0 alone runs it."""
+    (README only), so this is the from-scratch fp64 oracle (BASELINE.json north_star (2)); rank 0 alone runs it.
+    Warm-up is at least 20 steps: the first steps of a fresh oracle run ~1.5x slower (first-touch page placement of
+    its two lattices, OpenMP team start-up), which under-reported this arm in round 1."""
     if rank != 0:
         return
     wl = args.workload
     w = WORKLOADS[wl]
+    warm = max(args.warmup, 20)
     # bound the sample so that steps+warmup finish within a few minutes: probe speed on a thin slab first
-    probe, cores, _, ms = cpu_oracle_mlups(g, wl, steps=2, warmup=1, nz_sample=16)
-    budget_s = 150.0
-    per_plane_ms = ms / 16
-    nz = int(min(w["nz"], max(16, budget_s * 1e3 / max(args.steps + args.warmup, 1) / per_plane_ms)))
-    nz = max(16, nz - nz % 8)
+    _, cores, _, ms = cpu_oracle_mlups(g, wl, steps=2, warmup=1, nz_sample=16)
+    nz = oracle_sample_nz(wl, ms / 16, args.steps + warm, args.ref_budget_s)
     sim, _ = make_sim(g, "oracle", wl, 0, 1, 0, nz_override=nz)
-    cells = w["nx"] * w["ny"] * nz
-    sim.step(args.warmup)
+    cells = sim.nx * sim.ny * sim.nz
+    sim.step(warm)
     t0 = time.perf_counter()
     sim.step(args.steps)
     dt = time.perf_counter() - t0
     v = cells * args.steps / dt / 1e6
-    sample = f"{args.steps} steps of {w['nx']}x{w['ny']}x{nz} ({wl}; the full workload has nz={w['nz']}), fp64 OpenMP oracle, {cores} threads"
+    sample = (f"{args.steps} steps (after {warm} warm-up steps) of {sim.nx}x{sim.ny}x{nz} ({wl}; the full workload has nz={w['nz']} per GPU), "
+              f"fp64 OpenMP oracle, {cores} threads")
     line = {
-        "impl": "reference", "metric": "MLUPS (million lattice-cell updates per second), coupled D3Q19 MRT + IB step",
+        "impl": "reference", "metric": METRIC,
         "value": v, "unit": "MLUPS", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong" if w.get("strong") else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": w["desc"], "name": wl, "sampled_grid_xyz": [w["nx"], w["ny"], nz], "ranks": 1},
+        "config": base_config(wl, world),
+        "run": {"sampled_grid_xyz": [sim.nx, sim.ny, nz], "ranks": 1, "warmup_steps_run": warm},
         "cpu_baseline": {"value": v, "unit": "MLUPS", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -226,13 +323,257 @@ def run_reference(args, g, rank, world):
     print(json.dumps(line), flush=True)
 
 
+class Ctx:
+    """Rank plumbing shared by every measurement of one bench.py process."""
+
+    def __init__(self, g, args, rank, world, local, dist):
+        self.g, self.args, self.rank, self.world, self.local, self.dist = g, args, rank, world, local, dist
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+
+    def max_over_ranks(self, x):
+        if self.dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t[0])
+
+    def sum_over_ranks(self, x):
+        if self.dist is None:
+            return x
+        import torch
+        t = torch.tensor([float(x)], dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t[0])
+
+
+def connect(ctx, sim, wl):
+    if ctx.world == 1:
+        return
+    handles = [None] * ctx.world
+    ctx.dist.all_gather_object(handles, sim.peer_export())
+    per = wl in PERIODIC_Z
+    lo = handles[(ctx.rank - 1) % ctx.world] if (ctx.rank > 0 or per) else None
+    hi = handles[(ctx.rank + 1) % ctx.world] if (ctx.rank < ctx.world - 1 or per) else None
+    if wl == "school_1024x512x512":
+        sim.peer_connect_all(handles)
+    else:
+        sim.peer_connect(lo, hi)
+
+
+def add_school(g, sim):
+    # 4 x 2 x 2 school; heads placed so that bodies straddle slab faces (z = 512 at N=2) and the periodic wrap
+    for zc in (200.0, 456.0, 712.0, 968.0):
+        for yc in (128.0, 384.0):
+            for xc in (128.0, 384.0):
+                sim.add_fish(fish_desc(g, (xc, yc, zc)))
+
+
+def timed_steps(ctx, sim, steps, warmup, clocks=None):
+    """W untimed warm-up steps, then EXACTLY K steps in one fg_step call bracketed by barrier + sync on both sides; the
+    time is the library's CUDA-event pair around the call on its own stream, max over ranks."""
+    sim.step(warmup)
+    ctx.barrier()
+    sim.sync()
+    s0 = sim.stats()
+    ctx.barrier()
+    t0 = time.perf_counter()
+    sim.step(steps)               # events bracket exactly K steps on the library's stream
+    if clocks is not None:
+        clocks.sample_now()       # the GPU is busy with the K steps right now
+    sim.sync()                    # fg_step returns when the wrenches are there; the timing needs the last collide, too
+    t1 = time.perf_counter()
+    st = sim.stats()
+    ctx.barrier()
+    ms = ctx.max_over_ranks(st.last_step_ms)
+    return ms, st, s0, (t0, t1)
+
+
+def e2e_loop(ctx, sim, wl, markers, k2, cells_total):
+    """The same metric through the public C-ABI calls a user makes, with HOST buffers, every step: inputs up, one coupled
+    step, result down — wall clock around the loop (fg_sync at the end), max over ranks."""
+    g = ctx.g
+    if markers is not None:
+        X, U, dV, link, _ = markers
+        pin = [np.ascontiguousarray(a) for a in (X, U, dV, link)]
+        for _ in range(3):
+            sim.set_markers(*pin)
+            sim.step(1)
+            sim.get_link_wrenches()
+        ctx.barrier()
+        sim.sync()
+        t0 = time.perf_counter()
+        for _ in range(k2):
+            sim.set_markers(*pin)                    # H2D of this step's inputs (host buffers)
+            sim.step(1)                              # one coupled step
+            wr = sim.get_link_wrenches()             # D2H read of the step's result
+        sim.sync()
+        dt = ctx.max_over_ranks(time.perf_counter() - t0)
+        return {"value": cells_total * k2 / dt / 1e6, "unit": "MLUPS", "ms_per_step": dt / k2 * 1e3,
+                "h2d_bytes_per_step": int(sum(a.nbytes for a in pin)), "d2h_bytes_per_step": int(wr.nbytes + 4),
+                "steps": k2, "call": "fg_set_markers + fg_step(1) + fg_get_link_wrenches per step, host buffers",
+                "drag_Fz": float(wr[0, 2])}
+    if wl in ("tank_512x256x256", "school_1024x512x512"):
+        # the Gym loop: action down, 20 substeps, observation up (env steps/s)
+        nsub = 20
+        has_fish = sim.action_size() > 0
+        act = np.zeros(sim.action_size(), np.float32) if has_fish else None
+        nenv = max(3, k2 // nsub)
+        ctx.barrier()
+        sim.sync()
+        t0 = time.perf_counter()
+        for i in range(nenv):
+            if has_fish:
+                act[:] = np.sin(0.3 * i + np.arange(act.size))
+                sim.set_action(act)
+            sim.step(nsub)
+            if has_fish:
+                sim.get_obs()
+        sim.sync()
+        dt = ctx.max_over_ranks(time.perf_counter() - t0)
+        return {"value": cells_total * nenv * nsub / dt / 1e6, "unit": "MLUPS", "ms_per_step": dt / (nenv * nsub) * 1e3,
+                "env_steps_per_s": nenv / dt, "env_steps": nenv,
+                "substeps_per_env_step": nsub, "h2d_bytes_per_step": int(4 * sim.action_size()),
+                "d2h_bytes_per_step": int(4 * sim.obs_size()),
+                "call": "env.step: fg_set_action + fg_step(20) + fg_get_obs"}
+    # a pure periodic box has no body: the per-step host input is the set of probe coordinates, the result the fluid
+    # state (rho, u) at those points — the velocity-probe observation of the env (fg_probe), 16 points
+    rng = np.random.default_rng(99)
+    P = (rng.uniform(0.05, 0.95, (16, 3)) * np.array([sim.nx, sim.ny, sim.nz])).astype(np.float32)
+    P[:, 2] += ctx.rank * sim.nz
+    for _ in range(3):
+        sim.step(1)
+        out = sim.probe(P)
+    ctx.barrier()
+    sim.sync()
+    t0 = time.perf_counter()
+    for _ in range(k2):
+        sim.step(1)
+        out = sim.probe(P)                           # H2D: 16 points; D2H: (rho, u) at them, after THIS step
+    sim.sync()
+    dt = ctx.max_over_ranks(time.perf_counter() - t0)
+    return {"value": cells_total * k2 / dt / 1e6, "unit": "MLUPS", "ms_per_step": dt / k2 * 1e3,
+            "h2d_bytes_per_step": int(P.nbytes), "d2h_bytes_per_step": int(out.nbytes), "steps": k2,
+            "call": "fg_step(1) + fg_probe(16 points) per step, host buffers (a periodic box has no body: the probe coordinates are the "
+                    "step's input, the interpolated (rho, u) its result)",
+            "probe_u_mean": float(np.asarray(out)[:, 1:].mean())}
+
+
+def measure(ctx, wl, flags, steps, warmup, storage="f32", clocks=None, want_e2e=True, want_profile=True, keep=False, extra=None):
+    """One workload, timed as the contract says.  Returns a dict (and the live sim when keep=True)."""
+    g, args = ctx.g, ctx.args
+    w = WORKLOADS[wl]
+    backend = "cuda" if storage == "f32" else "cuda_f16"
+    bytes_per_update = BYTES_PER_CELL_UPDATE if storage == "f32" else BYTES_PER_CELL_UPDATE / 2
+    sim, markers = make_sim(g, backend, wl, ctx.rank, ctx.world, ctx.local, flags=flags, extra=extra)
+    connect(ctx, sim, wl)
+    if wl == "school_1024x512x512":
+        add_school(g, sim)
+    cells_local = sim.nx * sim.ny * sim.nz
+    cells_total = cells_local * ctx.world
+
+    ms, st, s0, window = timed_steps(ctx, sim, steps, warmup, clocks)
+    launches = int(ctx.sum_over_ranks(st.kernel_launches - s0.kernel_launches))
+    graph_launches = int(st.graph_launches - s0.graph_launches)
+    split = int(st.split_substeps - s0.split_substeps)
+    res = {"name": wl, "value": cells_total * steps / ms / 1e3, "unit": "MLUPS", "ms_per_step": ms / steps, "steps": steps, "warmup": warmup,
+           "gpu_launches": launches, "markers_per_gpu": int(st.n_markers), "cells_total": cells_total, "window": window,
+           "pct_of_hbm_roofline": None,
+           "launch_mode": {"graph_launches": graph_launches, "plane_split_substeps": split,
+                           "pair_substeps": int(st.pair_substeps - s0.pair_substeps),
+                           "how": ("every substep replayed as one CUDA graph" if graph_launches >= steps else
+                                   "kernel-by-kernel launches (substeps with a plane split are not captured)" if graph_launches == 0 else
+                                   "mixed: some substeps as graphs, some launched directly")}}
+    peak, peak_src = measured_peak()
+    res["pct_of_hbm_roofline"] = (res["value"] / ctx.world) * bytes_per_update / 1e3 / peak * 100.0
+    if want_profile:
+        # second pass of the same K steps with every stream-collide / IB launch bracketed by CUDA events on the library's
+        # stream (FG_FLAG_PROFILE; graphs off): the dominant kernel's own duration for the roofline
+        sim.set_flags(flags | g._abi.FLAG_PROFILE)
+        ctx.barrier()
+        sim.step(steps)
+        sp = sim.stats()
+        sim.set_flags(flags)
+        ctx.barrier()
+        if sp.collide_launches > 0 and sp.collide_ms > 0:
+            achieved = bytes_per_update * sp.collide_cells / (sp.collide_ms * 1e-3) / 1e9
+            traffic, traffic_src = None, None
+            for f in ("r2_traffic.json", "r1_traffic.json"):
+                try:
+                    tj = json.load(open(os.path.join(ROOT, "profiles", f)))[wl if storage == "f32" else wl + "_f16"]
+                    traffic = tj["dram_bytes_per_launch"]
+                    traffic_src = f"STATIC, not measured in this run: profiles/{f} (one `ncu --set full` capture of this workload's kernel, per launch)"
+                    break
+                except Exception:       # noqa: BLE001
+                    continue
+            res["roofline"] = {
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": traffic_src, "algorithmic_bytes_per_launch": bytes_per_update * sp.collide_cells / sp.collide_launches,
+                "kernel": "fg::StreamCollide<parity, MRT> (even+odd average)", "peak_source": peak_src,
+                "kernel_ms_per_launch": sp.collide_ms / sp.collide_launches, "launches_timed": int(sp.collide_launches),
+                "cells_per_launch": sp.collide_cells / sp.collide_launches, "bytes_per_cell_update": bytes_per_update,
+                "ib_ms_per_step": sp.ib_ms / steps,
+                "timed_in": "second pass of the same K steps with event brackets (FG_FLAG_PROFILE)",
+                "profiled_pass_ms_per_step": sp.last_step_ms / steps}
+    if want_e2e:
+        res["e2e"] = e2e_loop(ctx, sim, wl, markers, args.e2e_steps or steps, cells_total)
+    if keep:
+        return res, sim, markers
+    sim.close()
+    return res
+
+
+def parity_vs_one_gpu(ctx):
+    """N > 1: a small periodic MRT box split into N peered z-slabs (one per GPU, halos by peer stores exactly as in the timed
+    run) must leave bit-identical populations to the same box stepped on rank 0's GPU alone."""
+    g, world, rank = ctx.g, ctx.world, ctx.rank
+    kw = dict(nx=48, ny=40, nz=16 * world, tau=0.7, collision=g.MRT, body_force=[1e-4, 0, 2e-4])
+    nz, ny, nx = kw["nz"], kw["ny"], kw["nx"]
+    z, y, x = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    u = np.zeros((3, nz, ny, nx), np.float32)
+    u[0] = 0.02 * np.sin(2 * np.pi * x / nx) * np.cos(2 * np.pi * y / ny)
+    u[1] = -0.02 * np.cos(2 * np.pi * x / nx) * np.sin(2 * np.pi * z / nz)
+    u[2] = 0.01 * np.cos(2 * np.pi * y / ny)
+    rho = (1 + 0.01 * np.cos(2 * np.pi * z / nz)).astype(np.float32)
+    h = 16
+    s = g.Sim(backend="cuda", n_ranks=world, rank=rank, device=ctx.local, **kw)
+    s.set_fields(rho[rank * h:(rank + 1) * h], u[:, rank * h:(rank + 1) * h])
+    handles = [None] * world
+    ctx.dist.all_gather_object(handles, s.peer_export())
+    s.peer_connect(handles[(rank - 1) % world], handles[(rank + 1) % world])
+    ctx.barrier()
+    s.step(21)
+    s.step(12)
+    f = s.get_populations()
+    s.close()
+    import torch
+    parts = [torch.empty(f.shape, dtype=torch.float32) for _ in range(world)]
+    ctx.dist.all_gather(parts, torch.from_numpy(f))
+    ok = None
+    if rank == 0:
+        whole = g.Sim(backend="cuda", device=ctx.local, **kw)
+        whole.set_fields(rho, u)
+        whole.step(33)
+        ok = bool(np.array_equal(whole.get_populations(), torch.cat(parts, dim=1).numpy()))
+        whole.close()
+    return ok
+
+
+def strip(res, keys=("window", "cells_total")):
+    return {k: v for k, v in res.items() if k not in keys}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="sphere_256x128x128", choices=list(WORKLOADS))
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS))
+    ap.add_argument("--no-subrecords", action="store_true", help="only the main workload (no IB-overhead / env / sphere / overlap-off sub-records)")
     ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: halo after the full-slab kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="launch kernels directly instead of per-substep CUDA graphs")
@@ -245,6 +586,7 @@ def main():
                     help="f16: the opt-in 16-bit-storage build (fp32 arithmetic, 76 B per cell update; NOT the headline configuration)")
     ap.add_argument("--no-split", action="store_true", help="collide all planes after the IB kernels (no far-plane branch beside them)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer loop (default: --steps)")
+    ap.add_argument("--ref-budget-s", type=float, default=150.0, help="--impl reference: wall-clock budget that sizes the oracle's sample")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -254,7 +596,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    if args.gpus > 1 and world == 1:
+    if args.gpus > 1 and world == 1 and args.impl != "reference":
         raise SystemExit("for --gpus N > 1 launch with: python -m torch.distributed.run --nnodes=1 --nproc-per-node N "
                          "--master-addr 127.0.0.1 --master-port P bench.py --gpus N ...")
 
@@ -276,189 +618,95 @@ def main():
     if world > 1:
         import torch.distributed as dist   # plumbing only: handle exchange, barriers, max over ranks
         dist.init_process_group(backend="gloo", rank=rank, world_size=world)
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
+    ctx = Ctx(g, args, rank, world, local, dist)
 
     wl = args.workload
     w = WORKLOADS[wl]
-    flags = ((g._abi.FLAG_NO_OVERLAP if args.no_overlap else 0) | (g._abi.FLAG_NO_GRAPHS if args.no_graphs else 0) |
-             (g._abi.FLAG_NO_SPLIT if args.no_split else 0) | (g._abi.FLAG_NO_SWEEP_FLIP if args.no_flip else 0) |
-             (g._abi.FLAG_FUSED_PAIRS if args.pairs else 0) | (g._abi.FLAG_NO_XWARP if args.no_xwarp else 0) |
-             (g._abi.FLAG_WAVEFRONT if args.wavefront else 0))
-    gpu_backend = "cuda" if args.storage == "f32" else "cuda_f16"
+    A = g._abi
+    flags = ((A.FLAG_NO_OVERLAP if args.no_overlap else 0) | (A.FLAG_NO_GRAPHS if args.no_graphs else 0) |
+             (A.FLAG_NO_SPLIT if args.no_split else 0) | (A.FLAG_NO_SWEEP_FLIP if args.no_flip else 0) |
+             (A.FLAG_FUSED_PAIRS if args.pairs else 0) | (A.FLAG_NO_XWARP if args.no_xwarp else 0) |
+             (A.FLAG_WAVEFRONT if args.wavefront else 0))
     bytes_per_update = BYTES_PER_CELL_UPDATE if args.storage == "f32" else BYTES_PER_CELL_UPDATE / 2
-    sim, markers = make_sim(g, gpu_backend, wl, rank, world, local, flags=flags, extra=dict(pair_lag=args.pair_lag))
-    if world > 1:
-        handles = [None] * world
-        dist.all_gather_object(handles, sim.peer_export())
-        per = wl in ("box_512", "box_256", "box_512_ib", "tank_512x256x256", "school_1024x512x512")
-        lo = handles[(rank - 1) % world] if (rank > 0 or per) else None
-        hi = handles[(rank + 1) % world] if (rank < world - 1 or per) else None
-        if wl == "school_1024x512x512":
-            sim.peer_connect_all(handles)
-        else:
-            sim.peer_connect(lo, hi)
-    if wl == "school_1024x512x512":
-        # 4 x 2 x 2 school; heads placed so that bodies straddle slab faces (z = 512 at N=2) and the periodic wrap
-        for iz, zc in enumerate((200.0, 456.0, 712.0, 968.0)):
-            for yc in (128.0, 384.0):
-                for xc in (128.0, 384.0):
-                    d = g.FgFishDesc()
-                    d.n_links = 5
-                    for k, (length, rad) in enumerate([(28, 7), (24, 7), (22, 6), (20, 5), (18, 3.5)]):
-                        d.link_len[k], d.link_rad[k] = length, rad
-                    d.root_pos[0], d.root_pos[1], d.root_pos[2] = xc, yc, zc
-                    d.density_ratio, d.joint_gain, d.joint_limit, d.joint_rate_max, d.free_root = 1.0, 0.2, 0.5, 0.01, 1
-                    sim.add_fish(d)
-    nz_local = w["nz"] // world if w.get("strong") else w["nz"]
-    cells_local = w["nx"] * w["ny"] * nz_local
-    cells_total = cells_local * world
 
-    # ---- device-timed throughput: inputs resident in HBM, K steps in one call, CUDA events inside the library
-    clocks = ClockSampler(local)      # runs through warm-up and the timed region (same load), 100 ms period
-    sim.step(args.warmup)
-    barrier()
-    sim.sync()
-    launches0 = sim.stats().kernel_launches
-    barrier()
-    sim.step(args.steps)          # events bracket exactly K steps on the library's stream
-    sim.sync()                    # fg_step returns when the wrenches are there; the timing needs the last collide, too
-    st = sim.stats()
-    barrier()
-    clk = clocks.stop()
-    ms_local = st.last_step_ms
-    launches = st.kernel_launches - launches0
-    # second pass of the same K steps with every stream-collide / IB launch bracketed by CUDA events on the library's
-    # stream (FG_FLAG_PROFILE; graphs off): the dominant kernel's own duration for the roofline
-    sim.set_flags(flags | g._abi.FLAG_PROFILE)
-    barrier()
-    sim.step(args.steps)
-    sp = sim.stats()
-    collide_ms, collide_n, ib_ms, collide_cells = sp.collide_ms, sp.collide_launches, sp.ib_ms, sp.collide_cells
-    profiled_ms = sp.last_step_ms
-    sim.set_flags(flags)
-    barrier()
-    ms = ms_local
-    if dist is not None:
-        import torch
-        t = torch.tensor([ms_local], dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t[0])
-        tl = torch.tensor([float(launches)], dtype=torch.float64)
-        dist.all_reduce(tl, op=dist.ReduceOp.SUM)
-        launches = int(tl[0])
-    value = cells_total * args.steps / ms / 1e3     # MLUPS, whole job
+    clocks = ClockSampler(local) if rank == 0 else None      # runs through warm-up, the timed region and the profiled pass
+    main_res, sim, markers = measure(ctx, wl, flags, args.steps, args.warmup, storage=args.storage, clocks=clocks, keep=True,
+                                     extra=dict(pair_lag=args.pair_lag))
+    clk = clocks.stop(*main_res["window"]) if clocks is not None else None
 
-    # ---- end to end through the C ABI with host buffers: markers up, link wrenches down, every step
-    e2e = None
-    k2 = args.e2e_steps or args.steps
-    if markers is not None:
-        X, U, dV, link, _ = markers
-        pin = [np.ascontiguousarray(a) for a in (X, U, dV, link)]
-        for _ in range(3):
-            sim.set_markers(*pin)
-            sim.step(1)
-            sim.get_link_wrenches()
-        barrier()
-        sim.sync()
-        t0 = time.perf_counter()
-        for _ in range(k2):
-            sim.set_markers(*pin)                    # H2D of this step's inputs (host buffers)
-            sim.step(1)                              # one coupled step
-            wr = sim.get_link_wrenches()             # D2H read of the step's result
-        sim.sync()
-        dt = time.perf_counter() - t0
-        if dist is not None:
-            import torch
-            t = torch.tensor([dt], dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t[0])
-        e2e = {"value": cells_total * k2 / dt / 1e6, "unit": "MLUPS",
-               "h2d_bytes_per_step": int(sum(a.nbytes for a in pin)), "d2h_bytes_per_step": int(wr.nbytes + 4),
-               "steps": k2, "call": "fg_set_markers + fg_step(1) + fg_get_link_wrenches per step, host buffers",
-               "drag_Fz": float(wr[0, 2])}
-    elif wl in ("tank_512x256x256", "school_1024x512x512"):
-        # the Gym loop: action down, 20 substeps, observation up (env steps/s)
-        nsub = 20
-        has_fish = sim.action_size() > 0
-        act = np.zeros(sim.action_size(), np.float32) if has_fish else None
-        t0 = time.perf_counter()
-        nenv = max(3, k2 // nsub)
-        for i in range(nenv):
-            if has_fish:
-                act[:] = np.sin(0.3 * i + np.arange(act.size))
-                sim.set_action(act)
-            sim.step(nsub)
-            if has_fish:
-                sim.get_obs()
-        sim.sync()
-        dt = time.perf_counter() - t0
-        e2e = {"value": cells_total * nenv * nsub / dt / 1e6, "unit": "MLUPS", "env_steps_per_s": nenv / dt,
-               "substeps_per_env_step": nsub, "h2d_bytes_per_step": int(4 * sim.action_size()),
-               "d2h_bytes_per_step": int(4 * sim.obs_size()),
-               "call": "env.step: fg_set_action + fg_step(20) + fg_get_obs"}
-    else:
-        # no per-step host input exists for a pure periodic box: the host-facing call is fg_step(1) + a stats read
-        t0 = time.perf_counter()
-        for _ in range(k2):
-            sim.step(1)
-        sim.sync()
-        dt = time.perf_counter() - t0
-        e2e = {"value": cells_total * k2 / dt / 1e6, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-               "call": "fg_step(1) per step (no per-step host input or output exists for a pure periodic box; fg_sync at the end)"}
+    sub = {}
+    want_sub = not args.no_subrecords and wl == DEFAULT_WORKLOAD and args.storage == "f32"
+    if want_sub and world > 1 and not args.no_overlap:
+        # configs[4] "halo overlap on vs off": the same slabs, halo push after the full-slab kernel
+        sim.set_flags(flags | A.FLAG_NO_OVERLAP)
+        ms, st, s0, _ = timed_steps(ctx, sim, args.steps, max(3, args.warmup))
+        sim.set_flags(flags)
+        sub["overlap_off"] = {"value": main_res["cells_total"] * args.steps / ms / 1e3, "unit": "MLUPS", "ms_per_step": ms / args.steps,
+                              "overlap_on_over_off": (ms / args.steps) / main_res["ms_per_step"]}
+    sim.close()
+    del sim
+
+    if want_sub:
+        k_small = max(args.steps, 200)      # the small workloads step in ~0.1 ms: 20 steps would time 2 ms
+        if world == 1:
+            ib = measure(ctx, "box_512_ib", flags, args.steps, args.warmup)
+            plain_e2e = main_res["e2e"]["ms_per_step"]
+            sub["ib_overhead"] = {
+                "workload": WORKLOADS["box_512_ib"]["desc"], "markers": ib["markers_per_gpu"],
+                "static_markers": {"value": ib["value"], "ms_per_step": ib["ms_per_step"],
+                                   "overhead_pct": (ib["ms_per_step"] / main_res["ms_per_step"] - 1.0) * 100.0,
+                                   "note": "device-timed fg_step(K); marker set unchanged, index map and band reused"},
+                "resent_every_step": {"value": ib["e2e"]["value"], "ms_per_step": ib["e2e"]["ms_per_step"],
+                                      "overhead_pct": (ib["e2e"]["ms_per_step"] / plain_e2e - 1.0) * 100.0,
+                                      "h2d_bytes_per_step": ib["e2e"]["h2d_bytes_per_step"],
+                                      "note": "wall clock of fg_set_markers + fg_step(1) + fg_get_link_wrenches per step against the main "
+                                              "workload's own host loop; band cleared and re-registered every step"},
+                "target_pct": 15.0, "ib_kernels_ms_per_step": (ib.get("roofline") or {}).get("ib_ms_per_step"),
+                "launch_mode": ib["launch_mode"]}
+            tank = measure(ctx, "tank_512x256x256", flags, k_small, max(args.warmup, 20))
+            sub["env"] = {"workload": WORKLOADS["tank_512x256x256"]["desc"], "env_steps_per_s": tank["e2e"]["env_steps_per_s"],
+                          "substeps_per_env_step": 20, "value": tank["value"], "e2e_value": tank["e2e"]["value"], "markers": tank["markers_per_gpu"],
+                          "roofline_frac": (tank.get("roofline") or {}).get("frac"), "launch_mode": tank["launch_mode"]}
+        sph = measure(ctx, "sphere_256x128x128", flags, k_small, max(args.warmup, 20))
+        sub["sphere_256x128x128"] = {"workload": WORKLOADS["sphere_256x128x128"]["desc"], "value": sph["value"], "ms_per_step": sph["ms_per_step"],
+                                     "steps": k_small, "e2e_value": sph["e2e"]["value"], "roofline_frac": (sph.get("roofline") or {}).get("frac"),
+                                     "pct_of_hbm_roofline": sph["pct_of_hbm_roofline"], "launch_mode": sph["launch_mode"],
+                                     "scaling": "weak: one channel + sphere per GPU"}
+        if world > 1:
+            sub["parity_vs_1gpu"] = parity_vs_one_gpu(ctx)
 
     if rank != 0:
-        sim.close()
         if dist is not None:
             dist.barrier()
             dist.destroy_process_group()
         return
 
-    peak, peak_src = measured_peak()
-    roof = None
-    if collide_n > 0 and collide_ms > 0:
-        # algorithmic bytes per launch = 152 B x cells the launch updates; averaged over the bulk launches of the timed
-        # region (the thin checked launches for wall rows run beside them on another stream and are in neither sum)
-        achieved = bytes_per_update * collide_cells / (collide_ms * 1e-3) / 1e9
-        traffic, traffic_src = None, None
-        try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[wl if args.storage == "f32" else wl + "_f16"]
-            traffic, traffic_src = tj["dram_bytes_per_launch"], "profiles/r1_traffic.json (ncu --set full capture of this workload)"
-        except Exception:
-            pass
-        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "traffic_source": traffic_src, "algorithmic_bytes_per_launch": bytes_per_update * collide_cells / collide_n,
-                "kernel": "fg::StreamCollide<parity, MRT> (even+odd average)", "peak_source": peak_src,
-                "kernel_ms_per_launch": collide_ms / collide_n, "launches_timed": int(collide_n),
-                "cells_per_launch": collide_cells / collide_n,
-                "bytes_per_cell_update": bytes_per_update, "ib_ms_per_step": ib_ms / args.steps,
-                "timed_in": "second pass of the same K steps with event brackets (FG_FLAG_PROFILE)",
-                "profiled_pass_ms_per_step": profiled_ms / args.steps}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            v, cores, sample, _ = cpu_oracle_mlups(g, wl, seconds=12.0)
-            cpu = {"value": v, "unit": "MLUPS", "cores": cores, "kind": "port", "sample": sample}
-        except Exception as e:   # the baseline is informative; never let it kill the GPU number
+            _, _, _, ms16 = cpu_oracle_mlups(g, wl, steps=2, warmup=1, nz_sample=16)
+            nzs = oracle_sample_nz(wl, ms16 / 16, 40, 20.0)
+            v, cores, sample, _ = cpu_oracle_mlups(g, wl, seconds=12.0, warmup=20, nz_sample=nzs)
+            cpu = {"value": v, "unit": "MLUPS", "cores": cores, "kind": "port", "sample": sample + ", 20 warm-up steps"}
+        except Exception as e:   # noqa: BLE001 — the baseline is informative; never let it kill the GPU number
             cpu = {"value": None, "unit": "MLUPS", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+    cfg = base_config(wl, world)
     line = {
-        "metric": "MLUPS (million lattice-cell updates per second), coupled D3Q19 MRT + IB step",
-        "value": value, "unit": "MLUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if w.get("strong") else "weak", "vs_baseline": None,
+        "metric": METRIC,
+        "value": main_res["value"], "unit": "MLUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": main_res["ms_per_step"], "higher_is_better": True, "scaling": "strong" if w.get("strong") else "weak", "vs_baseline": None,
         "dtype": "f32" if args.storage == "f32" else "f32 arithmetic on f16-stored populations (opt-in build)", "data": "synthetic",
-        "config": {"workload": w["desc"], "name": wl, "population_storage": args.storage, "grid_per_gpu_xyz": [w["nx"], w["ny"], nz_local], "ranks": world,
-                   "markers_per_gpu": int(st.n_markers), "decomposition": "z-slabs, halos by peer stores over NVLink" if world > 1 else "single GPU",
-                   "halo_overlap": not args.no_overlap, "cuda_graphs": not args.no_graphs,
-                   "plane_split_substeps": int(st.split_substeps), "fused_pair_substeps": int(st.pair_substeps),
-                   "wavefront_pairs": bool(args.wavefront),
-                   "l2": f"populations {19 * (4 if args.storage == 'f32' else 2) * cells_local / 1e6:.0f} MB per GPU > 126 MB L2, no flush needed"},
-        "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
-        "pct_of_hbm_roofline": (value / world) * bytes_per_update / 1e3 / peak * 100.0,
+        "config": cfg,
+        "run": {"population_storage": args.storage, "markers_per_gpu": main_res["markers_per_gpu"],
+                "decomposition": "z-slabs, halos by peer stores over NVLink (CUDA IPC), no NCCL on the data path" if world > 1 else "single GPU",
+                "halo_overlap": not args.no_overlap, "launch_mode": main_res["launch_mode"], "wavefront_pairs": bool(args.wavefront)},
+        "roofline": main_res.get("roofline"), "cpu_baseline": cpu, "e2e": main_res.get("e2e"), "gpu_launches": main_res["gpu_launches"], "clocks": clk,
+        "pct_of_hbm_roofline": main_res["pct_of_hbm_roofline"],
+        "sub_records": sub or None,
     }
+    if SHRINK != 1:
+        line["dry_run_shrink"] = SHRINK
     print(json.dumps(line), flush=True)
-    sim.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

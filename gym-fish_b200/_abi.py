@@ -14,7 +14,7 @@ from typing import Optional
 
 import numpy as np
 
-FG_ABI_VERSION = 6
+FG_ABI_VERSION = 7
 Q = 19
 
 FG_OK, FG_EINVAL, FG_ENOMEM, FG_ECUDA, FG_ESTATE, FG_ENOTSUP, FG_EPEER = 0, -1, -2, -3, -4, -5, -6
@@ -31,6 +31,8 @@ FLAG_FUSED_PAIRS = 64
 FLAG_NO_XWARP = 128
 FLAG_SYNC_STEP = 256
 FLAG_WAVEFRONT = 512
+FLAG_EVEN_VEC4 = 1024
+FLAG_EVEN_VEC2 = 2048
 
 _ERR_NAMES = {FG_EINVAL: "FG_EINVAL", FG_ENOMEM: "FG_ENOMEM", FG_ECUDA: "FG_ECUDA", FG_ESTATE: "FG_ESTATE",
               FG_ENOTSUP: "FG_ENOTSUP", FG_EPEER: "FG_EPEER"}
@@ -81,7 +83,7 @@ class FgStats(C.Structure):
         ("n_markers", C.c_int32), ("n_links", C.c_int32),
         ("band_cells", C.c_int32), ("parity", C.c_int32),
         ("collide_ms", C.c_double), ("collide_launches", C.c_int64), ("ib_ms", C.c_double),
-        ("collide_cells", C.c_int64), ("split_substeps", C.c_int64), ("pair_substeps", C.c_int64), ("reserved", C.c_int64 * 1),
+        ("collide_cells", C.c_int64), ("split_substeps", C.c_int64), ("pair_substeps", C.c_int64), ("graph_launches", C.c_int64),
     ]
 
 
@@ -153,6 +155,7 @@ SYMBOLS = [
     ("fg_step", C.c_int, [_P, C.c_int32]),
     ("fg_sync", C.c_int, [_P]),
     ("fg_get_stats", C.c_int, [_P, C.POINTER(FgStats)]),
+    ("fg_check_finite", C.c_int, [_P, C.POINTER(C.c_int64)]),
     ("fg_set_flags", C.c_int, [_P, C.c_int32]),
     ("fg_halo_bytes", C.c_int64, [_P]),
     ("fg_halo_pack", C.c_int, [_P, C.c_int32, C.c_void_p]),
@@ -423,6 +426,12 @@ class Sim:
 
     def sync(self):
         self._ck(self.lib.fg_sync(self.h))
+
+    def check_finite(self) -> int:
+        """Cells of the local slab whose rest population is non-finite or out of range (0 = the fluid has not diverged)."""
+        n = C.c_int64(0)
+        self._ck(self.lib.fg_check_finite(self.h, C.byref(n)))
+        return int(n.value)
 
     def set_flags(self, flags: int):
         self._ck(self.lib.fg_set_flags(self.h, int(flags)))

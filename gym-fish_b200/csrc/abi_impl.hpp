@@ -206,6 +206,11 @@ int fg_get_stats(FgSim *s, FgStats *o) {
     FG_TRY return s->sim.get_stats(o); FG_CATCH(s)
 }
 
+int fg_check_finite(FgSim *s, int64_t *n_bad) {
+    if (!s || !n_bad) return FG_EINVAL;
+    FG_TRY return s->sim.check_finite(n_bad); FG_CATCH(s)
+}
+
 int fg_set_flags(FgSim *s, int32_t flags) {
     if (!s) return FG_EINVAL;
     s->sim.cfg.flags = flags;

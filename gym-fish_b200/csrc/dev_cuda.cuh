@@ -4,6 +4,7 @@
 #pragma once
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <cstdio>
 #include <cstdlib>
@@ -104,6 +105,13 @@ class CudaDev {
 public:
     std::string err;
     long long launches = 0;
+    long long graph_launches = 0;      // cudaGraphLaunch calls (FgStats.graph_launches)
+
+    int sm_count() const { return sm_count_; }
+    // NVTX ranges per kernel class (step / ib / collide / faces): free when no tool is attached (nvtx3 is header-only and
+    // resolves its injection library lazily), and they name the phases of a substep in an nsys / ncu timeline
+    void range_push(const char *name) { nvtxRangePushA(name); }
+    void range_pop() { nvtxRangePop(); }
 
     bool init(int device, std::string &e) {
         int n = 0;
@@ -457,6 +465,7 @@ public:
             return true;
         }
         gmode_ = 0;
+        ++graph_launches;
         return ck(cudaGraphLaunch(gexec_, stream_), "cudaGraphLaunch");
     }
     void graph_abort() {

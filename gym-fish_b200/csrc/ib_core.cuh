@@ -14,6 +14,7 @@
 #include "lbm_core.cuh"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -82,6 +83,10 @@ struct IbParams {
     int *band_count_next;        // the other counter: previous step's size until IbClearBand ran, then zeroed for the next
     int band_cap;
     uint8_t *rowflag;            // [(nz+2)*ny]
+    // static bodies: (stencil weight, band slot) of every stencil node, cached while the marker set is not re-sent
+    float *node_w;               // [n][64] or nullptr
+    int *node_s;                 // [n][64]
+    int cache_mode;              // 0: compute; 1: compute and fill the cache; 2: read the cache
     const float *origin;         // [links][3] torque reference points
     double *wrench;              // [links][6]
     int n_links;
@@ -235,12 +240,19 @@ struct IbBandMoments {
 };
 
 FG_HD float node_weight(const IbParams &p, int k, int node, long long &cell, int &slot) {
+    if (p.cache_mode == 2) {             // static body: weight and band slot of this node were stored by an earlier step
+        slot = p.node_s[(size_t)k * kNodes + node];
+        cell = slot >= 0 ? (long long)p.band_cell[slot] : -1;
+        return p.node_w[(size_t)k * kNodes + node];
+    }
     const float X = p.X[3 * k], Y = p.X[3 * k + 1], Z = p.X[3 * k + 2];
     const int i0 = p.base[3 * k], j0 = p.base[3 * k + 1], k0 = p.base[3 * k + 2];
     const int a = node & 3, b = (node >> 2) & 3, c = node >> 4;
     cell = stencil_cell(p, i0, j0, k0, a, b, c);
     slot = cell >= 0 ? p.cellslot[cell] - 1 : -1;
-    return peskin4(X - float(i0 + a)) * peskin4(Y - float(j0 + b)) * peskin4(Z - float(k0 + c));
+    const float w = peskin4(X - float(i0 + a)) * peskin4(Y - float(j0 + b)) * peskin4(Z - float(k0 + c));
+    if (p.cache_mode == 1) { p.node_w[(size_t)k * kNodes + node] = w; p.node_s[(size_t)k * kNodes + node] = slot; }
+    return w;
 }
 
 FG_HD float ld_cg(const float *p) {
@@ -314,13 +326,20 @@ struct IbInterpSpread {
         int s = -1;
         if (live) {
             const int lane = tx & 31;
-            const int sel = lane % 12, axis = sel >> 2, j = sel & 3;
-            const float w1 = peskin4(p.X[3 * k + axis] - float(p.base[3 * k + axis] + j));
-            const int a = node & 3, b = (node >> 2) & 3, c = node >> 4;
-            const float wx = __shfl_sync(0xffffffffu, w1, a), wy = __shfl_sync(0xffffffffu, w1, 4 + b), wz = __shfl_sync(0xffffffffu, w1, 8 + c);
-            w = wx * wy * wz;
-            const long long cell = stencil_cell(p, p.base[3 * k], p.base[3 * k + 1], p.base[3 * k + 2], a, b, c);
-            s = cell >= 0 ? p.cellslot[cell] - 1 : -1;
+            if (p.cache_mode == 2) {
+                // static body: one coalesced 8-byte read per node instead of the delta weights, the wrap logic and a
+                // scattered cellslot gather (cellslot is a dense 4 B-per-cell array: every gather costs a DRAM sector)
+                w = p.node_w[gt]; s = p.node_s[gt];
+            } else {
+                const int sel = lane % 12, axis = sel >> 2, j = sel & 3;
+                const float w1 = peskin4(p.X[3 * k + axis] - float(p.base[3 * k + axis] + j));
+                const int a = node & 3, b = (node >> 2) & 3, c = node >> 4;
+                const float wx = __shfl_sync(0xffffffffu, w1, a), wy = __shfl_sync(0xffffffffu, w1, 4 + b), wz = __shfl_sync(0xffffffffu, w1, 8 + c);
+                w = wx * wy * wz;
+                const long long cell = stencil_cell(p, p.base[3 * k], p.base[3 * k + 1], p.base[3 * k + 2], a, b, c);
+                s = cell >= 0 ? p.cellslot[cell] - 1 : -1;
+                if (p.cache_mode == 1) { p.node_w[gt] = w; p.node_s[gt] = s; }
+            }
             float u0 = 0.f, u1 = 0.f, u2 = 0.f;
             if (s >= 0) { u0 = w * p.band_u[s]; u1 = w * p.band_u[p.band_cap + s]; u2 = w * p.band_u[2 * p.band_cap + s]; }
             u0 = warp_sum(u0); u1 = warp_sum(u1); u2 = warp_sum(u2);
@@ -578,6 +597,7 @@ public:
     int create(Dev &dev, const FgConfig &cfg, const Lattice &L, std::string &err) {
         cap_ = cfg.max_markers;
         maxl_ = std::max(cfg.max_links, 1);
+        if (const char *e = std::getenv("FG_IB_CACHE_MIN")) kCacheMinMarkers = std::atoi(e);   // tests: exercise the static-body cache on small clouds
         const long long cells = L.slot;
         band_cap_ = int(std::min<long long>(64ll * cap_, (long long)L.plane * L.nz));
         per_[0] = cfg.bc[FG_XLO] == FG_BC_PERIODIC; per_[1] = cfg.bc[FG_YLO] == FG_BC_PERIODIC; per_[2] = cfg.bc[FG_ZLO] == FG_BC_PERIODIC;
@@ -613,8 +633,8 @@ public:
     }
 
     void destroy(Dev &dev) {
-        void *ps[] = {dmsg_, dbase_, downer_, dF_, dUs_, cellslot_, band_cell_, band_u_, bandF_, band_count_, rowflag_, dwrench_, xbuf_, dxside_};
-        xbuf_ = nullptr; dxside_ = nullptr; xchg_ = false;
+        void *ps[] = {dmsg_, dbase_, downer_, dF_, dUs_, cellslot_, band_cell_, band_u_, bandF_, band_count_, rowflag_, dwrench_, xbuf_, dxside_, node_w_, node_s_};
+        xbuf_ = nullptr; dxside_ = nullptr; xchg_ = false; node_w_ = nullptr; node_s_ = nullptr; cache_valid_ = false;
         for (void *p : ps) dev.free(p);
         dev.free_host(h_stage_[0]); dev.free_host(h_stage_[1]); dev.free_host(h_out_);
         h_stage_[0] = h_stage_[1] = nullptr; h_out_ = nullptr;
@@ -781,6 +801,7 @@ public:
         p.band_count = band_count_ + cur_; p.band_count_next = band_count_ + (cur_ ^ 1);
         p.band_cap = band_cap_; p.rowflag = rowflag_;
         p.wrench = dwrench_; p.n_links = nl_;
+        p.node_w = node_w_; p.node_s = node_s_; p.cache_mode = cache_mode_;
         p.rank = rank_; p.n_ranks = xchg_ ? n_ranks_ : 1; p.cap = cap_; p.maxl = maxl_;
         if (xchg_) {
             p.xside = dxside_;
@@ -801,6 +822,19 @@ public:
         const bool use_fused = fused_ && !xchg_ && dev.supports_phased();
         const bool rebuild = markers_dirty_ || !band_live_ || !reuse_static_ || use_fused;
         if (rebuild) cur_ ^= 1;                               // this step's counter; the other one still holds the old size
+        // static bodies with many markers: from the second step without a re-send on, stencil weights and band slots come
+        // from a per-node cache (8 B per node, allocated on first use) — filled by one step, read by the following ones
+        cache_mode_ = 0;
+        if (rebuild) cache_valid_ = false;
+        else if (!xchg_ && !fused_ && n_ >= kCacheMinMarkers && cache_ok_) {
+            if (!node_w_) {
+                std::string e;
+                node_w_ = static_cast<float *>(dev.alloc(sizeof(float) * size_t(cap_) * kNodes, e));
+                node_s_ = static_cast<int *>(dev.alloc(sizeof(int) * size_t(cap_) * kNodes, e));
+                if (!node_w_ || !node_s_) { dev.free(node_w_); dev.free(node_s_); node_w_ = nullptr; node_s_ = nullptr; cache_ok_ = false; }
+            }
+            if (node_w_) { cache_mode_ = cache_valid_ ? 2 : 1; cache_valid_ = true; }
+        }
         const IbParams p = params(L, C);
         bool ok = flush_upload(dev);
         const int nb = (n_ + kMarkersPerCta - 1) / kMarkersPerCta;
@@ -865,9 +899,15 @@ public:
     // what changes the IB launches of the next substep (CUDA-graph cache key, sim.hpp substep_key)
     void graph_key(uint64_t (&w)[3]) const {
         w[0] = uint64_t(cur_) | (uint64_t(stage_next_) << 1) | (uint64_t(band_live_) << 2) | (uint64_t(n_ > 0) << 3) | (uint64_t(fused_) << 4) |
-               (uint64_t(markers_dirty_ || !reuse_static_) << 5) | (uint64_t(xchg_) << 6);
+               (uint64_t(markers_dirty_ || !reuse_static_) << 5) | (uint64_t(xchg_) << 6) | (uint64_t(next_cache_mode()) << 7);
         w[1] = uint64_t(uint32_t(n_)) | (uint64_t(uint32_t(n_prev_)) << 32);
         w[2] = uint64_t(uint32_t(nl_));
+    }
+    // the cache mode the NEXT compute_forces will pick (part of the CUDA-graph key: it selects launch arguments)
+    int next_cache_mode() const {
+        const bool rebuild = markers_dirty_ || !band_live_ || !reuse_static_;
+        if (rebuild || fused_ || xchg_ || n_ < kCacheMinMarkers || !cache_ok_) return 0;
+        return cache_valid_ ? 2 : 1;
     }
     ForceField force_view() const { return ForceField{cellslot_, bandF_, band_cap_, rowflag_}; }
 
@@ -995,6 +1035,11 @@ private:
     int *dbase_ = nullptr, *downer_ = nullptr, *cellslot_ = nullptr, *band_cell_ = nullptr, *band_count_ = nullptr;
     uint8_t *rowflag_ = nullptr;
     double *dwrench_ = nullptr;
+    float *node_w_ = nullptr;                  // per-node cache of static bodies (lazily allocated): weight ...
+    int *node_s_ = nullptr;                    // ... and band slot
+    int cache_mode_ = 0;
+    bool cache_valid_ = false, cache_ok_ = true;
+    int kCacheMinMarkers = 8192;               // below this the IB kernels are launch-latency bound and the cache buys nothing
     float *h_stage_[2] = {nullptr, nullptr};   // pinned
     double *h_out_ = nullptr;                  // pinned: [6 maxl doubles][2 ints]
     std::vector<double> h_origin_;

@@ -21,6 +21,7 @@
 // loops over the grid on the CPU (test infrastructure only; the product library is CUDA-only).
 #pragma once
 #include <stdint.h>
+#include <math.h>
 
 #if defined(__CUDACC__)
 #define FG_HD __host__ __device__ __forceinline__
@@ -585,6 +586,63 @@ struct StreamCollide {
     }
 };
 
+// ---------------------------------------------------------------- even step, V cells per thread, 16-byte accesses
+// BASELINE.json:5 (a) names "128-bit vectorised coalesced loads".  In the EVEN step of the AA pattern all 19 accesses of a
+// cell are local and aligned, so a thread can take V = 4 (or 2) consecutive cells of a row with one LDG.128 / STG.128
+// (LDG.64) per slot: 19 + 19 memory instructions per V cells instead of 19 V + 19 V.  The V cells are collided one after
+// the other in the same registers (19 V population registers + the collide's temporaries), so the register budget is
+// what limits occupancy: ptxas numbers and the measured A/B against the scalar kernel are in profiles/r2_summary.md.
+// Same arithmetic per cell as StreamCollide<0>: bit-identical results (tests).  Opt-in: FG_FLAG_EVEN_VEC4 / _VEC2.
+#if !defined(FG_POP16)
+template <int V> struct alignas(4 * V) VecF { float a[V]; };
+
+template <bool MRT, int V>
+struct StreamCollideEvenVec {
+    static constexpr int kThreads = kCollideThreads;
+#if defined(FG_VEC_OCC)
+    static constexpr int kMinBlocks = FG_VEC_OCC;
+#else
+    static constexpr int kMinBlocks = V == 4 ? 4 : 6;
+#endif
+    using Scalar = StreamCollide<0, MRT, CHECK_NONE>;
+
+    template <int C>
+    FG_HD static void cell(VecF<V> (&v)[Q], const StepParams &p, int y, int zz, long long idx) {
+        float h[Q];
+        FG_UNROLL
+        for (int i = 0; i < Q; ++i) h[i] = v[i].a[C];
+        float Fx, Fy, Fz;
+        Scalar::force_at(p, y, zz, idx + C, Fx, Fy, Fz);
+        if (MRT) collide_mrt(h, Fx, Fy, Fz, p.C); else collide_bgk(h, Fx, Fy, Fz, p.C);
+        v[0].a[C] = h[0];
+#define FG_X(I) v[Dir<I>::opp].a[C] = h[I]; v[I].a[C] = h[Dir<I>::opp];
+        FG_FOR_PAIRS(FG_X)
+#undef FG_X
+    }
+
+    // grid: (ceil(nx / V / threads), rows, planes); requires nx % V == 0
+    FG_HD static void run(const StepParams &p, int bx, int by, int bz, int tx) {
+        const Lattice &L = p.L;
+        const int x0 = (bx * kThreads + tx) * V, y = p.y0 + by * p.ystride;
+        int zz = p.zz_begin + (p.zz_flip >= 0 ? p.zz_flip - bz : bz) * p.zz_stride;
+        if (zz >= p.zz_skip_begin) zz += p.zz_skip_len;
+        if (x0 >= L.nx) return;
+        const long long idx = ((long long)zz * L.ny + y) * L.nx + x0;
+        VecF<V> v[Q];
+        FG_UNROLL
+        for (int i = 0; i < Q; ++i) v[i] = *reinterpret_cast<const VecF<V> *>(L.f + i * L.slot + idx);
+        cell<0>(v, p, y, zz, idx);
+        cell<1>(v, p, y, zz, idx);
+        if (V == 4) {
+            cell<V == 4 ? 2 : 0>(v, p, y, zz, idx);
+            cell<V == 4 ? 3 : 0>(v, p, y, zz, idx);
+        }
+        FG_UNROLL
+        for (int i = 0; i < Q; ++i) *reinterpret_cast<VecF<V> *>(L.f + i * L.slot + idx) = v[i];
+    }
+};
+#endif
+
 // ---------------------------------------------------------------- two steps in one launch (L2-resident wavefront)
 // StreamCollidePair runs the EVEN step s and the ODD step s+1 of a range of planes in ONE launch: the odd step follows
 // the even step `lag` planes behind, so it finds the populations the even step has just written in the 126 MB L2 and
@@ -779,6 +837,33 @@ struct ScatterNatural {
         const long long l = ((long long)(zz - 1) * L.ny + y) * L.nx + x, n = (long long)L.nz * L.plane;
         FG_UNROLL
         for (int i = 0; i < Q; ++i) pop_st(L.f + i * L.slot + idx, p.out19[i * n + l]);
+    }
+};
+
+// divergence guard of the fluid (fg_check_finite): one thread per cell reads the REST population only (4 B per cell) and
+// counts cells where it is not finite or has left |h_0| <= 4 (the density would be off by more than 12).  A NaN in any
+// population of a cell reaches h_0 with the cell's next collision, so a blow-up is seen one step later at most.
+struct FiniteParams {
+    Lattice L;
+    unsigned long long *bad;    // [1], zeroed before the launch
+};
+struct FiniteCheck {
+    static constexpr int kThreads = 128;
+    static constexpr int kMinBlocks = 8;
+    FG_HD static void run(const FiniteParams &p, int bx, int by, int bz, int tx) {
+        const Lattice &L = p.L;
+        const int x = bx * kThreads + tx, y = by, zz = bz + 1;
+        bool bad = false;
+        if (x < L.nx) {
+            const long long idx = ((long long)zz * L.ny + y) * L.nx + x;
+            if (!(L.solid && L.solid[idx])) bad = !(fabsf(pop_ld(L.f + idx)) <= 4.0f);
+        }
+#if defined(__CUDA_ARCH__)
+        const unsigned m = __ballot_sync(0xffffffffu, bad);
+        if (m && (tx & 31) == 0) atomicAdd(p.bad, (unsigned long long)__popc(m));
+#else
+        if (bad) ++*p.bad;
+#endif
     }
 };
 

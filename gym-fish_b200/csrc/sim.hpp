@@ -81,6 +81,8 @@ public:
         dev.free(pair_ctr_); pair_ctr_ = nullptr;
         dev.free(solid_); solid_ = nullptr;
         dev.free(stage_[0]); dev.free(stage_[1]); stage_[0] = stage_[1] = nullptr;
+        dev.free(probe_d_); dev.free_host(probe_h_); probe_d_ = probe_h_ = nullptr; probe_cap_ = 0;
+        dev.free(finite_d_); finite_d_ = nullptr;
         dev.shutdown();
     }
 
@@ -114,7 +116,23 @@ public:
         return FG_OK;
     }
 
+    // Read-outs gather the populations ARRIVING at each cell; after an even step the boundary planes pull them from the
+    // ghost planes, i.e. from what the z-neighbours pushed after THEIR last step.  Host-staged slabs must have unpacked
+    // every face (as in the oracle); peered slabs wait for the neighbours' flags on the device — a neighbour may lag by a
+    // whole step (another process, another GPU), and without the wait the read-out raced with its push (found in round 2
+    // by running the two-process test on ONE device, where time slicing makes the lag the rule).
+    int halos_ready_for_readout() {
+        if (cfg.n_ranks <= 1 || parity_ == 0) return FG_OK;
+        if (!peers_) {
+            if (pending_faces_ > 0) return fail(FG_ESTATE, "halo exchange incomplete: unpack every internal face after fg_step");
+            return FG_OK;
+        }
+        if (!dev.wait_flags(flags_, has_lo_peer(), has_hi_peer()) || !dev.sync()) return cuda_fail();
+        return check_peer_timeout();
+    }
+
     int get_moments(std::vector<float> &mom) {
+        if (int rc = halos_ready_for_readout()) return rc;
         const size_t n = size_t(L_.plane) * L_.nz;
         float *d = static_cast<float *>(dev.alloc(4 * n * sizeof(float), err));
         if (!d) return FG_ENOMEM;
@@ -157,6 +175,7 @@ public:
     }
 
     int get_populations(float *f19) {
+        if (int rc = halos_ready_for_readout()) return rc;
         const size_t n = size_t(L_.plane) * L_.nz;
         float *d = static_cast<float *>(dev.alloc(size_t(Q) * n * sizeof(float), err));
         if (!d) return FG_ENOMEM;
@@ -256,15 +275,42 @@ public:
 
     int probe(int n, const float *X, float *out4) {
         if (n == 0) return FG_OK;
-        float *d = static_cast<float *>(dev.alloc(sizeof(float) * 7 * size_t(n), err));
-        if (!d) return FG_ENOMEM;
-        ProbeParams p{L_, C_, n, cfg.bc[FG_XLO] == FG_BC_PERIODIC, cfg.bc[FG_YLO] == FG_BC_PERIODIC, cfg.bc[FG_ZLO] == FG_BC_PERIODIC, d, d + 3 * size_t(n)};
+        if (int rc = halos_ready_for_readout()) return rc;
+        // persistent, grow-only buffers: the call sits in the per-step loop of an env with velocity probes, and a
+        // cudaMalloc / cudaFree pair per call would synchronise the device every step
+        if (n > probe_cap_) {
+            dev.free(probe_d_); dev.free_host(probe_h_);
+            probe_cap_ = 0;
+            const int cap = std::max(64, n);
+            probe_d_ = static_cast<float *>(dev.alloc(sizeof(float) * 7 * size_t(cap), err));
+            probe_h_ = static_cast<float *>(dev.alloc_host(sizeof(float) * 7 * size_t(cap), err));
+            if (!probe_d_ || !probe_h_) return FG_ENOMEM;
+            probe_cap_ = cap;
+        }
+        float *d = probe_d_;
+        const size_t N = size_t(n);
+        std::memcpy(probe_h_, X, sizeof(float) * 3 * N);
+        ProbeParams p{L_, C_, n, cfg.bc[FG_XLO] == FG_BC_PERIODIC, cfg.bc[FG_YLO] == FG_BC_PERIODIC, cfg.bc[FG_ZLO] == FG_BC_PERIODIC, d, d + 3 * N};
         Dim3 g{(n + kMarkersPerCta - 1) / kMarkersPerCta, 1, 1};
-        bool ok = dev.h2d(d, X, sizeof(float) * 3 * size_t(n)) && dev.zero(d + 3 * size_t(n), sizeof(float) * 4 * size_t(n));
+        bool ok = dev.h2d_async(d, probe_h_, sizeof(float) * 3 * N) && dev.zero(d + 3 * N, sizeof(float) * 4 * N);
         ok = ok && (parity_ == 0 ? dev.template launch<ProbeMoments<0>>(g, p) : dev.template launch<ProbeMoments<1>>(g, p));
-        ok = ok && dev.sync() && dev.d2h(out4, d + 3 * size_t(n), sizeof(float) * 4 * size_t(n));
-        dev.free(d);
-        return ok ? FG_OK : cuda_fail();
+        ok = ok && dev.d2h_async(probe_h_ + 3 * N, d + 3 * N, sizeof(float) * 4 * N) && dev.sync();
+        if (!ok) return cuda_fail();
+        std::memcpy(out4, probe_h_ + 3 * N, sizeof(float) * 4 * N);
+        return FG_OK;
+    }
+
+    // fg_check_finite: cells whose rest population is not finite / out of range (lbm_core.cuh FiniteCheck)
+    int check_finite(int64_t *n_bad) {
+        if (!finite_d_) finite_d_ = static_cast<unsigned long long *>(dev.alloc(sizeof(unsigned long long), err));
+        if (!finite_d_) return FG_ENOMEM;
+        FiniteParams p{L_, finite_d_};
+        unsigned long long h = 0;
+        const bool ok = dev.zero(finite_d_, sizeof(unsigned long long)) && dev.template launch<FiniteCheck>(grid_planes(L_.nz), p) &&
+                        dev.sync() && dev.d2h(&h, finite_d_, sizeof(h));
+        if (!ok) return cuda_fail();
+        *n_bad = int64_t(h);
+        return FG_OK;
     }
 
     int add_fish(const FgFishDesc &d, int32_t *id) {
@@ -312,6 +358,7 @@ public:
             return fail(FG_ESTATE, "halo exchange incomplete: unpack every internal face after fg_step");
         const bool prof = (cfg.flags & FG_FLAG_PROFILE) != 0;
         const bool graphs = !prof && !(cfg.flags & FG_FLAG_NO_GRAPHS);
+        Range step_range(dev, "fg_step");
         dev.marks_reset();
         dev.tic();
         for (int it = 0; it < n; ++it) {
@@ -339,6 +386,17 @@ public:
                     const int far = (a - lo) + (hi - b);
                     if (far * 4 >= hi - lo && (long long)far * L_.plane >= (cfg.split_min_cells > 0 ? cfg.split_min_cells : (1 << 20))) { split_ = true; near_a_ = a; near_b_ = b; }
                 }
+            }
+            // Peered z-slabs WITHOUT bodies: nothing waits for a force, so every interior plane is "far" — the interior
+            // collide goes to the low-priority branch and the high-priority chain (wait for the neighbours' flags ->
+            // boundary planes -> halo push -> signal) runs BESIDE it instead of in front of it.  In round 1 that chain
+            // (~10 us of latency-bound launches) sat serially before the interior kernel in the substep's graph and was
+            // the whole weak-scaling loss of small slabs.  Interior planes touch no location of
+            // the boundary planes' update (the AA update of plane p owns plane p-1's -z slots, plane p+1's +z slots
+            // and its own rest), so the two branches are independent.
+            if (!ib_on && overlap && !prof && !(cfg.flags & FG_FLAG_NO_SPLIT) &&
+                (long long)(hi - lo) * L_.plane >= (cfg.split_min_cells > 0 ? cfg.split_min_cells : (1 << 20))) {
+                split_ = true; near_a_ = near_b_ = lo;
             }
             // Two substeps as a launch-level wavefront (wave_pair below): opt-in experiment.
             if (!prof && (cfg.flags & FG_FLAG_WAVEFRONT) && parity_ == 0 && it + 1 < n && (!ranks || (peers_ && !ib_.exchange_on())) && L_.nz >= 8) {
@@ -395,7 +453,10 @@ public:
             if (ib_on) {
                 if (prof) dev.mark(1);
                 ib_.set_fused((cfg.flags & FG_FLAG_FUSED_IB) != 0);
-                if (int rc = ib_.compute_forces(dev, L_, C_, parity_, err)) return rc;
+                {
+                    Range r(dev, "fg:immersed_boundary");
+                    if (int rc = ib_.compute_forces(dev, L_, C_, parity_, err)) return rc;
+                }
                 if (prof) dev.mark(1);
                 F = ib_.force_view();
             }
@@ -489,6 +550,7 @@ public:
         o->collide_cells = last_collide_cells_;
         o->split_substeps = split_substeps_;
         o->pair_substeps = pair_substeps_ + wave_substeps_;
+        o->graph_launches = dev.graph_launches;
         return FG_OK;
     }
 
@@ -621,6 +683,12 @@ public:
     int cuda_fail() { err = dev.err; return FG_ECUDA; }
 
 private:
+    // NVTX range (CUDA policy; a no-op in the host emulation) around one phase of a substep
+    struct Range {
+        Dev &d;
+        Range(Dev &dev_, const char *name) : d(dev_) { d.range_push(name); }
+        ~Range() { d.range_pop(); }
+    };
     Dim3 grid_planes(int planes) const {
         return Dim3{(L_.nx + 127) / 128, L_.ny, planes};
     }
@@ -657,6 +725,26 @@ private:
         return cfg.collision == FG_MRT ? dev.template launch<StreamCollide<PARITY, true, MODE>>(g, p)
                                        : dev.template launch<StreamCollide<PARITY, false, MODE>>(g, p);
     }
+    // opt-in experiment: even step with 4 / 2 cells per thread and 16- / 8-byte accesses (lbm_core.cuh StreamCollideEvenVec)
+    int even_vec_width() const {
+#if defined(FG_POP16)
+        return 0;
+#else
+        if ((cfg.flags & FG_FLAG_EVEN_VEC4) && L_.nx % 4 == 0) return 4;
+        if ((cfg.flags & FG_FLAG_EVEN_VEC2) && L_.nx % 2 == 0) return 2;
+        return 0;
+#endif
+    }
+    bool launch_even_vec(const StepParams &p, Dim3 g, int vec) {
+#if defined(FG_POP16)
+        (void)p; (void)g; (void)vec;
+        return false;
+#else
+        const bool mrt = cfg.collision == FG_MRT;
+        if (vec == 4) return mrt ? dev.template launch<StreamCollideEvenVec<true, 4>>(g, p) : dev.template launch<StreamCollideEvenVec<false, 4>>(g, p);
+        return mrt ? dev.template launch<StreamCollideEvenVec<true, 2>>(g, p) : dev.template launch<StreamCollideEvenVec<false, 2>>(g, p);
+#endif
+    }
     // hole: planes [hole_b, hole_e) inside [zb, ze) are left out (zstride 1 only)
     bool launch_rows(int mode, int zb, int ze, int y0, int ystride, int rows, const ForceField &F, int zstride = 1, int hole_b = 0, int hole_e = 0,
                      bool timed = false) {
@@ -677,7 +765,9 @@ private:
         bool ok;
         if (parity_ == 0) {
             // the even step is purely local: only obstacles need the checked variant
-            ok = mode == CHECK_ALL && L_.solid ? launch_collide_pm<0, CHECK_ALL>(p, g) : launch_collide_pm<0, CHECK_NONE>(p, g);
+            const int vec = L_.solid ? 0 : even_vec_width();
+            if (vec) ok = launch_even_vec(p, Dim3{(L_.nx / vec + kCollideThreads - 1) / kCollideThreads, rows, planes}, vec);
+            else ok = mode == CHECK_ALL && L_.solid ? launch_collide_pm<0, CHECK_ALL>(p, g) : launch_collide_pm<0, CHECK_NONE>(p, g);
         } else {
             switch (mode) {
                 case CHECK_ALL: ok = launch_collide_pm<1, CHECK_ALL>(p, g); break;
@@ -692,6 +782,7 @@ private:
     // Partition planes [zz_begin, zz_end) (minus the hole) so that boundary code only runs where a link can be blocked.
     // zstride > 1 covers planes zz_begin, zz_begin + zstride, ... (the two boundary planes of a slab in one launch)
     bool launch_collide(int zz_begin, int zz_end, const ForceField &F, int zstride = 1, int hole_b = 0, int hole_e = 0) {
+        Range r(dev, "fg:stream_collide");
         if (hole_e <= hole_b || hole_e <= zz_begin || hole_b >= zz_end) hole_b = hole_e = 0;
         if (hole_e > hole_b) {           // a hole touching an end of the range just shortens the range
             if (hole_b <= zz_begin) { zz_begin = hole_e; hole_b = hole_e = 0; }
@@ -805,7 +896,7 @@ private:
         const long long plane_bytes = (long long)kPopBytes * Q * L_.plane;
         const long long target = std::max<long long>(1, std::min<long long>(64, (20ll << 20) / plane_bytes));
         const long long per_plane = (long long)((L_.nx + kCollideThreads - 1) / kCollideThreads) * std::max(1, L_.wall_y ? L_.ny - 2 : L_.ny);
-        const long long resident = 148 * 9;
+        const long long resident = (long long)dev.sm_count() * 9;
         const long long waves = std::max<long long>(1, (target * per_plane + resident / 2) / resident);
         return int(std::max<long long>(1, std::min<long long>(64, waves * resident / per_plane)));
     }
@@ -962,6 +1053,7 @@ private:
 
     // z-face plane ops after the step of parity `parity_`: one launch covers both faces
     bool launch_faces() {
+        Range r(dev, "fg:z_faces");
         HaloParams p{};
         p.L = L_; p.C = C_; p.parity_done = parity_;
         bool any = false;
@@ -1057,6 +1149,9 @@ private:
     pop_t *peer_f_[2] = {nullptr, nullptr};
     int *peer_flags_[2] = {nullptr, nullptr};
     int pending_faces_ = 0;
+    float *probe_d_ = nullptr, *probe_h_ = nullptr;   // fg_probe: device [7 cap] / pinned host [7 cap], grow-only
+    int probe_cap_ = 0;
+    unsigned long long *finite_d_ = nullptr;           // fg_check_finite counter
     IbState<Dev> ib_;
     std::vector<Fish> fish_;
     std::vector<float> action_;

@@ -82,6 +82,7 @@ class EnvConfig:
     waypoints: Sequence[Tuple[float, float]] = ()         # path task: (x, z) points to visit in order (first fish)
     waypoint_radius: float = 12.0
     probes: int = 0                                       # velocity probes per fish, on a ring ahead of the head
+    fluid_check_every: int = 1                            # env steps between fluid divergence checks (fg_check_finite; 0 = never)
 
 
 class FishEnv:
@@ -144,7 +145,14 @@ class FishEnv:
         truncated = self._t >= self.cfg.max_episode_steps
         st = self.sim.stats()
         # timing of the latest env step whose device work has finished (fg_step returns before its last collide has)
-        info = {"mlups": st.last_mlups, "step_ms": st.last_step_ms, "diverged": bool(not np.isfinite(obs).all())}
+        # divergence: the observation covers the bodies only, and a blown-up fluid around a pinned (or slow) body would go
+        # unnoticed there — fg_check_finite reads one population per cell (~0.1 % of an env step of 20 substeps)
+        bad_cells = 0
+        k = self.cfg.fluid_check_every
+        if k > 0 and self._t % k == 0:
+            bad_cells = self.sim.check_finite()
+        info = {"mlups": st.last_mlups, "step_ms": st.last_step_ms, "fluid_bad_cells": bad_cells,
+                "diverged": bool(bad_cells > 0 or not np.isfinite(obs).all())}
         return obs, float(reward), bool(terminated or info["diverged"]), bool(truncated), info
 
     def close(self):

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FG_ABI_VERSION 6
+#define FG_ABI_VERSION 7
 #define FG_Q 19
 
 /* error codes */
@@ -68,6 +68,8 @@ extern "C" {
 #define FG_FLAG_NO_XWARP 128   /* x walls: predicated wall selects in every thread (default: only the two warps at the row ends run the wall code) */
 #define FG_FLAG_SYNC_STEP 256  /* fg_step returns only when all its device work has finished (default: when wrenches / obs are there) */
 #define FG_FLAG_WAVEFRONT 512  /* EXPERIMENT (unmeasured): even step + following odd step as a launch-level wavefront of plane chunks on two streams, the odd step one chunk behind the even one, so that it finds its populations in L2 (one rank or peered z-slabs; prescribed markers or fish inside a slab — with fish the pair is launched directly, not as a graph; no bodies across slab faces) */
+#define FG_FLAG_EVEN_VEC4 1024 /* EXPERIMENT (A/B in profiles/r2_summary.md): even steps take 4 cells per thread with 128-bit loads / stores (needs nx % 4 == 0, no obstacles) */
+#define FG_FLAG_EVEN_VEC2 2048 /* ... 2 cells per thread with 64-bit accesses (nx % 2 == 0) */
 #define FG_FLAG_NO_SPLIT  16   /* collide all planes after the IB kernels (default: planes away from the bodies run beside them) */
 
 typedef struct FgConfig {
@@ -107,7 +109,7 @@ typedef struct FgStats {
     int64_t collide_cells;    /* ... and how many cell updates those launches did (thin wall-row launches are not in either) */
     int64_t split_substeps;   /* substeps since create whose far-plane collide ran beside the IB kernels (plane split) */
     int64_t pair_substeps;    /* substeps since create that ran as half of a fused even+odd pair (StreamCollidePair) */
-    int64_t reserved[1];
+    int64_t graph_launches;   /* CUDA graph launches since create (substeps replayed or captured-and-launched as one graph; direct launches are not in here) */
 } FgStats;
 
 /* articulated swimmer description: a planar chain of n_links ellipsoid links, yawing joints */
@@ -178,6 +180,10 @@ int fg_get_markers(FgSim *sim, float *X, float *U, int32_t *link_id, int32_t cap
 int fg_step(FgSim *sim, int32_t n_substeps);
 int fg_sync(FgSim *sim);
 int fg_get_stats(FgSim *sim, FgStats *out);
+/* divergence guard for the FLUID (the observation only covers the bodies): counts the cells of the local slab whose rest
+ * population is not finite or has left |f_0 - 1/3| <= 4 — one 4-byte read per cell (~85 us at 512^3 on a B200).  A NaN
+ * anywhere in a cell reaches its rest population with the next collision, so a blow-up shows here one step later at most. */
+int fg_check_finite(FgSim *sim, int64_t *n_bad_cells);
 int fg_set_flags(FgSim *sim, int32_t flags);        /* change FgConfig.flags (FG_FLAG_PROFILE, FG_FLAG_NO_GRAPHS, FG_FLAG_NO_OVERLAP) */
 
 /* ---- z-slab halos ----

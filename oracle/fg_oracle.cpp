@@ -813,6 +813,21 @@ int fg_get_stats(FgSim *s, FgStats *o) {
     return FG_OK;
 }
 
+// include/fishgym.h fg_check_finite: rest population not finite or |f_0 - 1/3| > 4 (solid cells are not fluid)
+int fg_check_finite(FgSim *s, int64_t *n_bad) {
+    if (!s || !n_bad) return FG_EINVAL;
+    int64_t bad = 0;
+    for (int z = 1; z <= s->nz; ++z)
+        for (size_t c = 0; c < s->plane; ++c) {
+            const size_t i = size_t(z) * s->plane + c;
+            if (s->has_solid && s->solid[i]) continue;
+            const double v = s->f[i] - 1.0 / 3.0;
+            if (!(std::fabs(v) <= 4.0)) ++bad;
+        }
+    *n_bad = bad;
+    return FG_OK;
+}
+
 int fg_set_flags(FgSim *s, int32_t flags) {
     if (!s) return FG_EINVAL;
     s->cfg.flags = flags;

@@ -26,6 +26,10 @@ class HostDev {
 public:
     std::string err;
     long long launches = 0;
+    long long graph_launches = 0;
+    int sm_count() const { return 148; }
+    void range_push(const char *) {}
+    void range_pop() {}
     long long n_submit = 0, n_record = 0, n_wait = 0;      // FG_EMU_DEBUG: operations queued (what the CUDA policy would issue as API calls)
     int wait_ms = 300;   // how long a slab waits for its neighbour's halo before reporting it is behind
 
@@ -231,6 +235,7 @@ public:
     bool graph_end() {
         if (gmode_ == 0) return true;
         gmode_ = 0;
+        ++graph_launches;
         std::vector<std::shared_ptr<bool>> inst(graph_->n_events);
         for (auto &e : inst) e = std::make_shared<bool>(sched_ == 0);
         for (const GOp &op : graph_->ops) {

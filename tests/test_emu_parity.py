@@ -256,3 +256,47 @@ def test_velocity_probes_match_oracle_at_both_parities(g, emu):
     # a probe on a node far from walls sees the cell values smoothed by the kernel: weights sum to one
     one = a.probe(np.array([[7.3, 6.4, 5.2]], np.float32))[0]
     assert abs(one[0] - 1.0) < 0.02
+
+
+@pytest.mark.parametrize("name", ["bgk_periodic", "mrt_force", "mrt_xy_walls", "mrt_all_walls_lid", "mrt_inlet_outlet_ywalls"])
+@pytest.mark.parametrize("vec", [4, 2])
+def test_vectorised_even_step_is_bit_identical(g, emu, name, vec):
+    """FG_FLAG_EVEN_VEC4 / _VEC2 (lbm_core.cuh StreamCollideEvenVec): V cells per thread with 16- / 8-byte accesses in the
+    even step — the same arithmetic per cell, so populations must equal the scalar kernel's bit for bit."""
+    kw = dict(util.parity_cases(g)[name])
+    flag = g._abi.FLAG_EVEN_VEC4 if vec == 4 else g._abi.FLAG_EVEN_VEC2
+    a, b = g.Sim(backend=emu, **kw), g.Sim(backend=emu, flags=flag, **kw)
+    rho, u = util.smooth_fields(a.shape)
+    for s in (a, b):
+        s.set_fields(rho, u)
+        s.step(7)
+    assert np.array_equal(a.get_populations(), b.get_populations())
+
+
+@pytest.mark.parametrize("graphs", [False, True])
+def test_static_body_node_cache_matches_recomputation(g, emu, graphs, monkeypatch):
+    """Static bodies (marker set not re-sent): from the second such step on, stencil weights and band slots come from a
+    per-node cache instead of being recomputed (ib_core.cuh node_weight / IbInterpSpread::cta).  Same values, same order of
+    additions in the emulation => bit-identical fluid and wrenches; re-sending the markers invalidates the cache."""
+    if graphs:
+        monkeypatch.setenv("FG_EMU_GRAPHS", "1")
+    kw = dict(nx=20, ny=18, nz=24, tau=0.8, collision=g.MRT, max_markers=600, max_links=2, body_force=[0, 0, 2e-5])
+    a = g.Sim(backend=emu, **kw)                       # 320 markers < 8192: never cached
+    monkeypatch.setenv("FG_IB_CACHE_MIN", "1")
+    b = g.Sim(backend=emu, **kw)                       # cached from the third step of each static stretch
+    X = np.concatenate([util.sphere_markers((10.3, 9.1, 8.2), 4.0, 200), util.sphere_markers((1.0, 16.5, 20.0), 3.0, 120)])   # wraps in x
+    link = np.array([0] * 200 + [1] * 120, np.int32)
+    rho, u = util.smooth_fields(a.shape)
+    for s in (a, b):
+        s.set_fields(rho, u)
+    for shift in (0.0, 0.6):
+        Xs = X.copy()
+        Xs[:, 2] += shift
+        for s in (a, b):
+            s.set_markers(Xs, np.zeros_like(Xs), np.ones(len(Xs), np.float32), link)
+            s.set_link_origins([[10.3, 9.1, 8.2 + shift], [1.0, 16.5, 20.0 + shift]])
+            s.step(1)
+            s.step(5)
+        assert np.array_equal(a.get_populations(), b.get_populations())
+        assert np.array_equal(a.get_link_wrenches(), b.get_link_wrenches())
+        assert np.array_equal(a.get_marker_forces(), b.get_marker_forces())

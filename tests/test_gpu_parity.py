@@ -356,3 +356,81 @@ def test_slab_that_runs_ahead_reports_fg_epeer(g, cuda, monkeypatch):
     assert ei.value.code == g._abi.FG_EPEER, ei.value
     for s in parts:
         s.close()
+
+
+@pytest.mark.parametrize("stop_at", [4, 5])
+def test_checkpoint_resume_on_gpu(g, cuda, stop_at, tmp_path):
+    """SURVEY.md §8 f3 on the CUDA path: fg_get_populations / fg_set_populations as a checkpoint, stopped after an even or
+    an odd number of steps (natural vs swapped AA storage), resumed in a FRESH handle from a file; plus the field snapshot
+    (npz + VTK).  The interface carries unshifted fp32 populations (one ulp of f = 3e-8), so the continuation agrees to
+    that round-off; the round trip itself is exact."""
+    from gym_fish_b200.env import save_snapshot
+    P, Wl = g.BC_PERIODIC, g.BC_WALL
+    kw = dict(nx=40, ny=24, nz=20, tau=0.7, collision=g.MRT, bc=[P, P, Wl, Wl, P, P], body_force=[1e-4, 0, 1e-4], max_markers=400, max_links=1)
+    a = g.Sim(backend=cuda, **kw)
+    rho, u = util.smooth_fields(a.shape)
+    X = util.sphere_markers((20.2, 12.1, 10.3), 4.0, 200)
+    a.set_fields(rho, u)
+    a.set_markers(X, np.zeros_like(X), np.ones(200, np.float32))
+    a.step(stop_at)
+    np.save(tmp_path / "ckpt.npy", a.get_populations())
+    save_snapshot(a, str(tmp_path / "snap"), vtk=True)
+    a.step(6)
+    b = g.Sim(backend=cuda, **kw)
+    snap = np.load(tmp_path / "ckpt.npy")
+    b.set_populations(snap)
+    assert np.array_equal(b.get_populations(), snap)            # exact round trip through the device
+    b.set_markers(X, np.zeros_like(X), np.ones(200, np.float32))
+    b.step(6)
+    assert np.abs(a.get_populations() - b.get_populations()).max() <= 1e-7
+    z = np.load(tmp_path / "snap.npz")
+    assert z["rho"].shape == a.shape and z["u"].shape == (3,) + a.shape and len(z["markers"]) == 200
+    assert (tmp_path / "snap.vtk").stat().st_size > 4 * 4 * a.shape[0] * a.shape[1] * a.shape[2]
+    a.close(); b.close()
+
+
+def test_fluid_divergence_guard_on_gpu(g, cuda):
+    """fg_check_finite: 0 bad cells on a healthy run; a NaN planted in one population of one cell is seen after the next
+    collision at the latest, and an over-driven flow (tau close to 1/2, Mach ~ 1) is flagged once it has blown up —
+    while the body observation alone would not notice (env.py info["diverged"])."""
+    kw = dict(nx=32, ny=24, nz=16, tau=0.8, collision=g.BGK)
+    s = g.Sim(backend=cuda, **kw)
+    rho, u = util.smooth_fields(s.shape)
+    s.set_fields(rho, u)
+    s.step(5)
+    assert s.check_finite() == 0
+    f = s.get_populations()
+    f[7, 3, 4, 5] = np.nan
+    s.set_populations(f)
+    s.step(1)
+    n1 = s.check_finite()
+    s.step(3)
+    assert n1 >= 1 and s.check_finite() > n1                     # the NaN spreads with the streaming
+    s.close()
+    t = g.Sim(backend=cuda, nx=32, ny=24, nz=16, tau=0.5005, collision=g.BGK)
+    rho, u = util.smooth_fields(t.shape, amp=0.6)
+    t.set_fields(rho, u)
+    t.step(400)
+    assert t.check_finite() > 0
+    t.close()
+
+
+@pytest.mark.parametrize("name", ["mrt_force", "mrt_all_walls_lid", "mrt_inlet_outlet_ywalls"])
+@pytest.mark.parametrize("vec", [4, 2])
+def test_vectorised_even_step_is_bit_identical_on_gpu(g, cuda, name, vec):
+    """FG_FLAG_EVEN_VEC4 / _VEC2: 128- / 64-bit accesses, 4 / 2 cells per thread in the even step (the A/B of
+    BASELINE.json:5 (a)); same arithmetic per cell => same bits as the scalar kernel, with an immersed sphere as well."""
+    kw = dict(util.parity_cases(g)[name], nx=40, ny=12, nz=10, max_markers=300, max_links=1)
+    flag = g._abi.FLAG_EVEN_VEC4 if vec == 4 else g._abi.FLAG_EVEN_VEC2
+    a, b = g.Sim(backend=cuda, **kw), g.Sim(backend=cuda, flags=flag, **kw)
+    rho, u = util.smooth_fields(a.shape)
+    X = util.sphere_markers((20.2, 6.1, 5.3), 2.5, 80)
+    for s in (a, b):
+        s.set_fields(rho, u)
+        s.step(7)
+    assert np.array_equal(a.get_populations(), b.get_populations())
+    for s in (a, b):
+        s.set_markers(X, np.zeros_like(X), np.ones(80, np.float32))
+        s.step(6)
+    assert np.abs(a.get_populations() - b.get_populations()).max() < 2e-7      # spreading atomics are unordered
+    a.close(); b.close()

@@ -125,3 +125,39 @@ def test_peer_connect_all_after_set_markers_is_refused(g, emu):
     for s in parts:
         s.set_markers(X, np.zeros_like(X), np.ones(60, np.float32))
         s.set_link_origins([[8.2, 7.1, 5.5]])
+
+
+def test_fluid_divergence_guard_counts_the_same_cells_on_oracle_and_product(g, emu):
+    """fg_check_finite (ABI v7): cells whose rest population is not finite or out of range — 0 on a healthy run, the same
+    count on the oracle and on the product's kernel body once a NaN has been planted and spreads with the streaming."""
+    counts = []
+    for be in ("oracle", emu):
+        s = g.Sim(backend=be, nx=32, ny=24, nz=16, tau=0.8, collision=g.BGK)
+        rho, u = util.smooth_fields(s.shape)
+        s.set_fields(rho, u)
+        s.step(5)
+        assert s.check_finite() == 0
+        f = s.get_populations()
+        f[7, 3, 4, 5] = np.nan
+        s.set_populations(f)
+        s.step(1)
+        n1 = s.check_finite()
+        s.step(3)
+        counts.append((n1, s.check_finite()))
+    assert counts[0] == counts[1] and counts[0][0] >= 1 and counts[0][1] > counts[0][0]
+
+
+def test_env_reports_a_diverged_fluid(g, emu):
+    """env.py: info["diverged"] looks at the FLUID (fg_check_finite), not only at the body observation (VERDICT r1 weak #11)."""
+    from gym_fish_b200.env import EnvConfig, FishEnv, FishSpec
+    fish = FishSpec(links=((8, 2.5), (7, 2.5)), root=(12, 10, 14), free_root=False)
+    env = FishEnv(EnvConfig(grid=(24, 20, 32), tau=0.8, collision=g.BGK, n_substeps=2, fish=(fish,)), backend=emu)
+    env.reset(seed=0)
+    _, _, term, _, info = env.step(np.zeros(1, np.float32))
+    assert not term and info["fluid_bad_cells"] == 0 and not info["diverged"]
+    f = env.sim.get_populations()
+    f[:, 20:24] = np.nan                      # the fluid far from the (pinned) body blows up: the observation stays finite
+    env.sim.set_populations(f)
+    obs, _, term, _, info = env.step(np.zeros(1, np.float32))
+    assert np.isfinite(obs).all() and info["fluid_bad_cells"] > 0 and info["diverged"] and term
+    env.close()

@@ -1,5 +1,8 @@
-"""Multi-GPU z-slabs on real hardware: one process per GPU (torchrun), CUDA-IPC peer mapping, halos pushed over
-NVLink by the library.  Needs >= 2 GPUs (skipped otherwise); run with `gpurun --gpus 2 -- python -m pytest tests -m gpu -k multi_gpu`."""
+"""Multi-GPU z-slabs on real hardware: one PROCESS per slab (torchrun), CUDA-IPC peer mapping, halos pushed by peer
+stores by the library.  With >= 2 GPUs every process owns one (`gpurun --gpus 2 -- python -m pytest tests -m gpu -k
+multi_gpu`); on a box with ONE GPU the two processes share it (`device = local_rank % visible GPUs`): CUDA IPC maps a
+lattice of another process on the same device just as well, so the cross-process path — handle export / open, peer
+stores, system-scope flags between two contexts — runs under the driver's 1-GPU test box, too (only the wire differs)."""
 import os
 import subprocess
 import sys
@@ -19,6 +22,14 @@ def gpu_count():
         return sum(1 for line in out.splitlines() if line.startswith("GPU "))
     except OSError:
         return 0
+
+
+def _layout():
+    """(visible GPUs, processes): one process per GPU with 2 or 4 GPUs, two processes sharing the GPU when there is one."""
+    n = gpu_count()
+    if n < 1:
+        pytest.skip("needs a GPU")
+    return n, (2 if n < 4 else 4)
 
 
 WORKER = r"""
@@ -41,7 +52,7 @@ if fish:
 spheres = case == "spheres"
 if spheres:      # plane split on every rank: its own moving sphere, far interior planes collide beside the IB kernels
     kw = dict(nx=40, ny=36, nz=64 * world, tau=0.8, collision=g.MRT, max_markers=1000, max_links=1, split_min_cells=1)
-s = g.Sim(backend="cuda", n_ranks=world, rank=rank, device=local, flags={flags}, **kw)
+s = g.Sim(backend="cuda", n_ranks=world, rank=rank, device=local % {ngpu}, flags={flags}, **kw)
 h = kw["nz"] // world
 rho, u = util.smooth_fields((kw["nz"], kw["ny"], kw["nx"]))
 s.set_fields(rho[rank*h:(rank+1)*h], u[:, rank*h:(rank+1)*h])
@@ -91,13 +102,10 @@ dist.barrier(); s.close(); dist.destroy_process_group()
 @pytest.mark.parametrize("case", ["periodic", "channel"])
 @pytest.mark.parametrize("overlap", [True, False])
 def test_multi_gpu_slabs_bit_identical_to_one_gpu(g, cuda, case, overlap, tmp_path):
-    n = gpu_count()
-    if n < 2:
-        pytest.skip("needs >= 2 GPUs")
-    world = 2 if n < 4 else 4
+    n, world = _layout()
     out = str(tmp_path / "f.npy")
     script = tmp_path / "worker.py"
-    script.write_text(WORKER.format(root=ROOT, tests=os.path.join(ROOT, "tests"), case=case, out=out,
+    script.write_text(WORKER.format(root=ROOT, tests=os.path.join(ROOT, "tests"), case=case, out=out, ngpu=n,
                                     flags=0 if overlap else g._abi.FLAG_NO_OVERLAP))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
                         "127.0.0.1", "--master-port", str(29500 + os.getpid() % 2000), str(script)], capture_output=True, text=True, timeout=600)
@@ -117,13 +125,10 @@ def test_multi_gpu_fish_across_slab_faces(g, cuda, tmp_path):
     """Bodies crossing slab faces on real GPUs (fg_peer_connect_all): partial marker velocities and link wrenches travel
     by peer stores; every rank integrates the same fish and must end up with bit-identical observations, equal to the
     1-GPU run to round-off."""
-    n = gpu_count()
-    if n < 2:
-        pytest.skip("needs >= 2 GPUs")
-    world = 2 if n < 4 else 4
+    n, world = _layout()
     out = str(tmp_path / "f.npy")
     script = tmp_path / "worker.py"
-    script.write_text(WORKER.format(root=ROOT, tests=os.path.join(ROOT, "tests"), case="fish", out=out, flags=0))
+    script.write_text(WORKER.format(root=ROOT, tests=os.path.join(ROOT, "tests"), case="fish", out=out, flags=0, ngpu=n))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
                         "127.0.0.1", "--master-port", str(29500 + os.getpid() % 2000), str(script)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-3000:]
@@ -149,13 +154,10 @@ def test_multi_gpu_plane_split_matches_one_gpu(g, cuda, overlap, tmp_path):
     """Plane split on z-slabs (each rank: far interior planes before it even waits for its neighbours, IB kernels and
     boundary planes at high priority): the fluid must match the unsplit one-GPU run up to the order of the spreading
     atomics."""
-    n = gpu_count()
-    if n < 2:
-        pytest.skip("needs >= 2 GPUs")
-    world = 2 if n < 4 else 4
+    n, world = _layout()
     out = str(tmp_path / "f.npy")
     script = tmp_path / "worker.py"
-    script.write_text(WORKER.format(root=ROOT, tests=os.path.join(ROOT, "tests"), case="spheres", out=out,
+    script.write_text(WORKER.format(root=ROOT, tests=os.path.join(ROOT, "tests"), case="spheres", out=out, ngpu=n,
                                     flags=0 if overlap else g._abi.FLAG_NO_OVERLAP))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
                         "127.0.0.1", "--master-port", str(29500 + os.getpid() % 2000), str(script)], capture_output=True, text=True, timeout=600)
@@ -183,13 +185,10 @@ def test_multi_gpu_plane_split_matches_one_gpu(g, cuda, overlap, tmp_path):
 def test_multi_gpu_wavefront_pairs_bit_identical_to_one_gpu(g, cuda, case, tmp_path):
     """FG_FLAG_WAVEFRONT on peered slabs across real GPUs: two halo exchanges inside every pair, the interior wavefront hiding
     both; 33 substeps in two calls must leave exactly the populations of the plain one-GPU run."""
-    n = gpu_count()
-    if n < 2:
-        pytest.skip("needs >= 2 GPUs")
-    world = 2 if n < 4 else 4
+    n, world = _layout()
     out = str(tmp_path / "f.npy")
     script = tmp_path / "worker.py"
-    script.write_text(WORKER.format(root=ROOT, tests=os.path.join(ROOT, "tests"), case=case, out=out, flags=g._abi.FLAG_WAVEFRONT))
+    script.write_text(WORKER.format(root=ROOT, tests=os.path.join(ROOT, "tests"), case=case, out=out, flags=g._abi.FLAG_WAVEFRONT, ngpu=n))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
                         "127.0.0.1", "--master-port", str(29500 + os.getpid() % 2000), str(script)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-3000:]

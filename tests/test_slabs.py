@@ -74,15 +74,19 @@ def test_host_staged_slabs_equal_unsplit(g, emu, backend_name, case, n_ranks):
 
 
 @pytest.mark.parametrize("case", ["periodic_mrt", "inlet_outlet_walls"])
-@pytest.mark.parametrize("overlap", [True, False])
+@pytest.mark.parametrize("overlap", [True, False, "beside"])
 def test_device_peer_pushes_equal_unsplit(g, emu, case, overlap):
     """The product's multi-GPU path (halo pushes into the neighbour's lattice + step flags), here with both slabs in
-    one process on the emulated device; boundary-first ordering (overlap) must not change a bit."""
+    one process on the emulated device; boundary-first ordering (overlap) must not change a bit.  "beside": the interior
+    collide on the low-priority branch BESIDE the boundary chain (what slabs of >= 2^20 cells do by default) — under the
+    stream-order policies of test_stream_order.py the interior then runs before or after the chain, with equal bits."""
     kw = split_case(g, case)
     kw["nz"] = 16
     periodic = kw.get("bc", [0] * 6)[4] == g.BC_PERIODIC
     whole = g.Sim(backend=emu, **kw)
     flags = 0 if overlap else g._abi.FLAG_NO_OVERLAP
+    if overlap == "beside":
+        kw = dict(kw, split_min_cells=1)
     parts = [g.Sim(backend=emu, n_ranks=2, rank=r, flags=flags, **kw) for r in range(2)]
     rho, u = util.smooth_fields(whole.shape)
     whole.set_fields(rho, u)
@@ -96,6 +100,7 @@ def test_device_peer_pushes_equal_unsplit(g, emu, case, overlap):
         for s in parts:
             s.step(1)
     assert np.array_equal(whole.get_populations(), np.concatenate([s.get_populations() for s in parts], axis=1))
+    assert (parts[0].stats().split_substeps == 9) == (overlap == "beside")
     with pytest.raises(g.FgError):       # a slab that runs ahead of its neighbour is caught, not silently wrong
         parts[0].step(1)
         parts[0].step(1)

@@ -14,5 +14,5 @@ for f in files:
             e = d.get("e2e") or {}
             c = d.get("clocks") or {}
             print(f"{os.path.basename(f):30s} value {d['value']:9.0f} ms {d['ms_per_step']:.4f} e2e {e.get('value', 0):9.0f} frac {r.get('frac', 0):.3f} "
-                  f"k_ms {r.get('kernel_ms_per_launch', 0):.4f} ib_ms {r.get('ib_ms_per_step', 0):.4f} split {d['config'].get('plane_split_substeps')} "
+                  f"k_ms {r.get('kernel_ms_per_launch', 0):.4f} ib_ms {r.get('ib_ms_per_step', 0):.4f} split {(d.get("run") or {}).get("launch_mode")} "
                   f"L {d.get('gpu_launches')} clk {c.get('sm_mhz')} {c.get('reasons')} env/s {e.get('env_steps_per_s')}")
