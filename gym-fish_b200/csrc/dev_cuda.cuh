@@ -36,6 +36,12 @@ __global__ void __launch_bounds__(K::kThreads, K::kMinBlocks) kern_ticket(const 
     K::cta(p, int(threadIdx.x));
 }
 
+// persistent kernel (StreamCollidePair::cta_persistent): as many CTAs as the GPU holds at once, each walks the work list with a stride
+template <class K, class P>
+__global__ void __launch_bounds__(K::kThreads, K::kMinBlocks) kern_persist(const __grid_constant__ P p) {
+    K::cta_persistent(p, int(blockIdx.x), int(gridDim.x), int(threadIdx.x));
+}
+
 // phased kernel: K::kPhases phases of grid-stride work separated by grid-wide barriers (cooperative launch)
 template <class K, class P>
 __global__ void __launch_bounds__(K::kThreads, K::kMinBlocks) kern_phased(const __grid_constant__ P p) {
@@ -108,6 +114,8 @@ public:
     long long graph_launches = 0;      // cudaGraphLaunch calls (FgStats.graph_launches)
 
     int sm_count() const { return sm_count_; }
+    // IbInterpSpread: one warp per marker on the GPU (4 per CTA); the host emulation runs the per-thread form (2 markers per block)
+    static int interp_spread_blocks(int n_markers) { return (n_markers + 3) / 4; }
     // NVTX ranges per kernel class (step / ib / collide / faces): free when no tool is attached (nvtx3 is header-only and
     // resolves its injection library lazily), and they name the phases of a substep in an nsys / ncu timeline
     void range_push(const char *name) { nvtxRangePushA(name); }
@@ -339,6 +347,20 @@ public:
         const long long n = (long long)g.x * g.y * g.z * K::kGridPhases;
         if (n > 0x7fffffffll) { err = "ticketed launch too large"; return false; }
         return launch_on_current(kern_ticket<K, P>, dim3(unsigned(n)), K::kThreads, p);
+    }
+    // n_ctas_wanted CTAs at most, never more than are resident at once (the kernel's CTAs wait for each other)
+    template <class K, class P>
+    bool launch_persistent(long long n_ctas_wanted, const P &p) {
+        ++launches;
+        if (gmode_ == 2) return true;
+        static thread_local int per_sm = 0;      // per kernel instantiation
+        if (per_sm == 0) {
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern_persist<K, P>, K::kThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+        }
+        long long g = (long long)per_sm * sm_count_;
+        if (g > n_ctas_wanted) g = n_ctas_wanted;
+        if (g < 1) g = 1;
+        return launch_on_current(kern_persist<K, P>, dim3(unsigned(g)), K::kThreads, p);
     }
     bool zero_on_current(void *d, size_t n) {
         if (gmode_ == 2) return true;

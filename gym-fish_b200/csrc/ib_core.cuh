@@ -303,59 +303,80 @@ struct IbForceSpread {
     }
 };
 
-// (a5-a7) in one launch: both phases of a marker run in the same CTA (2 markers x 64 nodes), so a CTA barrier between
-// them is all the ordering U*_k needs (single-rank path; across slabs the exchange sits between the two).
-// run(): the two phases as the host emulation executes them.  cta(): what the GPU runs — stencil weights and band slot
-// computed once and kept in registers across the barrier, the three 1-D delta weights of a node fetched by shuffles
-// from the 12 lanes that evaluated them (one sqrt per thread instead of three; same values, same arithmetic).
+// (a5-a7) in one launch (single-rank path; across slabs the exchange sits between the two kernels above).
+// run(): the two phases as the host emulation executes them.  cta(): what the GPU runs — ONE WARP PER MARKER, two stencil
+// nodes per lane (planes c and c + 2 of the 4 x 4 x 4 stencil).  U*_k is then a butterfly reduction inside the warp: no
+// atomics on U*, no fence, no CTA barrier between interpolation and spreading — the round-1 form (64 threads per marker,
+// two warps meeting through L2 atomics + __threadfence + __syncthreads) was a chain of four dependent L2 round trips
+// per CTA and ran at 117 us for 1e5 markers with the memory system idle (profiles/r2_summary.md).  The three 1-D delta
+// weights of a node come by shuffle from the 12 lanes that evaluated them; static bodies read (weight, slot) of their
+// nodes from the per-node cache instead (cache_mode 2).
 struct IbInterpSpread {
-    static constexpr int kThreads = kNodes * kMarkersPerCta;
-    static constexpr int kMinBlocks = 8;
+    static constexpr int kThreads = 128;
+    static constexpr int kMarkers = kThreads / 32;       // markers per CTA on the GPU
+    static constexpr int kMinBlocks = 16;                // 28 registers: the full 2048 threads per SM
     static constexpr int kBlockPhases = 2;
+    // host emulation: launched with the grid of the per-thread kernels (2 markers x 64 nodes per block)
     FG_HD static void run(const IbParams &p, int bx, int by, int bz, int tx, int phase) {
         if (phase == 0) IbInterpolate::run(p, bx, by, bz, tx);
         else IbForceSpread::run(p, bx, by, bz, tx);
     }
 #if defined(__CUDACC__)
+    __device__ __forceinline__ static float warp_all_sum(float v) {
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        return v;
+    }
     __device__ __forceinline__ static void cta(const IbParams &p, int bx, int tx) {
         const int gt = bx * kThreads + tx;
         if (gt < 6 * p.n_links) p.wrench[gt] = 0.0;           // accumulated by IbLinkReduce
-        const int k = bx * kMarkersPerCta + tx / kNodes, node = tx % kNodes;
-        const bool live = k < p.n && !(p.gidx && p.gidx[k] < 0);     // warp-uniform: a warp holds half a marker
-        float w = 0.f;
-        int s = -1;
-        if (live) {
-            const int lane = tx & 31;
-            if (p.cache_mode == 2) {
-                // static body: one coalesced 8-byte read per node instead of the delta weights, the wrap logic and a
-                // scattered cellslot gather (cellslot is a dense 4 B-per-cell array: every gather costs a DRAM sector)
-                w = p.node_w[gt]; s = p.node_s[gt];
-            } else {
-                const int sel = lane % 12, axis = sel >> 2, j = sel & 3;
-                const float w1 = peskin4(p.X[3 * k + axis] - float(p.base[3 * k + axis] + j));
-                const int a = node & 3, b = (node >> 2) & 3, c = node >> 4;
-                const float wx = __shfl_sync(0xffffffffu, w1, a), wy = __shfl_sync(0xffffffffu, w1, 4 + b), wz = __shfl_sync(0xffffffffu, w1, 8 + c);
-                w = wx * wy * wz;
-                const long long cell = stencil_cell(p, p.base[3 * k], p.base[3 * k + 1], p.base[3 * k + 2], a, b, c);
-                s = cell >= 0 ? p.cellslot[cell] - 1 : -1;
-                if (p.cache_mode == 1) { p.node_w[gt] = w; p.node_s[gt] = s; }
+        const int k = bx * kMarkers + (tx >> 5), lane = tx & 31;
+        if (k >= p.n || (p.gidx && p.gidx[k] < 0)) return;    // warp-uniform
+        float w0, w1;
+        int s0, s1;
+        const size_t nb = (size_t)k * kNodes;
+        if (p.cache_mode == 2) {
+            // static body: two coalesced 8-byte reads per lane instead of the delta weights, the wrap logic and two
+            // scattered cellslot gathers (cellslot is a dense 4 B-per-cell array: every gather costs a DRAM sector)
+            w0 = p.node_w[nb + lane]; w1 = p.node_w[nb + 32 + lane];
+            s0 = p.node_s[nb + lane]; s1 = p.node_s[nb + 32 + lane];
+        } else {
+            const int sel = lane % 12, axis = sel >> 2, j = sel & 3;
+            const float w1d = peskin4(p.X[3 * k + axis] - float(p.base[3 * k + axis] + j));
+            const int a = lane & 3, b = (lane >> 2) & 3, c = lane >> 4;          // node `lane`: plane c; node `lane + 32`: plane c + 2
+            const float wxy = __shfl_sync(0xffffffffu, w1d, a) * __shfl_sync(0xffffffffu, w1d, 4 + b);
+            w0 = wxy * __shfl_sync(0xffffffffu, w1d, 8 + c);
+            w1 = wxy * __shfl_sync(0xffffffffu, w1d, 10 + c);
+            const int i0 = p.base[3 * k], j0 = p.base[3 * k + 1], k0 = p.base[3 * k + 2];
+            const long long c0 = stencil_cell(p, i0, j0, k0, a, b, c), c1 = stencil_cell(p, i0, j0, k0, a, b, c + 2);
+            s0 = c0 >= 0 ? p.cellslot[c0] - 1 : -1;
+            s1 = c1 >= 0 ? p.cellslot[c1] - 1 : -1;
+            if (p.cache_mode == 1) {
+                p.node_w[nb + lane] = w0; p.node_w[nb + 32 + lane] = w1;
+                p.node_s[nb + lane] = s0; p.node_s[nb + 32 + lane] = s1;
             }
-            float u0 = 0.f, u1 = 0.f, u2 = 0.f;
-            if (s >= 0) { u0 = w * p.band_u[s]; u1 = w * p.band_u[p.band_cap + s]; u2 = w * p.band_u[2 * p.band_cap + s]; }
-            u0 = warp_sum(u0); u1 = warp_sum(u1); u2 = warp_sum(u2);
-            if (lane == 0) { atomicAdd(&p.Ustar[3 * k], u0); atomicAdd(&p.Ustar[3 * k + 1], u1); atomicAdd(&p.Ustar[3 * k + 2], u2); }
         }
-        __threadfence();          // the partial sums of the marker's two warps meet in L2
-        __syncthreads();
-        if (!live) return;
-        const float f0 = 2.0f * (p.U[3 * k] - __ldcg(&p.Ustar[3 * k])), f1 = 2.0f * (p.U[3 * k + 1] - __ldcg(&p.Ustar[3 * k + 1])),
-                    f2 = 2.0f * (p.U[3 * k + 2] - __ldcg(&p.Ustar[3 * k + 2]));
-        if (node == 0) { p.Fm[3 * k] = f0; p.Fm[3 * k + 1] = f1; p.Fm[3 * k + 2] = f2; }
-        if (s < 0) return;
-        w *= p.dV[k];
-        atomicAdd(&p.bandF[s], w * f0);
-        atomicAdd(&p.bandF[p.band_cap + s], w * f1);
-        atomicAdd(&p.bandF[2 * p.band_cap + s], w * f2);
+        float u0 = 0.f, u1 = 0.f, u2 = 0.f;
+        if (s0 >= 0) { u0 = w0 * p.band_u[s0]; u1 = w0 * p.band_u[p.band_cap + s0]; u2 = w0 * p.band_u[2 * p.band_cap + s0]; }
+        if (s1 >= 0) { u0 += w1 * p.band_u[s1]; u1 += w1 * p.band_u[p.band_cap + s1]; u2 += w1 * p.band_u[2 * p.band_cap + s1]; }
+        u0 = warp_all_sum(u0); u1 = warp_all_sum(u1); u2 = warp_all_sum(u2);          // every lane holds U*_k
+        const float f0 = 2.0f * (p.U[3 * k] - u0), f1 = 2.0f * (p.U[3 * k + 1] - u1), f2 = 2.0f * (p.U[3 * k + 2] - u2);
+        if (lane == 0) {
+            p.Ustar[3 * k] = u0; p.Ustar[3 * k + 1] = u1; p.Ustar[3 * k + 2] = u2;
+            p.Fm[3 * k] = f0; p.Fm[3 * k + 1] = f1; p.Fm[3 * k + 2] = f2;
+        }
+        const float dV = p.dV[k];
+        if (s0 >= 0) {
+            const float w = w0 * dV;
+            atomicAdd(&p.bandF[s0], w * f0); atomicAdd(&p.bandF[p.band_cap + s0], w * f1); atomicAdd(&p.bandF[2 * p.band_cap + s0], w * f2);
+        }
+        if (s1 >= 0) {
+            const float w = w1 * dV;
+            atomicAdd(&p.bandF[s1], w * f0); atomicAdd(&p.bandF[p.band_cap + s1], w * f1); atomicAdd(&p.bandF[2 * p.band_cap + s1], w * f2);
+        }
     }
 #endif
 };
@@ -856,7 +877,7 @@ public:
             ok = ok && (parity == 0 ? dev.template launch<IbBandMoments<0>>(Dim3x((bound2 + 127) / 128), p)
                                     : dev.template launch<IbBandMoments<1>>(Dim3x((bound2 + 127) / 128), p));
             if (!xchg_) {
-                ok = ok && dev.template launch_block_phased<IbInterpSpread>(Dim3x(std::max(nb, (6 * nl_ + 127) / 128)), p);
+                ok = ok && dev.template launch_block_phased<IbInterpSpread>(Dim3x(std::max(dev.interp_spread_blocks(n_), (6 * nl_ + 127) / 128)), p);
                 ok = ok && dev.template launch<IbLinkReduce>(Dim3x((n_ + 127) / 128), p);
             } else {
                 // bodies across slab faces: the exchange of partial U* sits between interpolation and spreading

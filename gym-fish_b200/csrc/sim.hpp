@@ -62,9 +62,9 @@ public:
         flags_ = static_cast<int *>(dev.alloc(4 * sizeof(int), err));
         if (!flags_) return FG_ENOMEM;
         if (!dev.zero(flags_, 4 * sizeof(int))) return cuda_fail();
-        pair_ctr_ = static_cast<int *>(dev.alloc(sizeof(int) * size_t(L_.nz + 3), err));
+        pair_ctr_ = static_cast<int *>(dev.alloc(pair_ctr_bytes(), err));
         if (!pair_ctr_) return FG_ENOMEM;
-        if (!dev.zero(pair_ctr_, sizeof(int) * size_t(L_.nz + 3))) return cuda_fail();
+        if (!dev.zero(pair_ctr_, pair_ctr_bytes())) return cuda_fail();
         setup_collision();
         if (cfg.max_markers > 0) {
             if (int rc = ib_.create(dev, cfg, L_, err)) return rc;
@@ -133,6 +133,7 @@ public:
 
     int get_moments(std::vector<float> &mom) {
         if (int rc = halos_ready_for_readout()) return rc;
+        if (int rc = check_pair_error()) return rc;
         const size_t n = size_t(L_.plane) * L_.nz;
         float *d = static_cast<float *>(dev.alloc(4 * n * sizeof(float), err));
         if (!d) return FG_ENOMEM;
@@ -176,6 +177,7 @@ public:
 
     int get_populations(float *f19) {
         if (int rc = halos_ready_for_readout()) return rc;
+        if (int rc = check_pair_error()) return rc;
         const size_t n = size_t(L_.plane) * L_.nz;
         float *d = static_cast<float *>(dev.alloc(size_t(Q) * n * sizeof(float), err));
         if (!d) return FG_ENOMEM;
@@ -417,6 +419,7 @@ public:
                 int done[2][2];
                 if (!launch_pair(1, L_.nz + 1, 0, 0, done) || !launch_faces()) return cuda_fail();
                 parity_ = 1;
+                if (!launch_pair_wall_rows(done)) return cuda_fail();
                 // the planes at the range ends (their z-neighbours are ghost planes, set by the face operations above)
                 if (!launch_collide_except(1, L_.nz + 1, ForceField{}, done) || !launch_faces()) return cuda_fail();
                 parity_ = 0;
@@ -680,6 +683,7 @@ public:
         return k;
     }
     int fail(int code, const std::string &m) { err = m; return code; }
+    int check_pair_error() { return check_pair_error_impl(); }
     int cuda_fail() { err = dev.err; return FG_ECUDA; }
 
 private:
@@ -730,8 +734,13 @@ private:
 #if defined(FG_POP16)
         return 0;
 #else
+        if (cfg.flags & FG_FLAG_EVEN_SCALAR) return 0;
         if ((cfg.flags & FG_FLAG_EVEN_VEC4) && L_.nx % 4 == 0) return 4;
         if ((cfg.flags & FG_FLAG_EVEN_VEC2) && L_.nx % 2 == 0) return 2;
+        // default (round 2, gpu pass 2): two cells per thread with 64-bit accesses wherever a row fills whole CTAs that way —
+        // +2.6 ... +3.2 % MLUPS on 256- and 512-wide lattices (fewer memory instructions per byte; the 4-cell form gains
+        // less: 125 registers leave 4 CTAs per SM).  Narrower rows would leave half of each CTA idle and keep the scalar kernel.
+        if (L_.nx % (2 * kCollideThreads) == 0) return 2;
         return 0;
 #endif
     }
@@ -859,16 +868,46 @@ private:
         p.odd_skip_v = hole ? hole_b - zb : -1;
         p.odd_y_lo = L_.wall_y ? 1 : 0; p.odd_y_hi = L_.wall_y ? L_.ny - 1 : L_.ny;
         p.ticket = pair_ctr_; p.done = pair_ctr_ + 1;
+        p.err = pair_ctr_ + 1 + (L_.nz + 2); p.wdone = p.err + 1;
         if (hole) { done[0][0] = zb + p.odd_lo; done[0][1] = hole_b - 1; done[1][0] = hole_e + 1; done[1][1] = ze - (out_hi ? 2 : 1); }
         else { done[0][0] = zb + p.odd_lo; done[0][1] = ze - (out_hi ? 2 : 1); }
         for (int i = 0; i < 2; ++i) if (done[i][1] < done[i][0]) done[i][0] = done[i][1] = 0;
         const Dim3 g{p.xblocks, p.rows, planes};
-        if (!dev.zero_on_current(pair_ctr_, sizeof(int) * size_t(planes + 1))) return false;
         const bool mrt = cfg.collision == FG_MRT;
+        if (cfg.flags & FG_FLAG_PAIR_PERSISTENT) {
+            p.skip_wall_rows = 1;
+            // persistent form: the error word stays (sticky), the per-plane warp counters start at zero
+            if (!dev.zero_on_current(p.wdone, sizeof(int) * size_t(planes) * kPairSub)) return false;
+            const long long items = 2ll * planes * p.rows * p.xblocks;
+            if (items > 0x7fffffffll) { dev.err = "persistent pair launch too large"; return false; }
+            if (L_.wall_x) return mrt ? dev.template launch_persistent<StreamCollidePair<true, CHECK_XEDGE>>(items, p)
+                                      : dev.template launch_persistent<StreamCollidePair<false, CHECK_XEDGE>>(items, p);
+            return mrt ? dev.template launch_persistent<StreamCollidePair<true, CHECK_NONE>>(items, p)
+                       : dev.template launch_persistent<StreamCollidePair<false, CHECK_NONE>>(items, p);
+        }
+        if (!dev.zero_on_current(pair_ctr_, sizeof(int) * size_t(planes + 1))) return false;
         if (L_.wall_x) return mrt ? dev.template launch_ticketed<StreamCollidePair<true, CHECK_XEDGE>>(g, p)
                                   : dev.template launch_ticketed<StreamCollidePair<false, CHECK_XEDGE>>(g, p);
         return mrt ? dev.template launch_ticketed<StreamCollidePair<true, CHECK_NONE>>(g, p)
                    : dev.template launch_ticketed<StreamCollidePair<false, CHECK_NONE>>(g, p);
+    }
+    // the persistent pair kernel leaves the y-wall rows of its odd phase to this thin checked launch (parity_ == 1)
+    bool launch_pair_wall_rows(const int done[2][2]) {
+        if (!(cfg.flags & FG_FLAG_PAIR_PERSISTENT) || !L_.wall_y) return true;
+        for (int i = 0; i < 2; ++i) {
+            if (done[i][1] <= done[i][0]) continue;
+            if (L_.ny >= 2) { if (!launch_rows(CHECK_ALL, done[i][0], done[i][1], 0, L_.ny - 1, 2, ForceField{})) return false; }
+            else if (!launch_rows(CHECK_ALL, done[i][0], done[i][1], 0, 1, 1, ForceField{})) return false;
+        }
+        return true;
+    }
+    size_t pair_ctr_bytes() const { return sizeof(int) * (size_t(L_.nz + 3) + 1 + size_t(L_.nz + 2) * kPairSub); }   // ticket, done[], err, wdone[]
+    // raised by the persistent pair kernel when a dependency wait gave up (a bug, or a grid that was not co-resident)
+    int check_pair_error_impl() {
+        if (!(cfg.flags & FG_FLAG_PAIR_PERSISTENT) || pair_substeps_ == 0) return FG_OK;
+        int e = 0;
+        if (!dev.sync() || !dev.d2h(&e, pair_ctr_ + 1 + (L_.nz + 2), sizeof(int))) return cuda_fail();
+        return e ? fail(FG_ECUDA, "persistent step-pair kernel: a dependency wait timed out (results of this handle are invalid)") : FG_OK;
     }
     // the odd step runs this many planes behind the even step: far enough that it never waits, near enough that the
     // planes in between (lag x 76 B x nx x ny) stay in L2

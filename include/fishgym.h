@@ -68,8 +68,10 @@ extern "C" {
 #define FG_FLAG_NO_XWARP 128   /* x walls: predicated wall selects in every thread (default: only the two warps at the row ends run the wall code) */
 #define FG_FLAG_SYNC_STEP 256  /* fg_step returns only when all its device work has finished (default: when wrenches / obs are there) */
 #define FG_FLAG_WAVEFRONT 512  /* EXPERIMENT (unmeasured): even step + following odd step as a launch-level wavefront of plane chunks on two streams, the odd step one chunk behind the even one, so that it finds its populations in L2 (one rank or peered z-slabs; prescribed markers or fish inside a slab — with fish the pair is launched directly, not as a graph; no bodies across slab faces) */
-#define FG_FLAG_EVEN_VEC4 1024 /* EXPERIMENT (A/B in profiles/r2_summary.md): even steps take 4 cells per thread with 128-bit loads / stores (needs nx % 4 == 0, no obstacles) */
-#define FG_FLAG_EVEN_VEC2 2048 /* ... 2 cells per thread with 64-bit accesses (nx % 2 == 0) */
+#define FG_FLAG_EVEN_VEC4 1024 /* even steps take 4 cells per thread with 128-bit loads / stores (needs nx % 4 == 0, no obstacles); measured +1.3 ... +2.4 %, less than the 2-cell form (profiles/r2_summary.md) */
+#define FG_FLAG_EVEN_VEC2 2048 /* ... 2 cells per thread with 64-bit accesses for any even nx (the DEFAULT when nx is a multiple of 256: +2.6 ... +3.2 %) */
+#define FG_FLAG_EVEN_SCALAR 8192 /* even steps with the scalar one-cell-per-thread kernel everywhere (A/B against the default) */
+#define FG_FLAG_PAIR_PERSISTENT 4096 /* with FG_FLAG_FUSED_PAIRS: the step pair as a PERSISTENT kernel (one CTA per resident slot walking the wavefront schedule, completion published one item late, no tickets / CTA barriers) */
 #define FG_FLAG_NO_SPLIT  16   /* collide all planes after the IB kernels (default: planes away from the bodies run beside them) */
 
 typedef struct FgConfig {

@@ -28,6 +28,7 @@ public:
     long long launches = 0;
     long long graph_launches = 0;
     int sm_count() const { return 148; }
+    static int interp_spread_blocks(int n_markers) { return (n_markers + 1) / 2; }
     void range_push(const char *) {}
     void range_pop() {}
     long long n_submit = 0, n_record = 0, n_wait = 0;      // FG_EMU_DEBUG: operations queued (what the CUDA policy would issue as API calls)
@@ -133,6 +134,8 @@ public:
             return true;
         });
     }
+    template <class K, class P>
+    bool launch_persistent(long long n_ctas, const P &p) { return launch_ticketed<K, P>(Dim3{p.xblocks, p.rows, p.planes}, p); (void)n_ctas; }
     bool zero_on_current(void *d, size_t n) { return submit(cur_, [=] { std::memset(d, 0, n); return true; }); }
 
     // phased kernels (one cooperative launch on the GPU): phases in order, every item of a phase before the next

@@ -125,12 +125,15 @@ def test_plane_split_far_collide_beside_ib_kernels(g, emu, walls):
 
 @pytest.mark.parametrize("name", ["bgk_periodic", "mrt_force", "bgk_ywall_moving", "mrt_xy_walls", "mrt_all_walls_lid", "bgk_inlet_outlet",
                                   "mrt_inlet_outlet_ywalls", "mrt_outlet_inlet_xwalls"])
-def test_fused_step_pairs_are_bit_identical_to_single_steps(g, emu, name):
+@pytest.mark.parametrize("persistent", [False, True])
+def test_fused_step_pairs_are_bit_identical_to_single_steps(g, emu, name, persistent):
     """StreamCollidePair (opt-in, FG_FLAG_FUSED_PAIRS): even step + following odd step of the same planes in one launch.  Per cell it is the same
     arithmetic in the same order, so populations must not differ by a bit from stepping one launch per step, for any
     number of substeps per call (pairs only form inside one fg_step call) and every boundary kind."""
     kw = dict(util.parity_cases(g)[name], nz=12)
-    a, b = g.Sim(backend=emu, flags=g._abi.FLAG_FUSED_PAIRS, **kw), g.Sim(backend=emu, **kw)
+    # persistent: the round-2 form of the pair kernel; it leaves the y-wall rows of its odd phase to a thin checked launch
+    fl = g._abi.FLAG_FUSED_PAIRS | (g._abi.FLAG_PAIR_PERSISTENT if persistent else 0)
+    a, b = g.Sim(backend=emu, flags=fl, **kw), g.Sim(backend=emu, **kw)
     rho, u = util.smooth_fields(a.shape)
     for s in (a, b):
         s.set_fields(rho, u)
@@ -300,3 +303,17 @@ def test_static_body_node_cache_matches_recomputation(g, emu, graphs, monkeypatc
         assert np.array_equal(a.get_populations(), b.get_populations())
         assert np.array_equal(a.get_link_wrenches(), b.get_link_wrenches())
         assert np.array_equal(a.get_marker_forces(), b.get_marker_forces())
+
+
+def test_default_even_step_on_wide_rows_is_the_two_cell_kernel_and_bit_identical(g, emu):
+    """nx a multiple of 256: the even step defaults to two cells per thread (sim.hpp even_vec_width); FG_FLAG_EVEN_SCALAR
+    is the one-cell kernel.  Same bits, with y walls and a body force; against the oracle as well."""
+    P, Wl = g.BC_PERIODIC, g.BC_WALL
+    kw = dict(nx=256, ny=5, nz=4, tau=0.7, collision=g.MRT, bc=[P, P, Wl, Wl, P, P], body_force=[1e-4, 0, 2e-4])
+    a, b, o = g.Sim(backend=emu, **kw), g.Sim(backend=emu, flags=g._abi.FLAG_EVEN_SCALAR, **kw), g.Sim(backend="oracle", **kw)
+    rho, u = util.smooth_fields(a.shape)
+    for s in (a, b, o):
+        s.set_fields(rho, u)
+        s.step(6)
+    assert np.array_equal(a.get_populations(), b.get_populations())
+    assert util.rel_l2(a.get_fields(f64=True)[1], o.get_fields(f64=True)[1]) <= TOL_FIELD
