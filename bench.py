@@ -579,14 +579,12 @@ def main():
     ap.add_argument("--no-graphs", action="store_true", help="launch kernels directly instead of per-substep CUDA graphs")
     ap.add_argument("--no-flip", action="store_true", help="sweep planes upwards in every step (no L2 reuse between steps)")
     ap.add_argument("--pairs", action="store_true", help="fused even+odd wavefront launches (opt-in experiment, measured slower)")
-    ap.add_argument("--pair-lag", type=int, default=0, help="planes between the even and odd wavefront / per wavefront chunk (0: automatic)")
-    ap.add_argument("--wavefront", action="store_true", help="even + odd step as a launch-level wavefront of plane chunks (opt-in experiment, FG_FLAG_WAVEFRONT)")
+    ap.add_argument("--pair-lag", type=int, default=0, help="--pairs: planes between the even and the odd wavefront (0: automatic)")
     ap.add_argument("--no-xwarp", action="store_true", help="x walls: predicated wall code in every thread instead of only in the row-end warps")
     ap.add_argument("--storage", default="f32", choices=["f32", "f16"],
                     help="f16: the opt-in 16-bit-storage build (fp32 arithmetic, 76 B per cell update; NOT the headline configuration)")
     ap.add_argument("--even-vec", type=int, default=0, choices=[0, 1, 2, 4],
                     help="even steps with 1 / 2 / 4 cells per thread (32- / 64- / 128-bit accesses); 0: the library's default (2 where nx %% 256 == 0)")
-    ap.add_argument("--persistent-pairs", action="store_true", help="even + odd step as ONE persistent wavefront kernel (FG_FLAG_FUSED_PAIRS | FG_FLAG_PAIR_PERSISTENT)")
     ap.add_argument("--no-split", action="store_true", help="collide all planes after the IB kernels (no far-plane branch beside them)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer loop (default: --steps)")
     ap.add_argument("--ref-budget-s", type=float, default=150.0, help="--impl reference: wall-clock budget that sizes the oracle's sample")
@@ -629,8 +627,7 @@ def main():
     flags = ((A.FLAG_NO_OVERLAP if args.no_overlap else 0) | (A.FLAG_NO_GRAPHS if args.no_graphs else 0) |
              (A.FLAG_NO_SPLIT if args.no_split else 0) | (A.FLAG_NO_SWEEP_FLIP if args.no_flip else 0) |
              (A.FLAG_FUSED_PAIRS if args.pairs else 0) | (A.FLAG_NO_XWARP if args.no_xwarp else 0) |
-             (A.FLAG_WAVEFRONT if args.wavefront else 0) | {0: 0, 1: A.FLAG_EVEN_SCALAR, 2: A.FLAG_EVEN_VEC2, 4: A.FLAG_EVEN_VEC4}[args.even_vec] |
-             ((A.FLAG_FUSED_PAIRS | A.FLAG_PAIR_PERSISTENT) if args.persistent_pairs else 0))
+             {0: 0, 1: A.FLAG_EVEN_SCALAR, 2: A.FLAG_EVEN_VEC2, 4: A.FLAG_EVEN_VEC4}[args.even_vec])
     bytes_per_update = BYTES_PER_CELL_UPDATE if args.storage == "f32" else BYTES_PER_CELL_UPDATE / 2
 
     clocks = ClockSampler(local) if rank == 0 else None      # runs through warm-up, the timed region and the profiled pass
@@ -703,9 +700,8 @@ def main():
         "config": cfg,
         "run": {"population_storage": args.storage, "markers_per_gpu": main_res["markers_per_gpu"],
                 "decomposition": "z-slabs, halos by peer stores over NVLink (CUDA IPC), no NCCL on the data path" if world > 1 else "single GPU",
-                "halo_overlap": not args.no_overlap, "launch_mode": main_res["launch_mode"], "wavefront_pairs": bool(args.wavefront),
-                "even_step_cells_per_thread": args.even_vec or "library default (2 where nx % 256 == 0, else 1)",
-                "persistent_pairs": bool(args.persistent_pairs)},
+                "halo_overlap": not args.no_overlap, "launch_mode": main_res["launch_mode"],
+                "even_step_cells_per_thread": args.even_vec or "library default (2 where nx % 256 == 0, else 1)"},
         "roofline": main_res.get("roofline"), "cpu_baseline": cpu, "e2e": main_res.get("e2e"), "gpu_launches": main_res["gpu_launches"], "clocks": clk,
         "pct_of_hbm_roofline": main_res["pct_of_hbm_roofline"],
         "sub_records": sub or None,

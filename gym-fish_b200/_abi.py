@@ -30,10 +30,8 @@ FLAG_NO_SWEEP_FLIP = 32
 FLAG_FUSED_PAIRS = 64
 FLAG_NO_XWARP = 128
 FLAG_SYNC_STEP = 256
-FLAG_WAVEFRONT = 512
 FLAG_EVEN_VEC4 = 1024
 FLAG_EVEN_VEC2 = 2048
-FLAG_PAIR_PERSISTENT = 4096
 FLAG_EVEN_SCALAR = 8192
 
 _ERR_NAMES = {FG_EINVAL: "FG_EINVAL", FG_ENOMEM: "FG_ENOMEM", FG_ECUDA: "FG_ECUDA", FG_ESTATE: "FG_ESTATE",

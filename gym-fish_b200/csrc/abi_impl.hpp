@@ -199,7 +199,6 @@ int fg_sync(FgSim *s) {
     if (!s) return FG_EINVAL;
     s->sim.dev.enter();
     if (!s->sim.dev.sync()) return s->sim.cuda_fail();
-    if (int rc = s->sim.check_pair_error()) return rc;
     return s->sim.check_peer_timeout();
 }
 int fg_get_stats(FgSim *s, FgStats *o) {

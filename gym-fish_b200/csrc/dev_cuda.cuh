@@ -36,12 +36,6 @@ __global__ void __launch_bounds__(K::kThreads, K::kMinBlocks) kern_ticket(const 
     K::cta(p, int(threadIdx.x));
 }
 
-// persistent kernel (StreamCollidePair::cta_persistent): as many CTAs as the GPU holds at once, each walks the work list with a stride
-template <class K, class P>
-__global__ void __launch_bounds__(K::kThreads, K::kMinBlocks) kern_persist(const __grid_constant__ P p) {
-    K::cta_persistent(p, int(blockIdx.x), int(gridDim.x), int(threadIdx.x));
-}
-
 // phased kernel: K::kPhases phases of grid-stride work separated by grid-wide barriers (cooperative launch)
 template <class K, class P>
 __global__ void __launch_bounds__(K::kThreads, K::kMinBlocks) kern_phased(const __grid_constant__ P p) {
@@ -348,20 +342,6 @@ public:
         if (n > 0x7fffffffll) { err = "ticketed launch too large"; return false; }
         return launch_on_current(kern_ticket<K, P>, dim3(unsigned(n)), K::kThreads, p);
     }
-    // n_ctas_wanted CTAs at most, never more than are resident at once (the kernel's CTAs wait for each other)
-    template <class K, class P>
-    bool launch_persistent(long long n_ctas_wanted, const P &p) {
-        ++launches;
-        if (gmode_ == 2) return true;
-        static thread_local int per_sm = 0;      // per kernel instantiation
-        if (per_sm == 0) {
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern_persist<K, P>, K::kThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
-        }
-        long long g = (long long)per_sm * sm_count_;
-        if (g > n_ctas_wanted) g = n_ctas_wanted;
-        if (g < 1) g = 1;
-        return launch_on_current(kern_persist<K, P>, dim3(unsigned(g)), K::kThreads, p);
-    }
     bool zero_on_current(void *d, size_t n) {
         if (gmode_ == 2) return true;
         return ck(cudaMemsetAsync(d, 0, n, s_[cur_]), "memset");
@@ -533,7 +513,7 @@ private:
     cudaEvent_t tev_[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
     int tpair_ = 0;
     std::vector<std::pair<std::string, void *>> opened_;
-    static constexpr int kStreams = 6;      // 0/1 high priority (main + thin branch), 2/3 and 4/5 low (far branch; odd wavefront)
+    static constexpr int kStreams = 4;      // 0/1 high priority (main + thin branch), 2/3 low (far branch + its thin branch)
     cudaStream_t s_[kStreams] = {};
     cudaEvent_t fork_ev_[kStreams] = {}, join_ev_[kStreams] = {};
     int cur_ = 0;

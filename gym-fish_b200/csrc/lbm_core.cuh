@@ -344,19 +344,9 @@ FG_HD Nbr make_nbr(const Lattice &L, int x, int y, int zz) {
     return n;
 }
 
-// L2-only load (ld.global.cg): for populations another SM wrote earlier in the SAME kernel (the persistent step-pair
-// kernel below) — the L1 of this SM is not coherent with those stores
-FG_HD float pop_ld_cg(const pop_t *p) {
-#if defined(__CUDA_ARCH__) && !defined(FG_POP16)
-    return __ldcg(p);
-#else
-    return pop_ld(p);
-#endif
-}
-
 // ---------------------------------------------------------------- AA-pattern loads / stores
 // Load the populations ARRIVING at the cell (f_i(x,t)) for the given storage parity.
-template <int I, bool CHECK, bool CG = false>
+template <int I, bool CHECK>
 FG_HD void odd_load_pair(float (&h)[Q], const Lattice &L, const Collision &C, const Nbr &nb, long long idx) {
     using D = Dir<I>;
     constexpr int J = D::opp;
@@ -368,12 +358,11 @@ FG_HD void odd_load_pair(float (&h)[Q], const Lattice &L, const Collision &C, co
         const int wp = nb.wall<D::cx, D::cy, D::cz>();
         const bool bm = wm >= 0 || (L.solid && L.solid[idx + om]);
         const bool bp = wp >= 0 || (L.solid && L.solid[idx + op]);
-        const pop_t *aI = bm ? fI + idx : fJ + idx + om, *aJ = bp ? fJ + idx : fI + idx + op;
-        h[I] = (CG ? pop_ld_cg(aI) : pop_ld(aI)) + (bm && wm >= 0 ? C.wallterm[wm][I] : 0.0f);
-        h[J] = (CG ? pop_ld_cg(aJ) : pop_ld(aJ)) + (bp && wp >= 0 ? C.wallterm[wp][J] : 0.0f);
+        h[I] = bm ? pop_ld(fI + idx) + (wm >= 0 ? C.wallterm[wm][I] : 0.0f) : pop_ld(fJ + idx + om);
+        h[J] = bp ? pop_ld(fJ + idx) + (wp >= 0 ? C.wallterm[wp][J] : 0.0f) : pop_ld(fI + idx + op);
     } else {
-        h[I] = CG ? pop_ld_cg(fJ + idx + om) : pop_ld(fJ + idx + om);
-        h[J] = CG ? pop_ld_cg(fI + idx + op) : pop_ld(fI + idx + op);
+        h[I] = pop_ld(fJ + idx + om);
+        h[J] = pop_ld(fI + idx + op);
     }
 }
 
@@ -399,14 +388,14 @@ FG_HD void odd_store_pair(const float (&h)[Q], const Lattice &L, const Collision
 
 #define FG_FOR_PAIRS(X) X(1) X(3) X(5) X(7) X(8) X(11) X(12) X(15) X(16)
 
-template <int PARITY, bool CHECK, bool CG = false>
+template <int PARITY, bool CHECK>
 FG_HD void load_arriving(float (&h)[Q], const Lattice &L, const Collision &C, const Nbr &nb, long long idx) {
     if (PARITY == 0) {
         FG_UNROLL
         for (int i = 0; i < Q; ++i) h[i] = pop_ld(L.f + i * L.slot + idx);
     } else {
-        h[0] = CG ? pop_ld_cg(L.f + idx) : pop_ld(L.f + idx);
-#define FG_X(I) odd_load_pair<I, CHECK, CG>(h, L, C, nb, idx);
+        h[0] = pop_ld(L.f + idx);
+#define FG_X(I) odd_load_pair<I, CHECK>(h, L, C, nb, idx);
         FG_FOR_PAIRS(FG_X)
 #undef FG_X
     }
@@ -464,7 +453,7 @@ FG_HD NbrPtrs make_ptrs(const Lattice &L, int x, int y, long long idx) {
     return n;
 }
 
-template <int I, bool XEDGE, bool CG = false>
+template <int I, bool XEDGE>
 FG_HD void fast_odd_load_pair(float (&h)[Q], const StepParams &p, const NbrPtrs &n) {
     using D = Dir<I>;
     constexpr int J = D::opp;
@@ -476,11 +465,11 @@ FG_HD void fast_odd_load_pair(float (&h)[Q], const StepParams &p, const NbrPtrs 
         const bool bp = D::cx > 0 ? n.bxp : n.bxm;   // the cell at x + c_I is behind the wall
         const char *own_i = n.p[1][1] + p.kz[I][1], *own_j = n.p[1][1] + p.kz[J][1];
         const float wi = p.C.wallterm[D::cx > 0 ? F_XLO : F_XHI][I], wj = p.C.wallterm[D::cx > 0 ? F_XHI : F_XLO][J];
-        h[I] = (CG ? pop_ld_cg(reinterpret_cast<const pop_t *>(bm ? own_i : am)) : pop_ld(reinterpret_cast<const pop_t *>(bm ? own_i : am))) + (bm ? wi : 0.0f);
-        h[J] = (CG ? pop_ld_cg(reinterpret_cast<const pop_t *>(bp ? own_j : ap)) : pop_ld(reinterpret_cast<const pop_t *>(bp ? own_j : ap))) + (bp ? wj : 0.0f);
+        h[I] = pop_ld(reinterpret_cast<const pop_t *>(bm ? own_i : am)) + (bm ? wi : 0.0f);
+        h[J] = pop_ld(reinterpret_cast<const pop_t *>(bp ? own_j : ap)) + (bp ? wj : 0.0f);
     } else {
-        h[I] = CG ? pop_ld_cg(reinterpret_cast<const pop_t *>(am)) : pop_ld(reinterpret_cast<const pop_t *>(am));
-        h[J] = CG ? pop_ld_cg(reinterpret_cast<const pop_t *>(ap)) : pop_ld(reinterpret_cast<const pop_t *>(ap));
+        h[I] = pop_ld(reinterpret_cast<const pop_t *>(am));
+        h[J] = pop_ld(reinterpret_cast<const pop_t *>(ap));
     }
 }
 
@@ -534,15 +523,14 @@ struct StreamCollide {
         }
     }
 
-    // general path: every link checked against walls and obstacles (CG: loads bypass L1, for the persistent pair kernel)
-    template <bool CG = false>
+    // general path: every link checked against walls and obstacles
     FG_HD static void checked_cell(const StepParams &p, int x, int y, int zz) {
         const Lattice &L = p.L;
         const long long idx = ((long long)zz * L.ny + y) * L.nx + x;
         if (L.solid && L.solid[idx]) return;
         const Nbr nb = make_nbr(L, x, y, zz);
         float h[Q];
-        load_arriving<PARITY, true, CG>(h, L, p.C, nb, idx);
+        load_arriving<PARITY, true>(h, L, p.C, nb, idx);
         float Fx, Fy, Fz;
         force_at(p, y, zz, idx, Fx, Fy, Fz);
         if (MRT) collide_mrt(h, Fx, Fy, Fz, p.C); else collide_bgk(h, Fx, Fy, Fz, p.C);
@@ -681,22 +669,12 @@ struct PairParams {
     int odd_y_lo, odd_y_hi; // rows [odd_y_lo, odd_y_hi) take the BULK odd step, the others (y-wall rows) the checked one
     int *ticket;            // [1], zero at launch
     int *done;              // [planes] even-phase CTAs finished per plane, zero at launch
-    // persistent form (cta_persistent): even-phase WARPS finished per plane, spread over kPairSub counters by row; [planes * kPairSub], zero
-    // at launch; err[0] is raised when a dependency wait gives up (never on a healthy run; it keeps a bug from hanging the GPU)
-    int *wdone;
-    int *err;
-    int skip_wall_rows;     // 1: the odd phase leaves rows outside [odd_y_lo, odd_y_hi) to a later launch (persistent form)
 };
-constexpr int kPairSub = 8;
 
 template <bool MRT, int MODE>
 struct StreamCollidePair {
     static constexpr int kThreads = 128;
-#if defined(FG_PAIR_OCC)
-    static constexpr int kMinBlocks = FG_PAIR_OCC;
-#else
     static constexpr int kMinBlocks = 8;
-#endif
     static constexpr int kGridPhases = 2;
     using Even = StreamCollide<0, MRT, CHECK_NONE>;
     using Odd = StreamCollide<1, MRT, MODE>;
@@ -723,7 +701,7 @@ struct StreamCollidePair {
         if (x >= p.s.L.nx) return;
         if (phase == 0) Even::template bulk_cell<false>(p.s, x, y, zz);
         else if (y >= p.odd_y_lo && y < p.odd_y_hi) Odd::template bulk_cell<MODE == CHECK_XEDGE>(p.s, x, y, zz);
-        else if (!p.skip_wall_rows) checked_row(p.s, x, y, zz);
+        else checked_row(p.s, x, y, zz);
     }
 #if defined(__CUDACC__)
     __device__ __noinline__
@@ -769,117 +747,6 @@ struct StreamCollidePair {
                 atomicAdd(p.done + v, 1);
             }
         }
-    }
-
-    // ---- persistent form (round 2).  What made the ticketed form lose was not the idea but WHERE it synchronised: a CTA
-    // had to wait for its stores to be acknowledged before counting itself done, and for a ticket + a CTA barrier before its
-    // first load — dead time in every 128-cell CTA.  Here the grid is as large as the GPU holds at once and every CTA walks
-    // the same wavefront schedule with a stride (item i -> CTA i mod G), so that
-    //   * no ticket is needed: a CTA's items are in schedule order, all CTAs are resident, and an item only ever waits for
-    //     items earlier in the schedule — no deadlock;
-    //   * completion of an even item is published one item LATE, right after the loads of the warp's next item have been
-    //     issued: the fence then waits for those loads (which the collide needs anyway) and for stores that left a whole
-    //     item ago, i.e. for nothing; one red.add per warp on one of kPairSub counters per plane, no CTA barrier;
-    //   * an odd item checks its three planes with ONE warp-wide load (24 lanes = 3 planes x 8 counters) + a vote; with a
-    //     lag of >= 2 planes the answer is "ready" on the first try;
-    //   * odd-phase loads bypass L1 (ld.cg): they read what other SMs stored earlier in this very kernel.
-    __device__ __forceinline__ static void publish(const PairParams &p, int &pending_v, int pending_r) {
-        if (pending_v < 0) return;
-        asm volatile("fence.acq_rel.gpu;" ::: "memory");      // every lane: its stores of the pending item are visible GPU-wide
-        __syncwarp();
-        if ((threadIdx.x & 31) == 0) atomicAdd(p.wdone + pending_v * kPairSub + (pending_r & (kPairSub - 1)), 1);
-        pending_v = -1;
-    }
-    // have all even-phase warps of planes v-1, v, v+1 published?  One warp-wide load: lanes 0..23 = 3 planes x 8 counters
-    __device__ __forceinline__ static bool planes_ready(const PairParams &p, int v, int need) {
-        const int lane = threadIdx.x & 31;
-        const int *c = p.wdone + (v - 1 + (lane >> 3)) * kPairSub + (lane & 7);
-        int n = 0;
-        if (lane < 24) asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(n) : "l"(c) : "memory");
-        n += __shfl_xor_sync(0xffffffffu, n, 1);
-        n += __shfl_xor_sync(0xffffffffu, n, 2);
-        n += __shfl_xor_sync(0xffffffffu, n, 4);
-        return __all_sync(0xffffffffu, lane >= 24 || n >= need);
-    }
-    // The warp's own unpublished even item may be what others are waiting for (and they for us): publish BEFORE spinning.
-    // (The first version of this kernel spun first — cycles of warps each holding the completion the next one needed.)
-    __device__ __forceinline__ static void wait_planes(const PairParams &p, int v, int need, int &pending_v, int pending_r) {
-        if (planes_ready(p, v, need)) return;             // the usual case with a lag of >= 2 planes
-        publish(p, pending_v, pending_r);
-        const int lane = threadIdx.x & 31;
-        long long t0 = 0;
-        for (int spin = 0;; ++spin) {
-            if (planes_ready(p, v, need)) break;
-            if (spin == 0) t0 = clock64();
-            else if (clock64() - t0 > 4000000000ll || *reinterpret_cast<volatile int *>(p.err)) {     // ~2 s: report (sticky), do not hang
-                if (lane == 0) atomicExch(p.err, 1);
-                break;
-            }
-            __nanosleep(200);
-        }
-        __syncwarp();
-    }
-    __device__ __forceinline__ static void cta_persistent(const PairParams &p, int first, int stride, int tx) {
-        const StepParams &s = p.s;
-        const Lattice &L = s.L;
-        const int per_plane = p.rows * p.xblocks;
-        const int n_items = 2 * p.planes * per_plane;            // < 2^31: checked by the host
-        const int need = per_plane * (kThreads / 32);
-        int pending_v = -1, pending_r = 0;
-        for (int it = first; it < n_items; it += stride) {
-            const int q = it / per_plane, w = it - q * per_plane;
-            const int r = w / p.xblocks, bx = w - r * p.xblocks;
-            int phase, v;
-            decode(p, q, phase, v);
-            if (phase == 1 && !odd_valid(p, v)) continue;
-            const int x = bx * kThreads + tx, y = s.y0 + r * s.ystride, zz = plane_of(p, v);
-            const bool in = x < L.nx;
-            const long long idx = ((long long)zz * L.ny + y) * L.nx + x;
-            float h[Q];
-            if (phase == 0) {
-                if (in) {
-                    FG_UNROLL
-                    for (int i = 0; i < Q; ++i) h[i] = pop_ld(L.f + i * L.slot + idx);
-                }
-                publish(p, pending_v, pending_r);
-                if (in) {
-                    float Fx, Fy, Fz;
-                    Even::force_at(s, y, zz, idx, Fx, Fy, Fz);
-                    if (MRT) collide_mrt(h, Fx, Fy, Fz, s.C); else collide_bgk(h, Fx, Fy, Fz, s.C);
-                    const Nbr nb{};
-                    store_departing<0, false>(h, L, s.C, nb, idx);
-                }
-                pending_v = v; pending_r = r;
-            } else {
-                if (!(y >= p.odd_y_lo && y < p.odd_y_hi)) continue;
-                wait_planes(p, v, need, pending_v, pending_r);
-                {
-                    constexpr bool XE = MODE == CHECK_XEDGE;
-                    NbrPtrs n;
-                    if (in) {
-                        n = make_ptrs<XE>(L, x, y, idx);
-                        h[0] = pop_ld_cg(reinterpret_cast<const pop_t *>(n.p[1][1] + s.kz[0][1]));
-#define FG_X(I) fast_odd_load_pair<I, XE, true>(h, s, n);
-                        FG_FOR_PAIRS(FG_X)
-#undef FG_X
-                    }
-                    publish(p, pending_v, pending_r);
-                    if (in) {
-                        float Fx, Fy, Fz;
-                        Even::force_at(s, y, zz, idx, Fx, Fy, Fz);
-                        if (MRT) collide_mrt(h, Fx, Fy, Fz, s.C); else collide_bgk(h, Fx, Fy, Fz, s.C);
-                        pop_st(reinterpret_cast<pop_t *>(n.p[1][1] + s.kz[0][1]), h[0]);
-#define FG_X(I) fast_odd_store_pair<I, XE>(h, s, n);
-                        FG_FOR_PAIRS(FG_X)
-#undef FG_X
-                    }
-                }
-                // rows outside [odd_y_lo, odd_y_hi) (y-wall rows) are NOT stepped here: the host runs the checked odd step
-                // on them in one thin launch after this kernel (sim.hpp launch_pair_wall_rows) — a call to the fully
-                // checked cell inside this loop cost 250 B of spills around the call site
-            }
-        }
-        publish(p, pending_v, pending_r);
     }
 #endif
 };

@@ -62,9 +62,9 @@ public:
         flags_ = static_cast<int *>(dev.alloc(4 * sizeof(int), err));
         if (!flags_) return FG_ENOMEM;
         if (!dev.zero(flags_, 4 * sizeof(int))) return cuda_fail();
-        pair_ctr_ = static_cast<int *>(dev.alloc(pair_ctr_bytes(), err));
+        pair_ctr_ = static_cast<int *>(dev.alloc(sizeof(int) * size_t(L_.nz + 3), err));
         if (!pair_ctr_) return FG_ENOMEM;
-        if (!dev.zero(pair_ctr_, pair_ctr_bytes())) return cuda_fail();
+        if (!dev.zero(pair_ctr_, sizeof(int) * size_t(L_.nz + 3))) return cuda_fail();
         setup_collision();
         if (cfg.max_markers > 0) {
             if (int rc = ib_.create(dev, cfg, L_, err)) return rc;
@@ -133,7 +133,6 @@ public:
 
     int get_moments(std::vector<float> &mom) {
         if (int rc = halos_ready_for_readout()) return rc;
-        if (int rc = check_pair_error()) return rc;
         const size_t n = size_t(L_.plane) * L_.nz;
         float *d = static_cast<float *>(dev.alloc(4 * n * sizeof(float), err));
         if (!d) return FG_ENOMEM;
@@ -177,7 +176,6 @@ public:
 
     int get_populations(float *f19) {
         if (int rc = halos_ready_for_readout()) return rc;
-        if (int rc = check_pair_error()) return rc;
         const size_t n = size_t(L_.plane) * L_.nz;
         float *d = static_cast<float *>(dev.alloc(size_t(Q) * n * sizeof(float), err));
         if (!d) return FG_ENOMEM;
@@ -400,15 +398,6 @@ public:
                 (long long)(hi - lo) * L_.plane >= (cfg.split_min_cells > 0 ? cfg.split_min_cells : (1 << 20))) {
                 split_ = true; near_a_ = near_b_ = lo;
             }
-            // Two substeps as a launch-level wavefront (wave_pair below): opt-in experiment.
-            if (!prof && (cfg.flags & FG_FLAG_WAVEFRONT) && parity_ == 0 && it + 1 < n && (!ranks || (peers_ && !ib_.exchange_on())) && L_.nz >= 8) {
-                int rc = FG_OK;
-                if (wave_pair(ib_on, graphs, rc)) {
-                    if (rc != FG_OK) return rc;
-                    ++it;
-                    continue;
-                }
-            }
             // Two substeps in one wavefront launch (StreamCollidePair): opt-in, measured slower than two plain launches
             // (lbm_core.cuh); no bodies, one rank.
             if (!prof && (cfg.flags & FG_FLAG_FUSED_PAIRS) && parity_ == 0 && it + 1 < n && !ib_on && !ranks && !L_.solid && L_.nz >= 8) {
@@ -419,7 +408,6 @@ public:
                 int done[2][2];
                 if (!launch_pair(1, L_.nz + 1, 0, 0, done) || !launch_faces()) return cuda_fail();
                 parity_ = 1;
-                if (!launch_pair_wall_rows(done)) return cuda_fail();
                 // the planes at the range ends (their z-neighbours are ghost planes, set by the face operations above)
                 if (!launch_collide_except(1, L_.nz + 1, ForceField{}, done) || !launch_faces()) return cuda_fail();
                 parity_ = 0;
@@ -552,7 +540,7 @@ public:
         o->collide_ms = collide_ms_; o->collide_launches = last_collide_launches_; o->ib_ms = ib_ms_;
         o->collide_cells = last_collide_cells_;
         o->split_substeps = split_substeps_;
-        o->pair_substeps = pair_substeps_ + wave_substeps_;
+        o->pair_substeps = pair_substeps_;
         o->graph_launches = dev.graph_launches;
         return FG_OK;
     }
@@ -683,7 +671,6 @@ public:
         return k;
     }
     int fail(int code, const std::string &m) { err = m; return code; }
-    int check_pair_error() { return check_pair_error_impl(); }
     int cuda_fail() { err = dev.err; return FG_ECUDA; }
 
 private:
@@ -760,7 +747,7 @@ private:
         const int hole = hole_e > hole_b ? hole_e - hole_b : 0;
         const int planes = (ze - zb - hole + zstride - 1) / zstride;
         if (planes <= 0 || rows <= 0) return true;
-        const bool down = parity_ == 1 && !(cfg.flags & FG_FLAG_NO_SWEEP_FLIP) && !wave_;
+        const bool down = parity_ == 1 && !(cfg.flags & FG_FLAG_NO_SWEEP_FLIP);
         StepParams p{L_, C_, F, zb, zstride, hole ? hole_b : 0x7fffffff, hole, down ? planes - 1 : -1, y0, ystride, {}};
         for (int s = 0; s < Q; ++s)
             for (int d = 0; d < 3; ++d) p.kz[s][d] = (long long)kPopBytes * (s * L_.slot + (long long)(d - 1) * L_.plane);
@@ -799,15 +786,7 @@ private:
         }
         if (zz_end <= zz_begin) return true;
         const int ny = L_.ny;
-        if (L_.solid || parity_ == 0) return wave_rows_ == 2 ? true : launch_rows(CHECK_ALL, zz_begin, zz_end, 0, 1, ny, F, zstride, hole_b, hole_e, true);
-        // wave_pair's far chunks: the two y-wall rows of ALL far planes go in one launch at the end of the pair (wave_rows_
-        // 1: everything but them, 2: only them) instead of a tiny checked launch + fork + join per chunk
-        if (wave_rows_ && L_.wall_y && ny >= 2) {
-            if (wave_rows_ == 2) return launch_rows(CHECK_ALL, zz_begin, zz_end, 0, ny - 1, 2, F, zstride, hole_b, hole_e);
-            const int bulk_only = L_.wall_x ? ((cfg.flags & FG_FLAG_NO_XWARP) ? CHECK_XEDGE : CHECK_XWARP) : CHECK_NONE;
-            return launch_rows(bulk_only, zz_begin, zz_end, 1, 1, ny - 2, F, zstride, hole_b, hole_e, true);
-        }
-        if (wave_rows_ == 2) return true;
+        if (L_.solid || parity_ == 0) return launch_rows(CHECK_ALL, zz_begin, zz_end, 0, 1, ny, F, zstride, hole_b, hole_e, true);
         const bool zlo_wall = L_.bc_zlo == BC_WALL && L_.z0 == 0, zhi_wall = L_.bc_zhi == BC_WALL && L_.z0 + L_.nz == L_.nzg;
         if (hole_e > hole_b && (zlo_wall || zhi_wall))   // wall planes are peeled off the ends below: keep that logic hole-free
             return launch_collide(zz_begin, hole_b, F) && launch_collide(hole_e, zz_end, F);
@@ -868,46 +847,16 @@ private:
         p.odd_skip_v = hole ? hole_b - zb : -1;
         p.odd_y_lo = L_.wall_y ? 1 : 0; p.odd_y_hi = L_.wall_y ? L_.ny - 1 : L_.ny;
         p.ticket = pair_ctr_; p.done = pair_ctr_ + 1;
-        p.err = pair_ctr_ + 1 + (L_.nz + 2); p.wdone = p.err + 1;
         if (hole) { done[0][0] = zb + p.odd_lo; done[0][1] = hole_b - 1; done[1][0] = hole_e + 1; done[1][1] = ze - (out_hi ? 2 : 1); }
         else { done[0][0] = zb + p.odd_lo; done[0][1] = ze - (out_hi ? 2 : 1); }
         for (int i = 0; i < 2; ++i) if (done[i][1] < done[i][0]) done[i][0] = done[i][1] = 0;
         const Dim3 g{p.xblocks, p.rows, planes};
         const bool mrt = cfg.collision == FG_MRT;
-        if (cfg.flags & FG_FLAG_PAIR_PERSISTENT) {
-            p.skip_wall_rows = 1;
-            // persistent form: the error word stays (sticky), the per-plane warp counters start at zero
-            if (!dev.zero_on_current(p.wdone, sizeof(int) * size_t(planes) * kPairSub)) return false;
-            const long long items = 2ll * planes * p.rows * p.xblocks;
-            if (items > 0x7fffffffll) { dev.err = "persistent pair launch too large"; return false; }
-            if (L_.wall_x) return mrt ? dev.template launch_persistent<StreamCollidePair<true, CHECK_XEDGE>>(items, p)
-                                      : dev.template launch_persistent<StreamCollidePair<false, CHECK_XEDGE>>(items, p);
-            return mrt ? dev.template launch_persistent<StreamCollidePair<true, CHECK_NONE>>(items, p)
-                       : dev.template launch_persistent<StreamCollidePair<false, CHECK_NONE>>(items, p);
-        }
         if (!dev.zero_on_current(pair_ctr_, sizeof(int) * size_t(planes + 1))) return false;
         if (L_.wall_x) return mrt ? dev.template launch_ticketed<StreamCollidePair<true, CHECK_XEDGE>>(g, p)
                                   : dev.template launch_ticketed<StreamCollidePair<false, CHECK_XEDGE>>(g, p);
         return mrt ? dev.template launch_ticketed<StreamCollidePair<true, CHECK_NONE>>(g, p)
                    : dev.template launch_ticketed<StreamCollidePair<false, CHECK_NONE>>(g, p);
-    }
-    // the persistent pair kernel leaves the y-wall rows of its odd phase to this thin checked launch (parity_ == 1)
-    bool launch_pair_wall_rows(const int done[2][2]) {
-        if (!(cfg.flags & FG_FLAG_PAIR_PERSISTENT) || !L_.wall_y) return true;
-        for (int i = 0; i < 2; ++i) {
-            if (done[i][1] <= done[i][0]) continue;
-            if (L_.ny >= 2) { if (!launch_rows(CHECK_ALL, done[i][0], done[i][1], 0, L_.ny - 1, 2, ForceField{})) return false; }
-            else if (!launch_rows(CHECK_ALL, done[i][0], done[i][1], 0, 1, 1, ForceField{})) return false;
-        }
-        return true;
-    }
-    size_t pair_ctr_bytes() const { return sizeof(int) * (size_t(L_.nz + 3) + 1 + size_t(L_.nz + 2) * kPairSub); }   // ticket, done[], err, wdone[]
-    // raised by the persistent pair kernel when a dependency wait gave up (a bug, or a grid that was not co-resident)
-    int check_pair_error_impl() {
-        if (!(cfg.flags & FG_FLAG_PAIR_PERSISTENT) || pair_substeps_ == 0) return FG_OK;
-        int e = 0;
-        if (!dev.sync() || !dev.d2h(&e, pair_ctr_ + 1 + (L_.nz + 2), sizeof(int))) return cuda_fail();
-        return e ? fail(FG_ECUDA, "persistent step-pair kernel: a dependency wait timed out (results of this handle are invalid)") : FG_OK;
     }
     // the odd step runs this many planes behind the even step: far enough that it never waits, near enough that the
     // planes in between (lag x 76 B x nx x ny) stay in L2
@@ -915,179 +864,6 @@ private:
         if (cfg.pair_lag > 0) return cfg.pair_lag;
         const long long plane_bytes = 76ll * L_.plane;
         return int(std::max<long long>(2, std::min<long long>(8, (24ll << 20) / plane_bytes)));
-    }
-
-    // ---- FG_FLAG_WAVEFRONT: an even step and the odd step after it as a wavefront of plane chunks.
-    // The odd step of a plane needs the even step of the planes below, at and above it and nothing else, so it may run one
-    // chunk behind the even step: chunk k+1 takes its even step on one stream while chunk k takes its odd step on another,
-    // and finds what the even step wrote a moment ago in the 126 MB L2 — DRAM then sees one read and one write per cell
-    // for TWO updates.  Unlike StreamCollidePair (tickets and fences inside one kernel, measured slower) the ordering is
-    // between launches: plain StreamCollide kernels, stream events, one CUDA graph per pair.
-    //   * planes next to the box ends take their odd step last: it needs the z-face operation of the even step, and a
-    //     zero-gradient outlet copies from the boundary plane what the odd step of the plane next to it would overwrite;
-    //   * with an immersed boundary, the planes around the bodies (+1 for the odd step) run on the main stream:
-    //     IB(t) -> even -> IB(t+1) -> odd, beside the far-plane wavefront, which needs no force.
-    // Returns false when the pair cannot be run this way (the caller steps normally); rc carries an error.
-    int wave_chunk() const {
-        if (cfg.pair_lag > 0) return cfg.pair_lag;
-        // ~20 MB of populations per chunk (three chunks in flight stay well inside the 126 MB L2), rounded to a whole number
-        // of waves of resident CTAs (148 SMs x 9) so that a chunk launch does not end on a half-empty wave
-        const long long plane_bytes = (long long)kPopBytes * Q * L_.plane;
-        const long long target = std::max<long long>(1, std::min<long long>(64, (20ll << 20) / plane_bytes));
-        const long long per_plane = (long long)((L_.nx + kCollideThreads - 1) / kCollideThreads) * std::max(1, L_.wall_y ? L_.ny - 2 : L_.ny);
-        const long long resident = (long long)dev.sm_count() * 9;
-        const long long waves = std::max<long long>(1, (target * per_plane + resident / 2) / resident);
-        return int(std::max<long long>(1, std::min<long long>(64, waves * resident / per_plane)));
-    }
-    bool launch_collide_at(int parity, int zb, int ze, const ForceField &F) {
-        const int keep = parity_;
-        parity_ = parity;
-        const bool ok = launch_collide(zb, ze, F);
-        parity_ = keep;
-        return ok;
-    }
-    bool far_odd(int zb, int ze, int rows, int hole_b = 0, int hole_e = 0) {
-        const int keep = parity_;
-        parity_ = 1; wave_rows_ = rows;
-        const bool ok = launch_collide(zb, ze, ForceField{}, 1, hole_b, hole_e);
-        parity_ = keep; wave_rows_ = 0;
-        return ok;
-    }
-    bool wave_pair(bool ib_on, bool graphs, int &rc) {
-        const int lo = 1, hi = L_.nz + 1;
-        const bool slab = cfg.n_ranks > 1;                                              // peered z-slab (the caller checked peers_)
-        const bool out_lo = L_.bc_zlo == BC_OUTLET && L_.z0 == 0, out_hi = L_.bc_zhi == BC_OUTLET && L_.z0 + L_.nz == L_.nzg;
-        const int late_lo = lo + (out_lo ? 2 : 1), late_hi = hi - (out_hi ? 2 : 1);     // odd wavefront: [late_lo, late_hi)
-        int na = hi, nb = hi;                                                           // even step of [na, nb) waits for IB(t)
-        if (ib_on) {
-            int a, b;
-            if (!ib_.near_planes(a, b)) return false;                                   // bodies everywhere: nothing is far
-            na = std::min(std::max(a, lo), hi); nb = std::max(std::min(b, hi), na);
-            if (nb <= na) { na = hi; nb = hi; }                                         // no stencil on this slab
-            else {
-                // fish move between the two IB passes of the pair (by less than a plane): one more plane on each side
-                if (!fish_.empty()) { na = std::max(na - 1, lo); nb = std::min(nb + 1, hi); }
-                // bodies next to a slab end: their band cells read ghost planes at odd parity and their planes include the
-                // boundary planes, which here go first without a force — such pairs are stepped normally
-                if (na <= lo || nb >= hi) return false;
-            }
-        }
-        if ((na - lo) + (hi - nb) < 6) return false;
-        const int oa = std::max(na - 1, late_lo), ob = std::min(nb + 1, late_hi);       // odd step of [oa, ob) waits for IB(t+1)
-        struct Scope {
-            Dev &d; bool on; bool done = false; bool &wave;
-            ~Scope() { wave = false; if (on && !done) d.graph_abort(); }
-        } scope{dev, false, false, wave_};
-        // the launch geometry depends on where the bodies are: (na, nb) belong to the key (na >= 1, so it never collides
-        // with the key of a plain substep, whose first word is < 4)
-        GraphKey key = substep_key();
-        key[0] = (key[0] & 0xffull) | (uint64_t(uint32_t(na)) << 8) | (uint64_t(uint32_t(nb)) << 36);
-        scope.on = graphs && fish_.empty() && dev.graph_begin(key);     // with fish the host integrates in the middle of the pair
-        wave_ = true;
-        const int c = wave_chunk();
-        bool ok = true;
-        // streams 2 (even chunks) and 4 (odd chunks) start here: the interior wavefront waits for nothing
-        ok = ok && dev.fork_to(4) && dev.switch_to(0) && dev.fork_to(2) && dev.switch_to(0);
-        // ---- A. boundary planes first (main stream): their even step, then the z-face operation of the even step — wrap,
-        // inlet / outlet, or the halo push into the z-neighbours' ghost planes, which the whole wavefront then hides.
-        // It reads slots of the boundary planes that the odd step of the planes next to them does not touch.
-        if (slab) ok = ok && dev.wait_flags(flags_, has_lo_peer(), has_hi_peer());     // halos of the previous odd step
-        {
-            const int keep = parity_;
-            parity_ = 0;
-            ok = ok && launch_collide(lo, hi, ForceField{}, L_.nz - 1);               // both boundary planes in one launch
-            parity_ = keep;
-        }
-        ok = ok && launch_faces();                                                      // parity_ == 0
-        ok = ok && dev.switch_to(4) && dev.join_from(0);                                // odd chunks touch the boundary planes
-        // ---- B. far planes: even chunks on stream 2, odd chunks one behind on stream 4; the planes around the bodies on the
-        // main stream beside them: IB(t) -> even, IB(t+1), then their odd step as soon as the even step of the planes
-        // next to them is queued
-        ForceField F0{}, F1{};
-        bool near_forces = !ib_on, near_odd = !ib_on;
-        const bool with_fish = !fish_.empty();
-        // IB(t) and the even step of the planes around the bodies: queued before the far chunks, so that the wrenches of
-        // this substep are on their way to the host as early as possible
-        if (ok && ib_on) {
-            ok = dev.switch_to(0);
-            ib_.set_fused(false);
-            if (with_fish && (rc = upload_bodies()) != FG_OK) return true;
-            if ((rc = ib_.compute_forces(dev, L_, C_, 0, err)) != FG_OK) return true;
-            F0 = ib_.force_view();
-            ok = ok && launch_collide_at(0, na, nb, F0);
-        }
-        // IB(t+1).  With fish this holds the host round trip of the second substep — wrenches of IB(t) down, bodies advanced,
-        // markers up — and is therefore called only after every far chunk is queued: the GPU works through them meanwhile.
-        auto near_forces_next = [&]() -> bool {
-            near_forces = true;
-            if (!dev.switch_to(0)) { rc = cuda_fail(); return false; }
-            if (with_fish) {
-                if ((rc = advance_bodies()) != FG_OK) return false;
-                emit_bodies();
-                int zmin, zmax;
-                // IB(t+1) reads and forces cells whose even step must be the one queued on THIS stream above
-                if (!ib_.stencil_planes(zmin, zmax) || zmin - 1 < na || zmax + 2 > nb) {
-                    rc = fail(FG_ESTATE, "a body moved more than a plane within one substep (FG_FLAG_WAVEFRONT)");
-                    return false;
-                }
-                if ((rc = upload_bodies()) != FG_OK) return false;
-            }
-            if ((rc = ib_.compute_forces(dev, L_, C_, 1, err)) != FG_OK) return false;
-            F1 = ib_.force_view();
-            return true;
-        };
-        auto near_part2 = [&]() -> bool {
-            near_odd = true;
-            if (!(dev.switch_to(0) && dev.join_from(2))) { rc = cuda_fail(); return false; }
-            if (ob > oa && !launch_collide_at(1, oa, ob, F1)) { rc = cuda_fail(); return false; }
-            return true;
-        };
-        if (ok && ib_on && !with_fish && !near_forces_next()) return true;
-        const int far[2][2] = {{lo + 1, std::min(na, hi - 1)}, {std::max(nb, lo + 1), hi - 1}};
-        for (int r = 0; r < 2 && ok; ++r) {
-            const int a = far[r][0], b = far[r][1];
-            const int fa = std::max(a, late_lo), fb = std::min(b, late_hi);            // ... minus the late planes
-            const int ra = r == 1 && nb < hi ? std::max(fa, nb + 1) : fa;               // ... minus the planes next to the bodies
-            const int rb = r == 0 && na < hi ? std::min(fb, na - 1) : fb;
-            for (int z = a, k = 0; z < b && ok; z += c, ++k) {
-                ok = ok && dev.switch_to(2);
-                // back-pressure: nothing else keeps the even stream from running ahead of the odd one and pushing the chunks
-                // the odd step still has to read out of L2 — even chunk k waits for odd chunk k-2
-                if (k >= 2) ok = ok && dev.join_from(4);
-                ok = ok && launch_collide_at(0, z, std::min(z + c, b), ForceField{});
-                if (k >= 1) {     // the even step now covers planes up to z + c: the chunk before takes its odd step
-                    const int za = std::max(z - c, ra), zb = std::min(z, rb);
-                    if (zb > za) ok = ok && dev.switch_to(4) && dev.join_from(2) && far_odd(za, zb, 1);
-                }
-                // the even step of the planes just above the bodies is queued: their own odd step need not wait for the rest
-                if (ok && r == 1 && near_forces && !near_odd && std::min(z + c, b) > std::min(nb + 1, b - 1)) { if (!near_part2()) return true; }
-            }
-            // the last odd chunk of the range: the even step of the plane above it is a boundary plane or was queued before
-            const int last = a + ((b - a - 1) / c) * c;                                 // first plane of the last chunk
-            const int ta = std::max(b > a ? last : b, ra);
-            if (ok && rb > ta) ok = dev.switch_to(4) && dev.join_from(2) && far_odd(ta, rb, 1);
-        }
-        if (ok && !near_forces) { if (!near_forces_next()) return true; }
-        if (ok && !near_odd) { if (!near_part2()) return true; }
-        // the y-wall rows of every far plane, in one launch with a hole over the planes around the bodies
-        ok = ok && dev.switch_to(4) && dev.join_from(2) && far_odd(late_lo, late_hi, 2, ib_on ? oa : 0, ib_on ? ob : 0);
-        ok = ok && dev.switch_to(0) && dev.join_from(2);
-        // ---- C. slab ends, beside the last odd chunks (which touch neither the late planes' own locations nor the slots of
-        // the boundary planes the z-face operation writes): odd step of the late planes — they read the ghost planes, i.e.
-        // wrap / inlet / outlet data or what the z-neighbours pushed after THEIR even step — then the z-face operation of
-        // the odd step
-        if (slab) ok = ok && dev.wait_flags(flags_, has_lo_peer(), has_hi_peer());
-        parity_ = 1;
-        ok = ok && launch_collide(lo, std::min(late_lo, hi), F1) && launch_collide(std::max(late_hi, late_lo), hi, F1) && launch_faces();
-        parity_ = 0;
-        ok = ok && dev.join_from(4);
-        if (!ok) { rc = cuda_fail(); return true; }
-        steps_ += 2; wave_substeps_ += 2;
-        if (scope.on) {
-            scope.done = true;
-            if (!dev.graph_end()) { rc = cuda_fail(); return true; }
-        }
-        return true;
     }
 
     // z-face plane ops after the step of parity `parity_`: one launch covers both faces
@@ -1174,9 +950,7 @@ private:
     bool timing_pending_ = false;
     int timed_substeps_ = 0;
     int64_t collide_launches_ = 0, last_collide_launches_ = 0, collide_cells_ = 0, last_collide_cells_ = 0;
-    int64_t split_substeps_ = 0, pair_substeps_ = 0, wave_substeps_ = 0;
-    bool wave_ = false;            // inside wave_pair: chunk launches do not flip the sweep direction
-    int wave_rows_ = 0;            // inside wave_pair's far odd launches: 1 = without the y-wall rows, 2 = only the y-wall rows
+    int64_t split_substeps_ = 0, pair_substeps_ = 0;
     int *pair_ctr_ = nullptr;      // [1 + nz + 2] ticket + per-plane completion counters of StreamCollidePair
     bool split_ = false;           // this substep: far planes collide beside the IB kernels
     int near_a_ = 1, near_b_ = 1;  // planes [near_a_, near_b_) wait for the IB force

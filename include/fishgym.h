@@ -64,14 +64,12 @@ extern "C" {
 #define FG_FLAG_FUSED_IB   8   /* run the IB phases as ONE cooperative kernel with grid barriers (measured slower on B200: r1) */
 #define FG_FLAG_NO_GRAPHS  4   /* launch every kernel directly instead of replaying per-substep CUDA graphs */
 #define FG_FLAG_NO_SWEEP_FLIP 32 /* sweep the planes upwards in every step (default: odd steps downwards, for L2 reuse between steps) */
-#define FG_FLAG_FUSED_PAIRS 64 /* even step + following odd step as ONE L2-resident wavefront launch (no bodies, one rank); halves DRAM traffic but measured slower on B200 (r1) */
+#define FG_FLAG_FUSED_PAIRS 64 /* even step + following odd step as ONE L2-resident wavefront launch (no bodies, one rank); halves DRAM traffic but measured slower on B200 (r1; so were a launch-level wavefront of plane chunks and a persistent-CTA form in r2, both removed: profiles/r2_summary.md) */
 #define FG_FLAG_NO_XWARP 128   /* x walls: predicated wall selects in every thread (default: only the two warps at the row ends run the wall code) */
 #define FG_FLAG_SYNC_STEP 256  /* fg_step returns only when all its device work has finished (default: when wrenches / obs are there) */
-#define FG_FLAG_WAVEFRONT 512  /* EXPERIMENT (unmeasured): even step + following odd step as a launch-level wavefront of plane chunks on two streams, the odd step one chunk behind the even one, so that it finds its populations in L2 (one rank or peered z-slabs; prescribed markers or fish inside a slab — with fish the pair is launched directly, not as a graph; no bodies across slab faces) */
 #define FG_FLAG_EVEN_VEC4 1024 /* even steps take 4 cells per thread with 128-bit loads / stores (needs nx % 4 == 0, no obstacles); measured +1.3 ... +2.4 %, less than the 2-cell form (profiles/r2_summary.md) */
 #define FG_FLAG_EVEN_VEC2 2048 /* ... 2 cells per thread with 64-bit accesses for any even nx (the DEFAULT when nx is a multiple of 256: +2.6 ... +3.2 %) */
 #define FG_FLAG_EVEN_SCALAR 8192 /* even steps with the scalar one-cell-per-thread kernel everywhere (A/B against the default) */
-#define FG_FLAG_PAIR_PERSISTENT 4096 /* with FG_FLAG_FUSED_PAIRS: the step pair as a PERSISTENT kernel (one CTA per resident slot walking the wavefront schedule, completion published one item late, no tickets / CTA barriers) */
 #define FG_FLAG_NO_SPLIT  16   /* collide all planes after the IB kernels (default: planes away from the bodies run beside them) */
 
 typedef struct FgConfig {
@@ -85,7 +83,7 @@ typedef struct FgConfig {
     int32_t max_links;        /* capacity for rigid links markers can belong to */
     int32_t flags;            /* FG_FLAG_* */
     int32_t split_min_cells;  /* plane split only when at least this many cells lie in far planes; 0 => 1<<20 (~25 us of work) */
-    int32_t pair_lag;         /* FG_FLAG_FUSED_PAIRS: planes between the even and the odd wavefront; FG_FLAG_WAVEFRONT: planes per chunk; 0 => chosen from the plane size */
+    int32_t pair_lag;         /* FG_FLAG_FUSED_PAIRS: planes between the even and the odd wavefront; 0 => chosen from the plane size */
     int32_t reserved_i[1];
     double  tau;              /* relaxation time; nu = (tau - 1/2)/3 */
     double  mrt_rates[19];    /* MRT relaxation rates per moment; all zero => SURVEY.md A3 defaults */

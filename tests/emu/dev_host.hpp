@@ -41,7 +41,7 @@ public:
     // / highest / a random runnable stream.  A missing fork / join between two launches that touch the same data then
     // shows up as a result that depends on the policy (tests/test_stream_order.py); work left on a side stream at a
     // synchronisation is reported as an error.  Nothing stays queued across ABI calls (toc_record drains).
-    static constexpr int kStreams = 6;
+    static constexpr int kStreams = 4;
     bool init(int, std::string &) {
         if (const char *e = std::getenv("FG_EMU_SCHED")) {
             const std::string v(e);
@@ -134,8 +134,6 @@ public:
             return true;
         });
     }
-    template <class K, class P>
-    bool launch_persistent(long long n_ctas, const P &p) { return launch_ticketed<K, P>(Dim3{p.xblocks, p.rows, p.planes}, p); (void)n_ctas; }
     bool zero_on_current(void *d, size_t n) { return submit(cur_, [=] { std::memset(d, 0, n); return true; }); }
 
     // phased kernels (one cooperative launch on the GPU): phases in order, every item of a phase before the next

@@ -125,14 +125,12 @@ def test_plane_split_far_collide_beside_ib_kernels(g, emu, walls):
 
 @pytest.mark.parametrize("name", ["bgk_periodic", "mrt_force", "bgk_ywall_moving", "mrt_xy_walls", "mrt_all_walls_lid", "bgk_inlet_outlet",
                                   "mrt_inlet_outlet_ywalls", "mrt_outlet_inlet_xwalls"])
-@pytest.mark.parametrize("persistent", [False, True])
-def test_fused_step_pairs_are_bit_identical_to_single_steps(g, emu, name, persistent):
+def test_fused_step_pairs_are_bit_identical_to_single_steps(g, emu, name):
     """StreamCollidePair (opt-in, FG_FLAG_FUSED_PAIRS): even step + following odd step of the same planes in one launch.  Per cell it is the same
     arithmetic in the same order, so populations must not differ by a bit from stepping one launch per step, for any
     number of substeps per call (pairs only form inside one fg_step call) and every boundary kind."""
     kw = dict(util.parity_cases(g)[name], nz=12)
-    # persistent: the round-2 form of the pair kernel; it leaves the y-wall rows of its odd phase to a thin checked launch
-    fl = g._abi.FLAG_FUSED_PAIRS | (g._abi.FLAG_PAIR_PERSISTENT if persistent else 0)
+    fl = g._abi.FLAG_FUSED_PAIRS
     a, b = g.Sim(backend=emu, flags=fl, **kw), g.Sim(backend=emu, **kw)
     rho, u = util.smooth_fields(a.shape)
     for s in (a, b):

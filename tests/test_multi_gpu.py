@@ -178,26 +178,3 @@ def test_multi_gpu_plane_split_matches_one_gpu(g, cuda, overlap, tmp_path):
         whole.step(1)
     whole.step(5)
     assert np.abs(whole.get_populations() - np.load(out)).max() < 2e-7
-
-
-@pytest.mark.skipif(not os.environ.get("FG_TEST_EXPERIMENTS"), reason="FG_FLAG_WAVEFRONT has not run on a GPU yet (tools/passes/r2_multi1.sh sets FG_TEST_EXPERIMENTS=1)")
-@pytest.mark.parametrize("case", ["periodic", "channel"])
-def test_multi_gpu_wavefront_pairs_bit_identical_to_one_gpu(g, cuda, case, tmp_path):
-    """FG_FLAG_WAVEFRONT on peered slabs across real GPUs: two halo exchanges inside every pair, the interior wavefront hiding
-    both; 33 substeps in two calls must leave exactly the populations of the plain one-GPU run."""
-    n, world = _layout()
-    out = str(tmp_path / "f.npy")
-    script = tmp_path / "worker.py"
-    script.write_text(WORKER.format(root=ROOT, tests=os.path.join(ROOT, "tests"), case=case, out=out, flags=g._abi.FLAG_WAVEFRONT, ngpu=n))
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
-                        "127.0.0.1", "--master-port", str(29500 + os.getpid() % 2000), str(script)], capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stderr[-3000:]
-    P, Wl, IN, OUT = g.BC_PERIODIC, g.BC_WALL, g.BC_INLET, g.BC_OUTLET
-    kw = dict(nx=40, ny=24, nz=16 * world, tau=0.7, collision=g.MRT, body_force=[1e-4, 0, 2e-4])
-    if case == "channel":
-        kw.update(bc=[P, P, Wl, Wl, IN, OUT], inlet_u=[0, 0.01, 0.04], body_force=[0, 0, 0])
-    whole = g.Sim(backend=cuda, **kw)
-    rho, u = util.smooth_fields(whole.shape)
-    whole.set_fields(rho, u)
-    whole.step(33)
-    assert np.array_equal(whole.get_populations(), np.load(out))

@@ -628,192 +628,3 @@ def test_random_api_sequences_cuda_vs_oracle(g, cuda):
     obstacle masks, flags of the random case, resets and read-outs in any order."""
     bad = [(seed, w) for seed in range(3000, 3120) for w in [run_api_sequence_case(g, cuda, seed)] if w is not None and w > 2e-5]
     assert not bad, bad[:5]
-
-
-def run_wavefront_case(g, emu, seed, exact=True):
-    """FG_FLAG_WAVEFRONT (sim.hpp wave_pair): even + odd step as a wavefront of plane chunks on two streams, with a drifting
-    marker cloud (so the near range moves, sometimes to a box end where the pair falls back to plain steps), obstacles,
-    every face combination, chunk sizes 1-8: populations and wrenches bit-identical to plain stepping.  Under
-    FG_EMU_SCHED (test_stream_order.py) this is what checks the event edges between the even and the odd stream."""
-    A = g._abi
-    rng = np.random.default_rng(seed)
-    kw, solid, _ = random_case(g, rng)
-    kw["nz"], kw["ny"] = int(rng.integers(8, 48)), max(kw["ny"], 3)
-    nx, ny, nz = kw["nx"], kw["ny"], kw["nz"]
-    if solid is not None:
-        solid = (rng.random((nz, ny, nx)) < 0.06).astype(np.uint8)
-    kw.update(max_markers=64, max_links=3, pair_lag=int(rng.integers(1, 9)) if rng.random() < 0.8 else 0)
-    base = kw["flags"]
-    a = g.Sim(backend=emu, **dict(kw, flags=base | A.FLAG_NO_SPLIT))
-    b = g.Sim(backend=emu, **dict(kw, flags=base | A.FLAG_WAVEFRONT))
-    rho, u = util.smooth_fields(a.shape)
-    rho = (rho + 0.003 * rng.standard_normal(a.shape)).astype(np.float32)
-    u = (u + 0.003 * rng.standard_normal((3,) + a.shape)).astype(np.float32)
-    for s in (a, b):
-        if solid is not None:
-            s.set_solid(solid)
-        s.set_fields(rho, u)
-    use_ib = rng.random() < 0.6
-    c, V = np.array([nx / 2, ny / 2, rng.uniform(0, nz)]), np.array([0, 0, rng.uniform(-1.5, 1.5)])
-    n = int(rng.integers(1, 30))
-    X0, link = rng.uniform(-2, 2, (n, 3)), np.sort(rng.integers(0, 3, n)).astype(np.int32)
-    same = True
-    for _ in range(5):
-        if use_ib and rng.random() < 0.7:
-            c = c + V
-            X, U = (c + X0).astype(np.float32), np.tile((V * 0.02).astype(np.float32), (n, 1))
-            for s in (a, b):
-                s.set_markers(X, U, np.ones(n, np.float32), link)
-                s.set_link_origins([list(c)] * 3)
-        k = int(rng.integers(1, 6))
-        a.step(k)
-        b.step(k)
-        if exact:
-            same = same and np.array_equal(a.get_populations(), b.get_populations())
-            same = same and (not use_ib or np.array_equal(a.get_link_wrenches(), b.get_link_wrenches()))
-        else:       # on the GPU the spreading atomics add in a different order from run to run
-            keep = 1 if solid is None else (solid == 0)
-            same = same and np.abs((a.get_populations() - b.get_populations()) * keep).max() < 5e-7
-            wa, wb = a.get_link_wrenches(), b.get_link_wrenches()
-            same = same and (wa.size == 0 or np.abs(wa - wb).max() <= 1e-5 * max(np.abs(wa).max(), 1e-3))
-    waves = b.stats().pair_substeps
-    a.close()
-    b.close()
-    return same, waves, kw
-
-
-def test_random_wavefront_pairs_equal_plain_steps(g, emu):
-    bad, with_waves = [], 0
-    for seed in range(150):
-        same, waves, kw = run_wavefront_case(g, emu, seed)
-        with_waves += waves > 0
-        if not same:
-            bad.append((seed, kw))
-    assert not bad, bad[:3]
-    assert with_waves >= 90
-
-
-@pytest.mark.gpu
-@pytest.mark.skipif(not os.environ.get("FG_TEST_EXPERIMENTS"), reason="FG_FLAG_WAVEFRONT is an opt-in experiment that has not run on a GPU "
-                    "yet (written after the GPU minutes of round 1 were spent); tools/passes/r2_pass2.sh sets FG_TEST_EXPERIMENTS=1")
-def test_random_wavefront_pairs_cuda(g, cuda):
-    """The same on the GPU, where the chunks really run on two streams (and, with graphs on, as one captured graph per pair)."""
-    bad, with_waves = [], 0
-    for seed in range(4000, 4080):
-        same, waves, kw = run_wavefront_case(g, cuda, seed, exact=False)
-        with_waves += waves > 0
-        if not same:
-            bad.append((seed, kw))
-    assert not bad, bad[:3]
-    assert with_waves >= 40
-
-
-def run_wavefront_slab_case(g, emu, seed):
-    """FG_FLAG_WAVEFRONT on 2-3 peered z-slabs (ranks stepped from threads: a pair holds two halo exchanges): boundary planes
-    first, their push hidden behind the wavefront of the interior planes, late planes after the neighbours' even-step halos.
-    One marker cloud inside one slab.  Populations bit-identical to the unsplit plain run."""
-    import test_slabs
-    A = g._abi
-    rng = np.random.default_rng(seed)
-    kw, solid, _ = random_case(g, rng)
-    n_ranks, h = int(rng.integers(2, 4)), int(rng.integers(8, 24))
-    kw["nz"], kw["ny"] = h * n_ranks, max(kw["ny"], 3)
-    nx, ny, nz = kw["nx"], kw["ny"], kw["nz"]
-    if solid is not None:
-        solid = (rng.random((nz, ny, nx)) < 0.06).astype(np.uint8)
-    kw.update(max_markers=64, max_links=2, pair_lag=int(rng.integers(1, 7)) if rng.random() < 0.8 else 0)
-    base = kw.pop("flags") | (A.FLAG_NO_OVERLAP if rng.random() < 0.3 else 0)
-    periodic = kw["bc"][4] == g.BC_PERIODIC
-    whole = g.Sim(backend=emu, flags=base | A.FLAG_NO_SPLIT, **kw)
-    parts = [g.Sim(backend=emu, n_ranks=n_ranks, rank=r, flags=base | A.FLAG_WAVEFRONT, **kw) for r in range(n_ranks)]
-    rho, u = util.smooth_fields(whole.shape)
-    rho = (rho + 0.003 * rng.standard_normal(whole.shape)).astype(np.float32)
-    u = (u + 0.003 * rng.standard_normal((3,) + whole.shape)).astype(np.float32)
-    for s in [whole] + parts:
-        if solid is not None:
-            s.set_solid(solid)
-    whole.set_fields(rho, u)
-    for r, s in enumerate(parts):
-        s.set_fields(rho[r * h:(r + 1) * h], u[:, r * h:(r + 1) * h])
-    hs = [s.peer_export() for s in parts]
-    for r, s in enumerate(parts):
-        s.peer_connect(hs[(r - 1) % n_ranks] if (r > 0 or periodic) else None, hs[(r + 1) % n_ranks] if (r < n_ranks - 1 or periodic) else None)
-    use_ib, rk = rng.random() < 0.5, int(rng.integers(0, n_ranks))
-    zc = rk * h + rng.uniform(3.5, h - 3.5)
-    n = int(rng.integers(1, 20))
-    X = (np.array([nx / 2, ny / 2, zc]) + rng.uniform(-1.2, 1.2, (n, 3))).astype(np.float32)
-    U, dV = np.full((n, 3), 0.01, np.float32), np.ones(n, np.float32)
-    same = True
-    keep = 1 if solid is None else (solid == 0)
-    for it in range(4):
-        if use_ib and it in (0, 2):
-            for s in (whole, parts[rk]):
-                s.set_markers(X, U, dV)
-                s.set_link_origins([[nx / 2, ny / 2, zc]])
-        k = int(rng.integers(1, 6))
-        whole.step(k)
-        test_slabs._run_threads([lambda s=s: s.step(k) for s in parts])
-        f, fs = whole.get_populations(), np.concatenate([s.get_populations() for s in parts], axis=1)
-        same = same and np.array_equal(f * keep, fs * keep)
-        same = same and (not use_ib or np.array_equal(whole.get_link_wrenches(), parts[rk].get_link_wrenches()))
-    waves = sum(s.stats().pair_substeps for s in parts)
-    for s in [whole] + parts:
-        s.close()
-    return same, waves, kw
-
-
-def test_random_wavefront_pairs_on_peered_slabs(g, emu):
-    bad, with_waves = [], 0
-    for seed in range(60):
-        same, waves, kw = run_wavefront_slab_case(g, emu, seed)
-        with_waves += waves > 0
-        if not same:
-            bad.append((seed, kw))
-    assert not bad, bad[:3]
-    assert with_waves >= 50
-
-
-def test_random_fish_in_wavefront_pairs_equal_plain_steps(g, emu):
-    """Fish inside FG_FLAG_WAVEFRONT pairs: the host round trip of the second substep (wrenches down, bodies advanced,
-    markers up) sits between the two IB passes on the main stream while the far-plane wavefront runs.  Observations,
-    wrenches and populations bit-identical to plain stepping."""
-    A = g._abi
-    P, Wl = g.BC_PERIODIC, g.BC_WALL
-    bad, ran, with_waves = [], 0, 0
-    for seed in range(16):
-        rng = np.random.default_rng(seed)
-        nx, ny, nz = int(rng.integers(16, 24)), int(rng.integers(14, 20)), int(rng.integers(56, 110))
-        kw = dict(nx=nx, ny=ny, nz=nz, tau=float(rng.uniform(0.65, 1.0)), collision=int(rng.integers(0, 2)),
-                  bc=[Wl] * 4 + [P] * 2 if rng.random() < 0.5 else [P] * 6, max_markers=6000, max_links=16,
-                  pair_lag=int(rng.integers(1, 9)) if rng.random() < 0.7 else 0)
-        a, b = g.Sim(backend=emu, flags=A.FLAG_NO_SPLIT, **kw), g.Sim(backend=emu, flags=A.FLAG_WAVEFRONT, **kw)
-        for f in range(int(rng.integers(1, 3))):
-            links = tuple((float(rng.uniform(4, 7)), float(rng.uniform(1.3, 2.3))) for _ in range(int(rng.integers(1, 5))))
-            d = util.fish_desc(g, root=(nx / 2 + rng.uniform(-2, 2), ny / 2, nz * (0.25 + 0.4 * f) + rng.uniform(-3, 3)), links=links,
-                               free=int(rng.random() < 0.7), heading=float(rng.uniform(-0.4, 0.4)))
-            d.joint_rate_max = float(rng.uniform(0.005, 0.03))
-            for s in (a, b):
-                s.add_fish(d)
-        same, ok = True, True
-        for it in range(5):
-            act, k = rng.uniform(-1, 1, a.action_size()).astype(np.float32), int(rng.integers(1, 8))
-            for s in (a, b):
-                s.set_action(act)
-                s.step(k)
-            oa, ob = a.get_obs(), b.get_obs()
-            if not np.isfinite(oa).all():
-                ok = False
-                break
-            same = same and np.array_equal(oa, ob) and np.array_equal(a.get_link_wrenches(), b.get_link_wrenches())
-            if it == 2 and rng.random() < 0.3:
-                for s in (a, b):
-                    s.reset(0)
-        if ok:
-            ran += 1
-            with_waves += b.stats().pair_substeps > 0
-            if not (same and np.array_equal(a.get_populations(), b.get_populations())):
-                bad.append((seed, kw))
-        a.close()
-        b.close()
-    assert not bad, bad[:3]
-    assert ran >= 12 and with_waves >= 10

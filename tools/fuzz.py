@@ -2,8 +2,8 @@
 """Run the randomised test generators of tests/test_random_cases.py over any seed range (CPU emulation by default).
 
     python tools/fuzz.py static 0 2000                  # random configurations vs the oracle
-    python tools/fuzz.py moving|fish|api|slabs|xslabs|wavefront|wavefront_slabs 0 500
-    FG_EMU_SCHED=rand:3 FG_EMU_GRAPHS=1 python tools/fuzz.py wavefront 0 500     # queued streams, emulated graphs
+    python tools/fuzz.py moving|fish|api|slabs|xslabs 0 500
+    FG_EMU_SCHED=rand:3 FG_EMU_GRAPHS=1 python tools/fuzz.py slabs 0 500     # queued streams, emulated graphs
     python tools/fuzz.py static 0 500 --lib cuda        # the real library on a GPU box
 
 Prints the seeds that fail; the committed tests run fixed ranges of the same generators."""
@@ -20,7 +20,6 @@ import util  # noqa: E402
 util.register_oracle(g)
 kind, lo, hi = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
 lib = sys.argv[sys.argv.index("--lib") + 1] if "--lib" in sys.argv else os.path.join(ROOT, "tests", "emu", "libfishgym_emu.so")
-exact = lib != "cuda"
 bad, ran = [], 0
 for seed in range(lo, hi):
     if kind == "static":
@@ -40,10 +39,6 @@ for seed in range(lo, hi):
     elif kind == "xslabs":
         w, kw, _ = t.run_bodies_across_slabs_case(g, lib, seed)
         ok = None if w is None else (w["f"] <= 1e-6 and w["wrench"] <= 1e-4)
-    elif kind == "wavefront":
-        ok, _, kw = t.run_wavefront_case(g, lib, seed, exact=exact)
-    elif kind == "wavefront_slabs":
-        ok, _, kw = t.run_wavefront_slab_case(g, lib, seed)
     else:
         raise SystemExit(__doc__)
     if ok is None:
