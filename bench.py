@@ -113,6 +113,8 @@ def make_sim(g, backend, wl, rank, world, device, flags=0, nz_override=None, ext
         for s_ in range(64):
             c = ((64.3 + 128 * (s_ % 4)) / shrink, (64.1 + 128 * ((s_ // 4) % 4)) / shrink, rank * nzl + (64.2 + 128 * (s_ // 16)) / shrink)
             Xs.append(sphere_markers(c, R, n1)); links.append(np.full(n1, s_, np.int32)); origins.append(c)
+        if os.environ.get("FG_BENCH_SORT_MARKERS"):      # A/B of the tile spread: list order follows the cells (z, y, x) within each sphere
+            Xs = [x[np.lexsort((np.floor(x[:, 0]), np.floor(x[:, 1]), np.floor(x[:, 2])))] for x in Xs]
         X = np.concatenate(Xs)
         markers = (X, np.zeros_like(X), np.full(len(X), 4 * np.pi * R * R / n1, np.float32), np.concatenate(links), np.array(origins))
     elif wl == "school_1024x512x512":
@@ -585,6 +587,8 @@ def main():
                     help="f16: the opt-in 16-bit-storage build (fp32 arithmetic, 76 B per cell update; NOT the headline configuration)")
     ap.add_argument("--even-vec", type=int, default=0, choices=[0, 1, 2, 4],
                     help="even steps with 1 / 2 / 4 cells per thread (32- / 64- / 128-bit accesses); 0: the library's default (2 where nx %% 256 == 0)")
+    ap.add_argument("--ib-tile-spread", action="store_true", help="A/B: spreading staged per CTA in shared memory (FG_FLAG_IB_TILE_SPREAD)")
+    ap.add_argument("--sort-markers", action="store_true", help="A/B: box_512_ib markers ordered by cell within each sphere (neighbours on the surface are neighbours in the list)")
     ap.add_argument("--no-split", action="store_true", help="collide all planes after the IB kernels (no far-plane branch beside them)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer loop (default: --steps)")
     ap.add_argument("--ref-budget-s", type=float, default=150.0, help="--impl reference: wall-clock budget that sizes the oracle's sample")
@@ -627,7 +631,10 @@ def main():
     flags = ((A.FLAG_NO_OVERLAP if args.no_overlap else 0) | (A.FLAG_NO_GRAPHS if args.no_graphs else 0) |
              (A.FLAG_NO_SPLIT if args.no_split else 0) | (A.FLAG_NO_SWEEP_FLIP if args.no_flip else 0) |
              (A.FLAG_FUSED_PAIRS if args.pairs else 0) | (A.FLAG_NO_XWARP if args.no_xwarp else 0) |
-             {0: 0, 1: A.FLAG_EVEN_SCALAR, 2: A.FLAG_EVEN_VEC2, 4: A.FLAG_EVEN_VEC4}[args.even_vec])
+             {0: 0, 1: A.FLAG_EVEN_SCALAR, 2: A.FLAG_EVEN_VEC2, 4: A.FLAG_EVEN_VEC4}[args.even_vec] |
+             (A.FLAG_IB_TILE_SPREAD if args.ib_tile_spread else 0))
+    if args.sort_markers:
+        os.environ["FG_BENCH_SORT_MARKERS"] = "1"
     bytes_per_update = BYTES_PER_CELL_UPDATE if args.storage == "f32" else BYTES_PER_CELL_UPDATE / 2
 
     clocks = ClockSampler(local) if rank == 0 else None      # runs through warm-up, the timed region and the profiled pass
@@ -674,6 +681,14 @@ def main():
                                      "pct_of_hbm_roofline": sph["pct_of_hbm_roofline"], "launch_mode": sph["launch_mode"],
                                      "scaling": "weak: one channel + sphere per GPU"}
         if world > 1:
+            # configs[3]: the school of 16 fish in the 1024x512x512 tank, z-slabs across the ranks (strong scaling), bodies and
+            # their marker / wrench exchange across slab faces; Gym loop of 20 substeps per env step
+            sch = measure(ctx, "school_1024x512x512", flags, max(args.steps, 100), max(args.warmup, 20))
+            sub["school_1024x512x512"] = {"workload": WORKLOADS["school_1024x512x512"]["desc"], "scaling": "strong", "value": sch["value"],
+                                          "ms_per_step": sch["ms_per_step"], "e2e_value": sch["e2e"]["value"],
+                                          "env_steps_per_s": sch["e2e"]["env_steps_per_s"], "substeps_per_env_step": 20,
+                                          "markers_per_gpu": sch["markers_per_gpu"], "roofline_frac": (sch.get("roofline") or {}).get("frac"),
+                                          "launch_mode": sch["launch_mode"]}
             sub["parity_vs_1gpu"] = parity_vs_one_gpu(ctx)
 
     if rank != 0:

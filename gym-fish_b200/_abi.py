@@ -30,6 +30,7 @@ FLAG_NO_SWEEP_FLIP = 32
 FLAG_FUSED_PAIRS = 64
 FLAG_NO_XWARP = 128
 FLAG_SYNC_STEP = 256
+FLAG_IB_TILE_SPREAD = 512
 FLAG_EVEN_VEC4 = 1024
 FLAG_EVEN_VEC2 = 2048
 FLAG_EVEN_SCALAR = 8192

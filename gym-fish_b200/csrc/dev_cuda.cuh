@@ -159,6 +159,7 @@ public:
                  ck(cudaEventCreateWithFlags(&fork_ev_[i], cudaEventDisableTiming), "cudaEventCreate") &&
                  ck(cudaEventCreateWithFlags(&join_ev_[i], cudaEventDisableTiming), "cudaEventCreate");
         stream_ = s_[0];
+        ok = ok && ck(cudaStreamCreateWithFlags(&copy_s_, cudaStreamNonBlocking), "cudaStreamCreate(copy)");
         for (int i = 0; i < 2 && ok; ++i)
             ok = ck(cudaEventCreate(&tev_[i][0]), "cudaEventCreate") && ck(cudaEventCreate(&tev_[i][1]), "cudaEventCreate");
         if (!ok) e = err;
@@ -175,6 +176,7 @@ public:
             fork_ev_[i] = join_ev_[i] = nullptr;
         }
         stream_ = nullptr;
+        if (copy_s_) { cudaStreamSynchronize(copy_s_); cudaStreamDestroy(copy_s_); copy_s_ = nullptr; }
         for (auto &pr : tev_)
             for (auto &e : pr) { if (e) cudaEventDestroy(e); e = nullptr; }
         if (timeout_word_) { cudaFreeHost(const_cast<int *>(timeout_word_)); timeout_word_ = nullptr; }
@@ -247,6 +249,16 @@ public:
     bool ev_sync(int id) {
         if (id < 0 || id >= kNamedEvents || !named_[id]) return true;
         return ck(cudaEventSynchronize(named_[id]), "cudaEventSynchronize");
+    }
+    // Host -> device copy that starts NOW on the copy stream (beside whatever the handle's streams are running), after the
+    // work event `after` marks (the last reader of the destination); event `done` is recorded behind it and stream 0 waits
+    // for it, so everything queued on the handle's streams from here on sees the data.  Never called inside a capture.
+    bool upload_early(void *d, const void *pinned, size_t n, int done, int after) {
+        if (done < 0 || done >= kNamedEvents || gmode_ != 0) { err = "upload_early: bad event or called inside a graph capture"; return false; }
+        if (!named_[done] && !ck(cudaEventCreateWithFlags(&named_[done], cudaEventDisableTiming), "cudaEventCreate")) return false;
+        if (after >= 0 && after < kNamedEvents && named_[after] && !ck(cudaStreamWaitEvent(copy_s_, named_[after], 0), "copy stream wait")) return false;
+        return ck(cudaMemcpyAsync(d, pinned, n, cudaMemcpyHostToDevice, copy_s_), "H2D early") &&
+               ck(cudaEventRecord(named_[done], copy_s_), "cudaEventRecord(copy)") && ck(cudaStreamWaitEvent(stream_, named_[done], 0), "wait for upload");
     }
     // Timing of one fg_step call: two event pairs used alternately, so that a call can record its own pair while the
     // previous call (which returned before its collide finished) still owns the other one.
@@ -509,7 +521,7 @@ private:
     }
 
     int device_ = -1;
-    cudaStream_t stream_ = nullptr;
+    cudaStream_t stream_ = nullptr, copy_s_ = nullptr;
     cudaEvent_t tev_[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
     int tpair_ = 0;
     std::vector<std::pair<std::string, void *>> opened_;

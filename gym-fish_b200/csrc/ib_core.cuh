@@ -330,11 +330,10 @@ struct IbInterpSpread {
         v += __shfl_xor_sync(0xffffffffu, v, 1);
         return v;
     }
-    __device__ __forceinline__ static void cta(const IbParams &p, int bx, int tx) {
-        const int gt = bx * kThreads + tx;
-        if (gt < 6 * p.n_links) p.wrench[gt] = 0.0;           // accumulated by IbLinkReduce
-        const int k = bx * kMarkers + (tx >> 5), lane = tx & 31;
-        if (k >= p.n || (p.gidx && p.gidx[k] < 0)) return;    // warp-uniform
+    // interpolation + direct forcing of marker k by one warp: (weight, band slot) of the lane's two nodes and the marker force
+    struct Nodes { float w0, w1, f0, f1, f2; int s0, s1; };
+    __device__ __forceinline__ static Nodes marker_force(const IbParams &p, int k, int lane) {
+        Nodes r;
         float w0, w1;
         int s0, s1;
         const size_t nb = (size_t)k * kNodes;
@@ -363,19 +362,72 @@ struct IbInterpSpread {
         if (s0 >= 0) { u0 = w0 * p.band_u[s0]; u1 = w0 * p.band_u[p.band_cap + s0]; u2 = w0 * p.band_u[2 * p.band_cap + s0]; }
         if (s1 >= 0) { u0 += w1 * p.band_u[s1]; u1 += w1 * p.band_u[p.band_cap + s1]; u2 += w1 * p.band_u[2 * p.band_cap + s1]; }
         u0 = warp_all_sum(u0); u1 = warp_all_sum(u1); u2 = warp_all_sum(u2);          // every lane holds U*_k
-        const float f0 = 2.0f * (p.U[3 * k] - u0), f1 = 2.0f * (p.U[3 * k + 1] - u1), f2 = 2.0f * (p.U[3 * k + 2] - u2);
+        r.f0 = 2.0f * (p.U[3 * k] - u0); r.f1 = 2.0f * (p.U[3 * k + 1] - u1); r.f2 = 2.0f * (p.U[3 * k + 2] - u2);
         if (lane == 0) {
             p.Ustar[3 * k] = u0; p.Ustar[3 * k + 1] = u1; p.Ustar[3 * k + 2] = u2;
-            p.Fm[3 * k] = f0; p.Fm[3 * k + 1] = f1; p.Fm[3 * k + 2] = f2;
+            p.Fm[3 * k] = r.f0; p.Fm[3 * k + 1] = r.f1; p.Fm[3 * k + 2] = r.f2;
         }
         const float dV = p.dV[k];
-        if (s0 >= 0) {
-            const float w = w0 * dV;
-            atomicAdd(&p.bandF[s0], w * f0); atomicAdd(&p.bandF[p.band_cap + s0], w * f1); atomicAdd(&p.bandF[2 * p.band_cap + s0], w * f2);
+        r.w0 = w0 * dV; r.w1 = w1 * dV; r.s0 = s0; r.s1 = s1;
+        return r;
+    }
+    __device__ __forceinline__ static void cta(const IbParams &p, int bx, int tx) {
+        const int gt = bx * kThreads + tx;
+        if (gt < 6 * p.n_links) p.wrench[gt] = 0.0;           // accumulated by IbLinkReduce
+        const int k = bx * kMarkers + (tx >> 5), lane = tx & 31;
+        if (k >= p.n || (p.gidx && p.gidx[k] < 0)) return;    // warp-uniform
+        const Nodes r = marker_force(p, k, lane);
+        if (r.s0 >= 0) {
+            atomicAdd(&p.bandF[r.s0], r.w0 * r.f0); atomicAdd(&p.bandF[p.band_cap + r.s0], r.w0 * r.f1); atomicAdd(&p.bandF[2 * p.band_cap + r.s0], r.w0 * r.f2);
         }
-        if (s1 >= 0) {
-            const float w = w1 * dV;
-            atomicAdd(&p.bandF[s1], w * f0); atomicAdd(&p.bandF[p.band_cap + s1], w * f1); atomicAdd(&p.bandF[2 * p.band_cap + s1], w * f2);
+        if (r.s1 >= 0) {
+            atomicAdd(&p.bandF[r.s1], r.w1 * r.f0); atomicAdd(&p.bandF[p.band_cap + r.s1], r.w1 * r.f1); atomicAdd(&p.bandF[2 * p.band_cap + r.s1], r.w1 * r.f2);
+        }
+    }
+#endif
+};
+
+// A/B variant (FG_FLAG_IB_TILE_SPREAD; BASELINE.json:5 (b) "shared-memory-staged tile accumulation"): the spread of a CTA's
+// markers is first accumulated in a shared-memory table keyed by band slot (open addressing, 512 entries for at most
+// 4 x 64 nodes), then every occupied entry goes to global memory with ONE reduction per component.  Markers that are
+// neighbours on the body surface share most of their 4 x 4 x 4 stencils, so a spatially ordered marker list needs ~2.3 x
+// fewer global atomics; a list without locality (the Fibonacci spheres of bench.py in generation order) pays the staging
+// and saves nothing.  A warp holds ONE marker whose 64 nodes are distinct cells, so warp-level aggregation
+// (__match_any_sync) has nothing to merge by construction.  Measured A/B: profiles/r2_summary.md.
+struct IbInterpSpreadTile {
+    static constexpr int kThreads = 128;
+    static constexpr int kMarkers = kThreads / 32;
+    static constexpr int kMinBlocks = 12;
+    static constexpr int kBlockPhases = 2;
+    static constexpr int kSlots = 512;
+    FG_HD static void run(const IbParams &p, int bx, int by, int bz, int tx, int phase) { IbInterpSpread::run(p, bx, by, bz, tx, phase); }
+#if defined(__CUDACC__)
+    __device__ __forceinline__ static void stage(int *keys, float (*vals)[kSlots], int s, float a, float b, float c) {
+        unsigned h = (unsigned(s) * 2654435761u) >> 23;
+        for (;;) {
+            const int old = atomicCAS(&keys[h], -1, s);
+            if (old == -1 || old == s) break;
+            h = (h + 1) & (kSlots - 1);
+        }
+        atomicAdd(&vals[0][h], a); atomicAdd(&vals[1][h], b); atomicAdd(&vals[2][h], c);
+    }
+    __device__ __forceinline__ static void cta(const IbParams &p, int bx, int tx) {
+        __shared__ int keys[kSlots];
+        __shared__ float vals[3][kSlots];
+        for (int i = tx; i < kSlots; i += kThreads) { keys[i] = -1; vals[0][i] = 0.f; vals[1][i] = 0.f; vals[2][i] = 0.f; }
+        const int gt = bx * kThreads + tx;
+        if (gt < 6 * p.n_links) p.wrench[gt] = 0.0;
+        __syncthreads();
+        const int k = bx * kMarkers + (tx >> 5), lane = tx & 31;
+        if (k < p.n && !(p.gidx && p.gidx[k] < 0)) {          // warp-uniform
+            const IbInterpSpread::Nodes r = IbInterpSpread::marker_force(p, k, lane);
+            if (r.s0 >= 0) stage(keys, vals, r.s0, r.w0 * r.f0, r.w0 * r.f1, r.w0 * r.f2);
+            if (r.s1 >= 0) stage(keys, vals, r.s1, r.w1 * r.f0, r.w1 * r.f1, r.w1 * r.f2);
+        }
+        __syncthreads();
+        for (int i = tx; i < kSlots; i += kThreads) {
+            const int s = keys[i];
+            if (s >= 0) { atomicAdd(&p.bandF[s], vals[0][i]); atomicAdd(&p.bandF[p.band_cap + s], vals[1][i]); atomicAdd(&p.bandF[2 * p.band_cap + s], vals[2][i]); }
         }
     }
 #endif
@@ -613,6 +665,7 @@ public:
     const double *origin_ptr() const { return h_origin_.data(); }
     void set_fused(bool on) { fused_ = on; }
     void set_reuse_static(bool on) { reuse_static_ = on; }
+    void set_tile_spread(bool on) { tile_spread_ = on; }
     void clear_wrenches() { if (h_out_) std::fill(h_out_, h_out_ + 6 * size_t(maxl_), 0.0); }
 
     int create(Dev &dev, const FgConfig &cfg, const Lattice &L, std::string &err) {
@@ -771,10 +824,20 @@ public:
         }
         const size_t head = (xchg_ ? 9 : 8) * M;
         for (size_t i = 0; i < 3 * size_t(maxl_); ++i) msg[head + i] = float(h_origin_[i]);
-        // The copy itself is queued by flush_upload() at the start of the next compute_forces(), i.e. AFTER the step has
-        // launched the far-plane collide, which therefore does not wait for the upload.
-        pending_sb_ = sb;
         pending_bytes_ = sizeof(float) * (head + 3 * size_t(maxl_));
+        if (!range_known) {
+            // fg_set_markers (a caller that re-sends its markers every step): the copy starts NOW on the copy stream, beside
+            // the collide of the previous step that is still running — the call came after fg_step returned, i.e. after the
+            // last IB pass (the only reader of the device message) finished.  3.2 MB at 1e5 markers: ~0.1 ms off the step.
+            if (!dev.upload_early(dmsg_, msg, pending_bytes_, EV_STAGE0 + sb, EV_WRENCH)) { err = dev.err; return FG_ECUDA; }
+            stage_used_[sb] = true;
+            pending_sb_ = -1;
+        } else {
+            // host-integrated bodies (inside fg_step, possibly inside a graph capture): the copy is queued by flush_upload()
+            // at the start of the next compute_forces(), i.e. AFTER the step has launched the far-plane collide, which
+            // therefore does not wait for the upload
+            pending_sb_ = sb;
+        }
         n_ = m;
         n_total_ = n;
         markers_dirty_ = true;
@@ -877,7 +940,8 @@ public:
             ok = ok && (parity == 0 ? dev.template launch<IbBandMoments<0>>(Dim3x((bound2 + 127) / 128), p)
                                     : dev.template launch<IbBandMoments<1>>(Dim3x((bound2 + 127) / 128), p));
             if (!xchg_) {
-                ok = ok && dev.template launch_block_phased<IbInterpSpread>(Dim3x(std::max(dev.interp_spread_blocks(n_), (6 * nl_ + 127) / 128)), p);
+                const Dim3 gs = Dim3x(std::max(dev.interp_spread_blocks(n_), (6 * nl_ + 127) / 128));
+                ok = ok && (tile_spread_ ? dev.template launch_block_phased<IbInterpSpreadTile>(gs, p) : dev.template launch_block_phased<IbInterpSpread>(gs, p));
                 ok = ok && dev.template launch<IbLinkReduce>(Dim3x((n_ + 127) / 128), p);
             } else {
                 // bodies across slab faces: the exchange of partial U* sits between interpolation and spreading
@@ -1046,7 +1110,7 @@ private:
     size_t msg_floats_ = 0;
     int per_[3] = {1, 1, 1};
     bool band_live_ = false, forces_valid_ = false, wrench_fetched_ = true, fused_ = false;
-    bool markers_dirty_ = true, reuse_static_ = true;
+    bool markers_dirty_ = true, reuse_static_ = true, tile_spread_ = false;
     bool z_any_ = false, z_all_ = true;
     int zmin_ = 1, zmax_ = 0;
     bool stage_used_[2] = {false, false};

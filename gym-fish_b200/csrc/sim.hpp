@@ -444,6 +444,7 @@ public:
             if (ib_on) {
                 if (prof) dev.mark(1);
                 ib_.set_fused((cfg.flags & FG_FLAG_FUSED_IB) != 0);
+                ib_.set_tile_spread((cfg.flags & FG_FLAG_IB_TILE_SPREAD) != 0);
                 {
                     Range r(dev, "fg:immersed_boundary");
                     if (int rc = ib_.compute_forces(dev, L_, C_, parity_, err)) return rc;

@@ -67,6 +67,7 @@ extern "C" {
 #define FG_FLAG_FUSED_PAIRS 64 /* even step + following odd step as ONE L2-resident wavefront launch (no bodies, one rank); halves DRAM traffic but measured slower on B200 (r1; so were a launch-level wavefront of plane chunks and a persistent-CTA form in r2, both removed: profiles/r2_summary.md) */
 #define FG_FLAG_NO_XWARP 128   /* x walls: predicated wall selects in every thread (default: only the two warps at the row ends run the wall code) */
 #define FG_FLAG_SYNC_STEP 256  /* fg_step returns only when all its device work has finished (default: when wrenches / obs are there) */
+#define FG_FLAG_IB_TILE_SPREAD 512 /* A/B: force spreading staged per CTA in a shared-memory table keyed by band cell, one global reduction per touched cell (default: one red.add per stencil node); pays only for spatially ordered marker lists (profiles/r2_summary.md) */
 #define FG_FLAG_EVEN_VEC4 1024 /* even steps take 4 cells per thread with 128-bit loads / stores (needs nx % 4 == 0, no obstacles); measured +1.3 ... +2.4 %, less than the 2-cell form (profiles/r2_summary.md) */
 #define FG_FLAG_EVEN_VEC2 2048 /* ... 2 cells per thread with 64-bit accesses for any even nx (the DEFAULT when nx is a multiple of 256: +2.6 ... +3.2 %) */
 #define FG_FLAG_EVEN_SCALAR 8192 /* even steps with the scalar one-cell-per-thread kernel everywhere (A/B against the default) */

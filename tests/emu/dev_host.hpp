@@ -41,7 +41,7 @@ public:
     // / highest / a random runnable stream.  A missing fork / join between two launches that touch the same data then
     // shows up as a result that depends on the policy (tests/test_stream_order.py); work left on a side stream at a
     // synchronisation is reported as an error.  Nothing stays queued across ABI calls (toc_record drains).
-    static constexpr int kStreams = 4;
+    static constexpr int kStreams = 5;      // 0-3 as in dev_cuda.cuh, 4 = its copy stream
     bool init(int, std::string &) {
         if (const char *e = std::getenv("FG_EMU_SCHED")) {
             const std::string v(e);
@@ -83,6 +83,15 @@ public:
         if (id < 0 || id >= 4 || !named_[id]) return true;
         std::shared_ptr<bool> e = named_[id];
         return drain_until([e] { return *e; });
+    }
+    // dev_cuda.cuh upload_early: the copy runs on its own stream behind event `after`, stream 0 waits for it
+    bool upload_early(void *d, const void *s, size_t n, int done, int after) {
+        if (gmode_ != 0) { err = "upload_early inside a graph capture"; return false; }
+        if (after >= 0 && after < 4 && named_[after]) wait(4, named_[after]);
+        if (!submit(4, [=] { std::memcpy(d, s, n); return true; })) return false;
+        named_[done] = record(4);
+        wait(0, named_[done]);
+        return true;
     }
     void tic() { t0_ = std::chrono::steady_clock::now(); }
     void marks_reset() {}

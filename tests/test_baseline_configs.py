@@ -118,10 +118,10 @@ def _many_spheres(n_side, spacing, R, z_shift=0.0):
     return X, np.concatenate(links), np.array(origins), np.full(len(X), 4 * np.pi * R * R / n1, np.float32)
 
 
-def _marker_cloud(g, backend, n_box, n_side, R, min_markers):
+def _marker_cloud(g, backend, n_box, n_side, R, min_markers, flags=0):
     """Static cloud for 5 steps (index map and band reused), then re-sent and displaced every step for 5 more."""
     kw = dict(nx=n_box, ny=n_box, nz=n_box, tau=0.6, collision=g.MRT, max_markers=110000, max_links=64)
-    ref, dev = g.Sim(backend="oracle", **kw), g.Sim(backend=backend, **kw)
+    ref, dev = g.Sim(backend="oracle", **kw), g.Sim(backend=backend, flags=flags, **kw)
     X, link, origins, dV = _many_spheres(n_side, n_box / n_side, R)
     assert len(X) >= min_markers
     rng = np.random.default_rng(7)
@@ -172,6 +172,14 @@ def test_config4_1e5_markers_on_256_cubed_match_oracle(g, cuda):
     interpolate / spread launch and IbClearBand of a moving cloud at this scale."""
     util.register_oracle(g)
     _marker_cloud(g, cuda, 256, 4, 11.1, 99000)
+
+
+@pytest.mark.gpu
+def test_config4_tile_spread_variant_matches_oracle(g, cuda):
+    """The A/B variant of the spreading (FG_FLAG_IB_TILE_SPREAD: per-CTA shared-memory table, one global reduction per touched
+    band cell) against the oracle on 27 spheres / 4 x 10^4 markers, static and moving."""
+    util.register_oracle(g)
+    _marker_cloud(g, cuda, 192, 3, 11.1, 41000, flags=g._abi.FLAG_IB_TILE_SPREAD)
 
 
 def test_config4_marker_cloud_reduced_emulated(g, emu):

@@ -72,10 +72,10 @@ def _ib_pair(g, cuda, kw, X, U, dV, link, origins, init_u, steps):
     return out
 
 
-@pytest.mark.parametrize("flags", ["default", "fused_ib", "no_graphs"])
+@pytest.mark.parametrize("flags", ["default", "fused_ib", "no_graphs", "tile_spread"])
 def test_immersed_boundary_prescribed_markers(g, cuda, flags):
     P, Wl, IN, OUT = g.BC_PERIODIC, g.BC_WALL, g.BC_INLET, g.BC_OUTLET
-    fl = {"default": 0, "fused_ib": g._abi.FLAG_FUSED_IB, "no_graphs": g._abi.FLAG_NO_GRAPHS}[flags]
+    fl = {"default": 0, "fused_ib": g._abi.FLAG_FUSED_IB, "no_graphs": g._abi.FLAG_NO_GRAPHS, "tile_spread": g._abi.FLAG_IB_TILE_SPREAD}[flags]
     kw = dict(nx=20, ny=18, nz=24, tau=0.8, collision=g.MRT, max_markers=4000, max_links=4,
               bc=[P, P, Wl, Wl, IN, OUT], inlet_u=[0, 0, 0.05], flags=fl)
     X = np.concatenate([util.sphere_markers((10.3, 9.1, 8.2), 4.0, 200), util.sphere_markers((1.0, 16.5, 20.0), 3.0, 120)])
