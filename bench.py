@@ -514,7 +514,12 @@ def measure(ctx, wl, flags, steps, warmup, storage="f32", clocks=None, want_e2e=
             res["roofline"] = {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": traffic_src, "algorithmic_bytes_per_launch": bytes_per_update * sp.collide_cells / sp.collide_launches,
-                "kernel": "fg::StreamCollide<parity, MRT> (even+odd average)", "peak_source": peak_src,
+                "kernel": "fg::StreamCollide (even + odd step average; at nx % 256 == 0 the two-cell forms StreamCollideEvenVec<MRT, 2> / StreamCollideOddVec2<MRT>)",
+                "peak_source": peak_src,
+                "frac_of_nominal_8000_gbs": achieved / 8000.0,
+                "frac_note": ("frac > 1 is not an accounting error: `peak` is the bandwidth of a torch device-to-device copy (MEASURED_PEAKS.json), and this kernel "
+                              "moves its algorithmic bytes (= its DRAM bytes, profiles/r2_traffic.json) faster than that copy does; ncu reports 6.8 TB/s DRAM "
+                              "throughput for the even step (profiles/r2_summary.md)") if achieved > peak else None,
                 "kernel_ms_per_launch": sp.collide_ms / sp.collide_launches, "launches_timed": int(sp.collide_launches),
                 "cells_per_launch": sp.collide_cells / sp.collide_launches, "bytes_per_cell_update": bytes_per_update,
                 "ib_ms_per_step": sp.ib_ms / steps,
@@ -587,6 +592,8 @@ def main():
                     help="f16: the opt-in 16-bit-storage build (fp32 arithmetic, 76 B per cell update; NOT the headline configuration)")
     ap.add_argument("--even-vec", type=int, default=0, choices=[0, 1, 2, 4],
                     help="even steps with 1 / 2 / 4 cells per thread (32- / 64- / 128-bit accesses); 0: the library's default (2 where nx %% 256 == 0)")
+    ap.add_argument("--odd-vec", type=int, default=0, choices=[0, 1, 2],
+                    help="bulk odd steps with 1 / 2 cells per thread; 0: the library's default (2 where nx %% 256 == 0 and x is periodic)")
     ap.add_argument("--ib-tile-spread", action="store_true", help="A/B: spreading staged per CTA in shared memory (FG_FLAG_IB_TILE_SPREAD)")
     ap.add_argument("--sort-markers", action="store_true", help="A/B: box_512_ib markers ordered by cell within each sphere (neighbours on the surface are neighbours in the list)")
     ap.add_argument("--no-split", action="store_true", help="collide all planes after the IB kernels (no far-plane branch beside them)")
@@ -632,7 +639,7 @@ def main():
              (A.FLAG_NO_SPLIT if args.no_split else 0) | (A.FLAG_NO_SWEEP_FLIP if args.no_flip else 0) |
              (A.FLAG_FUSED_PAIRS if args.pairs else 0) | (A.FLAG_NO_XWARP if args.no_xwarp else 0) |
              {0: 0, 1: A.FLAG_EVEN_SCALAR, 2: A.FLAG_EVEN_VEC2, 4: A.FLAG_EVEN_VEC4}[args.even_vec] |
-             (A.FLAG_IB_TILE_SPREAD if args.ib_tile_spread else 0))
+             (A.FLAG_IB_TILE_SPREAD if args.ib_tile_spread else 0) | {0: 0, 1: A.FLAG_ODD_SCALAR, 2: A.FLAG_ODD_VEC2}[args.odd_vec])
     if args.sort_markers:
         os.environ["FG_BENCH_SORT_MARKERS"] = "1"
     bytes_per_update = BYTES_PER_CELL_UPDATE if args.storage == "f32" else BYTES_PER_CELL_UPDATE / 2
@@ -716,7 +723,8 @@ def main():
         "run": {"population_storage": args.storage, "markers_per_gpu": main_res["markers_per_gpu"],
                 "decomposition": "z-slabs, halos by peer stores over NVLink (CUDA IPC), no NCCL on the data path" if world > 1 else "single GPU",
                 "halo_overlap": not args.no_overlap, "launch_mode": main_res["launch_mode"],
-                "even_step_cells_per_thread": args.even_vec or "library default (2 where nx % 256 == 0, else 1)"},
+                "even_step_cells_per_thread": args.even_vec or "library default (2 where nx % 256 == 0, else 1)",
+                "odd_step_cells_per_thread": args.odd_vec or "library default (2 in bulk rows where nx % 256 == 0 and x is periodic, else 1)"},
         "roofline": main_res.get("roofline"), "cpu_baseline": cpu, "e2e": main_res.get("e2e"), "gpu_launches": main_res["gpu_launches"], "clocks": clk,
         "pct_of_hbm_roofline": main_res["pct_of_hbm_roofline"],
         "sub_records": sub or None,

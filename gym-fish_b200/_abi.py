@@ -34,6 +34,8 @@ FLAG_IB_TILE_SPREAD = 512
 FLAG_EVEN_VEC4 = 1024
 FLAG_EVEN_VEC2 = 2048
 FLAG_EVEN_SCALAR = 8192
+FLAG_ODD_VEC2 = 16384
+FLAG_ODD_SCALAR = 32768
 
 _ERR_NAMES = {FG_EINVAL: "FG_EINVAL", FG_ENOMEM: "FG_ENOMEM", FG_ECUDA: "FG_ECUDA", FG_ESTATE: "FG_ESTATE",
               FG_ENOTSUP: "FG_ENOTSUP", FG_EPEER: "FG_EPEER"}

@@ -641,6 +641,100 @@ struct StreamCollideEvenVec {
         for (int i = 0; i < Q; ++i) *reinterpret_cast<VecF<V> *>(L.f + i * L.slot + idx) = v[i];
     }
 };
+
+// ---------------------------------------------------------------- odd step, 2 cells per thread (bulk rows without x walls)
+// The odd step reads f_i from slot opp(i) of the neighbour at x - c_i and writes f*_i to slot i of the neighbour at x + c_i.
+// For the 9 slots with c_x = 0 the two cells (x0, x0 + 1) of a thread are an aligned pair in the neighbour row: one 64-bit
+// access.  The 10 slots with c_x != 0 are one float off the pair boundary and stay 32-bit accesses.  Same arithmetic per
+// cell and the same 19 + 19 locations per cell as StreamCollide<1>: bit-identical results.  A/B: profiles/r2_summary.md.
+template <bool MRT>
+struct StreamCollideOddVec2 {
+    static constexpr int kThreads = kCollideThreads;
+#if defined(FG_ODDVEC_OCC)
+    static constexpr int kMinBlocks = FG_ODDVEC_OCC;
+#else
+    static constexpr int kMinBlocks = 6;      // 80 registers, no spills (ptxas); at 5 (<= 102 registers) the BGK variant spills
+#endif
+    using Scalar = StreamCollide<1, MRT, CHECK_NONE>;
+
+    template <int I>
+    FG_HD static void addr(const StepParams &p, char *pc, int dym, int dyp, char *&am, char *&ap) {
+        using D = Dir<I>;
+        constexpr int J = D::opp;
+        am = pc + (D::cy > 0 ? dym : (D::cy < 0 ? dyp : 0)) + p.kz[J][1 - D::cz];      // slot J, row y - c_y, plane z - c_z, at x0
+        ap = pc + (D::cy > 0 ? dyp : (D::cy < 0 ? dym : 0)) + p.kz[I][1 + D::cz];      // slot I, row y + c_y, plane z + c_z, at x0
+    }
+    template <int I>
+    FG_HD static void load_pair(float (&h0)[Q], float (&h1)[Q], const StepParams &p, char *pc, int dym, int dyp, int oxm, int oxp) {
+        using D = Dir<I>;
+        constexpr int J = D::opp;
+        char *am, *ap;
+        addr<I>(p, pc, dym, dyp, am, ap);
+        if (D::cx == 0) {
+            const VecF<2> vm = *reinterpret_cast<const VecF<2> *>(am), vp = *reinterpret_cast<const VecF<2> *>(ap);
+            h0[I] = vm.a[0]; h1[I] = vm.a[1]; h0[J] = vp.a[0]; h1[J] = vp.a[1];
+        } else if (D::cx > 0) {
+            h0[I] = *reinterpret_cast<const float *>(am + oxm); h1[I] = *reinterpret_cast<const float *>(am);
+            h0[J] = *reinterpret_cast<const float *>(ap + 4); h1[J] = *reinterpret_cast<const float *>(ap + oxp);
+        } else {
+            h0[I] = *reinterpret_cast<const float *>(am + 4); h1[I] = *reinterpret_cast<const float *>(am + oxp);
+            h0[J] = *reinterpret_cast<const float *>(ap + oxm); h1[J] = *reinterpret_cast<const float *>(ap);
+        }
+    }
+    // f*_I goes where f_J came from and f*_J where f_I came from
+    template <int I>
+    FG_HD static void store_pair(const float (&h0)[Q], const float (&h1)[Q], const StepParams &p, char *pc, int dym, int dyp, int oxm, int oxp) {
+        using D = Dir<I>;
+        constexpr int J = D::opp;
+        char *am, *ap;
+        addr<I>(p, pc, dym, dyp, am, ap);
+        if (D::cx == 0) {
+            VecF<2> vp, vm;
+            vp.a[0] = h0[I]; vp.a[1] = h1[I]; vm.a[0] = h0[J]; vm.a[1] = h1[J];
+            *reinterpret_cast<VecF<2> *>(ap) = vp; *reinterpret_cast<VecF<2> *>(am) = vm;
+        } else if (D::cx > 0) {
+            *reinterpret_cast<float *>(ap + 4) = h0[I]; *reinterpret_cast<float *>(ap + oxp) = h1[I];
+            *reinterpret_cast<float *>(am + oxm) = h0[J]; *reinterpret_cast<float *>(am) = h1[J];
+        } else {
+            *reinterpret_cast<float *>(ap + oxm) = h0[I]; *reinterpret_cast<float *>(ap) = h1[I];
+            *reinterpret_cast<float *>(am + 4) = h0[J]; *reinterpret_cast<float *>(am + oxp) = h1[J];
+        }
+    }
+
+    // grid: (nx / 2 / threads, rows, planes); requires nx % 2 == 0, periodic x, no blocked link in the rows of the launch
+    FG_HD static void run(const StepParams &p, int bx, int by, int bz, int tx) {
+        const Lattice &L = p.L;
+        const int x0 = (bx * kThreads + tx) * 2, y = p.y0 + by * p.ystride;
+        int zz = p.zz_begin + (p.zz_flip >= 0 ? p.zz_flip - bz : bz) * p.zz_stride;
+        if (zz >= p.zz_skip_begin) zz += p.zz_skip_len;
+        if (x0 >= L.nx) return;
+        const long long idx = ((long long)zz * L.ny + y) * L.nx + x0;
+        char *pc = reinterpret_cast<char *>(L.f + idx);
+        const int dym = (y == 0 ? (L.ny - 1) * L.nx : -L.nx) * 4, dyp = (y == L.ny - 1 ? -(L.ny - 1) * L.nx : L.nx) * 4;
+        const int oxm = (x0 == 0 ? L.nx - 1 : -1) * 4, oxp = (x0 + 2 == L.nx ? -(L.nx - 2) : 2) * 4;   // cells x0 - 1 and x0 + 2 (periodic)
+        float h0[Q], h1[Q];
+        {
+            const VecF<2> v = *reinterpret_cast<const VecF<2> *>(pc + p.kz[0][1]);
+            h0[0] = v.a[0]; h1[0] = v.a[1];
+        }
+#define FG_X(I) load_pair<I>(h0, h1, p, pc, dym, dyp, oxm, oxp);
+        FG_FOR_PAIRS(FG_X)
+#undef FG_X
+        float Fx, Fy, Fz;
+        Scalar::force_at(p, y, zz, idx, Fx, Fy, Fz);
+        if (MRT) collide_mrt(h0, Fx, Fy, Fz, p.C); else collide_bgk(h0, Fx, Fy, Fz, p.C);
+        Scalar::force_at(p, y, zz, idx + 1, Fx, Fy, Fz);
+        if (MRT) collide_mrt(h1, Fx, Fy, Fz, p.C); else collide_bgk(h1, Fx, Fy, Fz, p.C);
+        {
+            VecF<2> v;
+            v.a[0] = h0[0]; v.a[1] = h1[0];
+            *reinterpret_cast<VecF<2> *>(pc + p.kz[0][1]) = v;
+        }
+#define FG_X(I) store_pair<I>(h0, h1, p, pc, dym, dyp, oxm, oxp);
+        FG_FOR_PAIRS(FG_X)
+#undef FG_X
+    }
+};
 #endif
 
 // ---------------------------------------------------------------- two steps in one launch (L2-resident wavefront)

@@ -260,12 +260,14 @@ def test_velocity_probes_match_oracle_at_both_parities(g, emu):
 
 
 @pytest.mark.parametrize("name", ["bgk_periodic", "mrt_force", "mrt_xy_walls", "mrt_all_walls_lid", "mrt_inlet_outlet_ywalls"])
-@pytest.mark.parametrize("vec", [4, 2])
+@pytest.mark.parametrize("vec", [4, 2, "odd2", "even2+odd2"])
 def test_vectorised_even_step_is_bit_identical(g, emu, name, vec):
     """FG_FLAG_EVEN_VEC4 / _VEC2 (lbm_core.cuh StreamCollideEvenVec): V cells per thread with 16- / 8-byte accesses in the
     even step — the same arithmetic per cell, so populations must equal the scalar kernel's bit for bit."""
     kw = dict(util.parity_cases(g)[name])
-    flag = g._abi.FLAG_EVEN_VEC4 if vec == 4 else g._abi.FLAG_EVEN_VEC2
+    A = g._abi
+    # odd2: FG_FLAG_ODD_VEC2 (StreamCollideOddVec2), two cells per thread in the bulk odd step of rows without x walls
+    flag = {4: A.FLAG_EVEN_VEC4, 2: A.FLAG_EVEN_VEC2, "odd2": A.FLAG_ODD_VEC2, "even2+odd2": A.FLAG_EVEN_VEC2 | A.FLAG_ODD_VEC2}[vec]
     a, b = g.Sim(backend=emu, **kw), g.Sim(backend=emu, flags=flag, **kw)
     rho, u = util.smooth_fields(a.shape)
     for s in (a, b):
@@ -315,3 +317,18 @@ def test_default_even_step_on_wide_rows_is_the_two_cell_kernel_and_bit_identical
         s.step(6)
     assert np.array_equal(a.get_populations(), b.get_populations())
     assert util.rel_l2(a.get_fields(f64=True)[1], o.get_fields(f64=True)[1]) <= TOL_FIELD
+
+
+def test_default_two_cell_kernels_equal_the_scalar_ones_on_256_wide_rows(g, emu):
+    """nx % 256 == 0: the library picks the two-cell even and odd kernels by itself; bit-identical to the scalar kernels
+    (FG_FLAG_EVEN_SCALAR | FG_FLAG_ODD_SCALAR) and within tolerance of the oracle."""
+    A = g._abi
+    for name in ("mrt_force", "mrt_inlet_outlet_ywalls"):
+        kw = dict(util.parity_cases(g)[name], nx=256, ny=6, nz=8)
+        a, b, o = g.Sim(backend=emu, **kw), g.Sim(backend=emu, flags=A.FLAG_EVEN_SCALAR | A.FLAG_ODD_SCALAR, **kw), g.Sim(backend="oracle", **kw)
+        rho, u = util.smooth_fields(a.shape)
+        for s in (a, b, o):
+            s.set_fields(rho, u)
+            s.step(7)
+        assert np.array_equal(a.get_populations(), b.get_populations()), name
+        assert util.rel_l2(a.get_fields(f64=True)[1], o.get_fields(f64=True)[1]) <= TOL_FIELD
