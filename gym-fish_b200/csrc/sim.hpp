@@ -711,7 +711,7 @@ private:
         // 8 CTAs/SM (64 registers) on SMALL z-slabs, 9 (56 registers) otherwise (lbm_core.cuh StreamCollide): the ~4 us per
         // step that 9 cost the high-priority chain on slabs of 4.2 M cells outweigh its 2 % faster kernel only below ~8 M
         // cells per rank (512^3 and the school on 8 GPUs were measured with 9: 318 252 / 272 528 MLUPS)
-        if (peers_ && (long long)L_.plane * L_.nz < (8ll << 20))
+        if (peers_ && slab_occ8_ && (long long)L_.plane * L_.nz < (8ll << 20))
             return cfg.collision == FG_MRT ? dev.template launch<StreamCollide<PARITY, true, MODE, 8>>(g, p)
                                            : dev.template launch<StreamCollide<PARITY, false, MODE, 8>>(g, p);
         return cfg.collision == FG_MRT ? dev.template launch<StreamCollide<PARITY, true, MODE>>(g, p)
@@ -975,6 +975,7 @@ private:
     int timed_substeps_ = 0;
     int64_t collide_launches_ = 0, last_collide_launches_ = 0, collide_cells_ = 0, last_collide_cells_ = 0;
     int64_t split_substeps_ = 0, pair_substeps_ = 0;
+    bool slab_occ8_ = std::getenv("FG_SLAB_OCC9") == nullptr;     // A/B switch for launch_collide_pm's small-slab rule
     int *pair_ctr_ = nullptr;      // [1 + nz + 2] ticket + per-plane completion counters of StreamCollidePair
     bool split_ = false;           // this substep: far planes collide beside the IB kernels
     int near_a_ = 1, near_b_ = 1;  // planes [near_a_, near_b_) wait for the IB force
