@@ -629,7 +629,9 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist   # plumbing only: handle exchange, barriers, max over ranks
-        dist.init_process_group(backend="gloo", rank=rank, world_size=world)
+        import datetime
+        # a rank that dies inside a sub-record must not hold the others in a barrier for gloo's default 30 minutes
+        dist.init_process_group(backend="gloo", rank=rank, world_size=world, timeout=datetime.timedelta(seconds=300))
     ctx = Ctx(g, args, rank, world, local, dist)
 
     wl = args.workload
@@ -661,47 +663,83 @@ def main():
     sim.close()
     del sim
 
-    if want_sub:
-        k_small = max(args.steps, 200)      # the small workloads step in ~0.1 ms: 20 steps would time 2 ms
-        if world == 1:
-            ib = measure(ctx, "box_512_ib", flags, args.steps, args.warmup)
-            plain_e2e = main_res["e2e"]["ms_per_step"]
-            sub["ib_overhead"] = {
-                "workload": WORKLOADS["box_512_ib"]["desc"], "markers": ib["markers_per_gpu"],
-                "static_markers": {"value": ib["value"], "ms_per_step": ib["ms_per_step"],
-                                   "overhead_pct": (ib["ms_per_step"] / main_res["ms_per_step"] - 1.0) * 100.0,
-                                   "note": "device-timed fg_step(K); marker set unchanged, index map and band reused"},
-                "resent_every_step": {"value": ib["e2e"]["value"], "ms_per_step": ib["e2e"]["ms_per_step"],
-                                      "overhead_pct": (ib["e2e"]["ms_per_step"] / plain_e2e - 1.0) * 100.0,
-                                      "h2d_bytes_per_step": ib["e2e"]["h2d_bytes_per_step"],
-                                      "note": "wall clock of fg_set_markers + fg_step(1) + fg_get_link_wrenches per step against the main "
-                                              "workload's own host loop; band cleared and re-registered every step"},
-                "target_pct": 15.0, "ib_kernels_ms_per_step": (ib.get("roofline") or {}).get("ib_ms_per_step"),
-                "launch_mode": ib["launch_mode"]}
-            tank = measure(ctx, "tank_512x256x256", flags, k_small, max(args.warmup, 20))
-            sub["env"] = {"workload": WORKLOADS["tank_512x256x256"]["desc"], "env_steps_per_s": tank["e2e"]["env_steps_per_s"],
-                          "substeps_per_env_step": 20, "value": tank["value"], "e2e_value": tank["e2e"]["value"], "markers": tank["markers_per_gpu"],
-                          "roofline_frac": (tank.get("roofline") or {}).get("frac"), "launch_mode": tank["launch_mode"]}
+    # Sub-records never cost the main line: each one runs under `guarded`; after a failure (on any rank: a rank stuck in a barrier
+    # behind a dead peer leaves it by the process group's time-out) the remaining ones are skipped and the line is printed.
+    broken = []
+
+    def guarded(name, fn):
+        if broken:
+            sub[name] = {"skipped": f"after the failure of {broken[0]}"}
+            return
+        try:
+            fn()
+        except Exception as e:      # noqa: BLE001
+            broken.append(name)
+            sub[name] = {"error": f"{type(e).__name__}: {e}"[:400]}
+
+    def sub_ib():
+        ib = measure(ctx, "box_512_ib", flags, args.steps, args.warmup)
+        plain_e2e = main_res["e2e"]["ms_per_step"]
+        sub["ib_overhead"] = {
+            "workload": WORKLOADS["box_512_ib"]["desc"], "markers": ib["markers_per_gpu"],
+            "static_markers": {"value": ib["value"], "ms_per_step": ib["ms_per_step"],
+                               "overhead_pct": (ib["ms_per_step"] / main_res["ms_per_step"] - 1.0) * 100.0,
+                               "note": "device-timed fg_step(K); marker set unchanged, index map and band reused"},
+            "resent_every_step": {"value": ib["e2e"]["value"], "ms_per_step": ib["e2e"]["ms_per_step"],
+                                  "overhead_pct": (ib["e2e"]["ms_per_step"] / plain_e2e - 1.0) * 100.0,
+                                  "h2d_bytes_per_step": ib["e2e"]["h2d_bytes_per_step"],
+                                  "note": "wall clock of fg_set_markers + fg_step(1) + fg_get_link_wrenches per step against the main "
+                                          "workload's own host loop; band cleared and re-registered every step"},
+            "target_pct": 15.0, "ib_kernels_ms_per_step": (ib.get("roofline") or {}).get("ib_ms_per_step"),
+            "launch_mode": ib["launch_mode"]}
+
+    def sub_env():
+        tank = measure(ctx, "tank_512x256x256", flags, k_small, max(args.warmup, 20))
+        sub["env"] = {"workload": WORKLOADS["tank_512x256x256"]["desc"], "env_steps_per_s": tank["e2e"]["env_steps_per_s"],
+                      "substeps_per_env_step": 20, "value": tank["value"], "e2e_value": tank["e2e"]["value"], "markers": tank["markers_per_gpu"],
+                      "roofline_frac": (tank.get("roofline") or {}).get("frac"), "launch_mode": tank["launch_mode"]}
+
+    def sub_sphere():
         sph = measure(ctx, "sphere_256x128x128", flags, k_small, max(args.warmup, 20))
         sub["sphere_256x128x128"] = {"workload": WORKLOADS["sphere_256x128x128"]["desc"], "value": sph["value"], "ms_per_step": sph["ms_per_step"],
                                      "steps": k_small, "e2e_value": sph["e2e"]["value"], "roofline_frac": (sph.get("roofline") or {}).get("frac"),
                                      "pct_of_hbm_roofline": sph["pct_of_hbm_roofline"], "launch_mode": sph["launch_mode"],
                                      "scaling": "weak: one channel + sphere per GPU"}
+
+    def sub_school():
+        # configs[3]: the school of 16 fish in the 1024x512x512 tank, z-slabs across the ranks (strong scaling), bodies and
+        # their marker / wrench exchange across slab faces; Gym loop of 20 substeps per env step
+        sch = measure(ctx, "school_1024x512x512", flags, max(args.steps, 100), max(args.warmup, 20))
+        sub["school_1024x512x512"] = {"workload": WORKLOADS["school_1024x512x512"]["desc"], "scaling": "strong", "value": sch["value"],
+                                      "ms_per_step": sch["ms_per_step"], "e2e_value": sch["e2e"]["value"],
+                                      "env_steps_per_s": sch["e2e"]["env_steps_per_s"], "substeps_per_env_step": 20,
+                                      "markers_per_gpu": sch["markers_per_gpu"], "roofline_frac": (sch.get("roofline") or {}).get("frac"),
+                                      "launch_mode": sch["launch_mode"]}
+
+    def sub_parity():
+        sub["parity_vs_1gpu"] = parity_vs_one_gpu(ctx)
+
+    if want_sub:
+        k_small = max(args.steps, 200)      # the small workloads step in ~0.1 ms: 20 steps would time 2 ms
+        if world == 1:
+            guarded("ib_overhead", sub_ib)
+            guarded("env", sub_env)
+        guarded("sphere_256x128x128", sub_sphere)
         if world > 1:
-            # configs[3]: the school of 16 fish in the 1024x512x512 tank, z-slabs across the ranks (strong scaling), bodies and
-            # their marker / wrench exchange across slab faces; Gym loop of 20 substeps per env step
-            sch = measure(ctx, "school_1024x512x512", flags, max(args.steps, 100), max(args.warmup, 20))
-            sub["school_1024x512x512"] = {"workload": WORKLOADS["school_1024x512x512"]["desc"], "scaling": "strong", "value": sch["value"],
-                                          "ms_per_step": sch["ms_per_step"], "e2e_value": sch["e2e"]["value"],
-                                          "env_steps_per_s": sch["e2e"]["env_steps_per_s"], "substeps_per_env_step": 20,
-                                          "markers_per_gpu": sch["markers_per_gpu"], "roofline_frac": (sch.get("roofline") or {}).get("frac"),
-                                          "launch_mode": sch["launch_mode"]}
-            sub["parity_vs_1gpu"] = parity_vs_one_gpu(ctx)
+            guarded("parity_vs_1gpu", sub_parity)
+            guarded("school_1024x512x512", sub_school)
+
+    def leave():
+        if dist is not None:
+            try:
+                if not broken:
+                    dist.barrier()
+                dist.destroy_process_group()
+            except Exception:       # noqa: BLE001 — the line is what counts
+                pass
 
     if rank != 0:
-        if dist is not None:
-            dist.barrier()
-            dist.destroy_process_group()
+        leave()
         return
 
     cpu = None
@@ -732,9 +770,7 @@ def main():
     if SHRINK != 1:
         line["dry_run_shrink"] = SHRINK
     print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    leave()
 
 
 if __name__ == "__main__":

@@ -45,13 +45,15 @@ namespace fg {
 #if defined(FG_POP16)
 #if defined(__CUDACC__)
 typedef __half pop_t;
-FG_HD float pop_ld(const pop_t *p) { return __half2float(*p) * (1.0f / 4096.0f); }
-FG_HD void pop_st(pop_t *p, float v) { *p = __float2half_rn(v * 4096.0f); }
+FG_HD float pop_dec(pop_t v) { return __half2float(v) * (1.0f / 4096.0f); }
+FG_HD pop_t pop_enc(float v) { return __float2half_rn(v * 4096.0f); }
 #else
 typedef _Float16 pop_t;
-FG_HD float pop_ld(const pop_t *p) { return float(*p) * (1.0f / 4096.0f); }
-FG_HD void pop_st(pop_t *p, float v) { *p = pop_t(v * 4096.0f); }
+FG_HD float pop_dec(pop_t v) { return float(v) * (1.0f / 4096.0f); }
+FG_HD pop_t pop_enc(float v) { return pop_t(v * 4096.0f); }
 #endif
+FG_HD float pop_ld(const pop_t *p) { return pop_dec(*p); }
+FG_HD void pop_st(pop_t *p, float v) { *p = pop_enc(v); }
 #define FG_POP_NAME "f16"
 #else
 typedef float pop_t;
@@ -73,6 +75,8 @@ FG_HD void pop_st(pop_t *p, float v) {
     *p = v;
 #endif
 }
+FG_HD float pop_dec(pop_t v) { return v; }
+FG_HD pop_t pop_enc(float v) { return v; }
 #define FG_POP_NAME "f32"
 #endif
 constexpr int kPopBytes = int(sizeof(pop_t));
@@ -593,8 +597,7 @@ struct StreamCollide {
 // the other in the same registers (19 V population registers + the collide's temporaries), so the register budget is
 // what limits occupancy: ptxas numbers and the measured A/B against the scalar kernel are in profiles/r2_summary.md.
 // Same arithmetic per cell as StreamCollide<0>: bit-identical results (tests).  Opt-in: FG_FLAG_EVEN_VEC4 / _VEC2.
-#if !defined(FG_POP16)
-template <int V> struct alignas(4 * V) VecF { float a[V]; };
+template <int V> struct alignas(sizeof(pop_t) * V) VecF { pop_t a[V]; };      // V consecutive cells of one slot, in the storage type
 
 template <bool MRT, int V>
 struct StreamCollideEvenVec {
@@ -610,12 +613,12 @@ struct StreamCollideEvenVec {
     FG_HD static void cell(VecF<V> (&v)[Q], const StepParams &p, int y, int zz, long long idx) {
         float h[Q];
         FG_UNROLL
-        for (int i = 0; i < Q; ++i) h[i] = v[i].a[C];
+        for (int i = 0; i < Q; ++i) h[i] = pop_dec(v[i].a[C]);
         float Fx, Fy, Fz;
         Scalar::force_at(p, y, zz, idx + C, Fx, Fy, Fz);
         if (MRT) collide_mrt(h, Fx, Fy, Fz, p.C); else collide_bgk(h, Fx, Fy, Fz, p.C);
-        v[0].a[C] = h[0];
-#define FG_X(I) v[Dir<I>::opp].a[C] = h[I]; v[I].a[C] = h[Dir<I>::opp];
+        v[0].a[C] = pop_enc(h[0]);
+#define FG_X(I) v[Dir<I>::opp].a[C] = pop_enc(h[I]); v[I].a[C] = pop_enc(h[Dir<I>::opp]);
         FG_FOR_PAIRS(FG_X)
 #undef FG_X
     }
@@ -664,21 +667,24 @@ struct StreamCollideOddVec2 {
         am = pc + (D::cy > 0 ? dym : (D::cy < 0 ? dyp : 0)) + p.kz[J][1 - D::cz];      // slot J, row y - c_y, plane z - c_z, at x0
         ap = pc + (D::cy > 0 ? dyp : (D::cy < 0 ? dym : 0)) + p.kz[I][1 + D::cz];      // slot I, row y + c_y, plane z + c_z, at x0
     }
+    FG_HD static float lds(const char *q) { return pop_ld(reinterpret_cast<const pop_t *>(q)); }
+    FG_HD static void sts(char *q, float v) { pop_st(reinterpret_cast<pop_t *>(q), v); }
     template <int I>
     FG_HD static void load_pair(float (&h0)[Q], float (&h1)[Q], const StepParams &p, char *pc, int dym, int dyp, int oxm, int oxp) {
         using D = Dir<I>;
         constexpr int J = D::opp;
+        constexpr int B = kPopBytes;
         char *am, *ap;
         addr<I>(p, pc, dym, dyp, am, ap);
         if (D::cx == 0) {
             const VecF<2> vm = *reinterpret_cast<const VecF<2> *>(am), vp = *reinterpret_cast<const VecF<2> *>(ap);
-            h0[I] = vm.a[0]; h1[I] = vm.a[1]; h0[J] = vp.a[0]; h1[J] = vp.a[1];
+            h0[I] = pop_dec(vm.a[0]); h1[I] = pop_dec(vm.a[1]); h0[J] = pop_dec(vp.a[0]); h1[J] = pop_dec(vp.a[1]);
         } else if (D::cx > 0) {
-            h0[I] = *reinterpret_cast<const float *>(am + oxm); h1[I] = *reinterpret_cast<const float *>(am);
-            h0[J] = *reinterpret_cast<const float *>(ap + 4); h1[J] = *reinterpret_cast<const float *>(ap + oxp);
+            h0[I] = lds(am + oxm); h1[I] = lds(am);
+            h0[J] = lds(ap + B); h1[J] = lds(ap + oxp);
         } else {
-            h0[I] = *reinterpret_cast<const float *>(am + 4); h1[I] = *reinterpret_cast<const float *>(am + oxp);
-            h0[J] = *reinterpret_cast<const float *>(ap + oxm); h1[J] = *reinterpret_cast<const float *>(ap);
+            h0[I] = lds(am + B); h1[I] = lds(am + oxp);
+            h0[J] = lds(ap + oxm); h1[J] = lds(ap);
         }
     }
     // f*_I goes where f_J came from and f*_J where f_I came from
@@ -686,18 +692,19 @@ struct StreamCollideOddVec2 {
     FG_HD static void store_pair(const float (&h0)[Q], const float (&h1)[Q], const StepParams &p, char *pc, int dym, int dyp, int oxm, int oxp) {
         using D = Dir<I>;
         constexpr int J = D::opp;
+        constexpr int B = kPopBytes;
         char *am, *ap;
         addr<I>(p, pc, dym, dyp, am, ap);
         if (D::cx == 0) {
             VecF<2> vp, vm;
-            vp.a[0] = h0[I]; vp.a[1] = h1[I]; vm.a[0] = h0[J]; vm.a[1] = h1[J];
+            vp.a[0] = pop_enc(h0[I]); vp.a[1] = pop_enc(h1[I]); vm.a[0] = pop_enc(h0[J]); vm.a[1] = pop_enc(h1[J]);
             *reinterpret_cast<VecF<2> *>(ap) = vp; *reinterpret_cast<VecF<2> *>(am) = vm;
         } else if (D::cx > 0) {
-            *reinterpret_cast<float *>(ap + 4) = h0[I]; *reinterpret_cast<float *>(ap + oxp) = h1[I];
-            *reinterpret_cast<float *>(am + oxm) = h0[J]; *reinterpret_cast<float *>(am) = h1[J];
+            sts(ap + B, h0[I]); sts(ap + oxp, h1[I]);
+            sts(am + oxm, h0[J]); sts(am, h1[J]);
         } else {
-            *reinterpret_cast<float *>(ap + oxm) = h0[I]; *reinterpret_cast<float *>(ap) = h1[I];
-            *reinterpret_cast<float *>(am + 4) = h0[J]; *reinterpret_cast<float *>(am + oxp) = h1[J];
+            sts(ap + oxm, h0[I]); sts(ap, h1[I]);
+            sts(am + B, h0[J]); sts(am + oxp, h1[J]);
         }
     }
 
@@ -710,12 +717,12 @@ struct StreamCollideOddVec2 {
         if (x0 >= L.nx) return;
         const long long idx = ((long long)zz * L.ny + y) * L.nx + x0;
         char *pc = reinterpret_cast<char *>(L.f + idx);
-        const int dym = (y == 0 ? (L.ny - 1) * L.nx : -L.nx) * 4, dyp = (y == L.ny - 1 ? -(L.ny - 1) * L.nx : L.nx) * 4;
-        const int oxm = (x0 == 0 ? L.nx - 1 : -1) * 4, oxp = (x0 + 2 == L.nx ? -(L.nx - 2) : 2) * 4;   // cells x0 - 1 and x0 + 2 (periodic)
+        const int dym = (y == 0 ? (L.ny - 1) * L.nx : -L.nx) * kPopBytes, dyp = (y == L.ny - 1 ? -(L.ny - 1) * L.nx : L.nx) * kPopBytes;
+        const int oxm = (x0 == 0 ? L.nx - 1 : -1) * kPopBytes, oxp = (x0 + 2 == L.nx ? -(L.nx - 2) : 2) * kPopBytes;   // cells x0 - 1 and x0 + 2 (periodic)
         float h0[Q], h1[Q];
         {
             const VecF<2> v = *reinterpret_cast<const VecF<2> *>(pc + p.kz[0][1]);
-            h0[0] = v.a[0]; h1[0] = v.a[1];
+            h0[0] = pop_dec(v.a[0]); h1[0] = pop_dec(v.a[1]);
         }
 #define FG_X(I) load_pair<I>(h0, h1, p, pc, dym, dyp, oxm, oxp);
         FG_FOR_PAIRS(FG_X)
@@ -727,7 +734,7 @@ struct StreamCollideOddVec2 {
         if (MRT) collide_mrt(h1, Fx, Fy, Fz, p.C); else collide_bgk(h1, Fx, Fy, Fz, p.C);
         {
             VecF<2> v;
-            v.a[0] = h0[0]; v.a[1] = h1[0];
+            v.a[0] = pop_enc(h0[0]); v.a[1] = pop_enc(h1[0]);
             *reinterpret_cast<VecF<2> *>(pc + p.kz[0][1]) = v;
         }
 #define FG_X(I) store_pair<I>(h0, h1, p, pc, dym, dyp, oxm, oxp);
@@ -735,7 +742,6 @@ struct StreamCollideOddVec2 {
 #undef FG_X
     }
 };
-#endif
 
 // ---------------------------------------------------------------- two steps in one launch (L2-resident wavefront)
 // StreamCollidePair runs the EVEN step s and the ODD step s+1 of a range of planes in ONE launch: the odd step follows

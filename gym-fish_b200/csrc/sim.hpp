@@ -719,48 +719,39 @@ private:
     }
     // opt-in experiment: even step with 4 / 2 cells per thread and 16- / 8-byte accesses (lbm_core.cuh StreamCollideEvenVec)
     int even_vec_width() const {
-#if defined(FG_POP16)
-        return 0;
-#else
         if (cfg.flags & FG_FLAG_EVEN_SCALAR) return 0;
         if ((cfg.flags & FG_FLAG_EVEN_VEC4) && L_.nx % 4 == 0) return 4;
         if ((cfg.flags & FG_FLAG_EVEN_VEC2) && L_.nx % 2 == 0) return 2;
         // default (round 2, gpu pass 2): two cells per thread with 64-bit accesses wherever a row fills whole CTAs that way —
         // +2.6 ... +3.2 % MLUPS on 256- and 512-wide lattices (fewer memory instructions per byte; the 4-cell form gains
         // less: 125 registers leave 4 CTAs per SM).  Narrower rows would leave half of each CTA idle and keep the scalar kernel.
-        if (L_.nx % (2 * kCollideThreads) == 0) return 2;
+        if (L_.nx % (2 * kCollideThreads) == 0) return kVecDefault;
         return 0;
-#endif
     }
+    // what the library picks by itself where rows are wide enough: two cells per thread in the fp32 product; the opt-in
+    // 16-bit-storage build has the same kernels behind the flags (its own A/B: profiles/r2_summary.md)
+#if defined(FG_POP16) && !defined(FG_POP16_VEC_DEFAULT)
+    static constexpr int kVecDefault = 0;
+#elif defined(FG_POP16)
+    static constexpr int kVecDefault = FG_POP16_VEC_DEFAULT;
+#else
+    static constexpr int kVecDefault = 2;
+#endif
     // bulk odd step (rows without a blocked link, periodic x) with two cells per thread: the default wherever a row fills
     // whole CTAs that way, like the even step (round 2, gpu pass 7: +2.6 % MLUPS at 20 steps, +3.9 % sustained over 300 steps
     // on 512^3 — 19 % fewer instructions, 6 CTAs of 80 registers); FG_FLAG_ODD_VEC2 forces it for any even nx, FG_FLAG_ODD_SCALAR
     // the one-cell kernel
     bool odd_vec2() const {
-#if defined(FG_POP16)
-        return false;
-#else
         if ((cfg.flags & FG_FLAG_ODD_SCALAR) || L_.solid || L_.nx % 2 != 0 || L_.nx < 4) return false;
-        return (cfg.flags & FG_FLAG_ODD_VEC2) || L_.nx % (2 * kCollideThreads) == 0;
-#endif
+        return (cfg.flags & FG_FLAG_ODD_VEC2) || (kVecDefault != 0 && L_.nx % (2 * kCollideThreads) == 0);
     }
     bool launch_odd_vec2(const StepParams &p, Dim3 g) {
-#if defined(FG_POP16)
-        (void)p; (void)g;
-        return false;
-#else
         return cfg.collision == FG_MRT ? dev.template launch<StreamCollideOddVec2<true>>(g, p) : dev.template launch<StreamCollideOddVec2<false>>(g, p);
-#endif
     }
     bool launch_even_vec(const StepParams &p, Dim3 g, int vec) {
-#if defined(FG_POP16)
-        (void)p; (void)g; (void)vec;
-        return false;
-#else
         const bool mrt = cfg.collision == FG_MRT;
         if (vec == 4) return mrt ? dev.template launch<StreamCollideEvenVec<true, 4>>(g, p) : dev.template launch<StreamCollideEvenVec<false, 4>>(g, p);
         return mrt ? dev.template launch<StreamCollideEvenVec<true, 2>>(g, p) : dev.template launch<StreamCollideEvenVec<false, 2>>(g, p);
-#endif
     }
     // hole: planes [hole_b, hole_e) inside [zb, ze) are left out (zstride 1 only)
     bool launch_rows(int mode, int zb, int ze, int y0, int ystride, int rows, const ForceField &F, int zstride = 1, int hole_b = 0, int hole_e = 0,

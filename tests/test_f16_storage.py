@@ -102,3 +102,32 @@ def test_random_configurations_with_16_bit_storage(g, emu_f16):
         if worst is not None and any(worst[k] > limits[k] for k in worst):
             bad.append((seed, worst, kw))
     assert not bad, bad[:3]
+
+
+def _vec_forms_equal_scalar(g, backend, shape_kw):
+    """The two- / four-cell kernels of the fp32 product exist in the 16-bit build as well (same sources, VecF over the storage
+    type: 32- / 64-bit accesses); per cell they decode, collide and encode exactly as the scalar kernels do."""
+    A = g._abi
+    for name in ("mrt_force", "mrt_inlet_outlet_ywalls", "bgk_periodic"):
+        kw = dict(util.parity_cases(g)[name], **shape_kw)
+        ref = g.Sim(backend=backend, flags=A.FLAG_EVEN_SCALAR | A.FLAG_ODD_SCALAR, **kw)
+        rho, u = util.smooth_fields(ref.shape)
+        ref.set_fields(rho, u)
+        ref.step(9)
+        f = ref.get_populations()
+        ref.close()
+        for flags in (A.FLAG_EVEN_VEC2 | A.FLAG_ODD_VEC2, A.FLAG_EVEN_VEC4 | A.FLAG_ODD_SCALAR, A.FLAG_EVEN_SCALAR | A.FLAG_ODD_VEC2):
+            s = g.Sim(backend=backend, flags=flags, **kw)
+            s.set_fields(rho, u)
+            s.step(9)
+            assert np.array_equal(s.get_populations(), f), (name, flags)
+            s.close()
+
+
+def test_f16_storage_vector_kernels_equal_scalar_emulated(g, emu_f16):
+    _vec_forms_equal_scalar(g, emu_f16, dict(nx=16, ny=6, nz=8))
+
+
+@pytest.mark.gpu
+def test_f16_storage_vector_kernels_equal_scalar_gpu(g, cuda_f16):
+    _vec_forms_equal_scalar(g, cuda_f16, dict(nx=256, ny=10, nz=12))
