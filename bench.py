@@ -578,7 +578,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "cpu_leg"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS))
     ap.add_argument("--no-subrecords", action="store_true", help="only the main workload (no IB-overhead / env / sphere / overlap-off sub-records)")
     ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: halo after the full-slab kernel")
@@ -598,6 +598,8 @@ def main():
     ap.add_argument("--sort-markers", action="store_true", help="A/B: box_512_ib markers ordered by cell within each sphere (neighbours on the surface are neighbours in the list)")
     ap.add_argument("--no-split", action="store_true", help="collide all planes after the IB kernels (no far-plane branch beside them)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer loop (default: --steps)")
+    ap.add_argument("--sub-budget-s", type=float, default=480.0,
+                    help="wall-clock budget of everything after the main measurement (sub-records, CPU baseline); when it runs out the line is printed with what is there")
     ap.add_argument("--ref-budget-s", type=float, default=150.0, help="--impl reference: wall-clock budget that sizes the oracle's sample")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -614,7 +616,7 @@ def main():
 
     # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU legs (reference arm, cpu_baseline) are meant to use every
     # host core ("cores" in the JSON line is what they really get), so the variable is set before the oracle is loaded
-    if args.impl == "reference" or world == 1:
+    if args.impl in ("reference", "cpu_leg") or world == 1:
         os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     else:
         os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1))
@@ -624,6 +626,13 @@ def main():
 
     if args.impl == "reference":
         run_reference(args, g, rank, world)
+        return
+    if args.impl == "cpu_leg":
+        # the `cpu_baseline` object of the b200 arm's line (bounded sample, ~10-30 s), run as a child of that arm
+        _, _, _, ms16 = cpu_oracle_mlups(g, args.workload, steps=2, warmup=1, nz_sample=16)
+        nzs = oracle_sample_nz(args.workload, ms16 / 16, 40, 20.0)
+        v, cores, sample, _ = cpu_oracle_mlups(g, args.workload, seconds=12.0, warmup=20, nz_sample=nzs)
+        print(json.dumps({"value": v, "unit": "MLUPS", "cores": cores, "kind": "port", "sample": sample + ", 20 warm-up steps, own process"}), flush=True)
         return
 
     dist = None
@@ -653,6 +662,48 @@ def main():
 
     sub = {}
     want_sub = not args.no_subrecords and wl == DEFAULT_WORKLOAD and args.storage == "f32"
+    # The main measurement is done: from here on a watchdog guarantees the line.  Sub-records and the CPU baseline are
+    # extras; if they overrun --sub-budget-s (a rank stuck behind a dead peer, a box much slower than expected), rank 0
+    # prints the line with what it has and every rank leaves, instead of the driver's own limit ending the run with nothing.
+    cfg = base_config(wl, world)
+    line = {
+        "metric": METRIC,
+        "value": main_res["value"], "unit": "MLUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": main_res["ms_per_step"], "higher_is_better": True, "scaling": "strong" if w.get("strong") else "weak", "vs_baseline": None,
+        "dtype": "f32" if args.storage == "f32" else "f32 arithmetic on f16-stored populations (opt-in build)", "data": "synthetic",
+        "config": cfg,
+        "run": {"population_storage": args.storage, "markers_per_gpu": main_res["markers_per_gpu"],
+                "decomposition": "z-slabs, halos by peer stores over NVLink (CUDA IPC), no NCCL on the data path" if world > 1 else "single GPU",
+                "halo_overlap": not args.no_overlap, "launch_mode": main_res["launch_mode"],
+                "even_step_cells_per_thread": args.even_vec or "library default (2 where nx % 256 == 0, else 1)",
+                "odd_step_cells_per_thread": args.odd_vec or "library default (2 in bulk rows where nx % 256 == 0 and x is periodic, else 1)"},
+        "roofline": main_res.get("roofline"), "cpu_baseline": None, "e2e": main_res.get("e2e"), "gpu_launches": main_res["gpu_launches"], "clocks": clk,
+        "pct_of_hbm_roofline": main_res["pct_of_hbm_roofline"],
+        "sub_records": None,
+    }
+    if SHRINK != 1:
+        line["dry_run_shrink"] = SHRINK
+    emit_lock = threading.Lock()
+    emitted = []
+
+    def emit(note=None):
+        with emit_lock:
+            if emitted:
+                return
+            emitted.append(True)
+            if rank == 0:
+                line["sub_records"] = dict(sub) or None
+                if note:
+                    line["watchdog"] = note
+                print(json.dumps(line), flush=True)
+
+    def overrun():
+        emit(f"sub-records / CPU baseline exceeded --sub-budget-s {args.sub_budget_s:.0f} s: the line carries what was finished by then")
+        os._exit(0)
+
+    watchdog = threading.Timer(args.sub_budget_s + (0.0 if rank == 0 else 5.0), overrun)
+    watchdog.daemon = True
+    watchdog.start()
     if want_sub and world > 1 and not args.no_overlap:
         # configs[4] "halo overlap on vs off": the same slabs, halo push after the full-slab kernel
         sim.set_flags(flags | A.FLAG_NO_OVERLAP)
@@ -739,37 +790,23 @@ def main():
                 pass
 
     if rank != 0:
+        watchdog.cancel()
         leave()
         return
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
+        # in a fresh process, like the reference arm: timed inside this one (after the GPU legs: pinned buffers, a fragmented
+        # heap, helper threads) the same oracle ran 2.6x slower than in the arm on the same box (gpu pass b1: 35 against 91 MLUPS)
         try:
-            _, _, _, ms16 = cpu_oracle_mlups(g, wl, steps=2, warmup=1, nz_sample=16)
-            nzs = oracle_sample_nz(wl, ms16 / 16, 40, 20.0)
-            v, cores, sample, _ = cpu_oracle_mlups(g, wl, seconds=12.0, warmup=20, nz_sample=nzs)
-            cpu = {"value": v, "unit": "MLUPS", "cores": cores, "kind": "port", "sample": sample + ", 20 warm-up steps"}
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "cpu_leg", "--workload", wl], capture_output=True, text=True,
+                               timeout=max(60.0, args.sub_budget_s))
+            cpu = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
         except Exception as e:   # noqa: BLE001 — the baseline is informative; never let it kill the GPU number
             cpu = {"value": None, "unit": "MLUPS", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
-    cfg = base_config(wl, world)
-    line = {
-        "metric": METRIC,
-        "value": main_res["value"], "unit": "MLUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": main_res["ms_per_step"], "higher_is_better": True, "scaling": "strong" if w.get("strong") else "weak", "vs_baseline": None,
-        "dtype": "f32" if args.storage == "f32" else "f32 arithmetic on f16-stored populations (opt-in build)", "data": "synthetic",
-        "config": cfg,
-        "run": {"population_storage": args.storage, "markers_per_gpu": main_res["markers_per_gpu"],
-                "decomposition": "z-slabs, halos by peer stores over NVLink (CUDA IPC), no NCCL on the data path" if world > 1 else "single GPU",
-                "halo_overlap": not args.no_overlap, "launch_mode": main_res["launch_mode"],
-                "even_step_cells_per_thread": args.even_vec or "library default (2 where nx % 256 == 0, else 1)",
-                "odd_step_cells_per_thread": args.odd_vec or "library default (2 in bulk rows where nx % 256 == 0 and x is periodic, else 1)"},
-        "roofline": main_res.get("roofline"), "cpu_baseline": cpu, "e2e": main_res.get("e2e"), "gpu_launches": main_res["gpu_launches"], "clocks": clk,
-        "pct_of_hbm_roofline": main_res["pct_of_hbm_roofline"],
-        "sub_records": sub or None,
-    }
-    if SHRINK != 1:
-        line["dry_run_shrink"] = SHRINK
-    print(json.dumps(line), flush=True)
+    line["cpu_baseline"] = cpu
+    watchdog.cancel()
+    emit()
     leave()
 
 

@@ -82,6 +82,7 @@ struct IbParams {
     int *band_count;             // this step's band size (device counter)
     int *band_count_next;        // the other counter: previous step's size until IbClearBand ran, then zeroed for the next
     int band_cap;
+    int band_ctas;               // grid of the band kernels (IbBandMoments, IbClearBand): they walk the band grid-stride
     uint8_t *rowflag;            // [(nz+2)*ny]
     // static bodies: (stencil weight, band slot) of every stencil node, cached while the marker set is not re-sent
     float *node_w;               // [n][64] or nullptr
@@ -208,34 +209,38 @@ using IbIndexMarkLaunch = IbIndexMarkT<true>;
 using IbIndexMarkLaunch = IbIndexMarkT<false>;
 #endif
 
-// (a4) unforced velocity of the band cells from the populations arriving at time t (parity aware)
+// (a4) unforced velocity of the band cells from the populations arriving at time t (parity aware).
+// The band's size is a device counter the host only has a bound for (64 cells per marker; ~16 are distinct on a closed
+// surface), so the kernel walks the band grid-stride with a grid sized for the SMs: a grid sized for the bound spent a
+// quarter of its time dispatching CTAs that found nothing to do (49 536 CTAs for 1.6 M band cells at 1e5 markers).
 template <int PARITY>
 struct IbBandMoments {
     static constexpr int kThreads = 128;
     static constexpr int kMinBlocks = 4;
+    static constexpr int kCtasPerSm = 12;                     // 40 registers: 12 x 128 threads resident per SM
     FG_HD static void run(const IbParams &p, int bx, int, int, int tx) {
-        const int pos = bx * kThreads + tx;
-        if (pos == 0) *p.band_count_next = 0;                 // the other counter is free again (IbClearBand has run)
+        if (bx == 0 && tx == 0) *p.band_count_next = 0;       // the other counter is free again (IbClearBand has run)
         const int cnt = *p.band_count < p.band_cap ? *p.band_count : p.band_cap;
-        if (pos >= cnt) return;
         const Lattice &L = p.L;
-        const long long idx = p.band_cell[pos];
-        const int x = int(idx % L.nx), y = int((idx / L.nx) % L.ny), zz = int(idx / L.plane);
-        const Nbr nb = make_nbr(L, x, y, zz);
-        float h[Q];
-        if (L.solid && L.solid[idx]) {
-            FG_UNROLL
-            for (int i = 0; i < Q; ++i) h[i] = pop_ld(L.f + i * L.slot + idx);   // obstacles keep their initial state (as in the oracle)
-        } else {
-            load_arriving<PARITY, true>(h, L, p.C, nb, idx);
+        for (long long pos = (long long)bx * kThreads + tx; pos < cnt; pos += (long long)p.band_ctas * kThreads) {
+            const long long idx = p.band_cell[pos];
+            const int x = int(idx % L.nx), y = int((idx / L.nx) % L.ny), zz = int(idx / L.plane);
+            const Nbr nb = make_nbr(L, x, y, zz);
+            float h[Q];
+            if (L.solid && L.solid[idx]) {
+                FG_UNROLL
+                for (int i = 0; i < Q; ++i) h[i] = pop_ld(L.f + i * L.slot + idx);   // obstacles keep their initial state (as in the oracle)
+            } else {
+                load_arriving<PARITY, true>(h, L, p.C, nb, idx);
+            }
+            float dr, jx, jy, jz;
+            moments(h, dr, jx, jy, jz);
+            const float inv = 1.0f / (1.0f + dr);
+            p.band_u[pos] = jx * inv;
+            p.band_u[p.band_cap + pos] = jy * inv;
+            p.band_u[2 * p.band_cap + pos] = jz * inv;
+            p.bandF[pos] = 0.0f; p.bandF[p.band_cap + pos] = 0.0f; p.bandF[2 * p.band_cap + pos] = 0.0f;
         }
-        float dr, jx, jy, jz;
-        moments(h, dr, jx, jy, jz);
-        const float inv = 1.0f / (1.0f + dr);
-        p.band_u[pos] = jx * inv;
-        p.band_u[p.band_cap + pos] = jy * inv;
-        p.band_u[2 * p.band_cap + pos] = jz * inv;
-        p.bandF[pos] = 0.0f; p.bandF[p.band_cap + pos] = 0.0f; p.bandF[2 * p.band_cap + pos] = 0.0f;
     }
 };
 
@@ -522,17 +527,17 @@ struct ProbeMoments {
     }
 };
 
-// forget the band of the previous step
+// forget the band of the previous step (grid-stride like IbBandMoments)
 struct IbClearBand {
     static constexpr int kThreads = 128;
     static constexpr int kMinBlocks = 4;
     FG_HD static void run(const IbParams &p, int bx, int, int, int tx) {
-        const int pos = bx * kThreads + tx;
         const int cnt = *p.band_count_next < p.band_cap ? *p.band_count_next : p.band_cap;   // the previous step's counter
-        if (pos >= cnt) return;
-        const long long idx = p.band_cell[pos];
-        p.cellslot[idx] = 0;
-        p.rowflag[idx / p.L.nx] = 0;
+        for (long long pos = (long long)bx * kThreads + tx; pos < cnt; pos += (long long)p.band_ctas * kThreads) {
+            const long long idx = p.band_cell[pos];
+            p.cellslot[idx] = 0;
+            p.rowflag[idx / p.L.nx] = 0;
+        }
     }
 };
 
@@ -919,26 +924,29 @@ public:
             }
             if (node_w_) { cache_mode_ = cache_valid_ ? 2 : 1; cache_valid_ = true; }
         }
-        const IbParams p = params(L, C);
+        IbParams p = params(L, C);
         bool ok = flush_upload(dev);
         const int nb = (n_ + kMarkersPerCta - 1) / kMarkersPerCta;
+        // band kernels: a grid for the SMs (or for the bound of the band's size when that is smaller), walked grid-stride
+        const auto band_grid = [&](long long bound) { return int(std::max<long long>(1, std::min<long long>((bound + 127) / 128, (long long)dev.sm_count() * IbBandMoments<0>::kCtasPerSm))); };
         if (use_fused) {
             // upper bound of any phase's work, for the launch geometry (the kernel loops grid-stride)
             const long long most = std::max<long long>((long long)nb * 128, std::min<long long>(band_cap_, (long long)kNodes * std::max(n_, n_prev_)));
+            p.band_ctas = (band_cap_ + 127) / 128;                // one band cell per work item: the band kernels' own stride is never taken
             ok = ok && (parity == 0 ? dev.template launch_phased<IbFused<0>>(most, p) : dev.template launch_phased<IbFused<1>>(most, p));
         } else {
             if (rebuild) {
                 if (band_live_) {
-                    const int bound = int(std::min<long long>(band_cap_, (long long)kNodes * std::max(n_prev_, 1)));
-                    ok = ok && dev.template launch<IbClearBand>(Dim3x((bound + 127) / 128), p);
+                    p.band_ctas = band_grid(std::min<long long>(band_cap_, (long long)kNodes * std::max(n_prev_, 1)));
+                    ok = ok && dev.template launch<IbClearBand>(Dim3x(p.band_ctas), p);
                 }
                 ok = ok && dev.template launch<IbIndexMarkLaunch>(Dim3x((n_ + IbIndexMarkLaunch::kMarkers - 1) / IbIndexMarkLaunch::kMarkers), p);
             } else {
                 ok = ok && dev.zero(dUs_, sizeof(float) * 3 * size_t(n_));   // IbIndexMark would have cleared the U* accumulators
             }
-            const int bound2 = int(std::min<long long>(band_cap_, (long long)kNodes * n_));
-            ok = ok && (parity == 0 ? dev.template launch<IbBandMoments<0>>(Dim3x((bound2 + 127) / 128), p)
-                                    : dev.template launch<IbBandMoments<1>>(Dim3x((bound2 + 127) / 128), p));
+            p.band_ctas = band_grid(std::min<long long>(band_cap_, (long long)kNodes * n_));
+            ok = ok && (parity == 0 ? dev.template launch<IbBandMoments<0>>(Dim3x(p.band_ctas), p)
+                                    : dev.template launch<IbBandMoments<1>>(Dim3x(p.band_ctas), p));
             if (!xchg_) {
                 const Dim3 gs = Dim3x(std::max(dev.interp_spread_blocks(n_), (6 * nl_ + 127) / 128));
                 ok = ok && (tile_spread_ ? dev.template launch_block_phased<IbInterpSpreadTile>(gs, p) : dev.template launch_block_phased<IbInterpSpread>(gs, p));

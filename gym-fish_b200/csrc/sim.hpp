@@ -728,11 +728,10 @@ private:
         if (L_.nx % (2 * kCollideThreads) == 0) return kVecDefault;
         return 0;
     }
-    // what the library picks by itself where rows are wide enough: two cells per thread in the fp32 product; the opt-in
-    // 16-bit-storage build has the same kernels behind the flags (its own A/B: profiles/r2_summary.md)
-#if defined(FG_POP16) && !defined(FG_POP16_VEC_DEFAULT)
-    static constexpr int kVecDefault = 0;
-#elif defined(FG_POP16)
+    // what the library picks by itself where rows are wide enough: two cells per thread.  The opt-in 16-bit-storage build
+    // gains most from it (it is issue-bound: 512^3, 100 steps, gpu pass b1: 50 919 MLUPS with one cell per thread in both
+    // steps, 55 872 / 53 565 with two cells in the even / odd step only, 59 473 with both = +17 %)
+#if defined(FG_POP16_VEC_DEFAULT)
     static constexpr int kVecDefault = FG_POP16_VEC_DEFAULT;
 #else
     static constexpr int kVecDefault = 2;
