@@ -645,12 +645,16 @@ struct StreamCollideEvenVec {
     }
 };
 
-// ---------------------------------------------------------------- odd step, 2 cells per thread (bulk rows without x walls)
+// ---------------------------------------------------------------- odd step, 2 cells per thread (bulk rows)
 // The odd step reads f_i from slot opp(i) of the neighbour at x - c_i and writes f*_i to slot i of the neighbour at x + c_i.
 // For the 9 slots with c_x = 0 the two cells (x0, x0 + 1) of a thread are an aligned pair in the neighbour row: one 64-bit
 // access.  The 10 slots with c_x != 0 are one float off the pair boundary and stay 32-bit accesses.  Same arithmetic per
 // cell and the same 19 + 19 locations per cell as StreamCollide<1>: bit-identical results.  A/B: profiles/r2_summary.md.
-template <bool MRT>
+// XWALL (rows between x walls: the tank, the school): the first cell of a row has no neighbour at x - 1 and the last none at
+// x + 1; the links across those faces bounce back into the cell's own opposite slot (+ the moving-wall term), on the read
+// and on the write side, exactly as CHECK_XEDGE does for one cell per thread.  Only the two warps at the ends of a row run
+// that predicated code (warp-uniform branch, as CHECK_XWARP).
+template <bool MRT, bool XWALL = false>
 struct StreamCollideOddVec2 {
     static constexpr int kThreads = kCollideThreads;
 #if defined(FG_ODDVEC_OCC)
@@ -669,8 +673,9 @@ struct StreamCollideOddVec2 {
     }
     FG_HD static float lds(const char *q) { return pop_ld(reinterpret_cast<const pop_t *>(q)); }
     FG_HD static void sts(char *q, float v) { pop_st(reinterpret_cast<pop_t *>(q), v); }
-    template <int I>
-    FG_HD static void load_pair(float (&h0)[Q], float (&h1)[Q], const StepParams &p, char *pc, int dym, int dyp, int oxm, int oxp) {
+    // b0: cell x0 is the first of its row and x - 1 is behind a wall; b1: cell x0 + 1 is the last and x + 1 is behind a wall
+    template <int I, bool XW>
+    FG_HD static void load_pair(float (&h0)[Q], float (&h1)[Q], const StepParams &p, char *pc, int dym, int dyp, int oxm, int oxp, bool b0, bool b1) {
         using D = Dir<I>;
         constexpr int J = D::opp;
         constexpr int B = kPopBytes;
@@ -680,16 +685,28 @@ struct StreamCollideOddVec2 {
             const VecF<2> vm = *reinterpret_cast<const VecF<2> *>(am), vp = *reinterpret_cast<const VecF<2> *>(ap);
             h0[I] = pop_dec(vm.a[0]); h1[I] = pop_dec(vm.a[1]); h0[J] = pop_dec(vp.a[0]); h1[J] = pop_dec(vp.a[1]);
         } else if (D::cx > 0) {
-            h0[I] = lds(am + oxm); h1[I] = lds(am);
-            h0[J] = lds(ap + B); h1[J] = lds(ap + oxp);
+            if (XW) {
+                h0[I] = lds(b0 ? pc + p.kz[I][1] : am + oxm) + (b0 ? p.C.wallterm[F_XLO][I] : 0.0f);
+                h1[J] = lds(b1 ? pc + B + p.kz[J][1] : ap + oxp) + (b1 ? p.C.wallterm[F_XHI][J] : 0.0f);
+            } else {
+                h0[I] = lds(am + oxm); h1[J] = lds(ap + oxp);
+            }
+            h1[I] = lds(am);
+            h0[J] = lds(ap + B);
         } else {
-            h0[I] = lds(am + B); h1[I] = lds(am + oxp);
-            h0[J] = lds(ap + oxm); h1[J] = lds(ap);
+            if (XW) {
+                h1[I] = lds(b1 ? pc + B + p.kz[I][1] : am + oxp) + (b1 ? p.C.wallterm[F_XHI][I] : 0.0f);
+                h0[J] = lds(b0 ? pc + p.kz[J][1] : ap + oxm) + (b0 ? p.C.wallterm[F_XLO][J] : 0.0f);
+            } else {
+                h1[I] = lds(am + oxp); h0[J] = lds(ap + oxm);
+            }
+            h0[I] = lds(am + B);
+            h1[J] = lds(ap);
         }
     }
     // f*_I goes where f_J came from and f*_J where f_I came from
-    template <int I>
-    FG_HD static void store_pair(const float (&h0)[Q], const float (&h1)[Q], const StepParams &p, char *pc, int dym, int dyp, int oxm, int oxp) {
+    template <int I, bool XW>
+    FG_HD static void store_pair(const float (&h0)[Q], const float (&h1)[Q], const StepParams &p, char *pc, int dym, int dyp, int oxm, int oxp, bool b0, bool b1) {
         using D = Dir<I>;
         constexpr int J = D::opp;
         constexpr int B = kPopBytes;
@@ -700,31 +717,40 @@ struct StreamCollideOddVec2 {
             vp.a[0] = pop_enc(h0[I]); vp.a[1] = pop_enc(h1[I]); vm.a[0] = pop_enc(h0[J]); vm.a[1] = pop_enc(h1[J]);
             *reinterpret_cast<VecF<2> *>(ap) = vp; *reinterpret_cast<VecF<2> *>(am) = vm;
         } else if (D::cx > 0) {
-            sts(ap + B, h0[I]); sts(ap + oxp, h1[I]);
-            sts(am + oxm, h0[J]); sts(am, h1[J]);
+            sts(ap + B, h0[I]);
+            sts(am, h1[J]);
+            if (XW) {
+                sts(b1 ? pc + B + p.kz[J][1] : ap + oxp, h1[I] + (b1 ? p.C.wallterm[F_XHI][J] : 0.0f));
+                sts(b0 ? pc + p.kz[I][1] : am + oxm, h0[J] + (b0 ? p.C.wallterm[F_XLO][I] : 0.0f));
+            } else {
+                sts(ap + oxp, h1[I]); sts(am + oxm, h0[J]);
+            }
         } else {
-            sts(ap + oxm, h0[I]); sts(ap, h1[I]);
-            sts(am + B, h0[J]); sts(am + oxp, h1[J]);
+            sts(ap, h1[I]);
+            sts(am + B, h0[J]);
+            if (XW) {
+                sts(b0 ? pc + p.kz[J][1] : ap + oxm, h0[I] + (b0 ? p.C.wallterm[F_XLO][J] : 0.0f));
+                sts(b1 ? pc + B + p.kz[I][1] : am + oxp, h1[J] + (b1 ? p.C.wallterm[F_XHI][I] : 0.0f));
+            } else {
+                sts(ap + oxm, h0[I]); sts(am + oxp, h1[J]);
+            }
         }
     }
 
-    // grid: (nx / 2 / threads, rows, planes); requires nx % 2 == 0, periodic x, no blocked link in the rows of the launch
-    FG_HD static void run(const StepParams &p, int bx, int by, int bz, int tx) {
+    template <bool XW>
+    FG_HD static void body(const StepParams &p, int x0, int y, int zz) {
         const Lattice &L = p.L;
-        const int x0 = (bx * kThreads + tx) * 2, y = p.y0 + by * p.ystride;
-        int zz = p.zz_begin + (p.zz_flip >= 0 ? p.zz_flip - bz : bz) * p.zz_stride;
-        if (zz >= p.zz_skip_begin) zz += p.zz_skip_len;
-        if (x0 >= L.nx) return;
         const long long idx = ((long long)zz * L.ny + y) * L.nx + x0;
         char *pc = reinterpret_cast<char *>(L.f + idx);
         const int dym = (y == 0 ? (L.ny - 1) * L.nx : -L.nx) * kPopBytes, dyp = (y == L.ny - 1 ? -(L.ny - 1) * L.nx : L.nx) * kPopBytes;
         const int oxm = (x0 == 0 ? L.nx - 1 : -1) * kPopBytes, oxp = (x0 + 2 == L.nx ? -(L.nx - 2) : 2) * kPopBytes;   // cells x0 - 1 and x0 + 2 (periodic)
+        const bool b0 = XW && x0 == 0, b1 = XW && x0 + 2 == L.nx;
         float h0[Q], h1[Q];
         {
             const VecF<2> v = *reinterpret_cast<const VecF<2> *>(pc + p.kz[0][1]);
             h0[0] = pop_dec(v.a[0]); h1[0] = pop_dec(v.a[1]);
         }
-#define FG_X(I) load_pair<I>(h0, h1, p, pc, dym, dyp, oxm, oxp);
+#define FG_X(I) load_pair<I, XW>(h0, h1, p, pc, dym, dyp, oxm, oxp, b0, b1);
         FG_FOR_PAIRS(FG_X)
 #undef FG_X
         float Fx, Fy, Fz;
@@ -737,9 +763,26 @@ struct StreamCollideOddVec2 {
             v.a[0] = pop_enc(h0[0]); v.a[1] = pop_enc(h1[0]);
             *reinterpret_cast<VecF<2> *>(pc + p.kz[0][1]) = v;
         }
-#define FG_X(I) store_pair<I>(h0, h1, p, pc, dym, dyp, oxm, oxp);
+#define FG_X(I) store_pair<I, XW>(h0, h1, p, pc, dym, dyp, oxm, oxp, b0, b1);
         FG_FOR_PAIRS(FG_X)
 #undef FG_X
+    }
+
+    // grid: (nx / 2 / threads, rows, planes); requires nx % 2 == 0, x periodic or (XWALL) between walls, no other blocked
+    // link in the rows of the launch
+    FG_HD static void run(const StepParams &p, int bx, int by, int bz, int tx) {
+        const Lattice &L = p.L;
+        const int x0 = (bx * kThreads + tx) * 2, y = p.y0 + by * p.ystride;
+        int zz = p.zz_begin + (p.zz_flip >= 0 ? p.zz_flip - bz : bz) * p.zz_stride;
+        if (zz >= p.zz_skip_begin) zz += p.zz_skip_len;
+        if (x0 >= L.nx) return;
+        if (XWALL) {
+            const int w0 = x0 & ~63;                                   // first cell of this warp (32 lanes x 2 cells)
+            if (w0 == 0 || w0 + 64 >= L.nx) body<true>(p, x0, y, zz);
+            else body<false>(p, x0, y, zz);
+        } else {
+            body<false>(p, x0, y, zz);
+        }
     }
 };
 

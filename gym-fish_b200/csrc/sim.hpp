@@ -744,7 +744,9 @@ private:
         if ((cfg.flags & FG_FLAG_ODD_SCALAR) || L_.solid || L_.nx % 2 != 0 || L_.nx < 4) return false;
         return (cfg.flags & FG_FLAG_ODD_VEC2) || (kVecDefault != 0 && L_.nx % (2 * kCollideThreads) == 0);
     }
-    bool launch_odd_vec2(const StepParams &p, Dim3 g) {
+    bool launch_odd_vec2(const StepParams &p, Dim3 g, bool xwall = false) {
+        if (xwall)
+            return cfg.collision == FG_MRT ? dev.template launch<StreamCollideOddVec2<true, true>>(g, p) : dev.template launch<StreamCollideOddVec2<false, true>>(g, p);
         return cfg.collision == FG_MRT ? dev.template launch<StreamCollideOddVec2<true>>(g, p) : dev.template launch<StreamCollideOddVec2<false>>(g, p);
     }
     bool launch_even_vec(const StepParams &p, Dim3 g, int vec) {
@@ -779,7 +781,11 @@ private:
             switch (mode) {
                 case CHECK_ALL: ok = launch_collide_pm<1, CHECK_ALL>(p, g); break;
                 case CHECK_XEDGE: ok = launch_collide_pm<1, CHECK_XEDGE>(p, g); break;
-                case CHECK_XWARP: ok = launch_collide_pm<1, CHECK_XWARP>(p, g); break;
+                case CHECK_XWARP:
+                    // rows between x walls (the tank, the school): the two-cell kernel with the wall selects in its row-end warps
+                    if (odd_vec2()) ok = launch_odd_vec2(p, Dim3{(L_.nx / 2 + kCollideThreads - 1) / kCollideThreads, rows, planes}, true);
+                    else ok = launch_collide_pm<1, CHECK_XWARP>(p, g);
+                    break;
                 default:
                     if (odd_vec2()) ok = launch_odd_vec2(p, Dim3{(L_.nx / 2 + kCollideThreads - 1) / kCollideThreads, rows, planes});
                     else ok = launch_collide_pm<1, CHECK_NONE>(p, g);

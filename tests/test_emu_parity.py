@@ -259,16 +259,17 @@ def test_velocity_probes_match_oracle_at_both_parities(g, emu):
     assert abs(one[0] - 1.0) < 0.02
 
 
-@pytest.mark.parametrize("name", ["bgk_periodic", "mrt_force", "mrt_xy_walls", "mrt_all_walls_lid", "mrt_inlet_outlet_ywalls"])
+@pytest.mark.parametrize("name", ["bgk_periodic", "mrt_force", "mrt_xy_walls", "mrt_all_walls_lid", "mrt_inlet_outlet_ywalls", "mrt_xwalls_moving",
+                                  "mrt_outlet_inlet_xwalls"])
 @pytest.mark.parametrize("vec", [4, 2, "odd2", "even2+odd2"])
 def test_vectorised_even_step_is_bit_identical(g, emu, name, vec):
     """FG_FLAG_EVEN_VEC4 / _VEC2 (lbm_core.cuh StreamCollideEvenVec): V cells per thread with 16- / 8-byte accesses in the
     even step — the same arithmetic per cell, so populations must equal the scalar kernel's bit for bit."""
     kw = dict(util.parity_cases(g)[name])
     A = g._abi
-    # odd2: FG_FLAG_ODD_VEC2 (StreamCollideOddVec2), two cells per thread in the bulk odd step of rows without x walls
+    # odd2: FG_FLAG_ODD_VEC2 (StreamCollideOddVec2), two cells per thread in the bulk odd step; between x walls its XWALL form
     flag = {4: A.FLAG_EVEN_VEC4, 2: A.FLAG_EVEN_VEC2, "odd2": A.FLAG_ODD_VEC2, "even2+odd2": A.FLAG_EVEN_VEC2 | A.FLAG_ODD_VEC2}[vec]
-    a, b = g.Sim(backend=emu, **kw), g.Sim(backend=emu, flags=flag, **kw)
+    a, b = g.Sim(backend=emu, flags=A.FLAG_EVEN_SCALAR | A.FLAG_ODD_SCALAR, **kw), g.Sim(backend=emu, flags=flag, **kw)
     rho, u = util.smooth_fields(a.shape)
     for s in (a, b):
         s.set_fields(rho, u)
@@ -323,7 +324,8 @@ def test_default_two_cell_kernels_equal_the_scalar_ones_on_256_wide_rows(g, emu)
     """nx % 256 == 0: the library picks the two-cell even and odd kernels by itself; bit-identical to the scalar kernels
     (FG_FLAG_EVEN_SCALAR | FG_FLAG_ODD_SCALAR) and within tolerance of the oracle."""
     A = g._abi
-    for name in ("mrt_force", "mrt_inlet_outlet_ywalls"):
+    # the wall cases run StreamCollideOddVec2<MRT, XWALL>: wall selects in the two row-end warps, the plain pair code between
+    for name in ("mrt_force", "mrt_inlet_outlet_ywalls", "mrt_xy_walls", "mrt_xwalls_moving", "mrt_all_walls_lid"):
         kw = dict(util.parity_cases(g)[name], nx=256, ny=6, nz=8)
         a, b, o = g.Sim(backend=emu, **kw), g.Sim(backend=emu, flags=A.FLAG_EVEN_SCALAR | A.FLAG_ODD_SCALAR, **kw), g.Sim(backend="oracle", **kw)
         rho, u = util.smooth_fields(a.shape)

@@ -416,16 +416,16 @@ def test_fluid_divergence_guard_on_gpu(g, cuda):
     t.close()
 
 
-@pytest.mark.parametrize("name", ["mrt_force", "mrt_all_walls_lid", "mrt_inlet_outlet_ywalls"])
+@pytest.mark.parametrize("name", ["mrt_force", "mrt_all_walls_lid", "mrt_inlet_outlet_ywalls", "mrt_xwalls_moving"])
 @pytest.mark.parametrize("vec", [4, 2, "odd2", "even2+odd2"])
 def test_vectorised_even_step_is_bit_identical_on_gpu(g, cuda, name, vec):
     """FG_FLAG_EVEN_VEC4 / _VEC2: 128- / 64-bit accesses, 4 / 2 cells per thread in the even step (the A/B of
     BASELINE.json:5 (a)); same arithmetic per cell => same bits as the scalar kernel, with an immersed sphere as well."""
     kw = dict(util.parity_cases(g)[name], nx=40, ny=12, nz=10, max_markers=300, max_links=1)
     A = g._abi
-    # odd2: FG_FLAG_ODD_VEC2, two cells per thread in the bulk odd step as well (rows without x walls)
+    # odd2: FG_FLAG_ODD_VEC2, two cells per thread in the bulk odd step as well (between x walls: its XWALL form)
     flag = {4: A.FLAG_EVEN_VEC4, 2: A.FLAG_EVEN_VEC2, "odd2": A.FLAG_ODD_VEC2, "even2+odd2": A.FLAG_EVEN_VEC2 | A.FLAG_ODD_VEC2}[vec]
-    a, b = g.Sim(backend=cuda, **kw), g.Sim(backend=cuda, flags=flag, **kw)
+    a, b = g.Sim(backend=cuda, flags=A.FLAG_EVEN_SCALAR | A.FLAG_ODD_SCALAR, **kw), g.Sim(backend=cuda, flags=flag, **kw)
     rho, u = util.smooth_fields(a.shape)
     X = util.sphere_markers((20.2, 6.1, 5.3), 2.5, 80)
     for s in (a, b):
@@ -444,7 +444,7 @@ def test_default_two_cell_kernels_equal_the_scalar_ones_on_256_wide_rows(g, cuda
     with FG_FLAG_EVEN_SCALAR | FG_FLAG_ODD_SCALAR must leave the same bits — periodic box (every row bulk) and a channel with
     y walls + inlet / outlet (bulk rows between checked wall rows)."""
     A = g._abi
-    for name in ("mrt_force", "mrt_inlet_outlet_ywalls", "bgk_periodic"):
+    for name in ("mrt_force", "mrt_inlet_outlet_ywalls", "bgk_periodic", "mrt_xy_walls", "mrt_xwalls_moving", "mrt_all_walls_lid"):
         kw = dict(util.parity_cases(g)[name], nx=256, ny=10, nz=12)
         a, b = g.Sim(backend=cuda, **kw), g.Sim(backend=cuda, flags=A.FLAG_EVEN_SCALAR | A.FLAG_ODD_SCALAR, **kw)
         rho, u = util.smooth_fields(a.shape)

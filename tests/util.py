@@ -81,6 +81,8 @@ def parity_cases(g):
         "bgk_ywall_moving": dict(N, tau=0.8, bc=[P, P, Wl, Wl, P, P], wall_u={A.YHI: [0.05, 0, 0.02]}),
         "mrt_xy_walls": dict(N, tau=0.8, collision=g.MRT, bc=[Wl, Wl, Wl, Wl, P, P]),
         "mrt_all_walls_lid": dict(N, tau=0.8, collision=g.MRT, bc=[Wl] * 6, wall_u={A.ZHI: [0.03, 0.01, 0]}),
+        "mrt_xwalls_moving": dict(N, tau=0.8, collision=g.MRT, bc=[Wl, Wl, P, P, P, P], wall_u={A.XLO: [0, 0.03, -0.02], A.XHI: [0, -0.01, 0.04]},
+                                  body_force=[0, 1e-4, 0]),
         "bgk_inlet_outlet": dict(N, tau=0.8, bc=[P, P, P, P, IN, OUT], inlet_u=[0, 0, 0.04]),
         "mrt_inlet_outlet_ywalls": dict(N, tau=0.8, collision=g.MRT, bc=[P, P, Wl, Wl, IN, OUT], inlet_u=[0.01, 0, 0.04]),
         "mrt_outlet_inlet_xwalls": dict(N, tau=0.8, collision=g.MRT, bc=[Wl, Wl, P, P, OUT, IN], inlet_u=[0, 0.01, -0.04]),
