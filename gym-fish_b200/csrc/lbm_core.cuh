@@ -151,6 +151,9 @@ struct StepParams {
     int zz_skip_begin, zz_skip_len;   // ... and from zz_skip_begin on, zz_skip_len planes further up (a launch with a hole)
     int zz_flip;              // >= 0: blockIdx.z is replaced by zz_flip - blockIdx.z, i.e. the planes are swept downwards
     int y0, ystride;       // rows this launch covers: y = y0 + blockIdx.y * ystride
+    // two-cell kernels on rows narrower than a CTA's 256 cells (nx = 128, 64): a CTA covers 256 / nx consecutive rows of the
+    // launch (the NARROW instantiations), row = (blockIdx.y << rows_per_cta_log2) + (cell offset >> nx_log2)
+    int rows_per_cta_log2, nx_log2, rows;
     long long kz[Q][3];    // byte offset of (slot S, plane z-1 / z / z+1) from a cell of plane z: kPopBytes*(S*slot + dz*plane)
 };
 
@@ -599,7 +602,7 @@ struct StreamCollide {
 // Same arithmetic per cell as StreamCollide<0>: bit-identical results (tests).  Opt-in: FG_FLAG_EVEN_VEC4 / _VEC2.
 template <int V> struct alignas(sizeof(pop_t) * V) VecF { pop_t a[V]; };      // V consecutive cells of one slot, in the storage type
 
-template <bool MRT, int V>
+template <bool MRT, int V, bool NARROW = false>
 struct StreamCollideEvenVec {
     static constexpr int kThreads = kCollideThreads;
 #if defined(FG_VEC_OCC)
@@ -626,7 +629,13 @@ struct StreamCollideEvenVec {
     // grid: (ceil(nx / V / threads), rows, planes); requires nx % V == 0
     FG_HD static void run(const StepParams &p, int bx, int by, int bz, int tx) {
         const Lattice &L = p.L;
-        const int x0 = (bx * kThreads + tx) * V, y = p.y0 + by * p.ystride;
+        int x0 = (bx * kThreads + tx) * V, row = by;
+        if (NARROW) {                           // narrow rows: this CTA holds several of them
+            row = (by << p.rows_per_cta_log2) + (x0 >> p.nx_log2);
+            x0 &= L.nx - 1;
+            if (row >= p.rows) return;
+        }
+        const int y = p.y0 + row * p.ystride;
         int zz = p.zz_begin + (p.zz_flip >= 0 ? p.zz_flip - bz : bz) * p.zz_stride;
         if (zz >= p.zz_skip_begin) zz += p.zz_skip_len;
         if (x0 >= L.nx) return;
@@ -654,7 +663,7 @@ struct StreamCollideEvenVec {
 // x + 1; the links across those faces bounce back into the cell's own opposite slot (+ the moving-wall term), on the read
 // and on the write side, exactly as CHECK_XEDGE does for one cell per thread.  Only the two warps at the ends of a row run
 // that predicated code (warp-uniform branch, as CHECK_XWARP).
-template <bool MRT, bool XWALL = false>
+template <bool MRT, bool XWALL = false, bool NARROW = false>
 struct StreamCollideOddVec2 {
     static constexpr int kThreads = kCollideThreads;
 #if defined(FG_ODDVEC_OCC)
@@ -772,7 +781,13 @@ struct StreamCollideOddVec2 {
     // link in the rows of the launch
     FG_HD static void run(const StepParams &p, int bx, int by, int bz, int tx) {
         const Lattice &L = p.L;
-        const int x0 = (bx * kThreads + tx) * 2, y = p.y0 + by * p.ystride;
+        int x0 = (bx * kThreads + tx) * 2, row = by;
+        if (NARROW) {                           // narrow rows: this CTA holds several of them
+            row = (by << p.rows_per_cta_log2) + (x0 >> p.nx_log2);
+            x0 &= L.nx - 1;
+            if (row >= p.rows) return;
+        }
+        const int y = p.y0 + row * p.ystride;
         int zz = p.zz_begin + (p.zz_flip >= 0 ? p.zz_flip - bz : bz) * p.zz_stride;
         if (zz >= p.zz_skip_begin) zz += p.zz_skip_len;
         if (x0 >= L.nx) return;

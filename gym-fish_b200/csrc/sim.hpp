@@ -725,8 +725,24 @@ private:
         // default (round 2, gpu pass 2): two cells per thread with 64-bit accesses wherever a row fills whole CTAs that way —
         // +2.6 ... +3.2 % MLUPS on 256- and 512-wide lattices (fewer memory instructions per byte; the 4-cell form gains
         // less: 125 registers leave 4 CTAs per SM).  Narrower rows would leave half of each CTA idle and keep the scalar kernel.
-        if (L_.nx % (2 * kCollideThreads) == 0) return kVecDefault;
+        if (L_.nx % (2 * kCollideThreads) == 0 || narrow_rows_log2() > 0) return kVecDefault;
         return 0;
+    }
+    // rows of 128 or 64 cells: a CTA of the two-cell kernels (256 cells) takes 2 or 4 consecutive rows of the launch, so the
+    // 256x128x128 channel of BASELINE.json configs[1] runs the two-cell kernels as well; log2(rows per CTA), 0 otherwise
+    int narrow_rows_log2() const {
+        if (kCollideThreads != 128) return 0;
+        return L_.nx == 128 ? 1 : (L_.nx == 64 ? 2 : 0);
+    }
+    // launch geometry of a two-cell kernel over `rows` rows and `planes` planes (and the row mapping it needs in StepParams)
+    Dim3 vec2_grid(StepParams &p, int rows, int planes) const {
+        const int rl = narrow_rows_log2();
+        p.rows = rows;
+        if (rl > 0) {
+            p.rows_per_cta_log2 = rl; p.nx_log2 = L_.nx == 128 ? 7 : 6;
+            return Dim3{1, (rows + (1 << rl) - 1) >> rl, planes};
+        }
+        return Dim3{(L_.nx / 2 + kCollideThreads - 1) / kCollideThreads, rows, planes};
     }
     // what the library picks by itself where rows are wide enough: two cells per thread.  The opt-in 16-bit-storage build
     // gains most from it (it is issue-bound: 512^3, 100 steps, gpu pass b1: 50 919 MLUPS with one cell per thread in both
@@ -742,16 +758,22 @@ private:
     // the one-cell kernel
     bool odd_vec2() const {
         if ((cfg.flags & FG_FLAG_ODD_SCALAR) || L_.solid || L_.nx % 2 != 0 || L_.nx < 4) return false;
-        return (cfg.flags & FG_FLAG_ODD_VEC2) || (kVecDefault != 0 && L_.nx % (2 * kCollideThreads) == 0);
+        return (cfg.flags & FG_FLAG_ODD_VEC2) || (kVecDefault != 0 && (L_.nx % (2 * kCollideThreads) == 0 || narrow_rows_log2() > 0));
+    }
+    template <bool XW, bool NARROW>
+    bool launch_odd_vec2_t(const StepParams &p, Dim3 g) {
+        return cfg.collision == FG_MRT ? dev.template launch<StreamCollideOddVec2<true, XW, NARROW>>(g, p)
+                                       : dev.template launch<StreamCollideOddVec2<false, XW, NARROW>>(g, p);
     }
     bool launch_odd_vec2(const StepParams &p, Dim3 g, bool xwall = false) {
-        if (xwall)
-            return cfg.collision == FG_MRT ? dev.template launch<StreamCollideOddVec2<true, true>>(g, p) : dev.template launch<StreamCollideOddVec2<false, true>>(g, p);
-        return cfg.collision == FG_MRT ? dev.template launch<StreamCollideOddVec2<true>>(g, p) : dev.template launch<StreamCollideOddVec2<false>>(g, p);
+        if (p.rows_per_cta_log2 > 0) return xwall ? launch_odd_vec2_t<true, true>(p, g) : launch_odd_vec2_t<false, true>(p, g);
+        return xwall ? launch_odd_vec2_t<true, false>(p, g) : launch_odd_vec2_t<false, false>(p, g);
     }
     bool launch_even_vec(const StepParams &p, Dim3 g, int vec) {
         const bool mrt = cfg.collision == FG_MRT;
         if (vec == 4) return mrt ? dev.template launch<StreamCollideEvenVec<true, 4>>(g, p) : dev.template launch<StreamCollideEvenVec<false, 4>>(g, p);
+        if (p.rows_per_cta_log2 > 0)
+            return mrt ? dev.template launch<StreamCollideEvenVec<true, 2, true>>(g, p) : dev.template launch<StreamCollideEvenVec<false, 2, true>>(g, p);
         return mrt ? dev.template launch<StreamCollideEvenVec<true, 2>>(g, p) : dev.template launch<StreamCollideEvenVec<false, 2>>(g, p);
     }
     // hole: planes [hole_b, hole_e) inside [zb, ze) are left out (zstride 1 only)
@@ -761,7 +783,7 @@ private:
         const int planes = (ze - zb - hole + zstride - 1) / zstride;
         if (planes <= 0 || rows <= 0) return true;
         const bool down = parity_ == 1 && !(cfg.flags & FG_FLAG_NO_SWEEP_FLIP);
-        StepParams p{L_, C_, F, zb, zstride, hole ? hole_b : 0x7fffffff, hole, down ? planes - 1 : -1, y0, ystride, {}};
+        StepParams p{L_, C_, F, zb, zstride, hole ? hole_b : 0x7fffffff, hole, down ? planes - 1 : -1, y0, ystride, 0, 0, rows, {}};
         for (int s = 0; s < Q; ++s)
             for (int d = 0; d < 3; ++d) p.kz[s][d] = (long long)kPopBytes * (s * L_.slot + (long long)(d - 1) * L_.plane);
         const Dim3 g{(L_.nx + kCollideThreads - 1) / kCollideThreads, rows, planes};
@@ -775,7 +797,8 @@ private:
         if (parity_ == 0) {
             // the even step is purely local: only obstacles need the checked variant
             const int vec = L_.solid ? 0 : even_vec_width();
-            if (vec) ok = launch_even_vec(p, Dim3{(L_.nx / vec + kCollideThreads - 1) / kCollideThreads, rows, planes}, vec);
+            if (vec == 2) { const Dim3 g2 = vec2_grid(p, rows, planes); ok = launch_even_vec(p, g2, 2); }
+            else if (vec) ok = launch_even_vec(p, Dim3{(L_.nx / vec + kCollideThreads - 1) / kCollideThreads, rows, planes}, vec);
             else ok = mode == CHECK_ALL && L_.solid ? launch_collide_pm<0, CHECK_ALL>(p, g) : launch_collide_pm<0, CHECK_NONE>(p, g);
         } else {
             switch (mode) {
@@ -783,11 +806,11 @@ private:
                 case CHECK_XEDGE: ok = launch_collide_pm<1, CHECK_XEDGE>(p, g); break;
                 case CHECK_XWARP:
                     // rows between x walls (the tank, the school): the two-cell kernel with the wall selects in its row-end warps
-                    if (odd_vec2()) ok = launch_odd_vec2(p, Dim3{(L_.nx / 2 + kCollideThreads - 1) / kCollideThreads, rows, planes}, true);
+                    if (odd_vec2()) { const Dim3 g2 = vec2_grid(p, rows, planes); ok = launch_odd_vec2(p, g2, true); }
                     else ok = launch_collide_pm<1, CHECK_XWARP>(p, g);
                     break;
                 default:
-                    if (odd_vec2()) ok = launch_odd_vec2(p, Dim3{(L_.nx / 2 + kCollideThreads - 1) / kCollideThreads, rows, planes});
+                    if (odd_vec2()) { const Dim3 g2 = vec2_grid(p, rows, planes); ok = launch_odd_vec2(p, g2); }
                     else ok = launch_collide_pm<1, CHECK_NONE>(p, g);
                     break;
             }
@@ -855,7 +878,7 @@ private:
         done[0][0] = done[0][1] = done[1][0] = done[1][1] = 0;
         if (planes <= 0) return true;
         PairParams p{};
-        p.s = StepParams{L_, C_, ForceField{}, zb, 1, hole ? hole_b : 0x7fffffff, hole, -1, 0, 1, {}};
+        p.s = StepParams{L_, C_, ForceField{}, zb, 1, hole ? hole_b : 0x7fffffff, hole, -1, 0, 1, 0, 0, 0, {}};
         for (int s = 0; s < Q; ++s)
             for (int d = 0; d < 3; ++d) p.s.kz[s][d] = (long long)kPopBytes * (s * L_.slot + (long long)(d - 1) * L_.plane);
         p.planes = planes; p.rows = L_.ny; p.xblocks = (L_.nx + 127) / 128;

@@ -334,3 +334,20 @@ def test_default_two_cell_kernels_equal_the_scalar_ones_on_256_wide_rows(g, emu)
             s.step(7)
         assert np.array_equal(a.get_populations(), b.get_populations()), name
         assert util.rel_l2(a.get_fields(f64=True)[1], o.get_fields(f64=True)[1]) <= TOL_FIELD
+
+
+@pytest.mark.parametrize("nx", [128, 64])
+def test_two_cell_kernels_on_narrow_rows_take_several_rows_per_cta(g, emu, nx):
+    """nx = 128 / 64: a CTA of the two-cell kernels covers 2 / 4 consecutive rows of the launch (sim.hpp vec2_grid, the NARROW
+    instantiations) — the 256x128x128 channel of BASELINE.json configs[1] runs them by default.  Row counts that do not fill
+    the last CTA (ny = 7: 7 periodic rows, or 5 bulk rows between y walls), x walls, a plane hole from the split."""
+    A = g._abi
+    for name in ("mrt_force", "mrt_inlet_outlet_ywalls", "mrt_xy_walls", "mrt_xwalls_moving", "bgk_periodic"):
+        kw = dict(util.parity_cases(g)[name], nx=nx, ny=7, nz=6)
+        a, b, o = g.Sim(backend=emu, **kw), g.Sim(backend=emu, flags=A.FLAG_EVEN_SCALAR | A.FLAG_ODD_SCALAR, **kw), g.Sim(backend="oracle", **kw)
+        rho, u = util.smooth_fields(a.shape)
+        for s in (a, b, o):
+            s.set_fields(rho, u)
+            s.step(7)
+        assert np.array_equal(a.get_populations(), b.get_populations()), name
+        assert util.rel_l2(a.get_fields(f64=True)[1], o.get_fields(f64=True)[1]) <= TOL_FIELD

@@ -453,3 +453,25 @@ def test_default_two_cell_kernels_equal_the_scalar_ones_on_256_wide_rows(g, cuda
             s.step(9)
         assert np.array_equal(a.get_populations(), b.get_populations()), name
         a.close(); b.close()
+
+
+@pytest.mark.parametrize("nx", [128, 64])
+def test_two_cell_kernels_on_narrow_rows_take_several_rows_per_cta(g, cuda, nx):
+    """nx = 128 / 64: a CTA of the two-cell kernels covers 2 / 4 consecutive rows (the NARROW instantiations; default on the
+    256x128x128 channel of configs[1]); bit-identical to the scalar kernels, odd row counts, walls, and with an immersed
+    sphere so that the plane split launches ranges with a hole."""
+    A = g._abi
+    for name in ("mrt_force", "mrt_inlet_outlet_ywalls", "mrt_xy_walls", "mrt_xwalls_moving", "bgk_periodic"):
+        kw = dict(util.parity_cases(g)[name], nx=nx, ny=23, nz=20, max_markers=300, max_links=1)
+        a, b = g.Sim(backend=cuda, **kw), g.Sim(backend=cuda, flags=A.FLAG_EVEN_SCALAR | A.FLAG_ODD_SCALAR, **kw)
+        rho, u = util.smooth_fields(a.shape)
+        for s in (a, b):
+            s.set_fields(rho, u)
+            s.step(9)
+        assert np.array_equal(a.get_populations(), b.get_populations()), name
+        X = util.sphere_markers((nx / 2 + 0.2, 11.1, 9.3), 3.0, 100)
+        for s in (a, b):
+            s.set_markers(X, np.zeros_like(X), np.ones(100, np.float32))
+            s.step(6)
+        assert np.abs(a.get_populations() - b.get_populations()).max() < 2e-7, name      # spreading atomics are unordered
+        a.close(); b.close()
