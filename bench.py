@@ -242,6 +242,40 @@ class ClockSampler:
         return out
 
 
+class NvlinkCounters:
+    """NVLink data bytes sent / received by this rank's GPU (NVML field values NVLINK_THROUGHPUT_DATA_TX / _RX, KiB, summed
+    over the links) — read around the timed region at N > 1, so that the line carries the bytes the halo push really put on
+    the wire next to the 5 populations x nx x ny x 4 B per face the design says it should."""
+
+    def __init__(self, device):
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            idx = device
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    idx = int(vis.split(",")[device])
+                except (ValueError, IndexError):
+                    idx = device
+            self._nv, self._h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.ok = self.read() is not None
+        except Exception:           # noqa: BLE001
+            self.ok = False
+
+    def read(self):
+        try:
+            nv = self._nv
+            v = nv.nvmlDeviceGetFieldValues(self._h, [(nv.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, 0xFFFFFFFF),
+                                                      (nv.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX, 0xFFFFFFFF)])
+            if any(x.nvmlReturn != 0 for x in v):
+                return None
+            return int(v[0].value.ullVal) * 1024, int(v[1].value.ullVal) * 1024
+        except Exception:           # noqa: BLE001
+            return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -374,13 +408,14 @@ def add_school(g, sim):
                 sim.add_fish(fish_desc(g, (xc, yc, zc)))
 
 
-def timed_steps(ctx, sim, steps, warmup, clocks=None):
+def timed_steps(ctx, sim, steps, warmup, clocks=None, nvlink=None):
     """W untimed warm-up steps, then EXACTLY K steps in one fg_step call bracketed by barrier + sync on both sides; the
     time is the library's CUDA-event pair around the call on its own stream, max over ranks."""
     sim.step(warmup)
     ctx.barrier()
     sim.sync()
     s0 = sim.stats()
+    nv0 = nvlink.read() if nvlink is not None and nvlink.ok else None
     ctx.barrier()
     t0 = time.perf_counter()
     sim.step(steps)               # events bracket exactly K steps on the library's stream
@@ -390,6 +425,11 @@ def timed_steps(ctx, sim, steps, warmup, clocks=None):
     t1 = time.perf_counter()
     st = sim.stats()
     ctx.barrier()
+    if nv0 is not None:
+        time.sleep(0.2)           # the NVML counters are refreshed periodically, not per packet
+        nv1 = nvlink.read()
+        if nv1 is not None:
+            nvlink.delta = ((nv1[0] - nv0[0]) / steps, (nv1[1] - nv0[1]) / steps)
     ms = ctx.max_over_ranks(st.last_step_ms)
     return ms, st, s0, (t0, t1)
 
@@ -464,7 +504,7 @@ def e2e_loop(ctx, sim, wl, markers, k2, cells_total):
             "probe_u_mean": float(np.asarray(out)[:, 1:].mean())}
 
 
-def measure(ctx, wl, flags, steps, warmup, storage="f32", clocks=None, want_e2e=True, want_profile=True, keep=False, extra=None):
+def measure(ctx, wl, flags, steps, warmup, storage="f32", clocks=None, want_e2e=True, want_profile=True, keep=False, extra=None, nvlink=None):
     """One workload, timed as the contract says.  Returns a dict (and the live sim when keep=True)."""
     g, args = ctx.g, ctx.args
     w = WORKLOADS[wl]
@@ -477,7 +517,7 @@ def measure(ctx, wl, flags, steps, warmup, storage="f32", clocks=None, want_e2e=
     cells_local = sim.nx * sim.ny * sim.nz
     cells_total = cells_local * ctx.world
 
-    ms, st, s0, window = timed_steps(ctx, sim, steps, warmup, clocks)
+    ms, st, s0, window = timed_steps(ctx, sim, steps, warmup, clocks, nvlink)
     launches = int(ctx.sum_over_ranks(st.kernel_launches - s0.kernel_launches))
     graph_launches = int(st.graph_launches - s0.graph_launches)
     split = int(st.split_substeps - s0.split_substeps)
@@ -656,8 +696,9 @@ def main():
     bytes_per_update = BYTES_PER_CELL_UPDATE if args.storage == "f32" else BYTES_PER_CELL_UPDATE / 2
 
     clocks = ClockSampler(local) if rank == 0 else None      # runs through warm-up, the timed region and the profiled pass
+    nvlink = NvlinkCounters(local) if rank == 0 and world > 1 else None
     main_res, sim, markers = measure(ctx, wl, flags, args.steps, args.warmup, storage=args.storage, clocks=clocks, keep=True,
-                                     extra=dict(pair_lag=args.pair_lag))
+                                     extra=dict(pair_lag=args.pair_lag), nvlink=nvlink)
     clk = clocks.stop(*main_res["window"]) if clocks is not None else None
 
     sub = {}
@@ -683,6 +724,17 @@ def main():
     }
     if SHRINK != 1:
         line["dry_run_shrink"] = SHRINK
+    if nvlink is not None:
+        pop_bytes = 4 if args.storage == "f32" else 2
+        faces = 2 if (wl in PERIODIC_Z or world > 2) else 1      # rank 0: both faces internal when z is periodic
+        exp = faces * 5 * w["nx"] * w["ny"] * pop_bytes
+        d = getattr(nvlink, "delta", None)
+        line["nvlink"] = {"rank": 0, "tx_bytes_per_step": d[0] if d else None, "rx_bytes_per_step": d[1] if d else None,
+                          "expected_halo_bytes_per_step_per_direction": exp,
+                          "expected": f"{faces} internal face(s) x 5 outgoing populations x {w['nx']} x {w['ny']} cells x {pop_bytes} B, pushed by peer stores (ZFaceOp); "
+                                      "flags and (with bodies) marker / wrench exchange add a few hundred bytes",
+                          "source": "NVML NVLINK_THROUGHPUT_DATA_TX / _RX of rank 0's GPU, all links, read around the timed region" if d else
+                                    "NVML NVLink throughput counters not available on this box"}
     emit_lock = threading.Lock()
     emitted = []
 

@@ -33,3 +33,37 @@ def test_reference_arm_other_ranks_exit_quietly():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "3"],
                        capture_output=True, text=True, timeout=120, env=env)
     assert r.returncode == 0 and not [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+
+
+def _dry_run(*extra):
+    """The b200 arm itself cannot run here (no GPU); FG_BENCH_SHRINK + FG_CUDA_LIB point the same script at the CPU emulation of
+    the kernels on lattices 16x smaller — a dry run of the script's control flow, marked as such in its line."""
+    emu = os.path.join(ROOT, "tests", "emu", "libfishgym_emu.so")
+    subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "emu")], capture_output=True)
+    env = dict(os.environ, FG_BENCH_SHRINK="16", FG_CUDA_LIB=emu)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "4", "--warmup", "3", *extra],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    return json.loads(lines[0])
+
+
+def test_b200_arm_dry_run_prints_the_contract_keys():
+    d = _dry_run()
+    assert d["dry_run_shrink"] == 16 and d["n_gpus"] == 1 and d["unit"] == "MLUPS" and d["scaling"] == "weak" and d["vs_baseline"] is None
+    for k in ("metric", "value", "ms_per_step", "higher_is_better", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert k in d, k
+    assert d["config"]["name"] == "box_512" and d["gpu_launches"] > 0 and d["value"] > 0
+    # the emulation has no event timing of the bulk launches, so the dry run carries no roofline object; on a GPU it must
+    assert d["roofline"] is None or {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"])
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"]) and d["e2e"]["h2d_bytes_per_step"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0 and "own process" in d["cpu_baseline"]["sample"]
+    assert set(d["sub_records"]) == {"ib_overhead", "env", "sphere_256x128x128"} and "watchdog" not in d
+    assert not any("error" in v for v in d["sub_records"].values() if isinstance(v, dict))
+
+
+def test_b200_arm_watchdog_prints_the_line_when_the_extras_overrun():
+    """Sub-records and the CPU baseline are extras: when they exceed --sub-budget-s the main measurement is printed anyway."""
+    d = _dry_run("--sub-budget-s", "0.01")
+    assert d["value"] > 0 and d["e2e"] is not None and "watchdog" in d
