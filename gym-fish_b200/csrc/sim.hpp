@@ -711,7 +711,7 @@ private:
         // 8 CTAs/SM (64 registers) on SMALL z-slabs, 9 (56 registers) otherwise (lbm_core.cuh StreamCollide): the ~4 us per
         // step that 9 cost the high-priority chain on slabs of 4.2 M cells outweigh its 2 % faster kernel only below ~8 M
         // cells per rank (512^3 and the school on 8 GPUs were measured with 9: 318 252 / 272 528 MLUPS)
-        if (peers_ && slab_occ8_ && (long long)L_.plane * L_.nz < (8ll << 20))
+        if (small_peered_slab())
             return cfg.collision == FG_MRT ? dev.template launch<StreamCollide<PARITY, true, MODE, 8>>(g, p)
                                            : dev.template launch<StreamCollide<PARITY, false, MODE, 8>>(g, p);
         return cfg.collision == FG_MRT ? dev.template launch<StreamCollide<PARITY, true, MODE>>(g, p)
@@ -725,9 +725,17 @@ private:
         // default (round 2, gpu pass 2): two cells per thread with 64-bit accesses wherever a row fills whole CTAs that way —
         // +2.6 ... +3.2 % MLUPS on 256- and 512-wide lattices (fewer memory instructions per byte; the 4-cell form gains
         // less: 125 registers leave 4 CTAs per SM).  Narrower rows would leave half of each CTA idle and keep the scalar kernel.
+        if (small_peered_slab()) return 0;
         if (L_.nx % (2 * kCollideThreads) == 0 || narrow_rows_log2() > 0) return kVecDefault;
         return 0;
     }
+    // Peered z-slabs below 8 M cells keep the one-cell kernels (at 8 CTAs/SM, launch_collide_pm): there the high-priority chain
+    // (neighbour flags -> IB kernels -> boundary planes -> halo push -> near planes) is as long as the interior collide beside
+    // it, and each of its ~12 dependent launches waits for a resident interior CTA to retire — 3.5 us for a one-cell CTA,
+    // 5.3 us for a two-cell one.  Two GPUs, 256x128x128 channel + sphere per GPU, 2000 steps (gpu pass b5): one-cell kernels
+    // 71 636 MLUPS, two-cell even / odd / both 69 062 / 69 993 / 67 574, one-cell at 9 CTAs/SM 68 957 — although the two-cell
+    // kernel itself is 5 % faster per launch (54.4 against 57.4 us).  On 512^3 slabs the chain is 1 % of the step.
+    bool small_peered_slab() const { return peers_ && slab_occ8_ && (long long)L_.plane * L_.nz < (8ll << 20); }
     // rows of 128 or 64 cells: a CTA of the two-cell kernels (256 cells) takes 2 or 4 consecutive rows of the launch, so the
     // 256x128x128 channel of BASELINE.json configs[1] runs the two-cell kernels as well; log2(rows per CTA), 0 otherwise
     int narrow_rows_log2() const {
@@ -758,7 +766,8 @@ private:
     // the one-cell kernel
     bool odd_vec2() const {
         if ((cfg.flags & FG_FLAG_ODD_SCALAR) || L_.solid || L_.nx % 2 != 0 || L_.nx < 4) return false;
-        return (cfg.flags & FG_FLAG_ODD_VEC2) || (kVecDefault != 0 && (L_.nx % (2 * kCollideThreads) == 0 || narrow_rows_log2() > 0));
+        if (cfg.flags & FG_FLAG_ODD_VEC2) return true;
+        return kVecDefault != 0 && !small_peered_slab() && (L_.nx % (2 * kCollideThreads) == 0 || narrow_rows_log2() > 0);
     }
     template <bool XW, bool NARROW>
     bool launch_odd_vec2_t(const StepParams &p, Dim3 g) {
