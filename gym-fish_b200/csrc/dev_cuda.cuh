@@ -155,7 +155,7 @@ public:
         }
         bool ok = true;
         for (int i = 0; i < kStreams && ok; ++i)
-            ok = ck(cudaStreamCreateWithPriority(&s_[i], cudaStreamNonBlocking, i < 2 ? greatest : least), "cudaStreamCreate") &&
+            ok = ck(cudaStreamCreateWithPriority(&s_[i], cudaStreamNonBlocking, (i < 2 || i >= 4) ? greatest : least), "cudaStreamCreate") &&
                  ck(cudaEventCreateWithFlags(&fork_ev_[i], cudaEventDisableTiming), "cudaEventCreate") &&
                  ck(cudaEventCreateWithFlags(&join_ev_[i], cudaEventDisableTiming), "cudaEventCreate");
         stream_ = s_[0];
@@ -325,7 +325,8 @@ public:
     // Kernel launches go to stream `current()`.  fork_to(s): stream s starts where the current stream is now and
     // becomes current; switch_to(s): make s current (work already queued elsewhere keeps running beside it);
     // join_from(s): the current stream waits for everything queued on s.  Inside a capture these are the parallel
-    // branches of the graph.  Copies, memsets and event records always use stream 0.
+    // branches of the graph.  Copies, memsets, event records and the neighbour WAITS always use stream 0; the halo signal follows
+    // the current stream.
     int current() const { return cur_; }
     bool fork_to(int s) {
         const int from = cur_;
@@ -442,7 +443,7 @@ public:
     bool signal_flags(int *mine, int *lo, int *hi) {
         ++launches;
         if (gmode_ == 2) return true;
-        signal_kernel<<<1, 1, 0, stream_>>>(mine, lo, hi);
+        signal_kernel<<<1, 1, 0, s_[cur_]>>>(mine, lo, hi);        // on the current stream: the halo branch signals as soon as ITS push is queued
         return ck(cudaGetLastError(), "signal launch");
     }
     bool wait_flags(int *flags, bool lo, bool hi) {
@@ -525,7 +526,8 @@ private:
     cudaEvent_t tev_[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
     int tpair_ = 0;
     std::vector<std::pair<std::string, void *>> opened_;
-    static constexpr int kStreams = 4;      // 0/1 high priority (main + thin branch), 2/3 low (far branch + its thin branch)
+    static constexpr int kStreams = 6;      // 0/1 high priority (main + thin branch), 2/3 low (far branch + its thin branch),
+                                            // 4/5 high (halo branch of a slab: boundary planes -> push -> signal, + its thin branch)
     cudaStream_t s_[kStreams] = {};
     cudaEvent_t fork_ev_[kStreams] = {}, join_ev_[kStreams] = {};
     int cur_ = 0;

@@ -761,6 +761,12 @@ public:
         zmin = zmin_; zmax = zmax_;
         return true;
     }
+    // no marker stencil touches the first or the last plane of this slab (so their collide needs no IB force)
+    bool boundary_planes_free(int nz) const {
+        if (z_all_) return false;
+        if (!z_any_ || zmax_ < zmin_) return true;
+        return zmin_ > 1 && zmax_ < nz;
+    }
     bool near_planes(int &za, int &zb) const {
         if (z_all_) return false;
         if (!z_any_ || zmax_ < zmin_) { za = zb = 1; return true; }   // no stencil on this slab: everything is far

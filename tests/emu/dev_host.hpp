@@ -41,7 +41,8 @@ public:
     // / highest / a random runnable stream.  A missing fork / join between two launches that touch the same data then
     // shows up as a result that depends on the policy (tests/test_stream_order.py); work left on a side stream at a
     // synchronisation is reported as an error.  Nothing stays queued across ABI calls (toc_record drains).
-    static constexpr int kStreams = 5;      // 0-3 as in dev_cuda.cuh, 4 = its copy stream
+    static constexpr int kStreams = 7;      // 0-5 as in dev_cuda.cuh, 6 = its copy stream
+    static constexpr int kCopy = 6;
     bool init(int, std::string &) {
         if (const char *e = std::getenv("FG_EMU_SCHED")) {
             const std::string v(e);
@@ -87,9 +88,9 @@ public:
     // dev_cuda.cuh upload_early: the copy runs on its own stream behind event `after`, stream 0 waits for it
     bool upload_early(void *d, const void *s, size_t n, int done, int after) {
         if (gmode_ != 0) { err = "upload_early inside a graph capture"; return false; }
-        if (after >= 0 && after < 4 && named_[after]) wait(4, named_[after]);
-        if (!submit(4, [=] { std::memcpy(d, s, n); return true; })) return false;
-        named_[done] = record(4);
+        if (after >= 0 && after < 4 && named_[after]) wait(kCopy, named_[after]);
+        if (!submit(kCopy, [=] { std::memcpy(d, s, n); return true; })) return false;
+        named_[done] = record(kCopy);
         wait(0, named_[done]);
         return true;
     }
@@ -264,7 +265,7 @@ public:
     }
     void graph_clear() { drain_all(); graphs_.clear(); }
     bool signal_flags(int *mine, int *lo, int *hi) {
-        return submit(0, [=] {
+        return submit(cur_, [=] {
             const int value = ++mine[2];
             std::atomic_thread_fence(std::memory_order_release);
             if (lo) *static_cast<volatile int *>(lo) = value;

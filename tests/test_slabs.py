@@ -106,16 +106,21 @@ def test_device_peer_pushes_equal_unsplit(g, emu, case, overlap):
         parts[0].step(1)
 
 
+@pytest.mark.parametrize("split", [True, False])
 @pytest.mark.parametrize("overlap", [True, False])
-def test_plane_split_on_peered_slabs(g, emu, overlap):
+def test_plane_split_on_peered_slabs(g, emu, overlap, split):
     """Plane split + z-slabs: on each rank the interior planes away from its body collide before the rank even waits
     for its neighbours' halos (sim.hpp step()).  Each slab holds a moving sphere; populations must equal the unsplit,
-    un-decomposed run bit for bit (the emulation adds in a fixed order)."""
+    un-decomposed run bit for bit (the emulation adds in a fixed order).
+    Halo branch: while no stencil reaches a boundary plane, boundary planes -> halo push -> signal run on their own stream
+    beside the IB kernels; the spheres drift towards the slab faces, so the last steps fall back to the serial order —
+    with split=False the substeps are captured as graphs (under FG_EMU_GRAPHS, tests/test_stream_order.py), and the branch
+    is part of the graph key."""
     P = g.BC_PERIODIC
     kw = dict(nx=12, ny=10, nz=64, tau=0.8, collision=g.MRT, max_markers=400, max_links=2, bc=[P] * 6, body_force=[0, 0, 2e-5])
     whole = g.Sim(backend=emu, flags=g._abi.FLAG_NO_SPLIT, **kw)
     flags = 0 if overlap else g._abi.FLAG_NO_OVERLAP
-    parts = [g.Sim(backend=emu, n_ranks=2, rank=r, flags=flags, split_min_cells=1, **kw) for r in range(2)]
+    parts = [g.Sim(backend=emu, n_ranks=2, rank=r, flags=flags, split_min_cells=1 if split else 1 << 30, **kw) for r in range(2)]
     rho, u = util.smooth_fields(whole.shape, amp=0.01)
     whole.set_fields(rho, u)
     for r, s in enumerate(parts):
@@ -123,9 +128,9 @@ def test_plane_split_on_peered_slabs(g, emu, overlap):
     h = [s.peer_export() for s in parts]
     parts[0].peer_connect(h[1], h[1])
     parts[1].peer_connect(h[0], h[0])
-    for it in range(8):
-        Xa = util.sphere_markers((6.2, 5.1, 8.3 + 2.0 * it), 2.5, 100)           # stays inside slab 0
-        Xb = util.sphere_markers((5.7, 4.6, 56.1 - 2.0 * it), 2.5, 100)          # stays inside slab 1
+    for it in range(11):
+        Xa = util.sphere_markers((6.2, 5.1, 8.3 + 1.85 * it), 2.5, 100)          # stays inside slab 0; its stencils reach the top plane at the end
+        Xb = util.sphere_markers((5.7, 4.6, 56.1 - 2.0 * it), 2.5, 100)          # stays inside slab 1; reaches its bottom plane at the end
         U = np.zeros((100, 3), np.float32)
         U[:, 2] = 0.01
         one = np.ones(100, np.float32)
@@ -135,7 +140,10 @@ def test_plane_split_on_peered_slabs(g, emu, overlap):
         whole.step(1)
         for s in parts:
             s.step(1)
-    assert parts[0].stats().split_substeps >= 5 and parts[1].stats().split_substeps >= 5 and whole.stats().split_substeps == 0
+    if split:
+        assert parts[0].stats().split_substeps >= 5 and parts[1].stats().split_substeps >= 5 and whole.stats().split_substeps == 0
+    else:
+        assert parts[0].stats().split_substeps == 0
     assert np.array_equal(whole.get_populations(), np.concatenate([s.get_populations() for s in parts], axis=1))
 
 
