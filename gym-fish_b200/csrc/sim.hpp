@@ -378,10 +378,13 @@ public:
             // The collide of the other ("far") planes needs neither the force nor the marker upload, so it runs on a
             // low-priority branch BESIDE the IB kernels instead of after them.
             split_ = false; near_a_ = lo; near_b_ = hi;
-            // Halo branch (peered slabs with bodies): when no stencil reaches a boundary plane, the boundary planes need no
-            // IB force, so boundary planes -> halo push -> signal run on their own high-priority stream BESIDE the IB kernels
-            // instead of between them and the near-plane collide — the chain in front of the near planes is four launches
-            // shorter, and the neighbours get their halos ~30 us earlier.
+            // Halo branch (peered slabs with bodies; OPT-IN, FG_HALO_BRANCH=1): when no stencil reaches a boundary plane, the
+            // boundary planes need no IB force, so boundary planes -> halo push -> signal can run on their own high-priority
+            // stream BESIDE the IB kernels instead of between them and the near-plane collide.  Measured on two GPUs with one
+            // 256x128x128 channel + sphere each (gpu passes b7 / b8, 2000 steps): serial order 71 508 MLUPS, branch submitted
+            // before the IB kernels 67 386, after them 68 268 — slower with the one-cell kernels these slabs run; with the
+            // two-cell kernels 71 870 (serial: 67 574), a tie with the default.  Hence off by default; bit-identical either way
+            // (tests/test_slabs.py runs it under every stream-order policy of the emulation).
             bool halo_branch = false;
             if (ib_on && !prof && !(cfg.flags & FG_FLAG_NO_SPLIT)) {
                 int a, b;
@@ -447,9 +450,10 @@ public:
             // neighbours must have delivered the halos of the previous step before anything reads ghost planes
             // (the IB band moments do, at odd parity) or boundary planes
             if (ranks && peers_ && overlap && !dev.wait_flags(flags_, has_lo_peer(), has_hi_peer())) return cuda_fail();
-            if (halo_branch) {
-                if (!dev.fork_to(4) || !launch_boundary_planes(ForceField{}) || !launch_faces() || !dev.switch_to(0)) return cuda_fail();
-            }
+            // the branch starts here (behind the neighbour wait), but its kernels are SUBMITTED after the IB kernels: streams of
+            // equal priority are served in submission order, and the IB kernels head the longer chain
+            if (halo_branch && (!dev.fork_to(4) || !dev.switch_to(0))) return cuda_fail();
+            if (halo_branch && halo_first_ && (!dev.switch_to(4) || !launch_boundary_planes(ForceField{}) || !launch_faces() || !dev.switch_to(0))) return cuda_fail();
             ForceField F{};
             if (ib_on) {
                 if (prof) dev.mark(1);
@@ -462,6 +466,7 @@ public:
                 if (prof) dev.mark(1);
                 F = ib_.force_view();
             }
+            if (halo_branch && !halo_first_ && (!dev.switch_to(4) || !launch_boundary_planes(ForceField{}) || !launch_faces() || !dev.switch_to(0))) return cuda_fail();
             if (overlap && !halo_branch) {
                 // boundary planes first, push halos over NVLink, then the interior hides the exchange
                 if (!launch_boundary_planes(F) || !launch_faces()) return cuda_fail();
@@ -1017,7 +1022,8 @@ private:
     int64_t collide_launches_ = 0, last_collide_launches_ = 0, collide_cells_ = 0, last_collide_cells_ = 0;
     int64_t split_substeps_ = 0, pair_substeps_ = 0;
     bool slab_occ8_ = std::getenv("FG_SLAB_OCC9") == nullptr;     // A/B switch for launch_collide_pm's small-slab rule
-    bool halo_branch_ = std::getenv("FG_NO_HALO_BRANCH") == nullptr;   // A/B switch: boundary planes + push beside the IB kernels
+    bool halo_branch_ = std::getenv("FG_HALO_BRANCH") != nullptr;      // opt-in: boundary planes + push beside the IB kernels
+    bool halo_first_ = std::getenv("FG_HALO_FIRST") != nullptr;        // A/B: submit the branch before the IB kernels
     bool halo_branch_now_ = false;
     int *pair_ctr_ = nullptr;      // [1 + nz + 2] ticket + per-plane completion counters of StreamCollidePair
     bool split_ = false;           // this substep: far planes collide beside the IB kernels
