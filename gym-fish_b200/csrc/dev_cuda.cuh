@@ -316,7 +316,7 @@ public:
         lc.gridDim = grid; lc.blockDim = dim3(threads); lc.dynamicSmemBytes = 0; lc.stream = s_[cur_];
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributePriority;
-        at[0].val.priority = cur_ < 2 ? prio_high_ : prio_low_;
+        at[0].val.priority = (cur_ < 2 || cur_ >= 4) ? prio_high_ : prio_low_;
         lc.attrs = at; lc.numAttrs = 1;
         if (!ck(cudaLaunchKernelEx(&lc, kernel, p), "kernel launch")) return false;
         if (debug_sync_ && gmode_ == 0) return ck(cudaDeviceSynchronize(), "debug sync");

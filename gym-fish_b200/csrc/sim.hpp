@@ -378,18 +378,19 @@ public:
             // The collide of the other ("far") planes needs neither the force nor the marker upload, so it runs on a
             // low-priority branch BESIDE the IB kernels instead of after them.
             split_ = false; near_a_ = lo; near_b_ = hi;
-            // Halo branch (peered slabs with bodies; OPT-IN, FG_HALO_BRANCH=1): when no stencil reaches a boundary plane, the
-            // boundary planes need no IB force, so boundary planes -> halo push -> signal can run on their own high-priority
-            // stream BESIDE the IB kernels instead of between them and the near-plane collide.  Measured on two GPUs with one
-            // 256x128x128 channel + sphere each (gpu passes b7 / b8, 2000 steps): serial order 71 508 MLUPS, branch submitted
-            // before the IB kernels 67 386, after them 68 268 — slower with the one-cell kernels these slabs run; with the
-            // two-cell kernels 71 870 (serial: 67 574), a tie with the default.  Hence off by default; bit-identical either way
-            // (tests/test_slabs.py runs it under every stream-order policy of the emulation).
+            // Halo branch (peered slabs with bodies): when no stencil reaches a boundary plane, the boundary planes need no IB
+            // force, so boundary planes -> halo push -> signal run on their own high-priority stream (4, thin rows on 5) BESIDE
+            // the IB kernels instead of between them and the near-plane collide.  Default on slabs below 8 M cells, where that
+            // chain is as long as the interior collide beside it; FG_HALO_BRANCH=1 forces it on every slab, FG_NO_HALO_BRANCH=1
+            // turns it off.  Two GPUs, one 256x128x128 channel + sphere each, 2000 steps (gpu pass b10): serial order 71 650
+            // MLUPS (0.92 of two single GPUs); branch 75 200 with the one-cell kernels and 77 400 - 78 000 with the two-cell
+            // ones (0.99 - 1.00), which such a slab therefore runs while the branch is active (small_peered_slab()).
+            // Bit-identical either way (tests/test_slabs.py toggles it under every stream-order policy of the emulation).
             bool halo_branch = false;
             if (ib_on && !prof && !(cfg.flags & FG_FLAG_NO_SPLIT)) {
                 int a, b;
                 if (ib_.near_planes(a, b)) {
-                    halo_branch = overlap && halo_branch_ && ib_.boundary_planes_free(L_.nz);
+                    halo_branch = overlap && ib_.boundary_planes_free(L_.nz) && (halo_branch_ == 1 || (halo_branch_ < 0 && small_slab()));
                     a = std::min(std::max(a, lo), hi); b = std::max(std::min(b, hi), a);
                     // worth it when the far planes are at least a quarter of the slab and ~25 us of work (1 M cells)
                     const int far = (a - lo) + (hi - b);
@@ -740,13 +741,16 @@ private:
         if (L_.nx % (2 * kCollideThreads) == 0 || narrow_rows_log2() > 0) return kVecDefault;
         return 0;
     }
-    // Peered z-slabs below 8 M cells keep the one-cell kernels (at 8 CTAs/SM, launch_collide_pm): there the high-priority chain
-    // (neighbour flags -> IB kernels -> boundary planes -> halo push -> near planes) is as long as the interior collide beside
-    // it, and each of its ~12 dependent launches waits for a resident interior CTA to retire — 3.5 us for a one-cell CTA,
-    // 5.3 us for a two-cell one.  Two GPUs, 256x128x128 channel + sphere per GPU, 2000 steps (gpu pass b5): one-cell kernels
-    // 71 636 MLUPS, two-cell even / odd / both 69 062 / 69 993 / 67 574, one-cell at 9 CTAs/SM 68 957 — although the two-cell
-    // kernel itself is 5 % faster per launch (54.4 against 57.4 us).  On 512^3 slabs the chain is 1 % of the step.
-    bool small_peered_slab() const { return peers_ && slab_occ8_ && (long long)L_.plane * L_.nz < (8ll << 20); }
+    // Peered z-slabs below 8 M cells keep the one-cell kernels (at 8 CTAs/SM, launch_collide_pm) in substeps WITHOUT the halo
+    // branch (no bodies, or a body at a slab face): there the high-priority chain (neighbour flags -> IB kernels -> boundary
+    // planes -> halo push -> near planes) is as long as the interior collide beside it, and each of its ~12 dependent launches
+    // waits for a resident interior CTA to retire — 3.5 us for a one-cell CTA, 5.3 us for a two-cell one.  Two GPUs,
+    // 256x128x128 channel + sphere per GPU, 2000 steps, serial chain (gpu pass b5): one-cell kernels 71 636 MLUPS, two-cell even /
+    // odd / both 69 062 / 69 993 / 67 574, one-cell at 9 CTAs/SM 68 957 — although the two-cell kernel itself is 5 % faster per
+    // launch (54.4 against 57.4 us).  With the halo branch the chain is four launches shorter and the order flips (pass b10:
+    // 75 200 one-cell, 77 400 two-cell).  On 512^3 slabs the chain is 1 % of the step.
+    bool small_slab() const { return (long long)L_.plane * L_.nz < (8ll << 20); }
+    bool small_peered_slab() const { return peers_ && slab_occ8_ && small_slab() && !halo_branch_now_; }
     // rows of 128 or 64 cells: a CTA of the two-cell kernels (256 cells) takes 2 or 4 consecutive rows of the launch, so the
     // 256x128x128 channel of BASELINE.json configs[1] runs the two-cell kernels as well; log2(rows per CTA), 0 otherwise
     int narrow_rows_log2() const {
@@ -1022,7 +1026,8 @@ private:
     int64_t collide_launches_ = 0, last_collide_launches_ = 0, collide_cells_ = 0, last_collide_cells_ = 0;
     int64_t split_substeps_ = 0, pair_substeps_ = 0;
     bool slab_occ8_ = std::getenv("FG_SLAB_OCC9") == nullptr;     // A/B switch for launch_collide_pm's small-slab rule
-    bool halo_branch_ = std::getenv("FG_HALO_BRANCH") != nullptr;      // opt-in: boundary planes + push beside the IB kernels
+    // boundary planes + push beside the IB kernels: 1 forced on (FG_HALO_BRANCH), 0 off (FG_NO_HALO_BRANCH), -1 the default (small slabs)
+    int halo_branch_ = std::getenv("FG_NO_HALO_BRANCH") ? 0 : (std::getenv("FG_HALO_BRANCH") ? 1 : -1);
     bool halo_first_ = std::getenv("FG_HALO_FIRST") != nullptr;        // A/B: submit the branch before the IB kernels
     bool halo_branch_now_ = false;
     int *pair_ctr_ = nullptr;      // [1 + nz + 2] ticket + per-plane completion counters of StreamCollidePair

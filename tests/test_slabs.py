@@ -113,12 +113,11 @@ def test_plane_split_on_peered_slabs(g, emu, overlap, split, halo_branch, monkey
     """Plane split + z-slabs: on each rank the interior planes away from its body collide before the rank even waits
     for its neighbours' halos (sim.hpp step()).  Each slab holds a moving sphere; populations must equal the unsplit,
     un-decomposed run bit for bit (the emulation adds in a fixed order).
-    Halo branch (opt-in, FG_HALO_BRANCH=1): while no stencil reaches a boundary plane, boundary planes -> halo push -> signal
+    Halo branch (the default on small slabs; FG_HALO_BRANCH / FG_NO_HALO_BRANCH force it on / off): while no stencil reaches a boundary plane, boundary planes -> halo push -> signal
     run on their own stream beside the IB kernels; the spheres drift towards the slab faces, so the last steps fall back to
     the serial order — with split=False the substeps are captured as graphs (under FG_EMU_GRAPHS, tests/test_stream_order.py),
     and the branch is part of the graph key (removing it from the key fails this test)."""
-    if halo_branch:
-        monkeypatch.setenv("FG_HALO_BRANCH", "1")      # read when the handle is created
+    monkeypatch.setenv("FG_HALO_BRANCH" if halo_branch else "FG_NO_HALO_BRANCH", "1")      # read when the handle is created
     P = g.BC_PERIODIC
     kw = dict(nx=12, ny=10, nz=64, tau=0.8, collision=g.MRT, max_markers=400, max_links=2, bc=[P] * 6, body_force=[0, 0, 2e-5])
     whole = g.Sim(backend=emu, flags=g._abi.FLAG_NO_SPLIT, **kw)
