@@ -69,9 +69,9 @@ extern "C" {
 #define FG_FLAG_SYNC_STEP 256  /* fg_step returns only when all its device work has finished (default: when wrenches / obs are there) */
 #define FG_FLAG_IB_TILE_SPREAD 512 /* A/B: force spreading staged per CTA in a shared-memory table keyed by band cell, one global reduction per touched cell (default: one red.add per stencil node); pays only for spatially ordered marker lists (profiles/r2_summary.md) */
 #define FG_FLAG_EVEN_VEC4 1024 /* even steps take 4 cells per thread with 128-bit loads / stores (needs nx % 4 == 0, no obstacles); measured +1.3 ... +2.4 %, less than the 2-cell form (profiles/r2_summary.md) */
-#define FG_FLAG_EVEN_VEC2 2048 /* ... 2 cells per thread with 64-bit accesses for any even nx (the DEFAULT when nx is a multiple of 256: +2.6 ... +3.2 %) */
+#define FG_FLAG_EVEN_VEC2 2048 /* ... 2 cells per thread with 64-bit accesses for any even nx (the DEFAULT when nx is a multiple of 256 or 128 / 64: +2.6 ... +3.2 %) */
 #define FG_FLAG_EVEN_SCALAR 8192 /* even steps with the scalar one-cell-per-thread kernel everywhere (A/B against the default) */
-#define FG_FLAG_ODD_VEC2 16384 /* bulk odd steps (periodic x, no obstacles) with 2 cells per thread, 64-bit accesses for the 9 slots with c_x = 0, for any even nx (the DEFAULT when nx is a multiple of 256: +2.6 ... +3.9 %) */
+#define FG_FLAG_ODD_VEC2 16384 /* bulk odd steps (x periodic or between walls, no obstacles) with 2 cells per thread, 64-bit accesses for the 9 slots with c_x = 0, for any even nx (the DEFAULT when nx is a multiple of 256 or 128 / 64: +2.6 ... +3.9 %) */
 #define FG_FLAG_ODD_SCALAR 32768 /* bulk odd steps with the one-cell-per-thread kernel everywhere (A/B against the default) */
 #define FG_FLAG_NO_SPLIT  16   /* collide all planes after the IB kernels (default: planes away from the bodies run beside them) */
 
