@@ -738,6 +738,11 @@ private:
         // +2.6 ... +3.2 % MLUPS on 256- and 512-wide lattices (fewer memory instructions per byte; the 4-cell form gains
         // less: 125 registers leave 4 CTAs per SM).  Narrower rows would leave half of each CTA idle and keep the scalar kernel.
         if (small_peered_slab()) return 0;
+#if defined(FG_POP16)
+        // the 16-bit build is issue-bound: four cells per thread (64-bit accesses) where rows fill whole CTAs that way
+        // (512^3, 100 steps, gpu pass b14: 61 922 against 58 617 MLUPS with two cells)
+        if (kVecDefault != 0 && L_.nx % (4 * kCollideThreads) == 0) return 4;
+#endif
         if (L_.nx % (2 * kCollideThreads) == 0 || narrow_rows_log2() > 0) return kVecDefault;
         return 0;
     }

@@ -116,7 +116,8 @@ def _vec_forms_equal_scalar(g, backend, shape_kw):
         ref.step(9)
         f = ref.get_populations()
         ref.close()
-        for flags in (A.FLAG_EVEN_VEC2 | A.FLAG_ODD_VEC2, A.FLAG_EVEN_VEC4 | A.FLAG_ODD_SCALAR, A.FLAG_EVEN_SCALAR | A.FLAG_ODD_VEC2):
+        # 0: the build's own defaults (two cells per thread, four in the even step where nx % 512 == 0)
+        for flags in (0, A.FLAG_EVEN_VEC2 | A.FLAG_ODD_VEC2, A.FLAG_EVEN_VEC4 | A.FLAG_ODD_SCALAR, A.FLAG_EVEN_SCALAR | A.FLAG_ODD_VEC2):
             s = g.Sim(backend=backend, flags=flags, **kw)
             s.set_fields(rho, u)
             s.step(9)
@@ -126,8 +127,10 @@ def _vec_forms_equal_scalar(g, backend, shape_kw):
 
 def test_f16_storage_vector_kernels_equal_scalar_emulated(g, emu_f16):
     _vec_forms_equal_scalar(g, emu_f16, dict(nx=16, ny=6, nz=8))
+    _vec_forms_equal_scalar(g, emu_f16, dict(nx=512, ny=4, nz=4))       # rows on which the defaults are the vector kernels
 
 
 @pytest.mark.gpu
 def test_f16_storage_vector_kernels_equal_scalar_gpu(g, cuda_f16):
     _vec_forms_equal_scalar(g, cuda_f16, dict(nx=256, ny=10, nz=12))
+    _vec_forms_equal_scalar(g, cuda_f16, dict(nx=512, ny=6, nz=8))

@@ -299,6 +299,52 @@ def test_two_slabs_on_one_gpu_equal_unsplit(g, cuda):
         s.close()
 
 
+@pytest.mark.parametrize("branch", ["default", "off", "forced_first"])
+def test_halo_branch_on_two_peered_slabs_with_bodies(g, cuda, branch, monkeypatch):
+    """Peered slabs with a body inside each: while no stencil reaches a boundary plane, boundary planes -> halo push -> signal run
+    on their own high-priority stream beside the IB kernels (sim.hpp step(), the default on slabs below 8 M cells, which then
+    run the two-cell kernels).  128-wide rows (NARROW two-cell kernels), y walls (thin rows on the branch's second stream),
+    spheres that drift to the slab faces so that the last steps fall back to the serial chain; with and without the plane
+    split.  Against the unsplit handle: populations within the order of the spreading atomics, wrenches within 1e-6 relative."""
+    if branch == "off":
+        monkeypatch.setenv("FG_NO_HALO_BRANCH", "1")
+    elif branch == "forced_first":
+        monkeypatch.setenv("FG_HALO_BRANCH", "1")
+        monkeypatch.setenv("FG_HALO_FIRST", "1")
+    P, Wl = g.BC_PERIODIC, g.BC_WALL
+    for split_min in (1, 1 << 30):
+        kw = dict(nx=128, ny=12, nz=64, tau=0.8, collision=g.MRT, max_markers=400, max_links=2, bc=[P, P, Wl, Wl, P, P], body_force=[0, 0, 2e-5])
+        whole = g.Sim(backend=cuda, flags=g._abi.FLAG_NO_SPLIT, **kw)
+        parts = [g.Sim(backend=cuda, n_ranks=2, rank=r, split_min_cells=split_min, **kw) for r in range(2)]
+        rho, u = util.smooth_fields(whole.shape, amp=0.01)
+        whole.set_fields(rho, u)
+        for r, s in enumerate(parts):
+            s.set_fields(rho[32 * r:32 * r + 32], u[:, 32 * r:32 * r + 32])
+        h = [s.peer_export() for s in parts]
+        parts[0].peer_connect(h[1], h[1])
+        parts[1].peer_connect(h[0], h[0])
+        for it in range(11):
+            Xa = util.sphere_markers((60.2, 6.1, 8.3 + 1.85 * it), 2.5, 100)         # reaches slab 0's top plane at the end
+            Xb = util.sphere_markers((70.7, 5.6, 56.1 - 2.0 * it), 2.5, 100)         # reaches slab 1's bottom plane at the end
+            U = np.zeros((100, 3), np.float32)
+            U[:, 2] = 0.01
+            one = np.ones(100, np.float32)
+            whole.set_markers(np.concatenate([Xa, Xb]), np.concatenate([U, -U]), np.ones(200, np.float32), np.array([0] * 100 + [1] * 100, np.int32))
+            parts[0].set_markers(Xa, U, one, np.zeros(100, np.int32))
+            parts[1].set_markers(Xb, -U, one, np.zeros(100, np.int32))
+            whole.step(1)
+            for s in parts:
+                s.step(1)
+        f = whole.get_populations()
+        fs = np.concatenate([s.get_populations() for s in parts], axis=1)
+        assert np.abs(f - fs).max() < 5e-7, (branch, split_min)
+        w = whole.get_link_wrenches()
+        ws = np.stack([parts[0].get_link_wrenches()[0], parts[1].get_link_wrenches()[0]])
+        assert np.abs(w[:2] - ws).max() <= 1e-6 * np.abs(w).max() + 1e-12
+        for s in parts + [whole]:
+            s.close()
+
+
 def test_velocity_probes_match_oracle_on_gpu(g, cuda):
     P, Wl = g.BC_PERIODIC, g.BC_WALL
     kw = dict(nx=14, ny=12, nz=10, tau=0.8, collision=g.MRT, bc=[P, P, Wl, Wl, P, P], body_force=[1e-4, 0, 1e-4])
