@@ -65,11 +65,31 @@ def random_case(g, rng):
     return kw, solid, markers
 
 
-def run_case(g, backend, seed):
+def widen(g, rng, kw, solid, markers):
+    """The same random configuration on rows where the two-cell kernels run: nx = 64 / 128 / 256 (their defaults: NARROW rows
+    and whole CTAs) or another even width with the forms forced by flag; few rows and planes so that a case stays cheap."""
+    A = g._abi
+    nx = int(rng.choice([64, 128, 256, 2 * int(rng.integers(2, 40))]))
+    ny, nz = min(kw["ny"], 5), min(kw["nz"], 5)
+    old = (kw["nx"], kw["ny"], kw["nz"])
+    kw = dict(kw, nx=nx, ny=ny, nz=max(nz, 2))
+    if nx not in (64, 128, 256):
+        kw["flags"] |= int(rng.choice([A.FLAG_EVEN_VEC2 | A.FLAG_ODD_VEC2, A.FLAG_EVEN_VEC2, A.FLAG_ODD_VEC2, A.FLAG_EVEN_VEC4 if nx % 4 == 0 else A.FLAG_ODD_VEC2]))
+    if solid is not None:
+        solid = (rng.random((kw["nz"], ny, nx)) < 0.05).astype(np.uint8) if rng.random() < 0.3 else None   # obstacles: mostly off (they force the checked kernels)
+    if markers is not None:
+        X = (markers[0] / np.array(old, np.float32) * np.array([nx, ny, kw["nz"]], np.float32)).astype(np.float32)
+        markers = (X,) + tuple(markers[1:])
+    return kw, solid, markers
+
+
+def run_case(g, backend, seed, wide=False):
     """Worst absolute differences to the oracle over 5 checkpoints (9 steps, both parities), or None if the random
     configuration is not a stable simulation (the comparison of two diverging runs means nothing)."""
     rng = np.random.default_rng(seed)
     kw, solid, markers = random_case(g, rng)
+    if wide:
+        kw, solid, markers = widen(g, np.random.default_rng(10 ** 6 + seed), kw, solid, markers)
     a, b = g.Sim(backend="oracle", **kw), g.Sim(backend=backend, **kw)
     rho, u = util.smooth_fields(a.shape)
     rho = (rho + 0.003 * rng.standard_normal(a.shape)).astype(np.float32)
@@ -111,10 +131,10 @@ def run_case(g, backend, seed):
 LIMITS = dict(u=3e-6, rho=3e-6, f=1e-6, index_map=0.5, band=0.5, Fm=2e-5, wrench=1e-4)
 
 
-def check(g, backend, seeds):
+def check(g, backend, seeds, wide=False):
     bad, ran = [], 0
     for seed in seeds:
-        worst, kw = run_case(g, backend, seed)
+        worst, kw = run_case(g, backend, seed, wide)
         if worst is None:
             continue
         ran += 1
@@ -128,6 +148,11 @@ def test_random_configurations_emulated_kernels_vs_oracle(g, emu):
     check(g, emu, range(400))
 
 
+def test_random_configurations_on_wide_rows_emulated_kernels_vs_oracle(g, emu):
+    """The two-cell kernels (whole CTAs, NARROW rows, x walls, forced by flag on other even widths) under the random generator."""
+    check(g, emu, range(150), wide=True)
+
+
 @pytest.mark.parametrize("seed", [4, 36, 132, 17, 53, 268])
 def test_outlet_next_to_obstacles_regression(g, emu, seed):
     """Seeds that failed before the ZFaceOp fix: a zero-gradient outlet (or inlet / periodic wrap) whose boundary plane or
@@ -139,6 +164,7 @@ def test_outlet_next_to_obstacles_regression(g, emu, seed):
 @pytest.mark.gpu
 def test_random_configurations_cuda_vs_oracle(g, cuda):
     check(g, cuda, range(1000, 1150))
+    check(g, cuda, range(2000, 2150), wide=True)
 
 
 def run_slab_case(g, emu, seed):

@@ -2,6 +2,7 @@
 """Run the randomised test generators of tests/test_random_cases.py over any seed range (CPU emulation by default).
 
     python tools/fuzz.py static 0 2000                  # random configurations vs the oracle
+    python tools/fuzz.py wide 0 2000                    # the same on rows where the two-cell kernels run (nx = 64 / 128 / 256, forced forms)
     python tools/fuzz.py moving|fish|api|slabs|xslabs 0 500
     FG_EMU_SCHED=rand:3 FG_EMU_GRAPHS=1 python tools/fuzz.py slabs 0 500     # queued streams, emulated graphs
     python tools/fuzz.py static 0 500 --lib cuda        # the real library on a GPU box
@@ -22,8 +23,8 @@ kind, lo, hi = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
 lib = sys.argv[sys.argv.index("--lib") + 1] if "--lib" in sys.argv else os.path.join(ROOT, "tests", "emu", "libfishgym_emu.so")
 bad, ran = [], 0
 for seed in range(lo, hi):
-    if kind == "static":
-        w, kw = t.run_case(g, lib, seed)
+    if kind in ("static", "wide"):
+        w, kw = t.run_case(g, lib, seed, wide=kind == "wide")
         ok = None if w is None else all(w[k] <= t.LIMITS[k] for k in w)
     elif kind == "moving":
         w, kw, _, _ = t.run_moving_markers_case(g, lib, seed)
