@@ -682,8 +682,7 @@ public:
         per_[0] = cfg.bc[FG_XLO] == FG_BC_PERIODIC; per_[1] = cfg.bc[FG_YLO] == FG_BC_PERIODIC; per_[2] = cfg.bc[FG_ZLO] == FG_BC_PERIODIC;
         auto A = [&](size_t bytes) { void *p = dev.alloc(bytes, err); if (p && !dev.zero(p, bytes)) { err = dev.err; p = nullptr; } return p; };
         cap_pad_ = cfg.n_ranks > 1 ? (cap_ + kPad - 1) / kPad * kPad : cap_;
-        nzl_ = L.nz; nzg_ = L.nzg; ny_ = L.ny;
-        yocc_.assign(size_t(ny_), 0);
+        nzl_ = L.nz; nzg_ = L.nzg;
         msg_floats_ = 9 * size_t(cap_pad_) + 3 * size_t(maxl_);
         dmsg_ = (float *)A(sizeof(float) * msg_floats_);
         dbase_ = (int *)A(sizeof(int) * 3 * cap_pad_); downer_ = (int *)A(sizeof(int) * cap_pad_);
@@ -740,53 +739,16 @@ public:
     void update_range(int n, const float *X) {
         int kmin = 0x7fffffff, kmax = -0x7fffffff;
         const int z0 = rank_ * nzl_;
-        std::fill(yocc_.begin(), yocc_.end(), uint8_t(0));
         for (int k = 0; k < n; ++k) {
             const int k0 = int(std::floor(X[3 * k + 2])) - 1;
             if (xchg_ && slab_of(k0) != rank_ && slab_of(k0 + 3) != rank_) continue;
             kmin = std::min(kmin, k0); kmax = std::max(kmax, k0 + 3);
-            // rows (y) of this marker's stencil, wrapped on a periodic axis, clipped otherwise
-            const int j0 = int(std::floor(X[3 * k + 1])) - 1;
-            for (int b = 0; b < 4; ++b) {
-                int y = j0 + b;
-                if (y < 0 || y >= ny_) {
-                    if (!per_[1]) continue;
-                    y %= ny_;
-                    if (y < 0) y += ny_;
-                }
-                yocc_[size_t(y)] = 1;
-            }
         }
         z_any_ = kmin <= kmax;
         z_all_ = z_any_ && per_[2] && (kmin < 0 || kmax >= nzg_);
         if (!z_any_) { zmin_ = 1; zmax_ = 0; return; }        // no stencil on this slab
         zmin_ = std::max(kmin, z0) - z0 + 1;
         zmax_ = std::min(kmax, z0 + nzl_ - 1) - z0 + 1;
-    }
-    // Rows (y) that contain every cell the IB kernels of this step read or write, as at most kMaxBands bands [a, b) (one row
-    // of margin, snapped outwards to multiples of 4, bands closer than 16 rows merged): the collide of all OTHER rows may run
-    // beside the IB kernels — the same ownership argument as for near_planes(), along y instead of z.  A school of fish that
-    // swim along z fills every plane of a slab but only a few bands of rows.  false: no marker on this slab, or too many bands.
-    static constexpr int kMaxBands = 4;
-    bool near_rows(int (&bands)[kMaxBands][2], int &nb, int &rows_near) const {
-        nb = 0; rows_near = 0;
-        if (!z_any_) return false;
-        int a = -1;
-        for (int y = 0; y <= ny_; ++y) {
-            const bool occ = y < ny_ && yocc_[size_t(y)];
-            if (occ && a < 0) a = y;
-            if (!occ && a >= 0) {
-                int lo = std::max(0, (a - 1) / 4 * 4), hi = std::min(ny_, (y + 1 + 3) / 4 * 4);
-                if (nb > 0 && lo - bands[nb - 1][1] < 16) bands[nb - 1][1] = hi;      // merge with the previous band
-                else {
-                    if (nb == kMaxBands) return false;
-                    bands[nb][0] = lo; bands[nb][1] = hi; ++nb;
-                }
-                a = -1;
-            }
-        }
-        for (int i = 0; i < nb; ++i) rows_near += bands[i][1] - bands[i][0];
-        return nb > 0;
     }
     // planes [za, zb) contain every cell the IB kernels of this step read or write.  In the AA pattern every storage
     // location is read and written by exactly ONE cell per step, and IbBandMoments reads precisely the locations its
@@ -1150,8 +1112,7 @@ private:
         if (kc < 0) kc = k0 + 1 < 0 ? 0 : nzg_ - 1;
         return kc / nzl_;
     }
-    int cap_pad_ = 0, n_total_ = 0, nzl_ = 1, nzg_ = 1, ny_ = 1;
-    std::vector<uint8_t> yocc_;    // rows touched by this rank's marker stencils (update_range)
+    int cap_pad_ = 0, n_total_ = 0, nzl_ = 1, nzg_ = 1;
     std::vector<int> act_;
     std::vector<float> hX_;
     int cur_ = 0, stage_next_ = 0;

@@ -397,28 +397,6 @@ public:
                     if (far * 4 >= hi - lo && (long long)far * L_.plane >= (cfg.split_min_cells > 0 ? cfg.split_min_cells : (1 << 20))) { split_ = true; near_a_ = a; near_b_ = b; }
                 }
             }
-            // Row split: the same idea along y.  A school of fish swimming along z leaves no plane of a slab free, but its
-            // stencils touch only a few bands of rows; the collide of all other rows (every plane) is then the far branch.
-            // Taken when it leaves clearly more cells far than the plane split does.
-            row_split_ = false;
-            if (ib_on && !prof && !(cfg.flags & FG_FLAG_NO_SPLIT) && row_split_on_) {
-                int nb = 0, rows_near = 0;
-                if (ib_.near_rows(near_bands_, nb, rows_near)) {
-                    const long long far_rows = (long long)(L_.ny - rows_near) * L_.nx * (hi - lo);
-                    const long long far_planes = split_ ? (long long)((near_a_ - lo) + (hi - near_b_)) * L_.plane : 0;
-                    if ((L_.ny - rows_near) * 4 >= L_.ny && far_rows >= (cfg.split_min_cells > 0 ? cfg.split_min_cells : (1 << 20)) &&
-                        far_rows > far_planes + far_planes / 8) {
-                        row_split_ = true; split_ = true; near_a_ = lo; near_b_ = hi; n_near_bands_ = nb;
-                        n_far_ranges_ = 0;
-                        int at = 0;
-                        for (int i = 0; i <= nb; ++i) {                 // the complement of the bands
-                            const int end = i < nb ? near_bands_[i][0] : L_.ny;
-                            if (end > at) { far_ranges_[n_far_ranges_][0] = at; far_ranges_[n_far_ranges_][1] = end; ++n_far_ranges_; }
-                            if (i < nb) at = near_bands_[i][1];
-                        }
-                    }
-                }
-            }
             halo_branch_now_ = halo_branch;     // part of the substep's graph key: it changes the captured sequence
             // Peered z-slabs WITHOUT bodies: nothing waits for a force, so every interior plane is "far" — the interior
             // collide goes to the low-priority branch and the high-priority chain (wait for the neighbours' flags ->
@@ -465,9 +443,7 @@ public:
             if (ranks && peers_ && !overlap && !dev.wait_flags(flags_, has_lo_peer(), has_hi_peer())) return cuda_fail();
             if (split_) {
                 ++split_substeps_;
-                if (!dev.fork_to(2)) return cuda_fail();
-                if (!(row_split_ ? launch_collide_rows(lo, hi, ForceField{}, far_ranges_, n_far_ranges_) : launch_collide(lo, hi, ForceField{}, 1, near_a_, near_b_))) return cuda_fail();
-                if (!dev.switch_to(0)) return cuda_fail();
+                if (!dev.fork_to(2) || !launch_collide(lo, hi, ForceField{}, 1, near_a_, near_b_) || !dev.switch_to(0)) return cuda_fail();
             }
             if (!fish_.empty()) {
                 if (int rc = upload_bodies()) return rc;
@@ -496,7 +472,7 @@ public:
                 // boundary planes first, push halos over NVLink, then the interior hides the exchange
                 if (!launch_boundary_planes(F) || !launch_faces()) return cuda_fail();
             }
-            if (!(row_split_ ? launch_collide_rows(lo, hi, F, near_bands_, n_near_bands_) : launch_collide(near_a_, near_b_, F))) return cuda_fail();
+            if (!launch_collide(near_a_, near_b_, F)) return cuda_fail();
             if (split_ && !dev.join_from(2)) return cuda_fail();
             if (halo_branch && !dev.join_from(4)) return cuda_fail();
             if (!overlap && !launch_faces()) return cuda_fail();
@@ -882,10 +858,7 @@ private:
         }
         if (zz_end <= zz_begin) return true;
         const int ny = L_.ny;
-        // rows [ya, yb) of every plane: all of them, or the range a row split restricts this launch to (yr_a_, yr_b_)
-        const int ya = yr_b_ >= 0 ? yr_a_ : 0, yb = yr_b_ >= 0 ? yr_b_ : ny;
-        if (yb <= ya) return true;
-        if (L_.solid || parity_ == 0) return launch_rows(CHECK_ALL, zz_begin, zz_end, ya, 1, yb - ya, F, zstride, hole_b, hole_e, true);
+        if (L_.solid || parity_ == 0) return launch_rows(CHECK_ALL, zz_begin, zz_end, 0, 1, ny, F, zstride, hole_b, hole_e, true);
         const bool zlo_wall = L_.bc_zlo == BC_WALL && L_.z0 == 0, zhi_wall = L_.bc_zhi == BC_WALL && L_.z0 + L_.nz == L_.nzg;
         if (hole_e > hole_b && (zlo_wall || zhi_wall))   // wall planes are peeled off the ends below: keep that logic hole-free
             return launch_collide(zz_begin, hole_b, F) && launch_collide(hole_e, zz_end, F);
@@ -894,35 +867,20 @@ private:
         // The launches below touch disjoint cells, so the thin checked ones run on a forked stream (parallel
         // graph branches) while the bulk runs on the current one.
         const int base = dev.current();
-        const bool wy = L_.wall_y && ny >= 2;
-        const bool row0 = wy && ya == 0, rowN = wy && yb == ny;          // the y-wall rows inside the range
-        const bool thin = (zlo_wall && zb <= 1 && 1 < ze) || (zhi_wall && zb <= L_.nz && L_.nz < ze) || row0 || rowN;
+        const bool thin = (zlo_wall && zb <= 1 && 1 < ze) || (zhi_wall && zb <= L_.nz && L_.nz < ze) || (L_.wall_y && ny >= 2);
         if (thin) ok = dev.fork_to(base + 1);
-        if (zlo_wall && zb <= 1 && 1 < ze) { ok = ok && launch_rows(CHECK_ALL, 1, 2, ya, 1, yb - ya, F); zb = 2; }
-        if (zhi_wall && zb <= L_.nz && L_.nz < ze) { ok = ok && launch_rows(CHECK_ALL, L_.nz, L_.nz + 1, ya, 1, yb - ya, F); ze = L_.nz; }
+        if (zlo_wall && zb <= 1 && 1 < ze) { ok = ok && launch_rows(CHECK_ALL, 1, 2, 0, 1, ny, F); zb = 2; }
+        if (zhi_wall && zb <= L_.nz && L_.nz < ze) { ok = ok && launch_rows(CHECK_ALL, L_.nz, L_.nz + 1, 0, 1, ny, F); ze = L_.nz; }
         const int bulk = L_.wall_x ? ((cfg.flags & FG_FLAG_NO_XWARP) ? CHECK_XEDGE : CHECK_XWARP) : CHECK_NONE;
-        if (wy) {
-            if (row0 && rowN) ok = ok && launch_rows(CHECK_ALL, zb, ze, 0, ny - 1, 2, F, zstride, hole_b, hole_e);
-            else if (row0) ok = ok && launch_rows(CHECK_ALL, zb, ze, 0, 1, 1, F, zstride, hole_b, hole_e);
-            else if (rowN) ok = ok && launch_rows(CHECK_ALL, zb, ze, ny - 1, 1, 1, F, zstride, hole_b, hole_e);
+        if (L_.wall_y && ny >= 2) {
+            ok = ok && launch_rows(CHECK_ALL, zb, ze, 0, ny - 1, 2, F, zstride, hole_b, hole_e);
             if (thin) ok = ok && dev.switch_to(base);
-            const int b0 = row0 ? 1 : ya, b1 = rowN ? ny - 1 : yb;
-            ok = ok && launch_rows(bulk, zb, ze, b0, 1, b1 - b0, F, zstride, hole_b, hole_e, true);
+            ok = ok && launch_rows(bulk, zb, ze, 1, 1, ny - 2, F, zstride, hole_b, hole_e, true);
         } else {
             if (thin) ok = ok && dev.switch_to(base);
-            ok = ok && launch_rows(L_.wall_y ? CHECK_ALL : bulk, zb, ze, ya, 1, yb - ya, F, zstride, hole_b, hole_e, true);
+            ok = ok && launch_rows(L_.wall_y ? CHECK_ALL : bulk, zb, ze, 0, 1, ny, F, zstride, hole_b, hole_e, true);
         }
         if (thin) ok = dev.join_from(base + 1) && ok;
-        return ok;
-    }
-    // the same over a set of row ranges (row split: the far rows, or the near bands)
-    bool launch_collide_rows(int zz_begin, int zz_end, const ForceField &F, const int (*ranges)[2], int n) {
-        bool ok = true;
-        for (int i = 0; i < n && ok; ++i) {
-            yr_a_ = ranges[i][0]; yr_b_ = ranges[i][1];
-            ok = launch_collide(zz_begin, zz_end, F);
-        }
-        yr_a_ = 0; yr_b_ = -1;
         return ok;
     }
 
@@ -1078,11 +1036,6 @@ private:
     bool halo_first_ = std::getenv("FG_HALO_FIRST") != nullptr;        // A/B: submit the branch before the IB kernels
     bool halo_branch_now_ = false;
     int *pair_ctr_ = nullptr;      // [1 + nz + 2] ticket + per-plane completion counters of StreamCollidePair
-    int yr_a_ = 0, yr_b_ = -1;     // launch_collide: rows [yr_a_, yr_b_) only (yr_b_ < 0: every row)
-    bool row_split_ = false;       // this substep's split is along y (rows) instead of z (planes)
-    int near_bands_[IbState<Dev>::kMaxBands][2] = {}, far_ranges_[IbState<Dev>::kMaxBands + 1][2] = {};
-    int n_near_bands_ = 0, n_far_ranges_ = 0;
-    bool row_split_on_ = std::getenv("FG_NO_ROW_SPLIT") == nullptr;     // A/B switch
     bool split_ = false;           // this substep: far planes collide beside the IB kernels
     int near_a_ = 1, near_b_ = 1;  // planes [near_a_, near_b_) wait for the IB force
     uint8_t *solid_ = nullptr;

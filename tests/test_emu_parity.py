@@ -351,45 +351,3 @@ def test_two_cell_kernels_on_narrow_rows_take_several_rows_per_cta(g, emu, nx):
             s.step(7)
         assert np.array_equal(a.get_populations(), b.get_populations()), name
         assert util.rel_l2(a.get_fields(f64=True)[1], o.get_fields(f64=True)[1]) <= TOL_FIELD
-
-
-@pytest.mark.parametrize("case", ["periodic_two_bands", "ywalls_band_at_wall", "periodic_y_wrap", "xy_walls_inlet"])
-def test_row_split_matches_unsplit_and_oracle(g, emu, case):
-    """Row split (sim.hpp step(), IbState::near_rows): bodies that span every plane but only a few bands of rows — the collide
-    of all OTHER rows runs beside the IB kernels.  The emulation runs the far rows FIRST here and after the near rows without
-    the split, so equal bits prove the independence; against the oracle within the parity bar.  Two bands, a band at a y wall
-    (thin wall row inside a near band), a band that wraps around the periodic y axis, x + y walls with inlet / outlet."""
-    P, Wl, IN, OUT = g.BC_PERIODIC, g.BC_WALL, g.BC_INLET, g.BC_OUTLET
-    kw = dict(nx=14, ny=48, nz=12, tau=0.8, collision=g.MRT, max_markers=600, max_links=2, split_min_cells=1, body_force=[0, 0, 2e-5])
-    if case == "periodic_two_bands":
-        rods = [(7.2, 10.3), (6.1, 33.6)]
-    elif case == "ywalls_band_at_wall":
-        kw.update(bc=[P, P, Wl, Wl, P, P]); rods = [(7.2, 2.2), (6.1, 30.0)]
-    elif case == "periodic_y_wrap":
-        rods = [(7.2, 0.4)]
-    else:
-        kw.update(bc=[Wl, Wl, Wl, Wl, IN, OUT], inlet_u=[0, 0, 0.03], body_force=[0, 0, 0]); rods = [(7.2, 20.3)]
-    sims = [g.Sim(backend="oracle", **kw), g.Sim(backend=emu, **kw), g.Sim(backend=emu, flags=g._abi.FLAG_NO_SPLIT, **kw)]
-    rho, u = util.smooth_fields(sims[0].shape, amp=0.01)
-    for s in sims:
-        s.set_fields(rho, u)
-    for it in range(7):
-        X = np.concatenate([util.rod_markers(xc + 0.15 * it, yc + 0.35 * it, 0.3, 11.9) for xc, yc in rods])
-        link = np.concatenate([np.full(len(X) // len(rods), i, np.int32) for i in range(len(rods))])
-        U = np.zeros_like(X)
-        U[:, 1] = 0.01
-        for s in sims:
-            s.set_markers(X, U, np.full(len(X), 0.8, np.float32), link)
-            s.set_link_origins([[xc, yc, 6.0] for xc, yc in rods])
-            s.step(1)
-    for s in sims:
-        s.step(3)            # static reuse of the index map and band
-    o, a, b = sims
-    assert a.stats().split_substeps == 10 and b.stats().split_substeps == 0      # every plane holds band cells: only a ROW split can be taken
-    assert np.array_equal(a.get_populations(), b.get_populations())
-    assert np.array_equal(a.get_link_wrenches(), b.get_link_wrenches())
-    assert util.rel_l2(a.get_fields(f64=True)[1], o.get_fields(f64=True)[1]) <= TOL_FIELD
-    wa, wo = a.get_link_wrenches(), o.get_link_wrenches()
-    assert np.abs(wa - wo).max() / np.abs(wo).max() <= TOL_FORCE
-    (ba, oa), (bo, oo) = a.get_index_map(), o.get_index_map()
-    assert np.array_equal(ba, bo) and np.array_equal(oa, oo)

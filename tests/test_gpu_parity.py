@@ -521,43 +521,3 @@ def test_two_cell_kernels_on_narrow_rows_take_several_rows_per_cta(g, cuda, nx):
             s.step(6)
         assert np.abs(a.get_populations() - b.get_populations()).max() < 2e-7, name      # spreading atomics are unordered
         a.close(); b.close()
-
-
-@pytest.mark.parametrize("case", ["periodic_two_bands", "ywalls_band_at_wall", "xy_walls_inlet"])
-def test_row_split_matches_unsplit_and_oracle_on_gpu(g, cuda, case):
-    """Row split on the GPU (far rows of every plane on the low-priority stream beside the IB kernels): rods along z leave no
-    plane free, only rows.  Against FG_FLAG_NO_SPLIT within the order of the spreading atomics, against the oracle within the
-    parity bar; 128-wide rows so that the row ranges run the NARROW two-cell kernels (odd row counts per range included)."""
-    P, Wl, IN, OUT = g.BC_PERIODIC, g.BC_WALL, g.BC_INLET, g.BC_OUTLET
-    kw = dict(nx=128, ny=50, nz=12, tau=0.8, collision=g.MRT, max_markers=600, max_links=2, split_min_cells=1, body_force=[0, 0, 2e-5])
-    if case == "periodic_two_bands":
-        rods = [(60.2, 10.3), (70.1, 35.6)]
-    elif case == "ywalls_band_at_wall":
-        kw.update(bc=[P, P, Wl, Wl, P, P]); rods = [(60.2, 2.2), (70.1, 32.0)]
-    else:
-        kw.update(bc=[Wl, Wl, Wl, Wl, IN, OUT], inlet_u=[0, 0, 0.03], body_force=[0, 0, 0]); rods = [(60.2, 21.3)]
-    sims = [g.Sim(backend="oracle", **kw), g.Sim(backend=cuda, **kw), g.Sim(backend=cuda, flags=g._abi.FLAG_NO_SPLIT, **kw)]
-    rho, u = util.smooth_fields(sims[0].shape, amp=0.01)
-    for s in sims:
-        s.set_fields(rho, u)
-    for it in range(7):
-        X = np.concatenate([util.rod_markers(xc + 0.15 * it, yc + 0.35 * it, 0.3, 11.9) for xc, yc in rods])
-        link = np.concatenate([np.full(len(X) // len(rods), i, np.int32) for i in range(len(rods))])
-        U = np.zeros_like(X)
-        U[:, 1] = 0.01
-        for s in sims:
-            s.set_markers(X, U, np.full(len(X), 0.8, np.float32), link)
-            s.set_link_origins([[xc, yc, 6.0] for xc, yc in rods])
-            s.step(1)
-    for s in sims:
-        s.step(3)
-    o, a, b = sims
-    assert a.stats().split_substeps == 10 and b.stats().split_substeps == 0
-    assert np.abs(a.get_populations() - b.get_populations()).max() < 2e-7
-    assert util.rel_l2(a.get_fields(f64=True)[1], o.get_fields(f64=True)[1]) <= 1e-5
-    wa, wb, wo = a.get_link_wrenches(), b.get_link_wrenches(), o.get_link_wrenches()
-    assert np.abs(wa - wo).max() / np.abs(wo).max() <= 1e-4 and np.abs(wa - wb).max() / np.abs(wo).max() <= 1e-5
-    (ba, oa), (bo, oo) = a.get_index_map(), o.get_index_map()
-    assert np.array_equal(ba, bo) and np.array_equal(oa, oo)
-    for s in sims:
-        s.close()

@@ -284,43 +284,6 @@ def test_bodies_across_slab_faces_equal_unsplit(g, emu, n_ranks):
     assert set(np.unique(owner_p)) <= set(range(n_ranks)) and len(np.unique(owner_p)) >= 2
 
 
-@pytest.mark.parametrize("n_ranks", [2, 3])
-def test_row_split_on_peered_slabs_with_bodies_through_every_face(g, emu, n_ranks):
-    """Row split + fg_peer_connect_all: two rods along z run through every slab and around the periodic z boundary (the shape of a
-    school swimming along the swim axis), so no plane of any slab is free of band cells, but most rows are: on every rank the
-    far rows collide beside the IB kernels and their exchange.  Fields and wrenches as in the unsplit, un-decomposed run."""
-    nz = 12 * n_ranks
-    kw = dict(nx=14, ny=56, nz=nz, tau=0.8, collision=g.MRT, max_markers=1200, max_links=2, body_force=[0, 0, 2e-5])
-    whole = g.Sim(backend=emu, flags=g._abi.FLAG_NO_SPLIT, **kw)
-    parts = [g.Sim(backend=emu, n_ranks=n_ranks, rank=r, split_min_cells=1, **kw) for r in range(n_ranks)]
-    rho, u = util.smooth_fields(whole.shape, amp=0.01)
-    whole.set_fields(rho, u)
-    h = nz // n_ranks
-    handles = [s.peer_export() for s in parts]
-    for r, s in enumerate(parts):
-        s.set_fields(rho[r * h:(r + 1) * h], u[:, r * h:(r + 1) * h])
-        s.peer_connect_all(handles)
-    for it in range(5):
-        X = np.concatenate([util.rod_markers(7.2, 9.3 + 0.4 * it, 0.2, nz - 0.1), util.rod_markers(6.4, 42.1 - 0.3 * it, 0.2, nz - 0.1)])
-        link = np.concatenate([np.zeros(len(X) // 2, np.int32), np.ones(len(X) // 2, np.int32)])
-        U = np.zeros_like(X)
-        U[:, 1] = 0.01
-        for s in [whole] + parts:
-            s.set_markers(X, U, np.full(len(X), 0.8, np.float32), link)
-            s.set_link_origins([[7.2, 9.3, nz / 2], [6.4, 42.1, nz / 2]])
-        whole.step(2)
-        _run_threads([lambda s=s: s.step(2) for s in parts])
-    assert all(s.stats().split_substeps == 10 for s in parts) and whole.stats().split_substeps == 0
-    f = whole.get_populations()
-    fs = np.concatenate([s.get_populations() for s in parts], axis=1)
-    assert np.abs(f - fs).max() < 5e-7
-    w = whole.get_link_wrenches()
-    for s in parts:
-        ws = s.get_link_wrenches()
-        assert np.abs(ws - w).max() / np.abs(w).max() < 1e-5
-        assert np.array_equal(ws, parts[0].get_link_wrenches())
-
-
 def test_fish_swims_across_a_slab_face(g, emu):
     kw = dict(nx=20, ny=18, nz=48, tau=0.8, max_markers=4000, max_links=8)
     whole = g.Sim(backend=emu, **kw)

@@ -160,13 +160,3 @@ def cavity_vs_ghia(g, backend, n, steps, lid=0.1):
     du = np.abs(np.interp(GHIA_RE100_U[:, 0], at, ucl) - GHIA_RE100_U[:, 1]).max()
     dv = np.abs(np.interp(GHIA_RE100_V[:, 0], at, vcl) - GHIA_RE100_V[:, 1]).max()
     return float(du), float(dv), float(np.abs(u[2]).max())
-
-
-def rod_markers(xc, yc, z0, z1, radius=1.6, per_ring=10, spacing=0.9):
-    """A thin rod along z (rings of markers): its stencils touch every plane between z0 and z1 but only a narrow band of rows —
-    the shape of a fish swimming along the swim axis, for the row-split tests."""
-    zs = np.arange(z0, z1, spacing)
-    ph = 2 * np.pi * np.arange(per_ring) / per_ring
-    X = np.stack([(xc + radius * np.cos(ph))[None, :].repeat(len(zs), 0), (yc + radius * np.sin(ph))[None, :].repeat(len(zs), 0),
-                  zs[:, None].repeat(per_ring, 1)], -1).reshape(-1, 3)
-    return X.astype(np.float32)
