@@ -986,8 +986,16 @@ private:
             any = any || op.mode != BC_WALL;
         }
         if (any) {
-            Dim3 g{(L_.plane + ZFaceOp::kThreads - 1) / ZFaceOp::kThreads, 5, 2};
-            if (!dev.template launch<ZFaceOp>(g, p)) return false;
+            // plain copies of whole planes (periodic wrap, halo push; no x / y walls, no obstacles): four cells per thread
+            bool copies = !L_.wall_x && !L_.wall_y && !L_.solid && L_.plane % 4 == 0 && L_.slot % 4 == 0 && face_copy4_;
+            for (int s = 0; s < 2; ++s) copies = copies && (p.op[s].mode == BC_WALL || (p.op[s].mode == BC_PEER && !p.op[s].src_by_index));
+            if (copies) {
+                Dim3 g{int((L_.plane / 4 + ZFaceCopy4::kThreads - 1) / ZFaceCopy4::kThreads), 5, 2};
+                if (!dev.template launch<ZFaceCopy4>(g, p)) return false;
+            } else {
+                Dim3 g{(L_.plane + ZFaceOp::kThreads - 1) / ZFaceOp::kThreads, 5, 2};
+                if (!dev.template launch<ZFaceOp>(g, p)) return false;
+            }
         }
         if (peers_) {
             // publish "my halos of tick+1 are in your memory" to both neighbours
@@ -1033,6 +1041,7 @@ private:
     bool slab_occ8_ = std::getenv("FG_SLAB_OCC9") == nullptr;     // A/B switch for launch_collide_pm's small-slab rule
     // boundary planes + push beside the IB kernels: 1 forced on (FG_HALO_BRANCH), 0 off (FG_NO_HALO_BRANCH), -1 the default (small slabs)
     int halo_branch_ = std::getenv("FG_NO_HALO_BRANCH") ? 0 : (std::getenv("FG_HALO_BRANCH") ? 1 : -1);
+    bool face_copy4_ = std::getenv("FG_NO_FACE_COPY4") == nullptr;      // A/B switch: ZFaceCopy4 for plain plane copies
     bool halo_first_ = std::getenv("FG_HALO_FIRST") != nullptr;        // A/B: submit the branch before the IB kernels
     bool halo_branch_now_ = false;
     int *pair_ctr_ = nullptr;      // [1 + nz + 2] ticket + per-plane completion counters of StreamCollidePair
