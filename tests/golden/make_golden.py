@@ -19,13 +19,20 @@ import util  # noqa: E402
 util.register_oracle(g)
 
 STEPS = 11
-CASES = ["bgk_periodic", "mrt_force", "bgk_ywall_moving", "mrt_all_walls_lid", "mrt_inlet_outlet_ywalls", "mrt_ragged"]
+CASES = ["bgk_periodic", "mrt_force", "bgk_ywall_moving", "mrt_all_walls_lid", "mrt_inlet_outlet_ywalls", "mrt_ragged", "mrt_xwalls_moving"]
+# rows on which the library runs its two-cell kernels by default (round 2): whole CTAs between moving x walls, 128-wide NARROW rows
+WIDE = {"mrt_xwalls_moving_nx256": ("mrt_xwalls_moving", dict(nx=256, ny=6, nz=8)),
+        "mrt_inlet_outlet_ywalls_nx128": ("mrt_inlet_outlet_ywalls", dict(nx=128, ny=7, nz=8)),
+        "mrt_xy_walls_nx64": ("mrt_xy_walls", dict(nx=64, ny=9, nz=6))}
 
 
 def main():
     cases = util.parity_cases(g)
-    for name in CASES:
-        kw = cases[name]
+    only_missing = "--missing" in sys.argv      # add new fixtures without rewriting the committed ones
+    for name in CASES + list(WIDE):
+        if only_missing and os.path.exists(os.path.join(HERE, name + ".npz")):
+            continue
+        kw = dict(cases[WIDE[name][0]], **WIDE[name][1]) if name in WIDE else cases[name]
         s = g.Sim(backend="oracle", **kw)
         rho, u = util.smooth_fields(s.shape)
         s.set_fields(rho, u)
@@ -33,6 +40,8 @@ def main():
         r, v = s.get_fields(f64=True)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), rho=r, u=v, steps=STEPS)
         s.close()
+    if only_missing:
+        return
     # immersed boundary: sphere in a channel, 7 steps
     P, Wl, IN, OUT = g.BC_PERIODIC, g.BC_WALL, g.BC_INLET, g.BC_OUTLET
     kw = dict(nx=20, ny=18, nz=24, tau=0.8, collision=g.MRT, max_markers=512, max_links=1, bc=[P, P, Wl, Wl, IN, OUT], inlet_u=[0, 0, 0.05])

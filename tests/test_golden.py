@@ -10,11 +10,17 @@ import pytest
 import util
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = ["bgk_periodic", "mrt_force", "bgk_ywall_moving", "mrt_all_walls_lid", "mrt_inlet_outlet_ywalls", "mrt_ragged"]
+CASES = ["bgk_periodic", "mrt_force", "bgk_ywall_moving", "mrt_all_walls_lid", "mrt_inlet_outlet_ywalls", "mrt_ragged", "mrt_xwalls_moving",
+         "mrt_xwalls_moving_nx256", "mrt_inlet_outlet_ywalls_nx128", "mrt_xy_walls_nx64"]
+# fixtures on rows where the two-cell kernels are the default: (case of util.parity_cases, shape)
+WIDE = {"mrt_xwalls_moving_nx256": ("mrt_xwalls_moving", dict(nx=256, ny=6, nz=8)),
+        "mrt_inlet_outlet_ywalls_nx128": ("mrt_inlet_outlet_ywalls", dict(nx=128, ny=7, nz=8)),
+        "mrt_xy_walls_nx64": ("mrt_xy_walls", dict(nx=64, ny=9, nz=6))}
 
 
 def run_case(g, backend, name):
-    kw = util.parity_cases(g)[name]
+    cases = util.parity_cases(g)
+    kw = dict(cases[WIDE[name][0]], **WIDE[name][1]) if name in WIDE else cases[name]
     gold = np.load(os.path.join(GOLD, name + ".npz"))
     s = g.Sim(backend=backend, **kw)
     rho, u = util.smooth_fields(s.shape)
