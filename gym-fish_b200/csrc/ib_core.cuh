@@ -222,7 +222,7 @@ struct IbBandMoments {
         if (bx == 0 && tx == 0) *p.band_count_next = 0;       // the other counter is free again (IbClearBand has run)
         const int cnt = *p.band_count < p.band_cap ? *p.band_count : p.band_cap;
         const Lattice &L = p.L;
-        for (long long pos = (long long)bx * kThreads + tx; pos < cnt; pos += (long long)p.band_ctas * kThreads) {
+        for (long long pos = (long long)bx * kThreads + tx; pos < cnt; pos += (long long)(p.band_ctas > 0 ? p.band_ctas : 1) * kThreads) {
             const long long idx = p.band_cell[pos];
             const int x = int(idx % L.nx), y = int((idx / L.nx) % L.ny), zz = int(idx / L.plane);
             const Nbr nb = make_nbr(L, x, y, zz);
@@ -533,7 +533,7 @@ struct IbClearBand {
     static constexpr int kMinBlocks = 4;
     FG_HD static void run(const IbParams &p, int bx, int, int, int tx) {
         const int cnt = *p.band_count_next < p.band_cap ? *p.band_count_next : p.band_cap;   // the previous step's counter
-        for (long long pos = (long long)bx * kThreads + tx; pos < cnt; pos += (long long)p.band_ctas * kThreads) {
+        for (long long pos = (long long)bx * kThreads + tx; pos < cnt; pos += (long long)(p.band_ctas > 0 ? p.band_ctas : 1) * kThreads) {
             const long long idx = p.band_cell[pos];
             p.cellslot[idx] = 0;
             p.rowflag[idx / p.L.nx] = 0;
