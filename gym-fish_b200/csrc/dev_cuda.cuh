@@ -117,6 +117,11 @@ public:
 
     bool init(int device, std::string &e) {
         int n = 0;
+        // A handle owns 6 streams + a copy stream.  The default of 8 hardware work queues per device makes streams share queues, and
+        // a queue is served in submission order: harmless for one handle per process (the production layout), but with several
+        // PEERED handles in one process (tests, smoke) a neighbour-wait kernel could sit in front of the very push it waits for.
+        // More queues (the maximum is 32) before the context exists; a value the application has set itself is left alone.
+        setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
         cudaError_t rc = cudaGetDeviceCount(&n);
         if (rc != cudaSuccess || n == 0) {
             e = std::string("no CUDA device: ") + cudaGetErrorString(rc) + " — this library has no CPU path";
