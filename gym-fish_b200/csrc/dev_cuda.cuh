@@ -101,6 +101,32 @@ __global__ void wait_counters_kernel(int *mine, CounterList s, unsigned long lon
     }
 }
 
+// Every kernel this library launches registers itself here (static initialisation of KernelReg<...>::done, forced by the
+// launch wrappers), and CudaDev::init loads them all before the first step.  Under CUDA's lazy module loading a kernel is
+// loaded at its first launch, which synchronises the context — behind a neighbour-wait kernel that may be spinning for exactly
+// that launch (peered handles in one process: FG_EPEER in the first cases of a run, gpu passes b24 - b26; one process per GPU:
+// a stall in the first steps).  Loading our own kernels leaves the application's modules (CUDA_MODULE_LOADING) alone.
+// Internal linkage throughout (anonymous namespace): the fp32 and the 16-bit build are two shared libraries with the same symbol
+// names, and inline statics / static members of templates are GNU-unique symbols that the dynamic linker would merge across them.
+namespace {
+std::vector<const void *> &kernel_registry() {
+    static std::vector<const void *> v;
+    return v;
+}
+bool register_kernel(const void *f) {
+    kernel_registry().push_back(f);
+    return true;
+}
+template <class K, class P, int FORM>
+struct KernelReg {
+    static const bool done;
+};
+template <class K, class P, int FORM>
+const bool KernelReg<K, P, FORM>::done =
+    register_kernel(FORM == 0 ? reinterpret_cast<const void *>(kern<K, P>) : FORM == 1 ? reinterpret_cast<const void *>(kern_bp<K, P>)
+                                                                                      : reinterpret_cast<const void *>(kern_phased<K, P>));
+}  // namespace
+
 class CudaDev {
 public:
     std::string err;
@@ -165,6 +191,13 @@ public:
                  ck(cudaEventCreateWithFlags(&join_ev_[i], cudaEventDisableTiming), "cudaEventCreate");
         stream_ = s_[0];
         ok = ok && ck(cudaStreamCreateWithFlags(&copy_s_, cudaStreamNonBlocking), "cudaStreamCreate(copy)");
+        {   // load every kernel of the library now (see kernel_registry)
+            cudaFuncAttributes fa;
+            for (const void *f : kernel_registry()) if (ok) ok = ck(cudaFuncGetAttributes(&fa, f), "kernel preload");
+            const void *small[] = {reinterpret_cast<const void *>(signal_kernel), reinterpret_cast<const void *>(wait_kernel),
+                                   reinterpret_cast<const void *>(signal_counters_kernel), reinterpret_cast<const void *>(wait_counters_kernel)};
+            for (const void *f : small) if (ok) ok = ck(cudaFuncGetAttributes(&fa, f), "kernel preload");
+        }
         for (int i = 0; i < 2 && ok; ++i)
             ok = ck(cudaEventCreate(&tev_[i][0]), "cudaEventCreate") && ck(cudaEventCreate(&tev_[i][1]), "cudaEventCreate");
         if (!ok) e = err;
@@ -311,6 +344,7 @@ public:
     bool launch(Dim3 g, const P &p) {
         ++launches;
         if (gmode_ == 2) return true;   // replaying a captured substep
+        (void)KernelReg<K, P, 0>::done;
         return launch_on_current(kern<K, P>, dim3(g.x, g.y, g.z), K::kThreads, p);
     }
     // The priority travels as a launch attribute, not only as a stream property: a captured kernel node keeps it,
@@ -349,6 +383,7 @@ public:
     bool launch_block_phased(Dim3 g, const P &p) {
         ++launches;
         if (gmode_ == 2) return true;
+        (void)KernelReg<K, P, 1>::done;
         return launch_on_current(kern_bp<K, P>, dim3(g.x, g.y, g.z), K::kThreads, p);
     }
     // g = (x-blocks, rows, planes) of ONE phase; the launch holds K::kGridPhases times as many CTAs in one dimension
@@ -371,6 +406,7 @@ public:
         if (gmode_ == 2) return true;
         static thread_local int per_sm = 0;      // per kernel instantiation
         if (per_sm == 0) {
+            (void)KernelReg<K, P, 2>::done;
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern_phased<K, P>, K::kThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
         }
         long long want = (max_items + K::kThreads - 1) / K::kThreads;
