@@ -818,6 +818,19 @@ def main():
                                      "pct_of_hbm_roofline": sph["pct_of_hbm_roofline"], "launch_mode": sph["launch_mode"],
                                      "scaling": "weak: one channel + sphere per GPU"}
 
+    def sub_mdf():
+        # FgConfig.ib_iterations = 3 (multi-direct forcing: two correction passes after the direct-forcing pass) on the IB-overhead
+        # workload, static markers; runs last among the sub-records
+        passes = 3
+        m = measure(ctx, "box_512_ib", flags, args.steps, args.warmup, want_e2e=False, extra=dict(ib_iterations=passes))
+        one = (sub.get("ib_overhead") or {}).get("static_markers") or {}
+        sub["ib_multi_direct_forcing"] = {
+            "workload": WORKLOADS["box_512_ib"]["desc"], "ib_iterations": passes, "markers": m["markers_per_gpu"], "value": m["value"],
+            "ms_per_step": m["ms_per_step"], "overhead_pct_vs_no_markers": (m["ms_per_step"] / main_res["ms_per_step"] - 1.0) * 100.0,
+            "ms_per_extra_pass": (m["ms_per_step"] - one["ms_per_step"]) / (passes - 1) if one.get("ms_per_step") else None,
+            "ib_kernels_ms_per_step": (m.get("roofline") or {}).get("ib_ms_per_step"), "launch_mode": m["launch_mode"],
+            "note": "device-timed fg_step(K), marker set unchanged; each extra pass = IbMdfGather + IbMdfSpread over all markers"}
+
     def sub_school():
         # configs[3]: the school of 16 fish in the 1024x512x512 tank, z-slabs across the ranks (strong scaling), bodies and
         # their marker / wrench exchange across slab faces; Gym loop of 20 substeps per env step
@@ -837,6 +850,8 @@ def main():
             guarded("ib_overhead", sub_ib)
             guarded("env", sub_env)
         guarded("sphere_256x128x128", sub_sphere)
+        if world == 1:
+            guarded("ib_multi_direct_forcing", sub_mdf)
         if world > 1:
             guarded("parity_vs_1gpu", sub_parity)
             guarded("school_1024x512x512", sub_school)

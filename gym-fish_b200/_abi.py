@@ -14,7 +14,7 @@ from typing import Optional
 
 import numpy as np
 
-FG_ABI_VERSION = 7
+FG_ABI_VERSION = 8
 Q = 19
 
 FG_OK, FG_EINVAL, FG_ENOMEM, FG_ECUDA, FG_ESTATE, FG_ENOTSUP, FG_EPEER = 0, -1, -2, -3, -4, -5, -6
@@ -67,7 +67,7 @@ class FgConfig(C.Structure):
         ("flags", C.c_int32),
         ("split_min_cells", C.c_int32),
         ("pair_lag", C.c_int32),
-        ("reserved_i", C.c_int32 * 1),
+        ("ib_iterations", C.c_int32),
         ("tau", C.c_double),
         ("mrt_rates", C.c_double * 19),
         ("wall_u", (C.c_double * 3) * 6),

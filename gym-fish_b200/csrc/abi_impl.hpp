@@ -29,6 +29,7 @@ int validate(const FgConfig *cfg) {
         return create_fail(FG_EINVAL, "bad slab decomposition: need 0 <= rank < n_ranks and nz % n_ranks == 0");
     if (!(cfg->tau > 0.5)) return create_fail(FG_EINVAL, "tau must be > 0.5");
     if (cfg->collision != FG_BGK && cfg->collision != FG_MRT) return create_fail(FG_EINVAL, "unknown collision model");
+    if (cfg->ib_iterations < 0 || cfg->ib_iterations > 16) return create_fail(FG_EINVAL, "ib_iterations must be in 0 .. 16");
     for (int f = 0; f < 6; ++f) {
         const int b = cfg->bc[f];
         if (b < FG_BC_PERIODIC || b > FG_BC_OUTLET) return create_fail(FG_EINVAL, "unknown boundary condition");

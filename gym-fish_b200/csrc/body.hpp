@@ -18,6 +18,7 @@ namespace fg {
 
 class Fish {
 public:
+    void set_forcing_passes(int n) { passes_ = n > 1 ? double(n) : 1.0; }
     bool init(const FgFishDesc &d, std::string &why) {
         if (d.n_links < 1 || d.n_links > 8) { why = "fish: n_links must be 1..8"; return false; }
         d_ = d;
@@ -108,7 +109,9 @@ public:
             // F = 2(U_d - U*) is stiff against the body velocity (stiffness sum 2 dV).  A virtual mass
             // Mv = beta * stiffness low-pass filters the momentum increment, (M+Mv) a_new = F + Mv a_old;
             // the fixed point is a = F/M and the update is unconditionally stable for beta >= 1/4.
-            const double Mv = kBeta * pen_total_, Iv = kBeta * Crot;
+            // With n direct-forcing passes per substep (FgConfig.ib_iterations) the marker force is sum_m (I - A)^m 2(U_d - U*),
+            // A = interpolation of the spread force: at most n times as stiff, and the virtual mass follows that bound.
+            const double Mv = kBeta * passes_ * pen_total_, Iv = kBeta * passes_ * Crot;
             dpx_ = (M_ * Fx + Mv * dpx_) / (M_ + Mv);
             dpz_ = (M_ * Fz + Mv * dpz_) / (M_ + Mv);
             dLy_ = (Itot * Ty + Iv * dLy_) / (Itot + Iv);
@@ -198,6 +201,7 @@ private:
     std::vector<double> pts_, vol_;
     std::vector<double> q_, qd_;
     static constexpr double kBeta = 0.5;
+    double passes_ = 1.0;                  // direct-forcing passes per substep (set_forcing_passes)
     std::vector<double> pen_, pen2_;       // per link: sum 2 dV and sum 2 dV |xi|^2 (in the swimming plane)
     double pen_total_ = 0;
     double dpx_ = 0, dpz_ = 0, dLy_ = 0;   // filtered momentum increments of the last substep

@@ -75,6 +75,7 @@ struct IbParams {
     int *base;                   // [n][3]
     int *owner;                  // [n]
     float *Fm, *Ustar;           // [n][3]
+    float *mdfE;                 // [n][3] multi-direct forcing: the spread force gathered back at the markers (IbMdfGather), or nullptr
     int *cellslot;               // [(nz+2)*plane]
     int *band_cell;              // [cap]
     float *band_u;               // [3][cap]
@@ -305,6 +306,45 @@ struct IbForceSpread {
         atomic_add_f(&p.bandF[s], w * f0);
         atomic_add_f(&p.bandF[p.band_cap + s], w * f1);
         atomic_add_f(&p.bandF[2 * p.band_cap + s], w * f2);
+    }
+};
+
+// (a6, optional) multi-direct forcing, SURVEY.md A7 (4) "n_iter > 1" (FgConfig.ib_iterations; the oracle's loop in ib_forces()).
+// The collide works with u = u* + F/(2 rho0) (Guo half-force), so after one direct-forcing pass the markers see
+// U*_k + E_k/2 with E_k = sum_x F(x) delta_h(x - X_k) instead of U_d,k.  Every further pass is two launches over the same
+// stencils: IbMdfGather collects E_k from the band force spread so far (all markers, before any of them spreads again),
+// IbMdfSpread adds the Jacobi correction dF_k = 2 rho0 (U_d,k - U*_k) - E_k to the marker force and spreads it.
+struct IbMdfGather {
+    static constexpr int kThreads = kNodes * kMarkersPerCta;
+    static constexpr int kMinBlocks = 8;
+    FG_HD static void run(const IbParams &p, int bx, int, int, int tx) {
+        const int k = bx * kMarkersPerCta + tx / kNodes, node = tx % kNodes;
+        if (k >= p.n || (p.gidx && p.gidx[k] < 0)) return;    // whole warps leave together (64 threads per marker)
+        long long cell; int s;
+        const float w = node_weight(p, k, node, cell, s);
+        float e0 = 0.f, e1 = 0.f, e2 = 0.f;
+        if (s >= 0) { e0 = w * p.bandF[s]; e1 = w * p.bandF[p.band_cap + s]; e2 = w * p.bandF[2 * p.band_cap + s]; }
+        e0 = warp_sum(e0); e1 = warp_sum(e1); e2 = warp_sum(e2);
+        if (reduction_leader(tx)) {
+            atomic_add_f(&p.mdfE[3 * k], e0); atomic_add_f(&p.mdfE[3 * k + 1], e1); atomic_add_f(&p.mdfE[3 * k + 2], e2);
+        }
+    }
+};
+struct IbMdfSpread {
+    static constexpr int kThreads = kNodes * kMarkersPerCta;
+    static constexpr int kMinBlocks = 8;
+    FG_HD static void run(const IbParams &p, int bx, int, int, int tx) {
+        const int k = bx * kMarkersPerCta + tx / kNodes, node = tx % kNodes;
+        if (k >= p.n || (p.gidx && p.gidx[k] < 0)) return;
+        const float d0 = 2.0f * (p.U[3 * k] - p.Ustar[3 * k]) - p.mdfE[3 * k], d1 = 2.0f * (p.U[3 * k + 1] - p.Ustar[3 * k + 1]) - p.mdfE[3 * k + 1],
+                    d2 = 2.0f * (p.U[3 * k + 2] - p.Ustar[3 * k + 2]) - p.mdfE[3 * k + 2];
+        if (node == 0) { p.Fm[3 * k] += d0; p.Fm[3 * k + 1] += d1; p.Fm[3 * k + 2] += d2; }   // no other thread reads Fm in this launch
+        long long cell; int s;
+        const float w = node_weight(p, k, node, cell, s) * p.dV[k];
+        if (s < 0) return;
+        atomic_add_f(&p.bandF[s], w * d0);
+        atomic_add_f(&p.bandF[p.band_cap + s], w * d1);
+        atomic_add_f(&p.bandF[2 * p.band_cap + s], w * d2);
     }
 };
 
@@ -694,6 +734,8 @@ public:
         band_count_ = (int *)A(2 * sizeof(int));
         rowflag_ = (uint8_t *)A(size_t(L.nz + 2) * L.ny);
         dwrench_ = (double *)A(sizeof(double) * 6 * maxl_);
+        iters_ = std::max(1, int(cfg.ib_iterations));
+        if (iters_ > 1 && !(dE_ = (float *)A(sizeof(float) * 3 * cap_pad_))) return FG_ENOMEM;
         rank_ = cfg.rank; n_ranks_ = cfg.n_ranks;
         if (cfg.n_ranks > 1) {
             x_bytes_ = x_off_wrench() + sizeof(double) * 2 * size_t(cfg.n_ranks) * maxl_ * 6;
@@ -712,8 +754,8 @@ public:
     }
 
     void destroy(Dev &dev) {
-        void *ps[] = {dmsg_, dbase_, downer_, dF_, dUs_, cellslot_, band_cell_, band_u_, bandF_, band_count_, rowflag_, dwrench_, xbuf_, dxside_, node_w_, node_s_};
-        xbuf_ = nullptr; dxside_ = nullptr; xchg_ = false; node_w_ = nullptr; node_s_ = nullptr; cache_valid_ = false;
+        void *ps[] = {dmsg_, dbase_, downer_, dF_, dUs_, cellslot_, band_cell_, band_u_, bandF_, band_count_, rowflag_, dwrench_, xbuf_, dxside_, node_w_, node_s_, dE_};
+        xbuf_ = nullptr; dxside_ = nullptr; xchg_ = false; node_w_ = nullptr; node_s_ = nullptr; cache_valid_ = false; dE_ = nullptr;
         for (void *p : ps) dev.free(p);
         dev.free_host(h_stage_[0]); dev.free_host(h_stage_[1]); dev.free_host(h_out_);
         h_stage_[0] = h_stage_[1] = nullptr; h_out_ = nullptr;
@@ -724,6 +766,7 @@ public:
     size_t xbuf_bytes() const { return x_bytes_; }
     void *xbuf() const { return xbuf_; }
     bool exchange_on() const { return xchg_; }
+    int iterations() const { return iters_; }
     // layout of the exchange buffer: [ints: 4 + kMaxRanks][ustar_in floats][wrench_all doubles]
     static size_t x_off_ustar() { return 64; }
     size_t x_off_wrench() const { return (x_off_ustar() + sizeof(float) * 2 * 2 * size_t(cap_) * 3 + 15) / 16 * 16; }
@@ -891,7 +934,7 @@ public:
         p.X = dmsg_; p.U = dmsg_ + 3 * N; p.dV = dmsg_ + 6 * N; p.link = reinterpret_cast<const int *>(dmsg_ + 7 * N);
         p.gidx = xchg_ ? reinterpret_cast<const int *>(dmsg_ + 8 * N) : nullptr;
         p.origin = dmsg_ + (xchg_ ? 9 : 8) * N;
-        p.base = dbase_; p.owner = downer_; p.Fm = dF_; p.Ustar = dUs_;
+        p.base = dbase_; p.owner = downer_; p.Fm = dF_; p.Ustar = dUs_; p.mdfE = dE_;
         p.cellslot = cellslot_; p.band_cell = band_cell_; p.band_u = band_u_; p.bandF = bandF_;
         p.band_count = band_count_ + cur_; p.band_count_next = band_count_ + (cur_ ^ 1);
         p.band_cap = band_cap_; p.rowflag = rowflag_;
@@ -914,7 +957,7 @@ public:
     // SURVEY.md A7 (2)-(5),(7) on the device; the collide that follows reads force_view()
     int compute_forces(Dev &dev, const Lattice &L, const Collision &C, int parity, std::string &err) {
         // static bodies: the marker set was not re-sent since the last step, so its index map and band are still valid
-        const bool use_fused = fused_ && !xchg_ && dev.supports_phased();
+        const bool use_fused = fused_ && !xchg_ && iters_ == 1 && dev.supports_phased();
         const bool rebuild = markers_dirty_ || !band_live_ || !reuse_static_ || use_fused;
         if (rebuild) cur_ ^= 1;                               // this step's counter; the other one still holds the old size
         // static bodies with many markers: from the second step without a re-send on, stencil weights and band slots come
@@ -956,6 +999,16 @@ public:
             if (!xchg_) {
                 const Dim3 gs = Dim3x(std::max(dev.interp_spread_blocks(n_), (6 * nl_ + 127) / 128));
                 ok = ok && (tile_spread_ ? dev.template launch_block_phased<IbInterpSpreadTile>(gs, p) : dev.template launch_block_phased<IbInterpSpread>(gs, p));
+                if (iters_ > 1) {
+                    // multi-direct forcing: gather the spread force at every marker, then spread the corrections (IbMdfGather)
+                    IbParams q = p;
+                    if (q.cache_mode == 1) q.cache_mode = 2;          // the pass above has filled the per-node cache
+                    for (int it = 1; it < iters_; ++it) {
+                        ok = ok && dev.zero(dE_, sizeof(float) * 3 * size_t(n_));
+                        ok = ok && dev.template launch<IbMdfGather>(Dim3x(nb), q);
+                        ok = ok && dev.template launch<IbMdfSpread>(Dim3x(nb), q);
+                    }
+                }
                 ok = ok && dev.template launch<IbLinkReduce>(Dim3x((n_ + 127) / 128), p);
             } else {
                 // bodies across slab faces: the exchange of partial U* sits between interpolation and spreading
@@ -1131,6 +1184,8 @@ private:
     int pending_sb_ = -1;           // staging buffer holding a marker message that has not been queued yet
     size_t pending_bytes_ = 0;
     float *dmsg_ = nullptr, *dF_ = nullptr, *dUs_ = nullptr, *band_u_ = nullptr, *bandF_ = nullptr;
+    float *dE_ = nullptr;          // multi-direct forcing (FgConfig.ib_iterations > 1): gathered force per marker
+    int iters_ = 1;
     int *dbase_ = nullptr, *downer_ = nullptr, *cellslot_ = nullptr, *band_cell_ = nullptr, *band_count_ = nullptr;
     uint8_t *rowflag_ = nullptr;
     double *dwrench_ = nullptr;

@@ -319,6 +319,7 @@ public:
         if (!ib_.ready()) return fail(FG_ESTATE, "FgConfig.max_markers was 0 at create");
         Fish f;
         if (!f.init(d, err)) return FG_EINVAL;
+        f.set_forcing_passes(ib_.iterations());
         int n = f.n_markers(), nl = f.n_links();
         for (auto &o : fish_) { n += o.n_markers(); nl += o.n_links(); }
         if (n > cfg.max_markers || nl > cfg.max_links) return fail(FG_EINVAL, "fish exceeds FgConfig.max_markers / max_links");
@@ -655,6 +656,7 @@ public:
         const int lo = (cfg.rank - 1 + n) % n, hi = (cfg.rank + 1) % n;
         if (int rc = peer_connect(internal_lo() ? hs + lo : nullptr, internal_hi() ? hs + hi : nullptr)) return rc;
         if (!ib_.ready()) return FG_OK;
+        if (ib_.iterations() > 1) return fail(FG_ENOTSUP, "multi-direct forcing (ib_iterations > 1) is not supported with bodies across z-slab faces");
         if (L_.nz < 4) return fail(FG_EINVAL, "bodies across slabs need at least 4 planes per slab");
         void *all[kMaxRanks] = {};
         for (int r = 0; r < n; ++r) {

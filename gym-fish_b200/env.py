@@ -83,6 +83,7 @@ class EnvConfig:
     waypoint_radius: float = 12.0
     probes: int = 0                                       # velocity probes per fish, on a ring ahead of the head
     fluid_check_every: int = 1                            # env steps between fluid divergence checks (fg_check_finite; 0 = never)
+    ib_iterations: int = 1                                # direct-forcing passes per substep (FgConfig.ib_iterations; > 1: multi-direct forcing)
 
 
 class FishEnv:
@@ -108,7 +109,8 @@ class FishEnv:
                 a, r, p = length / 2, rad, 1.6075
                 cap += int(1.25 * 4 * np.pi * (((r * r) ** p + 2 * (r * a) ** p) / 3) ** (1 / p)) + 16
         self.sim = Sim(backend=backend, nx=nx, ny=ny, nz=nz, tau=self.cfg.tau, collision=self.cfg.collision, bc=bc,
-                       max_markers=cap, max_links=sum(len(f.links) for f in self.cfg.fish), device=self.cfg.device)
+                       max_markers=cap, max_links=sum(len(f.links) for f in self.cfg.fish), device=self.cfg.device,
+                       ib_iterations=int(self.cfg.ib_iterations))
         for d in descs:
             self.sim.add_fish(d)
         if self.cfg.task not in ("cruise", "pose", "path"):

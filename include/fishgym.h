@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FG_ABI_VERSION 7
+#define FG_ABI_VERSION 8
 #define FG_Q 19
 
 /* error codes */
@@ -87,7 +87,9 @@ typedef struct FgConfig {
     int32_t flags;            /* FG_FLAG_* */
     int32_t split_min_cells;  /* plane split only when at least this many cells lie in far planes; 0 => 1<<20 (~25 us of work) */
     int32_t pair_lag;         /* FG_FLAG_FUSED_PAIRS: planes between the even and the odd wavefront; 0 => chosen from the plane size */
-    int32_t reserved_i[1];
+    int32_t ib_iterations;    /* direct-forcing passes per substep (multi-direct forcing): 0 or 1 => one pass F_k = 2 rho0 (U_d - U*_k);
+                               * n > 1 => n - 1 Jacobi corrections dF_k = 2 rho0 (U_d - U*_k) - sum_x F(x) delta_h(x - X_k), F_k += dF_k, spread dF_k
+                               * (the no-slip residual at the markers shrinks with every pass); at most 16.  Not with bodies across z-slab faces. */
     double  tau;              /* relaxation time; nu = (tau - 1/2)/3 */
     double  mrt_rates[19];    /* MRT relaxation rates per moment; all zero => SURVEY.md A3 defaults */
     double  wall_u[6][3];     /* wall velocity per face (used where bc == WALL) */

@@ -307,6 +307,36 @@ inline int wrap_or_skip(int v, int n, bool periodic) {
     return v < 0 ? v + n : v;
 }
 
+// the stencil of marker k: fn(cell, w) for every node that lies on this rank's lattice, w = product of the three 1-D weights
+template <class Fn>
+void stencil_nodes(const FgSim *s, int k, Fn fn) {
+    const FgConfig &c = s->cfg;
+    const bool px = c.bc[FG_XLO] == FG_BC_PERIODIC, py = c.bc[FG_YLO] == FG_BC_PERIODIC, pz = c.bc[FG_ZLO] == FG_BC_PERIODIC;
+    double wx[4], wy[4], wz[4];
+    const double X = s->mX[3 * k], Y = s->mX[3 * k + 1], Z = s->mX[3 * k + 2];
+    const int i0 = s->mbase[3 * k], j0 = s->mbase[3 * k + 1], k0 = s->mbase[3 * k + 2];
+    for (int a = 0; a < 4; ++a) {
+        wx[a] = peskin4(X - (i0 + a));
+        wy[a] = peskin4(Y - (j0 + a));
+        wz[a] = peskin4(Z - (k0 + a));
+    }
+    for (int cz = 0; cz < 4; ++cz) {
+        const int zg = wrap_or_skip(k0 + cz, s->nzg, pz);
+        if (zg < 0) continue;
+        const int zl = zg - s->z0;
+        if (zl < 0 || zl >= s->nz) continue;
+        for (int cy = 0; cy < 4; ++cy) {
+            const int yy = wrap_or_skip(j0 + cy, s->ny, py);
+            if (yy < 0) continue;
+            for (int cx = 0; cx < 4; ++cx) {
+                const int xx = wrap_or_skip(i0 + cx, s->nx, px);
+                if (xx < 0) continue;
+                fn(s->idx(xx, yy, zl), wx[cx] * wy[cy] * wz[cz]);
+            }
+        }
+    }
+}
+
 void ib_forces(FgSim *s) {
     const int n = s->n_markers;
     const FgConfig &c = s->cfg;
@@ -394,6 +424,28 @@ void ib_forces(FgSim *s) {
             }
         }
     }
+    // (a6, optional) multi-direct forcing, SURVEY.md A7 (4) "n_iter > 1": with the Guo half-force the fluid velocity the
+    // collide works with is u = u* + F/(2 rho0), so after one pass the markers see U*_k + E_k/2, E_k = sum_x F(x) delta_h(x - X_k),
+    // not U_d,k.  Every further pass adds the Jacobi correction dF_k = 2 rho0 (U_d,k - U*_k - E_k/2) to ALL markers from the
+    // same force field (gather first, then spread), so the no-slip residual contracts pass by pass.
+    for (int it = 1; it < std::max(1, c.ib_iterations); ++it) {
+        std::vector<double> dF(3 * size_t(n), 0.0);
+#pragma omp parallel for schedule(static)
+        for (int k = 0; k < n; ++k) {
+            double e[3] = {0, 0, 0};
+            stencil_nodes(s, k, [&](size_t cell, double w) {
+                e[0] += w * s->Fx[cell]; e[1] += w * s->Fy[cell]; e[2] += w * s->Fz[cell];
+            });
+            for (int d = 0; d < 3; ++d) dF[3 * k + d] = 2.0 * (double(s->mU[3 * k + d]) - s->mUstar[3 * k + d]) - e[d];
+        }
+        for (int k = 0; k < n; ++k) {          // serial: fixed sum order
+            const double dV = s->mdV[k];
+            stencil_nodes(s, k, [&](size_t cell, double w) {
+                s->Fx[cell] += w * dV * dF[3 * k]; s->Fy[cell] += w * dV * dF[3 * k + 1]; s->Fz[cell] += w * dV * dF[3 * k + 2];
+            });
+            for (int d = 0; d < 3; ++d) s->mF[3 * k + d] += dF[3 * k + d];
+        }
+    }
     // (a8) per-link wrench ON the body = minus what the body exerts on the fluid
     std::fill(s->wrench.begin(), s->wrench.end(), 0.0);
     for (int k = 0; k < n; ++k) {
@@ -470,6 +522,7 @@ int fg_create(const FgConfig *cfg, FgSim **out) {
         return fail(nullptr, FG_EINVAL, "bad slab decomposition: need 0 <= rank < n_ranks and nz % n_ranks == 0");
     if (!(cfg->tau > 0.5)) return fail(nullptr, FG_EINVAL, "tau must be > 0.5");
     if (cfg->collision != FG_BGK && cfg->collision != FG_MRT) return fail(nullptr, FG_EINVAL, "unknown collision model");
+    if (cfg->ib_iterations < 0 || cfg->ib_iterations > 16) return fail(nullptr, FG_EINVAL, "ib_iterations must be in 0 .. 16");
     for (int f = 0; f < 6; ++f) {
         const int b = cfg->bc[f];
         if (b < FG_BC_PERIODIC || b > FG_BC_OUTLET) return fail(nullptr, FG_EINVAL, "unknown boundary condition");
@@ -728,6 +781,7 @@ int fg_add_fish(FgSim *s, const FgFishDesc *d, int32_t *fish_id) {
     obody::Fish fh;
     std::string why;
     if (!fh.init(*d, &why)) return fail(s, FG_EINVAL, why);
+    fh.forcing_passes(s->cfg.ib_iterations);
     int n = fh.n_markers(), nl = fh.n_links();
     for (auto &o : s->fish) { n += o.n_markers(); nl += o.n_links(); }
     if (n > s->cfg.max_markers || nl > s->cfg.max_links)

@@ -26,6 +26,7 @@ inline double cross_y(const V2 &a, const V2 &b) { return a.z * b.x - a.x * b.z; 
 
 class Fish {
 public:
+    void forcing_passes(int n) { npass_ = n > 1 ? double(n) : 1.0; }
     bool init(const FgFishDesc &d, std::string *why) {
         if (d.n_links < 1 || d.n_links > 8) { *why = "fish: n_links must be 1..8"; return false; }
         desc_ = d;
@@ -119,7 +120,8 @@ public:
             // explicit coupling with the direct-forcing penalty F = 2(U_d - U*) is unstable for light bodies
             // (added-mass instability); a virtual mass Mv = beta * sum(2 dV) filters the momentum increment:
             // (M + Mv) a_new = F + Mv a_old, fixed point a = F/M, unconditionally stable for beta >= 1/4
-            const double Mv = kBeta * ctot_, Iv = kBeta * Cr;
+            // n direct-forcing passes per substep (multi-direct forcing) make the penalty at most n times as stiff
+            const double Mv = kBeta * npass_ * ctot_, Iv = kBeta * npass_ * Cr;
             dP_.x = (M * F.x + Mv * dP_.x) / (M + Mv);
             dP_.z = (M * F.z + Mv * dP_.z) / (M + Mv);
             dL_ = (I * T + Iv * dL_) / (I + Iv);
@@ -221,6 +223,7 @@ private:
     std::vector<double> xi_, dV_;          // body-frame marker points [n][3] (lateral, y, axial), volumes
     std::vector<double> q_, qd_;
     static constexpr double kBeta = 0.5;
+    double npass_ = 1.0;
     std::vector<double> cmark_, cmark2_;   // per link: sum 2 dV, sum 2 dV |xi|^2 in the swimming plane
     double ctot_ = 0;
     double th0_ = 0, om0_ = 0, L_ = 0, dL_ = 0;

@@ -40,23 +40,29 @@ def main():
         r, v = s.get_fields(f64=True)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), rho=r, u=v, steps=STEPS)
         s.close()
+    # immersed boundary: sphere in a channel, 7 steps; the second fixture with three direct-forcing passes per step
+    # (FgConfig.ib_iterations = 3, multi-direct forcing)
+    P, Wl, IN, OUT = g.BC_PERIODIC, g.BC_WALL, g.BC_INLET, g.BC_OUTLET
+    for name, passes in (("ib_sphere", 1), ("ib_sphere_mdf3", 3)):
+        if only_missing and os.path.exists(os.path.join(HERE, name + ".npz")):
+            continue
+        kw = dict(nx=20, ny=18, nz=24, tau=0.8, collision=g.MRT, max_markers=512, max_links=1, bc=[P, P, Wl, Wl, IN, OUT], inlet_u=[0, 0, 0.05],
+                  ib_iterations=passes)
+        s = g.Sim(backend="oracle", **kw)
+        X = util.sphere_markers((10.3, 9.1, 8.2), 4.0, 200)
+        s.set_markers(X, np.zeros_like(X), np.ones(200, np.float32), np.zeros(200, np.int32))
+        s.set_link_origins([[10.3, 9.1, 8.2]])
+        u = np.zeros((3,) + s.shape)
+        u[2] = 0.05
+        s.set_fields(np.ones(s.shape), u)
+        s.step(7)
+        r, v = s.get_fields(f64=True)
+        base, owner = s.get_index_map()
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), rho=r, u=v, base=base, owner=owner, wrench=s.get_link_wrenches(),
+                            Fm=s.get_marker_forces(), steps=7, passes=passes)
+        s.close()
     if only_missing:
         return
-    # immersed boundary: sphere in a channel, 7 steps
-    P, Wl, IN, OUT = g.BC_PERIODIC, g.BC_WALL, g.BC_INLET, g.BC_OUTLET
-    kw = dict(nx=20, ny=18, nz=24, tau=0.8, collision=g.MRT, max_markers=512, max_links=1, bc=[P, P, Wl, Wl, IN, OUT], inlet_u=[0, 0, 0.05])
-    s = g.Sim(backend="oracle", **kw)
-    X = util.sphere_markers((10.3, 9.1, 8.2), 4.0, 200)
-    s.set_markers(X, np.zeros_like(X), np.ones(200, np.float32), np.zeros(200, np.int32))
-    s.set_link_origins([[10.3, 9.1, 8.2]])
-    u = np.zeros((3,) + s.shape)
-    u[2] = 0.05
-    s.set_fields(np.ones(s.shape), u)
-    s.step(7)
-    r, v = s.get_fields(f64=True)
-    base, owner = s.get_index_map()
-    np.savez_compressed(os.path.join(HERE, "ib_sphere.npz"), rho=r, u=v, base=base, owner=owner, wrench=s.get_link_wrenches(),
-                        Fm=s.get_marker_forces(), steps=7)
     # Poiseuille channel of BASELINE configs[1] height (NY = 128, walls on y, force along z, wall-exact MRT rates):
     # converged steady-state populations of one (x,z)-invariant column, so that full-size runs can start without the
     # O(NY^2/nu) start-up transient.  ~1 minute on 8 cores.

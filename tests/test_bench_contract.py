@@ -59,7 +59,9 @@ def test_b200_arm_dry_run_prints_the_contract_keys():
     assert d["roofline"] is None or {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"])
     assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"]) and d["e2e"]["h2d_bytes_per_step"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0 and "own process" in d["cpu_baseline"]["sample"]
-    assert set(d["sub_records"]) == {"ib_overhead", "env", "sphere_256x128x128"} and "watchdog" not in d
+    assert set(d["sub_records"]) == {"ib_overhead", "env", "sphere_256x128x128", "ib_multi_direct_forcing"} and "watchdog" not in d
+    mdf = d["sub_records"]["ib_multi_direct_forcing"]
+    assert mdf["ib_iterations"] == 3 and mdf["value"] > 0 and mdf["markers"] == d["sub_records"]["ib_overhead"]["markers"]
     assert not any("error" in v for v in d["sub_records"].values() if isinstance(v, dict))
 
 

@@ -31,10 +31,11 @@ def run_case(g, backend, name):
     return util.rel_l2(v, gold["u"]), util.rel_l2(r, gold["rho"])
 
 
-def run_ib(g, backend):
+def run_ib(g, backend, fixture="ib_sphere"):
     P, Wl, IN, OUT = g.BC_PERIODIC, g.BC_WALL, g.BC_INLET, g.BC_OUTLET
-    gold = np.load(os.path.join(GOLD, "ib_sphere.npz"))
-    kw = dict(nx=20, ny=18, nz=24, tau=0.8, collision=g.MRT, max_markers=512, max_links=1, bc=[P, P, Wl, Wl, IN, OUT], inlet_u=[0, 0, 0.05])
+    gold = np.load(os.path.join(GOLD, fixture + ".npz"))
+    kw = dict(nx=20, ny=18, nz=24, tau=0.8, collision=g.MRT, max_markers=512, max_links=1, bc=[P, P, Wl, Wl, IN, OUT], inlet_u=[0, 0, 0.05],
+              ib_iterations=int(gold["passes"]) if "passes" in gold.files else 1)
     s = g.Sim(backend=backend, **kw)
     X = util.sphere_markers((10.3, 9.1, 8.2), 4.0, 200)
     s.set_markers(X, np.zeros_like(X), np.ones(200, np.float32), np.zeros(200, np.int32))
@@ -64,10 +65,11 @@ def test_emulated_kernels_match_golden(g, emu, name):
     assert eu <= 1e-5 and er <= 1e-5
 
 
-def test_ib_golden_oracle_and_emulation(g, emu):
-    o = run_ib(g, "oracle")
+@pytest.mark.parametrize("fixture", ["ib_sphere", "ib_sphere_mdf3"])
+def test_ib_golden_oracle_and_emulation(g, emu, fixture):
+    o = run_ib(g, "oracle", fixture)
     assert o["u"] < 1e-12 and o["base"] and o["owner"] and o["wrench"] < 1e-6 and o["Fm"] < 1e-6
-    e = run_ib(g, emu)
+    e = run_ib(g, emu, fixture)
     assert e["u"] <= 1e-5 and e["rho"] <= 1e-5 and e["base"] and e["owner"] and e["wrench"] <= 1e-4 and e["Fm"] <= 1e-4
 
 
@@ -79,8 +81,9 @@ def test_cuda_matches_golden(g, cuda, name):
 
 
 @pytest.mark.gpu
-def test_cuda_ib_matches_golden(g, cuda):
-    e = run_ib(g, cuda)
+@pytest.mark.parametrize("fixture", ["ib_sphere", "ib_sphere_mdf3"])
+def test_cuda_ib_matches_golden(g, cuda, fixture):
+    e = run_ib(g, cuda, fixture)
     assert e["u"] <= 1e-5 and e["rho"] <= 1e-5 and e["base"] and e["owner"] and e["wrench"] <= 1e-4 and e["Fm"] <= 1e-4
 
 

@@ -61,6 +61,7 @@ class NumpyStep:
         s = np.array([0, 1.19, 1.4, 0, 1.2, 0, 1.2, 0, 1.2, sn, 1.4, sn, 1.4, sn, sn, sn, 1.98, 1.98, 1.98]) if rates is None else np.asarray(rates, float)
         self.s = s if mrt else np.full(19, sn)      # BGK: one rate on every row, the conserved ones included
         self.markers = None
+        self.ib_passes = 1
 
     def init(self, rho, u):
         self.f = equilibrium(np.asarray(rho, float), np.asarray(u, float))
@@ -85,6 +86,22 @@ class NumpyStep:
             ustar = np.einsum("dzyx,zyx->d", us[block], w3)
             self.Fm[k] = 2.0 * (U[k] - ustar)
             F[block] += self.Fm[k][:, None, None, None] * (w3 * dV[k])
+        if self.ib_passes > 1:
+            # A7 (4) "n_iter > 1", multi-direct forcing, stated with matrices instead of the oracle's gather / spread loops:
+            # D [markers x cells] holds the delta weights, so interpolation is D, spreading is D^T diag(dV), and with
+            # b = 2 (U_d - U*) every further pass is F_m <- F_m + b - D (D^T (dV F_m))   (what the markers see is U* + D F(x) / 2)
+            n, ncell = len(X), int(np.prod(self.shape))
+            D = np.zeros((n, ncell))
+            nz, ny, nx = self.shape
+            for k in range(n):
+                i0, j0, k0 = self.base[k]
+                wx, wy, wz = (peskin(X[k, d] - (self.base[k, d] + np.arange(4))) for d in range(3))
+                zz, yy, xx = np.meshgrid(k0 + np.arange(4), j0 + np.arange(4), i0 + np.arange(4), indexing="ij")
+                D[k, ((zz * ny + yy) * nx + xx).ravel()] = (wz[:, None, None] * wy[None, :, None] * wx[None, None, :]).ravel()
+            b = self.Fm.copy()
+            for _ in range(self.ib_passes - 1):
+                self.Fm = self.Fm + b - D @ (D.T @ (dV[:, None] * self.Fm))
+            F = (D.T @ (dV[:, None] * self.Fm)).T.reshape((3,) + self.shape)
         r = X - origin
         f = -self.Fm * dV[:, None]
         self.wrench = np.concatenate([f.sum(0), np.cross(r, f).sum(0)])
@@ -151,7 +168,8 @@ class NumpyStep:
         for _ in range(n):
             F = np.broadcast_to(self.g[:, None, None, None], (3,) + self.shape).copy()
             if self.markers is not None:
-                F += self.ib_force()
+                self.last_F = self.ib_force()
+                F += self.last_F
             self.f = self.stream(self.collide(F))
 
     def fields(self):
@@ -174,6 +192,7 @@ def both(g, kw_np, kw_abi, shape, steps, markers=None, f_tol=5e-15):
     P = g.BC_PERIODIC
     rho, u = start_fields(shape, 7)
     ref = NumpyStep(shape, **kw_np)
+    ref.ib_passes = max(1, int(kw_abi.get("ib_iterations", 1)))
     ref.init(rho, u)
     nz, ny, nx = shape
     s = g.Sim(backend="oracle", nx=nx, ny=ny, nz=nz, max_markers=0 if markers is None else len(markers[0]), max_links=1,
@@ -244,4 +263,20 @@ def test_immersed_sphere_direct_forcing(g):
     assert np.array_equal(base, ref.base)
     assert np.abs(s.get_marker_forces() - ref.Fm).max() < 1e-7            # float32 read-out
     assert np.abs(s.get_link_wrenches()[0] - ref.wrench).max() < 1e-12 * max(1.0, np.abs(ref.wrench).max())
+    s.close()
+
+
+@pytest.mark.parametrize("passes", [2, 5])
+def test_immersed_sphere_multi_direct_forcing(g, passes):
+    """FgConfig.ib_iterations > 1: the oracle's gather / spread passes against the matrix form F <- F + b - D D^T dV F."""
+    import util
+    shape = (16, 14, 15)
+    X = util.sphere_markers((7.3, 6.6, 8.2), 3.0, 60)
+    U = np.tile(np.float32([0.01, -0.02, 0.015]), (60, 1))
+    dV = np.full(60, 4 * np.pi * 9 / 60, np.float32)
+    origin = [7.3, 6.6, 8.2]
+    s, ref = both(g, dict(tau=0.8, mrt=True), dict(tau=0.8, collision=g.MRT, ib_iterations=passes), shape, 8, markers=(X, U, dV, origin), f_tol=5e-14)
+    assert np.abs(s.get_marker_forces() - ref.Fm).max() < 2e-7            # float32 read-out
+    assert np.abs(s.get_link_wrenches()[0] - ref.wrench).max() < 1e-12 * max(1.0, np.abs(ref.wrench).max())
+    assert util.rel_l2(s.get_force_field(), ref.last_F) < 1e-6
     s.close()

@@ -220,7 +220,7 @@ def stable(rho, keep=1):
     return bool(np.isfinite(rho).all() and 0.7 < (rho * keep + (1 - keep)).min() and (rho * keep).max() < 1.3)
 
 
-def run_moving_markers_case(g, backend, seed):
+def run_moving_markers_case(g, backend, seed, passes=1):
     """A marker cloud that drifts (up to 1.2 planes per step), is sometimes replaced by another one, left alone (static
     reuse of index map and band) or removed, steps of 1-3 substeps, obstacles, probes, the plane split and the fused
     step pairs switched on at random: everything the host logic decides per substep, against the oracle."""
@@ -233,6 +233,8 @@ def run_moving_markers_case(g, backend, seed):
     if solid is not None:
         solid = (rng.random((nz, ny, nx)) < 0.05).astype(np.uint8)
     kw.update(max_markers=64, max_links=4)
+    if passes > 1:
+        kw["ib_iterations"] = passes        # multi-direct forcing (tests/test_multi_direct_forcing.py); drawn outside this generator's stream
     if rng.random() < 0.3:
         kw["flags"] |= A.FLAG_FUSED_PAIRS
     a, b = g.Sim(backend="oracle", **kw), g.Sim(backend=backend, **kw)
