@@ -159,6 +159,7 @@ SYMBOLS = [
     ("fg_sync", C.c_int, [_P]),
     ("fg_get_stats", C.c_int, [_P, C.POINTER(FgStats)]),
     ("fg_check_finite", C.c_int, [_P, C.POINTER(C.c_int64)]),
+    ("fg_get_solid_force", C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     ("fg_set_flags", C.c_int, [_P, C.c_int32]),
     ("fg_halo_bytes", C.c_int64, [_P]),
     ("fg_halo_pack", C.c_int, [_P, C.c_int32, C.c_void_p]),
@@ -435,6 +436,15 @@ class Sim:
         n = C.c_int64(0)
         self._ck(self.lib.fg_check_finite(self.h, C.byref(n)))
         return int(n.value)
+
+    def get_solid_force(self, origin=None) -> np.ndarray:
+        """[6]: momentum-exchange force of the fluid on the obstacle cells (fg_set_solid) in the last step and, with `origin`
+        (x, y, global z), its torque about that point; the share of this rank's fluid cells on z-slabs."""
+        out = np.zeros(6, dtype=np.float64)
+        o = None if origin is None else np.ascontiguousarray(origin, dtype=np.float64).reshape(3)
+        self._ck(self.lib.fg_get_solid_force(self.h, None if o is None else o.ctypes.data_as(C.POINTER(C.c_double)),
+                                             out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
 
     def set_flags(self, flags: int):
         self._ck(self.lib.fg_set_flags(self.h, int(flags)))

@@ -212,6 +212,11 @@ int fg_check_finite(FgSim *s, int64_t *n_bad) {
     FG_TRY return s->sim.check_finite(n_bad); FG_CATCH(s)
 }
 
+int fg_get_solid_force(FgSim *s, const double *origin3, double *out6) {
+    if (!s || !out6) return FG_EINVAL;
+    FG_TRY return s->sim.get_solid_force(origin3, out6); FG_CATCH(s)
+}
+
 int fg_set_flags(FgSim *s, int32_t flags) {
     if (!s) return FG_EINVAL;
     s->sim.cfg.flags = flags;

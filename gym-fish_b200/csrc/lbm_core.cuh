@@ -998,6 +998,96 @@ struct ScatterNatural {
     }
 };
 
+// fg_get_solid_force (momentum exchange): one thread per cell gathers the populations arriving at its cell with the
+// parity-aware loader — a population that was reflected off an obstacle arrives from the cell's own opposite slot — and every
+// such link hands the obstacle -2 c_i f_i.  "Off an obstacle" is the loader's own test (no wall face crossed, obstacle flag of the
+// source cell set; the flags of the ghost planes encode periodic wrap / outlet clamping, sim.hpp set_solid).  Warp-reduced in
+// fp64, six atomics per warp that saw a link.  A read-out, not part of a step.
+struct SolidForceParams {
+    Lattice L;
+    Collision C;
+    double *out;            // [6], zeroed before the launch
+    double ox, oy, oz;      // torque reference point (global z)
+    int torque;
+};
+FG_HD double warp_sum_d(double v, bool &leader, int tx) {
+#if defined(__CUDA_ARCH__)
+    v += __shfl_down_sync(0xffffffffu, v, 16);
+    v += __shfl_down_sync(0xffffffffu, v, 8);
+    v += __shfl_down_sync(0xffffffffu, v, 4);
+    v += __shfl_down_sync(0xffffffffu, v, 2);
+    v += __shfl_down_sync(0xffffffffu, v, 1);
+    leader = (tx & 31) == 0;
+#else
+    (void)tx;
+    leader = true;      // host emulation: every "thread" adds its own part
+#endif
+    return v;
+}
+FG_HD void atomic_add_f64(double *p, double v) {
+#if defined(__CUDA_ARCH__)
+    atomicAdd(p, v);
+#else
+    *p += v;
+#endif
+}
+template <int PARITY>
+struct SolidForce {
+    static constexpr int kThreads = 128;
+    static constexpr int kMinBlocks = 4;
+    template <int I>
+    FG_HD static void link(const float (&h)[Q], const SolidForceParams &p, const Nbr &nb, long long idx, double rx, double ry, double rz, double (&a)[6]) {
+        using D = Dir<I>;
+        constexpr int J = D::opp;
+        const Lattice &L = p.L;
+        // f_I arrives from x - c_I, f_J from x + c_I (odd_load_pair)
+        const bool bm = nb.wall<-D::cx, -D::cy, -D::cz>() < 0 && L.solid[idx + nb.off<-D::cx, -D::cy, -D::cz>()];
+        const bool bp = nb.wall<D::cx, D::cy, D::cz>() < 0 && L.solid[idx + nb.off<D::cx, D::cy, D::cz>()];
+        constexpr double w = I < 7 ? 1.0 / 18 : 1.0 / 36;      // lattice weight of both directions of the pair (populations are stored shifted by it)
+        if (bm) add(2.0 * (double(h[I]) + w), -D::cx, -D::cy, -D::cz, p, rx, ry, rz, a);
+        if (bp) add(2.0 * (double(h[J]) + w), D::cx, D::cy, D::cz, p, rx, ry, rz, a);
+    }
+    // a population of mass m/2 reflected at the link midpoint x + e/2 (e points from the cell to the obstacle): the obstacle takes m e
+    FG_HD static void add(double m, int ex, int ey, int ez, const SolidForceParams &p, double rx, double ry, double rz, double (&a)[6]) {
+        const double fx = ex * m, fy = ey * m, fz = ez * m;
+        a[0] += fx; a[1] += fy; a[2] += fz;
+        if (p.torque) {
+            const double x = rx + 0.5 * ex, y = ry + 0.5 * ey, z = rz + 0.5 * ez;
+            a[3] += y * fz - z * fy; a[4] += z * fx - x * fz; a[5] += x * fy - y * fx;
+        }
+    }
+    FG_HD static void run(const SolidForceParams &p, int bx, int by, int bz, int tx) {
+        const Lattice &L = p.L;
+        const int x = bx * kThreads + tx, y = by, zz = bz + 1;
+        double a[6] = {0, 0, 0, 0, 0, 0};
+        bool any = false;
+        if (x < L.nx) {
+            const long long idx = ((long long)zz * L.ny + y) * L.nx + x;
+            if (!L.solid[idx]) {
+                const Nbr nb = make_nbr(L, x, y, zz);
+                float h[Q];
+                load_arriving<PARITY, true>(h, L, p.C, nb, idx);
+                const double rx = x - p.ox, ry = y - p.oy, rz = (L.z0 + zz - 1) - p.oz;
+#define FG_X(I) link<I>(h, p, nb, idx, rx, ry, rz, a);
+                FG_FOR_PAIRS(FG_X)
+#undef FG_X
+                any = a[0] != 0 || a[1] != 0 || a[2] != 0 || a[3] != 0 || a[4] != 0 || a[5] != 0;
+            }
+        }
+#if defined(__CUDA_ARCH__)
+        if (!__any_sync(0xffffffffu, any)) return;      // most warps see no obstacle
+#else
+        if (!any) return;
+#endif
+        FG_UNROLL
+        for (int c = 0; c < 6; ++c) {
+            bool leader;
+            const double v = warp_sum_d(a[c], leader, tx);
+            if (leader && v != 0) atomic_add_f64(p.out + c, v);
+        }
+    }
+};
+
 // divergence guard of the fluid (fg_check_finite): one thread per cell reads the REST population only (4 B per cell) and
 // counts cells where it is not finite or has left |h_0| <= 4 (the density would be off by more than 12).  A NaN in any
 // population of a cell reaches h_0 with the cell's next collision, so a blow-up is seen one step later at most.

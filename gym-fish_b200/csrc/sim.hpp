@@ -83,6 +83,7 @@ public:
         dev.free(stage_[0]); dev.free(stage_[1]); stage_[0] = stage_[1] = nullptr;
         dev.free(probe_d_); dev.free_host(probe_h_); probe_d_ = probe_h_ = nullptr; probe_cap_ = 0;
         dev.free(finite_d_); finite_d_ = nullptr;
+        dev.free(solid_force_d_); solid_force_d_ = nullptr;
         dev.shutdown();
     }
 
@@ -311,6 +312,20 @@ public:
         if (!ok) return cuda_fail();
         *n_bad = int64_t(h);
         return FG_OK;
+    }
+
+    // include/fishgym.h fg_get_solid_force: momentum exchange over the bounce-back links of the obstacle cells (lbm_core.cuh SolidForce)
+    int get_solid_force(const double *origin3, double *out6) {
+        std::fill(out6, out6 + 6, 0.0);
+        if (!L_.solid) return FG_OK;
+        if (int rc = halos_ready_for_readout()) return rc;
+        if (!solid_force_d_) solid_force_d_ = static_cast<double *>(dev.alloc(6 * sizeof(double), err));
+        if (!solid_force_d_) return FG_ENOMEM;
+        SolidForceParams p{L_, C_, solid_force_d_, origin3 ? origin3[0] : 0.0, origin3 ? origin3[1] : 0.0, origin3 ? origin3[2] : 0.0, origin3 ? 1 : 0};
+        bool ok = dev.zero(solid_force_d_, 6 * sizeof(double));
+        ok = ok && (parity_ == 0 ? dev.template launch<SolidForce<0>>(grid_planes(L_.nz), p) : dev.template launch<SolidForce<1>>(grid_planes(L_.nz), p));
+        ok = ok && dev.sync() && dev.d2h(out6, solid_force_d_, 6 * sizeof(double));
+        return ok ? FG_OK : cuda_fail();
     }
 
     int add_fish(const FgFishDesc &d, int32_t *id) {
@@ -1060,6 +1075,7 @@ private:
     float *probe_d_ = nullptr, *probe_h_ = nullptr;   // fg_probe: device [7 cap] / pinned host [7 cap], grow-only
     int probe_cap_ = 0;
     unsigned long long *finite_d_ = nullptr;           // fg_check_finite counter
+    double *solid_force_d_ = nullptr;                  // fg_get_solid_force accumulator [6]
     IbState<Dev> ib_;
     std::vector<Fish> fish_;
     std::vector<float> action_;

@@ -189,6 +189,13 @@ int fg_get_stats(FgSim *sim, FgStats *out);
  * population is not finite or has left |f_0 - 1/3| <= 4 — one 4-byte read per cell (~85 us at 512^3 on a B200).  A NaN
  * anywhere in a cell reaches its rest population with the next collision, so a blow-up shows here one step later at most. */
 int fg_check_finite(FgSim *sim, int64_t *n_bad_cells);
+/* Momentum-exchange force of the fluid ON the obstacle cells (fg_set_solid), SURVEY.md A5: every bounce-back link of the last step
+ * hands the obstacle the momentum of the population it reflected, out6[0..2] = sum over fluid cells x and directions i whose
+ * source x - c_i is an obstacle of -2 c_i f_i(x, t+1)  (f_i(x, t+1) = the reflected population now arriving at x), out6[3..5] =
+ * the torque of those link forces about origin3 (lattice coordinates x, y, global z; applied at the link midpoints x - c_i/2;
+ * NULL: zeros).  Domain walls (FG_BC_WALL) are not obstacles.  With z-slabs every rank returns the share of its own fluid
+ * cells: sum over ranks.  A read-out (one pass over the slab, synchronous); before the first step it reflects the initial state. */
+int fg_get_solid_force(FgSim *sim, const double *origin3, double *out6);
 int fg_set_flags(FgSim *sim, int32_t flags);        /* change FgConfig.flags (FG_FLAG_PROFILE, FG_FLAG_NO_GRAPHS, FG_FLAG_NO_OVERLAP) */
 
 /* ---- z-slab halos ----

@@ -882,6 +882,55 @@ int fg_check_finite(FgSim *s, int64_t *n_bad) {
     return FG_OK;
 }
 
+// include/fishgym.h fg_get_solid_force (SURVEY.md A5 "momentum-exchange force on solids").  A population that the pull rule
+// reflected off an obstacle (pull(): solid[src]) left cell x with momentum -c_i f and came back with +c_i f: the obstacle took
+// -2 c_i f_i(x, t+1).  Same source-cell rule as pull(): wall faces and the inlet are not obstacles, the outlet clamps the plane.
+inline bool reflected_off_obstacle(const FgSim *s, int i, int x, int y, int z) {
+    const FgConfig &c = s->cfg;
+    int sx = x - CX[i], sy = y - CY[i], sz = z - CZ[i];
+    if (sx < 0) { if (c.bc[FG_XLO] != FG_BC_PERIODIC) return false; sx = s->nx - 1; }
+    else if (sx >= s->nx) { if (c.bc[FG_XHI] != FG_BC_PERIODIC) return false; sx = 0; }
+    if (sy < 0) { if (c.bc[FG_YLO] != FG_BC_PERIODIC) return false; sy = s->ny - 1; }
+    else if (sy >= s->ny) { if (c.bc[FG_YHI] != FG_BC_PERIODIC) return false; sy = 0; }
+    const int zg = s->z0 + sz;
+    if (zg < 0 || zg >= s->nzg) {
+        switch (c.bc[zg < 0 ? FG_ZLO : FG_ZHI]) {
+            case FG_BC_PERIODIC: if (c.n_ranks <= 1) sz = zg < 0 ? s->nz - 1 : 0; break;
+            case FG_BC_OUTLET: sz = z; break;
+            default: return false;      // wall, inlet
+        }
+    }
+    return s->solid[s->idx(sx, sy, sz)] != 0;
+}
+
+int fg_get_solid_force(FgSim *s, const double *origin3, double *out6) {
+    if (!s || !out6) return FG_EINVAL;
+    if (int rc = finish_pending(s)) return rc;
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0;
+    if (s->has_solid) {
+#pragma omp parallel for schedule(static) reduction(+ : a0, a1, a2, a3, a4, a5)
+        for (int z = 0; z < s->nz; ++z)
+            for (int y = 0; y < s->ny; ++y)
+                for (int x = 0; x < s->nx; ++x) {
+                    const size_t c = s->idx(x, y, z);
+                    if (s->solid[c]) continue;
+                    for (int i = 1; i < Q; ++i) {
+                        if (!reflected_off_obstacle(s, i, x, y, z)) continue;
+                        const double m = 2.0 * s->F(s->f, i)[c];
+                        const double fx = -CX[i] * m, fy = -CY[i] * m, fz = -CZ[i] * m;
+                        a0 += fx; a1 += fy; a2 += fz;
+                        if (origin3) {
+                            const double rx = x - 0.5 * CX[i] - origin3[0], ry = y - 0.5 * CY[i] - origin3[1],
+                                         rz = (s->z0 + z) - 0.5 * CZ[i] - origin3[2];
+                            a3 += ry * fz - rz * fy; a4 += rz * fx - rx * fz; a5 += rx * fy - ry * fx;
+                        }
+                    }
+                }
+    }
+    out6[0] = a0; out6[1] = a1; out6[2] = a2; out6[3] = a3; out6[4] = a4; out6[5] = a5;
+    return FG_OK;
+}
+
 int fg_set_flags(FgSim *s, int32_t flags) {
     if (!s) return FG_EINVAL;
     s->cfg.flags = flags;

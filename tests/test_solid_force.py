@@ -1,0 +1,195 @@
+"""fg_get_solid_force: momentum-exchange force of the fluid on obstacle cells (SURVEY.md Appendix A5 "Momentum-exchange
+force on solids: sum over boundary links of c_i (f_i* + f_opp,in)"; with half-way bounce-back off a resting obstacle the
+two populations of a link are equal, so every reflected population f hands the obstacle 2 f along the link).
+
+CPU: the oracle against a numpy evaluation from its own populations, a steady-channel force balance and the zero net
+pressure force on a closed body; the product's kernel (SolidForce<parity>, emulated) against the oracle on every
+boundary kind, both parities, z-slabs.  GPU: the CUDA library against the oracle through the C ABI."""
+import numpy as np
+import pytest
+
+import util
+
+
+def numpy_force(g, f, solid, origin):
+    """Fully periodic box, one rank: f [19][nz][ny][nx] = populations arriving at the cells (fg_get_populations)."""
+    A = g._abi
+    F, T = np.zeros(3), np.zeros(3)
+    nz, ny, nx = solid.shape
+    z, y, x = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    for i in range(1, 19):
+        came_from_obstacle = np.roll(solid, (A.CZ[i], A.CY[i], A.CX[i]), axis=(0, 1, 2)) == 1      # flag of x - c_i
+        m = (solid == 0) & came_from_obstacle
+        c = np.array([A.CX[i], A.CY[i], A.CZ[i]], dtype=np.float64)
+        Fi = -c[None, :] * (2.0 * f[i][m].astype(np.float64))[:, None]
+        r = np.stack([x[m] - 0.5 * c[0] - origin[0], y[m] - 0.5 * c[1] - origin[1], z[m] - 0.5 * c[2] - origin[2]], 1)
+        F += Fi.sum(0)
+        T += np.cross(r, Fi).sum(0)
+    return np.concatenate([F, T])
+
+
+@pytest.mark.parametrize("collision", ["bgk", "mrt"])
+def test_oracle_against_numpy_from_its_own_populations(g, collision):
+    rng = np.random.default_rng(5)
+    kw = dict(nx=11, ny=9, nz=8, tau=0.7, collision=g.MRT if collision == "mrt" else g.BGK, body_force=[1e-4, -2e-4, 3e-4])
+    s = g.Sim(backend="oracle", **kw)
+    solid = (rng.random(s.shape) < 0.15).astype(np.uint8)
+    rho, u = util.smooth_fields(s.shape)
+    s.set_solid(solid)
+    s.set_fields(rho, u)
+    o = [4.5, 3.0, 2.5]
+    for n in (0, 1, 1, 5):
+        s.step(n)
+        got = s.get_solid_force(o)
+        ref = numpy_force(g, s.get_populations(), solid, o)          # float32 populations: ~1e-7 relative
+        assert np.abs(got - ref).max() <= 2e-6 * max(1.0, np.abs(ref).max()), (n, got, ref)
+        plain = s.get_solid_force()                 # no origin: no torque (the OpenMP reduction may associate differently per call)
+        assert np.abs(plain[:3] - got[:3]).max() < 1e-13 and not plain[3:].any()
+    s.close()
+
+
+def test_oracle_steady_channel_force_balance(g):
+    """Two obstacle layers as channel walls, body force along z: once steady, the walls take exactly what the force puts
+    into the fluid, g x (number of fluid cells), and nothing in the other directions."""
+    nx, ny, nz, gf = 3, 12, 3, 1e-5
+    s = g.Sim(backend="oracle", nx=nx, ny=ny, nz=nz, tau=0.9, collision=g.MRT, body_force=[0, 0, gf])
+    solid = np.zeros(s.shape, np.uint8)
+    solid[:, 0, :] = 1
+    solid[:, -1, :] = 1
+    s.set_solid(solid)
+    s.step(6000)                       # H^2 / nu = 100 / 0.133: many diffusion times
+    F = s.get_solid_force()
+    n_fluid = int((solid == 0).sum())
+    assert abs(F[2] / (gf * n_fluid) - 1.0) < 1e-6, F
+    assert abs(F[0]) < 1e-12 and abs(F[1]) < 1e-9       # the two walls take equal and opposite pressure forces
+    s.close()
+
+
+def test_closed_body_in_fluid_at_rest_feels_no_force(g, emu):
+    for backend in ("oracle", emu):
+        s = g.Sim(backend=backend, nx=10, ny=9, nz=8, tau=0.8)
+        solid = np.zeros(s.shape, np.uint8)
+        solid[2:5, 3:6, 4:8] = 1
+        s.set_solid(solid)
+        for n in (0, 1, 2):
+            s.step(n)
+            F = s.get_solid_force([3.0, 4.0, 5.5])
+            assert np.abs(F).max() < (1e-12 if backend == "oracle" else 2e-6), (backend, n, F)
+        s.close()
+
+
+def test_without_obstacles_the_force_is_zero(g, emu):
+    for backend in ("oracle", emu):
+        s = g.Sim(backend=backend, nx=6, ny=5, nz=4, tau=0.8, bc=[g.BC_WALL] * 6)
+        s.step(2)
+        assert not s.get_solid_force([1, 1, 1]).any()
+        s.close()
+
+
+def _pair(g, backend, kw, solid, origin=(5.0, 4.0, 3.0), steps=(0, 1, 1, 1, 7, 1)):
+    a, b = g.Sim(backend="oracle", **kw), g.Sim(backend=backend, **kw)
+    rho, u = util.smooth_fields(a.shape)
+    for s in (a, b):
+        s.set_solid(solid)
+        s.set_fields(rho, u)
+    worst = 0.0
+    for n in steps:                      # read-outs at both storage parities of the AA pattern
+        a.step(n)
+        b.step(n)
+        fa, fb = a.get_solid_force(origin), b.get_solid_force(origin)
+        worst = max(worst, float(np.abs(fb - fa).max() / max(np.abs(fa).max(), 1e-3)))
+    a.close()
+    b.close()
+    return worst
+
+
+CASES = ["bgk_periodic", "mrt_force", "bgk_ywall_moving", "mrt_xy_walls", "mrt_all_walls_lid", "mrt_xwalls_moving", "bgk_inlet_outlet",
+         "mrt_inlet_outlet_ywalls", "mrt_outlet_inlet_xwalls"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_emulated_kernel_matches_oracle(g, emu, name):
+    """Every boundary kind next to obstacles (walls are not obstacles; the outlet clamps its plane, the inlet has none),
+    obstacle cells on the first and last plane and in a corner."""
+    kw = util.parity_cases(g)[name]
+    assert _pair(g, emu, kw, util.solid_block(kw)) <= 1e-5
+
+
+@pytest.mark.parametrize("name", ["mrt_periodic", "mrt_xy_walls", "bgk_inlet_outlet"])
+def test_emulated_random_masks(g, emu, name):
+    rng = np.random.default_rng(11)
+    kw = dict(util.parity_cases(g)[name], nx=34, ny=7, nz=6)         # rows that end inside a warp
+    solid = (rng.random((kw["nz"], kw["ny"], kw["nx"])) < 0.2).astype(np.uint8)
+    assert _pair(g, emu, kw, solid) <= 1e-5
+
+
+def test_host_staged_slabs_sum_to_the_unsplit_force(g, emu):
+    """Obstacles across the slab face and on the periodic seam: every rank returns the share of its own fluid cells."""
+    A = g._abi
+    kw = dict(nx=10, ny=8, nz=12, tau=0.8, collision=g.MRT, body_force=[1e-4, 0, 2e-4])
+    solid = np.zeros((12, 8, 10), np.uint8)
+    solid[4:8, 2:5, 3:7] = 1          # straddles the face between slabs 0 and 1 (planes 5 | 6)
+    solid[0, 6, 1] = 1
+    solid[11, 6, 1] = 1               # neighbours across the periodic seam
+    one = g.Sim(backend="oracle", **kw)
+    rho, u = util.smooth_fields(one.shape)
+    one.set_solid(solid)
+    one.set_fields(rho, u)
+    for backend in ("oracle", emu):
+        ranks = [g.Sim(backend=backend, n_ranks=2, rank=r, **kw) for r in range(2)]
+        for r, s in enumerate(ranks):
+            s.set_solid(solid)
+            s.set_fields(rho[6 * r:6 * r + 6], u[:, 6 * r:6 * r + 6])
+        ref = g.Sim(backend="oracle", **kw)
+        ref.set_solid(solid)
+        ref.set_fields(rho, u)
+        o = [4.0, 3.0, 5.0]
+        for _ in range(5):
+            ref.step(1)
+            for s in ranks:
+                s.step(1)
+            msgs = [(s.halo_pack(A.ZLO), s.halo_pack(A.ZHI)) for s in ranks]
+            ranks[0].halo_unpack(A.ZHI, msgs[1][0])
+            ranks[0].halo_unpack(A.ZLO, msgs[1][1])
+            ranks[1].halo_unpack(A.ZLO, msgs[0][1])
+            ranks[1].halo_unpack(A.ZHI, msgs[0][0])
+            total = ranks[0].get_solid_force(o) + ranks[1].get_solid_force(o)
+            want = ref.get_solid_force(o)
+            assert np.abs(total - want).max() <= 1e-5 * max(np.abs(want).max(), 1e-3), (backend, total, want)
+        for s in ranks + [ref]:
+            s.close()
+    one.close()
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["mrt_force", "mrt_all_walls_lid", "mrt_inlet_outlet_ywalls", "mrt_outlet_inlet_xwalls"])
+def test_gpu_matches_oracle(g, cuda, name):
+    kw = util.parity_cases(g)[name]
+    assert _pair(g, cuda, kw, util.solid_block(kw)) <= 1e-5
+
+
+@pytest.mark.gpu
+def test_gpu_staircase_sphere_in_a_channel(g, cuda):
+    """A staircase sphere of 12 cells diameter in a 64 x 48 x 96 channel with inflow (rows of two whole warps, an obstacle
+    far larger than a warp's cells): drag and torque of the momentum exchange against the oracle's, both parities."""
+    P, Wl, IN, OUT = g.BC_PERIODIC, g.BC_WALL, g.BC_INLET, g.BC_OUTLET
+    kw = dict(nx=64, ny=48, nz=96, tau=0.6, collision=g.MRT, bc=[P, P, Wl, Wl, IN, OUT], inlet_u=[0, 0, 0.04])
+    z, y, x = np.meshgrid(np.arange(96), np.arange(48), np.arange(64), indexing="ij")
+    solid = (((x - 31.5) ** 2 + (y - 23.5) ** 2 + (z - 30.5) ** 2) <= 36.0).astype(np.uint8)
+    a, b = g.Sim(backend="oracle", **kw), g.Sim(backend=cuda, **kw)
+    u = np.zeros((3,) + a.shape)
+    u[2] = 0.04
+    for s in (a, b):
+        s.set_solid(solid)
+        s.set_fields(np.ones(a.shape), u)
+    o = [31.5, 23.5, 30.5]
+    for n in (30, 1):
+        a.step(n)
+        b.step(n)
+        fa, fb = a.get_solid_force(o), b.get_solid_force(o)
+        assert fa[2] > 0                                      # drag along the flow
+        assert np.abs(fb[:3] - fa[:3]).max() <= 1e-4 * np.abs(fa[:3]).max(), (fa, fb)
+        assert np.abs(fb[3:] - fa[3:]).max() <= 1e-4 * max(np.abs(fa[3:]).max(), np.abs(fa[:3]).max()), (fa, fb)
+    a.close()
+    b.close()
