@@ -58,6 +58,34 @@ def test_f16_storage_immersed_boundary_and_halo_bytes_emulated(g, emu_f16):
     assert f16.lib.fg_halo_bytes(f16.h) * 2 == f32.lib.fg_halo_bytes(f32.h)
 
 
+def test_f16_storage_multi_direct_forcing_and_obstacle_force_emulated(g, emu_f16):
+    """The 16-bit build compiles the same IB passes (fp32 band arrays) and the same momentum-exchange read-out (populations
+    widened on load): both against the oracle at this build's own tolerance."""
+    P, Wl, IN, OUT = g.BC_PERIODIC, g.BC_WALL, g.BC_INLET, g.BC_OUTLET
+    kw = dict(nx=20, ny=18, nz=24, tau=0.8, collision=g.MRT, max_markers=400, max_links=1, bc=[P, P, Wl, Wl, IN, OUT], inlet_u=[0, 0, 0.05],
+              ib_iterations=3)
+    X = util.sphere_markers((10.3, 9.1, 8.2), 4.0, 200)
+    solid = np.zeros((24, 18, 20), np.uint8)
+    solid[15:19, 6:10, 8:13] = 1
+    a, b = g.Sim(backend="oracle", **kw), g.Sim(backend=emu_f16, **kw)
+    u = np.zeros((3,) + a.shape)
+    u[2] = 0.05
+    for s in (a, b):
+        s.set_solid(solid)
+        s.set_markers(X, np.zeros_like(X), np.ones(200, np.float32))
+        s.set_link_origins([[10.3, 9.1, 8.2]])
+        s.set_fields(np.ones(a.shape), u)
+    for n in (10, 1):                       # read-outs at both parities
+        for s in (a, b):
+            s.step(n)
+        wa, wb = a.get_link_wrenches(), b.get_link_wrenches()
+        assert np.abs(wb - wa).max() / np.abs(wa).max() <= 5e-3
+        assert util.rel_l2(b.get_marker_forces(), a.get_marker_forces()) <= 5e-3
+        fa, fb = a.get_solid_force([10.0, 8.0, 17.0]), b.get_solid_force([10.0, 8.0, 17.0])
+        assert np.abs(fb - fa).max() <= 5e-3 * np.abs(fa).max(), (fa, fb)
+        assert util.rel_l2(b.get_fields(f64=True)[1] * (solid == 0), a.get_fields(f64=True)[1] * (solid == 0)) <= TOL_U
+
+
 def test_f16_storage_population_roundtrip_emulated(g, emu_f16):
     s = g.Sim(backend=emu_f16, nx=6, ny=5, nz=4, tau=0.9)
     rng = np.random.default_rng(3)
