@@ -21,11 +21,12 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--small", action="store_true")
 ap.add_argument("--lib", default="cuda")
 ap.add_argument("--steps", type=int, default=400)
+ap.add_argument("--passes", type=int, default=1, help="direct-forcing passes per step (FgConfig.ib_iterations; > 1: multi-direct forcing)")
 args = ap.parse_args()
 
 nx, ny, nz, D = (32, 32, 64, 8.0) if args.small else (128, 128, 256, 24.0)
 U0, Re = 0.04, 40.0
-sim = g.Sim(backend=args.lib, nx=nx, ny=ny, nz=nz, tau=3 * U0 * D / Re + 0.5, collision=g.MRT, max_markers=4096, max_links=1,
+sim = g.Sim(backend=args.lib, nx=nx, ny=ny, nz=nz, tau=3 * U0 * D / Re + 0.5, collision=g.MRT, max_markers=4096, max_links=1, ib_iterations=args.passes,
             bc=[g.BC_PERIODIC, g.BC_PERIODIC, g.BC_WALL, g.BC_WALL, g.BC_INLET, g.BC_OUTLET], inlet_u=[0, 0, U0])
 u = np.zeros((3,) + sim.shape, np.float32)
 u[2] = U0
@@ -45,6 +46,13 @@ X, Um = np.empty((n, 3), np.float32), np.empty((n, 3), np.float32)          # re
 rest = np.array([nx / 2 + 0.2, ny / 2 + 0.1, nz / 4])
 pos, vel = rest.copy(), np.zeros(3)
 mass, k_spring = 4 / 3 * np.pi * (D / 2) ** 3 * 2.0, 0.02        # a body twice as dense as the fluid on a soft spring
+# The coupling is explicit: this step's force comes from the velocity the body had when its markers were sent.  Direct forcing
+# F_k = 2 (U_d - U*) answers a change of the body's velocity with the stiffness sum 2 dV per pass, and an explicit update is
+# unstable once that exceeds ~2 x mass (added-mass instability: light bodies, or several passes).  A virtual mass
+# Mv = 1/2 x stiffness low-pass filters the momentum increment — (mass + Mv) dp_new = mass F + Mv dp_old, fixed point dp = F —
+# which is what the built-in fish integrator does (csrc/body.hpp).
+Mv = 0.5 * max(1, args.passes) * 2.0 * float(dV.sum())
+dp = np.zeros(3)
 
 t0 = time.perf_counter()
 for it in range(args.steps):
@@ -54,7 +62,8 @@ for it in range(args.steps):
     sim.set_link_origins([pos])
     sim.step(1)                               # IB coupling + fused stream-collide; returns when the wrench is there
     force = sim.get_link_wrenches()[0, :3]    # device -> host: hydrodynamic force on the body during this step
-    vel += (force - k_spring * (pos - rest)) / mass
+    dp = (mass * (force - k_spring * (pos - rest)) + Mv * dp) / (mass + Mv)
+    vel += dp / mass
     pos += vel
     if it % max(1, args.steps // 8) == 0:
         print(f"step {it:5d}  drag Fz {force[2]:+.4e}  displacement z {pos[2] - rest[2]:+.4f}")
