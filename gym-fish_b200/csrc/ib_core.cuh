@@ -1023,6 +1023,27 @@ public:
                     ok = ok && dev.template launch<IbAddPartial>(Dim3x((n_ + 127) / 128), p);
                 }
                 ok = ok && dev.template launch<IbForceSpread>(Dim3x(nb), p);
+                if (iters_ > 1) {
+                    // Multi-direct forcing across slab faces: every pass gathers E_k over the own cells, completes it with the
+                    // face neighbour's part (the U* exchange kernels, pointed at E) and spreads the correction into the own
+                    // cells.  Each exchange is an epoch of its own: the counter is bumped after it, so consecutive exchanges
+                    // use the two buffer sets in turn (a rank can write set s again only after its neighbour has signalled the
+                    // exchange in between, i.e. after that neighbour has read set s) and the counter values keep increasing.
+                    int *sig[2] = {peer_lo_x_ ? reinterpret_cast<int *>(peer_lo_x_) + 2 : nullptr, peer_hi_x_ ? reinterpret_cast<int *>(peer_hi_x_) + 1 : nullptr};
+                    int *wt[2] = {peer_lo_x_ ? mine + 1 : nullptr, peer_hi_x_ ? mine + 2 : nullptr};
+                    IbParams q = p;
+                    q.Ustar = dE_;                                    // what IbPushPartial / IbAddPartial move
+                    for (int it = 1; it < iters_; ++it) {
+                        ok = ok && dev.signal_counters(mine, nullptr, 0, true);   // the previous exchange (U*, or the last pass) is complete
+                        ok = ok && dev.zero(dE_, sizeof(float) * 3 * size_t(n_));
+                        ok = ok && dev.template launch<IbMdfGather>(Dim3x(nb), p);
+                        ok = ok && dev.template launch<IbPushPartial>(Dim3x((n_ + 127) / 128), q);
+                        ok = ok && dev.signal_counters(mine, sig, 2, false) && dev.wait_counters(mine, wt, 2);
+                        ok = ok && dev.template launch<IbAddPartial>(Dim3x((n_ + 127) / 128), q);
+                        ok = ok && dev.template launch<IbMdfSpread>(Dim3x(nb), p);
+                    }
+                    ok = ok && dev.signal_counters(mine, nullptr, 0, true);       // the wrench exchange below is the next epoch
+                }
                 ok = ok && dev.template launch<IbLinkReduce>(Dim3x((n_ + 127) / 128), p);
                 {   // owner-reduced link wrenches to every rank, summed in rank order (bit-identical totals everywhere)
                     int *sig[kMaxRanks], *wt[kMaxRanks];

@@ -671,7 +671,6 @@ public:
         const int lo = (cfg.rank - 1 + n) % n, hi = (cfg.rank + 1) % n;
         if (int rc = peer_connect(internal_lo() ? hs + lo : nullptr, internal_hi() ? hs + hi : nullptr)) return rc;
         if (!ib_.ready()) return FG_OK;
-        if (ib_.iterations() > 1) return fail(FG_ENOTSUP, "multi-direct forcing (ib_iterations > 1) is not supported with bodies across z-slab faces");
         if (L_.nz < 4) return fail(FG_EINVAL, "bodies across slabs need at least 4 planes per slab");
         void *all[kMaxRanks] = {};
         for (int r = 0; r < n; ++r) {

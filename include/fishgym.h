@@ -89,7 +89,8 @@ typedef struct FgConfig {
     int32_t pair_lag;         /* FG_FLAG_FUSED_PAIRS: planes between the even and the odd wavefront; 0 => chosen from the plane size */
     int32_t ib_iterations;    /* direct-forcing passes per substep (multi-direct forcing): 0 or 1 => one pass F_k = 2 rho0 (U_d - U*_k);
                                * n > 1 => n - 1 Jacobi corrections dF_k = 2 rho0 (U_d - U*_k) - sum_x F(x) delta_h(x - X_k), F_k += dF_k, spread dF_k
-                               * (the no-slip residual at the markers shrinks with every pass); at most 16.  Not with bodies across z-slab faces. */
+                               * (the no-slip residual at the markers shrinks with every pass); at most 16.  With bodies across z-slab faces (fg_peer_connect_all)
+                               * every pass exchanges the partial sums of face-crossing markers with the z-neighbours, like U*. */
     double  tau;              /* relaxation time; nu = (tau - 1/2)/3 */
     double  mrt_rates[19];    /* MRT relaxation rates per moment; all zero => SURVEY.md A3 defaults */
     double  wall_u[6][3];     /* wall velocity per face (used where bc == WALL) */

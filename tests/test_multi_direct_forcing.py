@@ -231,18 +231,103 @@ def test_host_staged_slabs_with_iterations_equal_oracle_slabs(g, emu):
     assert util.rel_l2(ranks[0].get_marker_forces(), one.get_marker_forces()) <= TOL_FORCE
 
 
+@pytest.mark.parametrize("n_ranks", [2, 3])
+@pytest.mark.parametrize("passes", [2, 3])
+def test_bodies_across_slab_faces_with_passes_equal_unsplit(g, emu, n_ranks, passes):
+    """fg_peer_connect_all + ib_iterations > 1: every pass completes the gathered force E_k of a face-crossing marker with the
+    neighbour's part (the U* exchange kernels, one exchange epoch per pass) before the correction is spread.  A sphere across a
+    face, one across the periodic seam, one inside a slab; peered emulation ranks on threads against the unsplit run."""
+    import test_slabs
+    nz = 12 * n_ranks
+    kw = dict(nx=16, ny=14, nz=nz, tau=0.8, collision=g.MRT, max_markers=600, max_links=3, body_force=[0, 0, 2e-5], ib_iterations=passes)
+    whole = g.Sim(backend=emu, **kw)
+    one_pass = g.Sim(backend=emu, **dict(kw, ib_iterations=1))
+    parts = [g.Sim(backend=emu, n_ranks=n_ranks, rank=r, **kw) for r in range(n_ranks)]
+    X = np.concatenate([util.sphere_markers((8.2, 7.1, 12.3), 3.0, 120), util.sphere_markers((5.0, 6.0, nz - 0.4), 2.5, 90),
+                        util.sphere_markers((10.0, 8.0, 5.5), 2.0, 60)])
+    U = np.zeros_like(X)
+    U[:120, 2] = 0.01
+    link = np.array([0] * 120 + [1] * 90 + [2] * 60, np.int32)
+    dV = np.full(len(X), 0.9, np.float32)
+    origins = [[8.2, 7.1, 12.3], [5.0, 6.0, nz - 0.4], [10.0, 8.0, 5.5]]
+    rho, u = util.smooth_fields(whole.shape, amp=0.01)
+    h = nz // n_ranks
+    handles = [s.peer_export() for s in parts]
+    for r, s in enumerate(parts):
+        s.set_fields(rho[r * h:(r + 1) * h], u[:, r * h:(r + 1) * h])
+        s.peer_connect_all(handles)
+    for s in (whole, one_pass):
+        s.set_fields(rho, u)
+    for s in [whole, one_pass] + parts:
+        s.set_markers(X, U, dV, link)
+        s.set_link_origins(origins)
+    for n in (1, 4, 4):                  # both parities, both buffer sets of the exchange, static reuse of the band
+        whole.step(n)
+        one_pass.step(n)
+        test_slabs._run_threads([lambda s=s: s.step(n) for s in parts])
+        f = whole.get_populations()
+        fs = np.concatenate([s.get_populations() for s in parts], axis=1)
+        assert np.abs(f - fs).max() < 5e-7
+        w = whole.get_link_wrenches()
+        for s in parts:
+            ws = s.get_link_wrenches()
+            assert np.abs(ws - w).max() / np.abs(w).max() < 1e-5
+            assert np.array_equal(ws, parts[0].get_link_wrenches())          # bit-identical on every rank
+        _, owner = parts[0].get_index_map()
+        fm_p = [s.get_marker_forces() for s in parts]
+        fm_own = np.stack([fm_p[owner[k]][k] for k in range(len(X))])
+        assert util.rel_l2(fm_own, whole.get_marker_forces()) < 1e-4
+        # a face-crossing marker carries the same completed force on both ranks that hold it
+        crossing = [k for k in range(len(X)) if sum(bool(np.any(f_[k] != 0)) for f_ in fm_p) >= 2]
+        assert len(crossing) >= 20
+        for k in crossing:
+            held = [f_[k] for f_ in fm_p if np.any(f_[k] != 0)]
+            assert all(np.abs(h_ - held[0]).max() < 2e-6 for h_ in held)
+    assert np.abs(whole.get_link_wrenches() - one_pass.get_link_wrenches()).max() / np.abs(w).max() > 1e-2     # the passes do act
+    # the marker set re-sent (band rebuilt) between steps
+    X2 = X.copy()
+    X2[:, 2] += 0.7
+    for s in [whole] + parts:
+        s.set_markers(X2, U, dV, link)
+    whole.step(3)
+    test_slabs._run_threads([lambda s=s: s.step(3) for s in parts])
+    fs = np.concatenate([s.get_populations() for s in parts], axis=1)
+    assert np.abs(whole.get_populations() - fs).max() < 5e-7
+
+
+def test_fish_swims_across_a_slab_face_with_passes(g, emu):
+    kw = dict(nx=20, ny=18, nz=48, tau=0.8, max_markers=4000, max_links=8, ib_iterations=2)
+    import test_slabs
+    whole = g.Sim(backend=emu, **kw)
+    parts = [g.Sim(backend=emu, n_ranks=2, rank=r, **kw) for r in range(2)]
+    handles = [s.peer_export() for s in parts]
+    for s in parts:
+        s.peer_connect_all(handles)
+    d = util.fish_desc(g, root=(10, 9, 17))        # head in slab 0, tail links reach into slab 1 (face at z = 24)
+    d.joint_rate_max = 0.006
+    for s in [whole] + parts:
+        s.add_fish(d)
+    for it in range(4):
+        act = np.sin(0.5 * it + np.arange(3))
+        whole.set_action(act)
+        whole.step(6)
+        for s in parts:
+            s.set_action(act)
+        test_slabs._run_threads([lambda s=s: s.step(6) for s in parts])
+        ow = whole.get_obs()
+        for s in parts:
+            assert np.abs(s.get_obs() - ow).max() < 1e-4
+        assert np.array_equal(parts[0].get_obs(), parts[1].get_obs())        # replicated integrators stay bit-identical
+    fs = np.concatenate([s.get_populations() for s in parts], axis=1)
+    assert np.abs(whole.get_populations() - fs).max() < 1e-6
+
+
 def test_error_paths(g, emu):
     for backend in ("oracle", emu):
         for bad in (-1, 17):
             with pytest.raises(g.FgError) as e:
                 g.Sim(backend=backend, nx=8, ny=8, nz=8, max_markers=10, ib_iterations=bad)
             assert e.value.code == g._abi.FG_EINVAL and "ib_iterations" in str(e.value)
-    # bodies across slab faces exchange partial U* between ranks once per step; the correction passes are not exchanged
-    s = g.Sim(backend=emu, nx=8, ny=8, nz=16, n_ranks=2, rank=0, max_markers=10, max_links=1, ib_iterations=2)
-    h = [s.peer_export(), s.peer_export()]
-    with pytest.raises(g.FgError) as e:
-        s.peer_connect_all(h)
-    assert e.value.code == g._abi.FG_ENOTSUP and "ib_iterations" in str(e.value)
 
 
 @pytest.mark.parametrize("passes", [2, 4])

@@ -19,7 +19,7 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SELECT = ["tests/test_emu_parity.py", "tests/test_slabs.py", "tests/test_random_cases.py", "-k",
+SELECT = ["tests/test_emu_parity.py", "tests/test_slabs.py", "tests/test_random_cases.py", "tests/test_multi_direct_forcing.py", "tests/test_solid_force.py", "-k",
           "not gloo and not cuda and not 16_bit and not emulated_kernels_vs_oracle or moving_markers"]
 
 
