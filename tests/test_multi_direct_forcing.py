@@ -295,6 +295,23 @@ def test_bodies_across_slab_faces_with_passes_equal_unsplit(g, emu, n_ranks, pas
     assert np.abs(whole.get_populations() - fs).max() < 5e-7
 
 
+@pytest.mark.parametrize("passes", [2, 3])
+def test_random_bodies_across_slab_faces_with_passes(g, emu, passes):
+    """The randomised generator of test_random_cases.py for bodies across faces (2 - 4 peered ranks, drifting clouds that
+    straddle faces, wrap around z or leave the box; walls, inlet / outlet, overlap and plane split switched at random)."""
+    import test_random_cases as T
+    bad, ran = [], 0
+    for seed in range(30):
+        worst, kw, n_ranks = T.run_bodies_across_slabs_case(g, emu, seed, passes)
+        if worst is None:
+            continue
+        ran += 1
+        if worst["f"] > 1e-6 or worst["wrench"] > 1e-4:
+            bad.append((seed, worst, n_ranks, kw))
+    assert not bad, bad[:3]
+    assert ran >= 24
+
+
 def test_fish_swims_across_a_slab_face_with_passes(g, emu):
     kw = dict(nx=20, ny=18, nz=48, tau=0.8, max_markers=4000, max_links=8, ib_iterations=2)
     import test_slabs

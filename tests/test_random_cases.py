@@ -396,7 +396,7 @@ def test_random_moving_markers_and_fish_cuda_vs_oracle(g, cuda):
     check_fish(g, cuda, range(2000, 2012))
 
 
-def run_bodies_across_slabs_case(g, emu, seed):
+def run_bodies_across_slabs_case(g, emu, seed, passes=1):
     """fg_peer_connect_all on 2-4 slabs (ranks stepped from threads): drifting marker clouds that straddle faces, wrap
     around a periodic z axis or leave a non-periodic box, against the unsplit run.  Its first run found that a marker
     whose stencil lies entirely outside the box was culled on every rank and dropped out of its link's wrench."""
@@ -419,6 +419,8 @@ def run_bodies_across_slabs_case(g, emu, seed):
             kw["flags"] |= flag
     if rng.random() < 0.6:
         kw["split_min_cells"] = 1
+    if passes > 1:
+        kw["ib_iterations"] = passes        # multi-direct forcing across faces; set outside this generator's random stream
     whole = g.Sim(backend=emu, **kw)
     parts = [g.Sim(backend=emu, n_ranks=n_ranks, rank=r, **kw) for r in range(n_ranks)]
     rho, u = util.smooth_fields(whole.shape, amp=0.01)
