@@ -279,10 +279,18 @@ void stream(FgSim *s) {
                 const size_t c = s->idx(x, y, z);
                 if (s->has_solid && s->solid[c]) continue;
                 const int zg = s->z0 + z;
-                if (!s->has_solid && x > 0 && x < s->nx - 1 && y > 0 && y < s->ny - 1 && zg > 0 && zg < s->nzg - 1) {
-                    // interior cell: no face is crossed, the pull rule reduces to f_i(x) = f*_i(x - c_i)
-                    for (int i = 0; i < Q; ++i)
-                        s->F(s->f, i)[c] = s->F(s->fs, i)[c - (ptrdiff_t(CZ[i]) * s->ny + CY[i]) * s->nx - CX[i]];
+                if (x > 0 && x < s->nx - 1 && y > 0 && y < s->ny - 1 && zg > 0 && zg < s->nzg - 1) {
+                    // interior cell: no face is crossed, the pull rule reduces to f_i(x) = f*_i(x - c_i), or to the cell's own
+                    // opposite population where x - c_i is an obstacle (what pull() returns for such a cell)
+                    if (!s->has_solid) {
+                        for (int i = 0; i < Q; ++i)
+                            s->F(s->f, i)[c] = s->F(s->fs, i)[c - (ptrdiff_t(CZ[i]) * s->ny + CY[i]) * s->nx - CX[i]];
+                    } else {
+                        for (int i = 0; i < Q; ++i) {
+                            const size_t src = c - (ptrdiff_t(CZ[i]) * s->ny + CY[i]) * s->nx - CX[i];
+                            s->F(s->f, i)[c] = s->solid[src] ? s->F(s->fs, OPP[i])[c] : s->F(s->fs, i)[src];
+                        }
+                    }
                     continue;
                 }
                 for (int i = 0; i < Q; ++i) s->F(s->f, i)[c] = pull(s, s->fs, i, x, y, z);
