@@ -97,6 +97,24 @@ def test_oracle_pass_identity(g):
     assert np.array_equal(c.get_marker_forces(), a.get_marker_forces())
 
 
+@pytest.mark.parametrize("passes", [1, 3, 6])
+def test_spread_force_equals_accumulated_marker_force(g, emu, passes):
+    """SURVEY.md §4b property "sum of the spread force == sum of the marker forces": spreading is linear, so after any number of
+    passes the force field is the spread of the ACCUMULATED marker forces (read-outs of both backends), and the link wrench is
+    minus their sum."""
+    X, U, dV, link = _sphere_case()
+    for backend, tol in (("oracle", 2e-6), (emu, 2e-5)):        # the read-outs are fp32
+        s = _make(g, backend, passes)
+        s.set_markers(X, U, dV, link)
+        s.set_link_origins([[10.3, 9.6, 11.2]])
+        s.step(2)
+        Fm = (s.get_marker_forces().astype(np.float64) * dV[:, None]).sum(0)
+        Fg = s.get_force_field().astype(np.float64).sum(axis=(1, 2, 3))
+        assert np.abs(Fg - Fm).max() <= tol * np.abs(Fm).max(), (backend, Fg, Fm)
+        assert np.abs(s.get_link_wrenches()[0][:3] + Fm).max() <= tol * np.abs(Fm).max()
+        s.close()
+
+
 def _compare(a, b, steps=(1, 1, 4)):
     for n in steps:
         a.step(n)
