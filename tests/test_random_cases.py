@@ -476,7 +476,7 @@ def test_random_bodies_across_slab_faces_equal_unsplit(g, emu):
     assert ran >= 80
 
 
-def run_api_sequence_case(g, backend, seed):
+def run_api_sequence_case(g, backend, seed, solid_force=False):
     """A random SEQUENCE of ABI calls, valid and invalid (too many markers, link ids beyond max_links, obstacles changed
     after an even or an odd step, read-outs before the first step, resets, zero-substep steps), issued to the oracle and to
     the product's host code: every call must have the same outcome (ok, or the same error code) on both, and every read-out
@@ -521,6 +521,12 @@ def run_api_sequence_case(g, backend, seed):
             elif op == 3:
                 k = int(rng.integers(0, 4))
                 both(lambda s: s.step(k), "step")
+                # the momentum-exchange read-out after whatever came before (obstacles changed after an even or odd step, a
+                # reset, populations set by hand, no obstacles at all); not drawn from the generator's stream
+                if solid_force:
+                    ok, fa, fb = both(lambda s: s.get_solid_force([nx / 2, ny / 2, nz / 2]), "get_solid_force")
+                    if ok and np.isfinite(fa).all() and np.abs(fa).max() < 1e3:
+                        worst = max(worst, float(np.abs(fa - fb).max() / max(np.abs(fa).max(), 0.1)))
             elif op == 4:
                 both(lambda s: s.reset(0), "reset")
             elif op == 5:
@@ -556,7 +562,7 @@ def run_api_sequence_case(g, backend, seed):
 def test_random_api_sequences_same_outcome_on_both_backends(g, emu):
     bad, ran = [], 0
     for seed in range(300):
-        w = run_api_sequence_case(g, emu, seed)
+        w = run_api_sequence_case(g, emu, seed, solid_force=True)
         if w is None:
             continue
         ran += 1

@@ -37,7 +37,7 @@ def one(seed):
         w, kw = t.run_fish_case(g, lib, seed)
         return (None if w is None else (w["obs"] <= 1e-4 and w["wrench"] <= 1e-4 and w["u"] <= 1e-5)), kw
     if kind == "api":
-        w = t.run_api_sequence_case(g, lib, seed)
+        w = t.run_api_sequence_case(g, lib, seed, solid_force=True)
         return (None if w is None else w <= 2e-5), None
     if kind == "slabs":
         return t.run_slab_case(g, lib, seed)
