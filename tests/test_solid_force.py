@@ -161,6 +161,37 @@ def test_host_staged_slabs_sum_to_the_unsplit_force(g, emu):
     one.close()
 
 
+@pytest.mark.parametrize("overlap", [True, False])
+def test_peered_slabs_sum_to_the_unsplit_force(g, emu, overlap):
+    """The product's multi-GPU layout (halo pushes into the neighbour's lattice, emulated in one process): the read-out waits
+    for the neighbours' halos of the last step like every other read-out, then each rank sums its own fluid cells."""
+    kw = dict(nx=10, ny=8, nz=16, tau=0.8, collision=g.MRT, body_force=[1e-4, 0, 2e-4])
+    solid = np.zeros((16, 8, 10), np.uint8)
+    solid[6:10, 2:5, 3:7] = 1         # across the face between the slabs (planes 7 | 8)
+    solid[0, 6, 1] = 1
+    solid[15, 6, 1] = 1               # neighbours across the periodic seam
+    whole = g.Sim(backend=emu, **kw)
+    parts = [g.Sim(backend=emu, n_ranks=2, rank=r, flags=0 if overlap else g._abi.FLAG_NO_OVERLAP, **kw) for r in range(2)]
+    rho, u = util.smooth_fields(whole.shape)
+    whole.set_solid(solid)
+    whole.set_fields(rho, u)
+    for r, s in enumerate(parts):
+        s.set_solid(solid)
+        s.set_fields(rho[8 * r:8 * r + 8], u[:, 8 * r:8 * r + 8])
+    h = [s.peer_export() for s in parts]
+    parts[0].peer_connect(h[1], h[1])
+    parts[1].peer_connect(h[0], h[0])
+    o = [4.0, 3.0, 7.5]
+    for it in range(6):
+        whole.step(1)
+        for s in parts:
+            s.step(1)
+        total = parts[0].get_solid_force(o) + parts[1].get_solid_force(o)
+        want = whole.get_solid_force(o)
+        assert np.abs(total - want).max() <= 1e-9 * max(np.abs(want).max(), 1e-3), (it, total, want)      # same fp32 populations, fp64 sums
+    assert np.array_equal(whole.get_populations(), np.concatenate([s.get_populations() for s in parts], axis=1))
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["mrt_force", "mrt_all_walls_lid", "mrt_inlet_outlet_ywalls", "mrt_outlet_inlet_xwalls"])
