@@ -24,6 +24,7 @@ ap.add_argument("--lib", default="cuda", help="library exporting the fishgym ABI
 ap.add_argument("--steps", type=int, default=20)
 ap.add_argument("--task", default="cruise", choices=["cruise", "pose", "path"])
 ap.add_argument("--probes", type=int, default=0, help="fluid-velocity probes ahead of the head, appended to the observation")
+ap.add_argument("--passes", type=int, default=1, help="direct-forcing passes per substep (EnvConfig.ib_iterations; > 1: multi-direct forcing)")
 args = ap.parse_args()
 
 if args.small:
@@ -31,6 +32,7 @@ if args.small:
                     fish=(FishSpec(links=((10, 3), (9, 3), (8, 2.5), (7, 2))),), waypoints=((24, 40), (30, 20)))
 else:
     cfg = EnvConfig(task=args.task, probes=args.probes, waypoints=((128, 300), (160, 200)))     # 256 x 256 x 512, 20 substeps
+cfg.ib_iterations = args.passes
 env = FishEnv(cfg, backend=args.lib)
 
 rng = np.random.default_rng(0)
