@@ -115,6 +115,28 @@ def test_spread_force_equals_accumulated_marker_force(g, emu, passes):
         s.close()
 
 
+@pytest.mark.parametrize("passes", [1, 2, 5])
+def test_oracle_fluid_momentum_changes_by_minus_the_wrench(g, passes):
+    """Newton's third law for the coupling, to round-off and for any number of passes: per step the fluid's momentum changes by the
+    body force on its cells minus the hydrodynamic force ON the bodies (the link wrenches, fp64 read-outs)."""
+    gf = np.array([2e-5, -1e-5, 3e-5])
+    X, U, dV, link = _sphere_case()
+    s = _make(g, "oracle", passes, body_force=list(gf))
+    s.set_markers(X, U, dV, link)
+
+    def momentum():
+        r, v = s.get_fields(f64=True)
+        return (r * v).sum(axis=(1, 2, 3))
+    p0 = momentum()
+    for _ in range(4):
+        s.step(1)
+        p1 = momentum()
+        w = s.get_link_wrenches().sum(axis=0)[:3]
+        assert np.abs((p1 - p0) + w - gf * np.prod(s.shape)).max() < 1e-12
+        p0 = p1
+    s.close()
+
+
 def _compare(a, b, steps=(1, 1, 4)):
     for n in steps:
         a.step(n)

@@ -48,6 +48,34 @@ def test_oracle_against_numpy_from_its_own_populations(g, collision):
     s.close()
 
 
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("collision", ["bgk", "mrt"])
+def test_oracle_momentum_balance_every_step(g, seed, collision):
+    """Newton's third law, exactly: in a periodic box with obstacles the fluid's momentum changes per step by the body force on
+    its cells minus what the bounce-back links handed the obstacles — P(t+1) - P(t) + F_obstacles = g x (fluid cells) to
+    round-off, in an unsteady flow, for any mask.  Independent of how the read-out is evaluated."""
+    rng = np.random.default_rng(seed)
+    gf = np.array([1e-4, -2e-4, 3e-4])
+    s = g.Sim(backend="oracle", nx=11, ny=9, nz=8, tau=float(rng.uniform(0.6, 1.2)), collision=g.MRT if collision == "mrt" else g.BGK,
+              body_force=list(gf))
+    solid = (rng.random(s.shape) < rng.uniform(0.05, 0.3)).astype(np.uint8)
+    rho, u = util.smooth_fields(s.shape)
+    s.set_solid(solid)
+    s.set_fields(rho + 0.01 * rng.standard_normal(s.shape), u + 0.01 * rng.standard_normal((3,) + s.shape))
+    fluid = solid == 0
+
+    def momentum():
+        r, v = s.get_fields(f64=True)
+        return (r * v * fluid).sum(axis=(1, 2, 3))
+    p0 = momentum()
+    for _ in range(6):
+        s.step(1)
+        p1 = momentum()
+        assert np.abs((p1 - p0) + s.get_solid_force()[:3] - gf * fluid.sum()).max() < 1e-13
+        p0 = p1
+    s.close()
+
+
 def test_oracle_steady_channel_force_balance(g):
     """Two obstacle layers as channel walls, body force along z: once steady, the walls take exactly what the force puts
     into the fluid, g x (number of fluid cells), and nothing in the other directions."""
