@@ -168,6 +168,76 @@ def test_sphere_drag_by_momentum_exchange_on_a_staircase_sphere(g):
     s.close()
 
 
+def _hasimoto(c):
+    """Stokes drag of a simple cubic array of spheres, volume fraction c: F = 6 pi mu a U K with U the mean velocity over the whole
+    cell and F the total force on a sphere INCLUDING the mean pressure gradient's buoyancy (H. Hasimoto, J. Fluid Mech. 5 (1959) 317,
+    series extended by Sangani & Acrivos, Int. J. Multiphase Flow 8 (1982) 343; K(0.027) = 2.008 and K(0.064) = 2.810 are the tabulated
+    values of Zick & Homsy, J. Fluid Mech. 115 (1982) 13).  A published analytic result — nothing of it comes from this repository."""
+    return 1.0 / (1 - 1.7601 * c ** (1 / 3) + c - 1.5593 * c ** 2 + 3.9799 * c ** (8 / 3) - 3.0734 * c ** (10 / 3))
+
+
+_MAGIC = lambda tau: [0, 1.19, 1.4, 0, 8 * (2 - 1 / tau) / (8 - 1 / tau), 0, 8 * (2 - 1 / tau) / (8 - 1 / tau), 0, 8 * (2 - 1 / tau) / (8 - 1 / tau),   # noqa: E731
+                      1 / tau, 1.4, 1 / tau, 1.4, 1 / tau, 1 / tau, 1 / tau] + [8 * (2 - 1 / tau) / (8 - 1 / tau)] * 3
+
+
+def test_hasimoto_series_reproduces_the_tabulated_values():
+    assert abs(_hasimoto(0.027) - 2.008) < 2e-3 and abs(_hasimoto(0.064) - 2.810) < 2e-3
+
+
+@pytest.mark.parametrize("tau", [1.0, 0.8])
+def test_stokes_drag_of_a_periodic_array_of_spheres_matches_hasimoto(g, tau):
+    """A sphere of obstacle cells in a fully periodic cube IS a simple cubic array.  A uniform body force g on the fluid drives the
+    flow (a mean pressure gradient whose buoyancy g V_sphere the body force does not exert on the obstacle, hence F = g L^3 in
+    Hasimoto's sense while the bounce-back links carry g x fluid cells — checked with fg_get_solid_force).  With the sphere's
+    volume-equivalent radius the drag coefficient K comes out 1.1 % above the series at c = 0.066 (24^3, a = 6; 1.3 % at 32^3,
+    a = 8; the same for both viscosities with the wall-exact rates): bounce-back, forcing, viscosity and the momentum-exchange read-out
+    in one number that is pinned from outside."""
+    L, a, gf = 24, 6.0, 1e-6
+    nu = (tau - 0.5) / 3
+    s = g.Sim(backend="oracle", nx=L, ny=L, nz=L, tau=tau, collision=g.MRT, body_force=[0, 0, gf], mrt_rates=_MAGIC(tau))
+    c0 = L / 2 - 0.5
+    z, y, x = np.meshgrid(np.arange(L), np.arange(L), np.arange(L), indexing="ij")
+    solid = (((x - c0) ** 2 + (y - c0) ** 2 + (z - c0) ** 2) <= a * a).astype(np.uint8)
+    s.set_solid(solid)
+    s.step(6000)            # the mean flow relaxes with U / g = 250 (tau 1.0) and 420 (tau 0.8) steps: e^-14 at least
+    r, v = s.get_fields(f64=True)
+    fluid = solid == 0
+    U = ((v[2] + gf / 2 / r) * fluid).sum() / L ** 3           # mean over the whole cell; Guo: the physical velocity carries half the force
+    F = s.get_solid_force()
+    assert abs(F[2] / (gf * fluid.sum()) - 1) < 1e-5 and np.abs(F[:2]).max() < 1e-12
+    vol = float(solid.sum())
+    a_eq = (3 * vol / (4 * np.pi)) ** (1 / 3)
+    K = gf * L ** 3 / (6 * np.pi * nu * a_eq * U)
+    assert abs(K / _hasimoto(vol / L ** 3) - 1) < 0.02, (K, _hasimoto(vol / L ** 3))
+    s.close()
+
+
+@pytest.mark.parametrize("passes", [1, 3])
+def test_hydrodynamic_radius_of_an_immersed_sphere_from_hasimoto(g, passes):
+    """The same array with the sphere as an immersed boundary of markers at radius a (the fluid inside is held by the markers, so
+    they carry the whole g L^3).  Solving Hasimoto's relation for the radius that explains the measured mean velocity gives
+    a + 0.47 (24^3, a = 6) and a + 0.45 (32^3, a = 8) with one direct-forcing pass — the "half a cell" by which the 4-point kernel
+    thickens a body, used as D + 1 in the drag tests — and a + 0.57 / a + 0.54 with three passes (no-slip enforced more fully)."""
+    from scipy.optimize import brentq
+    L, a, gf, tau = 24, 6.0, 1e-6, 1.0
+    nu = (tau - 0.5) / 3
+    n = int(round(4 * np.pi * a * a))
+    s = g.Sim(backend="oracle", nx=L, ny=L, nz=L, tau=tau, collision=g.MRT, body_force=[0, 0, gf], max_markers=n, max_links=1,
+              ib_iterations=passes, mrt_rates=_MAGIC(tau))
+    c0 = L / 2 - 0.5
+    X = util.sphere_markers((c0, c0, c0), a, n)
+    s.set_markers(X, np.zeros_like(X), np.full(n, 4 * np.pi * a * a / n, np.float32), np.zeros(n, np.int32))
+    s.step(2500)
+    r, v = s.get_fields(f64=True)
+    Fz = s.get_force_field().astype(np.float64)[2]
+    U = (v[2] + (gf + Fz) / 2 / r).sum() / L ** 3
+    assert abs(s.get_link_wrenches()[0][2] / (gf * L ** 3) - 1) < 1e-3          # steady: the markers carry the whole body force
+    a_h = brentq(lambda ah: 6 * np.pi * nu * ah * U * _hasimoto(4 / 3 * np.pi * ah ** 3 / L ** 3) - gf * L ** 3, 0.5 * a, 1.5 * a)
+    lo, hi = (0.40, 0.52) if passes == 1 else (0.50, 0.64)
+    assert a + lo < a_h < a + hi, a_h
+    s.close()
+
+
 @pytest.mark.parametrize("coll,tau", [("bgk", 1.0), ("mrt", 0.7)])
 def test_couette_linear_profile_is_exact_with_a_moving_wall(g, coll, tau):
     """Plane Couette flow between y walls, the upper one moving tangentially in x AND z: the linear profile is an exact
