@@ -254,6 +254,44 @@ def test_gpu_staircase_sphere_in_a_channel(g, cuda):
     b.close()
 
 
+def _hasimoto_array(g, backend, L=24, a=6.0, tau=1.0, steps=6000):
+    """Stokes drag of a simple cubic array of spheres (tests/test_oracle_physics.py: Hasimoto 1959) through `backend`: an obstacle
+    sphere in a fully periodic cube, body force g, drag by momentum exchange.  Returns (K / K_Hasimoto, F_z / (g x fluid cells),
+    lateral force / F_z)."""
+    import test_oracle_physics as T
+    gf, nu = 1e-6, (tau - 0.5) / 3
+    s = g.Sim(backend=backend, nx=L, ny=L, nz=L, tau=tau, collision=g.MRT, body_force=[0, 0, gf], mrt_rates=T._MAGIC(tau))
+    c0 = L / 2 - 0.5
+    z, y, x = np.meshgrid(np.arange(L), np.arange(L), np.arange(L), indexing="ij")
+    solid = (((x - c0) ** 2 + (y - c0) ** 2 + (z - c0) ** 2) <= a * a).astype(np.uint8)
+    s.set_solid(solid)
+    s.step(steps)
+    r, v = s.get_fields(f64=True)
+    fluid = solid == 0
+    U = ((v[2] + gf / 2 / r) * fluid).sum() / L ** 3
+    F = s.get_solid_force()
+    s.close()
+    vol = float(solid.sum())
+    K = gf * L ** 3 / (6 * np.pi * nu * (3 * vol / (4 * np.pi)) ** (1 / 3) * U)
+    return K / T._hasimoto(vol / L ** 3), F[2] / (gf * fluid.sum()), float(np.abs(F[:2]).max() / F[2])
+
+
+def test_hasimoto_array_drag_with_the_fp32_kernels_emulated(g, emu):
+    """The product's fp32 kernels (shifted populations, a body force of 1e-6 per step on velocities of 2.5e-4) reproduce the
+    oracle's number: K / K_Hasimoto = 1.0111 on both to seven digits."""
+    ratio, balance, lateral = _hasimoto_array(g, emu)
+    assert abs(ratio - 1.01111) < 2e-5 and abs(balance - 1) < 1e-6 and lateral < 1e-9, (ratio, balance, lateral)
+
+
+@pytest.mark.gpu
+def test_hasimoto_array_drag_gpu(g, cuda):
+    """(Written without a GPU, like the test below; the emulated fp32 kernels give 1.0111.)  The CUDA path alone against the
+    published analytic result, as test_gpu_physics.py does for the cavity table."""
+    ratio, balance, lateral = _hasimoto_array(g, cuda)
+    print(f"Hasimoto array on the GPU: K / K_Hasimoto = {ratio:.5f} (oracle and emulation 1.01111), force balance {balance:.7f}, lateral {lateral:.1e}")
+    assert abs(ratio - 1) < 0.02 and abs(balance - 1) < 1e-4 and lateral < 1e-4, (ratio, balance, lateral)
+
+
 @pytest.mark.gpu
 def test_staircase_sphere_drag_by_momentum_exchange_full_size(g, cuda):
     """(Last GPU test of the suite on purpose: written when the round's GPU budget was spent, so its expectation comes from the
