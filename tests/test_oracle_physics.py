@@ -238,6 +238,52 @@ def test_hydrodynamic_radius_of_an_immersed_sphere_from_hasimoto(g, passes):
     s.close()
 
 
+@pytest.mark.parametrize("passes", [1, 3])
+def test_taylor_couette_between_immersed_cylinders(g, passes):
+    """Circular Couette flow: an inner cylinder of markers rotating at Omega inside an outer one at rest (axis along z, 4 periodic
+    planes).  The analytic steady flow is u_theta = A r + B / r and the torque per length on either cylinder is 4 pi mu B.  Checked:
+    the profile in the gap has that form (residual 5e-4 of the wall speed); the radii at which it meets the two wall speeds lie
+    0.40 cells inside the fluid from the marker radii (0.45 with three passes; 0.39 / 0.44 at 72^2 with R = 16 / 28) — the same
+    thickening the Hasimoto test finds for a sphere; and the TORQUE of the link wrench on the inner cylinder is 4 pi mu B of that
+    profile to 1e-3: the first check of the torque read-out and of moving markers (U_d = Omega x r) against an analytic flow."""
+    N, nz, R1, R2, tau = 48, 4, 10.0, 19.0, 1.0
+    nu, Om, c = (tau - 0.5) / 3, 0.01 / R1, N / 2 - 0.5
+
+    def ring(R):
+        n = int(round(2 * np.pi * R))
+        th = 2 * np.pi * (np.arange(n) + 0.5) / n
+        return np.concatenate([np.stack([c + R * np.cos(th), c + R * np.sin(th), np.full(n, float(zz))], 1) for zz in range(nz)]).astype(np.float32), 2 * np.pi * R / n
+    (X1, ds1), (X2, ds2) = ring(R1), ring(R2)
+    X = np.concatenate([X1, X2])
+    U = np.zeros_like(X)
+    U[:len(X1), 0], U[:len(X1), 1] = -Om * (X1[:, 1] - c), Om * (X1[:, 0] - c)
+    dV = np.concatenate([np.full(len(X1), ds1), np.full(len(X2), ds2)]).astype(np.float32)
+    link = np.concatenate([np.zeros(len(X1)), np.ones(len(X2))]).astype(np.int32)
+    s = g.Sim(backend="oracle", nx=N, ny=N, nz=nz, tau=tau, collision=g.MRT, max_markers=len(X), max_links=2, ib_iterations=passes, mrt_rates=_MAGIC(tau))
+    s.set_markers(X, U, dV, link)
+    s.set_link_origins([[c, c, 0], [c, c, 0]])
+    s.step(4000)                                   # gap^2 / nu = 490 steps
+    W = s.get_link_wrenches()
+    r, v = s.get_fields(f64=True)
+    F3 = s.get_force_field().astype(np.float64)
+    ux, uy = (v[0] + F3[0] / 2 / r)[0], (v[1] + F3[1] / 2 / r)[0]          # physical velocity (Guo: half the force)
+    yy, xx = np.meshgrid(np.arange(N) - c, np.arange(N) - c, indexing="ij")
+    rr = np.hypot(xx, yy)
+    ut = (-yy * ux + xx * uy) / np.maximum(rr, 1e-9)
+    m = (rr > R1 + 2.5) & (rr < R2 - 2.5)                                  # clear of the smeared shells
+    basis = np.stack([rr[m], 1 / rr[m]], 1)
+    (A, B), *_ = np.linalg.lstsq(basis, ut[m], rcond=None)
+    assert np.abs(basis @ [A, B] - ut[m]).max() < 1e-3 * Om * R1
+    r1h, r2h = np.sqrt(B / (Om - A)), np.sqrt(-B / A)
+    lo, hi = (0.34, 0.46) if passes == 1 else (0.39, 0.51)
+    assert lo < r1h - R1 < hi and lo < R2 - r2h < hi and abs((r1h - R1) - (R2 - r2h)) < 0.02, (r1h, r2h)
+    Tin, Tout = W[0][5] / nz, W[1][5] / nz
+    assert Tin < 0 < Tout                                                  # the fluid brakes the rotor and drags the stator along
+    assert abs(-Tin / (4 * np.pi * nu * B) - 1) < 1e-3, (Tin, 4 * np.pi * nu * B)
+    assert np.abs(W[:, :2]).max() < 1e-3 * abs(W[0][5]) / R1                # no net in-plane force on either cylinder (torque / R = the shear force)
+    s.close()
+
+
 @pytest.mark.parametrize("coll,tau", [("bgk", 1.0), ("mrt", 0.7)])
 def test_couette_linear_profile_is_exact_with_a_moving_wall(g, coll, tau):
     """Plane Couette flow between y walls, the upper one moving tangentially in x AND z: the linear profile is an exact
