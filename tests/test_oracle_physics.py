@@ -238,6 +238,72 @@ def test_hydrodynamic_radius_of_an_immersed_sphere_from_hasimoto(g, passes):
     s.close()
 
 
+@pytest.mark.parametrize("coll,tau,tol", [("bgk", 0.8, 2.5e-3), ("mrt", 0.8, 4e-4), ("mrt", 0.6, 2.5e-3)])
+def test_stokes_first_problem_impulsively_started_wall(g, coll, tau, tol):
+    """Fluid at rest, the y-low wall moves at U from t = 0 on: u(y, t) = U erfc(y / (2 sqrt(nu t))), the classical similarity
+    solution (the far wall is 20 diffusion lengths away at the last checkpoint).  Unsteady viscous diffusion and the moving-wall
+    term of half-way bounce-back against an analytic TRANSIENT; the error falls with time as the start-up layer is resolved."""
+    from scipy.special import erfc
+    P, Wl = g.BC_PERIODIC, g.BC_WALL
+    NY, Uw = 96, 0.01
+    nu = (tau - 0.5) / 3
+    kw = dict(mrt_rates=_MAGIC(tau)) if coll == "mrt" else {}
+    s = g.Sim(backend="oracle", nx=3, ny=NY, nz=3, tau=tau, collision=g.MRT if coll == "mrt" else g.BGK, bc=[P, P, Wl, Wl, P, P],
+              wall_u={g._abi.YLO: [Uw, 0, 0]}, **kw)
+    y = np.arange(NY) + 0.5                    # the wall sits half a cell below the first node
+    done, errs = 0, []
+    for t in (100, 400, 1000):
+        s.step(t - done)
+        done = t
+        _, u = s.get_fields(f64=True)
+        errs.append(float(np.abs(u[0][0, :, 0] - Uw * erfc(y / (2 * np.sqrt(nu * t)))).max() / Uw))
+        assert np.abs(u[1]).max() < 1e-5 * Uw and np.abs(u[2]).max() < 1e-12      # wall-normal: O(Ma^2 U) compressibility only (measured 2e-6 U)
+    assert errs[0] < tol and errs[1] < errs[0] / 3 and errs[2] < errs[1] / 2, errs
+    s.close()
+
+
+@pytest.mark.parametrize("coll", ["bgk", "mrt"])
+def test_sound_speed_of_a_standing_wave(g, coll):
+    """A standing density wave of wavelength 64 oscillates with period lambda / c_s = 64 sqrt(3) = 110.85 steps: the isothermal
+    equation of state p = rho / 3 of the lattice (measured 110.88 / 110.87; the damping shifts the period by 1.5e-4)."""
+    N = 64
+    s = g.Sim(backend="oracle", nx=N, ny=2, nz=2, tau=0.55, collision=g.MRT if coll == "mrt" else g.BGK)
+    mode = np.cos(2 * np.pi * np.arange(N) / N)
+    s.set_fields(np.ones(s.shape) + 1e-4 * mode[None, None, :], np.zeros((3,) + s.shape))
+    amp = []
+    for _ in range(400):
+        r, _u = s.get_fields(f64=True)
+        amp.append(float(((r - 1)[0, 0, :] * mode).sum() * 2 / N))
+        s.step(1)
+    zero = [i + amp[i] / (amp[i] - amp[i + 1]) for i in range(len(amp) - 1) if amp[i] * amp[i + 1] < 0]
+    assert len(zero) >= 6
+    c_s = N / (2 * np.mean(np.diff(zero)))
+    assert abs(c_s * np.sqrt(3) - 1) < 5e-4, c_s
+    s.close()
+
+
+@pytest.mark.parametrize("NX,NY,tau,tol", [(16, 12, 0.8, 2e-3), (24, 16, 1.0, 1e-3)])
+def test_rectangular_duct_flow_matches_the_series_solution(g, NX, NY, tau, tol):
+    """Walls on x AND y, body force along z: the classical Fourier-series solution of Poiseuille flow in a rectangular duct
+    (e.g. White, Viscous Fluid Flow, eq. 3-48), walls half a cell outside the first / last nodes.  Edges and corners of the
+    half-way bounce-back (links that cross two wall faces) against an analytic field: 1.2e-3 at 16 x 12, 5e-4 at 24 x 16 (second order)."""
+    P, Wl = g.BC_PERIODIC, g.BC_WALL
+    gf, nu = 1e-6, (tau - 0.5) / 3
+    s = g.Sim(backend="oracle", nx=NX, ny=NY, nz=3, tau=tau, collision=g.MRT, bc=[Wl, Wl, Wl, Wl, P, P], body_force=[0, 0, gf], mrt_rates=_MAGIC(tau))
+    s.step(int(1.5 * max(NX, NY) ** 2 / nu))
+    _, u = s.get_fields(f64=True)
+    a, b = NX / 2, NY / 2
+    X, Y = np.meshgrid(np.arange(NX) + 0.5 - a, np.arange(NY) + 0.5 - b, indexing="xy")
+    ana = gf / (2 * nu) * (a * a - X * X)
+    for n in range(200):
+        k = (2 * n + 1) * np.pi / (2 * a)
+        ana -= gf / nu * 2 * (-1) ** n / (a * k ** 3) * np.cos(k * X) * np.cosh(k * Y) / np.cosh(k * b)
+    num = u[2][0] + gf / 2
+    assert util.rel_l2(num, ana) < tol and abs(num.sum() / ana.sum() - 1) < tol, (util.rel_l2(num, ana), num.sum() / ana.sum())
+    assert np.abs(u[2] - u[2][:1]).max() < 1e-15 and np.abs(u[0]).max() < 1e-5 * num.max() and np.abs(u[1]).max() < 1e-5 * num.max()
+    s.close()
+
+
 @pytest.mark.parametrize("passes", [1, 3])
 def test_taylor_couette_between_immersed_cylinders(g, passes):
     """Circular Couette flow: an inner cylinder of markers rotating at Omega inside an outer one at rest (axis along z, 4 periodic
