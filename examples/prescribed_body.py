@@ -50,8 +50,9 @@ mass, k_spring = 4 / 3 * np.pi * (D / 2) ** 3 * 2.0, 0.02        # a body twice 
 # F_k = 2 (U_d - U*) answers a change of the body's velocity with the stiffness sum 2 dV per pass, and an explicit update is
 # unstable once that exceeds ~2 x mass (added-mass instability: light bodies, or several passes).  A virtual mass
 # Mv = 1/2 x stiffness low-pass filters the momentum increment — (mass + Mv) dp_new = mass F + Mv dp_old, fixed point dp = F —
-# which is what the built-in fish integrator does (csrc/body.hpp).
-Mv = 0.5 * max(1, args.passes) * 2.0 * float(dV.sum())
+# which is what the built-in fish integrator does (csrc/body.hpp).  With n passes the forcing's own period-2 memory is damped
+# less and less (a pass aims at u* + F/2 = U_d, the fluid leaves the step with u* + F): the virtual mass grows like 2^n - 1.
+Mv = 0.5 * (2 ** max(1, args.passes) - 1) * 2.0 * float(dV.sum())
 dp = np.zeros(3)
 
 t0 = time.perf_counter()

@@ -26,7 +26,9 @@ inline double cross_y(const V2 &a, const V2 &b) { return a.z * b.x - a.x * b.z; 
 
 class Fish {
 public:
-    void forcing_passes(int n) { npass_ = n > 1 ? double(n) : 1.0; }
+    // n direct-forcing passes: the forcing's period-2 memory (it aims at u* + F/2 but leaves u* + F) is damped by 2 (1-l)^n only, so the
+    // virtual mass that keeps the explicit body update stable grows like (1 - q) / q, q = (1-l)^n; with l = 1/2: 2^n - 1
+    void forcing_passes(int n) { npass_ = n > 1 ? std::pow(2.0, std::min(n, 16)) - 1.0 : 1.0; }
     bool init(const FgFishDesc &d, std::string *why) {
         if (d.n_links < 1 || d.n_links > 8) { *why = "fish: n_links must be 1..8"; return false; }
         desc_ = d;
@@ -120,7 +122,7 @@ public:
             // explicit coupling with the direct-forcing penalty F = 2(U_d - U*) is unstable for light bodies
             // (added-mass instability); a virtual mass Mv = beta * sum(2 dV) filters the momentum increment:
             // (M + Mv) a_new = F + Mv a_old, fixed point a = F/M, unconditionally stable for beta >= 1/4
-            // n direct-forcing passes per substep (multi-direct forcing) make the penalty at most n times as stiff
+            // n direct-forcing passes per substep (multi-direct forcing): virtual mass x (2^n - 1), see forcing_passes()
             const double Mv = kBeta * npass_ * ctot_, Iv = kBeta * npass_ * Cr;
             dP_.x = (M * F.x + Mv * dP_.x) / (M + Mv);
             dP_.z = (M * F.z + Mv * dP_.z) / (M + Mv);

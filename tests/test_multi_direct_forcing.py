@@ -241,6 +241,34 @@ def test_emulated_swimming_fish_with_iterations(g, emu, free):
         assert util.rel_l2(b.get_fields(f64=True)[1], a.get_fields(f64=True)[1]) <= 5e-5
 
 
+@pytest.mark.parametrize("passes", [1, 3, 5])
+def test_passive_fish_is_advected_by_a_uniform_stream(g, emu, passes):
+    """A neutrally buoyant, unactuated, free fish released at rest into a uniform stream: it must pick up the stream's velocity and
+    the wrench must vanish (Galilean invariance of the coupling).  With 3 passes and the virtual mass of the one-pass scheme
+    scaled by the number of passes this blew up within 40 steps — the forcing's period-2 memory (eigenvalue 2 (1 - l)^n - 1) against
+    the explicit body update, body.hpp set_forcing_passes; with 2^n - 1 the body settles at 0.987 of the stream speed after 600 steps
+    for any number of passes (the one-pass scheme: the same 0.987).  Product's host integrator against the oracle's on the way."""
+    kw = dict(nx=24, ny=20, nz=48, tau=0.8, collision=g.MRT, max_markers=3000, max_links=4, ib_iterations=passes)
+    a, b = g.Sim(backend="oracle", **kw), g.Sim(backend=emu, **kw)
+    u = np.zeros((3,) + a.shape)
+    u[0], u[2] = 0.01, 0.02
+    for s in (a, b):
+        s.set_fields(np.ones(a.shape), u)
+        s.add_fish(util.fish_desc(g, root=(12, 10, 20), free=1, heading=0.0))
+        s.set_action(np.zeros(s.action_size(), np.float32))
+    peak = 0.0
+    for _ in range(6):
+        for s in (a, b):
+            s.step(100)
+        oa, ob = a.get_obs(), b.get_obs()
+        assert np.abs(oa - ob).max() < 2e-4
+        peak = max(peak, float(np.abs(a.get_link_wrenches()).max()))
+    assert abs(oa[4] / 0.01 - 1) < 0.03 and abs(oa[6] / 0.02 - 1) < 0.03 and abs(oa[7]) < 1e-4, oa      # velocity x, z; yaw rate
+    assert np.abs(a.get_link_wrenches()[:, :3].sum(0)).max() < 0.02 and peak < 5.0                         # start-up force was 24 (3 passes)
+    for s in (a, b):
+        s.close()
+
+
 def test_host_staged_slabs_with_iterations_equal_oracle_slabs(g, emu):
     """z-slabs whose halos travel through the host (fg_halo_pack / unpack), a body inside one slab: each rank runs the
     passes over its own cells, as the oracle's ranks do."""
