@@ -323,7 +323,7 @@ def test_random_moving_markers_emulated_kernels_vs_oracle(g, emu):
     check_moving(g, emu, range(120))
 
 
-def run_fish_case(g, backend, seed):
+def run_fish_case(g, backend, seed, passes=1):
     """One or two random articulated fish (1-5 links, pinned or free, random servo gains / limits / densities), random
     actions, 1-7 substeps per call, now and then a reset: the product's host integrator (csrc/body.hpp) + IB + fluid
     against the oracle's independently written one (oracle/oracle_body.hpp)."""
@@ -334,6 +334,8 @@ def run_fish_case(g, backend, seed):
               bc=[Wl] * 4 + [P] * 2 if rng.random() < 0.5 else [P] * 6, max_markers=6000, max_links=16)
     if rng.random() < 0.5:
         kw["split_min_cells"] = 1
+    if passes > 1:
+        kw["ib_iterations"] = passes        # multi-direct forcing; not drawn from this generator's stream
     a, b = g.Sim(backend="oracle", **kw), g.Sim(backend=backend, **kw)
     nf = int(rng.integers(1, 3))
     for f in range(nf):

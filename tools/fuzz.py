@@ -6,7 +6,7 @@
     python tools/fuzz.py moving|fish|api|slabs|xslabs 0 500
     FG_EMU_SCHED=rand:3 FG_EMU_GRAPHS=1 python tools/fuzz.py slabs 0 500     # queued streams, emulated graphs
     python tools/fuzz.py static 0 500 --lib cuda        # the real library on a GPU box
-    python tools/fuzz.py moving|xslabs 0 500 --passes 3 # ... with FgConfig.ib_iterations = 3 (multi-direct forcing)
+    python tools/fuzz.py moving|fish|xslabs 0 500 --passes 3 # ... with FgConfig.ib_iterations = 3 (multi-direct forcing)
 
 Prints the seeds that fail; the committed tests run fixed ranges of the same generators."""
 import os
@@ -34,7 +34,7 @@ def one(seed):
         w, kw, _, _ = t.run_moving_markers_case(g, lib, seed, passes)
         return (None if w is None else all(w[k] <= dict(t.LIMITS, probe=5e-6)[k] for k in w)), kw
     if kind == "fish":
-        w, kw = t.run_fish_case(g, lib, seed)
+        w, kw = t.run_fish_case(g, lib, seed, passes)
         return (None if w is None else (w["obs"] <= 1e-4 and w["wrench"] <= 1e-4 and w["u"] <= 1e-5)), kw
     if kind == "api":
         w = t.run_api_sequence_case(g, lib, seed, solid_force=True)
