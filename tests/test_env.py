@@ -120,3 +120,19 @@ def test_prescribed_body_example_runs_against_the_checker_library():
     d1, d3 = displacement(r.stdout), displacement(r3.stdout)
     # the explicit body update stays stable with the stiffer coupling (virtual mass in the example) and the two runs agree closely
     assert 0.0 < d1 < 5.0 and abs(d3 - d1) < 0.1 * d1 and d3 != d1, (d1, d3)
+
+
+def test_default_fish_survives_a_random_policy(g):
+    """The env's DEFAULT swimmer (112 cells long) under uniformly random actions, in a tank an eighth of the default volume so the
+    oracle can run it: with the former default joint-rate limit of 0.01 rad per substep the tail moved at 0.2 - 0.5 lattice units per
+    step and the fluid had diverged by the third env step; the limit is 0.005 now."""
+    from gym_fish_b200.env import EnvConfig, FishEnv
+    env = FishEnv(EnvConfig(grid=(128, 64, 256), max_episode_steps=100), backend="oracle")
+    env.reset(seed=0)
+    rng = np.random.default_rng(0)
+    for _ in range(4):
+        obs, _, terminated, _, info = env.step(rng.uniform(-1, 1, env.action_space.shape).astype(np.float32))
+        assert not info["diverged"] and not terminated and np.isfinite(obs).all()
+    assert np.abs(env.sim.get_link_wrenches()).max() < 500          # 1e4 - 1e6 on the way to divergence
+    env.close()
+
